@@ -1,0 +1,367 @@
+// extern "C" boundary of lrr_b200 (see include/lrr_b200.h for what each entry point replaces in the reference).
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace lrr {
+
+static thread_local std::string g_create_error;
+
+int fail(Ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int cuda_fail(Ctx* c, cudaError_t e, const char* what) {
+  std::string m = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  cudaGetLastError();  // clear sticky-less errors so the next call reports its own
+  return fail(c, LRR_ECUDA, m);
+}
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+void free_group(Group& g) {
+  cudaFree(g.d_basis);
+  cudaFree(g.d_qty);
+  cudaFree(g.d_yyp);
+  cudaFree(g.d_mask);
+  cudaFree(g.d_bq);
+  cudaFree(g.d_colscale);
+  g = Group();
+}
+
+void free_workspace(Ctx* c) {
+  cudaFree(c->d_counts);
+  cudaFree(c->d_dots);
+  c->d_counts = nullptr;
+  c->d_dots = nullptr;
+  c->reserved_variants = 0;
+  c->dots_offset.clear();
+}
+
+// scatter compact per-kept-sample columns into zero-initialised full-width planes and build the sample mask
+__global__ void scatter_basis_kernel(const double* __restrict__ cols, int C, int n, const int32_t* __restrict__ idx,
+                                     int64_t ns_pad, double* __restrict__ basis, uint32_t* __restrict__ mask) {
+  const int64_t total = (int64_t)C * n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i / n);
+    const int j = (int)(i - (int64_t)c * n);
+    const int64_t s = idx[j];
+    basis[(int64_t)c * ns_pad + s] = cols[i];
+    if (c == 0) atomicOr(mask + (s >> 4), 1u << sample_shift((int)(s & 15)));
+  }
+}
+
+int ensure_workspace(Ctx* c, int64_t M) {
+  if (M <= c->reserved_variants && c->dots_offset.size() == c->groups.size()) return LRR_OK;
+  const int64_t want = M > c->reserved_variants ? M : c->reserved_variants;
+  free_workspace(c);
+  const size_t G = c->groups.size();
+  int64_t total_c = 0;
+  c->dots_offset.resize(G);
+  for (size_t g = 0; g < G; ++g) {
+    c->dots_offset[g] = total_c * want;
+    total_c += c->groups[g].C;
+  }
+  LRR_CUDA(c, cudaMalloc(&c->d_counts, sizeof(int32_t) * 4 * (size_t)want * (G ? G : 1)));
+  LRR_CUDA(c, cudaMalloc(&c->d_dots, sizeof(double) * (size_t)want * (size_t)(total_c ? total_c : 1)));
+  c->reserved_variants = want;
+  return LRR_OK;
+}
+
+}  // namespace
+}  // namespace lrr
+
+using namespace lrr;
+
+extern "C" {
+
+const char* lrr_version(void) { return "lrr_b200 0.1 (sm_100a)"; }
+
+int lrr_create(lrr_ctx** out, int device) {
+  if (!out) return fail(nullptr, LRR_EINVAL, "lrr_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, LRR_ECUDA,
+                std::string("lrr_create: no CUDA device available (") + cudaGetErrorString(e) +
+                    "); this library has no CPU fallback");
+  if (device < 0 || device >= count) return fail(nullptr, LRR_EINVAL, "lrr_create: device index out of range");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, LRR_ECUDA, std::string("lrr_create: ") + cudaGetErrorString(e));
+  if (prop.major < 10)
+    return fail(nullptr, LRR_ECUDA, "lrr_create: device is not Blackwell (sm_100a) -- kernels are built for sm_100a only");
+  Ctx* c = new Ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  *out = reinterpret_cast<lrr_ctx*>(c);
+  return LRR_OK;
+}
+
+void lrr_destroy(lrr_ctx* ctx) {
+  if (!ctx) return;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  DeviceGuard guard(c->device);
+  for (auto& g : c->groups) free_group(g);
+  free_workspace(c);
+  tc_release(c);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  delete c;
+}
+
+const char* lrr_last_error(const lrr_ctx* ctx) {
+  if (!ctx) return g_create_error.c_str();
+  return reinterpret_cast<const Ctx*>(ctx)->err.c_str();
+}
+
+int64_t lrr_packed_stride(int64_t n_samples) {
+  if (n_samples <= 0) return kRowAlignBytes;
+  const int64_t bytes = (n_samples + 3) / 4;
+  return (bytes + kRowAlignBytes - 1) / kRowAlignBytes * kRowAlignBytes;
+}
+
+#define CTX_PROLOGUE                                      \
+  if (!ctx) return LRR_EINVAL;                            \
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);                   \
+  DeviceGuard guard(c->device);                           \
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
+
+static int check_packed(Ctx* c, int64_t n_samples, int64_t packed_stride) {
+  if (packed_stride % kRowAlignBytes != 0 || packed_stride * 4 < n_samples)
+    return fail(c, LRR_EINVAL, "packed_stride must be a multiple of 128 bytes covering n_samples (use lrr_packed_stride)");
+  return LRR_OK;
+}
+
+int lrr_pack_bed(lrr_ctx* ctx, const uint8_t* d_bed, int64_t n_variants, int64_t bed_stride, int64_t n_samples,
+                 uint8_t* d_packed, int64_t packed_stride, void* stream) {
+  CTX_PROLOGUE;
+  if (n_variants < 0 || n_samples <= 0 || bed_stride < (n_samples + 3) / 4)
+    return fail(c, LRR_EINVAL, "lrr_pack_bed: bed_stride must be >= ceil(n_samples/4) (LoadPlink.scala:240-251)");
+  if (int r = check_packed(c, n_samples, packed_stride)) return r;
+  return launch_pack_bed(c, d_bed, n_variants, bed_stride, n_samples, d_packed, packed_stride, st);
+}
+
+int lrr_pack_dosage_i8(lrr_ctx* ctx, const int8_t* d_dosage, int64_t n_variants, int64_t n_samples, uint8_t* d_packed,
+                       int64_t packed_stride, void* stream) {
+  CTX_PROLOGUE;
+  if (n_variants < 0 || n_samples <= 0) return fail(c, LRR_EINVAL, "lrr_pack_dosage_i8: bad shape");
+  if (int r = check_packed(c, n_samples, packed_stride)) return r;
+  return launch_pack_i8(c, d_dosage, n_variants, n_samples, d_packed, packed_stride, st);
+}
+
+int lrr_unpack_dosage_i8(lrr_ctx* ctx, const uint8_t* d_packed, int64_t packed_stride, int64_t n_variants,
+                         int64_t n_samples, int8_t* d_dosage, void* stream) {
+  CTX_PROLOGUE;
+  if (n_variants < 0 || n_samples <= 0) return fail(c, LRR_EINVAL, "lrr_unpack_dosage_i8: bad shape");
+  if (int r = check_packed(c, n_samples, packed_stride)) return r;
+  return launch_unpack_i8(c, d_packed, packed_stride, n_variants, n_samples, d_dosage, st);
+}
+
+int lrr_unpack_bed(lrr_ctx* ctx, const uint8_t* d_packed, int64_t packed_stride, int64_t n_variants, int64_t n_samples,
+                   uint8_t* d_bed, int64_t bed_stride, void* stream) {
+  CTX_PROLOGUE;
+  if (n_variants < 0 || n_samples <= 0 || bed_stride < (n_samples + 3) / 4)
+    return fail(c, LRR_EINVAL, "lrr_unpack_bed: bed_stride must be >= ceil(n_samples/4)");
+  if (int r = check_packed(c, n_samples, packed_stride)) return r;
+  return launch_unpack_bed(c, d_packed, packed_stride, n_variants, n_samples, d_bed, bed_stride, st);
+}
+
+int lrr_bn_fill(lrr_ctx* ctx, const uint32_t* d_thresholds, int n_pops, const uint8_t* d_pop, int64_t n_variants,
+                int64_t first_variant, int64_t n_samples, uint64_t seed, uint8_t* d_packed, int64_t packed_stride,
+                void* stream) {
+  CTX_PROLOGUE;
+  if (n_variants < 0 || n_samples <= 0 || n_pops <= 0 || n_pops > 255) return fail(c, LRR_EINVAL, "lrr_bn_fill: bad shape");
+  if (int r = check_packed(c, n_samples, packed_stride)) return r;
+  return launch_bn_fill(c, d_thresholds, n_pops, d_pop, n_variants, first_variant, n_samples, seed, d_packed,
+                        packed_stride, st);
+}
+
+int lrr_clear_groups(lrr_ctx* ctx) {
+  if (!ctx) return LRR_EINVAL;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  DeviceGuard guard(c->device);
+  cudaDeviceSynchronize();
+  for (auto& g : c->groups) free_group(g);
+  c->groups.clear();
+  free_workspace(c);
+  c->n_samples_total = 0;
+  return LRR_OK;
+}
+
+int lrr_num_groups(const lrr_ctx* ctx) {
+  return ctx ? (int)reinterpret_cast<const Ctx*>(ctx)->groups.size() : 0;
+}
+
+int lrr_add_group(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, int32_t P, int32_t has_intercept,
+                  const int32_t* complete_idx, const double* q_cols, const double* y_res, const double* qty,
+                  const double* yyp) {
+  if (!ctx) return LRR_EINVAL;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  DeviceGuard guard(c->device);
+  if (n_samples_total <= 0 || n <= 0 || n > n_samples_total) return fail(c, LRR_EINVAL, "lrr_add_group: bad sample counts");
+  if (P <= 0) return fail(c, LRR_EINVAL, "No phenotypes present.");  // RU:97-98
+  if (K < 0 || K + P > kMaxGroupCols) return fail(c, LRR_EINVAL, "lrr_add_group: K + P out of range");
+  has_intercept = has_intercept ? 1 : 0;
+  if (has_intercept && K < 1) return fail(c, LRR_EINVAL, "lrr_add_group: has_intercept needs K >= 1");
+  const int d = n - K - 1;
+  if (d < 1) {  // LR:55-58
+    char buf[160];
+    snprintf(buf, sizeof buf, "%d samples and %d %s (including x) implies %d degrees of freedom.", n, K + 1,
+             K == 1 ? "covariate" : "covariates", d);
+    return fail(c, LRR_EINVAL, buf);
+  }
+  if (!c->groups.empty() && c->n_samples_total != n_samples_total)
+    return fail(c, LRR_EINVAL, "lrr_add_group: all groups must share n_samples_total");
+  if (!complete_idx || !y_res || !yyp || (K > 0 && !qty) || (K - has_intercept > 0 && !q_cols))
+    return fail(c, LRR_EINVAL, "lrr_add_group: NULL input array");
+
+  Group g;
+  g.n = n;
+  g.K = K;
+  g.P = P;
+  g.has_intercept = has_intercept;
+  g.Kd = K - has_intercept;
+  g.C = g.Kd + P;
+  g.d = d;
+  g.lbeta = log_beta_half(0.5 * (double)d);
+  g.ns_pad = lrr_packed_stride(n_samples_total) * 4;
+
+  int32_t* d_idx = nullptr;
+  double* d_cols = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_idx);
+    cudaFree(d_cols);
+  };
+  auto bail = [&](cudaError_t e, const char* what) {
+    cleanup();
+    free_group(g);
+    return cuda_fail(c, e, what);
+  };
+  cudaError_t e;
+#define TRY(call) if ((e = (call)) != cudaSuccess) return bail(e, #call)
+  TRY(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)n));
+  TRY(cudaMemcpy(d_idx, complete_idx, sizeof(int32_t) * (size_t)n, cudaMemcpyDefault));
+  TRY(cudaMalloc(&d_cols, sizeof(double) * (size_t)g.C * n));
+  if (g.Kd > 0) TRY(cudaMemcpy(d_cols, q_cols, sizeof(double) * (size_t)g.Kd * n, cudaMemcpyDefault));
+  TRY(cudaMemcpy(d_cols + (size_t)g.Kd * n, y_res, sizeof(double) * (size_t)P * n, cudaMemcpyDefault));
+  TRY(cudaMalloc(&g.d_basis, sizeof(double) * (size_t)g.C * g.ns_pad));
+  TRY(cudaMemset(g.d_basis, 0, sizeof(double) * (size_t)g.C * g.ns_pad));
+  TRY(cudaMalloc(&g.d_mask, sizeof(uint32_t) * (size_t)(g.ns_pad / 16)));
+  TRY(cudaMemset(g.d_mask, 0, sizeof(uint32_t) * (size_t)(g.ns_pad / 16)));
+  TRY(cudaMalloc(&g.d_qty, sizeof(double) * (size_t)(K > 0 ? K : 1) * P));
+  if (K > 0) TRY(cudaMemcpy(g.d_qty, qty, sizeof(double) * (size_t)K * P, cudaMemcpyDefault));
+  TRY(cudaMalloc(&g.d_yyp, sizeof(double) * (size_t)P));
+  TRY(cudaMemcpy(g.d_yyp, yyp, sizeof(double) * (size_t)P, cudaMemcpyDefault));
+  {
+    const int64_t total = (int64_t)g.C * n;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 65535) grid = 65535;
+    scatter_basis_kernel<<<grid, 256>>>(d_cols, g.C, n, d_idx, g.ns_pad, g.d_basis, g.d_mask);
+    c->launches++;
+    TRY(cudaGetLastError());
+    TRY(cudaDeviceSynchronize());
+  }
+#undef TRY
+  cleanup();
+  c->groups.push_back(g);
+  c->n_samples_total = n_samples_total;
+  c->dots_offset.clear();  // workspace layout depends on the group list
+  return LRR_OK;
+}
+
+int lrr_reserve(lrr_ctx* ctx, int64_t max_variants) {
+  if (!ctx) return LRR_EINVAL;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  DeviceGuard guard(c->device);
+  if (c->groups.empty()) return fail(c, LRR_ESTATE, "lrr_reserve: add groups first");
+  if (max_variants < 0) return fail(c, LRR_EINVAL, "lrr_reserve: negative size");
+  return ensure_workspace(c, max_variants);
+}
+
+int lrr_run(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int64_t packed_stride, int64_t n_samples_total,
+            const lrr_group_out* outs, int32_t n_outs, int32_t kernel, void* stream) {
+  CTX_PROLOGUE;
+  if (c->groups.empty()) return fail(c, LRR_ESTATE, "lrr_run: no groups (call lrr_add_group)");
+  if (n_outs != (int32_t)c->groups.size() || !outs) return fail(c, LRR_EINVAL, "lrr_run: need one lrr_group_out per group");
+  if (n_variants < 0) return fail(c, LRR_EINVAL, "lrr_run: negative n_variants");
+  if (n_samples_total != c->n_samples_total) return fail(c, LRR_EINVAL, "lrr_run: n_samples_total differs from the groups'");
+  if (int r = check_packed(c, n_samples_total, packed_stride)) return r;
+  if (packed_stride * 4 != c->groups[0].ns_pad) return fail(c, LRR_EINVAL, "lrr_run: packed_stride must equal lrr_packed_stride(n_samples_total)");
+  if (n_variants == 0) return LRR_OK;
+  if (!d_packed) return fail(c, LRR_EINVAL, "lrr_run: d_packed is NULL");
+  if (int r = ensure_workspace(c, n_variants)) return r;
+
+  if (c->timing) {
+    if (!c->ev0) {
+      LRR_CUDA(c, cudaEventCreate(&c->ev0));
+      LRR_CUDA(c, cudaEventCreate(&c->ev1));
+    }
+    LRR_CUDA(c, cudaEventRecord(c->ev0, st));
+  }
+  int k = kernel;
+  if (k == LRR_KERNEL_AUTO) k = tc_supported(c) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
+  if (k == LRR_KERNEL_TC) {
+    if (!tc_supported(c)) return fail(c, LRR_EINVAL, "lrr_run: tensor-core kernel does not support this configuration");
+    if (int r = launch_tc_sweep(c, d_packed, n_variants, packed_stride, st)) return r;
+  } else if (k == LRR_KERNEL_FP64) {
+    if (int r = launch_fp64_sweep(c, d_packed, n_variants, packed_stride, st)) return r;
+  } else {
+    return fail(c, LRR_EINVAL, "lrr_run: unknown kernel id");
+  }
+  c->last_kernel = k;
+  if (c->timing) {
+    LRR_CUDA(c, cudaEventRecord(c->ev1, st));
+    c->ev_valid = true;
+  }
+  for (size_t g = 0; g < c->groups.size(); ++g)
+    if (int r = launch_stats_epilogue(c, (int)g, n_variants, outs[g], st)) return r;
+  return LRR_OK;
+}
+
+int64_t lrr_launch_count(const lrr_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->launches : 0; }
+int lrr_last_kernel(const lrr_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->last_kernel : 0; }
+
+int lrr_set_timing(lrr_ctx* ctx, int enabled) {
+  if (!ctx) return LRR_EINVAL;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  c->timing = enabled ? 1 : 0;
+  if (!enabled) c->ev_valid = false;
+  return LRR_OK;
+}
+
+float lrr_last_sweep_ms(lrr_ctx* ctx) {
+  if (!ctx) return -1.f;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c->ev_valid) return -1.f;
+  DeviceGuard guard(c->device);
+  if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.f;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+int lrr_student_t_two_sided(lrr_ctx* ctx, const double* d_t, int64_t count, double df, double* d_p, double* d_log10_p,
+                            void* stream) {
+  CTX_PROLOGUE;
+  if (count < 0 || !(df > 0)) return fail(c, LRR_EINVAL, "lrr_student_t_two_sided: bad arguments");
+  return launch_student_t(c, d_t, count, df, d_p, d_log10_p, st);
+}
+
+}  // extern "C"

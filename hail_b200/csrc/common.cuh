@@ -1,0 +1,88 @@
+// Shared definitions for the lrr_b200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lrr_b200.h"
+
+namespace lrr {
+
+constexpr int kSamplesPerWord = 16;    // 2 bits per call, 32-bit words
+constexpr int kRowAlignBytes = 128;    // packed row stride granularity (TMA boxes, 128-bit loads)
+constexpr int kMaxGroupCols = 4096;    // sanity bound on K + P per group
+
+// One group of phenotypes sharing a complete-sample set (LinearRegression.scala:228-255 ChainedLinregInput).
+struct Group {
+  int n = 0;              // complete samples
+  int K = 0;              // covariates
+  int P = 0;              // phenotypes
+  int has_intercept = 0;  // constant column handled exactly from integer counts
+  int Kd = 0;             // dot-product covariate columns = K - has_intercept
+  int C = 0;              // dot-product columns = Kd + P
+  int d = 0;              // degrees of freedom n - K - 1 (LR:50)
+  double lbeta = 0.0;     // log B(d/2, 1/2) for the Student-t epilogue
+  int64_t ns_pad = 0;     // padded sample count (= 4 * packed stride)
+  double* d_basis = nullptr;  // [C][ns_pad] column planes; zero rows for excluded / padding samples
+  double* d_qty = nullptr;    // [K][P]
+  double* d_yyp = nullptr;    // [P]
+  uint32_t* d_mask = nullptr; // [ns_pad/16] bit (8i+2s) set iff sample 16w+4s+i is in the group
+  // tensor-core path (filled lazily by tc_prepare_group)
+  int8_t* d_bq = nullptr;     // [ncols_pad][ns_pad] int8 digit planes, K-major rows
+  double* d_colscale = nullptr;  // [C] value of one unit of the lowest digit
+  int ncols_pad = 0;
+  int n_slices = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  std::string err;
+  std::vector<Group> groups;
+  int64_t n_samples_total = 0;
+  // workspaces
+  int64_t reserved_variants = 0;
+  int32_t* d_counts = nullptr;  // [G][M][4] n1, n2, nmiss, pad
+  double* d_dots = nullptr;     // [sum_g C_g][M]... laid out per group: [M][C_g]
+  std::vector<int64_t> dots_offset;  // per group offset (in doubles) into d_dots
+  int64_t launches = 0;
+  int last_kernel = 0;
+  int sm_count = 148;
+  void* tc_state = nullptr;  // opaque, owned by tc_kernel.cu
+  // optional device timing of the sweep kernel(s) of the last lrr_run (bench roofline)
+  int timing = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+};
+
+int fail(Ctx* c, int code, const std::string& msg);
+int cuda_fail(Ctx* c, cudaError_t e, const char* what);
+
+#define LRR_CUDA(ctx, call)                                  \
+  do {                                                       \
+    cudaError_t _e = (call);                                 \
+    if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call); \
+  } while (0)
+
+// kernels / stages implemented in the other translation units
+int launch_pack_bed(Ctx*, const uint8_t*, int64_t, int64_t, int64_t, uint8_t*, int64_t, cudaStream_t);
+int launch_pack_i8(Ctx*, const int8_t*, int64_t, int64_t, uint8_t*, int64_t, cudaStream_t);
+int launch_unpack_i8(Ctx*, const uint8_t*, int64_t, int64_t, int64_t, int8_t*, cudaStream_t);
+int launch_unpack_bed(Ctx*, const uint8_t*, int64_t, int64_t, int64_t, uint8_t*, int64_t, cudaStream_t);
+int launch_bn_fill(Ctx*, const uint32_t*, int, const uint8_t*, int64_t, int64_t, int64_t, uint64_t, uint8_t*, int64_t,
+                   cudaStream_t);
+int launch_fp64_sweep(Ctx*, const uint8_t* d_packed, int64_t M, int64_t stride, cudaStream_t);
+int launch_tc_sweep(Ctx*, const uint8_t* d_packed, int64_t M, int64_t stride, cudaStream_t);
+bool tc_supported(const Ctx*);
+void tc_release(Ctx*);
+int launch_stats_epilogue(Ctx*, int g, int64_t M, const lrr_group_out& out, cudaStream_t);
+int launch_student_t(Ctx*, const double*, int64_t, double, double*, double*, cudaStream_t);
+
+// position of sample `j` (0..15 within its word) in the packed word: bits [8i+2s, 8i+2s+1], j = 4s+i
+__host__ __device__ inline int sample_shift(int j) { return 8 * (j & 3) + 2 * (j >> 2); }
+
+// log B(a, 1/2) stable for large a (host)
+double log_beta_half(double a);
+
+}  // namespace lrr

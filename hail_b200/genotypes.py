@@ -1,0 +1,122 @@
+"""The device genotype store: 2-bit packed calls resident in HBM (ingest row of SURVEY.md 8).
+
+Replaces, for the GWAS case x = GT.n_alt_alleles(), the reference's per-entry region values
+(`array<struct{x: float64}>`, 16 B per entry; hail/hail/src/is/hail/types/physical/PCanonicalArray.scala:48-117)
+with 0.25 B per call.  Format authority for the PLINK side: hail/hail/src/is/hail/io/plink/LoadPlink.scala:37-38,
+240-251 (magic + size check), :475-481 and :525 (codes and bit order).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+BED_MAGIC = bytes([0x6C, 0x1B, 0x01])  # LoadPlink.scala:37-38 ; ExportPlink.scala:10
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class PackedGenotypes:
+    """[n_variants, stride] uint8 on one CUDA device, rows in the lrr_b200 store layout (include/lrr_b200.h)."""
+
+    def __init__(self, data: torch.Tensor, n_variants: int, n_samples: int):
+        assert data.is_cuda and data.dtype == torch.uint8 and data.dim() == 2
+        self.data = data
+        self.n_variants = int(n_variants)
+        self.n_samples = int(n_samples)
+        self.stride = int(data.shape[1])
+        assert data.shape[0] == self.n_variants
+        assert self.stride == packed_stride(self.n_samples)
+
+    @property
+    def device(self):
+        return self.data.device
+
+    @property
+    def nbytes(self):
+        return self.n_variants * self.stride
+
+    # ---- constructors -----------------------------------------------------------------------
+    @classmethod
+    def empty(cls, n_variants, n_samples, device=0):
+        dev = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        stride = packed_stride(n_samples)
+        return cls(torch.empty((n_variants, stride), dtype=torch.uint8, device=dev), n_variants, n_samples)
+
+    @classmethod
+    def from_bed_rows(cls, rows, n_samples, device=0, chunk_variants=1 << 16):
+        """rows: uint8 [M, >= ceil(N/4)] PLINK SNP-major body (host numpy or torch)."""
+        rows_t = torch.as_tensor(np.ascontiguousarray(rows) if isinstance(rows, np.ndarray) else rows)
+        assert rows_t.dtype == torch.uint8 and rows_t.dim() == 2
+        M, bed_stride = rows_t.shape
+        if bed_stride < (n_samples + 3) // 4:
+            raise ValueError("bed row shorter than ceil(n_samples/4) bytes (LoadPlink.scala:240-251)")
+        out = cls.empty(M, n_samples, device)
+        ctx = _lib.context(out.device.index)
+        with torch.cuda.device(out.device):
+            for lo in range(0, M, chunk_variants):
+                hi = min(M, lo + chunk_variants)
+                d_in = rows_t[lo:hi].to(out.device, non_blocking=True).contiguous()
+                ctx.check(ctx.lib.lrr_pack_bed(ctx.handle, d_in.data_ptr(), hi - lo, bed_stride, n_samples,
+                                               out.data[lo:hi].data_ptr(), out.stride, _stream_ptr(out.device)))
+        return out
+
+    @classmethod
+    def from_bed_file(cls, path, n_samples, n_variants, device=0):
+        raw = np.fromfile(path, dtype=np.uint8)
+        stride = (n_samples + 3) // 4
+        if raw.size < 3 or bytes(raw[:3]) != BED_MAGIC:
+            raise ValueError(f"{path}: not a SNP-major PLINK .bed (bad magic)")
+        if raw.size != 3 + n_variants * stride:
+            raise ValueError(f"{path}: size {raw.size} != 3 + n_variants*ceil(n_samples/4) = {3 + n_variants * stride}")
+        return cls.from_bed_rows(raw[3:].reshape(n_variants, stride), n_samples, device)
+
+    @classmethod
+    def from_dosage(cls, dosage, device=0, chunk_variants=1 << 14):
+        """dosage: int8 [M, N] with 0/1/2 and anything else (e.g. -1) = missing; float arrays with NaN accepted."""
+        d = np.asarray(dosage)
+        if d.dtype.kind == "f":
+            bad = ~np.isin(d, (0.0, 1.0, 2.0))
+            d = np.where(bad, -1, d).astype(np.int8)
+        d = np.ascontiguousarray(d, dtype=np.int8)
+        M, N = d.shape
+        out = cls.empty(M, N, device)
+        ctx = _lib.context(out.device.index)
+        with torch.cuda.device(out.device):
+            for lo in range(0, M, chunk_variants):
+                hi = min(M, lo + chunk_variants)
+                d_in = torch.from_numpy(d[lo:hi]).to(out.device)
+                ctx.check(ctx.lib.lrr_pack_dosage_i8(ctx.handle, d_in.data_ptr(), hi - lo, N,
+                                                     out.data[lo:hi].data_ptr(), out.stride, _stream_ptr(out.device)))
+        return out
+
+    # ---- views / export ---------------------------------------------------------------------
+    def rows(self, lo, hi):
+        lo, hi = int(lo), int(hi)
+        return PackedGenotypes(self.data[lo:hi], hi - lo, self.n_samples)
+
+    def to_dosage(self) -> np.ndarray:
+        """int8 [M, N], missing = -1."""
+        ctx = _lib.context(self.device.index)
+        out = torch.empty((self.n_variants, self.n_samples), dtype=torch.int8, device=self.device)
+        with torch.cuda.device(self.device):
+            ctx.check(ctx.lib.lrr_unpack_dosage_i8(ctx.handle, self.data.data_ptr(), self.stride, self.n_variants,
+                                                   self.n_samples, out.data_ptr(), _stream_ptr(self.device)))
+        return out.cpu().numpy()
+
+
+def packed_stride(n_samples: int) -> int:
+    return int(_lib.load().lrr_packed_stride(int(n_samples)))
+
+
+def read_plink_shape(bim_path, fam_path):
+    with open(bim_path) as f:
+        n_variants = sum(1 for line in f if line.strip())
+    with open(fam_path) as f:
+        n_samples = sum(1 for line in f if line.strip())
+    return n_variants, n_samples

@@ -1,0 +1,268 @@
+"""`linear_regression_rows` -- host side of the B200 path.
+
+Mirrors the reference's operator interface for this one path:
+  * Python API + validation     hail/python/hail/methods/statgen.py:195-224 (pass_through), 227-408
+  * plugin config + schema      hail/python/hail/ir/table_ir.py:948-997; LinearRegression.scala:18-44, 198-224
+  * driver prologue             LinearRegression.scala:47-78 / 228-257, RegressionUtils.scala:88-128
+The per-partition hot loop (LR:95-193 / 274-402) runs in the CUDA library behind include/lrr_b200.h.
+PyTorch is used only for device buffers / streams; there is no CPU fallback for the hot loop.
+"""
+from __future__ import annotations
+
+import ctypes
+import itertools
+import logging
+import warnings
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from .matrixtable import (ChainedField, ColumnExpression, EntryExpression, Expression, ExpressionException,
+                          MatrixTable, RowExpression, Table)
+
+log = logging.getLogger("hail_b200")
+
+STAT_FIELDS = ["y_transpose_x", "beta", "standard_error", "t_stat", "p_value"]
+
+
+class FatalError(Exception):
+    """hail.utils.java.FatalError -- what `fatal(...)` in the JVM surfaces as (py4j_backend.py:302-307)."""
+
+
+def _plural(n, word):
+    return word if n == 1 else word + "s"
+
+
+# ---- statgen.py:195-224 ------------------------------------------------------------------------
+def _get_regression_row_fields(mt: MatrixTable, pass_through, method) -> "OrderedDict[str, object]":
+    row_fields = OrderedDict((k, k) for k in mt.row_key)
+    for f in pass_through:
+        if isinstance(f, str):
+            if f not in mt.row:
+                raise ValueError(f"'{method}/pass_through': MatrixTable has no row field {f!r}")
+            if f in row_fields:
+                if f in mt.row_key:  # allow silent pass through of key fields
+                    pass
+                else:
+                    raise ValueError(f"'{method}/pass_through': found duplicated field {f!r}")
+            row_fields[f] = mt.row[f]
+        else:
+            assert isinstance(f, Expression)
+            if not f.is_nested_field:
+                raise ValueError(f"'{method}/pass_through': expect fields or nested fields, not complex expressions")
+            if f.axes != frozenset({"row"}):
+                raise ExpressionException(
+                    f"'{method}/pass_through': require row-indexed fields, found indices {sorted(f.axes)}")
+            name = f.name
+            if name in row_fields:
+                if not (name in mt.row_key and f.values is mt.row.get(name)):
+                    raise ValueError(f"'{method}/pass_through': found duplicated field {name!r}")
+            row_fields[name] = f.values
+    for k in mt.row_key:
+        del row_fields[k]
+    return row_fields
+
+
+# ---- statgen.py:4881-4888 ----------------------------------------------------------------------
+def _warn_if_no_intercept(caller, covariates):
+    if all(isinstance(e, Expression) and e.axes for e in covariates):
+        warnings.warn(f"{caller}: model appears to have no intercept covariate."
+                      "\n    To include an intercept, add 1.0 to the list of covariates.")
+        return True
+    return False
+
+
+def _column_values(e, mt, what):
+    """Evaluate a column-indexed float expression to float64 [n_cols] (NaN = missing)."""
+    if isinstance(e, ColumnExpression):
+        if e.source is not mt:
+            raise ExpressionException(f"'{what}': expression is not from the same MatrixTable as 'x'")
+        return e.values
+    if isinstance(e, Expression):
+        raise ExpressionException(f"'{what}': expected a column-indexed expression, found indices {sorted(e.axes)}")
+    if isinstance(e, (bool, int, float, np.integer, np.floating)):
+        return np.full(mt.count_cols(), float(e))
+    raise TypeError(f"'{what}': expected expression of type float64, found {type(e).__name__}")
+
+
+# ---- the driver prologue: RU:88-128 + LR:47-78 ---------------------------------------------------
+class GroupBasis:
+    """What the reference broadcasts per group (ChainedLinregInput, LR:409-417), in the residualised form the
+    device consumes (include/lrr_b200.h lrr_add_group)."""
+
+    def __init__(self, ys, cov, col_index, group_index=None):
+        ys = np.asarray(ys, dtype=np.float64)   # [n_cols, P]
+        cov = np.asarray(cov, dtype=np.float64).reshape(ys.shape[0], -1)  # [n_cols, K]
+        n_cols, P = ys.shape
+        K = cov.shape[1]
+        if P == 0:
+            raise FatalError("No phenotypes present.")  # RU:97-98
+        keep = ~np.isnan(ys).any(axis=1) & ~np.isnan(cov).any(axis=1)  # RU:100-110
+        n = int(keep.sum())
+        if n == 0:
+            raise FatalError("No complete samples: each sample is missing its phenotype or some covariate")  # RU:113-114
+        if n < n_cols:
+            log.warning("%d of %d samples have a missing phenotype or covariate.", n_cols - n, n_cols)  # RU:124-125
+        d = n - K - 1
+        if d < 1:  # LR:55-58
+            raise FatalError(f"{n} samples and {K + 1} {_plural(K, 'covariate')} (including x) implies {d} degrees of freedom.")
+        tag = "" if group_index is None else f"[{group_index}]"
+        log.info("linear_regression_rows%s: running on %d samples for %d response %s y,\n"
+                 "    with input variable x, and %d additional %s...", tag, n, P, _plural(P, "variable"), K,
+                 _plural(K, "covariate"))  # LR:60-63 / 241-244
+        y = ys[keep]
+        c = cov[keep]
+        self.n, self.K, self.P, self.d = n, K, P, d
+        self.complete_idx = np.ascontiguousarray(np.asarray(col_index)[keep], dtype=np.int32)  # into the packed store
+        if K > 0:
+            q, _ = np.linalg.qr(c, mode="reduced")  # LR:67 (only Q Q^T enters the results)
+            q, has_intercept = _rotate_constant_first(q)
+        else:
+            q, has_intercept = np.zeros((n, 0)), False
+        qty = q.T @ y                                  # LR:71
+        self.has_intercept = has_intercept
+        self.qty = np.ascontiguousarray(qty)           # [K, P]
+        self.yyp = np.ascontiguousarray(np.einsum("ij,ij->j", y, y) - np.einsum("ij,ij->j", qty, qty))  # LR:78
+        y_res = y - q @ qty                            # so that y_res . x == ytx - Qty^T qtx (LR:146)
+        y_res -= q @ (q.T @ y_res)                     # one re-orthogonalisation pass
+        kd0 = 1 if has_intercept else 0
+        self.q_cols = np.ascontiguousarray(q[:, kd0:].T)   # [Kd, n]
+        self.y_res = np.ascontiguousarray(y_res.T)          # [P, n]
+
+
+def _rotate_constant_first(q):
+    """If the constant vector lies in span(q), rotate the orthonormal basis so column 0 is exactly 1/sqrt(n).
+
+    Q Q^T (all that enters LR:139-146) is unchanged.  Lets the device form the constant column's projection
+    exactly from integer genotype counts, removing the dominant cancellation in x.x - |Q^T x|^2.
+    """
+    n, K = q.shape
+    one = np.full(n, 1.0 / np.sqrt(n))
+    u = q.T @ one
+    resid = one - q @ u
+    if np.linalg.norm(resid) > 1e-9:
+        return q, False
+    u /= np.linalg.norm(u)
+    # Householder reflection H with H e1 = u  ->  (q H)[:, 0] = q u = const
+    e1 = np.zeros(K)
+    e1[0] = 1.0
+    v = e1 - u
+    nv = np.linalg.norm(v)
+    H = np.eye(K) if nv < 1e-15 else np.eye(K) - 2.0 * np.outer(v, v) / (nv * nv)
+    q2 = q @ H
+    q2[:, 0] = one  # exact constant
+    # re-orthogonalise the remaining columns against the constant (and each other) to clean up roundoff
+    rest = q2[:, 1:] - np.outer(one, one @ q2[:, 1:])
+    if K > 1:
+        rest, _ = np.linalg.qr(rest, mode="reduced")
+        rest -= np.outer(one, one @ rest)
+    return np.column_stack([one, rest]), True
+
+
+def _run_device(genotypes, bases, kernel="auto", want_log10_p=False, chunk_variants=None):
+    """Push the group bases and sweep all rows.  Returns per-group dicts of torch CUDA tensors."""
+    dev = genotypes.device
+    ctx = _lib.context(dev.index)
+    M, N = genotypes.n_variants, genotypes.n_samples
+    with torch.cuda.device(dev):
+        ctx.check(ctx.lib.lrr_clear_groups(ctx.handle))
+        for b in bases:
+            ctx.check(ctx.lib.lrr_add_group(
+                ctx.handle, N, b.n, b.K, b.P, int(b.has_intercept), b.complete_idx.ctypes.data,
+                b.q_cols.ctypes.data if b.q_cols.size else None, b.y_res.ctypes.data,
+                b.qty.ctypes.data if b.qty.size else None, b.yyp.ctypes.data))
+        outs = []
+        for b in bases:
+            o = {
+                "n": torch.empty(M, dtype=torch.int32, device=dev),
+                "n_missing": torch.empty(M, dtype=torch.int32, device=dev),
+                "sum_x": torch.empty(M, dtype=torch.float64, device=dev),
+            }
+            for f in STAT_FIELDS:
+                o[f] = torch.empty((M, b.P), dtype=torch.float64, device=dev)
+            if want_log10_p:
+                o["log10_p"] = torch.empty((M, b.P), dtype=torch.float64, device=dev)
+            outs.append(o)
+        step = M if not chunk_variants else int(chunk_variants)
+        ctx.check(ctx.lib.lrr_reserve(ctx.handle, min(M, step) if M else 0))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        kid = _lib.KERNELS[kernel]
+        for lo in range(0, M, max(step, 1)):
+            hi = min(M, lo + step)
+            arr = (_lib.GroupOut * len(bases))()
+            for g, (b, o) in enumerate(zip(bases, outs)):
+                arr[g].n = o["n"][lo:hi].data_ptr()
+                arr[g].n_missing = o["n_missing"][lo:hi].data_ptr()
+                arr[g].sum_x = o["sum_x"][lo:hi].data_ptr()
+                for f in STAT_FIELDS:
+                    setattr(arr[g], f, o[f][lo:hi].data_ptr())
+                arr[g].log10_p = o["log10_p"][lo:hi].data_ptr() if want_log10_p else None
+            ctx.check(ctx.lib.lrr_run(ctx.handle, genotypes.data[lo:hi].data_ptr(), hi - lo, genotypes.stride, N,
+                                      arr, len(bases), kid, stream))
+    return outs
+
+
+def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, weights=None,
+                           _kernel="auto", _log10_p=False) -> Table:
+    """For each row, test an input variable for association with response variables using linear regression.
+
+    Drop-in for `hl.linear_regression_rows` (statgen.py:235): same arguments, same validation, same output
+    fields in the same order -- row key, pass_through, then `n, sum_x, y_transpose_x, beta, standard_error,
+    t_stat, p_value` (scalars when `y` is one expression, arrays of length P for a list, arrays over groups for
+    a list of lists).  `block_size` is accepted and numerically inert on the GPU.
+    """
+    if weights is not None:
+        raise NotImplementedError("linear_regression_rows: `weights` (WLS, statgen.py:557-581) is out of scope "
+                                  "for the B200 path")
+    if not isinstance(block_size, int):
+        raise TypeError("linear_regression_rows: 'block_size' must be int")
+    if not isinstance(x, EntryExpression):
+        raise ExpressionException("'linear_regression_rows/x': expected an entry-indexed expression "
+                                  "(e.g. mt.GT.n_alt_alleles())")
+    mt = x.source
+
+    y_is_list = isinstance(y, (list, tuple))
+    if y_is_list and len(y) == 0:
+        raise ValueError("'linear_regression_rows': found no values for 'y'")  # SG:351-352
+    is_chained = y_is_list and isinstance(y[0], (list, tuple))
+    if is_chained and any(len(lst) == 0 for lst in y):
+        raise ValueError("'linear_regression_rows': found empty inner list for 'y'")  # SG:354-355
+
+    groups = [list(g) for g in y] if is_chained else [list(y) if y_is_list else [y]]
+    y_vals = [[_column_values(e, mt, "linear_regression_rows/y") for e in g] for g in groups]
+    cov_vals = [_column_values(e, mt, "linear_regression_rows/covariates") for e in covariates]
+    _warn_if_no_intercept("linear_regression_rows", covariates)
+    row_fields = _get_regression_row_fields(mt, pass_through, "linear_regression_rows")
+
+    n_cols = mt.count_cols()
+    cov = np.column_stack(cov_vals) if cov_vals else np.empty((n_cols, 0))
+    bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None)
+             for i, g in enumerate(y_vals)]
+
+    outs = _run_device(mt.genotypes, bases, kernel=_kernel, want_log10_p=_log10_p)
+    torch.cuda.synchronize(mt.genotypes.device)
+    host = [{k: v.cpu().numpy() for k, v in o.items()} for o in outs]
+
+    fields = OrderedDict()
+    for k in mt.row_key:
+        fields[k] = mt.row[k]
+    for k, v in row_fields.items():
+        fields[k] = v
+    if is_chained:  # LR:208-216
+        fields["n"] = np.stack([h["n"] for h in host], axis=1)
+        fields["sum_x"] = np.stack([h["sum_x"] for h in host], axis=1)
+        for f in STAT_FIELDS:
+            fields[f] = ChainedField(h[f] for h in host)
+        if _log10_p:
+            fields["log10_p"] = ChainedField(h["log10_p"] for h in host)
+    else:
+        h = host[0]
+        fields["n"] = h["n"]
+        fields["sum_x"] = h["sum_x"]
+        for f in STAT_FIELDS + (["log10_p"] if _log10_p else []):
+            fields[f] = h[f] if y_is_list else h[f][:, 0]  # SG:404-406
+    t = Table(fields, key=mt.row_key, n_rows=mt.count_rows())
+    t.n_missing = [h["n_missing"] for h in host] if is_chained else host[0]["n_missing"]
+    return t

@@ -1,0 +1,142 @@
+/*
+ * lrr_b200 -- C ABI of the B200-native per-variant linear regression (Hail `linear_regression_rows`).
+ *
+ * This is the drop-in boundary for ONE reference path.  What each entry point replaces:
+ *
+ *   reference plugin           abstract class MatrixToTableFunction { typ; execute(ctx, MatrixValue): TableValue }
+ *                              hail/hail/src/is/hail/expr/ir/functions/RelationalFunctions.scala:24-32
+ *   lrr_add_group              the driver prologue's broadcasts (completeColIdx, y, Qt, Qty, yyp)
+ *                              hail/hail/src/is/hail/methods/LinearRegression.scala:47-78 (Single), :228-257 (Chained)
+ *   lrr_run                    the per-partition hot loop: setMeanImputedDoubles + block algebra + T.cumulative
+ *                              LinearRegression.scala:95-193 / :274-402, stats/RegressionUtils.scala:16-58
+ *   lrr_pack_bed / _dosage_i8  the upstream entry decode that feeds x (io/plink/LoadPlink.scala:470-530 codes;
+ *                              `GT.n_alt_alleles()` as the entry expression, methods/statgen.py:387-392)
+ *
+ * FFI precedent in the reference (caller-owned buffers, raw addresses, no exceptions across the ABI):
+ *   hail/hail/src/is/hail/methods/IBSFFI.scala:14-23  <->  hail/c/ibs.cpp:105-107   (JNA direct mapping)
+ *   hail/hail/src/is/hail/linalg/BLAS.scala:116-143                                  (raw Long addresses)
+ *   hail/hail/resources/include/hail/NativeStatus.h:12-37                            (errno + message)
+ *
+ * Conventions: every function returns 0 on success or a non-zero LRR_E* code; the message is available
+ * from lrr_last_error().  All `d_*` pointers are DEVICE pointers on the context's device.  A context is
+ * bound to one device and is not thread-safe; distinct contexts are independent.  `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream).  No allocation happens inside lrr_run once
+ * lrr_reserve() has been called for the largest M.
+ */
+#ifndef LRR_B200_H
+#define LRR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRR_OK 0
+#define LRR_EINVAL 1   /* bad argument */
+#define LRR_ECUDA 2    /* CUDA runtime error (message has the CUDA string) */
+#define LRR_ESTATE 3   /* call order / missing groups */
+#define LRR_ENOMEM 4
+
+/* kernels selectable in lrr_run */
+#define LRR_KERNEL_AUTO 0
+#define LRR_KERNEL_FP64 1  /* CUDA-core float64 reference-order kernel */
+#define LRR_KERNEL_TC 2    /* tcgen05 int8-sliced exact-integer kernel */
+
+typedef struct lrr_ctx lrr_ctx;
+
+/* per-group device output pointers; any pointer may be NULL to skip that field.  Arrays of
+ * phenotype-indexed fields are [M, P] row-major (row = variant), matching the reference's
+ * array<float64> of length P per row (LinearRegression.scala:26-34, 173-186). */
+typedef struct {
+  int32_t* n;             /* [M]   number of columns used (same for every row)       LR:170 */
+  int32_t* n_missing;     /* [M]   missing calls among the group's samples (extension; RU:51) */
+  double* sum_x;          /* [M]   LR:136,171 */
+  double* y_transpose_x;  /* [M,P] LR:143 */
+  double* beta;           /* [M,P] LR:150-155 */
+  double* standard_error; /* [M,P] LR:157 */
+  double* t_stat;         /* [M,P] LR:159 */
+  double* p_value;        /* [M,P] LR:160 */
+  double* log10_p;        /* [M,P] optional: log10 of p_value, finite below 1e-308 (extension) */
+} lrr_group_out;
+
+const char* lrr_version(void);
+int lrr_create(lrr_ctx** out, int device);
+void lrr_destroy(lrr_ctx* ctx);
+/* last error message of `ctx` (or of the failed lrr_create when ctx == NULL) */
+const char* lrr_last_error(const lrr_ctx* ctx);
+
+/* ---- ingest: the device genotype store ---------------------------------------------------------
+ * 2 bits per call, variant-major rows of lrr_packed_stride(N) bytes (a multiple of 128).  Codes:
+ * 0,1,2 = number of alternate alleles, 3 = missing.  Within each little-endian 32-bit word, which
+ * covers samples 16w..16w+15, sample 16w+4s+i sits at bits [8i+2s, 8i+2s+1] (so that
+ * (word >> 2s) & 0x03030303 yields four consecutive samples as four bytes).  Padding samples are 0. */
+int64_t lrr_packed_stride(int64_t n_samples);
+/* PLINK .bed SNP-major rows (no 3-byte header), a2_reference=True semantics (LoadPlink.scala:475-481) */
+int lrr_pack_bed(lrr_ctx* ctx, const uint8_t* d_bed, int64_t n_variants, int64_t bed_stride, int64_t n_samples,
+                 uint8_t* d_packed, int64_t packed_stride, void* stream);
+/* int8 dosages [M, N] row-major: 0/1/2, anything else (e.g. -1) = missing */
+int lrr_pack_dosage_i8(lrr_ctx* ctx, const int8_t* d_dosage, int64_t n_variants, int64_t n_samples,
+                       uint8_t* d_packed, int64_t packed_stride, void* stream);
+/* inverse of lrr_pack_dosage_i8 (missing -> -1); for tests and export */
+int lrr_unpack_dosage_i8(lrr_ctx* ctx, const uint8_t* d_packed, int64_t packed_stride, int64_t n_variants,
+                         int64_t n_samples, int8_t* d_dosage, void* stream);
+/* device store -> PLINK .bed SNP-major rows (inverse of lrr_pack_bed; the bytes ExportPlink would write,
+ * hail/hail/src/is/hail/expr/ir/MatrixWriter.scala:2270-2285).  bed_stride >= ceil(n_samples/4). */
+int lrr_unpack_bed(lrr_ctx* ctx, const uint8_t* d_packed, int64_t packed_stride, int64_t n_variants, int64_t n_samples,
+                   uint8_t* d_bed, int64_t bed_stride, void* stream);
+/* seeded Balding-Nichols style synthetic fill (methods/statgen.py:4182-4291 distributionally).  The host
+ * draws per-variant per-population allele frequencies and turns them into integer thresholds
+ * d_thresholds [M, n_pops, 3] (uint32, 16-bit scale, 0..65536): with u = 16 counter-based random bits,
+ * u < t0 -> missing, u < t1 -> 0 alt, u < t2 -> 1 alt, else 2 alt (call ~ Cat(q^2, 2pq, p^2), SG:4290-4291).
+ * d_pop [N] (uint8) is each sample's population (SG:4254).  The value of call (first_variant + r, j)
+ * depends only on (seed, first_variant + r, j), so any variant range can be regenerated anywhere. */
+int lrr_bn_fill(lrr_ctx* ctx, const uint32_t* d_thresholds, int n_pops, const uint8_t* d_pop, int64_t n_variants,
+                int64_t first_variant, int64_t n_samples, uint64_t seed, uint8_t* d_packed, int64_t packed_stride,
+                void* stream);
+
+/* ---- basis: one call per group of phenotypes (Single = 1 group, Chained = G groups) -------------
+ * The host has selected the group's complete samples (RU:88-128), computed an orthonormal basis Q of
+ * the covariates (LR:65-69) and residualised y against it.  Arrays may be host or device memory.
+ *   complete_idx [n]     ascending sample indices kept (RU:116-127)
+ *   q_cols  [Kd, n]      the Kd dot-product columns of Q restricted to the kept samples, row-major
+ *                        by column; Kd = K - has_intercept.  When has_intercept != 0 the caller has
+ *                        rotated Q so that its first column is the constant 1/sqrt(n) (dropped here:
+ *                        its projection is formed exactly from integer genotype counts) and the other
+ *                        K-1 columns are orthogonal to it.
+ *   y_res   [P, n]       y - Q Q^T y, row-major by phenotype
+ *   qty     [K, P]       Q^T y (full K rows, row 0 = the constant column when has_intercept), LR:71
+ *   yyp     [P]          y.y - Qty.Qty, LR:78
+ * Fails with LRR_EINVAL when n - K - 1 < 1 (LR:55-58). */
+int lrr_clear_groups(lrr_ctx* ctx);
+int lrr_add_group(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, int32_t P, int32_t has_intercept,
+                  const int32_t* complete_idx, const double* q_cols, const double* y_res, const double* qty,
+                  const double* yyp);
+int lrr_num_groups(const lrr_ctx* ctx);
+
+/* ---- the hot call ------------------------------------------------------------------------------ */
+/* pre-size internal workspaces for up to max_variants rows per lrr_run call */
+int lrr_reserve(lrr_ctx* ctx, int64_t max_variants);
+/* regress `n_variants` packed rows against every group; outs[g] receives group g's fields */
+int lrr_run(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int64_t packed_stride, int64_t n_samples_total,
+            const lrr_group_out* outs, int32_t n_outs, int32_t kernel, void* stream);
+/* number of kernel launches issued by this context since creation (for bench accounting) */
+int64_t lrr_launch_count(const lrr_ctx* ctx);
+/* which kernel LRR_KERNEL_AUTO resolved to on the last lrr_run */
+int lrr_last_kernel(const lrr_ctx* ctx);
+
+/* measurement hook: when enabled, lrr_run brackets its sweep kernel(s) -- not the per-variant epilogue -- with
+ * CUDA events on `stream`; lrr_last_sweep_ms synchronises on them and returns the elapsed milliseconds of the
+ * last lrr_run's sweep (negative if none was recorded). */
+int lrr_set_timing(lrr_ctx* ctx, int enabled);
+float lrr_last_sweep_ms(lrr_ctx* ctx);
+
+/* two-sided Student-t p-value on the device, exposed for unit tests of the epilogue:
+ * p[i] = 2 * P[T_df <= -|t[i]|]  (jdistlib T.cumulative call sites LR:160, LR:344) */
+int lrr_student_t_two_sided(lrr_ctx* ctx, const double* d_t, int64_t count, double df, double* d_p, double* d_log10_p,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRR_B200_H */

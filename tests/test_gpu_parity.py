@@ -1,0 +1,319 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Mirrors hail/python/test/hail/methods/test_statgen.py:62-93 (basic), 134-221 (chained), 223-284 (R goldens),
+366-457 (fam / multi-pheno).  Tolerances are BASELINE.json's: n / n_missing / integer sums exact; sum_x,
+y_transpose_x, beta, standard_error, t_stat relative 1e-6 (the reference's own `_same` comparator); p_value
+relative 1e-5.  `t_floor=1e-9` additionally accepts |delta t| <= 1e-9 for statistics whose true value is ~0
+(relative error of a float64 dot product that cancels to ~0 is unbounded in any implementation).
+"""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import bed as obed
+from oracle import linreg_oracle as O
+from tests.bn_mirror import bn_fill_numpy
+from tests.helpers import GOLDEN, assert_fields_close, load_regression_linear
+
+KERNELS = ["fp64"]
+
+
+def _hb():
+    import hail_b200 as hb
+    return hb
+
+
+def _kernel_available(kernel, hb, n_groups=1):
+    return True
+
+
+def _mt_from_dosage(x, **cols):
+    hb = _hb()
+    gt = hb.PackedGenotypes.from_dosage(np.where(np.isnan(x), -1, x).astype(np.int8))
+    rows = {"locus": np.array([("1", i + 1) for i in range(x.shape[0])], dtype=object),
+            "alleles": np.array([("C", "T")] * x.shape[0], dtype=object),
+            "qual": np.arange(x.shape[0], dtype=np.float64)}
+    return hb.MatrixTable(gt, rows=rows, cols=cols, row_key=("locus", "alleles"))
+
+
+def _as_oracle_dict(ht, P_list=False):
+    d = {"n": ht.n}
+    for f in ("sum_x", "y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+        v = np.asarray(ht[f])
+        d[f] = v if (v.ndim == 2 or f == "sum_x") else v[:, None]
+    return d
+
+
+# ---------------------------------------------------------------------------------------------
+def test_pack_roundtrips_and_bed_codes():
+    hb = _hb()
+    rng = np.random.default_rng(0)
+    for N in (1, 5, 16, 17, 250, 513, 1031):
+        x = rng.integers(-1, 3, size=(37, N)).astype(np.int8)
+        g = hb.PackedGenotypes.from_dosage(x)
+        assert g.stride % 128 == 0
+        assert np.array_equal(g.to_dosage(), x)
+        xf = np.where(x < 0, np.nan, x).astype(np.float64)
+        rows = obed.encode_rows(xf)
+        g2 = hb.PackedGenotypes.from_bed_rows(rows, N)
+        assert np.array_equal(g2.to_dosage(), x)
+        assert torch.equal(g.data, g2.data)  # both packers produce the identical store, padding included
+
+
+def test_pack_reference_plink_fixtures():
+    hb = _hb()
+    for name in ("fastlmm.npz", "bn_4x1024.npz"):
+        z = np.load(os.path.join(GOLDEN, name))
+        N, M = int(z["n_samples"]), int(z["n_variants"])
+        rows = obed.bed_body(z["bed"], N, M)
+        want = obed.decode_rows(rows, N)
+        got = hb.PackedGenotypes.from_bed_rows(rows, N).to_dosage().astype(np.float64)
+        got[got < 0] = np.nan
+        assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_bn_fill_matches_numpy_mirror():
+    hb = _hb()
+    from hail_b200 import bn
+    for (N, M, mr) in ((100, 64, 0.0), (1000, 300, 0.25)):
+        pop, th, af = bn.bn_parameters(3, N, M, missing_rate=mr, seed=7)
+        g = bn.bn_fill(hb.PackedGenotypes.empty(M, N), pop, th, seed=7)
+        want = bn_fill_numpy(th, pop, N, seed=7)
+        got = g.to_dosage()
+        assert np.array_equal(got, want)
+        # shard regeneration: rows [100, 164) generated on their own equal the slice
+        if M > 164:
+            pop2, th2, _ = bn.bn_parameters(3, N, 64, missing_rate=mr, seed=7, first_variant=100)
+            g2 = bn.bn_fill(hb.PackedGenotypes.empty(64, N), pop2, th2, seed=7, first_variant=100)
+            assert np.array_equal(g2.to_dosage(), want[100:164])
+        if mr:
+            assert abs((want < 0).mean() - mr) < 0.01
+        obs = np.where(want >= 0, want, 0).sum() / (2.0 * (want >= 0).sum())
+        assert abs(obs - af[:, pop].mean()) < 0.01
+
+
+def test_student_t_device_matches_oracle():
+    from hail_b200 import _lib
+    ctx = _lib.context(0)
+    t = np.concatenate([np.linspace(-45, 45, 721), [0.0, 1e-12, -1e-9, 1.73, 1.74, np.nan, np.inf, -np.inf]])
+    d_t = torch.from_numpy(t).cuda()
+    for df in (1, 2, 5, 30, 994, 399989, 499989):
+        d_p = torch.empty_like(d_t)
+        d_l = torch.empty_like(d_t)
+        ctx.check(ctx.lib.lrr_student_t_two_sided(ctx.handle, d_t.data_ptr(), t.size, float(df), d_p.data_ptr(),
+                                                  d_l.data_ptr(), None))
+        torch.cuda.synchronize()
+        p, l10 = d_p.cpu().numpy(), d_l.cpu().numpy()
+        want = O.two_sided_p(t, df)
+        fin = np.isfinite(t)
+        big = fin & (want > 1e-300)
+        assert np.allclose(p[big], want[big], rtol=1e-9, atol=0), df
+        assert np.isnan(p[np.isnan(t)]).all() and (p[np.isinf(t)] == 0).all()
+        # log scale, including where p underflows (BASELINE: log-scale comparison below 1e-300)
+        for i in np.nonzero(fin)[0][::40]:
+            wl = O.log_two_sided_p(t[i], df) / np.log(10.0)
+            assert abs(l10[i] - wl) <= 1e-8 * max(1.0, abs(wl)), (df, t[i], l10[i], wl)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_reference_golden_with_cov(kernel):  # TS:245-284
+    hb = _hb()
+    x, y, cov, doc = load_regression_linear()
+    mt = _mt_from_dosage(x, pheno=y, Cov1=cov[:, 0], Cov2=cov[:, 1])
+    ht = hb.linear_regression_rows(y=mt.pheno, x=mt.GT.n_alt_alleles(), covariates=[1.0, mt.Cov1, mt.Cov2],
+                                   _kernel=kernel)
+    exp = doc["expected"]["with_cov"]
+    assert (ht.n == 6).all()
+    for pos in ("1", "2", "3"):
+        for f, v in exp[pos].items():
+            assert abs(ht[f][int(pos) - 1] - v) < 5e-7, (pos, f)
+    for v in exp["nan_se"]:
+        assert np.isnan(ht.standard_error[v - 1]) and np.isnan(ht.t_stat[v - 1]) and np.isnan(ht.p_value[v - 1])
+    # against the oracle for the non-degenerate rows (rows 6-10 are roundoff garbage in the reference)
+    want = O.linreg_group(x, y[:, None], np.column_stack([np.ones(8), cov]))
+    got = _as_oracle_dict(ht)
+    good = slice(0, 5)
+    assert_fields_close({k: v[good] for k, v in got.items()}, {k: v[good] for k, v in want.items() if k != "_d"},
+                        t_floor=1e-9)
+    assert np.array_equal(got["sum_x"], want["sum_x"], equal_nan=True) or np.allclose(got["sum_x"], want["sum_x"], rtol=1e-15)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_reference_golden_no_covariates(kernel):  # TS:223-234
+    hb = _hb()
+    x, y, cov, doc = load_regression_linear()
+    mt = _mt_from_dosage(x, pheno=y)
+    with pytest.warns(UserWarning, match="no intercept"):
+        ht = hb.linear_regression_rows(y=mt.pheno, x=mt.GT.n_alt_alleles(), covariates=[], _kernel=kernel)
+    for f, v in doc["expected"]["no_intercept"]["1"].items():
+        assert abs(ht[f][0] - v) < 5e-7, f
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kind", ["is_case", "quant"])
+def test_reference_golden_fam(kernel, kind):  # TS:366-424
+    hb = _hb()
+    x, y, cov, doc = load_regression_linear(fam_pheno=kind)
+    mt = _mt_from_dosage(x, pheno=y, Cov1=cov[:, 0], Cov2=cov[:, 1])
+    ht = hb.linear_regression_rows(y=mt.pheno, x=mt.GT.n_alt_alleles(), covariates=[1.0, mt.Cov1, mt.Cov2],
+                                   _kernel=kernel)
+    exp = doc["expected"]["with_cov"]
+    for pos in ("1", "2"):
+        for f, v in exp[pos].items():
+            assert abs(ht[f][int(pos) - 1] - v) < 5e-7, (pos, f)
+    for v in (6, 7, 8, 9, 10):
+        assert np.isnan(ht.standard_error[v - 1])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_linreg_basic_call_shapes_agree(kernel):  # TS:62-93
+    hb = _hb()
+    x, y, cov, doc = load_regression_linear(pheno_missing_zero=False)
+    mt = _mt_from_dosage(x, pheno=y, cov={"Cov1": cov[:, 0], "Cov2": cov[:, 1]})
+    mt = mt.annotate_entries(x=mt.GT.n_alt_alleles())
+    covs = [1.0, mt.cov.Cov1, mt.cov.Cov2]
+    t1 = hb.linear_regression_rows(y=mt.pheno, x=mt.GT.n_alt_alleles(), covariates=[1.0, mt.cov.Cov1, mt.cov.Cov2 + 1 - 1], _kernel=kernel)
+    t2 = hb.linear_regression_rows(y=mt.pheno, x=mt.x, covariates=covs, _kernel=kernel)
+    t3 = hb.linear_regression_rows(y=[mt.pheno], x=mt.x, covariates=covs, _kernel=kernel)
+    t4 = hb.linear_regression_rows(y=[mt.pheno, mt.pheno], x=mt.x, covariates=covs, _kernel=kernel)
+    p1 = t1.select(p=t1.p_value)
+    assert p1._same(t2.select(p=t2.p_value))
+    assert p1._same(t3.select(p=t3.p_value[:, 0]))
+    assert p1._same(t4.select(p=t4.p_value[:, 0]))
+    assert p1._same(t4.select(p=t4.p_value[:, 1]))
+    assert list(t1.row) == ["locus", "alleles", "n", "sum_x", "y_transpose_x", "beta", "standard_error", "t_stat", "p_value"]
+    assert t1.n.dtype == np.int32 and t1.beta.ndim == 1 and t3.beta.shape == (10, 1) and t4.beta.shape == (10, 2)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_linreg_chained(kernel):  # TS:134-221
+    hb = _hb()
+    x, y, cov, doc = load_regression_linear(pheno_missing_zero=False)
+    mt = _mt_from_dosage(x, pheno=y, cov={"Cov1": cov[:, 0], "Cov2": cov[:, 1]})
+    mt = mt.annotate_entries(x=mt.GT.n_alt_alleles())
+
+    def eq(a, b):
+        a, b = np.asarray(a), np.asarray(b)
+        return bool(((a == b) | (np.isnan(a) & np.isnan(b))).all())
+
+    t1 = hb.linear_regression_rows(y=[[mt.pheno], [mt.pheno]], x=mt.x, covariates=[1, mt.cov.Cov1, mt.cov.Cov2], _kernel=kernel)
+    assert t1.n.shape == (10, 2) and eq(t1.n[:, 0], t1.n[:, 1]) and eq(t1.sum_x[:, 0], t1.sum_x[:, 1])
+    for f in ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+        assert eq(t1[f][0], t1[f][1]), f
+
+    mt2 = mt.filter_cols(mt.cov.Cov2 >= 0)
+    mt3 = mt.filter_cols(mt.cov.Cov2 <= 0)
+    t2 = hb.linear_regression_rows(y=mt2.pheno, x=mt2.x, covariates=[1, mt2.cov.Cov1], _kernel=kernel)
+    t3 = hb.linear_regression_rows(y=mt3.pheno, x=mt3.x, covariates=[1, mt3.cov.Cov1], _kernel=kernel)
+    chained = hb.linear_regression_rows(
+        y=[[mt.pheno.or_missing_unless(mt.cov.Cov2 >= 0)], [mt.pheno.or_missing_unless(mt.cov.Cov2 <= 0)]],
+        x=mt.x, covariates=[1, mt.cov.Cov1], _kernel=kernel)
+    for g, sep in enumerate((t2, t3)):
+        assert eq(chained.n[:, g], sep.n) and eq(chained.sum_x[:, g], sep.sum_x)
+        for f in ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+            assert eq(chained[f][g][:, 0], sep[f]), (g, f)
+
+    phenos = [mt.pheno.or_missing_unless(mt.cov.Cov2 >= -1), mt.pheno.or_missing_unless(mt.cov.Cov2 <= 1)]
+    t4 = hb.linear_regression_rows(phenos, mt.x, covariates=[1], _kernel=kernel)
+    t5 = hb.linear_regression_rows([phenos], mt.x, covariates=[1], _kernel=kernel)
+    assert eq(t4.n, t5.n[:, 0]) and eq(t4.sum_x, t5.sum_x[:, 0])
+    for f in ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+        assert hb.Table({"v": t4[f]}, n_rows=10)._same(hb.Table({"v": t5[f][0]}, n_rows=10)), f
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("P,K,intercept", [(1, 2, True), (3, 4, True), (2, 3, False), (1, 0, False), (5, 1, True)])
+def test_fastlmm_parity_vs_oracle(kernel, P, K, intercept):
+    hb = _hb()
+    z = np.load(os.path.join(GOLDEN, "fastlmm.npz"))
+    N, M = int(z["n_samples"]), int(z["n_variants"])
+    rows = obed.bed_body(z["bed"], N, M)
+    rng = np.random.default_rng(10 * P + K)
+    ys = np.column_stack([z["pheno"]] + [rng.normal(size=N) for _ in range(P - 1)])
+    ys[rng.random(ys.shape) < 0.03] = np.nan
+    cols = ([np.ones(N)] if intercept else []) + [z["cov"][:, 0]] + [rng.normal(size=N) + 0.5 for _ in range(8)]
+    cov = np.column_stack(cols)[:, :K] if K else np.empty((N, 0))
+    x = obed.decode_rows(rows, N)
+    want = O.linreg_group(x, ys, cov)
+    gt = hb.PackedGenotypes.from_bed_rows(rows, N)
+    mt = hb.MatrixTable(gt, cols={f"y{i}": ys[:, i] for i in range(P)} | {f"c{i}": cov[:, i] for i in range(K)})
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ht = hb.linear_regression_rows(y=[mt[f"y{i}"] for i in range(P)], x=mt.GT.n_alt_alleles(),
+                                       covariates=[mt[f"c{i}"] for i in range(K)], _kernel=kernel)
+    got = _as_oracle_dict(ht)
+    nondeg = np.isfinite(want["standard_error"]).all(axis=1)
+    assert nondeg.sum() > 0.9 * M
+    assert_fields_close({k: v[nondeg] for k, v in got.items()}, {k: v[nondeg] for k, v in want.items() if k != "_d"},
+                        t_floor=1e-9, ctx=f"{kernel} P={P} K={K}")
+    # bit-exact integer outputs: n, missing counts, and sum_x on missing-free rows
+    idx = O.complete_samples(ys, cov)[2]
+    nm = np.isnan(x[:, idx]).sum(axis=1)
+    assert np.array_equal(ht.n_missing, nm)
+    clean = nm == 0
+    assert np.array_equal(got["sum_x"][clean], want["sum_x"][clean])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_bn_missing_chained_vs_oracle(kernel):
+    """BASELINE config 3 in miniature: 25 % missing calls, y=[[y1],[y2]] with per-group phenotype missingness."""
+    hb = _hb()
+    N, M = 3000, 512
+    mt = hb.balding_nichols_model(3, N, M, missing_rate=0.25, seed=3)
+    rng = np.random.default_rng(5)
+    dos = mt.genotypes.to_dosage().astype(np.float64)
+    dos[dos < 0] = np.nan
+    cov = np.column_stack([np.ones(N)] + [rng.normal(size=N) for _ in range(9)])
+    y1 = rng.normal(size=N) + 0.3 * np.nan_to_num(dos[7]) ; y2 = rng.normal(size=N)
+    y1[rng.random(N) < 0.1] = np.nan
+    y2[rng.random(N) < 0.2] = np.nan
+    mt = mt.annotate_cols(y1=y1, y2=y2, **{f"c{i}": cov[:, i] for i in range(10)})
+    ht = hb.linear_regression_rows(y=[[mt.y1], [mt.y2]], x=mt.GT.n_alt_alleles(),
+                                   covariates=[mt[f"c{i}"] for i in range(10)], _kernel=kernel)
+    want = O.linreg_chained(dos, [y1[:, None], y2[:, None]], cov)
+    for g in range(2):
+        got = {"n": ht.n[:, g], "sum_x": ht.sum_x[:, g]}
+        for f in ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+            got[f] = ht[f][g]
+        assert_fields_close(got, {k: v for k, v in want[g].items() if k != "_d"}, t_floor=1e-9, ctx=f"{kernel} g={g}")
+        idx = O.complete_samples([y1, y2][g][:, None], cov)[2]
+        assert np.array_equal(ht.n_missing[g], np.isnan(dos[:, idx]).sum(axis=1))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_edge_cases(kernel):
+    hb = _hb()
+    rng = np.random.default_rng(2)
+    N = 70
+    x = rng.integers(0, 3, size=(9, N)).astype(np.float64)
+    x[0] = np.nan            # all-missing variant -> every statistic NaN, sum_x NaN (RU:52)
+    x[1] = 1.0               # constant -> degenerate
+    x[2, ::2] = np.nan
+    y = rng.normal(size=N)
+    mt = _mt_from_dosage(x, y=y, c=rng.normal(size=N))
+    ht = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=[1.0, mt.c], _kernel=kernel)
+    assert np.isnan(ht.sum_x[0]) and np.isnan(ht.beta[0]) and np.isnan(ht.p_value[0])
+    assert ht.sum_x[1] == N and np.isnan(ht.standard_error[1])
+    want = O.linreg_group(x, y[:, None], np.column_stack([np.ones(N), mt.c.values]))
+    got = _as_oracle_dict(ht)
+    assert_fields_close({k: v[2:] for k, v in got.items()}, {k: v[2:] for k, v in want.items() if k != "_d"}, t_floor=1e-9)
+    # empty row range
+    empty = hb.MatrixTable(hb.PackedGenotypes.empty(0, N), cols={"y": y})
+    ht0 = hb.linear_regression_rows(y=empty.y, x=empty.GT.n_alt_alleles(), covariates=[1.0], _kernel=kernel)
+    assert ht0.count() == 0 and ht0.beta.shape == (0,)
+
+
+def test_fatal_conditions_match_reference_messages():
+    hb = _hb()
+    x, y, cov, doc = load_regression_linear()
+    mt = _mt_from_dosage(x, pheno=y, Cov1=cov[:, 0], Cov2=cov[:, 1], allmiss=np.full(8, np.nan))
+    with pytest.raises(hb.FatalError, match="degrees of freedom"):
+        hb.linear_regression_rows(mt.pheno, mt.GT.n_alt_alleles(),
+                                  [1.0, mt.Cov1, mt.Cov2, mt.Cov1 * mt.Cov1, mt.Cov2 * mt.Cov2, mt.Cov1 * mt.Cov2])
+    with pytest.raises(hb.FatalError, match="No complete samples"):
+        hb.linear_regression_rows(mt.allmiss, mt.GT.n_alt_alleles(), [1.0])
