@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the `linear_regression_rows` hot path: genotypes/sec on synthetic Balding-Nichols genotypes.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm's CPU restatement
+
+Workload (BASELINE.json configs[1], "C2"): 400,000 samples x 1,000,000 variants, 1 phenotype, 10 covariates
+(intercept + 9 PCs).  One step = one pass of the hot path over the whole resident batch (sweep + per-variant
+epilogue).  N > 1: variants shard across ranks (weak scaling: every rank holds its own 1M-variant range of one
+global seeded matrix); rank 0's basis is broadcast over NCCL and result rows are all-gathered each step.
+
+Prints ONE JSON line on rank 0 (see README / DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SAMPLES, N_VARIANTS, N_COV, N_PHENO = 400_000, 1_000_000, 10, 1
+WORKLOAD = "C2: BN(3 pops) 400k samples x 1M variants, P=1, K=10 (intercept + 9 PCs)"
+METRIC = "genotypes/sec (variants x samples) for linear_regression_rows"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "fp64", "tc"])
+    ap.add_argument("--samples", type=int, default=N_SAMPLES)
+    ap.add_argument("--variants", type=int, default=N_VARIANTS, help="variants per GPU")
+    ap.add_argument("--missing-rate", type=float, default=0.0)
+    ap.add_argument("--e2e-variants", type=int, default=32768)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def phenotypes_and_covariates(n, seed=1):
+    rng = np.random.Generator(np.random.Philox(key=[seed, 0x9E]))
+    cov = np.column_stack([np.ones(n)] + [rng.standard_normal(n) for _ in range(N_COV - 1)])
+    y = rng.standard_normal((n, N_PHENO))
+    return y, cov
+
+
+def algorithmic_bytes(M, N, G, K, P, n):
+    """packed genotypes + result rows + basis read once."""
+    return M * ((N + 3) // 4) + M * G * (4 + 8 + 5 * 8 * P) + G * 8 * (n * K + n * P + K * P + P)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.samples = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ts, line in self.samples:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# =================================================================================================
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import hail_b200 as hb
+    from hail_b200 import _lib, bn
+    from hail_b200.statgen import GroupBasis, STAT_FIELDS
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, M = a.samples, a.variants
+    seed = 0
+
+    # ---- synthetic input, generated directly in HBM (not timed) --------------------------------
+    first = rank * M
+    pop, th, _ = bn.bn_parameters(3, N, M, missing_rate=a.missing_rate, seed=seed, first_variant=first)
+    gt = bn.bn_fill(hb.PackedGenotypes.empty(M, N, dev), pop, th, seed=seed, first_variant=first)
+    del th
+    y, cov = phenotypes_and_covariates(N)
+    ctx = _lib.context(local)
+    lib = ctx.lib
+
+    # ---- basis: host QR on rank 0, NCCL broadcast (the analogue of sc.broadcast, LR:74-78) ---------
+    def make_basis_tensors():
+        if rank == 0:
+            b = GroupBasis(y, cov, np.arange(N))
+            meta = torch.tensor([b.n, b.K, b.P, int(b.has_intercept)], dtype=torch.int64, device=dev)
+            t = [torch.from_numpy(x).to(dev) for x in (b.complete_idx, b.q_cols, b.y_res, b.qty, b.yyp)]
+        else:
+            meta = torch.zeros(4, dtype=torch.int64, device=dev)
+            t = None
+        if world > 1:
+            dist.broadcast(meta, 0)
+            n_, K_, P_, hi_ = [int(v) for v in meta.tolist()]
+            if rank != 0:
+                t = [torch.empty(n_, dtype=torch.int32, device=dev),
+                     torch.empty((K_ - hi_, n_), dtype=torch.float64, device=dev),
+                     torch.empty((P_, n_), dtype=torch.float64, device=dev),
+                     torch.empty((K_, P_), dtype=torch.float64, device=dev),
+                     torch.empty(P_, dtype=torch.float64, device=dev)]
+            for x in t:
+                dist.broadcast(x, 0)
+        return [int(v) for v in meta.tolist()], t
+
+    def push_basis(meta, t):
+        n_, K_, P_, hi_ = meta
+        ctx.check(lib.lrr_clear_groups(ctx.handle))
+        ctx.check(lib.lrr_add_group(ctx.handle, N, n_, K_, P_, hi_, t[0].data_ptr(),
+                                    t[1].data_ptr() if t[1].numel() else None, t[2].data_ptr(), t[3].data_ptr(),
+                                    t[4].data_ptr()))
+        ctx.check(lib.lrr_reserve(ctx.handle, M))
+
+    meta, bt = make_basis_tensors()
+    push_basis(meta, bt)
+    n_kept, K, P, _ = meta
+
+    out = {"n": torch.empty(M, dtype=torch.int32, device=dev), "n_missing": torch.empty(M, dtype=torch.int32, device=dev),
+           "sum_x": torch.empty(M, dtype=torch.float64, device=dev)}
+    for f in STAT_FIELDS:
+        out[f] = torch.empty((M, P), dtype=torch.float64, device=dev)
+    go = (_lib.GroupOut * 1)()
+    for k, v in out.items():
+        setattr(go[0], k, v.data_ptr())
+    go[0].log10_p = None
+    rows = torch.stack([out["sum_x"]] + [out[f][:, 0] for f in STAT_FIELDS], dim=1)  # result row block for the gather
+    gathered = [torch.empty_like(rows) for _ in range(world)] if world > 1 else None
+    kid = _lib.KERNELS[a.kernel]
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ctx.check(lib.lrr_set_timing(ctx.handle, 1))
+    launches0 = None
+    sweep_ms = []
+
+    def step(timed):
+        if world > 1:  # per-step basis broadcast + result gather (tiny next to the sweep)
+            for x in bt:
+                dist.broadcast(x, 0)
+        ctx.check(lib.lrr_run(ctx.handle, gt.data.data_ptr(), M, gt.stride, N, go, 1, kid, stream))
+        if world > 1:
+            torch.stack([out["sum_x"]] + [out[f][:, 0] for f in STAT_FIELDS], dim=1, out=rows)
+            dist.all_gather(gathered, rows)
+        if timed:
+            sweep_ms.append(lib.lrr_last_sweep_ms(ctx.handle))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(a.warmup):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(a.steps):
+        step(True)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    launches = ctx.launch_count - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    kernel_used = ctx.last_kernel
+    ms_per_step = total_ms / a.steps
+    value = world * M * float(n_kept) / (ms_per_step / 1e3)
+
+    # ---- roofline of the dominant (sweep) kernel: algorithmic bytes / its own event-timed duration ----
+    peak, peak_src = measured_peak()
+    abytes = algorithmic_bytes(M, N, 1, K, P, n_kept)
+    sweep = float(np.mean(sweep_ms))
+    achieved = abytes / (sweep / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "kernel": f"{kernel_used} sweep",
+                "kernel_ms": round(sweep, 3), "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src,
+                "frac_of_nominal_8TBps": round(achieved / 8000.0, 4)}
+
+    result = {
+        "metric": METRIC, "value": value, "unit": "genotypes/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 epilogue; sweep " + ("int8 x int8 -> int32 exact (tcgen05)" if kernel_used == "tc" else "f64 FMA"),
+        "data": "synthetic (seeded Balding-Nichols style, generated in HBM)",
+        "config": {"workload": WORKLOAD if (N, M) == (N_SAMPLES, N_VARIANTS) else f"REDUCED {N} samples x {M} variants",
+                   "samples": N, "variants_per_gpu": M, "phenotypes": P, "covariates": K, "missing_rate": a.missing_rate,
+                   "kernel": kernel_used, "parallelism": f"variant-sharded x{world}",
+                   "l2": "inputs larger than L2 (packed genotypes %.1f GB per GPU)" % (gt.nbytes / 1e9)},
+        "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+    }
+
+    # ---- e2e: public API, host buffers, H2D + ingest + sweep + D2H inside the timed region -----------
+    if not a.no_e2e:
+        Me = min(a.e2e_variants, M)
+        bed_stride = (N + 3) // 4
+        d_bed = torch.empty((Me, bed_stride), dtype=torch.uint8, device=dev)
+        ctx.check(lib.lrr_unpack_bed(ctx.handle, gt.data.data_ptr(), gt.stride, Me, N, d_bed.data_ptr(), bed_stride, stream))
+        h_bed = torch.empty((Me, bed_stride), dtype=torch.uint8).pin_memory()
+        h_bed.copy_(d_bed)
+        del d_bed
+        torch.cuda.synchronize(dev)
+        col = {"y": y[:, 0], **{f"c{i}": cov[:, i] for i in range(1, N_COV)}}
+
+        def e2e_step():
+            g = hb.PackedGenotypes.from_bed_rows(h_bed, N, dev, chunk_variants=4096)   # H2D + ingest
+            mt = hb.MatrixTable(g, cols=col)
+            ht = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(),
+                                           covariates=[1.0] + [mt[f"c{i}"] for i in range(1, N_COV)], _kernel=a.kernel)
+            return ht                                                                 # D2H inside (numpy fields)
+
+        e2e_step()
+        barrier()
+        t_e = time.time()
+        reps = max(2, min(a.steps, 3))
+        for _ in range(reps):
+            ht = e2e_step()
+        barrier()
+        dt = (time.time() - t_e) / reps
+        tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dt = float(tmax.item())
+        d2h = Me * (4 + 4 + 8 + 5 * 8 * P)
+        result["e2e"] = {"value": world * Me * float(n_kept) / dt, "unit": "genotypes/s",
+                         "h2d_bytes_per_step": int(Me * bed_stride + 8 * n_kept * (K + P)), "d2h_bytes_per_step": int(d2h),
+                         "sample": f"{Me} variants x {N} samples per GPU per step from pinned host .bed bytes via "
+                                   "PackedGenotypes.from_bed_rows + linear_regression_rows (host QR prologue included)"}
+        del h_bed
+
+    # ---- CPU baseline: the oracle's C restatement of the reference loop, rank 0, bounded sample -------
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        result["cpu_baseline"] = cpu_baseline(a, gt, y, cov, ctx, dev)
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(a, gt, y, cov, ctx, dev, sample_variants=None):
+    """Time oracle/linreg_oracle.c (kind "port") on the host cores over a bounded sample of the same workload."""
+    import torch
+
+    from oracle import c_oracle
+
+    threads = os.cpu_count() or 1
+    N = gt.n_samples
+    # ~0.03e9 genotypes/s/thread measured in the authoring container -> size the sample for ~cpu_seconds
+    Ms = sample_variants or int(max(64, min(gt.n_variants, a.cpu_seconds * 0.03e9 * threads / N)))
+    Ms = (Ms // 16) * 16
+    bed_stride = (N + 3) // 4
+    d_bed = torch.empty((Ms, bed_stride), dtype=torch.uint8, device=dev)
+    ctx.check(ctx.lib.lrr_unpack_bed(ctx.handle, gt.data.data_ptr(), gt.stride, Ms, N, d_bed.data_ptr(), bed_stride, None))
+    torch.cuda.synchronize(dev)
+    rows = d_bed.cpu().numpy()
+    del d_bed
+    prep = c_oracle.prepare(y, cov)
+    c_oracle.run_prepared(rows[:threads * 16], prep, n_threads=threads)  # warm
+    t0 = time.time()
+    c_oracle.run_prepared(rows, prep, n_threads=threads)
+    dt = time.time() - t0
+    return {"value": Ms * float(prep["n"]) / dt, "unit": "genotypes/s", "cores": threads, "kind": "port",
+            "sample": f"{Ms} variants x {N} samples of the same workload, {dt:.1f} s, OpenMP static over 16-row blocks"}
+
+
+# =================================================================================================
+def run_reference(a):
+    """The reference arm: the reference algorithm's CPU restatement (oracle C port -- the JVM/Spark reference
+    cannot be built or installed in this image: no java, no network), all host threads, bounded sample/step."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import bed as obed
+    from oracle import c_oracle
+    from tests.bn_mirror import bn_fill_numpy  # CPU mirror of the seeded generator (no GPU needed on this arm)
+    from hail_b200 import bn
+
+    c_oracle.build()
+    threads = os.cpu_count() or 1
+    N = a.samples
+    per_step = max(64, int(a.cpu_seconds / max(a.steps + a.warmup, 1) * 0.03e9 * threads / N) // 16 * 16)
+    per_step = min(per_step, a.variants)
+    pop, th, _ = bn.bn_parameters(3, N, per_step, missing_rate=a.missing_rate, seed=0)
+    dos = bn_fill_numpy(th, pop, N, seed=0)
+    rows = obed.encode_rows(np.where(dos < 0, np.nan, dos.astype(np.float64)))
+    y, cov = phenotypes_and_covariates(N)
+    prep = c_oracle.prepare(y, cov)
+    for _ in range(a.warmup):
+        c_oracle.run_prepared(rows, prep, n_threads=threads)
+    t0 = time.time()
+    for _ in range(a.steps):
+        c_oracle.run_prepared(rows, prep, n_threads=threads)
+    dt = (time.time() - t0) / a.steps
+    value = per_step * float(prep["n"]) / dt
+    sample = f"{per_step} variants x {N} samples per step (bounded sample of the workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "genotypes/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (same seeded generator, CPU mirror)",
+        "config": {"workload": WORKLOAD if (N, a.variants) == (N_SAMPLES, N_VARIANTS) else f"REDUCED {N} samples x {a.variants} variants",
+                   "samples": N, "phenotypes": N_PHENO, "covariates": N_COV, "missing_rate": a.missing_rate},
+        "cpu_baseline": {"value": value, "unit": "genotypes/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "genotypes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "Hail itself (JVM + Spark) cannot be installed here; this is oracle/linreg_oracle.c, the C restatement "
+                "of LinearRegression.scala:95-193, OpenMP over 16-row blocks on all host threads",
+    }))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

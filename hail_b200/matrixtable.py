@@ -123,8 +123,9 @@ class MatrixTable:
             if not isinstance(v, dict) and len(v) != genotypes.n_variants:
                 raise ValueError(f"row field {k!r} has {len(v)} values for {genotypes.n_variants} rows")
         for k, v in self._cols.items():
-            if len(v) != len(self.col_index):
-                raise ValueError(f"col field {k!r} has {len(v)} values for {len(self.col_index)} columns")
+            for kk, vv in (v.items() if isinstance(v, dict) else [(k, v)]):
+                if len(vv) != len(self.col_index):
+                    raise ValueError(f"col field {kk!r} has {len(vv)} values for {len(self.col_index)} columns")
 
     # ---- shape -------------------------------------------------------------------------------
     def count_rows(self): return self.genotypes.n_variants

@@ -49,18 +49,26 @@ def _dp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
 
-def linreg_group_bed(bed_rows, n_samples, ys, cov, block_size=16, n_threads=0):
-    """LR:46-195 over PLINK-coded rows `bed_rows` uint8 [M, stride]; ys [N,P], cov [N,K] (NaN = missing)."""
-    bed_rows = np.ascontiguousarray(bed_rows, dtype=np.uint8)
-    M, stride = bed_rows.shape
-    assert stride >= (n_samples + 3) // 4
+def prepare(ys, cov):
+    """Driver prologue (RU:88-128, LR:47-78) once; reuse across calls of `run_prepared`."""
     y, c, idx = O.complete_samples(ys, cov)
     n, K, d, Qt, Qty, yyp = O.prologue(y, c)
     P = y.shape[1]
-    y = np.ascontiguousarray(y)
-    Qt = np.ascontiguousarray(Qt if K > 0 else np.zeros((1, n)))
-    Qty = np.ascontiguousarray(Qty if K > 0 else np.zeros((1, P)))
-    idx32 = np.ascontiguousarray(idx, dtype=np.int32)
+    return {
+        "n": n, "K": K, "P": P, "d": d,
+        "y": np.ascontiguousarray(y),
+        "Qt": np.ascontiguousarray(Qt if K > 0 else np.zeros((1, n))),
+        "Qty": np.ascontiguousarray(Qty if K > 0 else np.zeros((1, P))),
+        "yyp": np.ascontiguousarray(yyp),
+        "idx": np.ascontiguousarray(idx, dtype=np.int32),
+    }
+
+
+def run_prepared(bed_rows, prep, block_size=16, n_threads=0):
+    """The per-partition loop (LR:95-193) over PLINK-coded rows uint8 [M, stride]."""
+    bed_rows = np.ascontiguousarray(bed_rows, dtype=np.uint8)
+    M, stride = bed_rows.shape
+    n, K, P = prep["n"], prep["K"], prep["P"]
     out = {
         "n": np.full(M, n, dtype=np.int32),
         "sum_x": np.empty(M),
@@ -71,13 +79,20 @@ def linreg_group_bed(bed_rows, n_samples, ys, cov, block_size=16, n_threads=0):
         "p_value": np.empty((M, P)),
     }
     lib().lrr_oracle_bed(
-        bed_rows.ctypes.data, M, stride, idx32.ctypes.data, n, _dp(Qt), _dp(y), _dp(Qty), _dp(np.ascontiguousarray(yyp)),
-        K, P, block_size, n_threads,
+        bed_rows.ctypes.data, M, stride, prep["idx"].ctypes.data, n, _dp(prep["Qt"]), _dp(prep["y"]), _dp(prep["Qty"]),
+        _dp(prep["yyp"]), K, P, block_size, n_threads,
         _dp(out["sum_x"]), _dp(out["y_transpose_x"]), _dp(out["beta"]), _dp(out["standard_error"]),
         _dp(out["t_stat"]), _dp(out["p_value"]),
     )
-    out["_d"] = d
+    out["_d"] = prep["d"]
     return out
+
+
+def linreg_group_bed(bed_rows, n_samples, ys, cov, block_size=16, n_threads=0):
+    """LR:46-195 over PLINK-coded rows `bed_rows` uint8 [M, stride]; ys [N,P], cov [N,K] (NaN = missing)."""
+    bed_rows = np.ascontiguousarray(bed_rows, dtype=np.uint8)
+    assert bed_rows.shape[1] >= (n_samples + 3) // 4
+    return run_prepared(bed_rows, prepare(ys, cov), block_size, n_threads)
 
 
 def max_threads():
