@@ -197,7 +197,7 @@ def run_ours(a):
         if world > 1:  # per-step basis broadcast + result gather (tiny next to the sweep)
             for x in bt:
                 dist.broadcast(x, 0)
-        ctx.check(lib.lrr_run(ctx.handle, gt.data.data_ptr(), M, gt.stride, N, go, 1, kid, stream))
+        ctx.check(lib.lrr_run(ctx.handle, gt.data.data_ptr(), gt.flags_ptr(), M, gt.stride, N, go, 1, kid, stream))
         if world > 1:
             torch.stack([out["sum_x"]] + [out[f][:, 0] for f in STAT_FIELDS], dim=1, out=rows)
             dist.all_gather(gathered, rows)

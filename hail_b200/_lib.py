@@ -38,24 +38,25 @@ SIGNATURES = {
     "lrr_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "lrr_packed_stride": (ctypes.c_int64, [ctypes.c_int64]),
     "lrr_pack_bed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
-                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "lrr_pack_dosage_i8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
-                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "lrr_unpack_dosage_i8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "lrr_unpack_bed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "lrr_bn_fill": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                    ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int64,
-                                   ctypes.c_void_p]),
+                                   ctypes.c_void_p, ctypes.c_void_p]),
     "lrr_clear_groups": (ctypes.c_int, [ctypes.c_void_p]),
     "lrr_add_group": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                      ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p]),
     "lrr_num_groups": (ctypes.c_int, [ctypes.c_void_p]),
     "lrr_reserve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
-    "lrr_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
-                               ctypes.POINTER(GroupOut), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
+    "lrr_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                               ctypes.c_int64, ctypes.POINTER(GroupOut), ctypes.c_int32, ctypes.c_int32,
+                               ctypes.c_void_p]),
     "lrr_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "lrr_last_kernel": (ctypes.c_int, [ctypes.c_void_p]),
     "lrr_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

@@ -66,6 +66,7 @@ def bn_fill(out: PackedGenotypes, pop, thresholds, seed=0, first_variant=0, chun
             d_th = torch.from_numpy(np.ascontiguousarray(thresholds[lo:hi]).view(np.int32)).to(dev)
             ctx.check(ctx.lib.lrr_bn_fill(ctx.handle, d_th.data_ptr(), n_pops, d_pop.data_ptr(), hi - lo,
                                           first_variant + lo, N, seed, out.data[lo:hi].data_ptr(), out.stride,
+                                          out.row_flags[lo:hi].data_ptr() if out.row_flags is not None else None,
                                           torch.cuda.current_stream(dev).cuda_stream))
     return out
 

@@ -150,20 +150,20 @@ static int check_packed(Ctx* c, int64_t n_samples, int64_t packed_stride) {
 }
 
 int lrr_pack_bed(lrr_ctx* ctx, const uint8_t* d_bed, int64_t n_variants, int64_t bed_stride, int64_t n_samples,
-                 uint8_t* d_packed, int64_t packed_stride, void* stream) {
+                 uint8_t* d_packed, int64_t packed_stride, uint8_t* d_row_flags, void* stream) {
   CTX_PROLOGUE;
   if (n_variants < 0 || n_samples <= 0 || bed_stride < (n_samples + 3) / 4)
     return fail(c, LRR_EINVAL, "lrr_pack_bed: bed_stride must be >= ceil(n_samples/4) (LoadPlink.scala:240-251)");
   if (int r = check_packed(c, n_samples, packed_stride)) return r;
-  return launch_pack_bed(c, d_bed, n_variants, bed_stride, n_samples, d_packed, packed_stride, st);
+  return launch_pack_bed(c, d_bed, n_variants, bed_stride, n_samples, d_packed, packed_stride, d_row_flags, st);
 }
 
 int lrr_pack_dosage_i8(lrr_ctx* ctx, const int8_t* d_dosage, int64_t n_variants, int64_t n_samples, uint8_t* d_packed,
-                       int64_t packed_stride, void* stream) {
+                       int64_t packed_stride, uint8_t* d_row_flags, void* stream) {
   CTX_PROLOGUE;
   if (n_variants < 0 || n_samples <= 0) return fail(c, LRR_EINVAL, "lrr_pack_dosage_i8: bad shape");
   if (int r = check_packed(c, n_samples, packed_stride)) return r;
-  return launch_pack_i8(c, d_dosage, n_variants, n_samples, d_packed, packed_stride, st);
+  return launch_pack_i8(c, d_dosage, n_variants, n_samples, d_packed, packed_stride, d_row_flags, st);
 }
 
 int lrr_unpack_dosage_i8(lrr_ctx* ctx, const uint8_t* d_packed, int64_t packed_stride, int64_t n_variants,
@@ -185,12 +185,12 @@ int lrr_unpack_bed(lrr_ctx* ctx, const uint8_t* d_packed, int64_t packed_stride,
 
 int lrr_bn_fill(lrr_ctx* ctx, const uint32_t* d_thresholds, int n_pops, const uint8_t* d_pop, int64_t n_variants,
                 int64_t first_variant, int64_t n_samples, uint64_t seed, uint8_t* d_packed, int64_t packed_stride,
-                void* stream) {
+                uint8_t* d_row_flags, void* stream) {
   CTX_PROLOGUE;
   if (n_variants < 0 || n_samples <= 0 || n_pops <= 0 || n_pops > 255) return fail(c, LRR_EINVAL, "lrr_bn_fill: bad shape");
   if (int r = check_packed(c, n_samples, packed_stride)) return r;
   return launch_bn_fill(c, d_thresholds, n_pops, d_pop, n_variants, first_variant, n_samples, seed, d_packed,
-                        packed_stride, st);
+                        packed_stride, d_row_flags, st);
 }
 
 int lrr_clear_groups(lrr_ctx* ctx) {
@@ -200,6 +200,7 @@ int lrr_clear_groups(lrr_ctx* ctx) {
   cudaDeviceSynchronize();
   for (auto& g : c->groups) free_group(g);
   c->groups.clear();
+  tc_invalidate(c);
   free_workspace(c);
   c->n_samples_total = 0;
   return LRR_OK;
@@ -281,6 +282,7 @@ int lrr_add_group(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, i
 #undef TRY
   cleanup();
   c->groups.push_back(g);
+  tc_invalidate(c);
   c->n_samples_total = n_samples_total;
   c->dots_offset.clear();  // workspace layout depends on the group list
   return LRR_OK;
@@ -295,8 +297,8 @@ int lrr_reserve(lrr_ctx* ctx, int64_t max_variants) {
   return ensure_workspace(c, max_variants);
 }
 
-int lrr_run(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int64_t packed_stride, int64_t n_samples_total,
-            const lrr_group_out* outs, int32_t n_outs, int32_t kernel, void* stream) {
+int lrr_run(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
+            int64_t n_samples_total, const lrr_group_out* outs, int32_t n_outs, int32_t kernel, void* stream) {
   CTX_PROLOGUE;
   if (c->groups.empty()) return fail(c, LRR_ESTATE, "lrr_run: no groups (call lrr_add_group)");
   if (n_outs != (int32_t)c->groups.size() || !outs) return fail(c, LRR_EINVAL, "lrr_run: need one lrr_group_out per group");
@@ -316,10 +318,12 @@ int lrr_run(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int64_t p
     LRR_CUDA(c, cudaEventRecord(c->ev0, st));
   }
   int k = kernel;
-  if (k == LRR_KERNEL_AUTO) k = tc_supported(c) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
+  const bool may_miss = true;  // the column budget is checked for the general (two-plane) mode
+  if (k == LRR_KERNEL_AUTO) k = tc_supported(c, may_miss) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
   if (k == LRR_KERNEL_TC) {
-    if (!tc_supported(c)) return fail(c, LRR_EINVAL, "lrr_run: tensor-core kernel does not support this configuration");
-    if (int r = launch_tc_sweep(c, d_packed, n_variants, packed_stride, st)) return r;
+    if (!tc_supported(c, may_miss))
+      return fail(c, LRR_EINVAL, "lrr_run: tensor-core kernel does not support this configuration: " + c->err);
+    if (int r = launch_tc_sweep(c, d_packed, d_row_flags, n_variants, packed_stride, st)) return r;
   } else if (k == LRR_KERNEL_FP64) {
     if (int r = launch_fp64_sweep(c, d_packed, n_variants, packed_stride, st)) return r;
   } else {

@@ -66,15 +66,16 @@ int cuda_fail(Ctx* c, cudaError_t e, const char* what);
   } while (0)
 
 // kernels / stages implemented in the other translation units
-int launch_pack_bed(Ctx*, const uint8_t*, int64_t, int64_t, int64_t, uint8_t*, int64_t, cudaStream_t);
-int launch_pack_i8(Ctx*, const int8_t*, int64_t, int64_t, uint8_t*, int64_t, cudaStream_t);
+int launch_pack_bed(Ctx*, const uint8_t*, int64_t, int64_t, int64_t, uint8_t*, int64_t, uint8_t*, cudaStream_t);
+int launch_pack_i8(Ctx*, const int8_t*, int64_t, int64_t, uint8_t*, int64_t, uint8_t*, cudaStream_t);
 int launch_unpack_i8(Ctx*, const uint8_t*, int64_t, int64_t, int64_t, int8_t*, cudaStream_t);
 int launch_unpack_bed(Ctx*, const uint8_t*, int64_t, int64_t, int64_t, uint8_t*, int64_t, cudaStream_t);
 int launch_bn_fill(Ctx*, const uint32_t*, int, const uint8_t*, int64_t, int64_t, int64_t, uint64_t, uint8_t*, int64_t,
-                   cudaStream_t);
+                   uint8_t*, cudaStream_t);
 int launch_fp64_sweep(Ctx*, const uint8_t* d_packed, int64_t M, int64_t stride, cudaStream_t);
-int launch_tc_sweep(Ctx*, const uint8_t* d_packed, int64_t M, int64_t stride, cudaStream_t);
-bool tc_supported(const Ctx*);
+int launch_tc_sweep(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, cudaStream_t);
+bool tc_supported(Ctx*, bool may_have_missing);
+void tc_invalidate(Ctx*);
 void tc_release(Ctx*);
 int launch_stats_epilogue(Ctx*, int g, int64_t M, const lrr_group_out& out, cudaStream_t);
 int launch_student_t(Ctx*, const double*, int64_t, double, double*, double*, cudaStream_t);

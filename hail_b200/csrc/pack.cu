@@ -28,8 +28,11 @@ __device__ __forceinline__ uint32_t valid_mask_store_order(int valid) {
   return m;
 }
 
+// 1 where a store word holds at least one missing call (code 3)
+__device__ __forceinline__ bool word_has_missing(uint32_t w) { return (w & (w >> 1) & 0x55555555u) != 0u; }
+
 __global__ void pack_bed_kernel(const uint8_t* __restrict__ bed, int64_t M, int64_t bed_stride, int64_t N,
-                                uint8_t* __restrict__ packed, int64_t packed_stride) {
+                                uint8_t* __restrict__ packed, int64_t packed_stride, uint8_t* __restrict__ flags) {
   const int64_t words_per_row = packed_stride / 4;
   const int64_t total = M * words_per_row;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -54,6 +57,7 @@ __global__ void pack_bed_kernel(const uint8_t* __restrict__ bed, int64_t M, int6
       const int64_t left = N - s0;
       out = x & valid_mask_store_order(left >= 16 ? 16 : (int)left);
     }
+    if (flags && word_has_missing(out)) flags[v] = 1;  // benign race: every writer stores 1
     reinterpret_cast<uint32_t*>(packed + v * packed_stride)[w] = out;
   }
 }
@@ -87,7 +91,7 @@ __global__ void unpack_bed_kernel(const uint8_t* __restrict__ packed, int64_t pa
 }
 
 __global__ void pack_i8_kernel(const int8_t* __restrict__ dos, int64_t M, int64_t N, uint8_t* __restrict__ packed,
-                               int64_t packed_stride) {
+                               int64_t packed_stride, uint8_t* __restrict__ flags) {
   const int64_t words_per_row = packed_stride / 4;
   const int64_t total = M * words_per_row;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -105,6 +109,7 @@ __global__ void pack_i8_kernel(const int8_t* __restrict__ dos, int64_t M, int64_
         out |= code << sample_shift(j);
       }
     }
+    if (flags && word_has_missing(out)) flags[v] = 1;
     reinterpret_cast<uint32_t*>(packed + v * packed_stride)[w] = out;
   }
 }
@@ -134,7 +139,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
 //   u < t0 -> missing; u < t1 -> 0 alt; u < t2 -> 1 alt; else 2 alt      (u = 16 random bits)
 __global__ void bn_fill_kernel(const uint32_t* __restrict__ thresh, int n_pops, const uint8_t* __restrict__ pop,
                                int64_t M, int64_t first_variant, int64_t N, uint64_t seed,
-                               uint8_t* __restrict__ packed, int64_t packed_stride) {
+                               uint8_t* __restrict__ packed, int64_t packed_stride, uint8_t* __restrict__ flags) {
   const int64_t words_per_row = packed_stride / 4;
   const int64_t total = M * words_per_row;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -162,6 +167,7 @@ __global__ void bn_fill_kernel(const uint32_t* __restrict__ thresh, int n_pops, 
         }
       }
     }
+    if (flags && word_has_missing(out)) flags[r] = 1;
     reinterpret_cast<uint32_t*>(packed + r * packed_stride)[w] = out;
   }
 }
@@ -175,19 +181,21 @@ static int grid_for(const Ctx* c, int64_t total, int block) {
 }
 
 int launch_pack_bed(Ctx* c, const uint8_t* bed, int64_t M, int64_t bed_stride, int64_t N, uint8_t* packed,
-                    int64_t packed_stride, cudaStream_t st) {
+                    int64_t packed_stride, uint8_t* flags, cudaStream_t st) {
   if (M == 0) return LRR_OK;
+  if (flags) LRR_CUDA(c, cudaMemsetAsync(flags, 0, (size_t)M, st));
   pack_bed_kernel<<<grid_for(c, M * (packed_stride / 4), 256), 256, 0, st>>>(bed, M, bed_stride, N, packed,
-                                                                               packed_stride);
+                                                                               packed_stride, flags);
   c->launches++;
   LRR_CUDA(c, cudaGetLastError());
   return LRR_OK;
 }
 
 int launch_pack_i8(Ctx* c, const int8_t* dos, int64_t M, int64_t N, uint8_t* packed, int64_t packed_stride,
-                   cudaStream_t st) {
+                   uint8_t* flags, cudaStream_t st) {
   if (M == 0) return LRR_OK;
-  pack_i8_kernel<<<grid_for(c, M * (packed_stride / 4), 256), 256, 0, st>>>(dos, M, N, packed, packed_stride);
+  if (flags) LRR_CUDA(c, cudaMemsetAsync(flags, 0, (size_t)M, st));
+  pack_i8_kernel<<<grid_for(c, M * (packed_stride / 4), 256), 256, 0, st>>>(dos, M, N, packed, packed_stride, flags);
   c->launches++;
   LRR_CUDA(c, cudaGetLastError());
   return LRR_OK;
@@ -213,10 +221,11 @@ int launch_unpack_bed(Ctx* c, const uint8_t* packed, int64_t packed_stride, int6
 }
 
 int launch_bn_fill(Ctx* c, const uint32_t* thresh, int n_pops, const uint8_t* pop, int64_t M, int64_t first_variant,
-                   int64_t N, uint64_t seed, uint8_t* packed, int64_t packed_stride, cudaStream_t st) {
+                   int64_t N, uint64_t seed, uint8_t* packed, int64_t packed_stride, uint8_t* flags, cudaStream_t st) {
   if (M == 0) return LRR_OK;
+  if (flags) LRR_CUDA(c, cudaMemsetAsync(flags, 0, (size_t)M, st));
   bn_fill_kernel<<<grid_for(c, M * (packed_stride / 4), 256), 256, 0, st>>>(thresh, n_pops, pop, M, first_variant, N,
-                                                                              seed, packed, packed_stride);
+                                                                              seed, packed, packed_stride, flags);
   c->launches++;
   LRR_CUDA(c, cudaGetLastError());
   return LRR_OK;

@@ -1,10 +1,674 @@
-// Kernel 2 (tcgen05 int8-sliced exact-integer sweep) -- placeholder until the tensor-core path lands.
+// Kernel 2: the throughput sweep on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// Formulation.  For a tile of 128 variants the projections  D[v, c] = sum_j x[v, j] * B[j, c]  against the
+// basis [Q' | Y_res] (LinearRegression.scala:139-146 restated: qtx = Qt * X, xyp = y_res^T X) are one skinny
+// GEMM whose A operand is the genotype tile and whose K dimension is the sample axis.  A is EXACT in 8 bits
+// (call codes 0..3), so only B needs precision: every basis column is stored as S balanced base-256 digits
+// (int8 planes, fixed point relative to the column's max), the MMA accumulates int8 x uint8 products in INT32
+// -- exactly, no rounding and no dependence on summation order -- and the per-variant epilogue recombines the
+// S exact integers in float64.  With S = 6 the only error is the 2^-47 quantisation of B.
+//
+// Dataflow per CTA (persistent over variant tiles), one CTA per SM:
+//   TMA warp      cp.async.bulk.tensor: packed genotype tile [128 variants x 512 samples] (16 KB, 128B swizzle)
+//                 + the matching basis panels [ncols x 512 samples] int8 -> a ring of shared-memory stages
+//   unpack warps  (8) LDS.128 of the thread's own variant row, 2-bit -> uint8 with shift/mask, exact popcount
+//                 of hom-alt calls, tcgen05.st of the uint8 row into a TMEM ring (A operand lives in TMEM)
+//   MMA warp      one thread issues tcgen05.mma.kind::i8 (M=128, N=ncols, K=32) with A from TMEM, B from the
+//                 swizzled shared-memory panels, D (int32) in TMEM; tcgen05.commit releases ring slots / stages
+//   epilogue      (unpack warps 0-3) tcgen05.ld the int32 accumulators, recombine digits, mean-impute correction
+//                 from the missing-indicator plane, write counts + float64 dot products for the stats epilogue
+//
+// Missing calls (RegressionUtils.scala:16-58 mean imputation): code 3.  Plane "c" carries the raw code
+// (0..3), plane "m" the indicator [code == 3]; sum_j B (x0 + mean * m) = (Dc - 3 Dm) + mean * Dm.  Tiles whose
+// rows carry no missing call (row_flags from ingest) skip plane m entirely.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace lrr {
-bool tc_supported(const Ctx*) { return false; }
-void tc_release(Ctx*) {}
-int launch_tc_sweep(Ctx* c, const uint8_t*, int64_t, int64_t, cudaStream_t) {
-  return fail(c, LRR_EINVAL, "tensor-core kernel not built");
+namespace tc {
+
+constexpr int TILE_M = 128;            // variants per tile == TMEM lanes
+constexpr int CHUNK = 512;             // samples per shared-memory stage (128 packed bytes per row)
+constexpr int SLOT = 128;              // samples per TMEM A slot (32 columns of 4 x uint8)
+constexpr int SLOTS = CHUNK / SLOT;    // 4
+constexpr int UNPACK_WARPS = 8;
+constexpr int WARP_TMA = 8, WARP_MMA = 9;
+constexpr int THREADS = 10 * 32;
+constexpr int GENO_BYTES = TILE_M * 128;   // 16 KB
+constexpr int MAX_GROUPS = 8;
+constexpr int N_SLICES = 6;            // digits per basis column (48-bit fixed point)
+// TMEM column map (512 columns x 128 lanes x 32 bit)
+constexpr int TM_DC = 0;               // accumulators, plane c: columns [0, ncols)
+constexpr int TM_DM = 128;             // accumulators, plane m (two-plane mode needs ncols <= 128)
+constexpr int TM_AC = 256;             // A ring, plane c: 4 slots x 32 columns
+constexpr int TM_AM = 384;             // A ring, plane m
+
+struct GroupMeta {
+  int col_off;        // first digit column of this group in B
+  int C;              // dot-product columns (Kd + P)
+  int n;              // complete samples
+  int32_t* counts;    // [M][4]
+  double* dots;       // [M][C]
+  const double* colscale;   // [C]
+  const uint32_t* mask;     // [ns_pad/16], low bit of each kept field
+};
+
+struct Params {
+  int64_t M;
+  int n_tiles;
+  int n_chunks;
+  int ncols;          // padded to 16
+  int n_stages;
+  int n_groups;
+  int two_plane_ok;   // ncols <= 128
+  const uint8_t* row_flags;  // nullable
+  GroupMeta g[MAX_GROUPS];
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]     (kind::i8, M=128, K=32)
+__device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);       // start address
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D = s32, A = u8 (K-major, from TMEM), B = s8 (K-major), M = 128, N = ncols
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  uint32_t d = 0;
+  d |= 2u << 4;                   // c_format = S32
+  d |= 0u << 7;                   // a_format = unsigned 8-bit
+  d |= 1u << 10;                  // b_format = signed 8-bit
+  d |= (uint32_t)(n >> 3) << 17;  // N
+  d |= (uint32_t)(TILE_M >> 4) << 24;  // M
+  return d;
+}
+
+struct Barriers {
+  uint64_t full[4];      // stage filled by TMA
+  uint64_t empty[4];     // stage drained (8 unpack warps + MMA commit)
+  uint64_t a_full[SLOTS];   // A ring slot written (4 quarter-warps)
+  uint64_t a_empty[SLOTS];  // A ring slot consumed (MMA commit)
+  uint64_t d_full;       // accumulators complete (MMA commit)
+  uint64_t d_empty;      // accumulators read out (4 epilogue warps)
+  uint32_t tmem_base;
+  uint32_t pad;
+  int32_t n2_xchg[MAX_GROUPS][TILE_M];  // hom-alt popcounts of the h=1 half, handed to the epilogue warps
+};
+
+__device__ __forceinline__ bool tile_has_missing(const Params& p, int tile) {
+  if (!p.row_flags) return true;
+  const int64_t r0 = (int64_t)tile * TILE_M;
+  uint32_t any = 0;
+  if (r0 + TILE_M <= p.M && ((reinterpret_cast<uintptr_t>(p.row_flags + r0) & 15) == 0)) {
+    const uint4* f = reinterpret_cast<const uint4*>(p.row_flags + r0);
+#pragma unroll
+    for (int i = 0; i < TILE_M / 16; ++i) {
+      const uint4 v = __ldg(f + i);
+      any |= v.x | v.y | v.z | v.w;
+    }
+  } else {
+    for (int64_t r = r0; r < p.M && r < r0 + TILE_M; ++r) any |= p.row_flags[r];
+  }
+  return any != 0;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_constant__ CUtensorMap b_map, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = GENO_BYTES + SLOTS * p.ncols * 128;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + (size_t)p.n_stages * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], UNPACK_WARPS + 1);
+    }
+    for (int s = 0; s < SLOTS; ++s) {
+      mbar_init(&bars->a_full[s], 4);
+      mbar_init(&bars->a_empty[s], 1);
+    }
+    mbar_init(&bars->d_full, 1);
+    mbar_init(&bars->d_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == WARP_TMA && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&geno_map) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&b_map) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  const int first_tile = blockIdx.x;
+  const int tile_step = gridDim.x;
+
+  if (warp == WARP_TMA) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      uint32_t chunk_g = 0;
+      for (int tile = first_tile; tile < p.n_tiles; tile += tile_step) {
+        for (int ch = 0; ch < p.n_chunks; ++ch, ++chunk_g) {
+          const int st = chunk_g % p.n_stages;
+          const uint32_t it = chunk_g / p.n_stages;
+          mbar_wait(&bars->empty[st], (it & 1) ^ 1);
+          uint8_t* sbase = smem + (size_t)st * stage_bytes;
+          mbar_arrive_expect_tx(&bars->full[st], (uint32_t)stage_bytes);
+          tma_load_2d(&geno_map, &bars->full[st], sbase, ch * 128, tile * TILE_M);
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s)
+            tma_load_2d(&b_map, &bars->full[st], sbase + GENO_BYTES + s * p.ncols * 128, ch * CHUNK + s * SLOT, 0);
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.ncols);
+      uint32_t chunk_g = 0;
+      uint32_t tile_i = 0;
+      for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++tile_i) {
+        const bool two_plane = tile_has_missing(p, tile);
+        mbar_wait(&bars->d_empty, (tile_i & 1) ^ 1);
+        tc_fence_after();
+        for (int ch = 0; ch < p.n_chunks; ++ch, ++chunk_g) {
+          const int st = chunk_g % p.n_stages;
+          const uint32_t it = chunk_g / p.n_stages;
+          mbar_wait(&bars->full[st], it & 1);
+          const uint32_t b_base = smem_u32(smem + (size_t)st * stage_bytes + GENO_BYTES);
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) {
+            mbar_wait(&bars->a_full[s], chunk_g & 1);
+            tc_fence_after();
+            const uint64_t bdesc = make_b_desc(b_base + s * p.ncols * 128);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t acc = (ch | s | j) ? 1u : 0u;
+              mma_i8_ts(tmem + TM_DC, tmem + TM_AC + s * 32 + j * 8, bdesc + (uint64_t)(j * 2), idesc, acc);
+              if (two_plane)
+                mma_i8_ts(tmem + TM_DM, tmem + TM_AM + s * 32 + j * 8, bdesc + (uint64_t)(j * 2), idesc, acc);
+            }
+            tc_commit(&bars->a_empty[s]);
+          }
+          tc_commit(&bars->empty[st]);
+        }
+        tc_commit(&bars->d_full);
+      }
+    }
+  } else {
+    // ============================== unpack + epilogue warps ==============================
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int h = warp >> 2;         // which half of the slots of a chunk this warp produces
+    const int row = q * 32 + lane;   // variant row within the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t chunk_g = 0;
+    uint32_t tile_i = 0;
+    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++tile_i) {
+      const bool two_plane = tile_has_missing(p, tile);
+      int n2[MAX_GROUPS];
+#pragma unroll
+      for (int g = 0; g < MAX_GROUPS; ++g) n2[g] = 0;
+
+      for (int ch = 0; ch < p.n_chunks; ++ch, ++chunk_g) {
+        const int st = chunk_g % p.n_stages;
+        const uint32_t it = chunk_g / p.n_stages;
+        mbar_wait(&bars->full[st], it & 1);
+        const uint8_t* grow = smem + (size_t)st * stage_bytes + row * 128;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int s = h + 2 * k;   // slot index within the chunk (and in the A ring)
+          // packed bytes of samples [128 s, 128 s + 128) of this row: 16-byte chunks 2s and 2s+1 (swizzled)
+          const uint4 w0 = *reinterpret_cast<const uint4*>(grow + (((2 * s) ^ (row & 7)) << 4));
+          const uint4 w1 = *reinterpret_cast<const uint4*>(grow + (((2 * s + 1) ^ (row & 7)) << 4));
+          const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          uint32_t rc[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            rc[4 * i + 0] = w[i] & 0x03030303u;
+            rc[4 * i + 1] = (w[i] >> 2) & 0x03030303u;
+            rc[4 * i + 2] = (w[i] >> 4) & 0x03030303u;
+            rc[4 * i + 3] = (w[i] >> 6) & 0x03030303u;
+          }
+          // exact hom-alt counts per group (code 2 = hi & ~lo), for x.x = n1 + 4 n2
+          const int word0 = ch * (CHUNK / 16) + s * 8;
+#pragma unroll
+          for (int g = 0; g < MAX_GROUPS; ++g) {
+            if (g < p.n_groups) {
+              const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(p.g[g].mask + word0));
+              const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(p.g[g].mask + word0 + 4));
+              const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+              int acc = 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc += __popc((w[i] >> 1) & ~w[i] & mm[i]);
+              n2[g] += acc;
+            }
+          }
+          mbar_wait(&bars->a_empty[s], (chunk_g & 1) ^ 1);
+          tc_fence_after();
+          tmem_st32(tmem + lane_addr + TM_AC + s * 32, rc);
+          if (two_plane) {
+            uint32_t rm[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t mw = w[i] & (w[i] >> 1);   // bit 2f set iff field f is code 3
+              rm[4 * i + 0] = mw & 0x01010101u;
+              rm[4 * i + 1] = (mw >> 2) & 0x01010101u;
+              rm[4 * i + 2] = (mw >> 4) & 0x01010101u;
+              rm[4 * i + 3] = (mw >> 6) & 0x01010101u;
+            }
+            tmem_st32(tmem + lane_addr + TM_AM + s * 32, rm);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->a_full[s]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->empty[st]);
+      }
+
+      // ------------------------------ per-tile epilogue ------------------------------
+      if (h == 1) {
+#pragma unroll
+        for (int g = 0; g < MAX_GROUPS; ++g)
+          if (g < p.n_groups) bars->n2_xchg[g][row] = n2[g];
+      }
+      named_bar_sync(1, UNPACK_WARPS * 32);
+      if (h == 0) {
+        mbar_wait(&bars->d_full, tile_i & 1);
+        tc_fence_after();
+        const int64_t v = (int64_t)tile * TILE_M + row;
+        for (int g = 0; g < p.n_groups; ++g) {
+          const GroupMeta& G = p.g[g];
+          const int n2g = n2[g] + bars->n2_xchg[g][row];
+          // the group's columns: C x N_SLICES digit columns then one "ones" column
+          const int ones_col = G.col_off + G.C * N_SLICES;
+          // read the ones column(s) first
+          uint32_t r16[16];
+          tmem_ld16(tmem + lane_addr + TM_DC + (ones_col & ~15), r16);
+          tmem_wait_ld();
+          int sc = 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i == (ones_col & 15)) sc = (int)r16[i];
+          int nm = 0;
+          if (two_plane) {
+            tmem_ld16(tmem + lane_addr + TM_DM + (ones_col & ~15), r16);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i == (ones_col & 15)) nm = (int)r16[i];
+          }
+          const int S = sc - 3 * nm;          // n1 + 2 n2
+          const int n1 = S - 2 * n2g;
+          const double mean = (double)S / (double)(G.n - nm);
+          if (v < p.M) reinterpret_cast<int4*>(G.counts)[v] = make_int4(n1, n2g, nm, 0);
+          // digit columns, 16 TMEM columns at a time
+          const int c_lo = G.col_off, c_hi = G.col_off + G.C * N_SLICES;
+          long long hi = 0, lo = 0, mhi = 0, mlo = 0;
+          for (int base = c_lo & ~15; base < c_hi; base += 16) {
+            uint32_t dc[16], dm[16];
+            tmem_ld16(tmem + lane_addr + TM_DC + base, dc);
+            if (two_plane) tmem_ld16(tmem + lane_addr + TM_DM + base, dm);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = base + i;
+              if (col >= c_lo && col < c_hi) {
+                const int rel = col - c_lo;
+                const int c = rel / N_SLICES, sl = rel - c * N_SLICES;
+                const long long dv = (long long)(int)dc[i] - (two_plane ? 3ll * (long long)(int)dm[i] : 0ll);
+                const long long mv = two_plane ? (long long)(int)dm[i] : 0ll;
+                if (sl < 3) {
+                  lo += dv * (1ll << (8 * sl));
+                  mlo += mv * (1ll << (8 * sl));
+                } else {
+                  hi += dv * (1ll << (8 * (sl - 3)));
+                  mhi += mv * (1ll << (8 * (sl - 3)));
+                }
+                if (sl == N_SLICES - 1) {
+                  const double scale = G.colscale[c];
+                  double dot = fma((double)hi, 16777216.0, (double)lo) * scale;
+                  if (two_plane && nm > 0) dot += mean * (fma((double)mhi, 16777216.0, (double)mlo) * scale);
+                  if (v < p.M) G.dots[v * G.C + c] = dot;
+                  hi = lo = mhi = mlo = 0;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->d_empty);
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// basis quantisation: float64 column -> N_SLICES balanced base-256 digits (int8), plus the mask "ones" column
+// ------------------------------------------------------------------------------------------------
+__global__ void colmax_kernel(const double* __restrict__ basis, int C, int64_t ns_pad, unsigned long long* colmax_bits) {
+  const int c = blockIdx.y;
+  double m = 0.0;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ns_pad; j += (int64_t)gridDim.x * blockDim.x)
+    m = fmax(m, fabs(basis[(int64_t)c * ns_pad + j]));
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(colmax_bits + c, (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void quantize_kernel(const double* __restrict__ basis, const uint32_t* __restrict__ mask, int C,
+                                int64_t ns_pad, const unsigned long long* __restrict__ colmax_bits, int col_off,
+                                int8_t* __restrict__ bq, double* __restrict__ colscale) {
+  // Imax = 127 * (256^S - 1) / 255 : the largest integer with S balanced digits in [-128, 127]
+  const double imax = 127.0 * ((double)((1ull << (8 * N_SLICES)) - 1ull) / 255.0);
+  const int c = blockIdx.y;  // 0..C-1 data columns, C = ones column
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ns_pad; j += (int64_t)gridDim.x * blockDim.x) {
+    if (c == C) {
+      const uint32_t mw = mask[j >> 4];
+      bq[(int64_t)(col_off + C * N_SLICES) * ns_pad + j] = (int8_t)((mw >> sample_shift((int)(j & 15))) & 1u);
+      continue;
+    }
+    const double cm = __longlong_as_double((long long)colmax_bits[c]);
+    long long I = 0;
+    if (cm > 0.0) I = __double2ll_rn(basis[(int64_t)c * ns_pad + j] / cm * imax);
+#pragma unroll
+    for (int s = 0; s < N_SLICES; ++s) {
+      long long d = ((I + 128) & 255) - 128;  // balanced digit in [-128, 127]
+      bq[(int64_t)(col_off + c * N_SLICES + s) * ns_pad + j] = (int8_t)d;
+      I = (I - d) >> 8;
+    }
+    if (j == 0) colscale[c] = cm > 0.0 ? cm / imax : 0.0;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct State {
+  bool prepared = false;
+  bool usable = false;
+  std::string why;
+  EncodeTiledFn encode = nullptr;
+  int ncols = 0;
+  int n_stages = 0;
+  int smem_bytes = 0;
+  int8_t* d_bq = nullptr;
+  double* d_colscale = nullptr;   // concatenated per group
+  unsigned long long* d_colmax = nullptr;
+  std::vector<int> col_off, scale_off;
+  CUtensorMap b_map;
+  bool attr_set = false;
+};
+
+static State* state(Ctx* c) {
+  if (!c->tc_state) c->tc_state = new State();
+  return static_cast<State*>(c->tc_state);
+}
+
+static void free_prepared(State* s) {
+  cudaFree(s->d_bq);
+  cudaFree(s->d_colscale);
+  cudaFree(s->d_colmax);
+  s->d_bq = nullptr;
+  s->d_colscale = nullptr;
+  s->d_colmax = nullptr;
+  s->prepared = false;
+  s->usable = false;
+}
+
+static int encode_2d(State* s, CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride,
+                     uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = s->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// build the quantised basis for the current group list
+static int prepare(Ctx* c) {
+  State* s = state(c);
+  if (s->prepared) return LRR_OK;
+  free_prepared(s);
+  s->prepared = true;
+  s->usable = false;
+  if (!s->encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      cudaGetLastError();
+      s->why = "cuTensorMapEncodeTiled is not available from the driver";
+      return LRR_OK;
+    }
+    s->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const size_t G = c->groups.size();
+  if (G == 0 || G > (size_t)MAX_GROUPS) {
+    s->why = "tensor-core kernel supports 1..8 groups";
+    return LRR_OK;
+  }
+  int cols = 0, nscale = 0;
+  s->col_off.assign(G, 0);
+  s->scale_off.assign(G, 0);
+  for (size_t g = 0; g < G; ++g) {
+    s->col_off[g] = cols;
+    s->scale_off[g] = nscale;
+    cols += c->groups[g].C * N_SLICES + 1;
+    nscale += c->groups[g].C;
+  }
+  s->ncols = (cols + 15) / 16 * 16;
+  if (s->ncols > 256) {
+    s->why = "more than 256 digit columns (K + P too large for one pass)";
+    return LRR_OK;
+  }
+  const int64_t ns_pad = c->groups[0].ns_pad;
+  LRR_CUDA(c, cudaMalloc(&s->d_bq, (size_t)s->ncols * ns_pad));
+  LRR_CUDA(c, cudaMemset(s->d_bq, 0, (size_t)s->ncols * ns_pad));
+  LRR_CUDA(c, cudaMalloc(&s->d_colscale, sizeof(double) * (size_t)nscale));
+  LRR_CUDA(c, cudaMalloc(&s->d_colmax, sizeof(unsigned long long) * (size_t)nscale));
+  LRR_CUDA(c, cudaMemset(s->d_colmax, 0, sizeof(unsigned long long) * (size_t)nscale));
+  for (size_t g = 0; g < G; ++g) {
+    const Group& gr = c->groups[g];
+    dim3 grid1((unsigned)std::min<int64_t>((ns_pad + 255) / 256, 1024), (unsigned)gr.C);
+    colmax_kernel<<<grid1, 256>>>(gr.d_basis, gr.C, ns_pad, s->d_colmax + s->scale_off[g]);
+    dim3 grid2((unsigned)std::min<int64_t>((ns_pad + 255) / 256, 1024), (unsigned)(gr.C + 1));
+    quantize_kernel<<<grid2, 256>>>(gr.d_basis, gr.d_mask, gr.C, ns_pad, s->d_colmax + s->scale_off[g], s->col_off[g],
+                                    s->d_bq, s->d_colscale + s->scale_off[g]);
+    c->launches += 2;
+  }
+  LRR_CUDA(c, cudaGetLastError());
+  LRR_CUDA(c, cudaDeviceSynchronize());
+  if (encode_2d(s, &s->b_map, s->d_bq, (uint64_t)ns_pad, (uint64_t)s->ncols, (uint64_t)ns_pad, SLOT, (uint32_t)s->ncols)) {
+    s->why = "cuTensorMapEncodeTiled failed for the basis panels";
+    return LRR_OK;
+  }
+  // shared memory: stages of (genotype tile + 4 basis panels) + barriers + 1 KB alignment slack
+  const int stage_bytes = GENO_BYTES + SLOTS * s->ncols * 128;
+  const int budget = 227 * 1024 - (int)sizeof(Barriers) - 1024;
+  int stages = budget / stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages < 2) {
+    s->why = "not enough shared memory for two pipeline stages";
+    return LRR_OK;
+  }
+  s->n_stages = stages;
+  s->smem_bytes = stages * stage_bytes + (int)sizeof(Barriers) + 1024;
+  if (!s->attr_set) {
+    LRR_CUDA(c, cudaFuncSetAttribute(tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    s->attr_set = true;
+  }
+  s->usable = true;
+  s->why.clear();
+  return LRR_OK;
+}
+
+}  // namespace tc
+
+bool tc_supported(Ctx* c, bool may_have_missing) {
+  if (tc::prepare(c) != LRR_OK) return false;
+  tc::State* s = tc::state(c);
+  if (!s->usable) {
+    c->err = s->why;
+    return false;
+  }
+  if (may_have_missing && s->ncols > 128) {
+    c->err = "more than 128 digit columns: the two-plane (missing-call) mode does not fit TMEM";
+    return false;
+  }
+  return true;
+}
+
+void tc_invalidate(Ctx* c) {
+  if (!c->tc_state) return;
+  tc::State* s = static_cast<tc::State*>(c->tc_state);
+  tc::free_prepared(s);
+}
+
+void tc_release(Ctx* c) {
+  if (!c->tc_state) return;
+  tc::State* s = static_cast<tc::State*>(c->tc_state);
+  tc::free_prepared(s);
+  delete s;
+  c->tc_state = nullptr;
+}
+
+int launch_tc_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride,
+                    cudaStream_t st) {
+  using namespace tc;
+  if (M == 0) return LRR_OK;
+  if (int r = prepare(c)) return r;
+  State* s = state(c);
+  if (!s->usable) return fail(c, LRR_EINVAL, "tensor-core kernel unavailable: " + s->why);
+  CUtensorMap geno_map;
+  if (encode_2d(s, &geno_map, d_packed, (uint64_t)stride, (uint64_t)M, (uint64_t)stride, 128, TILE_M))
+    return fail(c, LRR_ECUDA, "cuTensorMapEncodeTiled failed for the genotype store (pointer must be 16-byte aligned)");
+  Params p;
+  memset(&p, 0, sizeof p);
+  p.M = M;
+  p.n_tiles = (int)((M + TILE_M - 1) / TILE_M);
+  p.n_chunks = (int)(stride / 128);
+  p.ncols = s->ncols;
+  p.n_stages = s->n_stages;
+  p.n_groups = (int)c->groups.size();
+  p.two_plane_ok = s->ncols <= 128;
+  p.row_flags = d_row_flags;
+  for (int g = 0; g < p.n_groups; ++g) {
+    const Group& gr = c->groups[g];
+    p.g[g].col_off = s->col_off[g];
+    p.g[g].C = gr.C;
+    p.g[g].n = gr.n;
+    p.g[g].counts = c->d_counts + (int64_t)g * c->reserved_variants * 4;
+    p.g[g].dots = c->d_dots + c->dots_offset[g];
+    p.g[g].colscale = s->d_colscale + s->scale_off[g];
+    p.g[g].mask = gr.d_mask;
+  }
+  const int grid = p.n_tiles < c->sm_count ? p.n_tiles : c->sm_count;
+  tc_sweep_kernel<<<grid, THREADS, s->smem_bytes, st>>>(geno_map, s->b_map, p);
+  c->launches++;
+  LRR_CUDA(c, cudaGetLastError());
+  return LRR_OK;
+}
+
 }  // namespace lrr

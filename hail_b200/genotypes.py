@@ -24,9 +24,11 @@ def _stream_ptr(device):
 class PackedGenotypes:
     """[n_variants, stride] uint8 on one CUDA device, rows in the lrr_b200 store layout (include/lrr_b200.h)."""
 
-    def __init__(self, data: torch.Tensor, n_variants: int, n_samples: int):
+    def __init__(self, data: torch.Tensor, n_variants: int, n_samples: int, row_flags: torch.Tensor = None):
         assert data.is_cuda and data.dtype == torch.uint8 and data.dim() == 2
         self.data = data
+        # the "missing mask" side array: uint8 [M], 1 iff the row has a missing call (None = unknown)
+        self.row_flags = row_flags
         self.n_variants = int(n_variants)
         self.n_samples = int(n_samples)
         self.stride = int(data.shape[1])
@@ -46,7 +48,8 @@ class PackedGenotypes:
     def empty(cls, n_variants, n_samples, device=0):
         dev = torch.device("cuda", device) if not isinstance(device, torch.device) else device
         stride = packed_stride(n_samples)
-        return cls(torch.empty((n_variants, stride), dtype=torch.uint8, device=dev), n_variants, n_samples)
+        return cls(torch.empty((n_variants, stride), dtype=torch.uint8, device=dev), n_variants, n_samples,
+                   torch.zeros(n_variants, dtype=torch.uint8, device=dev))
 
     @classmethod
     def from_bed_rows(cls, rows, n_samples, device=0, chunk_variants=1 << 16):
@@ -63,7 +66,8 @@ class PackedGenotypes:
                 hi = min(M, lo + chunk_variants)
                 d_in = rows_t[lo:hi].to(out.device, non_blocking=True).contiguous()
                 ctx.check(ctx.lib.lrr_pack_bed(ctx.handle, d_in.data_ptr(), hi - lo, bed_stride, n_samples,
-                                               out.data[lo:hi].data_ptr(), out.stride, _stream_ptr(out.device)))
+                                               out.data[lo:hi].data_ptr(), out.stride,
+                                               out.row_flags[lo:hi].data_ptr(), _stream_ptr(out.device)))
         return out
 
     @classmethod
@@ -92,13 +96,18 @@ class PackedGenotypes:
                 hi = min(M, lo + chunk_variants)
                 d_in = torch.from_numpy(d[lo:hi]).to(out.device)
                 ctx.check(ctx.lib.lrr_pack_dosage_i8(ctx.handle, d_in.data_ptr(), hi - lo, N,
-                                                     out.data[lo:hi].data_ptr(), out.stride, _stream_ptr(out.device)))
+                                                     out.data[lo:hi].data_ptr(), out.stride,
+                                                     out.row_flags[lo:hi].data_ptr(), _stream_ptr(out.device)))
         return out
 
     # ---- views / export ---------------------------------------------------------------------
     def rows(self, lo, hi):
         lo, hi = int(lo), int(hi)
-        return PackedGenotypes(self.data[lo:hi], hi - lo, self.n_samples)
+        return PackedGenotypes(self.data[lo:hi], hi - lo, self.n_samples,
+                               None if self.row_flags is None else self.row_flags[lo:hi])
+
+    def flags_ptr(self, lo=0):
+        return None if self.row_flags is None else self.row_flags[lo:].data_ptr()
 
     def to_dosage(self) -> np.ndarray:
         """int8 [M, N], missing = -1."""

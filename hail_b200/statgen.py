@@ -199,8 +199,8 @@ def _run_device(genotypes, bases, kernel="auto", want_log10_p=False, chunk_varia
                 for f in STAT_FIELDS:
                     setattr(arr[g], f, o[f][lo:hi].data_ptr())
                 arr[g].log10_p = o["log10_p"][lo:hi].data_ptr() if want_log10_p else None
-            ctx.check(ctx.lib.lrr_run(ctx.handle, genotypes.data[lo:hi].data_ptr(), hi - lo, genotypes.stride, N,
-                                      arr, len(bases), kid, stream))
+            ctx.check(ctx.lib.lrr_run(ctx.handle, genotypes.data[lo:hi].data_ptr(), genotypes.flags_ptr(lo), hi - lo,
+                                      genotypes.stride, N, arr, len(bases), kid, stream))
     return outs
 
 

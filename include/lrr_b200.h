@@ -70,14 +70,18 @@ const char* lrr_last_error(const lrr_ctx* ctx);
  * 2 bits per call, variant-major rows of lrr_packed_stride(N) bytes (a multiple of 128).  Codes:
  * 0,1,2 = number of alternate alleles, 3 = missing.  Within each little-endian 32-bit word, which
  * covers samples 16w..16w+15, sample 16w+4s+i sits at bits [8i+2s, 8i+2s+1] (so that
- * (word >> 2s) & 0x03030303 yields four consecutive samples as four bytes).  Padding samples are 0. */
+ * (word >> 2s) & 0x03030303 yields four consecutive samples as four bytes).  Padding samples are 0.
+ * Every writer of the store can also emit the "missing mask" side array d_row_flags [n_variants] (uint8,
+ * may be NULL): 1 iff the row holds at least one missing call.  lrr_run uses it to skip the
+ * missing-indicator plane for tiles without missing calls; passing NULL there is always correct
+ * (every tile is then treated as possibly missing). */
 int64_t lrr_packed_stride(int64_t n_samples);
 /* PLINK .bed SNP-major rows (no 3-byte header), a2_reference=True semantics (LoadPlink.scala:475-481) */
 int lrr_pack_bed(lrr_ctx* ctx, const uint8_t* d_bed, int64_t n_variants, int64_t bed_stride, int64_t n_samples,
-                 uint8_t* d_packed, int64_t packed_stride, void* stream);
+                 uint8_t* d_packed, int64_t packed_stride, uint8_t* d_row_flags, void* stream);
 /* int8 dosages [M, N] row-major: 0/1/2, anything else (e.g. -1) = missing */
 int lrr_pack_dosage_i8(lrr_ctx* ctx, const int8_t* d_dosage, int64_t n_variants, int64_t n_samples,
-                       uint8_t* d_packed, int64_t packed_stride, void* stream);
+                       uint8_t* d_packed, int64_t packed_stride, uint8_t* d_row_flags, void* stream);
 /* inverse of lrr_pack_dosage_i8 (missing -> -1); for tests and export */
 int lrr_unpack_dosage_i8(lrr_ctx* ctx, const uint8_t* d_packed, int64_t packed_stride, int64_t n_variants,
                          int64_t n_samples, int8_t* d_dosage, void* stream);
@@ -93,7 +97,7 @@ int lrr_unpack_bed(lrr_ctx* ctx, const uint8_t* d_packed, int64_t packed_stride,
  * depends only on (seed, first_variant + r, j), so any variant range can be regenerated anywhere. */
 int lrr_bn_fill(lrr_ctx* ctx, const uint32_t* d_thresholds, int n_pops, const uint8_t* d_pop, int64_t n_variants,
                 int64_t first_variant, int64_t n_samples, uint64_t seed, uint8_t* d_packed, int64_t packed_stride,
-                void* stream);
+                uint8_t* d_row_flags, void* stream);
 
 /* ---- basis: one call per group of phenotypes (Single = 1 group, Chained = G groups) -------------
  * The host has selected the group's complete samples (RU:88-128), computed an orthonormal basis Q of
@@ -118,8 +122,8 @@ int lrr_num_groups(const lrr_ctx* ctx);
 /* pre-size internal workspaces for up to max_variants rows per lrr_run call */
 int lrr_reserve(lrr_ctx* ctx, int64_t max_variants);
 /* regress `n_variants` packed rows against every group; outs[g] receives group g's fields */
-int lrr_run(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int64_t packed_stride, int64_t n_samples_total,
-            const lrr_group_out* outs, int32_t n_outs, int32_t kernel, void* stream);
+int lrr_run(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
+            int64_t n_samples_total, const lrr_group_out* outs, int32_t n_outs, int32_t kernel, void* stream);
 /* number of kernel launches issued by this context since creation (for bench accounting) */
 int64_t lrr_launch_count(const lrr_ctx* ctx);
 /* which kernel LRR_KERNEL_AUTO resolved to on the last lrr_run */

@@ -19,7 +19,7 @@ from oracle import linreg_oracle as O
 from tests.bn_mirror import bn_fill_numpy
 from tests.helpers import GOLDEN, assert_fields_close, load_regression_linear
 
-KERNELS = ["fp64"]
+KERNELS = ["fp64", "tc"]
 
 
 def _hb():
