@@ -37,21 +37,25 @@ constexpr int WARP_TMA = 8, WARP_MMA = 9;
 constexpr int THREADS = 10 * 32;
 constexpr int GENO_BYTES = TILE_M * 128;   // 16 KB
 constexpr int MAX_GROUPS = 8;
+constexpr int MAX_STAGES = 4;
+constexpr int MAX_RING = 12;           // A ring slots (32 TMEM columns each)
 constexpr int N_SLICES = 6;            // digits per basis column (48-bit fixed point)
-// TMEM column map (512 columns x 128 lanes x 32 bit)
-constexpr int TM_DC = 0;               // accumulators, plane c: columns [0, ncols)
-constexpr int TM_DM = 128;             // accumulators, plane m (two-plane mode needs ncols <= 128)
-constexpr int TM_AC = 256;             // A ring, plane c: 4 slots x 32 columns
-constexpr int TM_AM = 384;             // A ring, plane m
+// TMEM column map (512 columns x 128 lanes x 32 bit), ncols = digit columns padded to 16:
+//   [0, ncols)            accumulators of plane c (raw call code)
+//   [ncols, 2 ncols)      accumulators of plane m (missing indicator), two-plane tiles only
+//   [ring_base, 512)      A operand ring, 32 columns per slot; ring_base = 2 ncols rounded up to 32
+//                         one-plane tiles use all `depth` slots for plane c; two-plane tiles use the first
+//                         depth/2 slots for plane c and the second depth/2 for plane m
 
 struct GroupMeta {
   int col_off;        // first digit column of this group in B
   int C;              // dot-product columns (Kd + P)
   int n;              // complete samples
+  int mask_all;       // every stored sample is in the group: no masking needed for the hom-alt count
   int32_t* counts;    // [M][4]
   double* dots;       // [M][C]
   const double* colscale;   // [C]
-  const uint32_t* mask;     // [ns_pad/16], low bit of each kept field
+  const uint32_t* mask_hi;  // [ns_pad/16], high bit of each kept field
 };
 
 struct Params {
@@ -61,7 +65,10 @@ struct Params {
   int ncols;          // padded to 16
   int n_stages;
   int n_groups;
-  int two_plane_ok;   // ncols <= 128
+  int ring_base;      // first TMEM column of the A ring
+  int depth;          // ring slots (even, <= MAX_RING)
+  int stage_bytes;
+  int mask_bytes;     // n_groups * 128 when any group needs masking, else 0
   const uint8_t* row_flags;  // nullable
   GroupMeta g[MAX_GROUPS];
 };
@@ -71,16 +78,16 @@ struct Params {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -89,22 +96,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
+      "}\n" ::"r"(bar),
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int x, int y) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y)
       : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem desc]     (kind::i8, M=128, K=32)
 __device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -142,6 +152,24 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+// one lane of the (converged) warp; the enclosing control flow stays warp-uniform so that descriptors and
+// barrier addresses are computed on the uniform datapath (UTCIMMA takes uniform-register operands)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row atoms 1024 B apart
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
@@ -166,12 +194,12 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 }
 
 struct Barriers {
-  uint64_t full[4];      // stage filled by TMA
-  uint64_t empty[4];     // stage drained (8 unpack warps + MMA commit)
-  uint64_t a_full[SLOTS];   // A ring slot written (4 quarter-warps)
-  uint64_t a_empty[SLOTS];  // A ring slot consumed (MMA commit)
-  uint64_t d_full;       // accumulators complete (MMA commit)
-  uint64_t d_empty;      // accumulators read out (4 epilogue warps)
+  uint64_t full[MAX_STAGES];     // stage filled by TMA
+  uint64_t empty[MAX_STAGES];    // stage drained (8 unpack warps + MMA commit)
+  uint64_t a_full[MAX_RING];     // A ring slot written (4 quarter-warps)
+  uint64_t a_empty[MAX_RING];    // A ring slot consumed (MMA commit)
+  uint64_t d_full;               // accumulators complete (MMA commit)
+  uint64_t d_empty;              // accumulators read out (4 epilogue warps)
   uint32_t tmem_base;
   uint32_t pad;
   int32_t n2_xchg[MAX_GROUPS][TILE_M];  // hom-alt popcounts of the h=1 half, handed to the epilogue warps
@@ -194,27 +222,37 @@ __device__ __forceinline__ bool tile_has_missing(const Params& p, int tile) {
   return any != 0;
 }
 
+// NG = number of groups known at compile time (1, 2) or 0 = run-time p.n_groups
+template <int NG>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_constant__ CUtensorMap b_map, const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int stage_bytes = GENO_BYTES + SLOTS * p.ncols * 128;
-  Barriers* bars = reinterpret_cast<Barriers*>(smem + (size_t)p.n_stages * stage_bytes);
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // stage ring base (shared window address)
+  uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_gen + (size_t)p.n_stages * p.stage_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+  auto AFULL = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
+  auto AEMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + MAX_RING + s); };
+  const uint32_t DFULL = bar0 + 8u * (2 * MAX_STAGES + 2 * MAX_RING);
+  const uint32_t DEMPTY = DFULL + 8u;
+  const int n_groups = NG ? NG : p.n_groups;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
-      mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], UNPACK_WARPS + 1);
+      mbar_init(FULL(s), 1);
+      mbar_init(EMPTY(s), UNPACK_WARPS + 1);
     }
-    for (int s = 0; s < SLOTS; ++s) {
-      mbar_init(&bars->a_full[s], 4);
-      mbar_init(&bars->a_empty[s], 1);
+    for (int s = 0; s < MAX_RING; ++s) {
+      mbar_init(AFULL(s), 4);
+      mbar_init(AEMPTY(s), 1);
     }
-    mbar_init(&bars->d_full, 1);
-    mbar_init(&bars->d_empty, 4);
+    mbar_init(DFULL, 1);
+    mbar_init(DEMPTY, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WARP_MMA) {
@@ -233,84 +271,114 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
 
   const int first_tile = blockIdx.x;
   const int tile_step = gridDim.x;
+  const int panel_bytes = p.ncols * 128;
 
   if (warp == WARP_TMA) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
-      uint32_t chunk_g = 0;
-      for (int tile = first_tile; tile < p.n_tiles; tile += tile_step) {
-        for (int ch = 0; ch < p.n_chunks; ++ch, ++chunk_g) {
-          const int st = chunk_g % p.n_stages;
-          const uint32_t it = chunk_g / p.n_stages;
-          mbar_wait(&bars->empty[st], (it & 1) ^ 1);
-          uint8_t* sbase = smem + (size_t)st * stage_bytes;
-          mbar_arrive_expect_tx(&bars->full[st], (uint32_t)stage_bytes);
-          tma_load_2d(&geno_map, &bars->full[st], sbase, ch * 128, tile * TILE_M);
+    // (whole warp runs the loop; one elected lane issues the copies)
+    int st = 0;
+    uint32_t st_phase = 0;   // parity of the number of completed passes over the stage ring
+    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step) {
+      for (int ch = 0; ch < p.n_chunks; ++ch) {
+        mbar_wait(EMPTY(st), st_phase ^ 1);
+        const uint32_t sbase = smem0 + st * p.stage_bytes;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(FULL(st), (uint32_t)(GENO_BYTES + SLOTS * panel_bytes + p.mask_bytes));
+          tma_load_2d(&geno_map, FULL(st), sbase, ch * 128, tile * TILE_M);
 #pragma unroll
           for (int s = 0; s < SLOTS; ++s)
-            tma_load_2d(&b_map, &bars->full[st], sbase + GENO_BYTES + s * p.ncols * 128, ch * CHUNK + s * SLOT, 0);
+            tma_load_2d(&b_map, FULL(st), sbase + GENO_BYTES + s * panel_bytes, ch * CHUNK + s * SLOT, 0);
+          if (p.mask_bytes) {
+            for (int g = 0; g < n_groups; ++g)
+              bulk_load_1d(sbase + GENO_BYTES + SLOTS * panel_bytes + g * 128, p.g[g].mask_hi + ch * (CHUNK / 16), 128,
+                           FULL(st));
+          }
         }
+        __syncwarp();
+        if (++st == p.n_stages) { st = 0; st_phase ^= 1; }
       }
     }
   } else if (warp == WARP_MMA) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.ncols);
-      uint32_t chunk_g = 0;
-      uint32_t tile_i = 0;
-      for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++tile_i) {
-        const bool two_plane = tile_has_missing(p, tile);
-        mbar_wait(&bars->d_empty, (tile_i & 1) ^ 1);
-        tc_fence_after();
-        for (int ch = 0; ch < p.n_chunks; ++ch, ++chunk_g) {
-          const int st = chunk_g % p.n_stages;
-          const uint32_t it = chunk_g / p.n_stages;
-          mbar_wait(&bars->full[st], it & 1);
-          const uint32_t b_base = smem_u32(smem + (size_t)st * stage_bytes + GENO_BYTES);
+    // (whole warp runs the loop in uniform control flow; one elected lane issues tcgen05.mma / commit)
+    const uint32_t idesc = make_idesc(p.ncols);
+    int st = 0;
+    uint32_t st_phase = 0;
+    uint32_t use_bits = 0;   // parity of the number of times each ring slot has been consumed
+    uint32_t tile_i = 0;
+    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++tile_i) {
+      const bool two_plane = tile_has_missing(p, tile);
+      const int depth = two_plane ? p.depth / 2 : p.depth;
+      mbar_wait(DEMPTY, (tile_i & 1) ^ 1);   // the previous tile's accumulators have been read out
+      tc_fence_after();
+      int ri = 0;
+      for (int ch = 0; ch < p.n_chunks; ++ch) {
+        mbar_wait(FULL(st), st_phase);
+        const uint32_t b_base = smem0 + st * p.stage_bytes + GENO_BYTES;
 #pragma unroll
-          for (int s = 0; s < SLOTS; ++s) {
-            mbar_wait(&bars->a_full[s], chunk_g & 1);
-            tc_fence_after();
-            const uint64_t bdesc = make_b_desc(b_base + s * p.ncols * 128);
+        for (int s = 0; s < SLOTS; ++s) {
+          mbar_wait(AFULL(ri), (use_bits >> ri) & 1u);
+          use_bits ^= 1u << ri;
+          tc_fence_after();
+          const uint64_t bdesc = make_b_desc(b_base + s * panel_bytes);
+          const uint32_t a_c = tmem + p.ring_base + ri * 32;
+          const uint32_t a_m = a_c + depth * 32;
+          if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t acc = (ch | s | j) ? 1u : 0u;
-              mma_i8_ts(tmem + TM_DC, tmem + TM_AC + s * 32 + j * 8, bdesc + (uint64_t)(j * 2), idesc, acc);
-              if (two_plane)
-                mma_i8_ts(tmem + TM_DM, tmem + TM_AM + s * 32 + j * 8, bdesc + (uint64_t)(j * 2), idesc, acc);
+              mma_i8_ts(tmem, a_c + j * 8, bdesc + (uint64_t)(j * 2), idesc, acc);
+              if (two_plane) mma_i8_ts(tmem + p.ncols, a_m + j * 8, bdesc + (uint64_t)(j * 2), idesc, acc);
             }
-            tc_commit(&bars->a_empty[s]);
+            tc_commit(AEMPTY(ri));
+            if (s == SLOTS - 1) tc_commit(EMPTY(st));
           }
-          tc_commit(&bars->empty[st]);
+          __syncwarp();
+          if (++ri == depth) ri = 0;
         }
-        tc_commit(&bars->d_full);
+        if (++st == p.n_stages) { st = 0; st_phase ^= 1; }
       }
+      if (elect_one()) tc_commit(DFULL);
+      __syncwarp();
     }
   } else {
     // ============================== unpack + epilogue warps ==============================
     const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int h = warp >> 2;         // which half of the slots of a chunk this warp produces
+    const int h = warp >> 2;         // this warp produces the ring slots of parity h
     const int row = q * 32 + lane;   // variant row within the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    uint32_t chunk_g = 0;
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t swz = (uint32_t)(row & 7);
+    int st = 0;
+    uint32_t st_phase = 0;
+    uint32_t use_bits = 0;           // parity of the number of times each ring slot has been produced
     uint32_t tile_i = 0;
+    bool prev_two_plane = false;
     for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++tile_i) {
       const bool two_plane = tile_has_missing(p, tile);
-      int n2[MAX_GROUPS];
+      const int depth = two_plane ? p.depth / 2 : p.depth;
+      if (tile_i > 0 && two_plane != prev_two_plane) {
+        // the ring is laid out differently: wait until every MMA of the previous tile has retired
+        mbar_wait(DFULL, (tile_i - 1) & 1);
+        tc_fence_after();
+      }
+      prev_two_plane = two_plane;
+      int n2[NG ? NG : MAX_GROUPS];
 #pragma unroll
-      for (int g = 0; g < MAX_GROUPS; ++g) n2[g] = 0;
+      for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) n2[g] = 0;
+      int ri = h;   // ring slot of this warp's next production (slots alternate between the two halves)
 
-      for (int ch = 0; ch < p.n_chunks; ++ch, ++chunk_g) {
-        const int st = chunk_g % p.n_stages;
-        const uint32_t it = chunk_g / p.n_stages;
-        mbar_wait(&bars->full[st], it & 1);
-        const uint8_t* grow = smem + (size_t)st * stage_bytes + row * 128;
+      for (int ch = 0; ch < p.n_chunks; ++ch) {
+        mbar_wait(FULL(st), st_phase);
+        const uint32_t sbase = smem0 + st * p.stage_bytes;
+        const uint32_t grow = sbase + row_off;
+        const uint32_t mrow = sbase + GENO_BYTES + SLOTS * panel_bytes;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          const int s = h + 2 * k;   // slot index within the chunk (and in the A ring)
+          const int s = h + 2 * k;   // slot index within the chunk
           // packed bytes of samples [128 s, 128 s + 128) of this row: 16-byte chunks 2s and 2s+1 (swizzled)
-          const uint4 w0 = *reinterpret_cast<const uint4*>(grow + (((2 * s) ^ (row & 7)) << 4));
-          const uint4 w1 = *reinterpret_cast<const uint4*>(grow + (((2 * s + 1) ^ (row & 7)) << 4));
+          const uint4 w0 = lds128(grow + (((uint32_t)(2 * s) ^ swz) << 4));
+          const uint4 w1 = lds128(grow + (((uint32_t)(2 * s + 1) ^ swz) << 4));
           const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
           uint32_t rc[32];
 #pragma unroll
@@ -320,23 +388,36 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
             rc[4 * i + 2] = (w[i] >> 4) & 0x03030303u;
             rc[4 * i + 3] = (w[i] >> 6) & 0x03030303u;
           }
-          // exact hom-alt counts per group (code 2 = hi & ~lo), for x.x = n1 + 4 n2
-          const int word0 = ch * (CHUNK / 16) + s * 8;
+          // exact hom-alt counts per group (code 2: high bit set, low bit clear), for x.x = n1 + 4 n2
 #pragma unroll
-          for (int g = 0; g < MAX_GROUPS; ++g) {
-            if (g < p.n_groups) {
-              const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(p.g[g].mask + word0));
-              const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(p.g[g].mask + word0 + 4));
-              const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
+            if (NG || g < n_groups) {
+              uint32_t mm[8];
+              if (p.g[g].mask_all) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mm[i] = 0xAAAAAAAAu;
+              } else {
+                const uint4 m0 = lds128(mrow + g * 128 + s * 32);
+                const uint4 m1 = lds128(mrow + g * 128 + s * 32 + 16);
+                mm[0] = m0.x; mm[1] = m0.y; mm[2] = m0.z; mm[3] = m0.w;
+                mm[4] = m1.x; mm[5] = m1.y; mm[6] = m1.z; mm[7] = m1.w;
+              }
               int acc = 0;
+              if (two_plane) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) acc += __popc((w[i] >> 1) & ~w[i] & mm[i]);
+                for (int i = 0; i < 8; ++i) acc += __popc(w[i] & ~(w[i] << 1) & mm[i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc += __popc(w[i] & mm[i]);
+              }
               n2[g] += acc;
             }
           }
-          mbar_wait(&bars->a_empty[s], (chunk_g & 1) ^ 1);
+          mbar_wait(AEMPTY(ri), ((use_bits >> ri) & 1u) ^ 1u);
+          use_bits ^= 1u << ri;
           tc_fence_after();
-          tmem_st32(tmem + lane_addr + TM_AC + s * 32, rc);
+          const uint32_t a_c = tmem + lane_addr + p.ring_base + ri * 32;
+          tmem_st32(a_c, rc);
           if (two_plane) {
             uint32_t rm[32];
 #pragma unroll
@@ -347,36 +428,41 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
               rm[4 * i + 2] = (mw >> 4) & 0x01010101u;
               rm[4 * i + 3] = (mw >> 6) & 0x01010101u;
             }
-            tmem_st32(tmem + lane_addr + TM_AM + s * 32, rm);
+            tmem_st32(a_c + depth * 32, rm);
           }
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->a_full[s]);
+          if (lane == 0) mbar_arrive(AFULL(ri));
+          ri += 2;
+          if (ri >= depth) ri -= depth;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->empty[st]);
+        if (lane == 0) mbar_arrive(EMPTY(st));
+        if (++st == p.n_stages) { st = 0; st_phase ^= 1; }
       }
 
       // ------------------------------ per-tile epilogue ------------------------------
       if (h == 1) {
 #pragma unroll
-        for (int g = 0; g < MAX_GROUPS; ++g)
-          if (g < p.n_groups) bars->n2_xchg[g][row] = n2[g];
+        for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g)
+          if (NG || g < n_groups) bars->n2_xchg[g][row] = n2[g];
       }
       named_bar_sync(1, UNPACK_WARPS * 32);
       if (h == 0) {
-        mbar_wait(&bars->d_full, tile_i & 1);
+        mbar_wait(DFULL, tile_i & 1);
         tc_fence_after();
         const int64_t v = (int64_t)tile * TILE_M + row;
-        for (int g = 0; g < p.n_groups; ++g) {
+        const uint32_t d_c = tmem + lane_addr, d_m = tmem + lane_addr + p.ncols;
+#pragma unroll
+        for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
+          if (!(NG || g < n_groups)) continue;
           const GroupMeta& G = p.g[g];
           const int n2g = n2[g] + bars->n2_xchg[g][row];
           // the group's columns: C x N_SLICES digit columns then one "ones" column
           const int ones_col = G.col_off + G.C * N_SLICES;
-          // read the ones column(s) first
           uint32_t r16[16];
-          tmem_ld16(tmem + lane_addr + TM_DC + (ones_col & ~15), r16);
+          tmem_ld16(d_c + (ones_col & ~15), r16);
           tmem_wait_ld();
           int sc = 0;
 #pragma unroll
@@ -384,7 +470,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
             if (i == (ones_col & 15)) sc = (int)r16[i];
           int nm = 0;
           if (two_plane) {
-            tmem_ld16(tmem + lane_addr + TM_DM + (ones_col & ~15), r16);
+            tmem_ld16(d_m + (ones_col & ~15), r16);
             tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < 16; ++i)
@@ -399,8 +485,8 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
           long long hi = 0, lo = 0, mhi = 0, mlo = 0;
           for (int base = c_lo & ~15; base < c_hi; base += 16) {
             uint32_t dc[16], dm[16];
-            tmem_ld16(tmem + lane_addr + TM_DC + base, dc);
-            if (two_plane) tmem_ld16(tmem + lane_addr + TM_DM + base, dm);
+            tmem_ld16(d_c + base, dc);
+            if (two_plane) tmem_ld16(d_m + base, dm);
             tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -430,7 +516,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->d_empty);
+        if (lane == 0) mbar_arrive(DEMPTY);
       }
     }
   }
@@ -478,6 +564,11 @@ __global__ void quantize_kernel(const double* __restrict__ basis, const uint32_t
   }
 }
 
+__global__ void mask_hi_kernel(const uint32_t* __restrict__ mask_lo, int64_t words, uint32_t* __restrict__ mask_hi) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x)
+    mask_hi[i] = mask_lo[i] << 1;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -493,6 +584,8 @@ struct State {
   int8_t* d_bq = nullptr;
   double* d_colscale = nullptr;   // concatenated per group
   unsigned long long* d_colmax = nullptr;
+  uint32_t* d_mask_hi = nullptr;  // [G][ns_pad/16] group masks shifted to the high bit of each field
+  int ring_base = 0, depth = 0, stage_bytes = 0, mask_bytes = 0;
   std::vector<int> col_off, scale_off;
   CUtensorMap b_map;
   bool attr_set = false;
@@ -507,6 +600,8 @@ static void free_prepared(State* s) {
   cudaFree(s->d_bq);
   cudaFree(s->d_colscale);
   cudaFree(s->d_colmax);
+  cudaFree(s->d_mask_hi);
+  s->d_mask_hi = nullptr;
   s->d_bq = nullptr;
   s->d_colscale = nullptr;
   s->d_colmax = nullptr;
@@ -569,8 +664,15 @@ static int prepare(Ctx* c) {
   LRR_CUDA(c, cudaMalloc(&s->d_colscale, sizeof(double) * (size_t)nscale));
   LRR_CUDA(c, cudaMalloc(&s->d_colmax, sizeof(unsigned long long) * (size_t)nscale));
   LRR_CUDA(c, cudaMemset(s->d_colmax, 0, sizeof(unsigned long long) * (size_t)nscale));
+  const int64_t mask_words = ns_pad / 16;
+  LRR_CUDA(c, cudaMalloc(&s->d_mask_hi, sizeof(uint32_t) * (size_t)mask_words * G));
+  bool any_masked = false;
   for (size_t g = 0; g < G; ++g) {
     const Group& gr = c->groups[g];
+    if ((int64_t)gr.n != c->n_samples_total) any_masked = true;
+    mask_hi_kernel<<<(unsigned)std::min<int64_t>((mask_words + 255) / 256, 1024), 256>>>(gr.d_mask, mask_words,
+                                                                                        s->d_mask_hi + g * mask_words);
+    c->launches++;
     dim3 grid1((unsigned)std::min<int64_t>((ns_pad + 255) / 256, 1024), (unsigned)gr.C);
     colmax_kernel<<<grid1, 256>>>(gr.d_basis, gr.C, ns_pad, s->d_colmax + s->scale_off[g]);
     dim3 grid2((unsigned)std::min<int64_t>((ns_pad + 255) / 256, 1024), (unsigned)(gr.C + 1));
@@ -584,19 +686,31 @@ static int prepare(Ctx* c) {
     s->why = "cuTensorMapEncodeTiled failed for the basis panels";
     return LRR_OK;
   }
-  // shared memory: stages of (genotype tile + 4 basis panels) + barriers + 1 KB alignment slack
-  const int stage_bytes = GENO_BYTES + SLOTS * s->ncols * 128;
+  // shared memory: stages of (genotype tile + 4 basis panels [+ group masks]) + barriers + 1 KB alignment slack
+  s->mask_bytes = any_masked ? (int)G * 128 : 0;
+  const int stage_bytes = (GENO_BYTES + SLOTS * s->ncols * 128 + s->mask_bytes + 1023) / 1024 * 1024;
+  s->stage_bytes = stage_bytes;
+  s->ring_base = (2 * s->ncols + 31) / 32 * 32;
+  s->depth = (512 - s->ring_base) / 32;
+  if (s->depth > MAX_RING) s->depth = MAX_RING;
+  s->depth &= ~3;   // even in both one-plane (depth) and two-plane (depth / 2) mode
   const int budget = 227 * 1024 - (int)sizeof(Barriers) - 1024;
   int stages = budget / stage_bytes;
-  if (stages > 4) stages = 4;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) {
     s->why = "not enough shared memory for two pipeline stages";
     return LRR_OK;
   }
   s->n_stages = stages;
   s->smem_bytes = stages * stage_bytes + (int)sizeof(Barriers) + 1024;
+  if (s->depth < 4) {
+    s->why = "not enough tensor memory for the A ring";
+    return LRR_OK;
+  }
   if (!s->attr_set) {
-    LRR_CUDA(c, cudaFuncSetAttribute(tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LRR_CUDA(c, cudaFuncSetAttribute(tc_sweep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LRR_CUDA(c, cudaFuncSetAttribute(tc_sweep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LRR_CUDA(c, cudaFuncSetAttribute(tc_sweep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     s->attr_set = true;
   }
   s->usable = true;
@@ -652,7 +766,10 @@ int launch_tc_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags,
   p.ncols = s->ncols;
   p.n_stages = s->n_stages;
   p.n_groups = (int)c->groups.size();
-  p.two_plane_ok = s->ncols <= 128;
+  p.ring_base = s->ring_base;
+  p.depth = s->depth;
+  p.stage_bytes = s->stage_bytes;
+  p.mask_bytes = s->mask_bytes;
   p.row_flags = d_row_flags;
   for (int g = 0; g < p.n_groups; ++g) {
     const Group& gr = c->groups[g];
@@ -662,10 +779,16 @@ int launch_tc_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags,
     p.g[g].counts = c->d_counts + (int64_t)g * c->reserved_variants * 4;
     p.g[g].dots = c->d_dots + c->dots_offset[g];
     p.g[g].colscale = s->d_colscale + s->scale_off[g];
-    p.g[g].mask = gr.d_mask;
+    p.g[g].mask_hi = s->d_mask_hi + (int64_t)g * (gr.ns_pad / 16);
+    p.g[g].mask_all = ((int64_t)gr.n == c->n_samples_total) ? 1 : 0;
   }
   const int grid = p.n_tiles < c->sm_count ? p.n_tiles : c->sm_count;
-  tc_sweep_kernel<<<grid, THREADS, s->smem_bytes, st>>>(geno_map, s->b_map, p);
+  if (p.n_groups == 1)
+    tc_sweep_kernel<1><<<grid, THREADS, s->smem_bytes, st>>>(geno_map, s->b_map, p);
+  else if (p.n_groups == 2)
+    tc_sweep_kernel<2><<<grid, THREADS, s->smem_bytes, st>>>(geno_map, s->b_map, p);
+  else
+    tc_sweep_kernel<0><<<grid, THREADS, s->smem_bytes, st>>>(geno_map, s->b_map, p);
   c->launches++;
   LRR_CUDA(c, cudaGetLastError());
   return LRR_OK;
