@@ -5,7 +5,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblrr_b200.so")
+# LRR_B200_LIB overrides the library file (A/B builds of the same sources during kernel tuning)
+LIB_PATH = os.environ.get("LRR_B200_LIB") or os.path.join(HERE, "liblrr_b200.so")
 
 KERNEL_AUTO, KERNEL_FP64, KERNEL_TC = 0, 1, 2
 KERNELS = {"auto": KERNEL_AUTO, "fp64": KERNEL_FP64, "tc": KERNEL_TC}

@@ -32,9 +32,12 @@ constexpr int TILE_M = 128;            // variants per tile == TMEM lanes
 constexpr int CHUNK = 512;             // samples per shared-memory stage (128 packed bytes per row)
 constexpr int SLOT = 128;              // samples per TMEM A slot (32 columns of 4 x uint8)
 constexpr int SLOTS = CHUNK / SLOT;    // 4
-constexpr int UNPACK_WARPS = 8;
-constexpr int WARP_TMA = 8, WARP_MMA = 9;
-constexpr int THREADS = 10 * 32;
+constexpr int UNPACK_WARPS = 16;       // warp w: TMEM lane quarter w & 3, slot (w >> 2) of every chunk
+constexpr int WARP_TMA = 16, WARP_MMA = 17;
+constexpr int THREADS = 18 * 32;
+#ifndef LRR_TC_SHIFT_ON_FMA
+#define LRR_TC_SHIFT_ON_FMA 1           // right shifts as mul.hi (IMAD.HI, FMA pipe) instead of SHF (ALU pipe)
+#endif
 constexpr int GENO_BYTES = TILE_M * 128;   // 16 KB
 constexpr int MAX_GROUPS = 8;
 constexpr int MAX_STAGES = 4;
@@ -66,7 +69,8 @@ struct Params {
   int n_stages;
   int n_groups;
   int ring_base;      // first TMEM column of the A ring
-  int depth;          // ring slots (even, <= MAX_RING)
+  int depth;          // ring slots of one-plane tiles (multiple of 4, <= MAX_RING)
+  int depth_tp;       // ring slots per plane of two-plane tiles (multiple of 4)
   int stage_bytes;
   int mask_bytes;     // n_groups * 128 when any group needs masking, else 0
   const uint8_t* row_flags;  // nullable
@@ -165,6 +169,17 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// w >> k for k in {2, 4, 6}
+template <int K>
+__device__ __forceinline__ uint32_t shr(uint32_t w) {
+#if LRR_TC_SHIFT_ON_FMA
+  uint32_t r;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(w), "r"(1u << (32 - K)));
+  return r;
+#else
+  return w >> K;
+#endif
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -202,7 +217,7 @@ struct Barriers {
   uint64_t d_empty;              // accumulators read out (4 epilogue warps)
   uint32_t tmem_base;
   uint32_t pad;
-  int32_t n2_xchg[MAX_GROUPS][TILE_M];  // hom-alt popcounts of the h=1 half, handed to the epilogue warps
+  int32_t n2_xchg[SLOTS - 1][MAX_GROUPS][TILE_M];  // hom-alt popcounts of slots 1..3, handed to the epilogue warps
 };
 
 __device__ __forceinline__ bool tile_has_missing(const Params& p, int tile) {
@@ -308,7 +323,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
     uint32_t tile_i = 0;
     for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++tile_i) {
       const bool two_plane = tile_has_missing(p, tile);
-      const int depth = two_plane ? p.depth / 2 : p.depth;
+      const int depth = two_plane ? p.depth_tp : p.depth;
       mbar_wait(DEMPTY, (tile_i & 1) ^ 1);   // the previous tile's accumulators have been read out
       tc_fence_after();
       int ri = 0;
@@ -344,11 +359,13 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
   } else {
     // ============================== unpack + epilogue warps ==============================
     const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int h = warp >> 2;         // this warp produces the ring slots of parity h
+    const int s = warp >> 2;         // slot of every chunk this warp produces
     const int row = q * 32 + lane;   // variant row within the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t ld0 = row_off + (((uint32_t)(2 * s) ^ swz) << 4);       // 16-byte chunks 2s, 2s+1 (swizzled)
+    const uint32_t ld1 = row_off + (((uint32_t)(2 * s + 1) ^ swz) << 4);
     int st = 0;
     uint32_t st_phase = 0;
     uint32_t use_bits = 0;           // parity of the number of times each ring slot has been produced
@@ -356,7 +373,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
     bool prev_two_plane = false;
     for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++tile_i) {
       const bool two_plane = tile_has_missing(p, tile);
-      const int depth = two_plane ? p.depth / 2 : p.depth;
+      const int depth = two_plane ? p.depth_tp : p.depth;
       if (tile_i > 0 && two_plane != prev_two_plane) {
         // the ring is laid out differently: wait until every MMA of the previous tile has retired
         mbar_wait(DFULL, (tile_i - 1) & 1);
@@ -366,43 +383,41 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
       int n2[NG ? NG : MAX_GROUPS];
 #pragma unroll
       for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) n2[g] = 0;
-      int ri = h;   // ring slot of this warp's next production (slots alternate between the two halves)
+      int ri = s;   // ring slot of this warp's next production (depth is a multiple of 4)
 
       for (int ch = 0; ch < p.n_chunks; ++ch) {
         mbar_wait(FULL(st), st_phase);
         const uint32_t sbase = smem0 + st * p.stage_bytes;
-        const uint32_t grow = sbase + row_off;
         const uint32_t mrow = sbase + GENO_BYTES + SLOTS * panel_bytes;
+        // packed bytes of samples [128 s, 128 s + 128) of this row
+        const uint4 w0 = lds128(sbase + ld0);
+        const uint4 w1 = lds128(sbase + ld1);
+        const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        uint32_t rc[32];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int s = h + 2 * k;   // slot index within the chunk
-          // packed bytes of samples [128 s, 128 s + 128) of this row: 16-byte chunks 2s and 2s+1 (swizzled)
-          const uint4 w0 = lds128(grow + (((uint32_t)(2 * s) ^ swz) << 4));
-          const uint4 w1 = lds128(grow + (((uint32_t)(2 * s + 1) ^ swz) << 4));
-          const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-          uint32_t rc[32];
+        for (int i = 0; i < 8; ++i) {
+          rc[4 * i + 0] = w[i] & 0x03030303u;
+          rc[4 * i + 1] = shr<2>(w[i]) & 0x03030303u;
+          rc[4 * i + 2] = shr<4>(w[i]) & 0x03030303u;
+          rc[4 * i + 3] = shr<6>(w[i]) & 0x03030303u;
+        }
+        // exact hom-alt counts per group (code 2: high bit set, low bit clear), for x.x = n1 + 4 n2
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            rc[4 * i + 0] = w[i] & 0x03030303u;
-            rc[4 * i + 1] = (w[i] >> 2) & 0x03030303u;
-            rc[4 * i + 2] = (w[i] >> 4) & 0x03030303u;
-            rc[4 * i + 3] = (w[i] >> 6) & 0x03030303u;
-          }
-          // exact hom-alt counts per group (code 2: high bit set, low bit clear), for x.x = n1 + 4 n2
+        for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
+          if (NG || g < n_groups) {
+            int acc = 0;
+            if (p.g[g].mask_all) {
+              if (two_plane) {
 #pragma unroll
-          for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
-            if (NG || g < n_groups) {
-              uint32_t mm[8];
-              if (p.g[g].mask_all) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) mm[i] = 0xAAAAAAAAu;
+                for (int i = 0; i < 8; ++i) acc += __popc(w[i] & ~(w[i] << 1) & 0xAAAAAAAAu);
               } else {
-                const uint4 m0 = lds128(mrow + g * 128 + s * 32);
-                const uint4 m1 = lds128(mrow + g * 128 + s * 32 + 16);
-                mm[0] = m0.x; mm[1] = m0.y; mm[2] = m0.z; mm[3] = m0.w;
-                mm[4] = m1.x; mm[5] = m1.y; mm[6] = m1.z; mm[7] = m1.w;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc += __popc(w[i] & 0xAAAAAAAAu);
               }
-              int acc = 0;
+            } else {
+              const uint4 m0 = lds128(mrow + g * 128 + s * 32);
+              const uint4 m1 = lds128(mrow + g * 128 + s * 32 + 16);
+              const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
               if (two_plane) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc += __popc(w[i] & ~(w[i] << 1) & mm[i]);
@@ -410,46 +425,47 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc += __popc(w[i] & mm[i]);
               }
-              n2[g] += acc;
             }
+            n2[g] += acc;
           }
-          mbar_wait(AEMPTY(ri), ((use_bits >> ri) & 1u) ^ 1u);
-          use_bits ^= 1u << ri;
-          tc_fence_after();
-          const uint32_t a_c = tmem + lane_addr + p.ring_base + ri * 32;
-          tmem_st32(a_c, rc);
-          if (two_plane) {
-            uint32_t rm[32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint32_t mw = w[i] & (w[i] >> 1);   // bit 2f set iff field f is code 3
-              rm[4 * i + 0] = mw & 0x01010101u;
-              rm[4 * i + 1] = (mw >> 2) & 0x01010101u;
-              rm[4 * i + 2] = (mw >> 4) & 0x01010101u;
-              rm[4 * i + 3] = (mw >> 6) & 0x01010101u;
-            }
-            tmem_st32(a_c + depth * 32, rm);
-          }
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(AFULL(ri));
-          ri += 2;
-          if (ri >= depth) ri -= depth;
         }
+        mbar_wait(AEMPTY(ri), ((use_bits >> ri) & 1u) ^ 1u);
+        use_bits ^= 1u << ri;
+        tc_fence_after();
+        const uint32_t a_c = tmem + lane_addr + p.ring_base + ri * 32;
+        tmem_st32(a_c, rc);
+        if (two_plane) {
+          uint32_t rm[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t mw = w[i] & (w[i] >> 1);   // bit 2f set iff field f is code 3
+            rm[4 * i + 0] = mw & 0x01010101u;
+            rm[4 * i + 1] = shr<2>(mw) & 0x01010101u;
+            rm[4 * i + 2] = shr<4>(mw) & 0x01010101u;
+            rm[4 * i + 3] = shr<6>(mw) & 0x01010101u;
+          }
+          tmem_st32(a_c + depth * 32, rm);
+        }
+        tmem_wait_st();
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(EMPTY(st));
+        if (lane == 0) {
+          mbar_arrive(AFULL(ri));
+          mbar_arrive(EMPTY(st));
+        }
+        ri += SLOTS;
+        if (ri >= depth) ri -= depth;
         if (++st == p.n_stages) { st = 0; st_phase ^= 1; }
       }
 
       // ------------------------------ per-tile epilogue ------------------------------
-      if (h == 1) {
+      if (s > 0) {
 #pragma unroll
         for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g)
-          if (NG || g < n_groups) bars->n2_xchg[g][row] = n2[g];
+          if (NG || g < n_groups) bars->n2_xchg[s - 1][g][row] = n2[g];
       }
       named_bar_sync(1, UNPACK_WARPS * 32);
-      if (h == 0) {
+      if (s == 0) {
         mbar_wait(DFULL, tile_i & 1);
         tc_fence_after();
         const int64_t v = (int64_t)tile * TILE_M + row;
@@ -458,7 +474,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
         for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
           if (!(NG || g < n_groups)) continue;
           const GroupMeta& G = p.g[g];
-          const int n2g = n2[g] + bars->n2_xchg[g][row];
+          const int n2g = n2[g] + bars->n2_xchg[0][g][row] + bars->n2_xchg[1][g][row] + bars->n2_xchg[2][g][row];
           // the group's columns: C x N_SLICES digit columns then one "ones" column
           const int ones_col = G.col_off + G.C * N_SLICES;
           uint32_t r16[16];
@@ -585,7 +601,7 @@ struct State {
   double* d_colscale = nullptr;   // concatenated per group
   unsigned long long* d_colmax = nullptr;
   uint32_t* d_mask_hi = nullptr;  // [G][ns_pad/16] group masks shifted to the high bit of each field
-  int ring_base = 0, depth = 0, stage_bytes = 0, mask_bytes = 0;
+  int ring_base = 0, depth = 0, depth_tp = 0, stage_bytes = 0, mask_bytes = 0;
   std::vector<int> col_off, scale_off;
   CUtensorMap b_map;
   bool attr_set = false;
@@ -693,7 +709,8 @@ static int prepare(Ctx* c) {
   s->ring_base = (2 * s->ncols + 31) / 32 * 32;
   s->depth = (512 - s->ring_base) / 32;
   if (s->depth > MAX_RING) s->depth = MAX_RING;
-  s->depth &= ~3;   // even in both one-plane (depth) and two-plane (depth / 2) mode
+  s->depth &= ~3;   // every unpack warp keeps its own slot-of-chunk: ring depths are multiples of 4
+  s->depth_tp = (s->depth / 2) & ~3;
   const int budget = 227 * 1024 - (int)sizeof(Barriers) - 1024;
   int stages = budget / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -703,7 +720,7 @@ static int prepare(Ctx* c) {
   }
   s->n_stages = stages;
   s->smem_bytes = stages * stage_bytes + (int)sizeof(Barriers) + 1024;
-  if (s->depth < 4) {
+  if (s->depth < 4 || s->depth_tp < 4) {
     s->why = "not enough tensor memory for the A ring";
     return LRR_OK;
   }
@@ -768,6 +785,7 @@ int launch_tc_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags,
   p.n_groups = (int)c->groups.size();
   p.ring_base = s->ring_base;
   p.depth = s->depth;
+  p.depth_tp = s->depth_tp;
   p.stage_bytes = s->stage_bytes;
   p.mask_bytes = s->mask_bytes;
   p.row_flags = d_row_flags;
