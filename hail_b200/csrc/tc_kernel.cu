@@ -22,6 +22,8 @@
 // (0..3), plane "m" the indicator [code == 3]; sum_j B (x0 + mean * m) = (Dc - 3 Dm) + mean * Dm.  Tiles whose
 // rows carry no missing call (row_flags from ingest) skip plane m entirely.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -33,22 +35,41 @@ constexpr int CHUNK = 512;             // samples per shared-memory stage (128 p
 constexpr int SLOT = 128;              // samples per TMEM A slot (32 columns of 4 x uint8)
 constexpr int SLOTS = CHUNK / SLOT;    // 4
 constexpr int UNPACK_WARPS = 16;       // warp w: TMEM lane quarter w & 3, slot (w >> 2) of every chunk
-constexpr int WARP_TMA = 16, WARP_MMA = 17;
-constexpr int THREADS = 18 * 32;
+constexpr int WARP_TMA_G = 16, WARP_TMA_B = 17, WARP_MMA = 18;
+constexpr int THREADS = 19 * 32;
+// timing-ablation switches (kernel tuning only; results are WRONG when any is non-zero)
+#ifndef LRR_ABL_NO_MMA
+#define LRR_ABL_NO_MMA 0
+#endif
+#ifndef LRR_ABL_MMA_NOWAIT
+#define LRR_ABL_MMA_NOWAIT 0
+#endif
+#ifndef LRR_ABL_NO_STTM
+#define LRR_ABL_NO_STTM 0
+#endif
+#ifndef LRR_ABL_NO_UNPACK
+#define LRR_ABL_NO_UNPACK 0
+#endif
+#ifndef LRR_ABL_NO_BPANEL
+#define LRR_ABL_NO_BPANEL 0
+#endif
 #ifndef LRR_TC_SHIFT_ON_FMA
-#define LRR_TC_SHIFT_ON_FMA 1           // right shifts as mul.hi (IMAD.HI, FMA pipe) instead of SHF (ALU pipe)
+#define LRR_TC_SHIFT_ON_FMA 0           // 1: right shifts as mul.hi (IMAD.HI, FMA pipe) instead of SHF -- measured slower
 #endif
 constexpr int GENO_BYTES = TILE_M * 128;   // 16 KB
-constexpr int MAX_GROUPS = 8;
-constexpr int MAX_STAGES = 4;
-constexpr int MAX_RING = 12;           // A ring slots (32 TMEM columns each)
+constexpr int MAX_GROUPS = 4;
+constexpr int MAX_GSTAGES = 10;        // genotype ring (16 KB per stage)
+constexpr int MAX_BSTAGES = 4;         // basis-panel ring (4 * ncols * 128 B per stage)
+constexpr int MAX_RING = 4;            // A ring groups (GROUP_COLS TMEM columns each)
+constexpr int GROUP_COLS = 128;        // one-plane: 4 slots of plane c; two-plane: 2 slots of plane c + 2 of plane m
 constexpr int N_SLICES = 6;            // digits per basis column (48-bit fixed point)
 // TMEM column map (512 columns x 128 lanes x 32 bit), ncols = digit columns padded to 16:
 //   [0, ncols)            accumulators of plane c (raw call code)
 //   [ncols, 2 ncols)      accumulators of plane m (missing indicator), two-plane tiles only
-//   [ring_base, 512)      A operand ring, 32 columns per slot; ring_base = 2 ncols rounded up to 32
-//                         one-plane tiles use all `depth` slots for plane c; two-plane tiles use the first
-//                         depth/2 slots for plane c and the second depth/2 for plane m
+//   [ring_base, 512)      A operand ring of `ring_groups` groups x 128 columns; ring_base = 2 ncols rounded up
+//                         to 32.  A group is the unit handed to the MMA warp: the 4 slots (512 samples) of a
+//                         chunk for one-plane tiles, or 2 slots of plane c + 2 slots of plane m (256 samples)
+//                         for two-plane tiles
 
 struct GroupMeta {
   int col_off;        // first digit column of this group in B
@@ -66,12 +87,11 @@ struct Params {
   int n_tiles;
   int n_chunks;
   int ncols;          // padded to 16
-  int n_stages;
+  int n_gstages, n_bstages;
   int n_groups;
   int ring_base;      // first TMEM column of the A ring
-  int depth;          // ring slots of one-plane tiles (multiple of 4, <= MAX_RING)
-  int depth_tp;       // ring slots per plane of two-plane tiles (multiple of 4)
-  int stage_bytes;
+  int ring_groups;    // groups of GROUP_COLS columns in the A ring (2..MAX_RING)
+  int gstage_bytes, bstage_bytes;
   int mask_bytes;     // n_groups * 128 when any group needs masking, else 0
   const uint8_t* row_flags;  // nullable
   GroupMeta g[MAX_GROUPS];
@@ -109,6 +129,40 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(x), "r"(y)
       : "memory");
+}
+// same copy delivered to the same shared-memory offset (and mbarrier) of every CTA in `cta_mask`
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint32_t bar, uint32_t dst, int x, int y,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t n_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -209,8 +263,10 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 }
 
 struct Barriers {
-  uint64_t full[MAX_STAGES];     // stage filled by TMA
-  uint64_t empty[MAX_STAGES];    // stage drained (8 unpack warps + MMA commit)
+  uint64_t gfull[MAX_GSTAGES];   // genotype stage filled by TMA
+  uint64_t gempty[MAX_GSTAGES];  // genotype stage read out by the 16 unpack warps
+  uint64_t bfull[MAX_BSTAGES];   // basis-panel stage filled by TMA (possibly multicast from cluster peers)
+  uint64_t bempty[MAX_BSTAGES];  // basis-panel stage consumed (MMA commit of every CTA in the cluster)
   uint64_t a_full[MAX_RING];     // A ring slot written (4 quarter-warps)
   uint64_t a_empty[MAX_RING];    // A ring slot consumed (MMA commit)
   uint64_t d_full;               // accumulators complete (MMA commit)
@@ -221,8 +277,9 @@ struct Barriers {
 };
 
 __device__ __forceinline__ bool tile_has_missing(const Params& p, int tile) {
-  if (!p.row_flags) return true;
   const int64_t r0 = (int64_t)tile * TILE_M;
+  if (r0 >= p.M) return false;   // padding tile of a cluster
+  if (!p.row_flags) return true;
   uint32_t any = 0;
   if (r0 + TILE_M <= p.M && ((reinterpret_cast<uintptr_t>(p.row_flags + r0) & 15) == 0)) {
     const uint4* f = reinterpret_cast<const uint4*>(p.row_flags + r0);
@@ -237,20 +294,30 @@ __device__ __forceinline__ bool tile_has_missing(const Params& p, int tile) {
   return any != 0;
 }
 
-// NG = number of groups known at compile time (1, 2) or 0 = run-time p.n_groups
-template <int NG>
+// NG = number of groups known at compile time (1, 2) or 0 = run-time p.n_groups.
+// CS = thread-block cluster size (1, 2, 4): the CTAs of a cluster sweep CS consecutive variant tiles in lockstep
+// and share every basis panel -- each CTA fetches 4/CS of the chunk's panels and TMA-multicasts them to all.
+//
+// Two independent shared-memory rings: the genotype tiles come from HBM (long latency, 16 KB per chunk, released
+// as soon as the unpack warps have read them -> deep prefetch), the basis panels come from L2 (short latency,
+// 4 * ncols * 128 B per chunk, held until the tensor core has consumed them).
+template <int NG, int CS>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_constant__ CUtensorMap b_map, const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // stage ring base (shared window address)
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // genotype ring base (shared window address)
   uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_gen + (size_t)p.n_stages * p.stage_bytes);
+  const uint32_t bring0 = smem0 + p.n_gstages * p.gstage_bytes;   // basis-panel ring base
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_gen + (size_t)p.n_gstages * p.gstage_bytes +
+                                               (size_t)p.n_bstages * p.bstage_bytes);
   const uint32_t bar0 = smem_u32(bars);
-  auto FULL = [&](int s) { return bar0 + 8u * s; };
-  auto EMPTY = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
-  auto AFULL = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
-  auto AEMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + MAX_RING + s); };
-  const uint32_t DFULL = bar0 + 8u * (2 * MAX_STAGES + 2 * MAX_RING);
+  auto GFULL = [&](int s) { return bar0 + 8u * s; };
+  auto GEMPTY = [&](int s) { return bar0 + 8u * (MAX_GSTAGES + s); };
+  auto BFULL = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + s); };
+  auto BEMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + MAX_BSTAGES + s); };
+  auto AFULL = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + 2 * MAX_BSTAGES + s); };
+  auto AEMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + 2 * MAX_BSTAGES + MAX_RING + s); };
+  const uint32_t DFULL = bar0 + 8u * (2 * MAX_GSTAGES + 2 * MAX_BSTAGES + 2 * MAX_RING);
   const uint32_t DEMPTY = DFULL + 8u;
   const int n_groups = NG ? NG : p.n_groups;
 
@@ -258,12 +325,16 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.n_stages; ++s) {
-      mbar_init(FULL(s), 1);
-      mbar_init(EMPTY(s), UNPACK_WARPS + 1);
+    for (int s = 0; s < p.n_gstages; ++s) {
+      mbar_init(GFULL(s), 1);
+      mbar_init(GEMPTY(s), UNPACK_WARPS);
     }
-    for (int s = 0; s < MAX_RING; ++s) {
-      mbar_init(AFULL(s), 4);
+    for (int s = 0; s < p.n_bstages; ++s) {
+      mbar_init(BFULL(s), 1);
+      mbar_init(BEMPTY(s), CS);   // the MMA commit of every CTA in the cluster
+    }
+    for (int s = 0; s < p.ring_groups; ++s) {
+      mbar_init(AFULL(s), UNPACK_WARPS);   // one-plane: 16 warps x 1 arrival; two-plane: 8 warps x 2 arrivals
       mbar_init(AEMPTY(s), 1);
     }
     mbar_init(DFULL, 1);
@@ -275,83 +346,127 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp == WARP_TMA && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&geno_map) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&b_map) : "memory");
-  }
+  if (warp == WARP_TMA_G && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&geno_map) : "memory");
+  if (warp == WARP_TMA_B && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&b_map) : "memory");
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();   // peers must see initialised barriers before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  const int first_tile = blockIdx.x;
-  const int tile_step = gridDim.x;
+  // tile schedule: cluster k sweeps tiles CS * (k + i * n_clusters) + rank; the trip count is cluster-uniform
+  // (tiles past the end are all-zero boxes whose results are never stored)
+  const int cta_rank = CS > 1 ? (int)cluster_ctarank() : 0;
+  const int first_tile = (CS > 1 ? (int)cluster_id_x() * CS : (int)blockIdx.x) + cta_rank;
+  const int tile_step = CS > 1 ? (int)n_clusters_x() * CS : (int)gridDim.x;
+  const int tile_end = CS > 1 ? p.n_tiles + cta_rank : p.n_tiles;   // (tile - rank) < n_tiles for every CTA alike
   const int panel_bytes = p.ncols * 128;
+  const uint16_t cluster_mask = (uint16_t)((1u << CS) - 1u);
 
-  if (warp == WARP_TMA) {
-    // ============================== TMA producer ==============================
-    // (whole warp runs the loop; one elected lane issues the copies)
-    int st = 0;
-    uint32_t st_phase = 0;   // parity of the number of completed passes over the stage ring
-    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step) {
+  if (warp == WARP_TMA_G) {
+    // ============================== genotype producer ==============================
+    int gs = 0;
+    uint32_t g_phase = 0;   // parity of the number of completed passes over the ring
+    for (int tile = first_tile; tile < tile_end; tile += tile_step) {
       for (int ch = 0; ch < p.n_chunks; ++ch) {
-        mbar_wait(EMPTY(st), st_phase ^ 1);
-        const uint32_t sbase = smem0 + st * p.stage_bytes;
+        mbar_wait(GEMPTY(gs), g_phase ^ 1);
+        const uint32_t sbase = smem0 + gs * p.gstage_bytes;
         if (elect_one()) {
-          mbar_arrive_expect_tx(FULL(st), (uint32_t)(GENO_BYTES + SLOTS * panel_bytes + p.mask_bytes));
-          tma_load_2d(&geno_map, FULL(st), sbase, ch * 128, tile * TILE_M);
-#pragma unroll
-          for (int s = 0; s < SLOTS; ++s)
-            tma_load_2d(&b_map, FULL(st), sbase + GENO_BYTES + s * panel_bytes, ch * CHUNK + s * SLOT, 0);
+          mbar_arrive_expect_tx(GFULL(gs), (uint32_t)(GENO_BYTES + p.mask_bytes));
+          tma_load_2d(&geno_map, GFULL(gs), sbase, ch * 128, tile * TILE_M);
           if (p.mask_bytes) {
             for (int g = 0; g < n_groups; ++g)
-              bulk_load_1d(sbase + GENO_BYTES + SLOTS * panel_bytes + g * 128, p.g[g].mask_hi + ch * (CHUNK / 16), 128,
-                           FULL(st));
+              bulk_load_1d(sbase + GENO_BYTES + g * 128, p.g[g].mask_hi + ch * (CHUNK / 16), 128, GFULL(gs));
           }
         }
         __syncwarp();
-        if (++st == p.n_stages) { st = 0; st_phase ^= 1; }
+        if (++gs == p.n_gstages) { gs = 0; g_phase ^= 1; }
+      }
+    }
+  } else if (warp == WARP_TMA_B) {
+    // ============================== basis-panel producer ==============================
+    int bs = 0;
+    uint32_t b_phase = 0;
+    for (int tile = first_tile; tile < tile_end; tile += tile_step) {
+      for (int ch = 0; ch < p.n_chunks; ++ch) {
+        mbar_wait(BEMPTY(bs), b_phase ^ 1);
+        const uint32_t sbase = bring0 + bs * p.bstage_bytes;
+        if (elect_one()) {
+#if LRR_ABL_NO_BPANEL
+          mbar_arrive(BFULL(bs));
+#else
+          mbar_arrive_expect_tx(BFULL(bs), (uint32_t)(SLOTS * panel_bytes));
+          if (CS == 1) {
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s)
+              tma_load_2d(&b_map, BFULL(bs), sbase + s * panel_bytes, ch * CHUNK + s * SLOT, 0);
+          } else {
+#pragma unroll
+            for (int k = 0; k < SLOTS / CS; ++k) {
+              const int s = cta_rank * (SLOTS / CS) + k;
+              tma_load_2d_mc(&b_map, BFULL(bs), sbase + s * panel_bytes, ch * CHUNK + s * SLOT, 0, cluster_mask);
+            }
+          }
+#endif
+        }
+        __syncwarp();
+        if (++bs == p.n_bstages) { bs = 0; b_phase ^= 1; }
       }
     }
   } else if (warp == WARP_MMA) {
     // ============================== MMA issuer ==============================
     // (whole warp runs the loop in uniform control flow; one elected lane issues tcgen05.mma / commit)
     const uint32_t idesc = make_idesc(p.ncols);
-    int st = 0;
-    uint32_t st_phase = 0;
-    uint32_t use_bits = 0;   // parity of the number of times each ring slot has been consumed
+    int bs = 0;
+    uint32_t b_phase = 0;
+    int rg = 0;              // ring group of the next group instance (instances are numbered across tiles)
+    uint32_t rg_par = 0;     // parity of the number of completed passes over the ring groups
     uint32_t tile_i = 0;
-    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++tile_i) {
+    for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
       const bool two_plane = tile_has_missing(p, tile);
-      const int depth = two_plane ? p.depth_tp : p.depth;
+      const int gsl = two_plane ? 2 : 4;   // slots per group
       mbar_wait(DEMPTY, (tile_i & 1) ^ 1);   // the previous tile's accumulators have been read out
       tc_fence_after();
-      int ri = 0;
       for (int ch = 0; ch < p.n_chunks; ++ch) {
-        mbar_wait(FULL(st), st_phase);
-        const uint32_t b_base = smem0 + st * p.stage_bytes + GENO_BYTES;
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-          mbar_wait(AFULL(ri), (use_bits >> ri) & 1u);
-          use_bits ^= 1u << ri;
+#if !LRR_ABL_MMA_NOWAIT
+        mbar_wait(BFULL(bs), b_phase);
+#endif
+        const uint32_t b_base = bring0 + bs * p.bstage_bytes;
+        for (int s0 = 0; s0 < SLOTS; s0 += gsl) {
+          mbar_wait(AFULL(rg), rg_par);
           tc_fence_after();
-          const uint64_t bdesc = make_b_desc(b_base + s * panel_bytes);
-          const uint32_t a_c = tmem + p.ring_base + ri * 32;
-          const uint32_t a_m = a_c + depth * 32;
+          const uint32_t a_g = tmem + p.ring_base + rg * GROUP_COLS;
           if (elect_one()) {
+            if (!two_plane) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t acc = (ch | s | j) ? 1u : 0u;
-              mma_i8_ts(tmem, a_c + j * 8, bdesc + (uint64_t)(j * 2), idesc, acc);
-              if (two_plane) mma_i8_ts(tmem + p.ncols, a_m + j * 8, bdesc + (uint64_t)(j * 2), idesc, acc);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t bdesc = make_b_desc(b_base + k * panel_bytes);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  mma_i8_ts(tmem, a_g + k * 32 + j * 8, bdesc + (uint64_t)(j * 2), idesc, (ch | k | j) ? 1u : 0u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const uint64_t bdesc = make_b_desc(b_base + (s0 + k) * panel_bytes);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t acc = (ch | s0 | k | j) ? 1u : 0u;
+                  mma_i8_ts(tmem, a_g + k * 32 + j * 8, bdesc + (uint64_t)(j * 2), idesc, acc);
+                  mma_i8_ts(tmem + p.ncols, a_g + 64 + k * 32 + j * 8, bdesc + (uint64_t)(j * 2), idesc, acc);
+                }
+              }
             }
-            tc_commit(AEMPTY(ri));
-            if (s == SLOTS - 1) tc_commit(EMPTY(st));
+            tc_commit(AEMPTY(rg));
+            if (s0 + gsl == SLOTS) {
+              if (CS == 1) tc_commit(BEMPTY(bs));
+              else tc_commit_mc(BEMPTY(bs), cluster_mask);   // the panels of this stage may be overwritten by any peer
+            }
           }
           __syncwarp();
-          if (++ri == depth) ri = 0;
+          if (++rg == p.ring_groups) { rg = 0; rg_par ^= 1; }
         }
-        if (++st == p.n_stages) { st = 0; st_phase ^= 1; }
+        if (++bs == p.n_bstages) { bs = 0; b_phase ^= 1; }
       }
       if (elect_one()) tc_commit(DFULL);
       __syncwarp();
@@ -366,14 +481,14 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
     const uint32_t swz = (uint32_t)(row & 7);
     const uint32_t ld0 = row_off + (((uint32_t)(2 * s) ^ swz) << 4);       // 16-byte chunks 2s, 2s+1 (swizzled)
     const uint32_t ld1 = row_off + (((uint32_t)(2 * s + 1) ^ swz) << 4);
-    int st = 0;
-    uint32_t st_phase = 0;
-    uint32_t use_bits = 0;           // parity of the number of times each ring slot has been produced
+    int gs = 0;
+    uint32_t g_phase = 0;
+    int rg0 = 0;                     // ring group of the next chunk's first group instance (see the MMA warp)
+    uint32_t rg0_par = 0;
     uint32_t tile_i = 0;
     bool prev_two_plane = false;
-    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++tile_i) {
+    for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
       const bool two_plane = tile_has_missing(p, tile);
-      const int depth = two_plane ? p.depth_tp : p.depth;
       if (tile_i > 0 && two_plane != prev_two_plane) {
         // the ring is laid out differently: wait until every MMA of the previous tile has retired
         mbar_wait(DFULL, (tile_i - 1) & 1);
@@ -383,12 +498,15 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
       int n2[NG ? NG : MAX_GROUPS];
 #pragma unroll
       for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) n2[g] = 0;
-      int ri = s;   // ring slot of this warp's next production (depth is a multiple of 4)
+      int pend_rg = -1;    // TMEM store issued but not yet published to the MMA warp
+      // one-plane: the 4 slots of a chunk form one group; two-plane: slots {0,1} and {2,3} form two groups
+      const int hh = two_plane ? (s >> 1) : 0;                   // which group of the chunk this warp feeds
+      const uint32_t in_group = two_plane ? (uint32_t)(s & 1) * 32u : (uint32_t)s * 32u;
 
       for (int ch = 0; ch < p.n_chunks; ++ch) {
-        mbar_wait(FULL(st), st_phase);
-        const uint32_t sbase = smem0 + st * p.stage_bytes;
-        const uint32_t mrow = sbase + GENO_BYTES + SLOTS * panel_bytes;
+        mbar_wait(GFULL(gs), g_phase);
+        const uint32_t sbase = smem0 + gs * p.gstage_bytes;
+        const uint32_t mrow = sbase + GENO_BYTES;
         // packed bytes of samples [128 s, 128 s + 128) of this row
         const uint4 w0 = lds128(sbase + ld0);
         const uint4 w1 = lds128(sbase + ld1);
@@ -396,10 +514,14 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
         uint32_t rc[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+#if !LRR_ABL_NO_UNPACK
           rc[4 * i + 0] = w[i] & 0x03030303u;
           rc[4 * i + 1] = shr<2>(w[i]) & 0x03030303u;
           rc[4 * i + 2] = shr<4>(w[i]) & 0x03030303u;
           rc[4 * i + 3] = shr<6>(w[i]) & 0x03030303u;
+#else
+          rc[4 * i + 0] = w[i]; rc[4 * i + 1] = w[i]; rc[4 * i + 2] = w[i]; rc[4 * i + 3] = w[i];
+#endif
         }
         // exact hom-alt counts per group (code 2: high bit set, low bit clear), for x.x = n1 + 4 n2
 #pragma unroll
@@ -429,13 +551,8 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
             n2[g] += acc;
           }
         }
-        mbar_wait(AEMPTY(ri), ((use_bits >> ri) & 1u) ^ 1u);
-        use_bits ^= 1u << ri;
-        tc_fence_after();
-        const uint32_t a_c = tmem + lane_addr + p.ring_base + ri * 32;
-        tmem_st32(a_c, rc);
+        uint32_t rm[32];
         if (two_plane) {
-          uint32_t rm[32];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const uint32_t mw = w[i] & (w[i] >> 1);   // bit 2f set iff field f is code 3
@@ -444,18 +561,43 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
             rm[4 * i + 2] = shr<4>(mw) & 0x01010101u;
             rm[4 * i + 3] = shr<6>(mw) & 0x01010101u;
           }
-          tmem_st32(a_c + depth * 32, rm);
         }
+        // the genotype stage is in registers now: hand it back to the TMA producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(GEMPTY(gs));
+        // retire the previous chunk's TMEM store only now: its latency hid behind this chunk's unpack arithmetic
+        if (pend_rg >= 0) {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane < (two_plane ? 2 : 1)) mbar_arrive(AFULL(pend_rg));
+        }
+        // this warp's group instance: rg0 (+1 for the second group of a two-plane chunk)
+        int rg = rg0 + hh;
+        uint32_t rg_par = rg0_par;
+        if (rg >= p.ring_groups) { rg -= p.ring_groups; rg_par ^= 1; }
+        mbar_wait(AEMPTY(rg), rg_par ^ 1u);
+        tc_fence_after();
+        const uint32_t a_c = tmem + lane_addr + p.ring_base + rg * GROUP_COLS + in_group;
+#if !LRR_ABL_NO_STTM
+        tmem_st32(a_c, rc);
+        if (two_plane) tmem_st32(a_c + 64, rm);
+#else
+        { uint32_t x = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x ^= rc[i];
+          if (x == 0x12345678u) n2[0] += 1; }
+#endif
+        pend_rg = rg;
+        rg0 += two_plane ? 2 : 1;
+        if (rg0 >= p.ring_groups) { rg0 -= p.ring_groups; rg0_par ^= 1; }
+        if (++gs == p.n_gstages) { gs = 0; g_phase ^= 1; }
+      }
+      if (pend_rg >= 0) {   // flush the last chunk of the tile
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(AFULL(ri));
-          mbar_arrive(EMPTY(st));
-        }
-        ri += SLOTS;
-        if (ri >= depth) ri -= depth;
-        if (++st == p.n_stages) { st = 0; st_phase ^= 1; }
+        if (lane < (two_plane ? 2 : 1)) mbar_arrive(AFULL(pend_rg));
       }
 
       // ------------------------------ per-tile epilogue ------------------------------
@@ -537,7 +679,9 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
     }
   }
 
+  tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();   // no CTA may exit while a peer can still multicast into it
   if (warp == WARP_MMA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
@@ -595,13 +739,14 @@ struct State {
   std::string why;
   EncodeTiledFn encode = nullptr;
   int ncols = 0;
-  int n_stages = 0;
+  int n_gstages = 0, n_bstages = 0, gstage_bytes = 0, bstage_bytes = 0;
   int smem_bytes = 0;
   int8_t* d_bq = nullptr;
   double* d_colscale = nullptr;   // concatenated per group
   unsigned long long* d_colmax = nullptr;
   uint32_t* d_mask_hi = nullptr;  // [G][ns_pad/16] group masks shifted to the high bit of each field
-  int ring_base = 0, depth = 0, depth_tp = 0, stage_bytes = 0, mask_bytes = 0;
+  int ring_base = 0, ring_groups = 0, mask_bytes = 0;
+  int cluster = 2;
   std::vector<int> col_off, scale_off;
   CUtensorMap b_map;
   bool attr_set = false;
@@ -657,7 +802,7 @@ static int prepare(Ctx* c) {
   }
   const size_t G = c->groups.size();
   if (G == 0 || G > (size_t)MAX_GROUPS) {
-    s->why = "tensor-core kernel supports 1..8 groups";
+    s->why = "tensor-core kernel supports 1..4 groups";
     return LRR_OK;
   }
   int cols = 0, nscale = 0;
@@ -702,33 +847,44 @@ static int prepare(Ctx* c) {
     s->why = "cuTensorMapEncodeTiled failed for the basis panels";
     return LRR_OK;
   }
-  // shared memory: stages of (genotype tile + 4 basis panels [+ group masks]) + barriers + 1 KB alignment slack
+  // shared memory: genotype ring (16 KB [+ group masks] per stage) + basis-panel ring + barriers + 1 KB slack
   s->mask_bytes = any_masked ? (int)G * 128 : 0;
-  const int stage_bytes = (GENO_BYTES + SLOTS * s->ncols * 128 + s->mask_bytes + 1023) / 1024 * 1024;
-  s->stage_bytes = stage_bytes;
+  s->gstage_bytes = (GENO_BYTES + s->mask_bytes + 1023) / 1024 * 1024;
+  s->bstage_bytes = SLOTS * s->ncols * 128;
   s->ring_base = (2 * s->ncols + 31) / 32 * 32;
-  s->depth = (512 - s->ring_base) / 32;
-  if (s->depth > MAX_RING) s->depth = MAX_RING;
-  s->depth &= ~3;   // every unpack warp keeps its own slot-of-chunk: ring depths are multiples of 4
-  s->depth_tp = (s->depth / 2) & ~3;
+  s->ring_groups = (512 - s->ring_base) / GROUP_COLS;
+  if (s->ring_groups > MAX_RING) s->ring_groups = MAX_RING;
   const int budget = 227 * 1024 - (int)sizeof(Barriers) - 1024;
-  int stages = budget / stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < 2) {
-    s->why = "not enough shared memory for two pipeline stages";
+  int bst = 3;
+  if (const char* e = getenv("LRR_TC_BSTAGES")) bst = atoi(e);
+  if (bst > MAX_BSTAGES) bst = MAX_BSTAGES;
+  while (bst > 2 && budget - bst * s->bstage_bytes < 3 * s->gstage_bytes) --bst;
+  int gst = (budget - bst * s->bstage_bytes) / s->gstage_bytes;
+  if (gst > MAX_GSTAGES) gst = MAX_GSTAGES;
+  if (const char* e = getenv("LRR_TC_GSTAGES")) { const int v = atoi(e); if (v >= 2 && v < gst) gst = v; }
+  if (bst < 2 || gst < 2) {
+    s->why = "not enough shared memory for the genotype / basis-panel rings";
     return LRR_OK;
   }
-  s->n_stages = stages;
-  s->smem_bytes = stages * stage_bytes + (int)sizeof(Barriers) + 1024;
-  if (s->depth < 4 || s->depth_tp < 4) {
+  s->n_gstages = gst;
+  s->n_bstages = bst;
+  s->smem_bytes = gst * s->gstage_bytes + bst * s->bstage_bytes + (int)sizeof(Barriers) + 1024;
+  if (s->ring_groups < 2) {
     s->why = "not enough tensor memory for the A ring";
     return LRR_OK;
   }
   if (!s->attr_set) {
-    LRR_CUDA(c, cudaFuncSetAttribute(tc_sweep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    LRR_CUDA(c, cudaFuncSetAttribute(tc_sweep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    LRR_CUDA(c, cudaFuncSetAttribute(tc_sweep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define LRR_SET_SMEM(NG_, CS_) \
+  LRR_CUDA(c, cudaFuncSetAttribute(tc_sweep_kernel<NG_, CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+    LRR_SET_SMEM(0, 1); LRR_SET_SMEM(1, 1); LRR_SET_SMEM(2, 1);
+    LRR_SET_SMEM(0, 2); LRR_SET_SMEM(1, 2); LRR_SET_SMEM(2, 2);
+    LRR_SET_SMEM(0, 4); LRR_SET_SMEM(1, 4); LRR_SET_SMEM(2, 4);
+#undef LRR_SET_SMEM
     s->attr_set = true;
+  }
+  if (const char* e = getenv("LRR_TC_CLUSTER")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) s->cluster = v;
   }
   s->usable = true;
   s->why.clear();
@@ -781,12 +937,13 @@ int launch_tc_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags,
   p.n_tiles = (int)((M + TILE_M - 1) / TILE_M);
   p.n_chunks = (int)(stride / 128);
   p.ncols = s->ncols;
-  p.n_stages = s->n_stages;
+  p.n_gstages = s->n_gstages;
+  p.n_bstages = s->n_bstages;
   p.n_groups = (int)c->groups.size();
   p.ring_base = s->ring_base;
-  p.depth = s->depth;
-  p.depth_tp = s->depth_tp;
-  p.stage_bytes = s->stage_bytes;
+  p.ring_groups = s->ring_groups;
+  p.gstage_bytes = s->gstage_bytes;
+  p.bstage_bytes = s->bstage_bytes;
   p.mask_bytes = s->mask_bytes;
   p.row_flags = d_row_flags;
   for (int g = 0; g < p.n_groups; ++g) {
@@ -800,13 +957,39 @@ int launch_tc_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags,
     p.g[g].mask_hi = s->d_mask_hi + (int64_t)g * (gr.ns_pad / 16);
     p.g[g].mask_all = ((int64_t)gr.n == c->n_samples_total) ? 1 : 0;
   }
-  const int grid = p.n_tiles < c->sm_count ? p.n_tiles : c->sm_count;
-  if (p.n_groups == 1)
-    tc_sweep_kernel<1><<<grid, THREADS, s->smem_bytes, st>>>(geno_map, s->b_map, p);
-  else if (p.n_groups == 2)
-    tc_sweep_kernel<2><<<grid, THREADS, s->smem_bytes, st>>>(geno_map, s->b_map, p);
-  else
-    tc_sweep_kernel<0><<<grid, THREADS, s->smem_bytes, st>>>(geno_map, s->b_map, p);
+  // cluster size: LRR_TC_CLUSTER env (1, 2, 4) overrides the default of 2
+  int cs = s->cluster;
+  if (p.n_tiles < 2 * cs) cs = 1;
+  void* kfn = nullptr;
+#define LRR_PICK(NG_)                                                                       \
+  (cs == 4 ? (void*)tc_sweep_kernel<NG_, 4> : cs == 2 ? (void*)tc_sweep_kernel<NG_, 2> : (void*)tc_sweep_kernel<NG_, 1>)
+  kfn = p.n_groups == 1 ? LRR_PICK(1) : p.n_groups == 2 ? LRR_PICK(2) : LRR_PICK(0);
+#undef LRR_PICK
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = (size_t)s->smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = c->sm_count / cs;
+  if (cs > 1) {
+    cfg.gridDim = dim3((unsigned)(c->sm_count / cs * cs));
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, kfn, &cfg) == cudaSuccess && nc > 0) max_clusters = nc;
+    else cudaGetLastError();
+  }
+  int n_cta = max_clusters * cs;
+  const int need = (p.n_tiles + cs - 1) / cs * cs;
+  if (n_cta > need) n_cta = need;
+  cfg.gridDim = dim3((unsigned)n_cta);
+  void* args[3] = {(void*)&geno_map, (void*)&s->b_map, (void*)&p};
+  LRR_CUDA(c, cudaLaunchKernelExC(&cfg, kfn, args));
   c->launches++;
   LRR_CUDA(c, cudaGetLastError());
   return LRR_OK;
