@@ -41,6 +41,12 @@ constexpr int THREADS = 19 * 32;
 #ifndef LRR_ABL_NO_MMA
 #define LRR_ABL_NO_MMA 0
 #endif
+#ifndef LRR_ABL_MMA_J
+#define LRR_ABL_MMA_J 4      // MMAs issued per slot (4 = all)
+#endif
+#ifndef LRR_ABL_MMA_N
+#define LRR_ABL_MMA_N 0      // override the MMA N dimension (0 = ncols)
+#endif
 #ifndef LRR_ABL_MMA_NOWAIT
 #define LRR_ABL_MMA_NOWAIT 0
 #endif
@@ -62,7 +68,12 @@ constexpr int MAX_GSTAGES = 10;        // genotype ring (16 KB per stage)
 constexpr int MAX_BSTAGES = 4;         // basis-panel ring (4 * ncols * 128 B per stage)
 constexpr int MAX_RING = 4;            // A ring groups (GROUP_COLS TMEM columns each)
 constexpr int GROUP_COLS = 128;        // one-plane: 4 slots of plane c; two-plane: 2 slots of plane c + 2 of plane m
-constexpr int N_SLICES = 6;            // digits per basis column (48-bit fixed point)
+// Balanced base-256 digits per basis column.  The residualised phenotype columns feed beta directly and get 48
+// bits (error 2^-47 of the column max, the float64 roundoff class of the reference's own dgemm); the centred
+// covariate columns only enter through |Q^T x|^2 and the y_transpose_x reconstruction, where 32 bits already
+// leave a relative error below 1e-10 (DESIGN.md "precision").
+constexpr int N_SLICES_Y = 6;
+constexpr int N_SLICES_Q = 4;
 // TMEM column map (512 columns x 128 lanes x 32 bit), ncols = digit columns padded to 16:
 //   [0, ncols)            accumulators of plane c (raw call code)
 //   [ncols, 2 ncols)      accumulators of plane m (missing indicator), two-plane tiles only
@@ -74,6 +85,7 @@ constexpr int N_SLICES = 6;            // digits per basis column (48-bit fixed 
 struct GroupMeta {
   int col_off;        // first digit column of this group in B
   int C;              // dot-product columns (Kd + P)
+  int Kd;             // of which covariate columns (N_SLICES_Q digits each; the rest have N_SLICES_Y)
   int n;              // complete samples
   int mask_all;       // every stored sample is in the group: no masking needed for the hom-alt count
   int32_t* counts;    // [M][4]
@@ -262,6 +274,9 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return d;
 }
 
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
+
 struct Barriers {
   uint64_t gfull[MAX_GSTAGES];   // genotype stage filled by TMA
   uint64_t gempty[MAX_GSTAGES];  // genotype stage read out by the 16 unpack warps
@@ -416,7 +431,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
   } else if (warp == WARP_MMA) {
     // ============================== MMA issuer ==============================
     // (whole warp runs the loop in uniform control flow; one elected lane issues tcgen05.mma / commit)
-    const uint32_t idesc = make_idesc(p.ncols);
+    const uint32_t idesc = make_idesc(LRR_ABL_MMA_N ? LRR_ABL_MMA_N : p.ncols);
     int bs = 0;
     uint32_t b_phase = 0;
     int rg = 0;              // ring group of the next group instance (instances are numbered across tiles)
@@ -442,7 +457,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
               for (int k = 0; k < 4; ++k) {
                 const uint64_t bdesc = make_b_desc(b_base + k * panel_bytes);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < LRR_ABL_MMA_J; ++j)
                   mma_i8_ts(tmem, a_g + k * 32 + j * 8, bdesc + (uint64_t)(j * 2), idesc, (ch | k | j) ? 1u : 0u);
               }
             } else {
@@ -481,44 +496,57 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
     const uint32_t swz = (uint32_t)(row & 7);
     const uint32_t ld0 = row_off + (((uint32_t)(2 * s) ^ swz) << 4);       // 16-byte chunks 2s, 2s+1 (swizzled)
     const uint32_t ld1 = row_off + (((uint32_t)(2 * s + 1) ^ swz) << 4);
-    int gs = 0;
+    uint32_t gaddr = smem0;          // shared address of the current genotype stage
+    uint32_t gbar = GFULL(0);        // its "full" barrier ("empty" is MAX_GSTAGES * 8 bytes further)
+    const uint32_t gaddr_end = smem0 + p.n_gstages * p.gstage_bytes;
     uint32_t g_phase = 0;
     int rg0 = 0;                     // ring group of the next chunk's first group instance (see the MMA warp)
     uint32_t rg0_par = 0;
     uint32_t tile_i = 0;
     bool prev_two_plane = false;
-    for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
-      const bool two_plane = tile_has_missing(p, tile);
-      if (tile_i > 0 && two_plane != prev_two_plane) {
-        // the ring is laid out differently: wait until every MMA of the previous tile has retired
-        mbar_wait(DFULL, (tile_i - 1) & 1);
-        tc_fence_after();
-      }
-      prev_two_plane = two_plane;
-      int n2[NG ? NG : MAX_GROUPS];
-#pragma unroll
-      for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) n2[g] = 0;
-      int pend_rg = -1;    // TMEM store issued but not yet published to the MMA warp
-      // one-plane: the 4 slots of a chunk form one group; two-plane: slots {0,1} and {2,3} form two groups
-      const int hh = two_plane ? (s >> 1) : 0;                   // which group of the chunk this warp feeds
-      const uint32_t in_group = two_plane ? (uint32_t)(s & 1) * 32u : (uint32_t)s * 32u;
+    const int ring_groups = p.ring_groups;
+    const uint32_t a_ring = tmem + lane_addr + p.ring_base;
+    int n2[NG ? NG : MAX_GROUPS];
 
+    // The chunk loop of one tile, specialised at compile time on the tile's mode (TP: two planes, the tile has
+    // missing calls) and on whether any group needs its sample mask for the hom-alt count (MA: none does).
+    auto run_chunks = [&](auto tp_tag, auto ma_tag) {
+      constexpr bool TP = decltype(tp_tag)::value;
+      constexpr bool MA = decltype(ma_tag)::value;
+      // one-plane: the 4 slots of a chunk form one group; two-plane: slots {0,1} and {2,3} form two groups
+      const int hh = TP ? (s >> 1) : 0;                   // which group of the chunk this warp feeds
+      const uint32_t in_group = TP ? (uint32_t)(s & 1) * 32u : (uint32_t)s * 32u;
+      int pend_rg = -1;    // TMEM store issued but not yet published to the MMA warp
       for (int ch = 0; ch < p.n_chunks; ++ch) {
-        mbar_wait(GFULL(gs), g_phase);
-        const uint32_t sbase = smem0 + gs * p.gstage_bytes;
-        const uint32_t mrow = sbase + GENO_BYTES;
+        mbar_wait(gbar, g_phase);
         // packed bytes of samples [128 s, 128 s + 128) of this row
-        const uint4 w0 = lds128(sbase + ld0);
-        const uint4 w1 = lds128(sbase + ld1);
+        const uint4 w0 = lds128(gaddr + ld0);
+        const uint4 w1 = lds128(gaddr + ld1);
         const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        uint32_t mm[NG ? NG : MAX_GROUPS][8];
+        if (!MA) {
+#pragma unroll
+          for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
+            if (NG || g < n_groups) {
+              const uint4 m0 = lds128(gaddr + GENO_BYTES + g * 128 + s * 32);
+              const uint4 m1 = lds128(gaddr + GENO_BYTES + g * 128 + s * 32 + 16);
+              mm[g][0] = m0.x; mm[g][1] = m0.y; mm[g][2] = m0.z; mm[g][3] = m0.w;
+              mm[g][4] = m1.x; mm[g][5] = m1.y; mm[g][6] = m1.z; mm[g][7] = m1.w;
+            }
+          }
+        }
+        // 2-bit fields -> bytes.  Fields at bit offsets 0 and 4 of every byte keep their value c; fields at
+        // offsets 2 and 6 are left in place (value 4c) -- their basis rows were quantised as v/4 -- so a
+        // 16-call word costs one shift and four masks.
         uint32_t rc[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
 #if !LRR_ABL_NO_UNPACK
+          const uint32_t t = shr<4>(w[i]);
           rc[4 * i + 0] = w[i] & 0x03030303u;
-          rc[4 * i + 1] = shr<2>(w[i]) & 0x03030303u;
-          rc[4 * i + 2] = shr<4>(w[i]) & 0x03030303u;
-          rc[4 * i + 3] = shr<6>(w[i]) & 0x03030303u;
+          rc[4 * i + 1] = w[i] & 0x0C0C0C0Cu;
+          rc[4 * i + 2] = t & 0x03030303u;
+          rc[4 * i + 3] = t & 0x0C0C0C0Cu;
 #else
           rc[4 * i + 0] = w[i]; rc[4 * i + 1] = w[i]; rc[4 * i + 2] = w[i]; rc[4 * i + 3] = w[i];
 #endif
@@ -528,60 +556,46 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
         for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
           if (NG || g < n_groups) {
             int acc = 0;
-            if (p.g[g].mask_all) {
-              if (two_plane) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc += __popc(w[i] & ~(w[i] << 1) & 0xAAAAAAAAu);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc += __popc(w[i] & 0xAAAAAAAAu);
-              }
-            } else {
-              const uint4 m0 = lds128(mrow + g * 128 + s * 32);
-              const uint4 m1 = lds128(mrow + g * 128 + s * 32 + 16);
-              const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-              if (two_plane) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc += __popc(w[i] & ~(w[i] << 1) & mm[i]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc += __popc(w[i] & mm[i]);
-              }
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t m = MA ? 0xAAAAAAAAu : mm[g][i];
+              acc += TP ? __popc(w[i] & ~(w[i] << 1) & m) : __popc(w[i] & m);
             }
             n2[g] += acc;
           }
         }
-        uint32_t rm[32];
-        if (two_plane) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t mw = w[i] & (w[i] >> 1);   // bit 2f set iff field f is code 3
-            rm[4 * i + 0] = mw & 0x01010101u;
-            rm[4 * i + 1] = shr<2>(mw) & 0x01010101u;
-            rm[4 * i + 2] = shr<4>(mw) & 0x01010101u;
-            rm[4 * i + 3] = shr<6>(mw) & 0x01010101u;
-          }
-        }
         // the genotype stage is in registers now: hand it back to the TMA producer
         __syncwarp();
-        if (lane == 0) mbar_arrive(GEMPTY(gs));
+        if (lane == 0) mbar_arrive(gbar + 8u * MAX_GSTAGES);
         // retire the previous chunk's TMEM store only now: its latency hid behind this chunk's unpack arithmetic
         if (pend_rg >= 0) {
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane < (two_plane ? 2 : 1)) mbar_arrive(AFULL(pend_rg));
+          if (lane < (TP ? 2 : 1)) mbar_arrive(AFULL(pend_rg));
         }
         // this warp's group instance: rg0 (+1 for the second group of a two-plane chunk)
         int rg = rg0 + hh;
         uint32_t rg_par = rg0_par;
-        if (rg >= p.ring_groups) { rg -= p.ring_groups; rg_par ^= 1; }
+        if (rg >= ring_groups) { rg -= ring_groups; rg_par ^= 1; }
         mbar_wait(AEMPTY(rg), rg_par ^ 1u);
         tc_fence_after();
-        const uint32_t a_c = tmem + lane_addr + p.ring_base + rg * GROUP_COLS + in_group;
+        const uint32_t a_c = a_ring + rg * GROUP_COLS + in_group;
 #if !LRR_ABL_NO_STTM
         tmem_st32(a_c, rc);
-        if (two_plane) tmem_st32(a_c + 64, rm);
+        if (TP) {
+          // missing-indicator plane, same byte scaling as plane c (1 or 4)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t mw = w[i] & (w[i] >> 1);   // bit 2f set iff field f is code 3
+            const uint32_t t = shr<4>(mw);
+            rc[4 * i + 0] = mw & 0x01010101u;
+            rc[4 * i + 1] = mw & 0x04040404u;
+            rc[4 * i + 2] = t & 0x01010101u;
+            rc[4 * i + 3] = t & 0x04040404u;
+          }
+          tmem_st32(a_c + 64, rc);
+        }
 #else
         { uint32_t x = 0;
 #pragma unroll
@@ -589,15 +603,34 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
           if (x == 0x12345678u) n2[0] += 1; }
 #endif
         pend_rg = rg;
-        rg0 += two_plane ? 2 : 1;
-        if (rg0 >= p.ring_groups) { rg0 -= p.ring_groups; rg0_par ^= 1; }
-        if (++gs == p.n_gstages) { gs = 0; g_phase ^= 1; }
+        rg0 += TP ? 2 : 1;
+        if (rg0 >= ring_groups) { rg0 -= ring_groups; rg0_par ^= 1; }
+        gaddr += p.gstage_bytes;
+        gbar += 8u;
+        if (gaddr == gaddr_end) { gaddr = smem0; gbar = GFULL(0); g_phase ^= 1; }
       }
       if (pend_rg >= 0) {   // flush the last chunk of the tile
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane < (two_plane ? 2 : 1)) mbar_arrive(AFULL(pend_rg));
+        if (lane < (TP ? 2 : 1)) mbar_arrive(AFULL(pend_rg));
+      }
+    };
+
+    for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
+      const bool two_plane = tile_has_missing(p, tile);
+      if (tile_i > 0 && two_plane != prev_two_plane) {
+        // the ring is laid out differently: wait until every MMA of the previous tile has retired
+        mbar_wait(DFULL, (tile_i - 1) & 1);
+        tc_fence_after();
+      }
+      prev_two_plane = two_plane;
+#pragma unroll
+      for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) n2[g] = 0;
+      if (two_plane) {
+        if (p.mask_bytes == 0) run_chunks(TrueTag{}, TrueTag{}); else run_chunks(TrueTag{}, FalseTag{});
+      } else {
+        if (p.mask_bytes == 0) run_chunks(FalseTag{}, TrueTag{}); else run_chunks(FalseTag{}, FalseTag{});
       }
 
       // ------------------------------ per-tile epilogue ------------------------------
@@ -617,8 +650,9 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
           if (!(NG || g < n_groups)) continue;
           const GroupMeta& G = p.g[g];
           const int n2g = n2[g] + bars->n2_xchg[0][g][row] + bars->n2_xchg[1][g][row] + bars->n2_xchg[2][g][row];
-          // the group's columns: C x N_SLICES digit columns then one "ones" column
-          const int ones_col = G.col_off + G.C * N_SLICES;
+          // the group's columns: Kd x N_SLICES_Q then P x N_SLICES_Y digit columns, then one "ones" column
+          const int n_digit_cols = G.Kd * N_SLICES_Q + (G.C - G.Kd) * N_SLICES_Y;
+          const int ones_col = G.col_off + n_digit_cols;
           uint32_t r16[16];
           tmem_ld16(d_c + (ones_col & ~15), r16);
           tmem_wait_ld();
@@ -634,13 +668,16 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
             for (int i = 0; i < 16; ++i)
               if (i == (ones_col & 15)) nm = (int)r16[i];
           }
+          sc >>= 2;                           // the ones column carries 4 per unit (see the quantiser)
+          nm >>= 2;
           const int S = sc - 3 * nm;          // n1 + 2 n2
           const int n1 = S - 2 * n2g;
           const double mean = (double)S / (double)(G.n - nm);
           if (v < p.M) reinterpret_cast<int4*>(G.counts)[v] = make_int4(n1, n2g, nm, 0);
-          // digit columns, 16 TMEM columns at a time
-          const int c_lo = G.col_off, c_hi = G.col_off + G.C * N_SLICES;
+          // digit columns, 16 TMEM columns at a time; (c, sl) walk the columns and their digits
+          const int c_lo = G.col_off, c_hi = ones_col;
           long long hi = 0, lo = 0, mhi = 0, mlo = 0;
+          int c = 0, sl = 0, nd = G.Kd > 0 ? N_SLICES_Q : N_SLICES_Y;
           for (int base = c_lo & ~15; base < c_hi; base += 16) {
             uint32_t dc[16], dm[16];
             tmem_ld16(d_c + base, dc);
@@ -650,8 +687,6 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
             for (int i = 0; i < 16; ++i) {
               const int col = base + i;
               if (col >= c_lo && col < c_hi) {
-                const int rel = col - c_lo;
-                const int c = rel / N_SLICES, sl = rel - c * N_SLICES;
                 const long long dv = (long long)(int)dc[i] - (two_plane ? 3ll * (long long)(int)dm[i] : 0ll);
                 const long long mv = two_plane ? (long long)(int)dm[i] : 0ll;
                 if (sl < 3) {
@@ -661,12 +696,15 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
                   hi += dv * (1ll << (8 * (sl - 3)));
                   mhi += mv * (1ll << (8 * (sl - 3)));
                 }
-                if (sl == N_SLICES - 1) {
+                if (++sl == nd) {
                   const double scale = G.colscale[c];
                   double dot = fma((double)hi, 16777216.0, (double)lo) * scale;
                   if (two_plane && nm > 0) dot += mean * (fma((double)mhi, 16777216.0, (double)mlo) * scale);
                   if (v < p.M) G.dots[v * G.C + c] = dot;
                   hi = lo = mhi = mlo = 0;
+                  sl = 0;
+                  ++c;
+                  nd = c < G.Kd ? N_SLICES_Q : N_SLICES_Y;
                 }
               }
             }
@@ -699,25 +737,28 @@ __global__ void colmax_kernel(const double* __restrict__ basis, int C, int64_t n
   if ((threadIdx.x & 31) == 0) atomicMax(colmax_bits + c, (unsigned long long)__double_as_longlong(m));
 }
 
-__global__ void quantize_kernel(const double* __restrict__ basis, const uint32_t* __restrict__ mask, int C,
+__global__ void quantize_kernel(const double* __restrict__ basis, const uint32_t* __restrict__ mask, int C, int Kd,
                                 int64_t ns_pad, const unsigned long long* __restrict__ colmax_bits, int col_off,
                                 int8_t* __restrict__ bq, double* __restrict__ colscale) {
-  // Imax = 127 * (256^S - 1) / 255 : the largest integer with S balanced digits in [-128, 127]
-  const double imax = 127.0 * ((double)((1ull << (8 * N_SLICES)) - 1ull) / 255.0);
   const int c = blockIdx.y;  // 0..C-1 data columns, C = ones column
+  const int nd = c < Kd ? N_SLICES_Q : N_SLICES_Y;
+  const int first = col_off + (c < Kd ? c * N_SLICES_Q : Kd * N_SLICES_Q + (c - Kd) * N_SLICES_Y);
+  // Imax = 127 * (256^S - 1) / 255 : the largest integer with S balanced digits in [-128, 127]
+  const double imax = 127.0 * ((double)((1ull << (8 * nd)) - 1ull) / 255.0);
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ns_pad; j += (int64_t)gridDim.x * blockDim.x) {
     if (c == C) {
       const uint32_t mw = mask[j >> 4];
-      bq[(int64_t)(col_off + C * N_SLICES) * ns_pad + j] = (int8_t)((mw >> sample_shift((int)(j & 15))) & 1u);
+      // fields at bit offsets 2 / 6 of a byte reach the tensor core as 4c, the others as c (see the unpack warps)
+      const int in_mask = (int)((mw >> sample_shift((int)(j & 15))) & 1u);
+      bq[(int64_t)first * ns_pad + j] = (int8_t)(in_mask * ((j & 4) ? 1 : 4));
       continue;
     }
     const double cm = __longlong_as_double((long long)colmax_bits[c]);
     long long I = 0;
-    if (cm > 0.0) I = __double2ll_rn(basis[(int64_t)c * ns_pad + j] / cm * imax);
-#pragma unroll
-    for (int s = 0; s < N_SLICES; ++s) {
+    if (cm > 0.0) I = __double2ll_rn(basis[(int64_t)c * ns_pad + j] / cm * ((j & 4) ? 0.25 * imax : imax));
+    for (int s = 0; s < nd; ++s) {
       long long d = ((I + 128) & 255) - 128;  // balanced digit in [-128, 127]
-      bq[(int64_t)(col_off + c * N_SLICES + s) * ns_pad + j] = (int8_t)d;
+      bq[(int64_t)(first + s) * ns_pad + j] = (int8_t)d;
       I = (I - d) >> 8;
     }
     if (j == 0) colscale[c] = cm > 0.0 ? cm / imax : 0.0;
@@ -811,7 +852,7 @@ static int prepare(Ctx* c) {
   for (size_t g = 0; g < G; ++g) {
     s->col_off[g] = cols;
     s->scale_off[g] = nscale;
-    cols += c->groups[g].C * N_SLICES + 1;
+    cols += c->groups[g].Kd * N_SLICES_Q + c->groups[g].P * N_SLICES_Y + 1;
     nscale += c->groups[g].C;
   }
   s->ncols = (cols + 15) / 16 * 16;
@@ -837,8 +878,8 @@ static int prepare(Ctx* c) {
     dim3 grid1((unsigned)std::min<int64_t>((ns_pad + 255) / 256, 1024), (unsigned)gr.C);
     colmax_kernel<<<grid1, 256>>>(gr.d_basis, gr.C, ns_pad, s->d_colmax + s->scale_off[g]);
     dim3 grid2((unsigned)std::min<int64_t>((ns_pad + 255) / 256, 1024), (unsigned)(gr.C + 1));
-    quantize_kernel<<<grid2, 256>>>(gr.d_basis, gr.d_mask, gr.C, ns_pad, s->d_colmax + s->scale_off[g], s->col_off[g],
-                                    s->d_bq, s->d_colscale + s->scale_off[g]);
+    quantize_kernel<<<grid2, 256>>>(gr.d_basis, gr.d_mask, gr.C, gr.Kd, ns_pad, s->d_colmax + s->scale_off[g],
+                                    s->col_off[g], s->d_bq, s->d_colscale + s->scale_off[g]);
     c->launches += 2;
   }
   LRR_CUDA(c, cudaGetLastError());
@@ -950,6 +991,7 @@ int launch_tc_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags,
     const Group& gr = c->groups[g];
     p.g[g].col_off = s->col_off[g];
     p.g[g].C = gr.C;
+    p.g[g].Kd = gr.Kd;
     p.g[g].n = gr.n;
     p.g[g].counts = c->d_counts + (int64_t)g * c->reserved_variants * 4;
     p.g[g].dots = c->d_dots + c->dots_offset[g];
