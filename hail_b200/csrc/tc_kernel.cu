@@ -41,6 +41,9 @@ constexpr int THREADS = 19 * 32;
 #ifndef LRR_ABL_NO_MMA
 #define LRR_ABL_NO_MMA 0
 #endif
+#ifndef LRR_ABL_NO_GENO
+#define LRR_ABL_NO_GENO 0    // skip the genotype TMA (barriers still cycle)
+#endif
 #ifndef LRR_ABL_MMA_J
 #define LRR_ABL_MMA_J 4      // MMAs issued per slot (4 = all)
 #endif
@@ -387,8 +390,12 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
         mbar_wait(GEMPTY(gs), g_phase ^ 1);
         const uint32_t sbase = smem0 + gs * p.gstage_bytes;
         if (elect_one()) {
+#if LRR_ABL_NO_GENO
+          mbar_arrive_expect_tx(GFULL(gs), (uint32_t)(p.mask_bytes));
+#else
           mbar_arrive_expect_tx(GFULL(gs), (uint32_t)(GENO_BYTES + p.mask_bytes));
           tma_load_2d(&geno_map, GFULL(gs), sbase, ch * 128, tile * TILE_M);
+#endif
           if (p.mask_bytes) {
             for (int g = 0; g < n_groups; ++g)
               bulk_load_1d(sbase + GENO_BYTES + g * 128, p.g[g].mask_hi + ch * (CHUNK / 16), 128, GFULL(gs));
@@ -430,59 +437,101 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
     }
   } else if (warp == WARP_MMA) {
     // ============================== MMA issuer ==============================
-    // (whole warp runs the loop in uniform control flow; one elected lane issues tcgen05.mma / commit)
+    // The whole warp runs the loop in uniform control flow; one elected lane issues tcgen05.mma / commit.
+    // This warp's serial instruction stream is what paces the kernel, so the steady state of one-plane tiles is
+    // unrolled over the (equal) depths of the basis-panel ring and the A ring: every shared-memory, tensor-memory
+    // and barrier address is then a base plus a compile-time constant and stays on the uniform datapath.
     const uint32_t idesc = make_idesc(LRR_ABL_MMA_N ? LRR_ABL_MMA_N : p.ncols);
     int bs = 0;
     uint32_t b_phase = 0;
     int rg = 0;              // ring group of the next group instance (instances are numbered across tiles)
     uint32_t rg_par = 0;     // parity of the number of completed passes over the ring groups
     uint32_t tile_i = 0;
+    const uint64_t desc0 = make_b_desc(bring0);
+    const uint32_t stage_d = (uint32_t)p.bstage_bytes >> 4;   // descriptor-address units (16 B)
+    const uint32_t panel_d = (uint32_t)panel_bytes >> 4;
+    const uint32_t a_ring = tmem + p.ring_base;
+
+    // one group instance, any mode (alignment, tails, two-plane tiles)
+    auto generic_group = [&](int ch, int s0, bool two_plane, int gsl) {
+      mbar_wait(AFULL(rg), rg_par);
+      tc_fence_after();
+      const uint32_t a_g = a_ring + rg * GROUP_COLS;
+      const uint64_t bd = desc0 + (uint64_t)(bs * stage_d);
+      if (elect_one()) {
+#if !LRR_ABL_NO_MMA
+        if (!two_plane) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < LRR_ABL_MMA_J; ++j)
+              mma_i8_ts(tmem, a_g + k * 32 + j * 8, bd + (uint64_t)(k * panel_d + j * 2), idesc, (ch | k | j) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t acc = (ch | s0 | k | j) ? 1u : 0u;
+              const uint64_t d = bd + (uint64_t)((s0 + k) * panel_d + j * 2);
+              mma_i8_ts(tmem, a_g + k * 32 + j * 8, d, idesc, acc);
+              mma_i8_ts(tmem + p.ncols, a_g + 64 + k * 32 + j * 8, d, idesc, acc);
+            }
+        }
+#endif
+        tc_commit(AEMPTY(rg));
+        if (s0 + gsl == SLOTS) {
+          if (CS == 1) tc_commit(BEMPTY(bs));
+          else tc_commit_mc(BEMPTY(bs), cluster_mask);   // the panels of this stage may be overwritten by any peer
+        }
+      }
+      __syncwarp();
+      if (++rg == p.ring_groups) { rg = 0; rg_par ^= 1; }
+    };
+    auto generic_chunk = [&](int ch, bool two_plane) {
+      const int gsl = two_plane ? 2 : 4;   // slots per group
+      mbar_wait(BFULL(bs), b_phase);
+      for (int s0 = 0; s0 < SLOTS; s0 += gsl) generic_group(ch, s0, two_plane, gsl);
+      if (++bs == p.n_bstages) { bs = 0; b_phase ^= 1; }
+    };
+
+    constexpr int NB = 3;   // unroll depth of the fast path (needs n_bstages == ring_groups == NB)
+    const bool can_unroll = (p.n_bstages == NB) && (p.ring_groups == NB);
     for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
       const bool two_plane = tile_has_missing(p, tile);
-      const int gsl = two_plane ? 2 : 4;   // slots per group
       mbar_wait(DEMPTY, (tile_i & 1) ^ 1);   // the previous tile's accumulators have been read out
       tc_fence_after();
-      for (int ch = 0; ch < p.n_chunks; ++ch) {
-#if !LRR_ABL_MMA_NOWAIT
-        mbar_wait(BFULL(bs), b_phase);
-#endif
-        const uint32_t b_base = bring0 + bs * p.bstage_bytes;
-        for (int s0 = 0; s0 < SLOTS; s0 += gsl) {
-          mbar_wait(AFULL(rg), rg_par);
-          tc_fence_after();
-          const uint32_t a_g = tmem + p.ring_base + rg * GROUP_COLS;
-          if (elect_one()) {
-            if (!two_plane) {
+      int ch = 0;
+      if (!two_plane && can_unroll && bs == rg && b_phase == rg_par) {
+        while (ch < p.n_chunks && bs != 0) generic_chunk(ch++, false);   // align to ring position 0
+        for (; ch + NB <= p.n_chunks; ch += NB) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t bdesc = make_b_desc(b_base + k * panel_bytes);
+          for (int u = 0; u < NB; ++u) {
+            mbar_wait(BFULL(u), b_phase);
+            mbar_wait(AFULL(u), b_phase);
+            tc_fence_after();
+            if (elect_one()) {
+#if !LRR_ABL_NO_MMA
+              const uint32_t a_g = a_ring + u * GROUP_COLS;
+              const uint64_t bd = desc0 + (uint64_t)(u * stage_d);
 #pragma unroll
-                for (int j = 0; j < LRR_ABL_MMA_J; ++j)
-                  mma_i8_ts(tmem, a_g + k * 32 + j * 8, bdesc + (uint64_t)(j * 2), idesc, (ch | k | j) ? 1u : 0u);
-              }
-            } else {
+              for (int k = 0; k < 4; ++k)
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const uint64_t bdesc = make_b_desc(b_base + (s0 + k) * panel_bytes);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint32_t acc = (ch | s0 | k | j) ? 1u : 0u;
-                  mma_i8_ts(tmem, a_g + k * 32 + j * 8, bdesc + (uint64_t)(j * 2), idesc, acc);
-                  mma_i8_ts(tmem + p.ncols, a_g + 64 + k * 32 + j * 8, bdesc + (uint64_t)(j * 2), idesc, acc);
+                for (int j = 0; j < LRR_ABL_MMA_J; ++j) {
+                  const uint32_t acc = (u | k | j) ? 1u : (ch ? 1u : 0u);
+                  mma_i8_ts(tmem, a_g + k * 32 + j * 8, bd + (uint64_t)(k * panel_d + j * 2), idesc, acc);
                 }
-              }
+#endif
+              tc_commit(AEMPTY(u));
+              if (CS == 1) tc_commit(BEMPTY(u));
+              else tc_commit_mc(BEMPTY(u), cluster_mask);
             }
-            tc_commit(AEMPTY(rg));
-            if (s0 + gsl == SLOTS) {
-              if (CS == 1) tc_commit(BEMPTY(bs));
-              else tc_commit_mc(BEMPTY(bs), cluster_mask);   // the panels of this stage may be overwritten by any peer
-            }
+            __syncwarp();
           }
-          __syncwarp();
-          if (++rg == p.ring_groups) { rg = 0; rg_par ^= 1; }
+          b_phase ^= 1;
+          rg_par ^= 1;
         }
-        if (++bs == p.n_bstages) { bs = 0; b_phase ^= 1; }
       }
+      for (; ch < p.n_chunks; ++ch) generic_chunk(ch, two_plane);
       if (elect_one()) tc_commit(DFULL);
       __syncwarp();
     }
