@@ -12,13 +12,13 @@ namespace lrr {
 namespace {
 
 __device__ double betacf_dev(double a, double b, double x) {
-  const double tiny = 1e-300, eps = 4e-16;  // ~2 ulp: a tighter test can bounce between 1 +- 1 ulp forever
+  const double tiny = 1e-300, eps = 3e-15;  // a tighter test can bounce a few ulp around 1 for hundreds of iterations
   const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
   double c = 1.0, d = 1.0 - qab * x / qap;
   if (fabs(d) < tiny) d = tiny;
   d = 1.0 / d;
   double h = d;
-  for (int m = 1; m <= 3000; ++m) {
+  for (int m = 1; m <= 1000; ++m) {
     const double m2 = 2.0 * m;
     double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
     d = 1.0 + aa * d;

@@ -29,7 +29,7 @@
 #endif
 
 static double betacf(double a, double b, double x) {
-  const double tiny = 1e-300, eps = 4e-16;  // ~2 ulp: a tighter test can bounce between 1 +- 1 ulp forever
+  const double tiny = 1e-300, eps = 3e-15;  // a tighter test can bounce a few ulp around 1 for hundreds of iterations
   double qab = a + b, qap = a + 1.0, qam = a - 1.0;
   double c = 1.0, d = 1.0 - qab * x / qap;
   if (fabs(d) < tiny) d = tiny;

@@ -58,7 +58,7 @@ def two_sided_p(t, d):
     return 2.0 * pt_lower(-np.abs(t), float(d))
 
 
-def _betacf(a, b, x, tol=4e-16, max_iter=200000):
+def _betacf(a, b, x, tol=3e-15, max_iter=200000):
     """Continued fraction for I_x(a,b) (modified Lentz).  Valid for x < (a+1)/(a+b+2)."""
     tiny = 1e-300
     qab, qap, qam = a + b, a + 1.0, a - 1.0
