@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--variants", type=int, default=N_VARIANTS, help="variants per GPU")
     ap.add_argument("--missing-rate", type=float, default=0.0)
-    ap.add_argument("--e2e-variants", type=int, default=32768)
+    ap.add_argument("--e2e-variants", type=int, default=65536)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -143,39 +143,22 @@ def run_ours(a):
     ctx = _lib.context(local)
     lib = ctx.lib
 
-    # ---- basis: host QR on rank 0, NCCL broadcast (the analogue of sc.broadcast, LR:74-78) ---------
-    def make_basis_tensors():
-        if rank == 0:
-            b = GroupBasis(y, cov, np.arange(N))
-            meta = torch.tensor([b.n, b.K, b.P, int(b.has_intercept)], dtype=torch.int64, device=dev)
-            t = [torch.from_numpy(x).to(dev) for x in (b.complete_idx, b.q_cols, b.y_res, b.qty, b.yyp)]
-        else:
-            meta = torch.zeros(4, dtype=torch.int64, device=dev)
-            t = None
-        if world > 1:
-            dist.broadcast(meta, 0)
-            n_, K_, P_, hi_ = [int(v) for v in meta.tolist()]
-            if rank != 0:
-                t = [torch.empty(n_, dtype=torch.int32, device=dev),
-                     torch.empty((K_ - hi_, n_), dtype=torch.float64, device=dev),
-                     torch.empty((P_, n_), dtype=torch.float64, device=dev),
-                     torch.empty((K_, P_), dtype=torch.float64, device=dev),
-                     torch.empty(P_, dtype=torch.float64, device=dev)]
-            for x in t:
-                dist.broadcast(x, 0)
-        return [int(v) for v in meta.tolist()], t
+    # ---- basis: host prologue on rank 0, NCCL broadcast (the analogue of sc.broadcast, LR:74-78) ---------
+    from hail_b200 import dist as hd
 
-    def push_basis(meta, t):
-        n_, K_, P_, hi_ = meta
+    bases = [GroupBasis(y, cov, np.arange(N))] if rank == 0 else None
+    bt = hd.broadcast_bases(bases, dev)[0]
+
+    def push_basis(b):
+        t = b.tensors
         ctx.check(lib.lrr_clear_groups(ctx.handle))
-        ctx.check(lib.lrr_add_group(ctx.handle, N, n_, K_, P_, hi_, t[0].data_ptr(),
+        ctx.check(lib.lrr_add_group(ctx.handle, N, b.n, b.K, b.P, b.has_intercept, t[0].data_ptr(),
                                     t[1].data_ptr() if t[1].numel() else None, t[2].data_ptr(), t[3].data_ptr(),
                                     t[4].data_ptr()))
         ctx.check(lib.lrr_reserve(ctx.handle, M))
 
-    meta, bt = make_basis_tensors()
-    push_basis(meta, bt)
-    n_kept, K, P, _ = meta
+    push_basis(bt)
+    n_kept, K, P = bt.n, bt.K, bt.P
 
     out = {"n": torch.empty(M, dtype=torch.int32, device=dev), "n_missing": torch.empty(M, dtype=torch.int32, device=dev),
            "sum_x": torch.empty(M, dtype=torch.float64, device=dev)}
@@ -186,7 +169,6 @@ def run_ours(a):
         setattr(go[0], k, v.data_ptr())
     go[0].log10_p = None
     rows = torch.stack([out["sum_x"]] + [out[f][:, 0] for f in STAT_FIELDS], dim=1)  # result row block for the gather
-    gathered = [torch.empty_like(rows) for _ in range(world)] if world > 1 else None
     kid = _lib.KERNELS[a.kernel]
     stream = torch.cuda.current_stream(dev).cuda_stream
     ctx.check(lib.lrr_set_timing(ctx.handle, 1))
@@ -195,12 +177,12 @@ def run_ours(a):
 
     def step(timed):
         if world > 1:  # per-step basis broadcast + result gather (tiny next to the sweep)
-            for x in bt:
+            for x in bt.tensors:
                 dist.broadcast(x, 0)
         ctx.check(lib.lrr_run(ctx.handle, gt.data.data_ptr(), gt.flags_ptr(), M, gt.stride, N, go, 1, kid, stream))
         if world > 1:
             torch.stack([out["sum_x"]] + [out[f][:, 0] for f in STAT_FIELDS], dim=1, out=rows)
-            dist.all_gather(gathered, rows)
+            hd.gather_rows(rows, counts=[M] * world)
         if timed:
             sweep_ms.append(lib.lrr_last_sweep_ms(ctx.handle))
 
@@ -264,7 +246,7 @@ def run_ours(a):
         bed_stride = (N + 3) // 4
         d_bed = torch.empty((Me, bed_stride), dtype=torch.uint8, device=dev)
         ctx.check(lib.lrr_unpack_bed(ctx.handle, gt.data.data_ptr(), gt.stride, Me, N, d_bed.data_ptr(), bed_stride, stream))
-        h_bed = torch.empty((Me, bed_stride), dtype=torch.uint8).pin_memory()
+        h_bed = torch.empty((Me, bed_stride), dtype=torch.uint8, pin_memory=True)
         h_bed.copy_(d_bed)
         del d_bed
         torch.cuda.synchronize(dev)

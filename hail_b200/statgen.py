@@ -24,6 +24,14 @@ from .matrixtable import (ChainedField, ColumnExpression, EntryExpression, Expre
 
 log = logging.getLogger("hail_b200")
 
+try:  # skinny (n x K) @ (K x K) products are 10x slower under multi-threaded OpenBLAS than on one thread
+    from threadpoolctl import threadpool_limits as _blas_limits
+except Exception:  # pragma: no cover
+    import contextlib
+
+    def _blas_limits(limits=None):
+        return contextlib.nullcontext()
+
 STAT_FIELDS = ["y_transpose_x", "beta", "standard_error", "t_stat", "p_value"]
 
 
@@ -112,13 +120,14 @@ class GroupBasis:
         log.info("linear_regression_rows%s: running on %d samples for %d response %s y,\n"
                  "    with input variable x, and %d additional %s...", tag, n, P, _plural(P, "variable"), K,
                  _plural(K, "covariate"))  # LR:60-63 / 241-244
-        y = ys[keep]
-        c = cov[keep]
+        with _blas_limits(limits=1):
+            self._build(ys[keep], cov[keep], np.asarray(col_index)[keep], n, K, P, d)
+
+    def _build(self, y, c, kept_index, n, K, P, d):
         self.n, self.K, self.P, self.d = n, K, P, d
-        self.complete_idx = np.ascontiguousarray(np.asarray(col_index)[keep], dtype=np.int32)  # into the packed store
+        self.complete_idx = np.ascontiguousarray(kept_index, dtype=np.int32)  # into the packed store
         if K > 0:
-            q, _ = np.linalg.qr(c, mode="reduced")  # LR:67 (only Q Q^T enters the results)
-            q, has_intercept = _rotate_constant_first(q)
+            q, has_intercept = orthonormal_basis(c)    # LR:67 (only Q Q^T enters the results)
         else:
             q, has_intercept = np.zeros((n, 0)), False
         qty = q.T @ y                                  # LR:71
@@ -132,32 +141,54 @@ class GroupBasis:
         self.y_res = np.ascontiguousarray(y_res.T)          # [P, n]
 
 
-def _rotate_constant_first(q):
-    """If the constant vector lies in span(q), rotate the orthonormal basis so column 0 is exactly 1/sqrt(n).
+def _gram_orthonormalise(a, rank_tol=1e-11):
+    """Orthonormal basis of span(a) from the K x K Gram matrix (two passes = CholeskyQR2-style accuracy).
 
-    Q Q^T (all that enters LR:139-146) is unchanged.  Lets the device form the constant column's projection
-    exactly from integer genotype counts, removing the dominant cancellation in x.x - |Q^T x|^2.
+    Returns (q [n, r], ok): ok is False when the columns are too ill-conditioned for the Gram route.
     """
-    n, K = q.shape
+    g = a.T @ a
+    w, v = np.linalg.eigh(g)
+    wmax = w.max() if w.size else 0.0
+    if not np.isfinite(wmax) or wmax <= 0.0:
+        return a[:, :0], True
+    keep = w > rank_tol * wmax
+    if w[keep].min() < 1e-7 * wmax:   # cond(a)^2 too large for one Gram pass to be safe
+        return None, False
+    q = a @ (v[:, keep] / np.sqrt(w[keep]))
+    g2 = q.T @ q                      # second pass removes the O(cond^2 eps) loss of orthogonality
+    w2, v2 = np.linalg.eigh(g2)
+    q = q @ ((v2 / np.sqrt(w2)) @ v2.T)
+    return q, True
+
+
+def orthonormal_basis(c):
+    """Orthonormal basis Q of the covariate column space, as `qr.reduced.justQ(cov)` provides in LR:67.
+
+    Only the projector Q Q^T enters LR:139-146, so any orthonormal basis of the same space gives the same
+    results.  When the constant vector lies in the span, column 0 is made exactly 1/sqrt(n) and the other K-1
+    columns are orthogonal to it: the device then forms that column's projection exactly from integer genotype
+    counts, which removes the dominant cancellation in x.x - |Q^T x|^2.  Returns (Q [n, K], has_intercept).
+    """
+    n, K = c.shape
     one = np.full(n, 1.0 / np.sqrt(n))
-    u = q.T @ one
-    resid = one - q @ u
-    if np.linalg.norm(resid) > 1e-9:
-        return q, False
-    u /= np.linalg.norm(u)
-    # Householder reflection H with H e1 = u  ->  (q H)[:, 0] = q u = const
-    e1 = np.zeros(K)
-    e1[0] = 1.0
-    v = e1 - u
-    nv = np.linalg.norm(v)
-    H = np.eye(K) if nv < 1e-15 else np.eye(K) - 2.0 * np.outer(v, v) / (nv * nv)
-    q2 = q @ H
-    q2[:, 0] = one  # exact constant
-    # re-orthogonalise the remaining columns against the constant (and each other) to clean up roundoff
-    rest = q2[:, 1:] - np.outer(one, one @ q2[:, 1:])
-    if K > 1:
-        rest, _ = np.linalg.qr(rest, mode="reduced")
-        rest -= np.outer(one, one @ rest)
+    # is the constant in the span?  (least squares on the small Gram system; verified by the residual)
+    q_all, ok = _gram_orthonormalise(c)
+    if not ok or q_all.shape[1] != K:
+        q_all, _ = np.linalg.qr(c, mode="reduced")        # ill-conditioned or rank-deficient: Householder QR
+    u = q_all.T @ one
+    resid = one - q_all @ u
+    if np.linalg.norm(resid) > 1e-9 or q_all.shape[1] != K:
+        return q_all, False
+    # rotate inside the span: centre the columns, orthonormalise what is left (rank K-1)
+    cc = q_all - np.outer(one, u)                            # = (I - 1 1^T/n) q_all
+    rest, ok = _gram_orthonormalise(cc, rank_tol=1e-9)
+    if not ok or rest.shape[1] != K - 1:
+        q2, _ = np.linalg.qr(cc, mode="reduced")
+        w = np.abs(np.linalg.svd(cc, compute_uv=False))
+        rest = q2[:, : K - 1] if K > 1 else q2[:, :0]
+        if K > 1 and w[K - 2] < 1e-9:
+            return q_all, False
+    rest = rest - np.outer(one, one @ rest)                  # exact-zero column sums up to roundoff
     return np.column_stack([one, rest]), True
 
 
