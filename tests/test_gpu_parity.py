@@ -317,3 +317,73 @@ def test_fatal_conditions_match_reference_messages():
                                   [1.0, mt.Cov1, mt.Cov2, mt.Cov1 * mt.Cov1, mt.Cov2 * mt.Cov2, mt.Cov1 * mt.Cov2])
     with pytest.raises(hb.FatalError, match="No complete samples"):
         hb.linear_regression_rows(mt.allmiss, mt.GT.n_alt_alleles(), [1.0])
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json sample sizes (400k / 500k samples): parity against the C oracle on a variant slice, plus
+# size-independent properties (kernel-vs-kernel agreement, exact integer fields, planted signal ranking).
+# ---------------------------------------------------------------------------------------------
+def _big_case(N, M, K, missing_rate, seed):
+    hb = _hb()
+    from hail_b200 import bn
+    rng = np.random.Generator(np.random.Philox(key=[seed, 77]))
+    pop, th, _ = bn.bn_parameters(3, N, M, missing_rate=missing_rate, seed=seed)
+    gt = bn.bn_fill(hb.PackedGenotypes.empty(M, N), pop, th, seed=seed)
+    cov = np.column_stack([np.ones(N)] + [rng.standard_normal(N) for _ in range(K - 1)])
+    # pull the bed bytes of the same store back for the CPU side
+    from hail_b200 import _lib
+    ctx = _lib.context(0)
+    bed_stride = (N + 3) // 4
+    d_bed = torch.empty((M, bed_stride), dtype=torch.uint8, device="cuda")
+    ctx.check(ctx.lib.lrr_unpack_bed(ctx.handle, gt.data.data_ptr(), gt.stride, M, N, d_bed.data_ptr(), bed_stride, None))
+    torch.cuda.synchronize()
+    return gt, d_bed.cpu().numpy(), cov, rng
+
+
+@pytest.mark.parametrize("N,missing_rate", [(400_000, 0.0), (400_000, 0.25), (500_000, 0.0)])
+def test_full_sample_size_parity_vs_c_oracle(N, missing_rate):
+    """C2 / C3 / C5 sample counts, K = 10 (intercept + 9 PCs); variant slice sized for seconds of CPU."""
+    hb = _hb()
+    from oracle import c_oracle
+    M, K = 1024, 10
+    gt, bed_rows, cov, rng = _big_case(N, M, K, missing_rate, seed=21)
+    dos0 = obed.decode_rows(bed_rows[:1], N)[0]
+    y = rng.standard_normal(N) + 0.02 * np.nan_to_num(dos0)      # variant 0 is causal
+    y[rng.random(N) < 0.05] = np.nan
+    want = c_oracle.linreg_group_bed(bed_rows, N, y[:, None], cov)
+    mt = hb.MatrixTable(gt, cols={"y": y, **{f"c{i}": cov[:, i] for i in range(1, K)}})
+    covs = [1.0] + [mt[f"c{i}"] for i in range(1, K)]
+    res = {}
+    for kernel in KERNELS:
+        ht = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=covs, _kernel=kernel, _log10_p=True)
+        got = _as_oracle_dict(ht)
+        assert_fields_close(got, {k: v for k, v in want.items() if k != "_d"}, t_floor=1e-9,
+                            ctx=f"{kernel} N={N} miss={missing_rate}")
+        res[kernel] = ht
+        # the causal variant is by far the strongest signal and its log10 p is finite
+        assert int(np.nanargmin(ht.p_value)) == 0 and np.isfinite(ht.log10_p[0]) and ht.log10_p[0] < -6
+    # the two kernels agree far below the tolerance (exact integer path vs float64 FMA path)
+    a, b = res["tc"], res["fp64"]
+    assert np.array_equal(a.n, b.n) and np.array_equal(a.n_missing, b.n_missing)
+    clean = a.n_missing == 0
+    assert np.array_equal(a.sum_x[clean], b.sum_x[clean])
+    assert np.nanmax(np.abs(a.t_stat - b.t_stat)) < 1e-8
+
+
+def test_tc_kernel_is_deterministic_and_order_independent():
+    """Exact integer accumulation: the same rows give bit-identical results wherever they sit in the sweep."""
+    hb = _hb()
+    N, M = 100_000, 1500
+    gt, _, cov, rng = _big_case(N, M, 4, 0.1, seed=5)
+    y = rng.standard_normal(N)
+    cols = {"y": y, **{f"c{i}": cov[:, i] for i in range(1, 4)}}
+    mt = hb.MatrixTable(gt, cols=cols)
+    covs = [1.0] + [mt[f"c{i}"] for i in range(1, 4)]
+    full = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=covs, _kernel="tc")
+    again = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=covs, _kernel="tc")
+    sub = hb.MatrixTable(gt.rows(512, 1400), cols=cols)   # different tile alignment / CTA assignment
+    part = hb.linear_regression_rows(y=sub.y, x=sub.GT.n_alt_alleles(),
+                                     covariates=[1.0] + [sub[f"c{i}"] for i in range(1, 4)], _kernel="tc")
+    for f in ("sum_x", "y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+        assert np.array_equal(full[f], again[f], equal_nan=True), f
+        assert np.array_equal(full[f][512:1400], part[f], equal_nan=True), f
