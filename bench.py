@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--variants", type=int, default=N_VARIANTS, help="variants per GPU")
     ap.add_argument("--missing-rate", type=float, default=0.0)
+    ap.add_argument("--chained", action="store_true",
+                    help="BASELINE config 3: y=[[y1],[y2]] with 10 %% / 20 %% phenotype missingness (use with --missing-rate 0.25)")
     ap.add_argument("--e2e-variants", type=int, default=65536)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -146,28 +148,43 @@ def run_ours(a):
     # ---- basis: host prologue on rank 0, NCCL broadcast (the analogue of sc.broadcast, LR:74-78) ---------
     from hail_b200 import dist as hd
 
-    bases = [GroupBasis(y, cov, np.arange(N))] if rank == 0 else None
-    bt = hd.broadcast_bases(bases, dev)[0]
+    if a.chained:
+        rng_m = np.random.Generator(np.random.Philox(key=[2, 0xC3]))
+        y1 = np.where(rng_m.random(N) < 0.10, np.nan, y[:, 0])
+        y2 = np.where(rng_m.random(N) < 0.20, np.nan, rng_m.standard_normal(N))
+        y_groups = [y1[:, None], y2[:, None]]
+    else:
+        y_groups = [y]
+    bases = [GroupBasis(yg, cov, np.arange(N), i if a.chained else None) for i, yg in enumerate(y_groups)] if rank == 0 else None
+    bts = hd.broadcast_bases(bases, dev)
+    bt = bts[0]
+    G = len(bts)
 
-    def push_basis(b):
-        t = b.tensors
+    def push_basis(bl):
         ctx.check(lib.lrr_clear_groups(ctx.handle))
-        ctx.check(lib.lrr_add_group(ctx.handle, N, b.n, b.K, b.P, b.has_intercept, t[0].data_ptr(),
-                                    t[1].data_ptr() if t[1].numel() else None, t[2].data_ptr(), t[3].data_ptr(),
-                                    t[4].data_ptr()))
+        for b in bl:
+            t = b.tensors
+            ctx.check(lib.lrr_add_group(ctx.handle, N, b.n, b.K, b.P, b.has_intercept, t[0].data_ptr(),
+                                        t[1].data_ptr() if t[1].numel() else None, t[2].data_ptr(), t[3].data_ptr(),
+                                        t[4].data_ptr()))
         ctx.check(lib.lrr_reserve(ctx.handle, M))
 
-    push_basis(bt)
+    push_basis(bts)
     n_kept, K, P = bt.n, bt.K, bt.P
+    n_kept_all = [b.n for b in bts]
 
-    out = {"n": torch.empty(M, dtype=torch.int32, device=dev), "n_missing": torch.empty(M, dtype=torch.int32, device=dev),
-           "sum_x": torch.empty(M, dtype=torch.float64, device=dev)}
-    for f in STAT_FIELDS:
-        out[f] = torch.empty((M, P), dtype=torch.float64, device=dev)
-    go = (_lib.GroupOut * 1)()
-    for k, v in out.items():
-        setattr(go[0], k, v.data_ptr())
-    go[0].log10_p = None
+    outs_all = []
+    go = (_lib.GroupOut * G)()
+    for g in range(G):
+        o = {"n": torch.empty(M, dtype=torch.int32, device=dev), "n_missing": torch.empty(M, dtype=torch.int32, device=dev),
+             "sum_x": torch.empty(M, dtype=torch.float64, device=dev)}
+        for f in STAT_FIELDS:
+            o[f] = torch.empty((M, bts[g].P), dtype=torch.float64, device=dev)
+        for k, v in o.items():
+            setattr(go[g], k, v.data_ptr())
+        go[g].log10_p = None
+        outs_all.append(o)
+    out = outs_all[0]
     rows = torch.stack([out["sum_x"]] + [out[f][:, 0] for f in STAT_FIELDS], dim=1)  # result row block for the gather
     kid = _lib.KERNELS[a.kernel]
     stream = torch.cuda.current_stream(dev).cuda_stream
@@ -177,9 +194,10 @@ def run_ours(a):
 
     def step(timed):
         if world > 1:  # per-step basis broadcast + result gather (tiny next to the sweep)
-            for x in bt.tensors:
-                dist.broadcast(x, 0)
-        ctx.check(lib.lrr_run(ctx.handle, gt.data.data_ptr(), gt.flags_ptr(), M, gt.stride, N, go, 1, kid, stream))
+            for b in bts:
+                for x in b.tensors:
+                    dist.broadcast(x, 0)
+        ctx.check(lib.lrr_run(ctx.handle, gt.data.data_ptr(), gt.flags_ptr(), M, gt.stride, N, go, G, kid, stream))
         if world > 1:
             torch.stack([out["sum_x"]] + [out[f][:, 0] for f in STAT_FIELDS], dim=1, out=rows)
             hd.gather_rows(rows, counts=[M] * world)
@@ -216,11 +234,12 @@ def run_ours(a):
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     kernel_used = ctx.last_kernel
     ms_per_step = total_ms / a.steps
-    value = world * M * float(n_kept) / (ms_per_step / 1e3)
+    # genotypes = variants x samples kept, summed over the groups regressed (reference: one imputed column per group)
+    value = world * M * float(sum(n_kept_all)) / (ms_per_step / 1e3)
 
     # ---- roofline of the dominant (sweep) kernel: algorithmic bytes / its own event-timed duration ----
     peak, peak_src = measured_peak()
-    abytes = algorithmic_bytes(M, N, 1, K, P, n_kept)
+    abytes = algorithmic_bytes(M, N, G, K, P, n_kept)
     sweep = float(np.mean(sweep_ms))
     achieved = abytes / (sweep / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
@@ -234,7 +253,7 @@ def run_ours(a):
         "dtype": "f64 epilogue; sweep " + ("int8 x int8 -> int32 exact (tcgen05)" if kernel_used == "tc" else "f64 FMA"),
         "data": "synthetic (seeded Balding-Nichols style, generated in HBM)",
         "config": {"workload": WORKLOAD if (N, M) == (N_SAMPLES, N_VARIANTS) else f"REDUCED {N} samples x {M} variants",
-                   "samples": N, "variants_per_gpu": M, "phenotypes": P, "covariates": K, "missing_rate": a.missing_rate,
+                   "samples": N, "variants_per_gpu": M, "phenotypes": P, "covariates": K, "missing_rate": a.missing_rate, "groups": G,
                    "kernel": kernel_used, "parallelism": f"variant-sharded x{world}",
                    "l2": "inputs larger than L2 (packed genotypes %.1f GB per GPU)" % (gt.nbytes / 1e9)},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,

@@ -277,6 +277,7 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return d;
 }
 
+template <int V> struct IntTag { static constexpr int value = V; };
 struct TrueTag { static constexpr bool value = true; };
 struct FalseTag { static constexpr bool value = false; };
 
@@ -494,41 +495,76 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
       if (++bs == p.n_bstages) { bs = 0; b_phase ^= 1; }
     };
 
-    constexpr int NB = 3;   // unroll depth of the fast path (needs n_bstages == ring_groups == NB)
-    const bool can_unroll = (p.n_bstages == NB) && (p.ring_groups == NB);
+    constexpr int NB = 3;   // the fast path is unrolled over NB chunks == the depth of the basis-panel ring
+    // Fast path of one tile, compile-time mode (TP) and A-ring depth (RG).  Requires b-stage 0 and ring group 0 at
+    // entry and (NB * groups-per-chunk) % RG == 0, so that ring positions repeat every NB chunks.
+    auto fast_chunks = [&](auto tp_tag, auto rg_tag, int& ch) {
+      constexpr bool TP = decltype(tp_tag)::value;
+      constexpr int RG = decltype(rg_tag)::value;
+      constexpr int GPC = TP ? 2 : 1;              // group instances per chunk
+      constexpr int WRAPS = NB * GPC / RG;         // ring passes per unrolled block
+      static_assert((NB * GPC) % RG == 0, "ring positions must repeat every NB chunks");
+      for (; ch + NB <= p.n_chunks; ch += NB) {
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          mbar_wait(BFULL(u), b_phase);
+          const uint64_t bd = desc0 + (uint64_t)(u * stage_d);
+#pragma unroll
+          for (int h = 0; h < GPC; ++h) {
+            constexpr int dummy = 0; (void)dummy;
+            const int inst = u * GPC + h;
+            const int g = inst % RG;
+            const uint32_t par = rg_par ^ (uint32_t)((inst / RG) & 1);
+            mbar_wait(AFULL(g), par);
+            tc_fence_after();
+            if (elect_one()) {
+#if !LRR_ABL_NO_MMA
+              const uint32_t a_g = a_ring + g * GROUP_COLS;
+              if (!TP) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                  for (int j = 0; j < LRR_ABL_MMA_J; ++j) {
+                    const uint32_t acc = (u | k | j) ? 1u : (ch ? 1u : 0u);
+                    mma_i8_ts(tmem, a_g + k * 32 + j * 8, bd + (uint64_t)(k * panel_d + j * 2), idesc, acc);
+                  }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t acc = (u | h | k | j) ? 1u : (ch ? 1u : 0u);
+                    const uint64_t d = bd + (uint64_t)((2 * h + k) * panel_d + j * 2);
+                    mma_i8_ts(tmem, a_g + k * 32 + j * 8, d, idesc, acc);
+                    mma_i8_ts(tmem + p.ncols, a_g + 64 + k * 32 + j * 8, d, idesc, acc);
+                  }
+              }
+#endif
+              tc_commit(AEMPTY(g));
+              if (h == GPC - 1) {
+                if (CS == 1) tc_commit(BEMPTY(u));
+                else tc_commit_mc(BEMPTY(u), cluster_mask);   // any peer may overwrite this stage's panels
+              }
+            }
+            __syncwarp();
+          }
+        }
+        b_phase ^= 1;
+        if (WRAPS & 1) rg_par ^= 1;
+      }
+    };
+
     for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
       const bool two_plane = tile_has_missing(p, tile);
       mbar_wait(DEMPTY, (tile_i & 1) ^ 1);   // the previous tile's accumulators have been read out
       tc_fence_after();
       int ch = 0;
-      if (!two_plane && can_unroll && bs == rg && b_phase == rg_par) {
-        while (ch < p.n_chunks && bs != 0) generic_chunk(ch++, false);   // align to ring position 0
-        for (; ch + NB <= p.n_chunks; ch += NB) {
-#pragma unroll
-          for (int u = 0; u < NB; ++u) {
-            mbar_wait(BFULL(u), b_phase);
-            mbar_wait(AFULL(u), b_phase);
-            tc_fence_after();
-            if (elect_one()) {
-#if !LRR_ABL_NO_MMA
-              const uint32_t a_g = a_ring + u * GROUP_COLS;
-              const uint64_t bd = desc0 + (uint64_t)(u * stage_d);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-#pragma unroll
-                for (int j = 0; j < LRR_ABL_MMA_J; ++j) {
-                  const uint32_t acc = (u | k | j) ? 1u : (ch ? 1u : 0u);
-                  mma_i8_ts(tmem, a_g + k * 32 + j * 8, bd + (uint64_t)(k * panel_d + j * 2), idesc, acc);
-                }
-#endif
-              tc_commit(AEMPTY(u));
-              if (CS == 1) tc_commit(BEMPTY(u));
-              else tc_commit_mc(BEMPTY(u), cluster_mask);
-            }
-            __syncwarp();
-          }
-          b_phase ^= 1;
-          rg_par ^= 1;
+      if (p.n_bstages == NB) {
+        while (ch < p.n_chunks && bs != 0) generic_chunk(ch++, two_plane);   // align to b-stage 0
+        if (rg == 0 && ch < p.n_chunks) {
+          if (!two_plane && p.ring_groups == 3) fast_chunks(FalseTag{}, IntTag<3>{}, ch);
+          else if (two_plane && p.ring_groups == 3) fast_chunks(TrueTag{}, IntTag<3>{}, ch);
+          else if (two_plane && p.ring_groups == 2) fast_chunks(TrueTag{}, IntTag<2>{}, ch);
         }
       }
       for (; ch < p.n_chunks; ++ch) generic_chunk(ch, two_plane);

@@ -387,3 +387,33 @@ def test_tc_kernel_is_deterministic_and_order_independent():
     for f in ("sum_x", "y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
         assert np.array_equal(full[f], again[f], equal_nan=True), f
         assert np.array_equal(full[f][512:1400], part[f], equal_nan=True), f
+
+
+def test_mixed_one_plane_two_plane_tiles_many_tiles_per_cta():
+    """Tiles with and without missing calls interleaved, > 2 tiles per CTA, odd tail: exercises the mode switches
+    of the TMEM ring and the cluster padding tiles."""
+    hb = _hb()
+    rng = np.random.default_rng(9)
+    N, M = 1500, 148 * 128 * 2 + 128 * 5 + 37
+    x = rng.integers(0, 3, size=(M, N)).astype(np.int8)
+    tile = np.arange(M) // 128
+    miss_rows = (tile % 3 == 1) | (tile % 7 == 0)
+    mask = (rng.random((M, N)) < 0.08) & miss_rows[:, None]
+    x[mask] = -1
+    gt = hb.PackedGenotypes.from_dosage(x)
+    assert np.array_equal(gt.row_flags.cpu().numpy().astype(bool), (x < 0).any(axis=1))
+    cov = np.column_stack([np.ones(N), rng.normal(size=(N, 2))])
+    y = rng.normal(size=N)
+    mt = hb.MatrixTable(gt, cols={"y": y, "c1": cov[:, 1], "c2": cov[:, 2]})
+    xf = np.where(x < 0, np.nan, x).astype(np.float64)
+    want = O.linreg_group(xf, y[:, None], cov)
+    for kernel in KERNELS:
+        ht = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=[1.0, mt.c1, mt.c2], _kernel=kernel)
+        got = _as_oracle_dict(ht)
+        assert_fields_close(got, {k: v for k, v in want.items() if k != "_d"}, t_floor=1e-9, ctx=kernel)
+        assert np.array_equal(ht.n_missing, (x < 0).sum(axis=1))
+    # unknown flags (None) must give the same answer: every tile is then treated as possibly missing
+    gt2 = hb.PackedGenotypes(gt.data, M, N, None)
+    mt2 = hb.MatrixTable(gt2, cols={"y": y, "c1": cov[:, 1], "c2": cov[:, 2]})
+    h2 = hb.linear_regression_rows(y=mt2.y, x=mt2.GT.n_alt_alleles(), covariates=[1.0, mt2.c1, mt2.c2], _kernel="tc")
+    assert np.array_equal(h2.beta, ht.beta, equal_nan=True) and np.array_equal(h2.p_value, ht.p_value, equal_nan=True)
