@@ -92,7 +92,8 @@ struct GroupMeta {
   int n;              // complete samples
   int mask_all;       // every stored sample is in the group: no masking needed for the hom-alt count
   int32_t* counts;    // [M][4]
-  double* dots;       // [M][C]
+  double* dots;       // [M][dots_stride], already offset to this segment's first dot column
+  int dots_stride;    // the group's total number of dot columns
   const double* colscale;   // [C]
   const uint32_t* mask_hi;  // [ns_pad/16], high bit of each kept field
 };
@@ -785,7 +786,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
                   const double scale = G.colscale[c];
                   double dot = fma((double)hi, 16777216.0, (double)lo) * scale;
                   if (two_plane && nm > 0) dot += mean * (fma((double)mhi, 16777216.0, (double)mlo) * scale);
-                  if (v < p.M) G.dots[v * G.C + c] = dot;
+                  if (v < p.M) G.dots[v * G.dots_stride + c] = dot;
                   hi = lo = mhi = mlo = 0;
                   sl = 0;
                   ++c;
@@ -859,22 +860,40 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// One sweep over the genotypes covers at most PASS_COLS digit columns (so that both accumulator planes and the A ring
+// fit the 512 TMEM columns).  Wider problems (e.g. 128 phenotypes) run several passes, each over a contiguous range
+// of every group's dot columns ("segment") plus that group's ones column.
+constexpr int PASS_COLS = 128;
+
+struct Segment {
+  int group;     // index into Ctx::groups
+  int c_first;   // first dot column of the group in this segment
+  int n_cols;    // dot columns in this segment
+  int kd_in;     // of which (leading) covariate columns
+  int row0;      // first row of this segment in the pass's panel matrix (digit rows, then the ones row)
+};
+
+struct Pass {
+  int ncols = 0;                 // panel rows, padded to 16
+  int64_t bq_row0 = 0;           // first row of this pass in State::d_bq
+  std::vector<Segment> segs;
+  int n_gstages = 0, n_bstages = 0, gstage_bytes = 0, bstage_bytes = 0, smem_bytes = 0;
+  int ring_base = 0, ring_groups = 0, mask_bytes = 0;
+  CUtensorMap b_map;
+};
+
 struct State {
   bool prepared = false;
   bool usable = false;
   std::string why;
   EncodeTiledFn encode = nullptr;
-  int ncols = 0;
-  int n_gstages = 0, n_bstages = 0, gstage_bytes = 0, bstage_bytes = 0;
-  int smem_bytes = 0;
+  std::vector<Pass> passes;
   int8_t* d_bq = nullptr;
   double* d_colscale = nullptr;   // concatenated per group
   unsigned long long* d_colmax = nullptr;
   uint32_t* d_mask_hi = nullptr;  // [G][ns_pad/16] group masks shifted to the high bit of each field
-  int ring_base = 0, ring_groups = 0, mask_bytes = 0;
+  std::vector<int> scale_off;
   int cluster = 2;
-  std::vector<int> col_off, scale_off;
-  CUtensorMap b_map;
   bool attr_set = false;
 };
 
@@ -892,6 +911,7 @@ static void free_prepared(State* s) {
   s->d_bq = nullptr;
   s->d_colscale = nullptr;
   s->d_colmax = nullptr;
+  s->passes.clear();
   s->prepared = false;
   s->usable = false;
 }
@@ -906,6 +926,49 @@ static int encode_2d(State* s, CUtensorMap* map, const void* ptr, uint64_t inner
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// split every group's dot columns into passes of at most PASS_COLS panel rows
+static void plan_passes(const Ctx* c, std::vector<Pass>& passes) {
+  passes.clear();
+  Pass cur;
+  int used = 0;
+  auto close = [&]() {
+    if (!cur.segs.empty()) {
+      cur.ncols = (used + 15) / 16 * 16;
+      passes.push_back(cur);
+    }
+    cur = Pass();
+    used = 0;
+  };
+  for (size_t g = 0; g < c->groups.size(); ++g) {
+    const Group& gr = c->groups[g];
+    int col = 0;
+    while (col < gr.C) {
+      // open a segment of group g in the current pass (needs room for one column + the ones row)
+      const int nd0 = col < gr.Kd ? N_SLICES_Q : N_SLICES_Y;
+      if (used + nd0 + 1 > PASS_COLS || (int)cur.segs.size() == MAX_GROUPS) close();
+      Segment sg;
+      sg.group = (int)g;
+      sg.c_first = col;
+      sg.n_cols = 0;
+      sg.kd_in = 0;
+      sg.row0 = used;
+      int rows = 0;
+      while (col < gr.C) {
+        const int nd = col < gr.Kd ? N_SLICES_Q : N_SLICES_Y;
+        if (used + rows + nd + 1 > PASS_COLS) break;
+        rows += nd;
+        if (col < gr.Kd) sg.kd_in++;
+        sg.n_cols++;
+        col++;
+      }
+      used += rows + 1;   // + ones row
+      cur.segs.push_back(sg);
+      if (col < gr.C) close();
+    }
+  }
+  close();
 }
 
 // build the quantised basis for the current group list
@@ -927,77 +990,91 @@ static int prepare(Ctx* c) {
     s->encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
   const size_t G = c->groups.size();
-  if (G == 0 || G > (size_t)MAX_GROUPS) {
-    s->why = "tensor-core kernel supports 1..4 groups";
+  if (G == 0) {
+    s->why = "no groups";
     return LRR_OK;
   }
-  int cols = 0, nscale = 0;
-  s->col_off.assign(G, 0);
+  if (c->n_samples_total > 1300000) {
+    s->why = "more than 1.3M samples: INT32 accumulators could overflow";
+    return LRR_OK;
+  }
+  int nscale = 0;
   s->scale_off.assign(G, 0);
   for (size_t g = 0; g < G; ++g) {
-    s->col_off[g] = cols;
     s->scale_off[g] = nscale;
-    cols += c->groups[g].Kd * N_SLICES_Q + c->groups[g].P * N_SLICES_Y + 1;
     nscale += c->groups[g].C;
   }
-  s->ncols = (cols + 15) / 16 * 16;
-  if (s->ncols > 256) {
-    s->why = "more than 256 digit columns (K + P too large for one pass)";
-    return LRR_OK;
+  plan_passes(c, s->passes);
+  int64_t total_rows = 0;
+  for (auto& ps : s->passes) {
+    ps.bq_row0 = total_rows;
+    total_rows += ps.ncols;
   }
   const int64_t ns_pad = c->groups[0].ns_pad;
-  LRR_CUDA(c, cudaMalloc(&s->d_bq, (size_t)s->ncols * ns_pad));
-  LRR_CUDA(c, cudaMemset(s->d_bq, 0, (size_t)s->ncols * ns_pad));
+  LRR_CUDA(c, cudaMalloc(&s->d_bq, (size_t)total_rows * ns_pad));
+  LRR_CUDA(c, cudaMemset(s->d_bq, 0, (size_t)total_rows * ns_pad));
   LRR_CUDA(c, cudaMalloc(&s->d_colscale, sizeof(double) * (size_t)nscale));
   LRR_CUDA(c, cudaMalloc(&s->d_colmax, sizeof(unsigned long long) * (size_t)nscale));
   LRR_CUDA(c, cudaMemset(s->d_colmax, 0, sizeof(unsigned long long) * (size_t)nscale));
   const int64_t mask_words = ns_pad / 16;
   LRR_CUDA(c, cudaMalloc(&s->d_mask_hi, sizeof(uint32_t) * (size_t)mask_words * G));
   bool any_masked = false;
+  const unsigned gx = (unsigned)std::min<int64_t>((ns_pad + 255) / 256, 1024);
   for (size_t g = 0; g < G; ++g) {
     const Group& gr = c->groups[g];
     if ((int64_t)gr.n != c->n_samples_total) any_masked = true;
     mask_hi_kernel<<<(unsigned)std::min<int64_t>((mask_words + 255) / 256, 1024), 256>>>(gr.d_mask, mask_words,
                                                                                         s->d_mask_hi + g * mask_words);
-    c->launches++;
-    dim3 grid1((unsigned)std::min<int64_t>((ns_pad + 255) / 256, 1024), (unsigned)gr.C);
-    colmax_kernel<<<grid1, 256>>>(gr.d_basis, gr.C, ns_pad, s->d_colmax + s->scale_off[g]);
-    dim3 grid2((unsigned)std::min<int64_t>((ns_pad + 255) / 256, 1024), (unsigned)(gr.C + 1));
-    quantize_kernel<<<grid2, 256>>>(gr.d_basis, gr.d_mask, gr.C, gr.Kd, ns_pad, s->d_colmax + s->scale_off[g],
-                                    s->col_off[g], s->d_bq, s->d_colscale + s->scale_off[g]);
+    for (int c0 = 0; c0 < gr.C; c0 += 65535)   // grid.y limit
+      colmax_kernel<<<dim3(gx, (unsigned)std::min(gr.C - c0, 65535)), 256>>>(gr.d_basis + (int64_t)c0 * ns_pad,
+                                                                            std::min(gr.C - c0, 65535), ns_pad,
+                                                                            s->d_colmax + s->scale_off[g] + c0);
     c->launches += 2;
+  }
+  for (auto& ps : s->passes) {
+    for (const Segment& sg : ps.segs) {
+      const Group& gr = c->groups[sg.group];
+      quantize_kernel<<<dim3(gx, (unsigned)(sg.n_cols + 1)), 256>>>(
+          gr.d_basis + (int64_t)sg.c_first * ns_pad, gr.d_mask, sg.n_cols, sg.kd_in, ns_pad,
+          s->d_colmax + s->scale_off[sg.group] + sg.c_first, (int)(ps.bq_row0 + sg.row0), s->d_bq,
+          s->d_colscale + s->scale_off[sg.group] + sg.c_first);
+      c->launches++;
+    }
   }
   LRR_CUDA(c, cudaGetLastError());
   LRR_CUDA(c, cudaDeviceSynchronize());
-  if (encode_2d(s, &s->b_map, s->d_bq, (uint64_t)ns_pad, (uint64_t)s->ncols, (uint64_t)ns_pad, SLOT, (uint32_t)s->ncols)) {
-    s->why = "cuTensorMapEncodeTiled failed for the basis panels";
-    return LRR_OK;
-  }
-  // shared memory: genotype ring (16 KB [+ group masks] per stage) + basis-panel ring + barriers + 1 KB slack
-  s->mask_bytes = any_masked ? (int)G * 128 : 0;
-  s->gstage_bytes = (GENO_BYTES + s->mask_bytes + 1023) / 1024 * 1024;
-  s->bstage_bytes = SLOTS * s->ncols * 128;
-  s->ring_base = (2 * s->ncols + 31) / 32 * 32;
-  s->ring_groups = (512 - s->ring_base) / GROUP_COLS;
-  if (s->ring_groups > MAX_RING) s->ring_groups = MAX_RING;
   const int budget = 227 * 1024 - (int)sizeof(Barriers) - 1024;
-  int bst = 3;
-  if (const char* e = getenv("LRR_TC_BSTAGES")) bst = atoi(e);
-  if (bst > MAX_BSTAGES) bst = MAX_BSTAGES;
-  while (bst > 2 && budget - bst * s->bstage_bytes < 3 * s->gstage_bytes) --bst;
-  int gst = (budget - bst * s->bstage_bytes) / s->gstage_bytes;
-  if (gst > MAX_GSTAGES) gst = MAX_GSTAGES;
-  if (const char* e = getenv("LRR_TC_GSTAGES")) { const int v = atoi(e); if (v >= 2 && v < gst) gst = v; }
-  if (bst < 2 || gst < 2) {
-    s->why = "not enough shared memory for the genotype / basis-panel rings";
-    return LRR_OK;
-  }
-  s->n_gstages = gst;
-  s->n_bstages = bst;
-  s->smem_bytes = gst * s->gstage_bytes + bst * s->bstage_bytes + (int)sizeof(Barriers) + 1024;
-  if (s->ring_groups < 2) {
-    s->why = "not enough tensor memory for the A ring";
-    return LRR_OK;
+  for (auto& ps : s->passes) {
+    if (encode_2d(s, &ps.b_map, s->d_bq + ps.bq_row0 * ns_pad, (uint64_t)ns_pad, (uint64_t)ps.ncols, (uint64_t)ns_pad,
+                  SLOT, (uint32_t)ps.ncols)) {
+      s->why = "cuTensorMapEncodeTiled failed for the basis panels";
+      return LRR_OK;
+    }
+    // shared memory: genotype ring (16 KB [+ group masks] per stage) + basis-panel ring + barriers + 1 KB slack
+    ps.mask_bytes = any_masked ? (int)ps.segs.size() * 128 : 0;
+    ps.gstage_bytes = (GENO_BYTES + ps.mask_bytes + 1023) / 1024 * 1024;
+    ps.bstage_bytes = SLOTS * ps.ncols * 128;
+    ps.ring_base = (2 * ps.ncols + 31) / 32 * 32;
+    ps.ring_groups = (512 - ps.ring_base) / GROUP_COLS;
+    if (ps.ring_groups > MAX_RING) ps.ring_groups = MAX_RING;
+    int bst = 3;
+    if (const char* e = getenv("LRR_TC_BSTAGES")) bst = atoi(e);
+    if (bst > MAX_BSTAGES) bst = MAX_BSTAGES;
+    while (bst > 2 && budget - bst * ps.bstage_bytes < 3 * ps.gstage_bytes) --bst;
+    int gst = (budget - bst * ps.bstage_bytes) / ps.gstage_bytes;
+    if (gst > MAX_GSTAGES) gst = MAX_GSTAGES;
+    if (const char* e = getenv("LRR_TC_GSTAGES")) { const int v = atoi(e); if (v >= 2 && v < gst) gst = v; }
+    if (bst < 2 || gst < 2) {
+      s->why = "not enough shared memory for the genotype / basis-panel rings";
+      return LRR_OK;
+    }
+    if (ps.ring_groups < 2) {
+      s->why = "not enough tensor memory for the A ring";
+      return LRR_OK;
+    }
+    ps.n_gstages = gst;
+    ps.n_bstages = bst;
+    ps.smem_bytes = gst * ps.gstage_bytes + bst * ps.bstage_bytes + (int)sizeof(Barriers) + 1024;
   }
   if (!s->attr_set) {
 #define LRR_SET_SMEM(NG_, CS_) \
@@ -1019,15 +1096,11 @@ static int prepare(Ctx* c) {
 
 }  // namespace tc
 
-bool tc_supported(Ctx* c, bool may_have_missing) {
+bool tc_supported(Ctx* c, bool /*may_have_missing*/) {
   if (tc::prepare(c) != LRR_OK) return false;
   tc::State* s = tc::state(c);
   if (!s->usable) {
     c->err = s->why;
-    return false;
-  }
-  if (may_have_missing && s->ncols > 128) {
-    c->err = "more than 128 digit columns: the two-plane (missing-call) mode does not fit TMEM";
     return false;
   }
   return true;
@@ -1057,68 +1130,72 @@ int launch_tc_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags,
   CUtensorMap geno_map;
   if (encode_2d(s, &geno_map, d_packed, (uint64_t)stride, (uint64_t)M, (uint64_t)stride, 128, TILE_M))
     return fail(c, LRR_ECUDA, "cuTensorMapEncodeTiled failed for the genotype store (pointer must be 16-byte aligned)");
-  Params p;
-  memset(&p, 0, sizeof p);
-  p.M = M;
-  p.n_tiles = (int)((M + TILE_M - 1) / TILE_M);
-  p.n_chunks = (int)(stride / 128);
-  p.ncols = s->ncols;
-  p.n_gstages = s->n_gstages;
-  p.n_bstages = s->n_bstages;
-  p.n_groups = (int)c->groups.size();
-  p.ring_base = s->ring_base;
-  p.ring_groups = s->ring_groups;
-  p.gstage_bytes = s->gstage_bytes;
-  p.bstage_bytes = s->bstage_bytes;
-  p.mask_bytes = s->mask_bytes;
-  p.row_flags = d_row_flags;
-  for (int g = 0; g < p.n_groups; ++g) {
-    const Group& gr = c->groups[g];
-    p.g[g].col_off = s->col_off[g];
-    p.g[g].C = gr.C;
-    p.g[g].Kd = gr.Kd;
-    p.g[g].n = gr.n;
-    p.g[g].counts = c->d_counts + (int64_t)g * c->reserved_variants * 4;
-    p.g[g].dots = c->d_dots + c->dots_offset[g];
-    p.g[g].colscale = s->d_colscale + s->scale_off[g];
-    p.g[g].mask_hi = s->d_mask_hi + (int64_t)g * (gr.ns_pad / 16);
-    p.g[g].mask_all = ((int64_t)gr.n == c->n_samples_total) ? 1 : 0;
-  }
-  // cluster size: LRR_TC_CLUSTER env (1, 2, 4) overrides the default of 2
-  int cs = s->cluster;
-  if (p.n_tiles < 2 * cs) cs = 1;
-  void* kfn = nullptr;
+  for (const Pass& ps : s->passes) {
+    Params p;
+    memset(&p, 0, sizeof p);
+    p.M = M;
+    p.n_tiles = (int)((M + TILE_M - 1) / TILE_M);
+    p.n_chunks = (int)(stride / 128);
+    p.ncols = ps.ncols;
+    p.n_gstages = ps.n_gstages;
+    p.n_bstages = ps.n_bstages;
+    p.n_groups = (int)ps.segs.size();
+    p.ring_base = ps.ring_base;
+    p.ring_groups = ps.ring_groups;
+    p.gstage_bytes = ps.gstage_bytes;
+    p.bstage_bytes = ps.bstage_bytes;
+    p.mask_bytes = ps.mask_bytes;
+    p.row_flags = d_row_flags;
+    for (int i = 0; i < p.n_groups; ++i) {
+      const Segment& sg = ps.segs[i];
+      const Group& gr = c->groups[sg.group];
+      p.g[i].col_off = sg.row0;
+      p.g[i].C = sg.n_cols;
+      p.g[i].Kd = sg.kd_in;
+      p.g[i].n = gr.n;
+      p.g[i].counts = c->d_counts + (int64_t)sg.group * c->reserved_variants * 4;
+      p.g[i].dots = c->d_dots + c->dots_offset[sg.group] + sg.c_first;
+      p.g[i].dots_stride = gr.C;
+      p.g[i].colscale = s->d_colscale + s->scale_off[sg.group] + sg.c_first;
+      p.g[i].mask_hi = s->d_mask_hi + (int64_t)sg.group * (gr.ns_pad / 16);
+      p.g[i].mask_all = ((int64_t)gr.n == c->n_samples_total) ? 1 : 0;
+    }
+    // cluster size: LRR_TC_CLUSTER env (1, 2, 4) overrides the default of 2
+    int cs = s->cluster;
+    if (p.n_tiles < 2 * cs) cs = 1;
+    void* kfn = nullptr;
 #define LRR_PICK(NG_)                                                                       \
   (cs == 4 ? (void*)tc_sweep_kernel<NG_, 4> : cs == 2 ? (void*)tc_sweep_kernel<NG_, 2> : (void*)tc_sweep_kernel<NG_, 1>)
-  kfn = p.n_groups == 1 ? LRR_PICK(1) : p.n_groups == 2 ? LRR_PICK(2) : LRR_PICK(0);
+    kfn = p.n_groups == 1 ? LRR_PICK(1) : p.n_groups == 2 ? LRR_PICK(2) : LRR_PICK(0);
 #undef LRR_PICK
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = (size_t)s->smem_bytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int max_clusters = c->sm_count / cs;
-  if (cs > 1) {
-    cfg.gridDim = dim3((unsigned)(c->sm_count / cs * cs));
-    int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, kfn, &cfg) == cudaSuccess && nc > 0) max_clusters = nc;
-    else cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = (size_t)ps.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = c->sm_count / cs;
+    if (cs > 1) {
+      cfg.gridDim = dim3((unsigned)(c->sm_count / cs * cs));
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, kfn, &cfg) == cudaSuccess && nc > 0) max_clusters = nc;
+      else cudaGetLastError();
+    }
+    int n_cta = max_clusters * cs;
+    const int need = (p.n_tiles + cs - 1) / cs * cs;
+    if (n_cta > need) n_cta = need;
+    cfg.gridDim = dim3((unsigned)n_cta);
+    void* args[3] = {(void*)&geno_map, (void*)&ps.b_map, (void*)&p};
+    LRR_CUDA(c, cudaLaunchKernelExC(&cfg, kfn, args));
+    c->launches++;
+    LRR_CUDA(c, cudaGetLastError());
   }
-  int n_cta = max_clusters * cs;
-  const int need = (p.n_tiles + cs - 1) / cs * cs;
-  if (n_cta > need) n_cta = need;
-  cfg.gridDim = dim3((unsigned)n_cta);
-  void* args[3] = {(void*)&geno_map, (void*)&s->b_map, (void*)&p};
-  LRR_CUDA(c, cudaLaunchKernelExC(&cfg, kfn, args));
-  c->launches++;
-  LRR_CUDA(c, cudaGetLastError());
   return LRR_OK;
 }
 

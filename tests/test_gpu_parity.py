@@ -417,3 +417,53 @@ def test_mixed_one_plane_two_plane_tiles_many_tiles_per_cta():
     mt2 = hb.MatrixTable(gt2, cols={"y": y, "c1": cov[:, 1], "c2": cov[:, 2]})
     h2 = hb.linear_regression_rows(y=mt2.y, x=mt2.GT.n_alt_alleles(), covariates=[1.0, mt2.c1, mt2.c2], _kernel="tc")
     assert np.array_equal(h2.beta, ht.beta, equal_nan=True) and np.array_equal(h2.p_value, ht.p_value, equal_nan=True)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_many_phenotypes_multi_pass(kernel):
+    """BASELINE config 4 in miniature: many phenotypes -> more digit columns than one sweep holds (multi-pass)."""
+    hb = _hb()
+    N, M, P, K = 3000, 640, 45, 6
+    mt = hb.balding_nichols_model(3, N, M, missing_rate=0.02, seed=13)
+    rng = np.random.default_rng(14)
+    dos = mt.genotypes.to_dosage().astype(np.float64)
+    dos[dos < 0] = np.nan
+    cov = np.column_stack([np.ones(N)] + [rng.normal(size=N) for _ in range(K - 1)])
+    ys = rng.normal(size=(N, P)) + 0.1 * np.nan_to_num(dos[:P].T)
+    ys[rng.random(N) < 0.03, 0] = np.nan
+    mt = mt.annotate_cols(**{f"y{i}": ys[:, i] for i in range(P)}, **{f"c{i}": cov[:, i] for i in range(1, K)})
+    ht = hb.linear_regression_rows(y=[mt[f"y{i}"] for i in range(P)], x=mt.GT.n_alt_alleles(),
+                                   covariates=[1.0] + [mt[f"c{i}"] for i in range(1, K)], _kernel=kernel)
+    want = O.linreg_group(dos, ys, cov)
+    assert ht.beta.shape == (M, P)
+    assert_fields_close(_as_oracle_dict(ht), {k: v for k, v in want.items() if k != "_d"}, t_floor=1e-9, ctx=kernel)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_many_chained_groups(kernel):
+    """More groups than one sweep's segment table holds (5 chained groups with different missingness)."""
+    hb = _hb()
+    N, M, G = 1200, 300, 5
+    mt = hb.balding_nichols_model(3, N, M, missing_rate=0.1, seed=17)
+    rng = np.random.default_rng(18)
+    dos = mt.genotypes.to_dosage().astype(np.float64)
+    dos[dos < 0] = np.nan
+    cov = np.column_stack([np.ones(N), rng.normal(size=(N, 2))])
+    ys = []
+    for g in range(G):
+        y = rng.normal(size=(N, 1 + g % 2))
+        y[rng.random(N) < 0.05 * (g + 1)] = np.nan
+        ys.append(y)
+    cols = {f"c{i}": cov[:, i] for i in range(1, 3)}
+    for g in range(G):
+        for j in range(ys[g].shape[1]):
+            cols[f"y{g}_{j}"] = ys[g][:, j]
+    mt = mt.annotate_cols(**cols)
+    ht = hb.linear_regression_rows(y=[[mt[f"y{g}_{j}"] for j in range(ys[g].shape[1])] for g in range(G)],
+                                   x=mt.GT.n_alt_alleles(), covariates=[1.0, mt.c1, mt.c2], _kernel=kernel)
+    want = O.linreg_chained(dos, ys, cov)
+    for g in range(G):
+        got = {"n": ht.n[:, g], "sum_x": ht.sum_x[:, g]}
+        for f in ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+            got[f] = ht[f][g]
+        assert_fields_close(got, {k: v for k, v in want[g].items() if k != "_d"}, t_floor=1e-9, ctx=f"{kernel} g={g}")
