@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--variants", type=int, default=N_VARIANTS, help="variants per GPU")
     ap.add_argument("--missing-rate", type=float, default=0.0)
+    ap.add_argument("--phenotypes", type=int, default=N_PHENO, help="BASELINE config 4 uses 128")
     ap.add_argument("--chained", action="store_true",
                     help="BASELINE config 3: y=[[y1],[y2]] with 10 %% / 20 %% phenotype missingness (use with --missing-rate 0.25)")
     ap.add_argument("--e2e-variants", type=int, default=65536)
@@ -50,10 +51,10 @@ def parse():
     return ap.parse_args()
 
 
-def phenotypes_and_covariates(n, seed=1):
+def phenotypes_and_covariates(n, seed=1, n_pheno=N_PHENO):
     rng = np.random.Generator(np.random.Philox(key=[seed, 0x9E]))
     cov = np.column_stack([np.ones(n)] + [rng.standard_normal(n) for _ in range(N_COV - 1)])
-    y = rng.standard_normal((n, N_PHENO))
+    y = rng.standard_normal((n, n_pheno))
     return y, cov
 
 
@@ -141,7 +142,7 @@ def run_ours(a):
     pop, th, _ = bn.bn_parameters(3, N, M, missing_rate=a.missing_rate, seed=seed, first_variant=first)
     gt = bn.bn_fill(hb.PackedGenotypes.empty(M, N, dev), pop, th, seed=seed, first_variant=first)
     del th
-    y, cov = phenotypes_and_covariates(N)
+    y, cov = phenotypes_and_covariates(N, n_pheno=a.phenotypes)
     ctx = _lib.context(local)
     lib = ctx.lib
 
@@ -185,7 +186,7 @@ def run_ours(a):
         go[g].log10_p = None
         outs_all.append(o)
     out = outs_all[0]
-    rows = torch.stack([out["sum_x"]] + [out[f][:, 0] for f in STAT_FIELDS], dim=1)  # result row block for the gather
+    rows = torch.cat([out["sum_x"][:, None]] + [out[f] for f in STAT_FIELDS], dim=1)  # result row block for the gather
     kid = _lib.KERNELS[a.kernel]
     stream = torch.cuda.current_stream(dev).cuda_stream
     ctx.check(lib.lrr_set_timing(ctx.handle, 1))
@@ -199,7 +200,7 @@ def run_ours(a):
                     dist.broadcast(x, 0)
         ctx.check(lib.lrr_run(ctx.handle, gt.data.data_ptr(), gt.flags_ptr(), M, gt.stride, N, go, G, kid, stream))
         if world > 1:
-            torch.stack([out["sum_x"]] + [out[f][:, 0] for f in STAT_FIELDS], dim=1, out=rows)
+            torch.cat([out["sum_x"][:, None]] + [out[f] for f in STAT_FIELDS], dim=1, out=rows)
             hd.gather_rows(rows, counts=[M] * world)
         if timed:
             sweep_ms.append(lib.lrr_last_sweep_ms(ctx.handle))
@@ -252,7 +253,8 @@ def run_ours(a):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 epilogue; sweep " + ("int8 x int8 -> int32 exact (tcgen05)" if kernel_used == "tc" else "f64 FMA"),
         "data": "synthetic (seeded Balding-Nichols style, generated in HBM)",
-        "config": {"workload": WORKLOAD if (N, M) == (N_SAMPLES, N_VARIANTS) else f"REDUCED {N} samples x {M} variants",
+        "config": {"workload": WORKLOAD if (N, M, P, G, a.missing_rate) == (N_SAMPLES, N_VARIANTS, N_PHENO, 1, 0.0)
+                   else f"NON-HEADLINE {N} samples x {M} variants, P={P}, groups={G}, missing={a.missing_rate}",
                    "samples": N, "variants_per_gpu": M, "phenotypes": P, "covariates": K, "missing_rate": a.missing_rate, "groups": G,
                    "kernel": kernel_used, "parallelism": f"variant-sharded x{world}",
                    "l2": "inputs larger than L2 (packed genotypes %.1f GB per GPU)" % (gt.nbytes / 1e9)},

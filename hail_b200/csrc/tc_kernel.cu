@@ -293,7 +293,9 @@ struct Barriers {
   uint64_t d_empty;              // accumulators read out (4 epilogue warps)
   uint32_t tmem_base;
   uint32_t pad;
-  int32_t n2_xchg[SLOTS - 1][MAX_GROUPS][TILE_M];  // hom-alt popcounts of slots 1..3, handed to the epilogue warps
+  // hom-alt popcounts of slots 1..3, handed to the epilogue warps; double-buffered by tile parity because the
+  // producing warps may finish the whole next tile (when it has <= ring-depth chunks) during this tile's epilogue
+  int32_t n2_xchg[2][SLOTS - 1][MAX_GROUPS][TILE_M];
 };
 
 __device__ __forceinline__ bool tile_has_missing(const Params& p, int tile) {
@@ -603,7 +605,9 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
       const int hh = TP ? (s >> 1) : 0;                   // which group of the chunk this warp feeds
       const uint32_t in_group = TP ? (uint32_t)(s & 1) * 32u : (uint32_t)s * 32u;
       int pend_rg = -1;    // TMEM store issued but not yet published to the MMA warp
-      for (int ch = 0; ch < p.n_chunks; ++ch) {
+      // one chunk: `rg` / `rg_par` = ring group and pass parity of this warp's group instance, `pend` = the ring
+      // group of the previous chunk's store (-1: none).  With compile-time arguments everything folds.
+      auto chunk_body = [&](const int rg, const uint32_t rg_par, const int pend) {
         mbar_wait(gbar, g_phase);
         // packed bytes of samples [128 s, 128 s + 128) of this row
         const uint4 w0 = lds128(gaddr + ld0);
@@ -654,16 +658,12 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(gbar + 8u * MAX_GSTAGES);
         // retire the previous chunk's TMEM store only now: its latency hid behind this chunk's unpack arithmetic
-        if (pend_rg >= 0) {
+        if (pend >= 0) {
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane < (TP ? 2 : 1)) mbar_arrive(AFULL(pend_rg));
+          if (lane < (TP ? 2 : 1)) mbar_arrive(AFULL(pend));
         }
-        // this warp's group instance: rg0 (+1 for the second group of a two-plane chunk)
-        int rg = rg0 + hh;
-        uint32_t rg_par = rg0_par;
-        if (rg >= ring_groups) { rg -= ring_groups; rg_par ^= 1; }
         mbar_wait(AEMPTY(rg), rg_par ^ 1u);
         tc_fence_after();
         const uint32_t a_c = a_ring + rg * GROUP_COLS + in_group;
@@ -688,13 +688,33 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
           for (int i = 0; i < 32; ++i) x ^= rc[i];
           if (x == 0x12345678u) n2[0] += 1; }
 #endif
-        pend_rg = rg;
-        rg0 += TP ? 2 : 1;
-        if (rg0 >= ring_groups) { rg0 -= ring_groups; rg0_par ^= 1; }
         gaddr += p.gstage_bytes;
         gbar += 8u;
         if (gaddr == gaddr_end) { gaddr = smem0; gbar = GFULL(0); g_phase ^= 1; }
+      };
+      // generic step: ring position from the running counters
+      auto generic_chunk = [&]() {
+        int rg = rg0 + hh;   // this warp's group instance: rg0 (+1 for the second group of a two-plane chunk)
+        uint32_t rg_par = rg0_par;
+        if (rg >= ring_groups) { rg -= ring_groups; rg_par ^= 1; }
+        chunk_body(rg, rg_par, pend_rg);
+        pend_rg = rg;
+        rg0 += TP ? 2 : 1;
+        if (rg0 >= ring_groups) { rg0 -= ring_groups; rg0_par ^= 1; }
+      };
+      int ch = 0;
+      if (!TP && ring_groups == 3) {
+        // steady state of one-plane tiles: unrolled over the 3 ring groups (positions become constants)
+        do { generic_chunk(); ++ch; } while (ch < p.n_chunks && rg0 != 0);
+        for (; ch + 3 <= p.n_chunks; ch += 3) {   // entered with rg0 == 0 and pend_rg == 2
+          chunk_body(0, rg0_par, pend_rg);
+          chunk_body(1, rg0_par, 0);
+          chunk_body(2, rg0_par, 1);
+          rg0_par ^= 1;
+          pend_rg = 2;
+        }
       }
+      for (; ch < p.n_chunks; ++ch) generic_chunk();
       if (pend_rg >= 0) {   // flush the last chunk of the tile
         tmem_wait_st();
         tc_fence_before();
@@ -723,7 +743,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
       if (s > 0) {
 #pragma unroll
         for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g)
-          if (NG || g < n_groups) bars->n2_xchg[s - 1][g][row] = n2[g];
+          if (NG || g < n_groups) bars->n2_xchg[tile_i & 1][s - 1][g][row] = n2[g];
       }
       named_bar_sync(1, UNPACK_WARPS * 32);
       if (s == 0) {
@@ -735,7 +755,8 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
         for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
           if (!(NG || g < n_groups)) continue;
           const GroupMeta& G = p.g[g];
-          const int n2g = n2[g] + bars->n2_xchg[0][g][row] + bars->n2_xchg[1][g][row] + bars->n2_xchg[2][g][row];
+          const int n2g = n2[g] + bars->n2_xchg[tile_i & 1][0][g][row] + bars->n2_xchg[tile_i & 1][1][g][row] +
+                          bars->n2_xchg[tile_i & 1][2][g][row];
           // the group's columns: Kd x N_SLICES_Q then P x N_SLICES_Y digit columns, then one "ones" column
           const int n_digit_cols = G.Kd * N_SLICES_Q + (G.C - G.Kd) * N_SLICES_Y;
           const int ones_col = G.col_off + n_digit_cols;
