@@ -22,6 +22,7 @@
 // (0..3), plane "m" the indicator [code == 3]; sum_j B (x0 + mean * m) = (Dc - 3 Dm) + mean * Dm.  Tiles whose
 // rows carry no missing call (row_flags from ingest) skip plane m entirely.
 #include <cuda.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 
@@ -59,6 +60,9 @@ constexpr int THREADS = 19 * 32;
 #ifndef LRR_ABL_NO_UNPACK
 #define LRR_ABL_NO_UNPACK 0
 #endif
+#ifndef LRR_ABL_HALF_B
+#define LRR_ABL_HALF_B 0     // 1: fetch only half of every basis-panel stage (pair mode)
+#endif
 #ifndef LRR_ABL_NO_BPANEL
 #define LRR_ABL_NO_BPANEL 0
 #endif
@@ -68,7 +72,10 @@ constexpr int THREADS = 19 * 32;
 constexpr int GENO_BYTES = TILE_M * 128;   // 16 KB
 constexpr int MAX_GROUPS = 4;
 constexpr int MAX_GSTAGES = 10;        // genotype ring (16 KB per stage)
-constexpr int MAX_BSTAGES = 4;         // basis-panel ring (4 * ncols * 128 B per stage)
+#ifndef LRR_TC_NB
+#define LRR_TC_NB 6                     // preferred depth of the basis-panel ring (6 or 3: the depths the MMA fast path is unrolled for)
+#endif
+constexpr int MAX_BSTAGES = 6;         // basis-panel ring (4 * ncols * 128 B per stage)
 constexpr int MAX_RING = 4;            // A ring groups (GROUP_COLS TMEM columns each)
 constexpr int GROUP_COLS = 128;        // one-plane: 4 slots of plane c; two-plane: 2 slots of plane c + 2 of plane m
 // Balanced base-256 digits per basis column.  The residualised phenotype columns feed beta directly and get 48
@@ -146,20 +153,32 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
       "l"(map), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
-// same copy delivered to the same shared-memory offset (and mbarrier) of every CTA in `cta_mask`
-__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint32_t bar, uint32_t dst, int x, int y,
-                                               uint16_t cta_mask) {
+// commit of a CTA pair's MMAs: arrives on the barrier at the same offset in both CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
-      "%4}], [%2], %5;" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(x), "r"(y), "h"(cta_mask)
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
       : "memory");
 }
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
+// TMA load issued by either CTA of a pair whose completion bytes are counted on the LEADER's mbarrier
+// (`bar` is a shared::cluster address, see mapa_leader)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar, uint32_t dst, int x, int y) {
   asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-      "h"(cta_mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y)
       : "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA 0 of the cluster
+__device__ __forceinline__ uint32_t mapa_leader(uint32_t addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(0));
+  return r;
+}
+// arrive on a barrier of the peer CTA.  Default (.release.cta) semantics on purpose: what is handed over lives in
+// tensor memory and is ordered by tcgen05.fence::before/after_thread_sync around the barrier; a .release.cluster
+// arrive compiles to a GPU-scope MEMBAR per call (measured: 2x slower sweep).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -198,6 +217,18 @@ __device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same for a CTA pair (M = 256: 128 rows in each CTA's tensor memory, B halves in each CTA's shared memory)
+__device__ __forceinline__ void mma_i8_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -268,13 +299,13 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 }
 
 // instruction descriptor: D = s32, A = u8 (K-major, from TMEM), B = s8 (K-major), M = 128, N = ncols
-__device__ __forceinline__ uint32_t make_idesc(int n) {
+__device__ __forceinline__ uint32_t make_idesc(int n, int m) {
   uint32_t d = 0;
   d |= 2u << 4;                   // c_format = S32
   d |= 0u << 7;                   // a_format = unsigned 8-bit
   d |= 1u << 10;                  // b_format = signed 8-bit
   d |= (uint32_t)(n >> 3) << 17;  // N
-  d |= (uint32_t)(TILE_M >> 4) << 24;  // M
+  d |= (uint32_t)(m >> 4) << 24;       // M (256 for a CTA pair)
   return d;
 }
 
@@ -317,8 +348,14 @@ __device__ __forceinline__ bool tile_has_missing(const Params& p, int tile) {
 }
 
 // NG = number of groups known at compile time (1, 2) or 0 = run-time p.n_groups.
-// CS = thread-block cluster size (1, 2, 4): the CTAs of a cluster sweep CS consecutive variant tiles in lockstep
-// and share every basis panel -- each CTA fetches 4/CS of the chunk's panels and TMA-multicasts them to all.
+// CS = 1: one CTA per 128-variant tile, tcgen05.mma.cta_group::1.
+// CS = 2: a CTA pair (cluster of 2, two SMs of one TPC) sweeps two consecutive tiles as ONE M = 256 MMA
+//   (tcgen05.mma.cta_group::2 issued by the leader, rank 0): each CTA unpacks its own 128 variants into its own
+//   tensor memory and holds HALF of the rows of every basis panel in its shared memory, so the L2 -> SM traffic of
+//   the basis halves against two single CTAs and one instruction feeds both tensor cores.  Cross-CTA hand-offs:
+//   "A ring slot written" and "accumulators read out" are counted on the leader's barriers (remote arrives of the
+//   peer's warps); the leader's commits are multicast to both CTAs' "slot / stage / accumulator" barriers; the basis
+//   TMA of either CTA completes its bytes on the leader's "stage filled" barrier.
 //
 // Two independent shared-memory rings: the genotype tiles come from HBM (long latency, 16 KB per chunk, released
 // as soon as the unpack warps have read them -> deep prefetch), the basis panels come from L2 (short latency,
@@ -326,6 +363,7 @@ __device__ __forceinline__ bool tile_has_missing(const Params& p, int tile) {
 template <int NG, int CS>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_constant__ CUtensorMap b_map, const Params p) {
+  static_assert(CS == 1 || CS == 2, "one CTA or a CTA pair");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // genotype ring base (shared window address)
   uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
@@ -353,20 +391,26 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
     }
     for (int s = 0; s < p.n_bstages; ++s) {
       mbar_init(BFULL(s), 1);
-      mbar_init(BEMPTY(s), CS);   // the MMA commit of every CTA in the cluster
+      mbar_init(BEMPTY(s), 1);    // the (pair-multicast) MMA commit
     }
     for (int s = 0; s < p.ring_groups; ++s) {
-      mbar_init(AFULL(s), UNPACK_WARPS);   // one-plane: 16 warps x 1 arrival; two-plane: 8 warps x 2 arrivals
+      mbar_init(AFULL(s), UNPACK_WARPS * CS);   // per CTA, one-plane: 16 warps x 1 arrival; two-plane: 8 warps x 2
       mbar_init(AEMPTY(s), 1);
     }
     mbar_init(DFULL, 1);
-    mbar_init(DEMPTY, 4);
+    mbar_init(DEMPTY, 4 * CS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WARP_MMA) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CS == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   if (warp == WARP_TMA_G && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&geno_map) : "memory");
   if (warp == WARP_TMA_B && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&b_map) : "memory");
@@ -382,8 +426,13 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
   const int first_tile = (CS > 1 ? (int)cluster_id_x() * CS : (int)blockIdx.x) + cta_rank;
   const int tile_step = CS > 1 ? (int)n_clusters_x() * CS : (int)gridDim.x;
   const int tile_end = CS > 1 ? p.n_tiles + cta_rank : p.n_tiles;   // (tile - rank) < n_tiles for every CTA alike
-  const int panel_bytes = p.ncols * 128;
-  const uint16_t cluster_mask = (uint16_t)((1u << CS) - 1u);
+  const int panel_bytes = p.ncols / CS * 128;   // this CTA's rows of one basis panel
+  // the mode of a tile pair is the pair's: both CTAs, and the one MMA stream, must agree on the ring layout
+  auto tile_mode = [&](int tile) {
+    if (CS == 1) return tile_has_missing(p, tile);
+    const int t0 = tile - cta_rank;
+    return tile_has_missing(p, t0) || tile_has_missing(p, t0 + 1);
+  };
 
   if (warp == WARP_TMA_G) {
     // ============================== genotype producer ==============================
@@ -421,17 +470,19 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
 #if LRR_ABL_NO_BPANEL
           mbar_arrive(BFULL(bs));
 #else
-          mbar_arrive_expect_tx(BFULL(bs), (uint32_t)(SLOTS * panel_bytes));
           if (CS == 1) {
+            mbar_arrive_expect_tx(BFULL(bs), (uint32_t)(SLOTS * panel_bytes));
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s)
               tma_load_2d(&b_map, BFULL(bs), sbase + s * panel_bytes, ch * CHUNK + s * SLOT, 0);
           } else {
+            // both halves complete on the leader's barrier; only the leader arms it (for the bytes of both)
+            if (cta_rank == 0) mbar_arrive_expect_tx(BFULL(bs), (uint32_t)(2 * (SLOTS >> LRR_ABL_HALF_B) * panel_bytes));
+            const uint32_t full_leader = mapa_leader(BFULL(bs));
 #pragma unroll
-            for (int k = 0; k < SLOTS / CS; ++k) {
-              const int s = cta_rank * (SLOTS / CS) + k;
-              tma_load_2d_mc(&b_map, BFULL(bs), sbase + s * panel_bytes, ch * CHUNK + s * SLOT, 0, cluster_mask);
-            }
+            for (int s = 0; s < (SLOTS >> LRR_ABL_HALF_B); ++s)
+              tma_load_2d_pair(&b_map, full_leader, sbase + s * panel_bytes, ch * CHUNK + s * SLOT,
+                               cta_rank * (p.ncols / 2));
           }
 #endif
         }
@@ -441,11 +492,22 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
     }
   } else if (warp == WARP_MMA) {
     // ============================== MMA issuer ==============================
+    // (CTA pair: only the leader issues; the peer's MMA warp just owns its half of the tensor-memory allocation)
+    if (CS == 1 || cta_rank == 0) {
     // The whole warp runs the loop in uniform control flow; one elected lane issues tcgen05.mma / commit.
     // This warp's serial instruction stream is what paces the kernel, so the steady state of one-plane tiles is
     // unrolled over the (equal) depths of the basis-panel ring and the A ring: every shared-memory, tensor-memory
     // and barrier address is then a base plus a compile-time constant and stays on the uniform datapath.
-    const uint32_t idesc = make_idesc(LRR_ABL_MMA_N ? LRR_ABL_MMA_N : p.ncols);
+    const uint32_t idesc = make_idesc(LRR_ABL_MMA_N ? LRR_ABL_MMA_N : p.ncols, TILE_M * CS);
+    auto mma = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t acc) {
+      if (CS == 1) mma_i8_ts(d, a, b, idesc, acc); else mma_i8_ts_pair(d, a, b, idesc, acc);
+    };
+    auto commit = [&](uint32_t bar) {
+      if (CS == 1) tc_commit(bar); else tc_commit_pair(bar);
+    };
+    auto wait_peer = [&](uint32_t bar, uint32_t parity) {   // barriers the peer CTA's warps arrive on, too
+      mbar_wait(bar, parity);
+    };
     int bs = 0;
     uint32_t b_phase = 0;
     int rg = 0;              // ring group of the next group instance (instances are numbered across tiles)
@@ -458,7 +520,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
 
     // one group instance, any mode (alignment, tails, two-plane tiles)
     auto generic_group = [&](int ch, int s0, bool two_plane, int gsl) {
-      mbar_wait(AFULL(rg), rg_par);
+      wait_peer(AFULL(rg), rg_par);
       tc_fence_after();
       const uint32_t a_g = a_ring + rg * GROUP_COLS;
       const uint64_t bd = desc0 + (uint64_t)(bs * stage_d);
@@ -469,7 +531,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
           for (int k = 0; k < 4; ++k)
 #pragma unroll
             for (int j = 0; j < LRR_ABL_MMA_J; ++j)
-              mma_i8_ts(tmem, a_g + k * 32 + j * 8, bd + (uint64_t)(k * panel_d + j * 2), idesc, (ch | k | j) ? 1u : 0u);
+              mma(tmem, a_g + k * 32 + j * 8, bd + (uint64_t)(k * panel_d + j * 2), (ch | k | j) ? 1u : 0u);
         } else {
 #pragma unroll
           for (int k = 0; k < 2; ++k)
@@ -477,16 +539,13 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
             for (int j = 0; j < 4; ++j) {
               const uint32_t acc = (ch | s0 | k | j) ? 1u : 0u;
               const uint64_t d = bd + (uint64_t)((s0 + k) * panel_d + j * 2);
-              mma_i8_ts(tmem, a_g + k * 32 + j * 8, d, idesc, acc);
-              mma_i8_ts(tmem + p.ncols, a_g + 64 + k * 32 + j * 8, d, idesc, acc);
+              mma(tmem, a_g + k * 32 + j * 8, d, acc);
+              mma(tmem + p.ncols, a_g + 64 + k * 32 + j * 8, d, acc);
             }
         }
 #endif
-        tc_commit(AEMPTY(rg));
-        if (s0 + gsl == SLOTS) {
-          if (CS == 1) tc_commit(BEMPTY(bs));
-          else tc_commit_mc(BEMPTY(bs), cluster_mask);   // the panels of this stage may be overwritten by any peer
-        }
+        commit(AEMPTY(rg));
+        if (s0 + gsl == SLOTS) commit(BEMPTY(bs));
       }
       __syncwarp();
       if (++rg == p.ring_groups) { rg = 0; rg_par ^= 1; }
@@ -498,12 +557,14 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
       if (++bs == p.n_bstages) { bs = 0; b_phase ^= 1; }
     };
 
-    constexpr int NB = 3;   // the fast path is unrolled over NB chunks == the depth of the basis-panel ring
+    // the fast path is unrolled over NB chunks == the depth of the basis-panel ring (6 when shared memory allows:
+    // the panels come from L2 behind the HBM stream and 3 stages do not cover that latency; measured +10 %)
     // Fast path of one tile, compile-time mode (TP) and A-ring depth (RG).  Requires b-stage 0 and ring group 0 at
     // entry and (NB * groups-per-chunk) % RG == 0, so that ring positions repeat every NB chunks.
-    auto fast_chunks = [&](auto tp_tag, auto rg_tag, int& ch) {
+    auto fast_chunks = [&](auto tp_tag, auto rg_tag, auto nb_tag, int& ch) {
       constexpr bool TP = decltype(tp_tag)::value;
       constexpr int RG = decltype(rg_tag)::value;
+      constexpr int NB = decltype(nb_tag)::value;
       constexpr int GPC = TP ? 2 : 1;              // group instances per chunk
       constexpr int WRAPS = NB * GPC / RG;         // ring passes per unrolled block
       static_assert((NB * GPC) % RG == 0, "ring positions must repeat every NB chunks");
@@ -518,7 +579,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
             const int inst = u * GPC + h;
             const int g = inst % RG;
             const uint32_t par = rg_par ^ (uint32_t)((inst / RG) & 1);
-            mbar_wait(AFULL(g), par);
+            wait_peer(AFULL(g), par);
             tc_fence_after();
             if (elect_one()) {
 #if !LRR_ABL_NO_MMA
@@ -529,7 +590,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
 #pragma unroll
                   for (int j = 0; j < LRR_ABL_MMA_J; ++j) {
                     const uint32_t acc = (u | k | j) ? 1u : (ch ? 1u : 0u);
-                    mma_i8_ts(tmem, a_g + k * 32 + j * 8, bd + (uint64_t)(k * panel_d + j * 2), idesc, acc);
+                    mma(tmem, a_g + k * 32 + j * 8, bd + (uint64_t)(k * panel_d + j * 2), acc);
                   }
               } else {
 #pragma unroll
@@ -538,16 +599,13 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
                   for (int j = 0; j < 4; ++j) {
                     const uint32_t acc = (u | h | k | j) ? 1u : (ch ? 1u : 0u);
                     const uint64_t d = bd + (uint64_t)((2 * h + k) * panel_d + j * 2);
-                    mma_i8_ts(tmem, a_g + k * 32 + j * 8, d, idesc, acc);
-                    mma_i8_ts(tmem + p.ncols, a_g + 64 + k * 32 + j * 8, d, idesc, acc);
+                    mma(tmem, a_g + k * 32 + j * 8, d, acc);
+                    mma(tmem + p.ncols, a_g + 64 + k * 32 + j * 8, d, acc);
                   }
               }
 #endif
-              tc_commit(AEMPTY(g));
-              if (h == GPC - 1) {
-                if (CS == 1) tc_commit(BEMPTY(u));
-                else tc_commit_mc(BEMPTY(u), cluster_mask);   // any peer may overwrite this stage's panels
-              }
+              commit(AEMPTY(g));
+              if (h == GPC - 1) commit(BEMPTY(u));
             }
             __syncwarp();
           }
@@ -558,21 +616,28 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
     };
 
     for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
-      const bool two_plane = tile_has_missing(p, tile);
-      mbar_wait(DEMPTY, (tile_i & 1) ^ 1);   // the previous tile's accumulators have been read out
+      const bool two_plane = tile_mode(tile);
+      wait_peer(DEMPTY, (tile_i & 1) ^ 1);   // the previous tile's accumulators have been read out (by both CTAs)
       tc_fence_after();
       int ch = 0;
-      if (p.n_bstages == NB) {
+      if (p.n_bstages == 6 || p.n_bstages == 3) {
         while (ch < p.n_chunks && bs != 0) generic_chunk(ch++, two_plane);   // align to b-stage 0
         if (rg == 0 && ch < p.n_chunks) {
-          if (!two_plane && p.ring_groups == 3) fast_chunks(FalseTag{}, IntTag<3>{}, ch);
-          else if (two_plane && p.ring_groups == 3) fast_chunks(TrueTag{}, IntTag<3>{}, ch);
-          else if (two_plane && p.ring_groups == 2) fast_chunks(TrueTag{}, IntTag<2>{}, ch);
+          if (p.n_bstages == 6) {
+            if (!two_plane && p.ring_groups == 3) fast_chunks(FalseTag{}, IntTag<3>{}, IntTag<6>{}, ch);
+            else if (two_plane && p.ring_groups == 3) fast_chunks(TrueTag{}, IntTag<3>{}, IntTag<6>{}, ch);
+            else if (two_plane && p.ring_groups == 2) fast_chunks(TrueTag{}, IntTag<2>{}, IntTag<6>{}, ch);
+          } else {
+            if (!two_plane && p.ring_groups == 3) fast_chunks(FalseTag{}, IntTag<3>{}, IntTag<3>{}, ch);
+            else if (two_plane && p.ring_groups == 3) fast_chunks(TrueTag{}, IntTag<3>{}, IntTag<3>{}, ch);
+            else if (two_plane && p.ring_groups == 2) fast_chunks(TrueTag{}, IntTag<2>{}, IntTag<3>{}, ch);
+          }
         }
       }
       for (; ch < p.n_chunks; ++ch) generic_chunk(ch, two_plane);
-      if (elect_one()) tc_commit(DFULL);
+      if (elect_one()) commit(DFULL);
       __syncwarp();
+    }
     }
   } else {
     // ============================== unpack + epilogue warps ==============================
@@ -595,6 +660,12 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
     const int ring_groups = p.ring_groups;
     const uint32_t a_ring = tmem + lane_addr + p.ring_base;
     int n2[NG ? NG : MAX_GROUPS];
+    // "slot written" / "accumulators read out" are counted on the pair leader's barriers
+    const uint32_t afull_leader = (CS == 2) ? mapa_leader(AFULL(0)) : 0u;
+    const uint32_t dempty_leader = (CS == 2) ? mapa_leader(DEMPTY) : 0u;
+    auto arrive_afull = [&](int g) {
+      if (CS == 1) mbar_arrive(AFULL(g)); else mbar_arrive_cluster(afull_leader + 8u * (uint32_t)g);
+    };
 
     // The chunk loop of one tile, specialised at compile time on the tile's mode (TP: two planes, the tile has
     // missing calls) and on whether any group needs its sample mask for the hom-alt count (MA: none does).
@@ -627,7 +698,8 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
         }
         // 2-bit fields -> bytes.  Fields at bit offsets 0 and 4 of every byte keep their value c; fields at
         // offsets 2 and 6 are left in place (value 4c) -- their basis rows were quantised as v/4 -- so a
-        // 16-call word costs one shift and four masks.
+        // 16-call word costs one shift and four masks.  (Leaving all four fields in place -- c, 4c, 16c, 64c, no
+        // shift -- was measured: no faster, and it costs 4 more bits of the covariate digits.)
         uint32_t rc[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -641,15 +713,21 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
           rc[4 * i + 0] = w[i]; rc[4 * i + 1] = w[i]; rc[4 * i + 2] = w[i]; rc[4 * i + 3] = w[i];
 #endif
         }
-        // exact hom-alt counts per group (code 2: high bit set, low bit clear), for x.x = n1 + 4 n2
+        // exact counts per group for x.x = n1 + 4 n2.  Tiles without missing calls whose groups keep every sample
+        // count all set bits (n1 + n2; the epilogue solves with the ones column n1 + 2 n2); otherwise the hom-alt
+        // calls (code 2: high bit set, low bit clear) of the group's samples are counted directly.
 #pragma unroll
         for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
           if (NG || g < n_groups) {
             int acc = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const uint32_t m = MA ? 0xAAAAAAAAu : mm[g][i];
-              acc += TP ? __popc(w[i] & ~(w[i] << 1) & m) : __popc(w[i] & m);
+              if (MA && !TP) {
+                acc += __popc(w[i]);
+              } else {
+                const uint32_t m = MA ? 0xAAAAAAAAu : mm[g][i];
+                acc += TP ? __popc(w[i] & ~(w[i] << 1) & m) : __popc(w[i] & m);
+              }
             }
             n2[g] += acc;
           }
@@ -662,7 +740,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane < (TP ? 2 : 1)) mbar_arrive(AFULL(pend));
+          if (lane < (TP ? 2 : 1)) arrive_afull(pend);
         }
         mbar_wait(AEMPTY(rg), rg_par ^ 1u);
         tc_fence_after();
@@ -719,12 +797,12 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane < (TP ? 2 : 1)) mbar_arrive(AFULL(pend_rg));
+        if (lane < (TP ? 2 : 1)) arrive_afull(pend_rg);
       }
     };
 
     for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
-      const bool two_plane = tile_has_missing(p, tile);
+      const bool two_plane = tile_mode(tile);
       if (tile_i > 0 && two_plane != prev_two_plane) {
         // the ring is laid out differently: wait until every MMA of the previous tile has retired
         mbar_wait(DFULL, (tile_i - 1) & 1);
@@ -755,7 +833,7 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
         for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
           if (!(NG || g < n_groups)) continue;
           const GroupMeta& G = p.g[g];
-          const int n2g = n2[g] + bars->n2_xchg[tile_i & 1][0][g][row] + bars->n2_xchg[tile_i & 1][1][g][row] +
+          const int cnt = n2[g] + bars->n2_xchg[tile_i & 1][0][g][row] + bars->n2_xchg[tile_i & 1][1][g][row] +
                           bars->n2_xchg[tile_i & 1][2][g][row];
           // the group's columns: Kd x N_SLICES_Q then P x N_SLICES_Y digit columns, then one "ones" column
           const int n_digit_cols = G.Kd * N_SLICES_Q + (G.C - G.Kd) * N_SLICES_Y;
@@ -778,6 +856,8 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
           sc >>= 2;                           // the ones column carries 4 per unit (see the quantiser)
           nm >>= 2;
           const int S = sc - 3 * nm;          // n1 + 2 n2
+          // one-plane tiles of unmasked passes counted every set bit: n1 + n2 (see the unpack warps)
+          const int n2g = (!two_plane && p.mask_bytes == 0) ? S - cnt : cnt;
           const int n1 = S - 2 * n2g;
           const double mean = (double)S / (double)(G.n - nm);
           if (v < p.M) reinterpret_cast<int4*>(G.counts)[v] = make_int4(n1, n2g, nm, 0);
@@ -819,16 +899,19 @@ tc_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(DEMPTY);
+        if (lane == 0) {
+          if (CS == 1) mbar_arrive(DEMPTY); else mbar_arrive_cluster(dempty_leader);
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (CS > 1) cluster_sync_all();   // no CTA may exit while a peer can still multicast into it
+  if (CS > 1) cluster_sync_all();   // no CTA may exit while its peer can still signal / run MMAs into it
   if (warp == WARP_MMA) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (CS == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
 }
 
@@ -853,22 +936,44 @@ __global__ void quantize_kernel(const double* __restrict__ basis, const uint32_t
   // Imax = 127 * (256^S - 1) / 255 : the largest integer with S balanced digits in [-128, 127]
   const double imax = 127.0 * ((double)((1ull << (8 * nd)) - 1ull) / 255.0);
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ns_pad; j += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)((j >> 2) & 1);   // 1: the sample's field sits at bit offset 2 or 6 of its byte and reaches the MMA as 4c
     if (c == C) {
       const uint32_t mw = mask[j >> 4];
       // fields at bit offsets 2 / 6 of a byte reach the tensor core as 4c, the others as c (see the unpack warps)
       const int in_mask = (int)((mw >> sample_shift((int)(j & 15))) & 1u);
-      bq[(int64_t)first * ns_pad + j] = (int8_t)(in_mask * ((j & 4) ? 1 : 4));
+      bq[(int64_t)first * ns_pad + j] = (int8_t)(in_mask * (f ? 1 : 4));
       continue;
     }
     const double cm = __longlong_as_double((long long)colmax_bits[c]);
     long long I = 0;
-    if (cm > 0.0) I = __double2ll_rn(basis[(int64_t)c * ns_pad + j] / cm * ((j & 4) ? 0.25 * imax : imax));
+    if (cm > 0.0) I = __double2ll_rn(basis[(int64_t)c * ns_pad + j] / cm * (f ? 0.25 * imax : imax));
     for (int s = 0; s < nd; ++s) {
       long long d = ((I + 128) & 255) - 128;  // balanced digit in [-128, 127]
       bq[(int64_t)(first + s) * ns_pad + j] = (int8_t)d;
       I = (I - d) >> 8;
     }
     if (j == 0) colscale[c] = cm > 0.0 ? cm / imax : 0.0;
+  }
+}
+
+// Worst-case magnitude of any partial sum of one accumulator column: the A bytes are 3 (or 12, fields left in place)
+// at most, so for any genotypes |sum_j A_j d_j| <= max(sum_{d>0} a_j d_j, sum_{d<0} a_j |d_j|).  Checked against INT32
+// on the host: the tensor-core path is only used when no accumulator can overflow.
+__global__ void acc_bound_kernel(const int8_t* __restrict__ bq, int64_t ns_pad, unsigned long long* __restrict__ bound) {
+  const int64_t r = blockIdx.y;
+  unsigned long long pos = 0, neg = 0;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ns_pad; j += (int64_t)gridDim.x * blockDim.x) {
+    const int d = bq[r * ns_pad + j];
+    const unsigned long long a = ((j >> 2) & 1) ? 12ull : 3ull;
+    if (d > 0) pos += a * (unsigned long long)d; else neg += a * (unsigned long long)(-d);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    pos += __shfl_xor_sync(0xffffffffu, pos, o);
+    neg += __shfl_xor_sync(0xffffffffu, neg, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(bound + 2 * r, pos);
+    atomicAdd(bound + 2 * r + 1, neg);
   }
 }
 
@@ -894,13 +999,20 @@ struct Segment {
   int row0;      // first row of this segment in the pass's panel matrix (digit rows, then the ones row)
 };
 
+// launch shape of one pass for a given cluster size (the basis-panel box and ring depend on it: a CTA of a pair
+// holds half of the panel rows)
+struct PassShape {
+  int n_gstages = 0, n_bstages = 0, bstage_bytes = 0, smem_bytes = 0;
+  CUtensorMap b_map;
+};
+
 struct Pass {
   int ncols = 0;                 // panel rows, padded to 16
   int64_t bq_row0 = 0;           // first row of this pass in State::d_bq
   std::vector<Segment> segs;
-  int n_gstages = 0, n_bstages = 0, gstage_bytes = 0, bstage_bytes = 0, smem_bytes = 0;
+  int gstage_bytes = 0;
   int ring_base = 0, ring_groups = 0, mask_bytes = 0;
-  CUtensorMap b_map;
+  PassShape shape[2];            // [cluster size - 1]
 };
 
 struct State {
@@ -1015,10 +1127,6 @@ static int prepare(Ctx* c) {
     s->why = "no groups";
     return LRR_OK;
   }
-  if (c->n_samples_total > 1300000) {
-    s->why = "more than 1.3M samples: INT32 accumulators could overflow";
-    return LRR_OK;
-  }
   int nscale = 0;
   s->scale_off.assign(G, 0);
   for (size_t g = 0; g < G; ++g) {
@@ -1063,52 +1171,78 @@ static int prepare(Ctx* c) {
     }
   }
   LRR_CUDA(c, cudaGetLastError());
+  {
+    // exactness guard: no INT32 accumulator can overflow, whatever the genotypes are
+    unsigned long long* d_bound = nullptr;
+    LRR_CUDA(c, cudaMalloc(&d_bound, sizeof(unsigned long long) * 2 * (size_t)total_rows));
+    LRR_CUDA(c, cudaMemset(d_bound, 0, sizeof(unsigned long long) * 2 * (size_t)total_rows));
+    for (int64_t r0 = 0; r0 < total_rows; r0 += 65535)
+      acc_bound_kernel<<<dim3(gx, (unsigned)std::min<int64_t>(total_rows - r0, 65535)), 256>>>(s->d_bq + r0 * ns_pad, ns_pad,
+                                                                                            d_bound + 2 * r0);
+    c->launches++;
+    std::vector<unsigned long long> h_bound(2 * (size_t)total_rows);
+    cudaError_t e = cudaMemcpy(h_bound.data(), d_bound, sizeof(unsigned long long) * h_bound.size(), cudaMemcpyDeviceToHost);
+    cudaFree(d_bound);
+    if (e != cudaSuccess) return cuda_fail(c, e, "acc_bound_kernel");
+    unsigned long long worst = 0;
+    for (unsigned long long v : h_bound) worst = std::max(worst, v);
+    if (worst > 2147483647ull) {
+      s->why = "INT32 accumulators could overflow for this many samples (worst-case column bound " +
+               std::to_string(worst) + " > 2^31 - 1)";
+      return LRR_OK;
+    }
+  }
   LRR_CUDA(c, cudaDeviceSynchronize());
   const int budget = 227 * 1024 - (int)sizeof(Barriers) - 1024;
   for (auto& ps : s->passes) {
-    if (encode_2d(s, &ps.b_map, s->d_bq + ps.bq_row0 * ns_pad, (uint64_t)ns_pad, (uint64_t)ps.ncols, (uint64_t)ns_pad,
-                  SLOT, (uint32_t)ps.ncols)) {
-      s->why = "cuTensorMapEncodeTiled failed for the basis panels";
-      return LRR_OK;
-    }
     // shared memory: genotype ring (16 KB [+ group masks] per stage) + basis-panel ring + barriers + 1 KB slack
     ps.mask_bytes = any_masked ? (int)ps.segs.size() * 128 : 0;
     ps.gstage_bytes = (GENO_BYTES + ps.mask_bytes + 1023) / 1024 * 1024;
-    ps.bstage_bytes = SLOTS * ps.ncols * 128;
     ps.ring_base = (2 * ps.ncols + 31) / 32 * 32;
     ps.ring_groups = (512 - ps.ring_base) / GROUP_COLS;
     if (ps.ring_groups > MAX_RING) ps.ring_groups = MAX_RING;
-    int bst = 3;
-    if (const char* e = getenv("LRR_TC_BSTAGES")) bst = atoi(e);
-    if (bst > MAX_BSTAGES) bst = MAX_BSTAGES;
-    while (bst > 2 && budget - bst * ps.bstage_bytes < 3 * ps.gstage_bytes) --bst;
-    int gst = (budget - bst * ps.bstage_bytes) / ps.gstage_bytes;
-    if (gst > MAX_GSTAGES) gst = MAX_GSTAGES;
-    if (const char* e = getenv("LRR_TC_GSTAGES")) { const int v = atoi(e); if (v >= 2 && v < gst) gst = v; }
-    if (bst < 2 || gst < 2) {
-      s->why = "not enough shared memory for the genotype / basis-panel rings";
-      return LRR_OK;
-    }
     if (ps.ring_groups < 2) {
       s->why = "not enough tensor memory for the A ring";
       return LRR_OK;
     }
-    ps.n_gstages = gst;
-    ps.n_bstages = bst;
-    ps.smem_bytes = gst * ps.gstage_bytes + bst * ps.bstage_bytes + (int)sizeof(Barriers) + 1024;
+    for (int cs = 1; cs <= 2; ++cs) {
+      PassShape& sh = ps.shape[cs - 1];
+      const int rows = ps.ncols / cs;   // panel rows held by one CTA
+      if (encode_2d(s, &sh.b_map, s->d_bq + ps.bq_row0 * ns_pad, (uint64_t)ns_pad, (uint64_t)ps.ncols, (uint64_t)ns_pad,
+                    SLOT, (uint32_t)rows)) {
+        s->why = "cuTensorMapEncodeTiled failed for the basis panels";
+        return LRR_OK;
+      }
+      sh.bstage_bytes = SLOTS * rows * 128;
+      // basis-panel ring: 6 stages if at least 6 genotype stages still fit, else 3, else whatever fits (generic path)
+      int bst = LRR_TC_NB;
+      if (const char* e = getenv("LRR_TC_BSTAGES")) bst = atoi(e);
+      if (bst > MAX_BSTAGES) bst = MAX_BSTAGES;
+      if (bst > 3 && budget - bst * sh.bstage_bytes < 6 * ps.gstage_bytes) bst = 3;
+      while (bst > 2 && budget - bst * sh.bstage_bytes < 3 * ps.gstage_bytes) --bst;
+      int gst = (budget - bst * sh.bstage_bytes) / ps.gstage_bytes;
+      if (gst > MAX_GSTAGES) gst = MAX_GSTAGES;
+      if (const char* e = getenv("LRR_TC_GSTAGES")) { const int v = atoi(e); if (v >= 2 && v < gst) gst = v; }
+      if (bst < 2 || gst < 2) {
+        s->why = "not enough shared memory for the genotype / basis-panel rings";
+        return LRR_OK;
+      }
+      sh.n_gstages = gst;
+      sh.n_bstages = bst;
+      sh.smem_bytes = gst * ps.gstage_bytes + bst * sh.bstage_bytes + (int)sizeof(Barriers) + 1024;
+    }
   }
   if (!s->attr_set) {
 #define LRR_SET_SMEM(NG_, CS_) \
   LRR_CUDA(c, cudaFuncSetAttribute(tc_sweep_kernel<NG_, CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
     LRR_SET_SMEM(0, 1); LRR_SET_SMEM(1, 1); LRR_SET_SMEM(2, 1);
     LRR_SET_SMEM(0, 2); LRR_SET_SMEM(1, 2); LRR_SET_SMEM(2, 2);
-    LRR_SET_SMEM(0, 4); LRR_SET_SMEM(1, 4); LRR_SET_SMEM(2, 4);
 #undef LRR_SET_SMEM
     s->attr_set = true;
   }
   if (const char* e = getenv("LRR_TC_CLUSTER")) {
     const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4) s->cluster = v;
+    if (v == 1 || v == 2) s->cluster = v;
   }
   s->usable = true;
   s->why.clear();
@@ -1158,13 +1292,17 @@ int launch_tc_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags,
     p.n_tiles = (int)((M + TILE_M - 1) / TILE_M);
     p.n_chunks = (int)(stride / 128);
     p.ncols = ps.ncols;
-    p.n_gstages = ps.n_gstages;
-    p.n_bstages = ps.n_bstages;
+    // cluster size: a CTA pair by default (LRR_TC_CLUSTER=1 forces single CTAs); tiny inputs run single CTAs
+    int cs = s->cluster;
+    if (p.n_tiles < 2 * cs) cs = 1;
+    const PassShape& sh = ps.shape[cs - 1];
+    p.n_gstages = sh.n_gstages;
+    p.n_bstages = sh.n_bstages;
     p.n_groups = (int)ps.segs.size();
     p.ring_base = ps.ring_base;
     p.ring_groups = ps.ring_groups;
     p.gstage_bytes = ps.gstage_bytes;
-    p.bstage_bytes = ps.bstage_bytes;
+    p.bstage_bytes = sh.bstage_bytes;
     p.mask_bytes = ps.mask_bytes;
     p.row_flags = d_row_flags;
     for (int i = 0; i < p.n_groups; ++i) {
@@ -1181,18 +1319,15 @@ int launch_tc_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags,
       p.g[i].mask_hi = s->d_mask_hi + (int64_t)sg.group * (gr.ns_pad / 16);
       p.g[i].mask_all = ((int64_t)gr.n == c->n_samples_total) ? 1 : 0;
     }
-    // cluster size: LRR_TC_CLUSTER env (1, 2, 4) overrides the default of 2
-    int cs = s->cluster;
-    if (p.n_tiles < 2 * cs) cs = 1;
     void* kfn = nullptr;
 #define LRR_PICK(NG_)                                                                       \
-  (cs == 4 ? (void*)tc_sweep_kernel<NG_, 4> : cs == 2 ? (void*)tc_sweep_kernel<NG_, 2> : (void*)tc_sweep_kernel<NG_, 1>)
+  (cs == 2 ? (void*)tc_sweep_kernel<NG_, 2> : (void*)tc_sweep_kernel<NG_, 1>)
     kfn = p.n_groups == 1 ? LRR_PICK(1) : p.n_groups == 2 ? LRR_PICK(2) : LRR_PICK(0);
 #undef LRR_PICK
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = (size_t)ps.smem_bytes;
+    cfg.dynamicSmemBytes = (size_t)sh.smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1212,7 +1347,7 @@ int launch_tc_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags,
     const int need = (p.n_tiles + cs - 1) / cs * cs;
     if (n_cta > need) n_cta = need;
     cfg.gridDim = dim3((unsigned)n_cta);
-    void* args[3] = {(void*)&geno_map, (void*)&ps.b_map, (void*)&p};
+    void* args[3] = {(void*)&geno_map, (void*)&sh.b_map, (void*)&p};
     LRR_CUDA(c, cudaLaunchKernelExC(&cfg, kfn, args));
     c->launches++;
     LRR_CUDA(c, cudaGetLastError());
