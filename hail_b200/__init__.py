@@ -9,7 +9,7 @@ from .statgen import FatalError, linear_regression_rows, _get_regression_row_fie
 
 
 def __getattr__(name):  # lazy: these import torch-side helpers
-    if name in ("PackedGenotypes", "packed_stride"):
+    if name in ("PackedGenotypes", "HostBedGenotypes", "packed_stride"):
         from . import genotypes
         return getattr(genotypes, name)
     if name == "import_plink":
@@ -22,4 +22,4 @@ def __getattr__(name):  # lazy: these import torch-side helpers
 
 
 __all__ = ["linear_regression_rows", "MatrixTable", "Table", "FatalError", "ExpressionException", "PackedGenotypes",
-           "import_plink", "balding_nichols_model"]
+           "HostBedGenotypes", "import_plink", "balding_nichols_model"]

@@ -62,6 +62,11 @@ SIGNATURES = {
     "lrr_last_kernel": (ctypes.c_int, [ctypes.c_void_p]),
     "lrr_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "lrr_last_sweep_ms": (ctypes.c_float, [ctypes.c_void_p]),
+    "lrr_stream_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32]),
+    "lrr_stream_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(GroupOut), ctypes.c_int32,
+                                      ctypes.c_int32]),
+    "lrr_stream_end": (None, [ctypes.c_void_p, ctypes.c_void_p]),
     "lrr_student_t_two_sided": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double,
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 }

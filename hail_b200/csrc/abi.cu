@@ -21,19 +21,6 @@ int cuda_fail(Ctx* c, cudaError_t e, const char* what) {
 
 namespace {
 
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-  }
-  ~DeviceGuard() {
-    int cur = -1;
-    cudaGetDevice(&cur);
-    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
-  }
-};
-
 void free_group(Group& g) {
   cudaFree(g.d_basis);
   cudaFree(g.d_qty);
@@ -84,6 +71,50 @@ int ensure_workspace(Ctx* c, int64_t M) {
 }
 
 }  // namespace
+
+// the hot call behind lrr_run and the streaming loop (stream.cu): sweep + per-variant statistics of one row block
+int run_rows(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
+             int64_t n_samples_total, const lrr_group_out* outs, int32_t n_outs, int32_t kernel, cudaStream_t st) {
+  if (c->groups.empty()) return fail(c, LRR_ESTATE, "lrr_run: no groups (call lrr_add_group)");
+  if (n_outs != (int32_t)c->groups.size() || !outs) return fail(c, LRR_EINVAL, "lrr_run: need one lrr_group_out per group");
+  if (n_variants < 0) return fail(c, LRR_EINVAL, "lrr_run: negative n_variants");
+  if (n_samples_total != c->n_samples_total) return fail(c, LRR_EINVAL, "lrr_run: n_samples_total differs from the groups'");
+  if (packed_stride % kRowAlignBytes != 0 || packed_stride * 4 < n_samples_total)
+    return fail(c, LRR_EINVAL, "packed_stride must be a multiple of 128 bytes covering n_samples (use lrr_packed_stride)");
+  if (packed_stride * 4 != c->groups[0].ns_pad) return fail(c, LRR_EINVAL, "lrr_run: packed_stride must equal lrr_packed_stride(n_samples_total)");
+  if (n_variants == 0) return LRR_OK;
+  if (!d_packed) return fail(c, LRR_EINVAL, "lrr_run: d_packed is NULL");
+  if (int r = ensure_workspace(c, n_variants)) return r;
+
+  if (c->timing) {
+    if (!c->ev0) {
+      LRR_CUDA(c, cudaEventCreate(&c->ev0));
+      LRR_CUDA(c, cudaEventCreate(&c->ev1));
+    }
+    LRR_CUDA(c, cudaEventRecord(c->ev0, st));
+  }
+  int k = kernel;
+  const bool may_miss = true;  // the column budget is checked for the general (two-plane) mode
+  if (k == LRR_KERNEL_AUTO) k = tc_supported(c, may_miss) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
+  if (k == LRR_KERNEL_TC) {
+    if (!tc_supported(c, may_miss))
+      return fail(c, LRR_EINVAL, "lrr_run: tensor-core kernel does not support this configuration: " + c->err);
+    if (int r = launch_tc_sweep(c, d_packed, d_row_flags, n_variants, packed_stride, st)) return r;
+  } else if (k == LRR_KERNEL_FP64) {
+    if (int r = launch_fp64_sweep(c, d_packed, n_variants, packed_stride, st)) return r;
+  } else {
+    return fail(c, LRR_EINVAL, "lrr_run: unknown kernel id");
+  }
+  c->last_kernel = k;
+  if (c->timing) {
+    LRR_CUDA(c, cudaEventRecord(c->ev1, st));
+    c->ev_valid = true;
+  }
+  for (size_t g = 0; g < c->groups.size(); ++g)
+    if (int r = launch_stats_epilogue(c, (int)g, n_variants, outs[g], st)) return r;
+  return LRR_OK;
+}
+
 }  // namespace lrr
 
 using namespace lrr;
@@ -121,6 +152,7 @@ void lrr_destroy(lrr_ctx* ctx) {
   for (auto& g : c->groups) free_group(g);
   free_workspace(c);
   tc_release(c);
+  cudaFree(c->arena);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   delete c;
@@ -300,43 +332,7 @@ int lrr_reserve(lrr_ctx* ctx, int64_t max_variants) {
 int lrr_run(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
             int64_t n_samples_total, const lrr_group_out* outs, int32_t n_outs, int32_t kernel, void* stream) {
   CTX_PROLOGUE;
-  if (c->groups.empty()) return fail(c, LRR_ESTATE, "lrr_run: no groups (call lrr_add_group)");
-  if (n_outs != (int32_t)c->groups.size() || !outs) return fail(c, LRR_EINVAL, "lrr_run: need one lrr_group_out per group");
-  if (n_variants < 0) return fail(c, LRR_EINVAL, "lrr_run: negative n_variants");
-  if (n_samples_total != c->n_samples_total) return fail(c, LRR_EINVAL, "lrr_run: n_samples_total differs from the groups'");
-  if (int r = check_packed(c, n_samples_total, packed_stride)) return r;
-  if (packed_stride * 4 != c->groups[0].ns_pad) return fail(c, LRR_EINVAL, "lrr_run: packed_stride must equal lrr_packed_stride(n_samples_total)");
-  if (n_variants == 0) return LRR_OK;
-  if (!d_packed) return fail(c, LRR_EINVAL, "lrr_run: d_packed is NULL");
-  if (int r = ensure_workspace(c, n_variants)) return r;
-
-  if (c->timing) {
-    if (!c->ev0) {
-      LRR_CUDA(c, cudaEventCreate(&c->ev0));
-      LRR_CUDA(c, cudaEventCreate(&c->ev1));
-    }
-    LRR_CUDA(c, cudaEventRecord(c->ev0, st));
-  }
-  int k = kernel;
-  const bool may_miss = true;  // the column budget is checked for the general (two-plane) mode
-  if (k == LRR_KERNEL_AUTO) k = tc_supported(c, may_miss) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
-  if (k == LRR_KERNEL_TC) {
-    if (!tc_supported(c, may_miss))
-      return fail(c, LRR_EINVAL, "lrr_run: tensor-core kernel does not support this configuration: " + c->err);
-    if (int r = launch_tc_sweep(c, d_packed, d_row_flags, n_variants, packed_stride, st)) return r;
-  } else if (k == LRR_KERNEL_FP64) {
-    if (int r = launch_fp64_sweep(c, d_packed, n_variants, packed_stride, st)) return r;
-  } else {
-    return fail(c, LRR_EINVAL, "lrr_run: unknown kernel id");
-  }
-  c->last_kernel = k;
-  if (c->timing) {
-    LRR_CUDA(c, cudaEventRecord(c->ev1, st));
-    c->ev_valid = true;
-  }
-  for (size_t g = 0; g < c->groups.size(); ++g)
-    if (int r = launch_stats_epilogue(c, (int)g, n_variants, outs[g], st)) return r;
-  return LRR_OK;
+  return run_rows(c, d_packed, d_row_flags, n_variants, packed_stride, n_samples_total, outs, n_outs, kernel, st);
 }
 
 int64_t lrr_launch_count(const lrr_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->launches : 0; }

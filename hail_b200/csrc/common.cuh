@@ -54,6 +54,24 @@ struct Ctx {
   int timing = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
+  // device arena of the streaming loop (staging + slots), kept between streams (stream.cu)
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  int streams_alive = 0;
+};
+
+// make `dev` current for the lifetime of the guard
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
 };
 
 int fail(Ctx* c, int code, const std::string& msg);
@@ -78,6 +96,8 @@ bool tc_supported(Ctx*, bool may_have_missing);
 void tc_invalidate(Ctx*);
 void tc_release(Ctx*);
 int launch_stats_epilogue(Ctx*, int g, int64_t M, const lrr_group_out& out, cudaStream_t);
+int run_rows(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, int64_t n_samples_total,
+             const lrr_group_out* outs, int32_t n_outs, int32_t kernel, cudaStream_t);
 int launch_student_t(Ctx*, const double*, int64_t, double, double*, double*, cudaStream_t);
 
 // position of sample `j` (0..15 within its word) in the packed word: bits [8i+2s, 8i+2s+1], j = 4s+i

@@ -119,6 +119,58 @@ class PackedGenotypes:
         return out.cpu().numpy()
 
 
+class HostBedGenotypes:
+    """A SNP-major PLINK .bed body kept in page-locked HOST memory: uint8 [n_variants, ceil(n_samples/4)].
+
+    The out-of-core form of the entry matrix: `linear_regression_rows` streams it through the device block by
+    block (lrr_stream_*), the way the reference's per-partition loop consumes rows as LoadPlink decodes them
+    (LinearRegression.scala:95; io/plink/LoadPlink.scala:470-530).  Nothing is resident on the device between calls.
+    """
+
+    def __init__(self, rows, n_samples: int, device=0):
+        t = torch.as_tensor(np.ascontiguousarray(rows) if isinstance(rows, np.ndarray) else rows)
+        assert t.dtype == torch.uint8 and t.dim() == 2
+        if t.shape[1] < (n_samples + 3) // 4:
+            raise ValueError("bed row shorter than ceil(n_samples/4) bytes (LoadPlink.scala:240-251)")
+        if t.is_cuda:
+            raise ValueError("HostBedGenotypes holds host memory; use PackedGenotypes.from_bed_rows for device data")
+        if not t.is_pinned():  # one copy into page-locked memory so that the block copies run at PCIe rate
+            p = torch.empty(t.shape, dtype=torch.uint8, pin_memory=True)
+            p.copy_(t)
+            t = p
+        self.rows = t.contiguous()
+        self.n_variants, self.bed_stride = int(t.shape[0]), int(t.shape[1])
+        self.n_samples = int(n_samples)
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+
+    @property
+    def nbytes(self):
+        return self.n_variants * self.bed_stride
+
+    @classmethod
+    def from_bed_file(cls, path, n_samples, n_variants, device=0):
+        """Read `path` (magic 6c 1b 01, SNP-major) straight into page-locked memory."""
+        stride = (n_samples + 3) // 4
+        size = os.path.getsize(path)
+        with open(path, "rb") as f:
+            if size < 3 or f.read(3) != BED_MAGIC:
+                raise ValueError(f"{path}: not a SNP-major PLINK .bed (bad magic)")
+            if size != 3 + n_variants * stride:
+                raise ValueError(f"{path}: size {size} != 3 + n_variants*ceil(n_samples/4) = {3 + n_variants * stride}")
+            t = torch.empty((n_variants, stride), dtype=torch.uint8, pin_memory=True)
+            if n_variants:
+                got = f.readinto(memoryview(t.numpy()).cast("B"))
+                assert got == n_variants * stride
+        return cls(t, n_samples, device)
+
+    def to_device(self, chunk_variants=1 << 14) -> PackedGenotypes:
+        """The resident 2-bit store of the same calls."""
+        return PackedGenotypes.from_bed_rows(self.rows, self.n_samples, self.device, chunk_variants=chunk_variants)
+
+    def to_dosage(self) -> np.ndarray:
+        return self.to_device().to_dosage()
+
+
 def packed_stride(n_samples: int) -> int:
     return int(_lib.load().lrr_packed_stride(int(n_samples)))
 

@@ -198,12 +198,7 @@ def _run_device(genotypes, bases, kernel="auto", want_log10_p=False, chunk_varia
     ctx = _lib.context(dev.index)
     M, N = genotypes.n_variants, genotypes.n_samples
     with torch.cuda.device(dev):
-        ctx.check(ctx.lib.lrr_clear_groups(ctx.handle))
-        for b in bases:
-            ctx.check(ctx.lib.lrr_add_group(
-                ctx.handle, N, b.n, b.K, b.P, int(b.has_intercept), b.complete_idx.ctypes.data,
-                b.q_cols.ctypes.data if b.q_cols.size else None, b.y_res.ctypes.data,
-                b.qty.ctypes.data if b.qty.size else None, b.yyp.ctypes.data))
+        _push_groups(ctx, N, bases)
         outs = []
         for b in bases:
             o = {
@@ -235,8 +230,75 @@ def _run_device(genotypes, bases, kernel="auto", want_log10_p=False, chunk_varia
     return outs
 
 
+def _push_groups(ctx, N, bases):
+    ctx.check(ctx.lib.lrr_clear_groups(ctx.handle))
+    for b in bases:
+        ctx.check(ctx.lib.lrr_add_group(
+            ctx.handle, N, b.n, b.K, b.P, int(b.has_intercept), b.complete_idx.ctypes.data,
+            b.q_cols.ctypes.data if b.q_cols.size else None, b.y_res.ctypes.data,
+            b.qty.ctypes.data if b.qty.size else None, b.yyp.ctypes.data))
+
+
+class _HostStream:
+    """lrr_stream_* over a HostBedGenotypes: begun before the driver prologue so that the first blocks cross PCIe
+    while the host computes the covariate basis."""
+
+    def __init__(self, genotypes, block_variants=0, depth=0):
+        self.g = genotypes
+        self.ctx = _lib.context(genotypes.device.index)
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(genotypes.device):
+            # groups of an earlier call are dropped first: lrr_clear_groups synchronises the device, which must not
+            # happen behind the copies queued by lrr_stream_begin
+            self.ctx.check(self.ctx.lib.lrr_clear_groups(self.ctx.handle))
+            self.ctx.check(self.ctx.lib.lrr_stream_begin(
+                self.ctx.handle, ctypes.byref(self.handle), genotypes.rows.data_ptr(), genotypes.n_variants,
+                genotypes.bed_stride, genotypes.n_samples, int(block_variants), int(depth)))
+
+    def run(self, bases, kernel="auto", want_log10_p=False):
+        """Returns per-group dicts of numpy arrays (views of one page-locked result buffer)."""
+        ctx, M, N = self.ctx, self.g.n_variants, self.g.n_samples
+        with torch.cuda.device(self.g.device):
+            for b in bases:
+                ctx.check(ctx.lib.lrr_add_group(
+                    ctx.handle, N, b.n, b.K, b.P, int(b.has_intercept), b.complete_idx.ctypes.data,
+                    b.q_cols.ctypes.data if b.q_cols.size else None, b.y_res.ctypes.data,
+                    b.qty.ctypes.data if b.qty.size else None, b.yyp.ctypes.data))
+            fields = [("n", np.int32, 0), ("n_missing", np.int32, 0), ("sum_x", np.float64, 0)]
+            fields += [(f, np.float64, 1) for f in STAT_FIELDS + (["log10_p"] if want_log10_p else [])]
+            total, layout = 0, []
+            for b in bases:
+                lay = {}
+                for name, dt, per_p in fields:
+                    nbytes = M * (b.P if per_p else 1) * np.dtype(dt).itemsize
+                    lay[name] = (total, nbytes)
+                    total += (nbytes + 255) // 256 * 256
+                layout.append(lay)
+            buf = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True)
+            base, host = buf.data_ptr(), buf.numpy()
+            arr = (_lib.GroupOut * len(bases))()
+            outs = []
+            for g, (b, lay) in enumerate(zip(bases, layout)):
+                o = {}
+                for name, dt, per_p in fields:
+                    off, nbytes = lay[name]
+                    setattr(arr[g], name, base + off)
+                    v = host[off:off + nbytes].view(dt)
+                    o[name] = v.reshape(M, b.P) if per_p else v
+                if not want_log10_p:
+                    arr[g].log10_p = None
+                outs.append(o)
+            ctx.check(ctx.lib.lrr_stream_run(ctx.handle, self.handle, arr, len(bases), _lib.KERNELS[kernel]))
+        return outs
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.lrr_stream_end(self.ctx.handle, self.handle)
+            self.handle = ctypes.c_void_p()
+
+
 def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, weights=None,
-                           _kernel="auto", _log10_p=False) -> Table:
+                           _kernel="auto", _log10_p=False, _stream_block=0, _stream_depth=0) -> Table:
     """For each row, test an input variable for association with response variables using linear regression.
 
     Drop-in for `hl.linear_regression_rows` (statgen.py:235): same arguments, same validation, same output
@@ -269,12 +331,23 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
 
     n_cols = mt.count_cols()
     cov = np.column_stack(cov_vals) if cov_vals else np.empty((n_cols, 0))
-    bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None)
-             for i, g in enumerate(y_vals)]
+    from .genotypes import HostBedGenotypes
 
-    outs = _run_device(mt.genotypes, bases, kernel=_kernel, want_log10_p=_log10_p)
-    torch.cuda.synchronize(mt.genotypes.device)
-    host = [{k: v.cpu().numpy() for k, v in o.items()} for o in outs]
+    if isinstance(mt.genotypes, HostBedGenotypes):
+        # host-resident .bed rows: stream them through the device; the copies start before the prologue
+        stream = _HostStream(mt.genotypes, _stream_block, _stream_depth)
+        try:
+            bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None)
+                     for i, g in enumerate(y_vals)]
+            host = stream.run(bases, kernel=_kernel, want_log10_p=_log10_p)
+        finally:
+            stream.close()
+    else:
+        bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None)
+                 for i, g in enumerate(y_vals)]
+        outs = _run_device(mt.genotypes, bases, kernel=_kernel, want_log10_p=_log10_p)
+        torch.cuda.synchronize(mt.genotypes.device)
+        host = [{k: v.cpu().numpy() for k, v in o.items()} for o in outs]
 
     fields = OrderedDict()
     for k in mt.row_key:

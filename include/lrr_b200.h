@@ -135,6 +135,23 @@ int lrr_last_kernel(const lrr_ctx* ctx);
 int lrr_set_timing(lrr_ctx* ctx, int enabled);
 float lrr_last_sweep_ms(lrr_ctx* ctx);
 
+/* ---- the hot call on HOST-resident input: the streaming loop ------------------------------------------
+ * The reference's loop consumes each partition's rows as they are decoded from storage (LinearRegression.scala:95,
+ * io/plink/LoadPlink.scala:470-530).  lrr_stream_* is that loop for a SNP-major PLINK .bed body (no 3-byte
+ * header) in host memory -- page-locked memory gives the full PCIe rate: blocks of `block_variants` rows are
+ * copied to the device, packed, swept and their result rows copied back to host arrays, copies and compute
+ * overlapped on internal streams over a ring of `depth` device slots (0 = defaults: ~256 MB blocks, up to 16 GB
+ * in flight).  lrr_stream_begin needs only the genotype bytes and returns at once, so it can be called BEFORE
+ * the groups exist: the first `depth` blocks are copied and packed while the host runs the driver prologue
+ * (LR:47-78).  lrr_stream_run takes lrr_group_out structs of HOST pointers ([M] / [M, P] arrays as in lrr_run,
+ * NULL = skip) and returns when every result row is in host memory.  A stream runs once; lrr_stream_end frees
+ * it (always call it, also after an error). */
+typedef struct lrr_stream lrr_stream;
+int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64_t n_variants, int64_t bed_stride,
+                     int64_t n_samples, int64_t block_variants, int32_t depth);
+int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs, int32_t n_outs, int32_t kernel);
+void lrr_stream_end(lrr_ctx* ctx, lrr_stream* stream);
+
 /* two-sided Student-t p-value on the device, exposed for unit tests of the epilogue:
  * p[i] = 2 * P[T_df <= -|t[i]|]  (jdistlib T.cumulative call sites LR:160, LR:344) */
 int lrr_student_t_two_sided(lrr_ctx* ctx, const double* d_t, int64_t count, double df, double* d_p, double* d_log10_p,

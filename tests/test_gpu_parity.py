@@ -467,3 +467,76 @@ def test_many_chained_groups(kernel):
         for f in ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
             got[f] = ht[f][g]
         assert_fields_close(got, {k: v for k, v in want[g].items() if k != "_d"}, t_floor=1e-9, ctx=f"{kernel} g={g}")
+
+
+# ---------------------------------------------------------------------------------------------
+# host-resident input: the streaming loop (lrr_stream_*) must give exactly the resident path's rows
+@pytest.mark.parametrize("block,depth", [(0, 0), (128, 2), (300, 3), (1000, 1), (4096, 5)])
+def test_stream_from_host_bed_matches_resident(block, depth):
+    hb = _hb()
+    z = np.load(os.path.join(GOLDEN, "fastlmm.npz"))
+    N, M = int(z["n_samples"]), int(z["n_variants"])
+    rows = obed.bed_body(z["bed"], N, M)
+    rng = np.random.default_rng(3)
+    ys = np.column_stack([z["pheno"], rng.normal(size=N)])
+    ys[rng.random(ys.shape) < 0.03] = np.nan
+    cov = np.column_stack([np.ones(N), z["cov"][:, 0], rng.normal(size=N)])
+    cols = {"y0": ys[:, 0], "y1": ys[:, 1], "c1": cov[:, 1], "c2": cov[:, 2]}
+    host = hb.HostBedGenotypes(rows, N)
+    assert host.rows.is_pinned() and host.n_variants == M
+    mt_h = hb.MatrixTable(host, cols=cols)
+    mt_d = hb.MatrixTable(hb.PackedGenotypes.from_bed_rows(rows, N), cols=cols)
+    for y_of in (lambda mt: [mt.y0, mt.y1], lambda mt: [[mt.y0], [mt.y1]]):   # Single and Chained
+        th = hb.linear_regression_rows(y=y_of(mt_h), x=mt_h.GT.n_alt_alleles(), covariates=[1.0, mt_h.c1, mt_h.c2],
+                                       _kernel="tc", _stream_block=block, _stream_depth=depth)
+        td = hb.linear_regression_rows(y=y_of(mt_d), x=mt_d.GT.n_alt_alleles(), covariates=[1.0, mt_d.c1, mt_d.c2],
+                                       _kernel="tc")
+        assert np.array_equal(th.n, td.n) and np.array_equal(np.asarray(th.n_missing), np.asarray(td.n_missing))
+        for f in ("sum_x", "y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+            a, b = th[f], td[f]
+            if isinstance(a, (list, tuple)) or hasattr(a, "__iter__") and not isinstance(a, np.ndarray):
+                for ga, gb in zip(a, b):
+                    assert np.array_equal(np.asarray(ga), np.asarray(gb), equal_nan=True), f
+            else:
+                assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), f   # same kernels, same bits
+    # and against the oracle
+    want = O.linreg_group(obed.decode_rows(rows, N), ys, cov)
+    th = hb.linear_regression_rows(y=[mt_h.y0, mt_h.y1], x=mt_h.GT.n_alt_alleles(), covariates=[1.0, mt_h.c1, mt_h.c2],
+                                   _stream_block=block, _stream_depth=depth)
+    got = _as_oracle_dict(th)
+    nondeg = np.isfinite(want["standard_error"]).all(axis=1)
+    assert_fields_close({k: v[nondeg] for k, v in got.items()}, {k: v[nondeg] for k, v in want.items() if k != "_d"},
+                        t_floor=1e-9, ctx=f"stream block={block} depth={depth}")
+
+
+def test_stream_empty_errors_and_file(tmp_path):
+    hb = _hb()
+    from hail_b200 import _lib
+    z = np.load(os.path.join(GOLDEN, "fastlmm.npz"))
+    N, M = int(z["n_samples"]), int(z["n_variants"])
+    rows = obed.bed_body(z["bed"], N, M)
+    # file -> page-locked memory
+    path = tmp_path / "t.bed"
+    path.write_bytes(bytes([0x6C, 0x1B, 0x01]) + rows.tobytes())
+    host = hb.HostBedGenotypes.from_bed_file(str(path), N, M)
+    assert np.array_equal(host.rows.numpy(), rows)
+    with pytest.raises(ValueError):
+        hb.HostBedGenotypes.from_bed_file(str(path), N, M + 1)
+    # a FatalError in the prologue (no degrees of freedom) must close the stream so the next call works
+    mt = hb.MatrixTable(host, cols={"y": z["pheno"], **{f"c{i}": np.random.default_rng(i).normal(size=N) for i in range(260)}})
+    with pytest.raises(hb.FatalError):
+        hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=[1.0] + [mt[f"c{i}"] for i in range(260)])
+    t = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=[1.0])
+    assert t.count() == M and np.isfinite(np.asarray(t.beta)).sum() > 0.9 * M
+    # zero rows
+    e = hb.MatrixTable(hb.HostBedGenotypes(rows[:0], N), cols={"y": z["pheno"]})
+    t0 = hb.linear_regression_rows(y=e.y, x=e.GT.n_alt_alleles(), covariates=[1.0])
+    assert t0.count() == 0
+    # two open streams on one context are refused
+    ctx = _lib.context(0)
+    import ctypes
+    h1, h2 = ctypes.c_void_p(), ctypes.c_void_p()
+    ctx.check(ctx.lib.lrr_stream_begin(ctx.handle, ctypes.byref(h1), host.rows.data_ptr(), M, host.bed_stride, N, 0, 0))
+    rc = ctx.lib.lrr_stream_begin(ctx.handle, ctypes.byref(h2), host.rows.data_ptr(), M, host.bed_stride, N, 0, 0)
+    assert rc != 0 and b"still open" in ctx.lib.lrr_last_error(ctx.handle)
+    ctx.lib.lrr_stream_end(ctx.handle, h1)
