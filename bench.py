@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "fp64", "tc"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "fp64", "tc", "tc4"])
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--variants", type=int, default=N_VARIANTS, help="variants per GPU")
     ap.add_argument("--missing-rate", type=float, default=0.0)

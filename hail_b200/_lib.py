@@ -8,8 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # LRR_B200_LIB overrides the library file (A/B builds of the same sources during kernel tuning)
 LIB_PATH = os.environ.get("LRR_B200_LIB") or os.path.join(HERE, "liblrr_b200.so")
 
-KERNEL_AUTO, KERNEL_FP64, KERNEL_TC = 0, 1, 2
-KERNELS = {"auto": KERNEL_AUTO, "fp64": KERNEL_FP64, "tc": KERNEL_TC}
+KERNEL_AUTO, KERNEL_FP64, KERNEL_TC, KERNEL_TC4 = 0, 1, 2, 3
+KERNELS = {"auto": KERNEL_AUTO, "fp64": KERNEL_FP64, "tc": KERNEL_TC, "tc4": KERNEL_TC4}
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_f64p = ctypes.POINTER(ctypes.c_double)

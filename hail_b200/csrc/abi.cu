@@ -95,8 +95,15 @@ int run_rows(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_
   }
   int k = kernel;
   const bool may_miss = true;  // the column budget is checked for the general (two-plane) mode
-  if (k == LRR_KERNEL_AUTO) k = tc_supported(c, may_miss) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
-  if (k == LRR_KERNEL_TC) {
+  // AUTO: the 4-bit tensor-core sweep when one sweep covers every column and its exactness bound holds, else the
+  // int8 tensor-core sweep (multi-pass for many phenotypes), else the float64 CUDA-core kernel
+  if (k == LRR_KERNEL_AUTO)
+    k = tc4_supported(c, true) ? LRR_KERNEL_TC4 : tc_supported(c, may_miss) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
+  if (k == LRR_KERNEL_TC4) {
+    if (!tc4_supported(c, false))
+      return fail(c, LRR_EINVAL, "lrr_run: 4-bit tensor-core kernel does not support this configuration: " + c->err);
+    if (int r = launch_tc4_sweep(c, d_packed, d_row_flags, n_variants, packed_stride, st)) return r;
+  } else if (k == LRR_KERNEL_TC) {
     if (!tc_supported(c, may_miss))
       return fail(c, LRR_EINVAL, "lrr_run: tensor-core kernel does not support this configuration: " + c->err);
     if (int r = launch_tc_sweep(c, d_packed, d_row_flags, n_variants, packed_stride, st)) return r;
@@ -152,6 +159,7 @@ void lrr_destroy(lrr_ctx* ctx) {
   for (auto& g : c->groups) free_group(g);
   free_workspace(c);
   tc_release(c);
+  tc4_release(c);
   cudaFree(c->arena);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -233,6 +241,7 @@ int lrr_clear_groups(lrr_ctx* ctx) {
   for (auto& g : c->groups) free_group(g);
   c->groups.clear();
   tc_invalidate(c);
+  tc4_invalidate(c);
   free_workspace(c);
   c->n_samples_total = 0;
   return LRR_OK;
@@ -315,6 +324,7 @@ int lrr_add_group(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, i
   cleanup();
   c->groups.push_back(g);
   tc_invalidate(c);
+  tc4_invalidate(c);
   c->n_samples_total = n_samples_total;
   c->dots_offset.clear();  // workspace layout depends on the group list
   return LRR_OK;

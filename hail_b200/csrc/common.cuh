@@ -50,6 +50,7 @@ struct Ctx {
   int last_kernel = 0;
   int sm_count = 148;
   void* tc_state = nullptr;  // opaque, owned by tc_kernel.cu
+  void* tc4_state = nullptr; // opaque, owned by tc4_kernel.cu
   // optional device timing of the sweep kernel(s) of the last lrr_run (bench roofline)
   int timing = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -95,6 +96,10 @@ int launch_tc_sweep(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, i
 bool tc_supported(Ctx*, bool may_have_missing);
 void tc_invalidate(Ctx*);
 void tc_release(Ctx*);
+int launch_tc4_sweep(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, cudaStream_t);
+bool tc4_supported(Ctx*, bool single_pass_only);
+void tc4_invalidate(Ctx*);
+void tc4_release(Ctx*);
 int launch_stats_epilogue(Ctx*, int g, int64_t M, const lrr_group_out& out, cudaStream_t);
 int run_rows(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, int64_t n_samples_total,
              const lrr_group_out* outs, int32_t n_outs, int32_t kernel, cudaStream_t);

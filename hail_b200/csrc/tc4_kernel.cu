@@ -1,0 +1,1090 @@
+// Kernel 3: the sweep on the tensor cores' 4-bit path (tcgen05.mma.kind::mxf4, sm_100a) -- half the tensor-memory
+// traffic and half the unpack arithmetic of the int8 kernel (tc_kernel.cu), same exact-integer results.
+//
+// Same formulation as tc_kernel.cu (D[v, c] = sum_j x[v, j] B[j, c] per 128-variant tile, LinearRegression.scala:139-146
+// restated), but both operands are E2M1 (4-bit float) elements:
+//   A  call code c in {0..3} as the nibble 00cc = c / 2 (exactly representable: 0, .5, 1, 1.5), 64 samples per MMA;
+//   B  every basis column as balanced base-13 digits u in {0, +-1, +-2, +-3, +-4, +-6, +-8} stored as u / 2 (the E2M1
+//      values 0, .5, 1, 1.5, 2, 3, 4): a complete residue system mod 13, 13 digits (46.5 bits) for phenotype
+//      columns, 9 digits (31.7 bits) for covariate columns; block scales are all 1 (UE8M0 0x7F).
+// Every product is a multiple of 1/4 and the f32 accumulator holds sum c u / 4 EXACTLY as long as |sum c u| <= 2^24;
+// the host checks the worst case over all possible genotypes for every column (acc_bound_kernel) and refuses the
+// kernel otherwise, so the result is independent of tiling and summation order, like the int8 kernel's INT32 sums.
+// (Exactness of the hardware accumulation for such sums: scratch/fp4_probe.cu, and the bit-exact n / sum_x tests.)
+//
+// On-SM cost per 512-sample chunk against the int8 kernel (measured components, profiles/README.md): tcgen05.st
+// 32 KB instead of 64 KB (it blocks the issuing SM sub-partition at 256 B/clk), 3 instead of 5 ALU operations per
+// 16 calls, 8 instead of 16 MMAs of the same duration (N/2 cycles, K = 64 instead of 32).
+//
+// Structure (warps, rings, CTA pair with tcgen05.mma.cta_group::2) is the int8 kernel's; differences:
+//   * A ring in units of 64 TMEM columns (one chunk of one plane); a one-plane chunk takes one unit, a two-plane
+//     chunk (tile with missing calls) two consecutive units [plane c | plane m]; every unit has its own
+//     full / empty barrier pair and BOTH sides track the phase parity per barrier, so units may be skipped;
+//   * the scale-factor operands point at 16 TMEM columns filled with 0x7F bytes -- all scales are 1, which makes
+//     the result independent of the scale-factor layout.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace lrr {
+namespace tc4 {
+
+using namespace ptx;
+
+constexpr int TILE_M = 128;            // variants per tile == TMEM lanes
+constexpr int CHUNK = 512;             // samples per genotype stage (128 packed bytes per row)
+constexpr int SLOT = 128;              // samples per unpack warp and chunk (16 TMEM columns of 8 nibbles)
+constexpr int SLOTS = CHUNK / SLOT;    // 4
+constexpr int SLOT_COLS = 16;
+constexpr int UNIT_COLS = SLOTS * SLOT_COLS;   // 64: one chunk of one plane
+constexpr int NU = 4;                  // ring units
+constexpr int PANEL = 256;             // samples per basis-panel row (128 bytes of nibbles)
+constexpr int PANELS = CHUNK / PANEL;  // 2
+constexpr int UNPACK_WARPS = 16;       // warp w: TMEM lane quarter w & 3, slot w >> 2 of every chunk
+constexpr int WARP_TMA_G = 16, WARP_TMA_B = 17, WARP_MMA = 18;
+constexpr int THREADS = 19 * 32;
+constexpr int GENO_BYTES = TILE_M * 128;   // 16 KB
+constexpr int MAX_GROUPS = 4;
+constexpr int MAX_GSTAGES = 10;
+constexpr int NB = 6;                  // basis-panel ring depth the MMA fast path is unrolled for
+constexpr int MAX_BSTAGES = NB;
+constexpr int SF_COLS = 16;            // scale-factor columns (A: first 8, B: last 8), all bytes 0x7F
+constexpr int DIG_Y = 13, DIG_Q = 9;   // base-13 digits per phenotype / covariate column
+constexpr int PASS_COLS = 112;         // digit columns per sweep: 2 * 112 accumulators + 16 + ring of 4 * 64 <= 512
+constexpr int UNROLL = 12;             // chunks per unrolled block of the MMA fast path (lcm of NB and NU)
+
+struct GroupMeta {
+  int col_off;        // first digit column of this group in B
+  int C;              // dot-product columns (Kd + P)
+  int Kd;             // of which covariate columns (DIG_Q digits each; the rest have DIG_Y)
+  int n;              // complete samples
+  int32_t* counts;    // [M][4]
+  double* dots;       // [M][dots_stride], already offset to this segment's first dot column
+  int dots_stride;
+  const double* colscale;   // [C]
+  const uint32_t* mask_hi;  // [ns_pad/16], high bit of each kept field
+};
+
+struct Params {
+  int64_t M;
+  int n_tiles;
+  int n_chunks;
+  int ncols;          // padded to 16
+  int n_gstages, n_bstages;
+  int n_groups;
+  int sf_base;        // first scale-factor column
+  int ring_base;      // first TMEM column of the A ring (NU units of 64 columns)
+  int gstage_bytes, bstage_bytes;
+  int mask_bytes;     // n_groups * 128 when any group needs masking, else 0
+  const uint8_t* row_flags;  // nullable
+  int abl_contig;     // timing ablation: read every genotype box as one contiguous 16 KB block (results are WRONG)
+  GroupMeta g[MAX_GROUPS];
+};
+
+// D[tmem] (+)= A[tmem] * B[smem desc], E2M1 x E2M1 -> f32, K = 64, block scales from tensor memory
+template <int CS>
+__device__ __forceinline__ void mma_mxf4_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t sfa,
+                                            uint32_t sfb, uint32_t accumulate) {
+  if (CS == 1)
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], [%1], %2, %3, [%5], [%6], p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
+        : "memory");
+  else
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], [%1], %2, %3, [%5], [%6], p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
+        : "memory");
+}
+
+// block-scaled instruction descriptor: A = B = E2M1, scales UE8M0, K = 64 dense, both K-major
+__device__ __forceinline__ uint32_t make_idesc(int n, int m) {
+  uint32_t d = 0;
+  d |= 1u << 7;                   // a_format = E2M1
+  d |= 1u << 10;                  // b_format = E2M1
+  d |= (uint32_t)(n >> 3) << 17;  // N
+  d |= 1u << 23;                  // scale format UE8M0
+  d |= (uint32_t)(m >> 4) << 24;  // M (256 for a CTA pair)
+  return d;                       // scale-factor ids 0
+}
+
+template <int V> struct IntTag { static constexpr int value = V; };
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
+
+struct Barriers {
+  uint64_t gfull[MAX_GSTAGES];   // genotype stage filled by TMA
+  uint64_t gempty[MAX_GSTAGES];  // genotype stage read out by the 16 unpack warps
+  uint64_t bfull[MAX_BSTAGES];   // basis-panel stage filled by TMA (both CTAs of a pair complete on the leader's)
+  uint64_t bempty[MAX_BSTAGES];  // basis-panel stage consumed (MMA commit)
+  uint64_t a_full[NU];           // ring unit written (16 warps of each CTA)
+  uint64_t a_empty[NU];          // ring unit consumed (MMA commit)
+  uint64_t d_full;               // accumulators complete (MMA commit)
+  uint64_t d_empty;              // accumulators read out (4 epilogue warps of each CTA)
+  uint32_t tmem_base;
+  uint32_t pad;
+  int32_t n2_xchg[2][SLOTS - 1][MAX_GROUPS][TILE_M];   // see tc_kernel.cu
+};
+
+__device__ __forceinline__ bool tile_has_missing(const Params& p, int tile) {
+  const int64_t r0 = (int64_t)tile * TILE_M;
+  if (r0 >= p.M) return false;   // padding tile of a pair
+  if (!p.row_flags) return true;
+  uint32_t any = 0;
+  if (r0 + TILE_M <= p.M && ((reinterpret_cast<uintptr_t>(p.row_flags + r0) & 15) == 0)) {
+    const uint4* f = reinterpret_cast<const uint4*>(p.row_flags + r0);
+#pragma unroll
+    for (int i = 0; i < TILE_M / 16; ++i) {
+      const uint4 v = __ldg(f + i);
+      any |= v.x | v.y | v.z | v.w;
+    }
+  } else {
+    for (int64_t r = r0; r < p.M && r < r0 + TILE_M; ++r) any |= p.row_flags[r];
+  }
+  return any != 0;
+}
+
+// NG = number of groups known at compile time (1, 2) or 0 = run-time p.n_groups; CS = 1 (one CTA per tile) or 2 (CTA
+// pair, tcgen05.mma.cta_group::2, see tc_kernel.cu for the cross-CTA protocol).
+template <int NG, int CS>
+__global__ void __launch_bounds__(THREADS, 1)
+tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_constant__ CUtensorMap b_map, const Params p) {
+  static_assert(CS == 1 || CS == 2, "one CTA or a CTA pair");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // genotype ring base (shared window address)
+  uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  const uint32_t bring0 = smem0 + p.n_gstages * p.gstage_bytes;   // basis-panel ring base
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_gen + (size_t)p.n_gstages * p.gstage_bytes +
+                                               (size_t)p.n_bstages * p.bstage_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  auto GFULL = [&](int s) { return bar0 + 8u * s; };
+  auto GEMPTY = [&](int s) { return bar0 + 8u * (MAX_GSTAGES + s); };
+  auto BFULL = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + s); };
+  auto BEMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + MAX_BSTAGES + s); };
+  auto AFULL = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + 2 * MAX_BSTAGES + s); };
+  auto AEMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + 2 * MAX_BSTAGES + NU + s); };
+  const uint32_t DFULL = bar0 + 8u * (2 * MAX_GSTAGES + 2 * MAX_BSTAGES + 2 * NU);
+  const uint32_t DEMPTY = DFULL + 8u;
+  const int n_groups = NG ? NG : p.n_groups;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.n_gstages; ++s) {
+      mbar_init(GFULL(s), 1);
+      mbar_init(GEMPTY(s), UNPACK_WARPS);
+    }
+    for (int s = 0; s < p.n_bstages; ++s) {
+      mbar_init(BFULL(s), 1);
+      mbar_init(BEMPTY(s), 1);
+    }
+    for (int s = 0; s < NU; ++s) {
+      mbar_init(AFULL(s), UNPACK_WARPS * CS);
+      mbar_init(AEMPTY(s), 1);
+    }
+    mbar_init(DFULL, 1);
+    mbar_init(DEMPTY, 4 * CS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WARP_MMA) {
+    if (CS == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  if (warp == WARP_TMA_G && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&geno_map) : "memory");
+  if (warp == WARP_TMA_B && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&b_map) : "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  // unit scale factors: every byte of the SF columns is UE8M0 1.0 in every lane of both CTAs
+  if (warp < 4) {
+    uint32_t sf[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sf[i] = 0x7F7F7F7Fu;
+    tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + p.sf_base, sf);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CS > 1) cluster_sync_all();   // peers must see initialised barriers / scale factors before any remote arrive / MMA
+  tc_fence_after();
+
+  const int cta_rank = CS > 1 ? (int)cluster_ctarank() : 0;
+  const int first_tile = (CS > 1 ? (int)cluster_id_x() * CS : (int)blockIdx.x) + cta_rank;
+  const int tile_step = CS > 1 ? (int)n_clusters_x() * CS : (int)gridDim.x;
+  const int tile_end = CS > 1 ? p.n_tiles + cta_rank : p.n_tiles;   // (tile - rank) < n_tiles for every CTA alike
+  const int panel_bytes = p.ncols / CS * 128;   // this CTA's rows of one basis panel (256 samples)
+  auto tile_mode = [&](int tile) {
+    if (CS == 1) return tile_has_missing(p, tile);
+    const int t0 = tile - cta_rank;
+    return tile_has_missing(p, t0) || tile_has_missing(p, t0 + 1);
+  };
+
+  if (warp == WARP_TMA_G) {
+    // ============================== genotype producer ==============================
+    int gs = 0;
+    uint32_t g_phase = 0;
+    for (int tile = first_tile; tile < tile_end; tile += tile_step) {
+      for (int ch = 0; ch < p.n_chunks; ++ch) {
+        mbar_wait(GEMPTY(gs), g_phase ^ 1);
+        const uint32_t sbase = smem0 + gs * p.gstage_bytes;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(GFULL(gs), (uint32_t)(GENO_BYTES + p.mask_bytes));
+          if (p.abl_contig) tma_load_2d(&geno_map, GFULL(gs), sbase, 0, (tile * p.n_chunks + ch) * TILE_M);
+          else tma_load_2d(&geno_map, GFULL(gs), sbase, ch * 128, tile * TILE_M);
+          if (p.mask_bytes) {
+            for (int g = 0; g < n_groups; ++g)
+              bulk_load_1d(sbase + GENO_BYTES + g * 128, p.g[g].mask_hi + ch * (CHUNK / 16), 128, GFULL(gs));
+          }
+        }
+        __syncwarp();
+        if (++gs == p.n_gstages) { gs = 0; g_phase ^= 1; }
+      }
+    }
+  } else if (warp == WARP_TMA_B) {
+    // ============================== basis-panel producer ==============================
+    int bs = 0;
+    uint32_t b_phase = 0;
+    for (int tile = first_tile; tile < tile_end; tile += tile_step) {
+      for (int ch = 0; ch < p.n_chunks; ++ch) {
+        mbar_wait(BEMPTY(bs), b_phase ^ 1);
+        const uint32_t sbase = bring0 + bs * p.bstage_bytes;
+        if (elect_one()) {
+          if (CS == 1) {
+            mbar_arrive_expect_tx(BFULL(bs), (uint32_t)(PANELS * panel_bytes));
+#pragma unroll
+            for (int s = 0; s < PANELS; ++s)
+              tma_load_2d(&b_map, BFULL(bs), sbase + s * panel_bytes, ch * (CHUNK / 2) + s * (PANEL / 2), 0);
+          } else {
+            if (cta_rank == 0) mbar_arrive_expect_tx(BFULL(bs), (uint32_t)(2 * PANELS * panel_bytes));
+            const uint32_t full_leader = mapa_leader(BFULL(bs));
+#pragma unroll
+            for (int s = 0; s < PANELS; ++s)
+              tma_load_2d_pair(&b_map, full_leader, sbase + s * panel_bytes, ch * (CHUNK / 2) + s * (PANEL / 2),
+                               cta_rank * (p.ncols / 2));
+          }
+        }
+        __syncwarp();
+        if (++bs == p.n_bstages) { bs = 0; b_phase ^= 1; }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ============================== MMA issuer (pair: the leader only) ==============================
+    if (CS == 1 || cta_rank == 0) {
+      const uint32_t idesc = make_idesc(p.ncols, TILE_M * CS);
+      const uint32_t sfa = tmem + p.sf_base, sfb = tmem + p.sf_base + 8;
+      auto commit = [&](uint32_t bar) {
+        if (CS == 1) tc_commit(bar); else tc_commit_pair(bar);
+      };
+      int bs = 0;
+      uint32_t b_phase = 0;
+      int ru = 0;               // next ring unit
+      uint32_t full_par = 0;    // bit u: parity of the next completion of AFULL(u) this warp waits for
+      uint32_t tile_i = 0;
+      const uint64_t desc0 = make_kmajor_sw128_desc(bring0);
+      const uint32_t stage_d = (uint32_t)p.bstage_bytes >> 4;   // descriptor-address units (16 B)
+      const uint32_t panel_d = (uint32_t)panel_bytes >> 4;
+      const uint32_t a_ring = tmem + p.ring_base;
+
+      // the MMAs of one chunk: unit `u` (+ `u + 1` = plane m), basis stage descriptor `bd`
+      auto issue = [&](auto tp_tag, const int u, const uint64_t bd, const uint32_t first_acc) {
+        constexpr bool TP = decltype(tp_tag)::value;
+        const uint32_t a_c = a_ring + u * UNIT_COLS;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t acc = (s | j) ? 1u : first_acc;
+            const uint64_t d = bd + (uint64_t)((s >> 1) * panel_d + ((s & 1) * 2 + j) * 2);
+            mma_mxf4_ts<CS>(tmem, a_c + s * SLOT_COLS + j * 8, d, idesc, sfa, sfb, acc);
+            if (TP) mma_mxf4_ts<CS>(tmem + p.ncols, a_c + UNIT_COLS + s * SLOT_COLS + j * 8, d, idesc, sfa, sfb, acc);
+          }
+      };
+      auto generic_chunk = [&](int ch, bool two_plane) {
+        mbar_wait(BFULL(bs), b_phase);
+        if (two_plane && (ru & 1)) ru = (ru + 1) & (NU - 1);
+        mbar_wait(AFULL(ru), (full_par >> ru) & 1u);
+        full_par ^= 1u << ru;
+        tc_fence_after();
+        const uint64_t bd = desc0 + (uint64_t)(bs * stage_d);
+        if (elect_one()) {
+          if (two_plane) issue(TrueTag{}, ru, bd, ch ? 1u : 0u); else issue(FalseTag{}, ru, bd, ch ? 1u : 0u);
+          commit(AEMPTY(ru));
+          commit(BEMPTY(bs));
+        }
+        __syncwarp();
+        ru = (ru + (two_plane ? 2 : 1)) & (NU - 1);
+        if (++bs == p.n_bstages) { bs = 0; b_phase ^= 1; }
+      };
+      // fast path: UNROLL chunks with every ring position a compile-time constant (entered with bs == 0, ru == 0)
+      auto fast_chunks = [&](auto tp_tag, int& ch) {
+        constexpr bool TP = decltype(tp_tag)::value;
+        for (; ch + UNROLL <= p.n_chunks; ch += UNROLL) {
+#pragma unroll
+          for (int k = 0; k < UNROLL; ++k) {
+            constexpr int dummy = 0; (void)dummy;
+            const int b = k % NB;
+            const int u = TP ? (2 * k) % NU : k % NU;
+            mbar_wait(BFULL(b), b_phase ^ (uint32_t)((k / NB) & 1));
+            mbar_wait(AFULL(u), (full_par >> u) & 1u);
+            full_par ^= 1u << u;
+            tc_fence_after();
+            const uint64_t bd = desc0 + (uint64_t)(b * stage_d);
+            if (elect_one()) {
+              issue(tp_tag, u, bd, k ? 1u : (ch ? 1u : 0u));
+              commit(AEMPTY(u));
+              commit(BEMPTY(b));
+            }
+            __syncwarp();
+          }
+          // UNROLL / NB = 2 passes over the basis ring: its parity is unchanged
+        }
+      };
+
+      for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
+        const bool two_plane = tile_mode(tile);
+        mbar_wait(DEMPTY, (tile_i & 1) ^ 1);   // the previous tile's accumulators have been read out (by both CTAs)
+        tc_fence_after();
+        int ch = 0;
+        if (p.n_bstages == NB) {
+          while (ch < p.n_chunks && (bs != 0 || ru != 0)) generic_chunk(ch++, two_plane);
+          if (ch < p.n_chunks) {
+            if (two_plane) fast_chunks(TrueTag{}, ch); else fast_chunks(FalseTag{}, ch);
+          }
+        }
+        for (; ch < p.n_chunks; ++ch) generic_chunk(ch, two_plane);
+        if (elect_one()) commit(DFULL);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============================== unpack + epilogue warps ==============================
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int s = warp >> 2;         // slot of every chunk this warp produces
+    const int row = q * 32 + lane;   // variant row within the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t ld0 = row_off + (((uint32_t)(2 * s) ^ swz) << 4);       // 16-byte chunks 2s, 2s+1 (swizzled)
+    const uint32_t ld1 = row_off + (((uint32_t)(2 * s + 1) ^ swz) << 4);
+    uint32_t gaddr = smem0;          // shared address of the current genotype stage
+    uint32_t gbar = GFULL(0);        // its "full" barrier ("empty" is MAX_GSTAGES * 8 bytes further)
+    const uint32_t gaddr_end = smem0 + p.n_gstages * p.gstage_bytes;
+    uint32_t g_phase = 0;
+    int ru = 0;                      // next ring unit (same sequence as the MMA warp's)
+    uint32_t empty_par = 0;          // bit u: parity of the last completion of AEMPTY(u) this warp relies on
+    uint32_t tile_i = 0;
+    bool prev_two_plane = false;
+    const uint32_t a_slot = tmem + lane_addr + p.ring_base + s * SLOT_COLS;
+    int n2[NG ? NG : MAX_GROUPS];
+    const uint32_t afull_leader = (CS == 2) ? mapa_leader(AFULL(0)) : 0u;
+    const uint32_t dempty_leader = (CS == 2) ? mapa_leader(DEMPTY) : 0u;
+    auto arrive_afull = [&](int u) {
+      if (CS == 1) mbar_arrive(AFULL(u)); else mbar_arrive_cluster(afull_leader + 8u * (uint32_t)u);
+    };
+
+    // The chunk loop of one tile, specialised on the tile's mode (TP: two planes) and on whether any group needs its
+    // sample mask for the hom-alt count (MA: none does).
+    auto run_chunks = [&](auto tp_tag, auto ma_tag) {
+      constexpr bool TP = decltype(tp_tag)::value;
+      constexpr bool MA = decltype(ma_tag)::value;
+      int pend = -1;    // unit whose TMEM store is issued but not yet published to the MMA warp
+      auto chunk_body = [&](const int u, const int pend_u) {
+        mbar_wait(gbar, g_phase);
+        const uint4 w0 = lds128(gaddr + ld0);   // packed bytes of samples [128 s, 128 s + 128) of this row
+        const uint4 w1 = lds128(gaddr + ld1);
+        const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        uint32_t mm[NG ? NG : MAX_GROUPS][8];
+        if (!MA) {
+#pragma unroll
+          for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
+            if (NG || g < n_groups) {
+              const uint4 m0 = lds128(gaddr + GENO_BYTES + g * 128 + s * 32);
+              const uint4 m1 = lds128(gaddr + GENO_BYTES + g * 128 + s * 32 + 16);
+              mm[g][0] = m0.x; mm[g][1] = m0.y; mm[g][2] = m0.z; mm[g][3] = m0.w;
+              mm[g][4] = m1.x; mm[g][5] = m1.y; mm[g][6] = m1.z; mm[g][7] = m1.w;
+            }
+          }
+        }
+        // 2-bit fields -> nibbles 00cc: word i gives column 2i (fields 0 / 2 of every byte in the low / high nibble)
+        // and column 2i + 1 (fields 1 / 3); the basis panels are stored in the same element order (quantize_kernel)
+        uint32_t rc[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rc[2 * i + 0] = w[i] & 0x33333333u;
+          rc[2 * i + 1] = (w[i] >> 2) & 0x33333333u;
+        }
+        // exact counts for x.x = n1 + 4 n2 (see tc_kernel.cu)
+#pragma unroll
+        for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
+          if (NG || g < n_groups) {
+            int acc = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (MA && !TP) {
+                acc += __popc(w[i]);
+              } else {
+                const uint32_t m = MA ? 0xAAAAAAAAu : mm[g][i];
+                acc += TP ? __popc(w[i] & ~(w[i] << 1) & m) : __popc(w[i] & m);
+              }
+            }
+            n2[g] += acc;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gbar + 8u * MAX_GSTAGES);   // genotype stage back to the TMA producer
+        if (pend_u >= 0) {   // retire the previous chunk's TMEM store behind this chunk's arithmetic
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_afull(pend_u);
+        }
+        mbar_wait(AEMPTY(u), ((empty_par >> u) & 1u) ^ 1u);
+        empty_par ^= 1u << u;
+        tc_fence_after();
+        tmem_st16(a_slot + u * UNIT_COLS, rc);
+        if (TP) {
+          // missing-indicator plane: nibble 0001 (= 0.5) where the call is code 3
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t mw = w[i] & (w[i] >> 1);   // bit 2f set iff field f is code 3
+            rc[2 * i + 0] = mw & 0x11111111u;
+            rc[2 * i + 1] = (mw >> 2) & 0x11111111u;
+          }
+          tmem_st16(a_slot + (u + 1) * UNIT_COLS, rc);
+        }
+        gaddr += p.gstage_bytes;
+        gbar += 8u;
+        if (gaddr == gaddr_end) { gaddr = smem0; gbar = GFULL(0); g_phase ^= 1; }
+      };
+      auto generic_chunk = [&]() {
+        if (TP && (ru & 1)) ru = (ru + 1) & (NU - 1);
+        chunk_body(ru, pend);
+        pend = ru;
+        ru = (ru + (TP ? 2 : 1)) & (NU - 1);
+      };
+      int ch = 0;
+      // steady state unrolled over the ring (positions become constants): entered with ru == 0
+      do { generic_chunk(); ++ch; } while (ch < p.n_chunks && ru != 0);
+      if (!TP) {
+        for (; ch + 4 <= p.n_chunks; ch += 4) {   // pend == 3 here
+          chunk_body(0, pend);
+          chunk_body(1, 0);
+          chunk_body(2, 1);
+          chunk_body(3, 2);
+          pend = 3;
+        }
+      } else {
+        for (; ch + 2 <= p.n_chunks; ch += 2) {   // pend == 2 here
+          chunk_body(0, pend);
+          chunk_body(2, 0);
+          pend = 2;
+        }
+      }
+      for (; ch < p.n_chunks; ++ch) generic_chunk();
+      if (pend >= 0) {   // flush the last chunk of the tile
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_afull(pend);
+      }
+    };
+
+    for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
+      const bool two_plane = tile_mode(tile);
+      if (tile_i > 0 && two_plane != prev_two_plane) {
+        // the ring is laid out differently: wait until every MMA of the previous tile has retired
+        mbar_wait(DFULL, (tile_i - 1) & 1);
+        tc_fence_after();
+      }
+      prev_two_plane = two_plane;
+#pragma unroll
+      for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) n2[g] = 0;
+      if (two_plane) {
+        if (p.mask_bytes == 0) run_chunks(TrueTag{}, TrueTag{}); else run_chunks(TrueTag{}, FalseTag{});
+      } else {
+        if (p.mask_bytes == 0) run_chunks(FalseTag{}, TrueTag{}); else run_chunks(FalseTag{}, FalseTag{});
+      }
+
+      // ------------------------------ per-tile epilogue ------------------------------
+      if (s > 0) {
+#pragma unroll
+        for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g)
+          if (NG || g < n_groups) bars->n2_xchg[tile_i & 1][s - 1][g][row] = n2[g];
+      }
+      named_bar_sync(1, UNPACK_WARPS * 32);
+      if (s == 0) {
+        mbar_wait(DFULL, tile_i & 1);
+        tc_fence_after();
+        const int64_t v = (int64_t)tile * TILE_M + row;
+        const uint32_t d_c = tmem + lane_addr, d_m = tmem + lane_addr + p.ncols;
+#pragma unroll
+        for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
+          if (!(NG || g < n_groups)) continue;
+          const GroupMeta& G = p.g[g];
+          const int cnt = n2[g] + bars->n2_xchg[tile_i & 1][0][g][row] + bars->n2_xchg[tile_i & 1][1][g][row] +
+                          bars->n2_xchg[tile_i & 1][2][g][row];
+          // the group's columns: Kd x DIG_Q then P x DIG_Y digit columns, then one "ones" column (digit value 1.0)
+          const int n_digit_cols = G.Kd * DIG_Q + (G.C - G.Kd) * DIG_Y;
+          const int ones_col = G.col_off + n_digit_cols;
+          uint32_t r16[16];
+          tmem_ld16(d_c + (ones_col & ~15), r16);
+          tmem_wait_ld();
+          float sc_f = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i == (ones_col & 15)) sc_f = __uint_as_float(r16[i]);
+          float nm_f = 0.f;
+          if (two_plane) {
+            tmem_ld16(d_m + (ones_col & ~15), r16);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i == (ones_col & 15)) nm_f = __uint_as_float(r16[i]);
+          }
+          const int sc = __float2int_rn(2.f * sc_f);   // sum of codes: A = c / 2, ones digit = 1.0
+          const int nm = __float2int_rn(2.f * nm_f);   // missing calls: A = 1 / 2
+          const int S = sc - 3 * nm;                   // n1 + 2 n2
+          const int n2g = (!two_plane && p.mask_bytes == 0) ? S - cnt : cnt;
+          const int n1 = S - 2 * n2g;
+          const double mean = (double)S / (double)(G.n - nm);
+          if (v < p.M) reinterpret_cast<int4*>(G.counts)[v] = make_int4(n1, n2g, nm, 0);
+          // digit columns, 16 TMEM columns at a time: accumulator = sum c u / 4 with u the base-13 digit
+          const int c_lo = G.col_off, c_hi = ones_col;
+          long long hi = 0, lo = 0, mhi = 0, mlo = 0;
+          long long pw = 1;   // 13^sl (sl < 6) or 13^(sl - 6)
+          int c = 0, sl = 0, nd = G.Kd > 0 ? DIG_Q : DIG_Y;
+          for (int base = c_lo & ~15; base < c_hi; base += 16) {
+            uint32_t dc[16], dm[16];
+            tmem_ld16(d_c + base, dc);
+            if (two_plane) tmem_ld16(d_m + base, dm);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = base + i;
+              if (col >= c_lo && col < c_hi) {
+                const long long cv = (long long)__float2int_rn(4.f * __uint_as_float(dc[i]));
+                const long long mv = two_plane ? (long long)__float2int_rn(4.f * __uint_as_float(dm[i])) : 0ll;
+                const long long dv = cv - 3ll * mv;
+                if (sl < 6) {
+                  lo += dv * pw;
+                  mlo += mv * pw;
+                } else {
+                  hi += dv * pw;
+                  mhi += mv * pw;
+                }
+                pw *= 13;
+                if (++sl == 6) pw = 1;
+                if (sl == nd) {
+                  const double scale = G.colscale[c];
+                  double dot = fma((double)hi, 4826809.0, (double)lo) * scale;
+                  if (two_plane && nm > 0) dot += mean * (fma((double)mhi, 4826809.0, (double)mlo) * scale);
+                  if (v < p.M) G.dots[v * G.dots_stride + c] = dot;
+                  hi = lo = mhi = mlo = 0;
+                  sl = 0;
+                  pw = 1;
+                  ++c;
+                  nd = c < G.Kd ? DIG_Q : DIG_Y;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CS == 1) mbar_arrive(DEMPTY); else mbar_arrive_cluster(dempty_leader);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (CS > 1) cluster_sync_all();   // no CTA may exit while its peer can still signal / run MMAs into it
+  if (warp == WARP_MMA) {
+    if (CS == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// basis quantisation: float64 column -> balanced base-13 digits as E2M1 nibbles, in the A operand's element order
+// ------------------------------------------------------------------------------------------------
+__global__ void colmax_kernel(const double* __restrict__ basis, int C, int64_t ns_pad, unsigned long long* colmax_bits) {
+  const int c = blockIdx.y;
+  double m = 0.0;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ns_pad; j += (int64_t)gridDim.x * blockDim.x)
+    m = fmax(m, fabs(basis[(int64_t)c * ns_pad + j]));
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(colmax_bits + c, (unsigned long long)__double_as_longlong(m));
+}
+
+// digit of residue r = I mod 13, chosen from {0, +-1, +-2, +-3, +-4, +-6, +-8} (complete residue system mod 13)
+__device__ __forceinline__ int digit13(long long& I) {
+  const int r = (int)(((I % 13) + 13) % 13);
+  const int d = (r <= 4) ? r : (r == 5 ? -8 : (r == 6 ? 6 : (r == 7 ? -6 : (r == 8 ? 8 : r - 13))));
+  I = (I - d) / 13;
+  return d;
+}
+// E2M1 code of the value u / 2 for a digit u
+__device__ __forceinline__ uint32_t e2m1_code(int u) {
+  const int a = u < 0 ? -u : u;
+  const uint32_t m = a <= 4 ? (uint32_t)a : (a == 6 ? 5u : 6u);   // 0, .5, 1, 1.5, 2 | 3 | 4
+  return m | (u < 0 ? 8u : 0u);
+}
+__host__ __device__ inline double imax13(int nd) {   // floor(13^nd / 3): every |I| up to it has nd digits
+  double p13 = 1.0;
+  for (int i = 0; i < nd; ++i) p13 *= 13.0;
+  return floor(p13 / 3.0);
+}
+
+// One thread per byte of a panel row.  Byte b of a row covers word wd = b / 8 of the packed genotype row (16 samples):
+// with r = (b % 8) / 4 and i = b % 4 its low nibble is sample 16 wd + 4 r + i, its high nibble sample 16 wd + 4 (r + 2) + i
+// -- the order in which the unpack warps emit the calls of a word.
+__global__ void quantize_kernel(const double* __restrict__ basis, const uint32_t* __restrict__ mask, int C, int Kd,
+                                int64_t ns_pad, const unsigned long long* __restrict__ colmax_bits, int col_off,
+                                uint8_t* __restrict__ bq, double* __restrict__ colscale) {
+  const int c = blockIdx.y;  // 0..C-1 data columns, C = ones column
+  const int nd = c < Kd ? DIG_Q : DIG_Y;
+  const int first = col_off + (c < Kd ? c * DIG_Q : Kd * DIG_Q + (c - Kd) * DIG_Y);
+  const double imax = imax13(nd);
+  const int64_t row_bytes = ns_pad / 2;
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < row_bytes; b += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t wd = b >> 3;
+    const int r = (int)((b >> 2) & 1), i = (int)(b & 3);
+    const int64_t j_lo = 16 * wd + 4 * r + i, j_hi = j_lo + 8;
+    if (c == C) {
+      const uint32_t mw = mask[wd];
+      const uint32_t in_lo = (mw >> sample_shift((int)(j_lo & 15))) & 1u, in_hi = (mw >> sample_shift((int)(j_hi & 15))) & 1u;
+      bq[(int64_t)first * row_bytes + b] = (uint8_t)((in_lo ? 2u : 0u) | ((in_hi ? 2u : 0u) << 4));   // digit value 1.0
+      continue;
+    }
+    const double cm = __longlong_as_double((long long)colmax_bits[c]);
+    long long I_lo = 0, I_hi = 0;
+    if (cm > 0.0) {
+      I_lo = __double2ll_rn(basis[(int64_t)c * ns_pad + j_lo] / cm * imax);
+      I_hi = __double2ll_rn(basis[(int64_t)c * ns_pad + j_hi] / cm * imax);
+    }
+    for (int s = 0; s < nd; ++s) {
+      const uint32_t lo = e2m1_code(digit13(I_lo)), hi = e2m1_code(digit13(I_hi));
+      bq[(int64_t)(first + s) * row_bytes + b] = (uint8_t)(lo | (hi << 4));
+    }
+    if (b == 0) colscale[c] = cm > 0.0 ? cm / imax : 0.0;
+  }
+}
+
+// Worst case of |sum_j c_j u_j| over all genotypes (c <= 3) for one panel row; the f32 accumulator holds sum c u / 4
+// exactly while this stays <= 2^24.
+__global__ void acc_bound_kernel(const uint8_t* __restrict__ bq, int64_t row_bytes, unsigned long long* __restrict__ bound) {
+  const int64_t r = blockIdx.y;
+  unsigned long long pos = 0, neg = 0;
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < row_bytes; b += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t byte = bq[r * row_bytes + b];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t code = (byte >> (4 * h)) & 15u;
+      const uint32_t m = code & 7u;
+      const unsigned long long u = m <= 4 ? m : (m == 5 ? 6ull : (m == 6 ? 8ull : 12ull));
+      if (code & 8u) neg += 3ull * u; else pos += 3ull * u;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    pos += __shfl_xor_sync(0xffffffffu, pos, o);
+    neg += __shfl_xor_sync(0xffffffffu, neg, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(bound + 2 * r, pos);
+    atomicAdd(bound + 2 * r + 1, neg);
+  }
+}
+
+__global__ void mask_hi_kernel(const uint32_t* __restrict__ mask_lo, int64_t words, uint32_t* __restrict__ mask_hi) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x)
+    mask_hi[i] = mask_lo[i] << 1;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Segment {
+  int group;     // index into Ctx::groups
+  int c_first;   // first dot column of the group in this segment
+  int n_cols;    // dot columns in this segment
+  int kd_in;     // of which (leading) covariate columns
+  int row0;      // first row of this segment in the pass's panel matrix (digit rows, then the ones row)
+};
+
+struct PassShape {
+  int n_gstages = 0, n_bstages = 0, bstage_bytes = 0, smem_bytes = 0;
+  CUtensorMap b_map;
+};
+
+struct Pass {
+  int ncols = 0;                 // panel rows, padded to 16
+  int64_t bq_row0 = 0;           // first row of this pass in State::d_bq
+  std::vector<Segment> segs;
+  int gstage_bytes = 0;
+  int sf_base = 0, ring_base = 0, mask_bytes = 0;
+  PassShape shape[2];            // [cluster size - 1]
+};
+
+struct State {
+  bool prepared = false;
+  bool usable = false;
+  std::string why;
+  EncodeTiledFn encode = nullptr;
+  std::vector<Pass> passes;
+  uint8_t* d_bq = nullptr;
+  double* d_colscale = nullptr;
+  unsigned long long* d_colmax = nullptr;
+  uint32_t* d_mask_hi = nullptr;
+  std::vector<int> scale_off;
+  int cluster = 2;
+  bool attr_set = false;
+};
+
+static State* state(Ctx* c) {
+  if (!c->tc4_state) c->tc4_state = new State();
+  return static_cast<State*>(c->tc4_state);
+}
+
+static void free_prepared(State* s) {
+  cudaFree(s->d_bq);
+  cudaFree(s->d_colscale);
+  cudaFree(s->d_colmax);
+  cudaFree(s->d_mask_hi);
+  s->d_mask_hi = nullptr;
+  s->d_bq = nullptr;
+  s->d_colscale = nullptr;
+  s->d_colmax = nullptr;
+  s->passes.clear();
+  s->prepared = false;
+  s->usable = false;
+}
+
+static int encode_2d(State* s, CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride,
+                     uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = s->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         getenv("LRR_ABL_L2P128") ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                         : getenv("LRR_ABL_L2PNONE") ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// split every group's dot columns into passes of at most PASS_COLS panel rows
+static void plan_passes(const Ctx* c, std::vector<Pass>& passes) {
+  passes.clear();
+  Pass cur;
+  int used = 0;
+  auto close = [&]() {
+    if (!cur.segs.empty()) {
+      cur.ncols = (used + 15) / 16 * 16;
+      passes.push_back(cur);
+    }
+    cur = Pass();
+    used = 0;
+  };
+  for (size_t g = 0; g < c->groups.size(); ++g) {
+    const Group& gr = c->groups[g];
+    int col = 0;
+    while (col < gr.C) {
+      const int nd0 = col < gr.Kd ? DIG_Q : DIG_Y;
+      if (used + nd0 + 1 > PASS_COLS || (int)cur.segs.size() == MAX_GROUPS) close();
+      Segment sg;
+      sg.group = (int)g;
+      sg.c_first = col;
+      sg.n_cols = 0;
+      sg.kd_in = 0;
+      sg.row0 = used;
+      int rows = 0;
+      while (col < gr.C) {
+        const int nd = col < gr.Kd ? DIG_Q : DIG_Y;
+        if (used + rows + nd + 1 > PASS_COLS) break;
+        rows += nd;
+        if (col < gr.Kd) sg.kd_in++;
+        sg.n_cols++;
+        col++;
+      }
+      used += rows + 1;   // + ones row
+      cur.segs.push_back(sg);
+      if (col < gr.C) close();
+    }
+  }
+  close();
+}
+
+static int prepare(Ctx* c) {
+  State* s = state(c);
+  if (s->prepared) return LRR_OK;
+  free_prepared(s);
+  s->prepared = true;
+  s->usable = false;
+  if (!s->encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      cudaGetLastError();
+      s->why = "cuTensorMapEncodeTiled is not available from the driver";
+      return LRR_OK;
+    }
+    s->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const size_t G = c->groups.size();
+  if (G == 0) {
+    s->why = "no groups";
+    return LRR_OK;
+  }
+  int nscale = 0;
+  s->scale_off.assign(G, 0);
+  for (size_t g = 0; g < G; ++g) {
+    s->scale_off[g] = nscale;
+    nscale += c->groups[g].C;
+  }
+  plan_passes(c, s->passes);
+  int64_t total_rows = 0;
+  for (auto& ps : s->passes) {
+    ps.bq_row0 = total_rows;
+    total_rows += ps.ncols;
+  }
+  const int64_t ns_pad = c->groups[0].ns_pad;
+  const int64_t row_bytes = ns_pad / 2;
+  LRR_CUDA(c, cudaMalloc(&s->d_bq, (size_t)total_rows * row_bytes));
+  LRR_CUDA(c, cudaMemset(s->d_bq, 0, (size_t)total_rows * row_bytes));
+  LRR_CUDA(c, cudaMalloc(&s->d_colscale, sizeof(double) * (size_t)nscale));
+  LRR_CUDA(c, cudaMalloc(&s->d_colmax, sizeof(unsigned long long) * (size_t)nscale));
+  LRR_CUDA(c, cudaMemset(s->d_colmax, 0, sizeof(unsigned long long) * (size_t)nscale));
+  const int64_t mask_words = ns_pad / 16;
+  LRR_CUDA(c, cudaMalloc(&s->d_mask_hi, sizeof(uint32_t) * (size_t)mask_words * G));
+  bool any_masked = false;
+  const unsigned gx = (unsigned)std::min<int64_t>((ns_pad + 255) / 256, 1024);
+  const unsigned gxb = (unsigned)std::min<int64_t>((row_bytes + 255) / 256, 1024);
+  for (size_t g = 0; g < G; ++g) {
+    const Group& gr = c->groups[g];
+    if ((int64_t)gr.n != c->n_samples_total) any_masked = true;
+    mask_hi_kernel<<<(unsigned)std::min<int64_t>((mask_words + 255) / 256, 1024), 256>>>(gr.d_mask, mask_words,
+                                                                                        s->d_mask_hi + g * mask_words);
+    for (int c0 = 0; c0 < gr.C; c0 += 65535)
+      colmax_kernel<<<dim3(gx, (unsigned)std::min(gr.C - c0, 65535)), 256>>>(gr.d_basis + (int64_t)c0 * ns_pad,
+                                                                            std::min(gr.C - c0, 65535), ns_pad,
+                                                                            s->d_colmax + s->scale_off[g] + c0);
+    c->launches += 2;
+  }
+  for (auto& ps : s->passes) {
+    for (const Segment& sg : ps.segs) {
+      const Group& gr = c->groups[sg.group];
+      quantize_kernel<<<dim3(gxb, (unsigned)(sg.n_cols + 1)), 256>>>(
+          gr.d_basis + (int64_t)sg.c_first * ns_pad, gr.d_mask, sg.n_cols, sg.kd_in, ns_pad,
+          s->d_colmax + s->scale_off[sg.group] + sg.c_first, (int)(ps.bq_row0 + sg.row0), s->d_bq,
+          s->d_colscale + s->scale_off[sg.group] + sg.c_first);
+      c->launches++;
+    }
+  }
+  LRR_CUDA(c, cudaGetLastError());
+  {
+    // exactness guard: no f32 accumulator can leave the exactly-representable range, whatever the genotypes are
+    unsigned long long* d_bound = nullptr;
+    LRR_CUDA(c, cudaMalloc(&d_bound, sizeof(unsigned long long) * 2 * (size_t)total_rows));
+    LRR_CUDA(c, cudaMemset(d_bound, 0, sizeof(unsigned long long) * 2 * (size_t)total_rows));
+    for (int64_t r0 = 0; r0 < total_rows; r0 += 65535)
+      acc_bound_kernel<<<dim3(gxb, (unsigned)std::min<int64_t>(total_rows - r0, 65535)), 256>>>(s->d_bq + r0 * row_bytes,
+                                                                                             row_bytes, d_bound + 2 * r0);
+    c->launches++;
+    std::vector<unsigned long long> h_bound(2 * (size_t)total_rows);
+    cudaError_t e = cudaMemcpy(h_bound.data(), d_bound, sizeof(unsigned long long) * h_bound.size(), cudaMemcpyDeviceToHost);
+    cudaFree(d_bound);
+    if (e != cudaSuccess) return cuda_fail(c, e, "tc4 acc_bound_kernel");
+    unsigned long long worst = 0;
+    for (unsigned long long v : h_bound) worst = std::max(worst, v);
+    if (worst > (1ull << 24)) {
+      s->why = "f32 accumulators could leave the exact range for this many samples (worst-case column bound " +
+               std::to_string(worst) + " > 2^24)";
+      return LRR_OK;
+    }
+  }
+  LRR_CUDA(c, cudaDeviceSynchronize());
+  const int budget = 227 * 1024 - (int)sizeof(Barriers) - 1024;
+  for (auto& ps : s->passes) {
+    ps.mask_bytes = any_masked ? (int)ps.segs.size() * 128 : 0;
+    ps.gstage_bytes = (GENO_BYTES + ps.mask_bytes + 1023) / 1024 * 1024;
+    ps.sf_base = 2 * ps.ncols;
+    ps.ring_base = (2 * ps.ncols + SF_COLS + 31) / 32 * 32;
+    if (ps.ring_base + NU * UNIT_COLS > 512) {
+      s->why = "not enough tensor memory for the A ring";
+      return LRR_OK;
+    }
+    for (int cs = 1; cs <= 2; ++cs) {
+      PassShape& sh = ps.shape[cs - 1];
+      const int rows = ps.ncols / cs;   // panel rows held by one CTA
+      if (encode_2d(s, &sh.b_map, s->d_bq + ps.bq_row0 * row_bytes, (uint64_t)row_bytes, (uint64_t)ps.ncols,
+                    (uint64_t)row_bytes, PANEL / 2, (uint32_t)rows)) {
+        s->why = "cuTensorMapEncodeTiled failed for the basis panels";
+        return LRR_OK;
+      }
+      sh.bstage_bytes = PANELS * rows * 128;
+      int bst = NB;
+      if (bst > 3 && budget - bst * sh.bstage_bytes < 6 * ps.gstage_bytes) bst = 3;
+      while (bst > 2 && budget - bst * sh.bstage_bytes < 3 * ps.gstage_bytes) --bst;
+      int gst = (budget - bst * sh.bstage_bytes) / ps.gstage_bytes;
+      if (gst > MAX_GSTAGES) gst = MAX_GSTAGES;
+      if (bst < 2 || gst < 2) {
+        s->why = "not enough shared memory for the genotype / basis-panel rings";
+        return LRR_OK;
+      }
+      sh.n_gstages = gst;
+      sh.n_bstages = bst;
+      sh.smem_bytes = gst * ps.gstage_bytes + bst * sh.bstage_bytes + (int)sizeof(Barriers) + 1024;
+    }
+  }
+  if (!s->attr_set) {
+#define LRR_SET_SMEM(NG_, CS_) \
+  LRR_CUDA(c, cudaFuncSetAttribute(tc4_sweep_kernel<NG_, CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+    LRR_SET_SMEM(0, 1); LRR_SET_SMEM(1, 1); LRR_SET_SMEM(2, 1);
+    LRR_SET_SMEM(0, 2); LRR_SET_SMEM(1, 2); LRR_SET_SMEM(2, 2);
+#undef LRR_SET_SMEM
+    s->attr_set = true;
+  }
+  if (const char* e = getenv("LRR_TC_CLUSTER")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2) s->cluster = v;
+  }
+  s->usable = true;
+  s->why.clear();
+  return LRR_OK;
+}
+
+}  // namespace tc4
+
+// usable at all; `single_pass_only`: only when one sweep covers every column (what LRR_KERNEL_AUTO asks)
+bool tc4_supported(Ctx* c, bool single_pass_only) {
+  if (tc4::prepare(c) != LRR_OK) return false;
+  tc4::State* s = tc4::state(c);
+  if (!s->usable) {
+    c->err = s->why;
+    return false;
+  }
+  if (single_pass_only && s->passes.size() > 1) {
+    c->err = "more digit columns than one 4-bit sweep holds";
+    return false;
+  }
+  return true;
+}
+
+void tc4_invalidate(Ctx* c) {
+  if (!c->tc4_state) return;
+  tc4::free_prepared(static_cast<tc4::State*>(c->tc4_state));
+}
+
+void tc4_release(Ctx* c) {
+  if (!c->tc4_state) return;
+  tc4::State* s = static_cast<tc4::State*>(c->tc4_state);
+  tc4::free_prepared(s);
+  delete s;
+  c->tc4_state = nullptr;
+}
+
+int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride,
+                     cudaStream_t st) {
+  using namespace tc4;
+  if (M == 0) return LRR_OK;
+  if (int r = prepare(c)) return r;
+  State* s = state(c);
+  if (!s->usable) return fail(c, LRR_EINVAL, "4-bit tensor-core kernel unavailable: " + s->why);
+  CUtensorMap geno_map;
+  const bool abl_contig = getenv("LRR_ABL_CONTIG") != nullptr;   // timing ablation only
+  if (abl_contig) {
+    if (encode_2d(s, &geno_map, d_packed, 128, (uint64_t)(M * stride / 128), 128, 128, TILE_M))
+      return fail(c, LRR_ECUDA, "cuTensorMapEncodeTiled failed (contiguous ablation)");
+  } else if (encode_2d(s, &geno_map, d_packed, (uint64_t)stride, (uint64_t)M, (uint64_t)stride, 128, TILE_M))
+    return fail(c, LRR_ECUDA, "cuTensorMapEncodeTiled failed for the genotype store (pointer must be 16-byte aligned)");
+  for (const Pass& ps : s->passes) {
+    Params p;
+    memset(&p, 0, sizeof p);
+    p.M = M;
+    p.n_tiles = (int)((M + TILE_M - 1) / TILE_M);
+    p.n_chunks = (int)(stride / 128);
+    p.ncols = ps.ncols;
+    int cs = s->cluster;
+    if (p.n_tiles < 2 * cs) cs = 1;
+    const PassShape& sh = ps.shape[cs - 1];
+    p.n_gstages = sh.n_gstages;
+    p.n_bstages = sh.n_bstages;
+    p.n_groups = (int)ps.segs.size();
+    p.sf_base = ps.sf_base;
+    p.ring_base = ps.ring_base;
+    p.gstage_bytes = ps.gstage_bytes;
+    p.bstage_bytes = sh.bstage_bytes;
+    p.mask_bytes = ps.mask_bytes;
+    p.row_flags = d_row_flags;
+    p.abl_contig = abl_contig ? 1 : 0;
+    for (int i = 0; i < p.n_groups; ++i) {
+      const Segment& sg = ps.segs[i];
+      const Group& gr = c->groups[sg.group];
+      p.g[i].col_off = sg.row0;
+      p.g[i].C = sg.n_cols;
+      p.g[i].Kd = sg.kd_in;
+      p.g[i].n = gr.n;
+      p.g[i].counts = c->d_counts + (int64_t)sg.group * c->reserved_variants * 4;
+      p.g[i].dots = c->d_dots + c->dots_offset[sg.group] + sg.c_first;
+      p.g[i].dots_stride = gr.C;
+      p.g[i].colscale = s->d_colscale + s->scale_off[sg.group] + sg.c_first;
+      p.g[i].mask_hi = s->d_mask_hi + (int64_t)sg.group * (gr.ns_pad / 16);
+    }
+    void* kfn = nullptr;
+#define LRR_PICK(NG_) (cs == 2 ? (void*)tc4_sweep_kernel<NG_, 2> : (void*)tc4_sweep_kernel<NG_, 1>)
+    kfn = p.n_groups == 1 ? LRR_PICK(1) : p.n_groups == 2 ? LRR_PICK(2) : LRR_PICK(0);
+#undef LRR_PICK
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = (size_t)sh.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = c->sm_count / cs;
+    if (cs > 1) {
+      cfg.gridDim = dim3((unsigned)(c->sm_count / cs * cs));
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, kfn, &cfg) == cudaSuccess && nc > 0) max_clusters = nc;
+      else cudaGetLastError();
+    }
+    int n_cta = max_clusters * cs;
+    const int need = (p.n_tiles + cs - 1) / cs * cs;
+    if (n_cta > need) n_cta = need;
+    cfg.gridDim = dim3((unsigned)n_cta);
+    void* args[3] = {(void*)&geno_map, (void*)&sh.b_map, (void*)&p};
+    LRR_CUDA(c, cudaLaunchKernelExC(&cfg, kfn, args));
+    c->launches++;
+    LRR_CUDA(c, cudaGetLastError());
+  }
+  return LRR_OK;
+}
+
+}  // namespace lrr

@@ -41,7 +41,8 @@ extern "C" {
 /* kernels selectable in lrr_run */
 #define LRR_KERNEL_AUTO 0
 #define LRR_KERNEL_FP64 1  /* CUDA-core float64 reference-order kernel */
-#define LRR_KERNEL_TC 2    /* tcgen05 int8-sliced exact-integer kernel */
+#define LRR_KERNEL_TC 2    /* tcgen05 int8-sliced exact-integer kernel (INT32 accumulators) */
+#define LRR_KERNEL_TC4 3   /* tcgen05 4-bit (E2M1 digits) exact-integer kernel (f32 accumulators within 2^24) */
 
 typedef struct lrr_ctx lrr_ctx;
 

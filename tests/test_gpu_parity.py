@@ -19,7 +19,8 @@ from oracle import linreg_oracle as O
 from tests.bn_mirror import bn_fill_numpy
 from tests.helpers import GOLDEN, assert_fields_close, load_regression_linear
 
-KERNELS = ["fp64", "tc"]
+KERNELS = ["fp64", "tc", "tc4"]
+TC_KERNELS = ["tc", "tc4"]   # the exact-integer tensor-core sweeps: int8 digits / INT32 sums, E2M1 digits / f32 sums
 
 
 def _hb():
@@ -362,15 +363,19 @@ def test_full_sample_size_parity_vs_c_oracle(N, missing_rate):
         res[kernel] = ht
         # the causal variant is by far the strongest signal and its log10 p is finite
         assert int(np.nanargmin(ht.p_value)) == 0 and np.isfinite(ht.log10_p[0]) and ht.log10_p[0] < -6
-    # the two kernels agree far below the tolerance (exact integer path vs float64 FMA path)
-    a, b = res["tc"], res["fp64"]
-    assert np.array_equal(a.n, b.n) and np.array_equal(a.n_missing, b.n_missing)
-    clean = a.n_missing == 0
-    assert np.array_equal(a.sum_x[clean], b.sum_x[clean])
-    assert np.nanmax(np.abs(a.t_stat - b.t_stat)) < 1e-8
+    # the kernels agree far below the tolerance (exact integer paths vs float64 FMA path)
+    for name in TC_KERNELS:
+        a, b = res[name], res["fp64"]
+        assert np.array_equal(a.n, b.n) and np.array_equal(a.n_missing, b.n_missing)
+        clean = a.n_missing == 0
+        assert np.array_equal(a.sum_x[clean], b.sum_x[clean])
+        assert np.nanmax(np.abs(a.t_stat - b.t_stat)) < 1e-8
+    # integer outputs of the two tensor-core sweeps are identical bit for bit, missing calls or not
+    assert np.array_equal(res["tc"].sum_x, res["tc4"].sum_x)
 
 
-def test_tc_kernel_is_deterministic_and_order_independent():
+@pytest.mark.parametrize("tck", TC_KERNELS)
+def test_tc_kernel_is_deterministic_and_order_independent(tck):
     """Exact integer accumulation: the same rows give bit-identical results wherever they sit in the sweep."""
     hb = _hb()
     N, M = 100_000, 1500
@@ -379,11 +384,11 @@ def test_tc_kernel_is_deterministic_and_order_independent():
     cols = {"y": y, **{f"c{i}": cov[:, i] for i in range(1, 4)}}
     mt = hb.MatrixTable(gt, cols=cols)
     covs = [1.0] + [mt[f"c{i}"] for i in range(1, 4)]
-    full = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=covs, _kernel="tc")
-    again = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=covs, _kernel="tc")
+    full = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=covs, _kernel=tck)
+    again = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=covs, _kernel=tck)
     sub = hb.MatrixTable(gt.rows(512, 1400), cols=cols)   # different tile alignment / CTA assignment
     part = hb.linear_regression_rows(y=sub.y, x=sub.GT.n_alt_alleles(),
-                                     covariates=[1.0] + [sub[f"c{i}"] for i in range(1, 4)], _kernel="tc")
+                                     covariates=[1.0] + [sub[f"c{i}"] for i in range(1, 4)], _kernel=tck)
     for f in ("sum_x", "y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
         assert np.array_equal(full[f], again[f], equal_nan=True), f
         assert np.array_equal(full[f][512:1400], part[f], equal_nan=True), f
@@ -415,8 +420,10 @@ def test_mixed_one_plane_two_plane_tiles_many_tiles_per_cta():
     # unknown flags (None) must give the same answer: every tile is then treated as possibly missing
     gt2 = hb.PackedGenotypes(gt.data, M, N, None)
     mt2 = hb.MatrixTable(gt2, cols={"y": y, "c1": cov[:, 1], "c2": cov[:, 2]})
-    h2 = hb.linear_regression_rows(y=mt2.y, x=mt2.GT.n_alt_alleles(), covariates=[1.0, mt2.c1, mt2.c2], _kernel="tc")
-    assert np.array_equal(h2.beta, ht.beta, equal_nan=True) and np.array_equal(h2.p_value, ht.p_value, equal_nan=True)
+    for tck in TC_KERNELS:
+        h1 = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=[1.0, mt.c1, mt.c2], _kernel=tck)
+        h2 = hb.linear_regression_rows(y=mt2.y, x=mt2.GT.n_alt_alleles(), covariates=[1.0, mt2.c1, mt2.c2], _kernel=tck)
+        assert np.array_equal(h2.beta, h1.beta, equal_nan=True) and np.array_equal(h2.p_value, h1.p_value, equal_nan=True)
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
