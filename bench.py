@@ -244,15 +244,20 @@ def run_ours(a):
     abytes = algorithmic_bytes(M, N, G, K, P, n_kept)
     sweep = float(np.mean(sweep_ms))
     achieved = abytes / (sweep / 1e3) / 1e9
+    # DRAM bytes of one sweep launch from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum), captured on
+    # this exact workload: profiles/r01_tc4_full_c2_ncu_full.txt (103.105 GB + 0.201 GB).  Only valid for the headline.
+    headline = (N, M, P, G, a.missing_rate) == (N_SAMPLES, N_VARIANTS, N_PHENO, 1, 0.0)
+    traffic = 103306471048 if (headline and kernel_used == "tc4") else None
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "kernel": f"{kernel_used} sweep",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": f"{kernel_used} sweep",
                 "kernel_ms": round(sweep, 3), "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src,
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4)}
 
     result = {
         "metric": METRIC, "value": value, "unit": "genotypes/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 epilogue; sweep " + ("int8 x int8 -> int32 exact (tcgen05)" if kernel_used == "tc" else "f64 FMA"),
+        "dtype": "f64 epilogue; sweep " + {"tc": "u8 x s8 digits -> s32 exact (tcgen05 kind::i8)",
+                                           "tc4": "e2m1 x e2m1 digits -> f32 exact within 2^24 (tcgen05 kind::mxf4)"}.get(kernel_used, "f64 FMA"),
         "data": "synthetic (seeded Balding-Nichols style, generated in HBM)",
         "config": {"workload": WORKLOAD if (N, M, P, G, a.missing_rate) == (N_SAMPLES, N_VARIANTS, N_PHENO, 1, 0.0)
                    else f"NON-HEADLINE {N} samples x {M} variants, P={P}, groups={G}, missing={a.missing_rate}",
