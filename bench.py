@@ -121,6 +121,7 @@ def measured_peak():
 
 # =================================================================================================
 def run_ours(a):
+    os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     import torch
     import torch.distributed as dist
 
