@@ -12,9 +12,9 @@ def __getattr__(name):  # lazy: these import torch-side helpers
     if name in ("PackedGenotypes", "HostBedGenotypes", "packed_stride"):
         from . import genotypes
         return getattr(genotypes, name)
-    if name == "import_plink":
-        from .impex import import_plink
-        return import_plink
+    if name in ("import_plink", "export_plink", "import_fam"):
+        from . import impex
+        return getattr(impex, name)
     if name in ("balding_nichols_model", "bn_parameters", "bn_fill"):
         from . import bn
         return getattr(bn, name)
@@ -22,4 +22,4 @@ def __getattr__(name):  # lazy: these import torch-side helpers
 
 
 __all__ = ["linear_regression_rows", "MatrixTable", "Table", "FatalError", "ExpressionException", "PackedGenotypes",
-           "HostBedGenotypes", "import_plink", "balding_nichols_model"]
+           "HostBedGenotypes", "import_plink", "export_plink", "import_fam", "balding_nichols_model"]
