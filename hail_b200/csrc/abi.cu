@@ -251,9 +251,10 @@ int lrr_num_groups(const lrr_ctx* ctx) {
   return ctx ? (int)reinterpret_cast<const Ctx*>(ctx)->groups.size() : 0;
 }
 
-int lrr_add_group(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, int32_t P, int32_t has_intercept,
-                  const int32_t* complete_idx, const double* q_cols, const double* y_res, const double* qty,
-                  const double* yyp) {
+// shared body of lrr_add_group / lrr_add_group_weighted (`sqrt_w` != NULL: weighted group, has_intercept must be 0)
+static int add_group_impl(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, int32_t P, int32_t has_intercept,
+                          const int32_t* complete_idx, const double* q_cols, const double* y_res, const double* qty,
+                          const double* yyp, const double* sqrt_w) {
   if (!ctx) return LRR_EINVAL;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   DeviceGuard guard(c->device);
@@ -280,7 +281,8 @@ int lrr_add_group(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, i
   g.P = P;
   g.has_intercept = has_intercept;
   g.Kd = K - has_intercept;
-  g.C = g.Kd + P;
+  g.weighted = sqrt_w ? 1 : 0;
+  g.C = g.Kd + P + (sqrt_w ? 2 : 0);
   g.d = d;
   g.lbeta = log_beta_half(0.5 * (double)d);
   g.ns_pad = lrr_packed_stride(n_samples_total) * 4;
@@ -303,6 +305,13 @@ int lrr_add_group(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, i
   TRY(cudaMalloc(&d_cols, sizeof(double) * (size_t)g.C * n));
   if (g.Kd > 0) TRY(cudaMemcpy(d_cols, q_cols, sizeof(double) * (size_t)g.Kd * n, cudaMemcpyDefault));
   TRY(cudaMemcpy(d_cols + (size_t)g.Kd * n, y_res, sizeof(double) * (size_t)P * n, cudaMemcpyDefault));
+  if (sqrt_w) {   // column C-2 = sqrt(w), column C-1 = w
+    std::vector<double> sw(n), w(n);
+    TRY(cudaMemcpy(sw.data(), sqrt_w, sizeof(double) * (size_t)n, cudaMemcpyDefault));
+    for (int i = 0; i < n; ++i) w[i] = sw[i] * sw[i];
+    TRY(cudaMemcpy(d_cols + (size_t)(g.Kd + P) * n, sw.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    TRY(cudaMemcpy(d_cols + (size_t)(g.Kd + P + 1) * n, w.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  }
   TRY(cudaMalloc(&g.d_basis, sizeof(double) * (size_t)g.C * g.ns_pad));
   TRY(cudaMemset(g.d_basis, 0, sizeof(double) * (size_t)g.C * g.ns_pad));
   TRY(cudaMalloc(&g.d_mask, sizeof(uint32_t) * (size_t)(g.ns_pad / 16)));
@@ -328,6 +337,19 @@ int lrr_add_group(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, i
   c->n_samples_total = n_samples_total;
   c->dots_offset.clear();  // workspace layout depends on the group list
   return LRR_OK;
+}
+
+int lrr_add_group(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, int32_t P, int32_t has_intercept,
+                  const int32_t* complete_idx, const double* q_cols, const double* y_res, const double* qty,
+                  const double* yyp) {
+  return add_group_impl(ctx, n_samples_total, n, K, P, has_intercept, complete_idx, q_cols, y_res, qty, yyp, nullptr);
+}
+
+int lrr_add_group_weighted(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, int32_t P,
+                           const int32_t* complete_idx, const double* q_cols, const double* y_res, const double* qty,
+                           const double* yyp, const double* sqrt_w) {
+  if (ctx && !sqrt_w) return fail(reinterpret_cast<Ctx*>(ctx), LRR_EINVAL, "lrr_add_group_weighted: sqrt_w is NULL");
+  return add_group_impl(ctx, n_samples_total, n, K, P, 0, complete_idx, q_cols, y_res, qty, yyp, sqrt_w);
 }
 
 int lrr_reserve(lrr_ctx* ctx, int64_t max_variants) {

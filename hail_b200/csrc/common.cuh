@@ -21,7 +21,9 @@ struct Group {
   int P = 0;              // phenotypes
   int has_intercept = 0;  // constant column handled exactly from integer counts
   int Kd = 0;             // dot-product covariate columns = K - has_intercept
-  int C = 0;              // dot-product columns = Kd + P
+  int C = 0;              // dot-product columns = Kd + P (weighted groups: + 2, see `weighted`)
+  int weighted = 0;       // WLS group (statgen.py:557-581): columns are sqrt(w)-scaled, column C-2 = sqrt(w) (its dot is
+                          // sum_x of the scaled x), column C-1 = w accumulated against x^2 (the scaled x.x)
   int d = 0;              // degrees of freedom n - K - 1 (LR:50)
   double lbeta = 0.0;     // log B(d/2, 1/2) for the Student-t epilogue
   int64_t ns_pad = 0;     // padded sample count (= 4 * packed stride)

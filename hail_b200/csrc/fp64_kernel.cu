@@ -27,6 +27,7 @@ struct SweepArgs {
   int C;
   int32_t* counts;       // [M][4]
   double* dots;          // [M][C]
+  int sq_col;            // column accumulated against x^2 instead of x (weighted groups: sum_j w_j x_j^2), or -1
 };
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fp64_sweep_kernel(SweepArgs a) 
           const uint32_t code = (w >> sh) & 3u;
           const double x = (code == 3u) ? mean[v] : (double)code;
 #pragma unroll
-          for (int c = 0; c < CB; ++c) acc[v][c] = fma(q[c], x, acc[v][c]);
+          for (int c = 0; c < CB; ++c) acc[v][c] = fma(q[c], (c0 + c == a.sq_col) ? x * x : x, acc[v][c]);
         }
       }
     }
@@ -155,6 +156,7 @@ int launch_fp64_sweep(Ctx* c, const uint8_t* d_packed, int64_t M, int64_t stride
     a.mask = G.d_mask;
     a.n = G.n;
     a.C = G.C;
+    a.sq_col = G.weighted ? G.C - 1 : -1;
     a.counts = c->d_counts + (int64_t)g * c->reserved_variants * 4;
     a.dots = c->d_dots + c->dots_offset[g];
     const int64_t per_cta = (int64_t)WARPS * VW;

@@ -77,7 +77,7 @@ struct EpiArgs {
   const double* qty;      // [K][P]
   const double* yyp;      // [P]
   int64_t M;
-  int n, K, Kd, P, C, has_intercept, d;
+  int n, K, Kd, P, C, has_intercept, d, weighted;
   double lbeta;
   lrr_group_out out;
 };
@@ -95,9 +95,10 @@ __global__ void stats_epilogue_kernel(EpiArgs a) {
     const double S = (double)(n1 + 2 * n2);
     const double xx_int = (double)(n1 + 4 * n2);
     const double mean = S / nv;                        // RU:52
-    const double sum_x = S + (double)nm * mean;        // LR:136 (column sum of the imputed x)
-    const double xx_imp = xx_int + (double)nm * mean * mean;
     const double* dv = a.dots + v * a.C;
+    // weighted groups (statgen.py:636-660): the column sum and x.x of the sqrt(w)-scaled imputed x are dot products
+    const double sum_x = a.weighted ? dv[a.Kd + a.P] : S + (double)nm * mean;        // LR:136
+    const double xx_imp = a.weighted ? dv[a.Kd + a.P + 1] : xx_int + (double)nm * mean * mean;
 
     double qq = 0.0;
     for (int c = 0; c < a.Kd; ++c) qq += dv[c] * dv[c];
@@ -174,6 +175,7 @@ int launch_stats_epilogue(Ctx* c, int g, int64_t M, const lrr_group_out& out, cu
   a.P = G.P;
   a.C = G.C;
   a.has_intercept = G.has_intercept;
+  a.weighted = G.weighted;
   a.d = G.d;
   a.lbeta = G.lbeta;
   a.out = out;

@@ -857,6 +857,11 @@ static int prepare(Ctx* c) {
     s->why = "no groups";
     return LRR_OK;
   }
+  for (const Group& gr : c->groups)
+    if (gr.weighted) {
+      s->why = "weighted groups (x.x is not linear in the call codes) run on the float64 kernel";
+      return LRR_OK;
+    }
   int nscale = 0;
   s->scale_off.assign(G, 0);
   for (size_t g = 0; g < G; ++g) {

@@ -100,7 +100,7 @@ class GroupBasis:
     """What the reference broadcasts per group (ChainedLinregInput, LR:409-417), in the residualised form the
     device consumes (include/lrr_b200.h lrr_add_group)."""
 
-    def __init__(self, ys, cov, col_index, group_index=None):
+    def __init__(self, ys, cov, col_index, group_index=None, weights=None):
         ys = np.asarray(ys, dtype=np.float64)   # [n_cols, P]
         cov = np.asarray(cov, dtype=np.float64).reshape(ys.shape[0], -1)  # [n_cols, K]
         n_cols, P = ys.shape
@@ -108,6 +108,9 @@ class GroupBasis:
         if P == 0:
             raise FatalError("No phenotypes present.")  # RU:97-98
         keep = ~np.isnan(ys).any(axis=1) & ~np.isnan(cov).any(axis=1)  # RU:100-110
+        if weights is not None:   # a sample also needs its weight (statgen.py:539-543)
+            weights = np.asarray(weights, dtype=np.float64)
+            keep &= ~np.isnan(weights)
         n = int(keep.sum())
         if n == 0:
             raise FatalError("No complete samples: each sample is missing its phenotype or some covariate")  # RU:113-114
@@ -120,8 +123,35 @@ class GroupBasis:
         log.info("linear_regression_rows%s: running on %d samples for %d response %s y,\n"
                  "    with input variable x, and %d additional %s...", tag, n, P, _plural(P, "variable"), K,
                  _plural(K, "covariate"))  # LR:60-63 / 241-244
+        self.weighted = weights is not None
         with _blas_limits(limits=1):
-            self._build(ys[keep], cov[keep], np.asarray(col_index)[keep], n, K, P, d)
+            if self.weighted:
+                self._build_weighted(ys[keep], cov[keep], np.sqrt(weights[keep]), np.asarray(col_index)[keep], n, K, P, d)
+            else:
+                self._build(ys[keep], cov[keep], np.asarray(col_index)[keep], n, K, P, d)
+
+    def _build_weighted(self, y, c, sw, kept_index, n, K, P, d):
+        """statgen.py:557-581: y and the covariates are scaled by sqrt(w) before the QR; x is scaled on the device
+        (the shipped columns carry a second factor sqrt(w), see lrr_add_group_weighted)."""
+        self.n, self.K, self.P, self.d = n, K, P, d
+        self.complete_idx = np.ascontiguousarray(kept_index, dtype=np.int32)
+        y = y * sw[:, None]
+        c = c * sw[:, None]
+        if K > 0:
+            q, ok = _gram_orthonormalise(c)
+            if not ok or q.shape[1] != K:
+                q, _ = np.linalg.qr(c, mode="reduced")
+        else:
+            q = np.zeros((n, 0))
+        qty = q.T @ y
+        self.has_intercept = False
+        self.qty = np.ascontiguousarray(qty)
+        self.yyp = np.ascontiguousarray(np.einsum("ij,ij->j", y, y) - np.einsum("ij,ij->j", qty, qty))
+        y_res = y - q @ qty
+        y_res -= q @ (q.T @ y_res)
+        self.q_cols = np.ascontiguousarray((q * sw[:, None]).T)        # [K, n]
+        self.y_res = np.ascontiguousarray((y_res * sw[:, None]).T)     # [P, n]
+        self.sqrt_w = np.ascontiguousarray(sw)
 
     def _build(self, y, c, kept_index, n, K, P, d):
         self.n, self.K, self.P, self.d = n, K, P, d
@@ -230,13 +260,21 @@ def _run_device(genotypes, bases, kernel="auto", want_log10_p=False, chunk_varia
     return outs
 
 
+def _add_group(ctx, N, b):
+    q = b.q_cols.ctypes.data if b.q_cols.size else None
+    qty = b.qty.ctypes.data if b.qty.size else None
+    if getattr(b, "weighted", False):
+        ctx.check(ctx.lib.lrr_add_group_weighted(ctx.handle, N, b.n, b.K, b.P, b.complete_idx.ctypes.data, q,
+                                                 b.y_res.ctypes.data, qty, b.yyp.ctypes.data, b.sqrt_w.ctypes.data))
+    else:
+        ctx.check(ctx.lib.lrr_add_group(ctx.handle, N, b.n, b.K, b.P, int(b.has_intercept), b.complete_idx.ctypes.data,
+                                        q, b.y_res.ctypes.data, qty, b.yyp.ctypes.data))
+
+
 def _push_groups(ctx, N, bases):
     ctx.check(ctx.lib.lrr_clear_groups(ctx.handle))
     for b in bases:
-        ctx.check(ctx.lib.lrr_add_group(
-            ctx.handle, N, b.n, b.K, b.P, int(b.has_intercept), b.complete_idx.ctypes.data,
-            b.q_cols.ctypes.data if b.q_cols.size else None, b.y_res.ctypes.data,
-            b.qty.ctypes.data if b.qty.size else None, b.yyp.ctypes.data))
+        _add_group(ctx, N, b)
 
 
 class _HostStream:
@@ -260,10 +298,7 @@ class _HostStream:
         ctx, M, N = self.ctx, self.g.n_variants, self.g.n_samples
         with torch.cuda.device(self.g.device):
             for b in bases:
-                ctx.check(ctx.lib.lrr_add_group(
-                    ctx.handle, N, b.n, b.K, b.P, int(b.has_intercept), b.complete_idx.ctypes.data,
-                    b.q_cols.ctypes.data if b.q_cols.size else None, b.y_res.ctypes.data,
-                    b.qty.ctypes.data if b.qty.size else None, b.yyp.ctypes.data))
+                _add_group(ctx, N, b)
             fields = [("n", np.int32, 0), ("n_missing", np.int32, 0), ("sum_x", np.float64, 0)]
             fields += [(f, np.float64, 1) for f in STAT_FIELDS + (["log10_p"] if want_log10_p else [])]
             total, layout = 0, []
@@ -304,11 +339,10 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
     Drop-in for `hl.linear_regression_rows` (statgen.py:235): same arguments, same validation, same output
     fields in the same order -- row key, pass_through, then `n, sum_x, y_transpose_x, beta, standard_error,
     t_stat, p_value` (scalars when `y` is one expression, arrays of length P for a list, arrays over groups for
-    a list of lists).  `block_size` is accepted and numerically inert on the GPU.
+    a list of lists).  `block_size` is accepted and numerically inert on the GPU.  `weights` (one expression, or one
+    per group of a chained `y`): weighted least squares as the reference's `_linear_regression_rows_nd` does it
+    (statgen.py:557-581, 636-660): samples without a weight are dropped, x is mean-imputed and then scaled by sqrt(w).
     """
-    if weights is not None:
-        raise NotImplementedError("linear_regression_rows: `weights` (WLS, statgen.py:557-581) is out of scope "
-                                  "for the B200 path")
     if not isinstance(block_size, int):
         raise TypeError("linear_regression_rows: 'block_size' must be int")
     if not isinstance(x, EntryExpression):
@@ -323,9 +357,22 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
     if is_chained and any(len(lst) == 0 for lst in y):
         raise ValueError("'linear_regression_rows': found empty inner list for 'y'")  # SG:354-355
 
+    if weights is not None:   # statgen.py:437-467
+        if y_is_list and is_chained and not isinstance(weights, list):
+            raise ValueError("When y is a list of lists, weights should be a list.")
+        elif y_is_list and not is_chained and isinstance(weights, list):
+            raise ValueError("When y is a single list, weights should be a single expression.")
+        elif not y_is_list and isinstance(weights, list):
+            raise ValueError("When y is a single expression, weights should be a single expression.")
+        weights = weights if isinstance(weights, list) else [weights]
+        if len(weights) != (len(y) if is_chained else 1):
+            raise ValueError("Must specify same number of weights as groups of phenotypes")
+
     groups = [list(g) for g in y] if is_chained else [list(y) if y_is_list else [y]]
     y_vals = [[_column_values(e, mt, "linear_regression_rows/y") for e in g] for g in groups]
     cov_vals = [_column_values(e, mt, "linear_regression_rows/covariates") for e in covariates]
+    w_vals = [None] * len(groups) if weights is None else \
+        [_column_values(e, mt, "linear_regression_rows/weights") for e in weights]
     _warn_if_no_intercept("linear_regression_rows", covariates)
     row_fields = _get_regression_row_fields(mt, pass_through, "linear_regression_rows")
 
@@ -337,13 +384,13 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
         # host-resident .bed rows: stream them through the device; the copies start before the prologue
         stream = _HostStream(mt.genotypes, _stream_block, _stream_depth)
         try:
-            bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None)
+            bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None, w_vals[i])
                      for i, g in enumerate(y_vals)]
             host = stream.run(bases, kernel=_kernel, want_log10_p=_log10_p)
         finally:
             stream.close()
     else:
-        bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None)
+        bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None, w_vals[i])
                  for i, g in enumerate(y_vals)]
         outs = _run_device(mt.genotypes, bases, kernel=_kernel, want_log10_p=_log10_p)
         torch.cuda.synchronize(mt.genotypes.device)

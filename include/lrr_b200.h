@@ -117,6 +117,16 @@ int lrr_clear_groups(lrr_ctx* ctx);
 int lrr_add_group(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, int32_t P, int32_t has_intercept,
                   const int32_t* complete_idx, const double* q_cols, const double* y_res, const double* qty,
                   const double* yyp);
+/* Weighted least squares group (`weights=` of hl.linear_regression_rows; the reference routes it through
+ * _linear_regression_rows_nd, methods/statgen.py:557-581, 636-660): x is mean-imputed first, then every quantity is
+ * scaled by sqrt(w).  The host passes the sqrt(w)-SCALED arrays: Q = orthonormal basis of sqrt(w) * covariates,
+ * q_cols [K, n] = Q columns TIMES sqrt(w) again (so that a dot product with the unscaled imputed x is Q^T (sqrt(w) x)),
+ * y_res [P, n] = (sqrt(w) y - Q Q^T sqrt(w) y) TIMES sqrt(w), qty / yyp from the scaled y, and sqrt_w [n].
+ * `sum_x` is then the column sum of the scaled x (statgen.py:646).  No intercept shortcut applies; weighted groups run
+ * on the float64 kernel (x.x = sum w x^2 is not linear in the call codes). */
+int lrr_add_group_weighted(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, int32_t P,
+                           const int32_t* complete_idx, const double* q_cols, const double* y_res, const double* qty,
+                           const double* yyp, const double* sqrt_w);
 int lrr_num_groups(const lrr_ctx* ctx);
 
 /* ---- the hot call ------------------------------------------------------------------------------ */

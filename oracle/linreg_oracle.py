@@ -265,6 +265,37 @@ def linreg_group(x, ys, cov, block_size=16):
     return out
 
 
+def linreg_group_weighted(x, ys, cov, w, block_size=16):
+    """One group of `_linear_regression_rows_nd` with `weights` (statgen.py:530-545 kept samples: weight defined too;
+    :557-581 sqrt-weight scaling of y and the covariates; :636-660 X = mean_impute(x) * sqrt(w), then the same algebra
+    as LR:134-160 on the scaled quantities -- `sum_x` is the column sum of the SCALED X, statgen.py:646)."""
+    x = np.asarray(x, dtype=np.float64)
+    ys = np.asarray(ys, dtype=np.float64)
+    w = np.asarray(w, dtype=np.float64)
+    cov = np.asarray(cov, dtype=np.float64).reshape(ys.shape[0], -1)
+    keep = ~np.isnan(ys).any(axis=1) & ~np.isnan(cov).any(axis=1) & ~np.isnan(w)
+    idx = np.nonzero(keep)[0]
+    if idx.size == 0:
+        raise OracleFatal("No complete samples: each sample is missing its phenotype or some covariate")
+    sw = np.sqrt(w[idx])
+    y = ys[idx] * sw[:, None]
+    c = cov[idx] * sw[:, None]
+    n, k, d, Qt, Qty, yyp = prologue(y, c)
+    M, P = x.shape[0], y.shape[1]
+    out = {"n": np.full(M, n, dtype=np.int32), "sum_x": np.empty(M)}
+    for f in ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+        out[f] = np.empty((M, P))
+    for r0 in range(0, M, block_size):
+        r1 = min(M, r0 + block_size)
+        X = mean_imputed_block(x[r0:r1], idx) * sw[:, None]          # statgen.py:637-644
+        AC, ytx, b, se, t, p = block_algebra(X, y, Qt, Qty, yyp, d)
+        out["sum_x"][r0:r1] = AC
+        for f, v in (("y_transpose_x", ytx), ("beta", b), ("standard_error", se), ("t_stat", t), ("p_value", p)):
+            out[f][r0:r1] = v.T
+    out["_d"] = d
+    return out
+
+
 def linreg_chained(x, y_groups, cov, block_size=16):
     """LinearRegressionRowsChained.execute (LR:226-407): independent groups, outer array of length G.
 

@@ -77,8 +77,15 @@ def test_argument_validation_matches_reference():  # statgen.py:351-355, 195-224
         hb.linear_regression_rows(mt.pheno, x, [1.0], pass_through=[mt.filters.length()])
     with pytest.raises(hb.ExpressionException):
         hb.linear_regression_rows(mt.pheno, x, [1.0], pass_through=[mt.pheno])
-    with pytest.raises(NotImplementedError, match="weights"):
-        hb.linear_regression_rows(mt.pheno, x, [1.0], weights=mt.c1)
+    # weights: statgen.py:437-467
+    with pytest.raises(ValueError, match="When y is a list of lists, weights should be a list."):
+        hb.linear_regression_rows([[mt.pheno]], x, [1.0], weights=mt.c1)
+    with pytest.raises(ValueError, match="When y is a single list, weights should be a single expression."):
+        hb.linear_regression_rows([mt.pheno], x, [1.0], weights=[mt.c1])
+    with pytest.raises(ValueError, match="When y is a single expression, weights should be a single expression."):
+        hb.linear_regression_rows(mt.pheno, x, [1.0], weights=[mt.c1])
+    with pytest.raises(ValueError, match="Must specify same number of weights as groups of phenotypes"):
+        hb.linear_regression_rows([[mt.pheno], [mt.pheno]], x, [1.0], weights=[mt.c1])
     with pytest.raises(hb.ExpressionException):
         hb.linear_regression_rows(mt.pheno, mt.pheno, [1.0])
     # key fields pass silently; nested fields keep their leaf name (TS:118-126)

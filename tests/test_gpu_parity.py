@@ -547,3 +547,50 @@ def test_stream_empty_errors_and_file(tmp_path):
     rc = ctx.lib.lrr_stream_begin(ctx.handle, ctypes.byref(h2), host.rows.data_ptr(), M, host.bed_stride, N, 0, 0)
     assert rc != 0 and b"still open" in ctx.lib.lrr_last_error(ctx.handle)
     ctx.lib.lrr_stream_end(ctx.handle, h1)
+
+
+# ---------------------------------------------------------------------------------------------
+# weights (WLS): the reference routes it through _linear_regression_rows_nd (statgen.py:344-345, 557-581, 636-660)
+def test_weighted_linear_regression_vs_oracle():
+    hb = _hb()
+    z = np.load(os.path.join(GOLDEN, "fastlmm.npz"))
+    N, M = int(z["n_samples"]), int(z["n_variants"])
+    rows = obed.bed_body(z["bed"], N, M)
+    x = obed.decode_rows(rows, N)
+    rng = np.random.default_rng(31)
+    ys = np.column_stack([z["pheno"], rng.normal(size=N)])
+    ys[rng.random(ys.shape) < 0.03] = np.nan
+    cov = np.column_stack([np.ones(N), z["cov"][:, 0], rng.normal(size=N)])
+    w1 = rng.uniform(0.2, 4.0, size=N)
+    w1[rng.random(N) < 0.04] = np.nan                      # missing weights drop the sample (test_statgen.py:610-660)
+    w2 = np.arange(N, dtype=np.float64) + 5.0             # test_statgen.py:596 uses col_idx + 5
+    mt = hb.MatrixTable(hb.PackedGenotypes.from_bed_rows(rows, N),
+                        cols={"y0": ys[:, 0], "y1": ys[:, 1], "c1": cov[:, 1], "c2": cov[:, 2], "w1": w1, "w2": w2})
+    covs = [1.0, mt.c1, mt.c2]
+    # one weight expression, list of phenotypes
+    ht = hb.linear_regression_rows(y=[mt.y0, mt.y1], x=mt.GT.n_alt_alleles(), covariates=covs, weights=mt.w1)
+    want = O.linreg_group_weighted(x, ys, cov, w1)
+    nondeg = np.isfinite(want["standard_error"]).all(axis=1)
+    assert nondeg.sum() > 0.9 * M
+    assert_fields_close({k: v[nondeg] for k, v in _as_oracle_dict(ht).items()},
+                        {k: v[nondeg] for k, v in want.items() if k != "_d"}, t_floor=1e-9, ctx="weighted")
+    # chained: one weight per group (test_statgen.py:595-607)
+    hc = hb.linear_regression_rows(y=[[mt.y0], [mt.y1]], x=mt.GT.n_alt_alleles(), covariates=covs, weights=[mt.w1, mt.w2])
+    for g, (yy, ww) in enumerate(((ys[:, :1], w1), (ys[:, 1:], w2))):
+        wg = O.linreg_group_weighted(x, yy, cov, ww)
+        got = {"n": hc.n[:, g], "sum_x": hc.sum_x[:, g]}
+        for f in ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+            got[f] = hc[f][g]
+        nd = np.isfinite(wg["standard_error"]).all(axis=1)
+        assert_fields_close({k: v[nd] for k, v in got.items()}, {k: v[nd] for k, v in wg.items() if k != "_d"},
+                            t_floor=1e-9, ctx=f"weighted chained g={g}")
+    # unit weights reproduce the unweighted regression (statistics; sum_x is then the plain column sum)
+    mt1 = mt.annotate_cols(one=np.ones(N))
+    hu = hb.linear_regression_rows(y=mt1.y0, x=mt1.GT.n_alt_alleles(), covariates=[1.0, mt1.c1, mt1.c2], weights=mt1.one)
+    h0 = hb.linear_regression_rows(y=mt1.y0, x=mt1.GT.n_alt_alleles(), covariates=[1.0, mt1.c1, mt1.c2])
+    ok = np.isfinite(h0.standard_error)
+    assert np.allclose(hu.beta[ok], h0.beta[ok], rtol=1e-7) and np.allclose(hu.p_value[ok], h0.p_value[ok], rtol=1e-6)
+    # the tensor-core kernels refuse weighted groups instead of computing something else
+    from hail_b200 import _lib
+    with pytest.raises(_lib.LrrError, match="float64 kernel"):
+        hb.linear_regression_rows(y=mt.y0, x=mt.GT.n_alt_alleles(), covariates=covs, weights=mt.w1, _kernel="tc4")

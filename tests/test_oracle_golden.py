@@ -149,3 +149,28 @@ def test_sequential_and_vectorised_imputation_agree():
     for r in range(40):
         col = O.mean_imputed_column(x[r], idx)
         assert np.array_equal(col, X[:, r], equal_nan=True)
+
+
+def test_weighted_oracle_equals_preweighted_ols():
+    """test_statgen.py:553-593: regression with weights w == OLS on y, x, covariates all scaled by sqrt(w) (no missing
+    calls, as the reference test arranges with coalesce)."""
+    rng = np.random.default_rng(3)
+    N, M = 60, 25
+    x = rng.integers(0, 3, size=(M, N)).astype(np.float64)
+    y = rng.normal(size=(N, 2))
+    cov = np.column_stack([np.ones(N), rng.normal(size=(N, 2))])
+    w = rng.uniform(0.5, 3.0, size=N)
+    got = O.linreg_group_weighted(x, y, cov, w)
+    sw = np.sqrt(w)
+    want = O.linreg_group(x * sw[None, :], y * sw[:, None], cov * sw[:, None])
+    for f in ("sum_x", "y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+        assert np.allclose(got[f], want[f], rtol=1e-10, atol=0), f
+    # missing weights drop the sample (test_statgen.py:610-660)
+    w2 = w.copy()
+    w2[[3, 17]] = np.nan
+    keep = ~np.isnan(w2)
+    a = O.linreg_group_weighted(x, y, cov, w2)
+    b = O.linreg_group_weighted(x[:, keep], y[keep], cov[keep], w2[keep])
+    assert (a["n"] == N - 2).all()
+    for f in ("beta", "p_value"):
+        assert np.allclose(a[f], b[f], rtol=1e-12, atol=0), f
