@@ -31,6 +31,12 @@ class GroupOut(ctypes.Structure):
     ]
 
 
+class ScoreOut(ctypes.Structure):
+    """lrr_score_out"""
+
+    _fields_ = [("chi_sq_stat", ctypes.c_void_p), ("p_value", ctypes.c_void_p), ("n_missing", ctypes.c_void_p)]
+
+
 # name -> (restype, argtypes); must list every symbol include/lrr_b200.h declares (tests check this)
 SIGNATURES = {
     "lrr_version": (ctypes.c_char_p, []),
@@ -70,6 +76,11 @@ SIGNATURES = {
     "lrr_stream_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(GroupOut), ctypes.c_int32,
                                       ctypes.c_int32]),
     "lrr_stream_end": (None, [ctypes.c_void_p, ctypes.c_void_p]),
+    "lrr_set_score_model": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p]),
+    "lrr_run_score": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                     ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "lrr_student_t_two_sided": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double,
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 }

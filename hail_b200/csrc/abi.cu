@@ -2,6 +2,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace lrr {
@@ -76,6 +78,7 @@ int ensure_workspace(Ctx* c, int64_t M) {
 int run_rows(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
              int64_t n_samples_total, const lrr_group_out* outs, int32_t n_outs, int32_t kernel, cudaStream_t st) {
   if (c->groups.empty()) return fail(c, LRR_ESTATE, "lrr_run: no groups (call lrr_add_group)");
+  if (c->groups[0].score) return fail(c, LRR_ESTATE, "lrr_run: the context holds a logistic score model (use lrr_run_score)");
   if (n_outs != (int32_t)c->groups.size() || !outs) return fail(c, LRR_EINVAL, "lrr_run: need one lrr_group_out per group");
   if (n_variants < 0) return fail(c, LRR_EINVAL, "lrr_run: negative n_variants");
   if (n_samples_total != c->n_samples_total) return fail(c, LRR_EINVAL, "lrr_run: n_samples_total differs from the groups'");
@@ -254,7 +257,8 @@ int lrr_num_groups(const lrr_ctx* ctx) {
 // shared body of lrr_add_group / lrr_add_group_weighted (`sqrt_w` != NULL: weighted group, has_intercept must be 0)
 static int add_group_impl(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, int32_t P, int32_t has_intercept,
                           const int32_t* complete_idx, const double* q_cols, const double* y_res, const double* qty,
-                          const double* yyp, const double* sqrt_w) {
+                          const double* yyp, const double* sqrt_w, const double* w_col = nullptr, int qty_len = -1,
+                          int yyp_len = -1) {
   if (!ctx) return LRR_EINVAL;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   DeviceGuard guard(c->device);
@@ -309,6 +313,7 @@ static int add_group_impl(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int3
     std::vector<double> sw(n), w(n);
     TRY(cudaMemcpy(sw.data(), sqrt_w, sizeof(double) * (size_t)n, cudaMemcpyDefault));
     for (int i = 0; i < n; ++i) w[i] = sw[i] * sw[i];
+    if (w_col) TRY(cudaMemcpy(w.data(), w_col, sizeof(double) * (size_t)n, cudaMemcpyDefault));
     TRY(cudaMemcpy(d_cols + (size_t)(g.Kd + P) * n, sw.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
     TRY(cudaMemcpy(d_cols + (size_t)(g.Kd + P + 1) * n, w.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
   }
@@ -316,10 +321,12 @@ static int add_group_impl(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int3
   TRY(cudaMemset(g.d_basis, 0, sizeof(double) * (size_t)g.C * g.ns_pad));
   TRY(cudaMalloc(&g.d_mask, sizeof(uint32_t) * (size_t)(g.ns_pad / 16)));
   TRY(cudaMemset(g.d_mask, 0, sizeof(uint32_t) * (size_t)(g.ns_pad / 16)));
-  TRY(cudaMalloc(&g.d_qty, sizeof(double) * (size_t)(K > 0 ? K : 1) * P));
-  if (K > 0) TRY(cudaMemcpy(g.d_qty, qty, sizeof(double) * (size_t)K * P, cudaMemcpyDefault));
-  TRY(cudaMalloc(&g.d_yyp, sizeof(double) * (size_t)P));
-  TRY(cudaMemcpy(g.d_yyp, yyp, sizeof(double) * (size_t)P, cudaMemcpyDefault));
+  const size_t n_qty = qty_len >= 0 ? (size_t)qty_len : (size_t)K * P;
+  const size_t n_yyp = yyp_len >= 0 ? (size_t)yyp_len : (size_t)P;
+  TRY(cudaMalloc(&g.d_qty, sizeof(double) * (n_qty ? n_qty : 1)));
+  if (n_qty) TRY(cudaMemcpy(g.d_qty, qty, sizeof(double) * n_qty, cudaMemcpyDefault));
+  TRY(cudaMalloc(&g.d_yyp, sizeof(double) * n_yyp));
+  TRY(cudaMemcpy(g.d_yyp, yyp, sizeof(double) * n_yyp, cudaMemcpyDefault));
   {
     const int64_t total = (int64_t)g.C * n;
     int grid = (int)((total + 255) / 256);
@@ -350,6 +357,44 @@ int lrr_add_group_weighted(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int
                            const double* yyp, const double* sqrt_w) {
   if (ctx && !sqrt_w) return fail(reinterpret_cast<Ctx*>(ctx), LRR_EINVAL, "lrr_add_group_weighted: sqrt_w is NULL");
   return add_group_impl(ctx, n_samples_total, n, K, P, 0, complete_idx, q_cols, y_res, qty, yyp, sqrt_w);
+}
+
+int lrr_set_score_model(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, const int32_t* complete_idx,
+                        const double* wc, const double* resid, const double* w, const double* finv, const double* score0) {
+  if (!ctx) return LRR_EINVAL;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (K < 1) return fail(c, LRR_EINVAL, "logistic regression requires at least one covariate expression");
+  if (!wc || !resid || !w || !finv || !score0) return fail(c, LRR_EINVAL, "lrr_set_score_model: NULL input array");
+  if (int r = lrr_clear_groups(ctx)) return r;
+  // u = F00^-1 s0 and s0' u: the part of chi2 = s' F^-1 s that does not depend on the variant
+  std::vector<double> aux((size_t)K + 1, 0.0), sw((size_t)n);
+  for (int i = 0; i < K; ++i)
+    for (int j = 0; j < K; ++j) aux[i] += finv[(size_t)i * K + j] * score0[j];
+  for (int i = 0; i < K; ++i) aux[K] += score0[i] * aux[i];
+  for (int i = 0; i < n; ++i) sw[i] = sqrt(w[i]);
+  if (int r = add_group_impl(ctx, n_samples_total, n, K, 1, 0, complete_idx, wc, resid, finv, aux.data(), sw.data(), w,
+                             K * K, K + 1))
+    return r;
+  c->groups.back().score = 1;
+  return LRR_OK;
+}
+
+int lrr_run_score(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
+                  int64_t n_samples_total, const lrr_score_out* out, void* stream) {
+  CTX_PROLOGUE;
+  (void)d_row_flags;
+  if (c->groups.size() != 1 || !c->groups[0].score) return fail(c, LRR_ESTATE, "lrr_run_score: call lrr_set_score_model first");
+  if (!out) return fail(c, LRR_EINVAL, "lrr_run_score: out is NULL");
+  if (n_variants < 0) return fail(c, LRR_EINVAL, "lrr_run_score: negative n_variants");
+  if (n_samples_total != c->n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_score: n_samples_total differs from the model's");
+  if (int r = check_packed(c, n_samples_total, packed_stride)) return r;
+  if (packed_stride * 4 != c->groups[0].ns_pad) return fail(c, LRR_EINVAL, "lrr_run_score: packed_stride must equal lrr_packed_stride(n_samples_total)");
+  if (n_variants == 0) return LRR_OK;
+  if (!d_packed) return fail(c, LRR_EINVAL, "lrr_run_score: d_packed is NULL");
+  if (int r = ensure_workspace(c, n_variants)) return r;
+  if (int r = launch_fp64_sweep(c, d_packed, n_variants, packed_stride, st)) return r;
+  c->last_kernel = LRR_KERNEL_FP64;
+  return launch_score_epilogue(c, n_variants, *out, st);
 }
 
 int lrr_reserve(lrr_ctx* ctx, int64_t max_variants) {

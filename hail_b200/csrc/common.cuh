@@ -22,6 +22,8 @@ struct Group {
   int has_intercept = 0;  // constant column handled exactly from integer counts
   int Kd = 0;             // dot-product covariate columns = K - has_intercept
   int C = 0;              // dot-product columns = Kd + P (weighted groups: + 2, see `weighted`)
+  int score = 0;          // logistic score-test model (lrr_set_score_model): columns [w c_k (K) | y - mu | sqrt(w) | w^sq],
+                          // d_qty = F00^-1 [K, K], d_yyp = [u = F00^-1 s0 (K) | s0' u]
   int weighted = 0;       // WLS group (statgen.py:557-581): columns are sqrt(w)-scaled, column C-2 = sqrt(w) (its dot is
                           // sum_x of the scaled x), column C-1 = w accumulated against x^2 (the scaled x.x)
   int d = 0;              // degrees of freedom n - K - 1 (LR:50)
@@ -106,6 +108,7 @@ int launch_stats_epilogue(Ctx*, int g, int64_t M, const lrr_group_out& out, cuda
 int run_rows(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, int64_t n_samples_total,
              const lrr_group_out* outs, int32_t n_outs, int32_t kernel, cudaStream_t);
 int launch_student_t(Ctx*, const double*, int64_t, double, double*, double*, cudaStream_t);
+int launch_score_epilogue(Ctx*, int64_t M, const lrr_score_out& out, cudaStream_t);
 
 // position of sample `j` (0..15 within its word) in the packed word: bits [8i+2s, 8i+2s+1], j = 4s+i
 __host__ __device__ inline int sample_shift(int j) { return 8 * (j & 3) + 2 * (j >> 2); }

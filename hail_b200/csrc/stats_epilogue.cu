@@ -142,6 +142,46 @@ __global__ void stats_epilogue_kernel(EpiArgs a) {
   }
 }
 
+// Logistic score test per variant (LogisticRegressionModel.scala:211-264 restated through the Schur complement of the
+// null block): with f01 = C' W x, f11 = x' W x, s1 = x' (y - mu) from the sweep and F00^-1, u = F00^-1 s0, a0 = s0' u
+// from the host,  chi2 = a0 + (s1 - f01' u)^2 / (f11 - f01' F00^-1 f01),  p = pchisqtail(chi2, 1) = erfc(sqrt(chi2 / 2)).
+struct ScoreArgs {
+  const int32_t* counts;  // [M][4]
+  const double* dots;     // [M][K + 3]: f01 (K), s1, sum sqrt(w) x (unused), f11
+  const double* finv;     // [K][K]
+  const double* aux;      // [K + 1]: u, a0
+  int64_t M;
+  int K;
+  lrr_score_out out;
+};
+
+__global__ void score_epilogue_kernel(ScoreArgs a) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < a.M; v += (int64_t)gridDim.x * blockDim.x) {
+    const double* dv = a.dots + v * (a.K + 3);
+    const double s1 = dv[a.K], f11 = dv[a.K + 2];
+    double quad = 0.0, fu = 0.0;
+    for (int i = 0; i < a.K; ++i) {
+      double t = 0.0;
+      for (int j = 0; j < a.K; ++j) t += a.finv[i * a.K + j] * dv[j];
+      quad += dv[i] * t;
+      fu += dv[i] * a.aux[i];
+    }
+    const double denom = f11 - quad;
+    double chi2, p;
+    // x in the span of the covariates (e.g. a constant call): the full Fisher matrix is singular -> missing (:256-259)
+    if (!(denom > 1e-11 * f11)) {
+      chi2 = p = __longlong_as_double(0x7ff8000000000000ll);
+    } else {
+      const double num = s1 - fu;
+      chi2 = a.aux[a.K] + num * num / denom;
+      p = erfc(sqrt(0.5 * chi2));
+    }
+    if (a.out.chi_sq_stat) a.out.chi_sq_stat[v] = chi2;
+    if (a.out.p_value) a.out.p_value[v] = p;
+    if (a.out.n_missing) a.out.n_missing[v] = reinterpret_cast<const int4*>(a.counts)[v].z;
+  }
+}
+
 __global__ void student_t_kernel(const double* t, int64_t count, double df, double lbeta, double* p, double* l10) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     double l = 0.0;
@@ -183,6 +223,25 @@ int launch_stats_epilogue(Ctx* c, int g, int64_t M, const lrr_group_out& out, cu
   int64_t grid = (total + 127) / 128;
   if (grid > (int64_t)c->sm_count * 32) grid = (int64_t)c->sm_count * 32;
   stats_epilogue_kernel<<<(int)grid, 128, 0, st>>>(a);
+  c->launches++;
+  LRR_CUDA(c, cudaGetLastError());
+  return LRR_OK;
+}
+
+int launch_score_epilogue(Ctx* c, int64_t M, const lrr_score_out& out, cudaStream_t st) {
+  if (M == 0) return LRR_OK;
+  const Group& G = c->groups[0];
+  ScoreArgs a;
+  a.counts = c->d_counts;
+  a.dots = c->d_dots + c->dots_offset[0];
+  a.finv = G.d_qty;
+  a.aux = G.d_yyp;
+  a.M = M;
+  a.K = G.K;
+  a.out = out;
+  int64_t grid = (M + 127) / 128;
+  if (grid > (int64_t)c->sm_count * 32) grid = (int64_t)c->sm_count * 32;
+  score_epilogue_kernel<<<(int)grid, 128, 0, st>>>(a);
   c->launches++;
   LRR_CUDA(c, cudaGetLastError());
   return LRR_OK;

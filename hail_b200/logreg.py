@@ -1,0 +1,151 @@
+"""`logistic_regression_rows` (score test) -- host side of the B200 path.
+
+Mirrors, for test='score',
+  * Python API + validation   hail/python/hail/methods/statgen.py:731-1012 (defaults max_iterations=25, tolerance=1e-6;
+                              ValueError for no covariates / empty y; same pass_through rules as the linear path)
+  * driver prologue           hail/hail/src/is/hail/methods/LogisticRegression.scala:38-100: complete samples over ALL
+                              phenotypes and covariates, 0/1 and non-constant checks, d >= 1, one null model fit per
+                              phenotype (fatal when Newton does not converge), stats/LogisticRegressionModel.scala:279-370
+  * output schema             key, pass_through, `chi_sq_stat`, `p_value` (scalars for one y; for a list of y the
+                              reference nests them in `logistic_regression: array<struct>` -- here arrays [M, P])
+The per-row loop (LogisticRegression.scala:115-157 with LogisticScoreTest, LogisticRegressionModel.scala:211-264) runs in
+the CUDA library behind lrr_set_score_model / lrr_run_score.  'wald', 'lrt' and 'firth' need per-variant Newton
+iterations and are not implemented.
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from .matrixtable import EntryExpression, ExpressionException, Table
+from .statgen import FatalError, _column_values, _get_regression_row_fields, _plural, _warn_if_no_intercept
+
+log = logging.getLogger("hail_b200")
+
+
+def _sigmoid(z):
+    return 1.0 / (1.0 + np.exp(-z))
+
+
+def _fit_null(C, y, max_iter, tol):
+    """LogisticRegressionModel.fit from the intercept-only start (LogisticRegressionModel.scala:286-351)."""
+    n, m = C.shape
+    b = np.zeros(m)
+    avg = y.sum() / n
+    b[0] = np.log(avg / (1.0 - avg))
+    mu = _sigmoid(C @ b)
+    score = C.T @ (y - mu)
+    fisher = C.T @ (C * (mu * (1.0 - mu))[:, None])
+    it, converged, exploded = 0, False, False
+    while not converged and not exploded and it < max_iter:
+        it += 1
+        try:
+            delta = np.linalg.solve(fisher, score)
+        except np.linalg.LinAlgError:
+            exploded = True
+            break
+        if np.isnan(delta[0]):
+            exploded = True
+        elif np.max(np.abs(delta)) < tol:
+            converged = True
+        else:
+            b = b + delta
+            mu = _sigmoid(C @ b)
+            score = C.T @ (y - mu)
+            fisher = C.T @ (C * (mu * (1.0 - mu))[:, None])
+    return b, mu, score, fisher, it, converged, exploded
+
+
+def logistic_regression_rows(test, y, x, covariates, pass_through=(), *, max_iterations=None, tolerance=None) -> Table:
+    """For each row, test an input variable for association with a binary response using logistic regression
+    (drop-in for `hl.logistic_regression_rows(test='score', ...)`, statgen.py:731)."""
+    if test not in ("wald", "lrt", "score", "firth"):
+        raise TypeError("logistic_regression_rows: parameter 'test': expected one of 'wald', 'lrt', 'score', 'firth', "
+                        f"found {test!r}")
+    if test != "score":
+        raise NotImplementedError(f"logistic_regression_rows: test={test!r} needs per-variant Newton iterations; only the "
+                                  "score test runs on the B200 path")
+    if max_iterations is None:
+        max_iterations = 25
+    if tolerance is None:
+        tolerance = 1e-6
+    assert tolerance > 0.0
+    if len(covariates) == 0:
+        raise ValueError("logistic regression requires at least one covariate expression")
+    if not isinstance(x, EntryExpression):
+        raise ExpressionException("'logistic_regresion_rows/x': expected an entry-indexed expression "
+                                  "(e.g. mt.GT.n_alt_alleles())")
+    mt = x.source
+    y_is_list = isinstance(y, list)
+    if y_is_list and len(y) == 0:
+        raise ValueError("'logistic_regression_rows': found no values for 'y'")
+    ys = np.column_stack([_column_values(e, mt, "logistic_regression_rows/y") for e in (y if y_is_list else [y])])
+    cov = np.column_stack([_column_values(e, mt, "logistic_regression_rows/covariates") for e in covariates])
+    _warn_if_no_intercept("logistic_regression_rows", covariates)
+    row_fields = _get_regression_row_fields(mt, pass_through, "logistic_regression_rows")
+
+    # ---- LogisticRegression.scala:41-61 ----
+    keep = ~np.isnan(ys).any(axis=1) & ~np.isnan(cov).any(axis=1)
+    if not keep.any():
+        raise FatalError("No complete samples: each sample is missing its phenotype or some covariate")
+    yk, C = ys[keep], cov[keep]
+    idx = np.ascontiguousarray(np.asarray(mt.col_index)[keep], dtype=np.int32)
+    for col in range(yk.shape[1]):
+        if not np.all((yk[:, col] == 0.0) | (yk[:, col] == 1.0)):
+            raise FatalError(f"For logistic regression, y at index {col} must be bool or numeric with all present "
+                             "values equal to 0 or 1")
+        sy = yk[:, col].sum()
+        if sy == 0.0 or sy == yk.shape[0]:
+            raise FatalError(f"For logistic regression, y at index {col} must be non-constant")
+    n, k = C.shape
+    d = n - k - 1
+    if d < 1:
+        raise FatalError(f"{n} samples and {k + 1} {_plural(k, 'covariate')} (including x) implies {d} degrees of freedom.")
+    log.info("logistic_regression_rows: running %s on %d samples for response variable y,\n"
+             "    with input variable x, and %d additional %s...", test, n, k, _plural(k, "covariate"))
+
+    from .genotypes import HostBedGenotypes
+    g = mt.genotypes
+    if isinstance(g, HostBedGenotypes):   # the score path sweeps a resident store
+        g = g.to_device()
+    dev = g.device
+    ctx = _lib.context(dev.index)
+    M, N, P = g.n_variants, g.n_samples, yk.shape[1]
+    chi = np.empty((M, P))
+    pv = np.empty((M, P))
+    with torch.cuda.device(dev):
+        d_chi = torch.empty(M, dtype=torch.float64, device=dev)
+        d_p = torch.empty(M, dtype=torch.float64, device=dev)
+        out = _lib.ScoreOut(d_chi.data_ptr(), d_p.data_ptr(), None)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        for col in range(P):
+            b, mu, score, fisher, it, converged, exploded = _fit_null(C, yk[:, col], max_iterations, tolerance)
+            if not converged:   # LogisticRegression.scala:83-90
+                raise FatalError("Failed to fit logistic regression null model (standard MLE with covariates only): " +
+                                 (f"exploded at Newton iteration {it}" if exploded else "Newton iteration failed to converge"))
+            w = mu * (1.0 - mu)
+            wc = np.ascontiguousarray((C * w[:, None]).T)        # [K, n]
+            resid = np.ascontiguousarray(yk[:, col] - mu)
+            finv = np.ascontiguousarray(np.linalg.inv(fisher))
+            ctx.check(ctx.lib.lrr_set_score_model(ctx.handle, N, n, k, idx.ctypes.data, wc.ctypes.data, resid.ctypes.data,
+                                                  np.ascontiguousarray(w).ctypes.data, finv.ctypes.data,
+                                                  np.ascontiguousarray(score).ctypes.data))
+            ctx.check(ctx.lib.lrr_run_score(ctx.handle, g.data.data_ptr(), g.flags_ptr(), M, g.stride, N,
+                                            ctypes.byref(out), stream))
+            torch.cuda.synchronize(dev)
+            chi[:, col] = d_chi.cpu().numpy()
+            pv[:, col] = d_p.cpu().numpy()
+        ctx.check(ctx.lib.lrr_clear_groups(ctx.handle))
+    fields = OrderedDict()
+    for kf in mt.row_key:
+        fields[kf] = mt.row[kf]
+    for kf, v in row_fields.items():
+        fields[kf] = v
+    fields["chi_sq_stat"] = chi if y_is_list else chi[:, 0]
+    fields["p_value"] = pv if y_is_list else pv[:, 0]
+    return Table(fields, key=mt.row_key, n_rows=mt.count_rows())

@@ -163,6 +163,25 @@ int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64
 int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs, int32_t n_outs, int32_t kernel);
 void lrr_stream_end(lrr_ctx* ctx, lrr_stream* stream);
 
+/* ---- logistic regression, score test (`hl.logistic_regression_rows(test='score', ...)`) --------
+ * Replaces the per-row loop of hail/hail/src/is/hail/methods/LogisticRegression.scala:115-157 for
+ * LogisticScoreTest (stats/LogisticRegressionModel.scala:211-264) on the same ingest, complete-sample and
+ * mean-imputation logic as the linear path.  The host fits the null model (covariates only, LogisticRegression.scala:67-91)
+ * and passes, for the n complete samples (ascending complete_idx): wc [K, n] = w_j c_jk with w = mu (1 - mu),
+ * resid [n] = y - mu, w [n], finv [K, K] = inverse of the null Fisher information, score0 [K] = null score.
+ * lrr_set_score_model replaces any groups of the context; lrr_run_score sweeps packed rows (float64 kernel: the
+ * x'Wx term is not linear in the call codes) and writes chi_sq_stat / p_value [M] (NaN where the reference yields
+ * missing: x in the span of the covariates) and optionally n_missing [M]. */
+typedef struct {
+  double* chi_sq_stat;
+  double* p_value;
+  int32_t* n_missing;
+} lrr_score_out;
+int lrr_set_score_model(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, const int32_t* complete_idx,
+                        const double* wc, const double* resid, const double* w, const double* finv, const double* score0);
+int lrr_run_score(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
+                  int64_t n_samples_total, const lrr_score_out* out, void* stream);
+
 /* two-sided Student-t p-value on the device, exposed for unit tests of the epilogue:
  * p[i] = 2 * P[T_df <= -|t[i]|]  (jdistlib T.cumulative call sites LR:160, LR:344) */
 int lrr_student_t_two_sided(lrr_ctx* ctx, const double* d_t, int64_t count, double df, double* d_p, double* d_log10_p,

@@ -594,3 +594,71 @@ def test_weighted_linear_regression_vs_oracle():
     from hail_b200 import _lib
     with pytest.raises(_lib.LrrError, match="float64 kernel"):
         hb.linear_regression_rows(y=mt.y0, x=mt.GT.n_alt_alleles(), covariates=covs, weights=mt.w1, _kernel="tc4")
+
+
+# ---------------------------------------------------------------------------------------------
+# logistic regression, score test: R-derived golden values and oracle parity
+def test_logistic_score_reference_golden():   # test_statgen.py:987-1021
+    hb = _hb()
+    from tests.test_oracle_logistic import load_regression_logistic
+    doc, x, y, cov = load_regression_logistic()
+    mt = _mt_from_dosage(x, y=y, c1=cov[:, 1], c2=cov[:, 2])
+    ht = hb.logistic_regression_rows(test="score", y=mt.y, x=mt.GT.n_alt_alleles(), covariates=[1.0, mt.c1, mt.c2])
+    for pos, want in doc["expected_score"].items():
+        if pos == "constant":
+            continue
+        i = int(pos) - 1
+        assert abs(ht.chi_sq_stat[i] - want["chi_sq_stat"]) < 5e-7 and abs(ht.p_value[i] - want["p_value"]) < 5e-7, pos
+    for pos in doc["expected_score"]["constant"]:
+        c = ht.chi_sq_stat[pos - 1]
+        assert np.isnan(c) or c < 1e-6
+
+
+def test_logistic_score_vs_oracle_and_errors():
+    hb = _hb()
+    from oracle import logreg_oracle as L
+    z = np.load(os.path.join(GOLDEN, "fastlmm.npz"))
+    N, M = int(z["n_samples"]), int(z["n_variants"])
+    rows = obed.bed_body(z["bed"], N, M)
+    x = obed.decode_rows(rows, N)
+    rng = np.random.default_rng(41)
+    cov = np.column_stack([np.ones(N), z["cov"][:, 0], rng.normal(size=N)])
+    eta = 0.4 * cov[:, 1] - 0.3 * cov[:, 2] + 0.8 * np.nan_to_num(x[5]) - 0.5
+    y1 = (rng.random(N) < 1 / (1 + np.exp(-eta))).astype(np.float64)
+    y2 = (rng.random(N) < 0.3).astype(np.float64)
+    y1[rng.random(N) < 0.03] = np.nan
+    mt = hb.MatrixTable(hb.PackedGenotypes.from_bed_rows(rows, N), rows={"rsid": np.arange(M)},
+                        cols={"y1": y1, "y2": y2, "c1": cov[:, 1], "c2": cov[:, 2]})
+    ht = hb.logistic_regression_rows("score", [mt.y1, mt.y2], mt.GT.n_alt_alleles(), [1.0, mt.c1, mt.c2],
+                                     pass_through=["rsid"])
+    assert ht.chi_sq_stat.shape == (M, 2) and list(ht.rsid) == list(range(M))
+    # the Scala path keeps the samples complete for ALL phenotypes (LogisticRegression.scala:41-42)
+    keep = ~np.isnan(y1)
+    for col, yy in enumerate((y1, y2)):
+        want = L.logreg_score(x[:, keep], yy[keep], cov[keep])
+        ok = np.isfinite(want["chi_sq_stat"])
+        assert ok.sum() > 0.9 * M
+        assert np.allclose(ht.chi_sq_stat[ok, col], want["chi_sq_stat"][ok], rtol=1e-6, atol=1e-9), col
+        assert np.allclose(ht.p_value[ok, col], want["p_value"][ok], rtol=1e-5, atol=1e-300), col
+    assert int(np.nanargmin(ht.p_value[:, 0])) == 5        # the causal variant
+    single = hb.logistic_regression_rows("score", mt.y2, mt.GT.n_alt_alleles(), [1.0, mt.c1, mt.c2])
+    assert single.chi_sq_stat.shape == (M,)
+    # errors: statgen.py:976-984, LogisticRegression.scala:44-61, 83-90
+    with pytest.raises(ValueError, match="at least one covariate"):
+        hb.logistic_regression_rows("score", mt.y2, mt.GT.n_alt_alleles(), [])
+    with pytest.raises(ValueError, match="found no values for 'y'"):
+        hb.logistic_regression_rows("score", [], mt.GT.n_alt_alleles(), [1.0])
+    with pytest.raises(TypeError):
+        hb.logistic_regression_rows("rao", mt.y2, mt.GT.n_alt_alleles(), [1.0])
+    with pytest.raises(NotImplementedError):
+        hb.logistic_regression_rows("wald", mt.y2, mt.GT.n_alt_alleles(), [1.0])
+    bad = mt.annotate_cols(q=rng.normal(size=N), one=np.ones(N), sep=np.where(y2 > 0, 9.0, -9.0))
+    with pytest.raises(hb.FatalError, match="equal to 0 or 1"):
+        hb.logistic_regression_rows("score", bad.q, bad.GT.n_alt_alleles(), [1.0])
+    with pytest.raises(hb.FatalError, match="must be non-constant"):
+        hb.logistic_regression_rows("score", bad.one, bad.GT.n_alt_alleles(), [1.0])
+    with pytest.raises(hb.FatalError, match="Failed to fit logistic regression null model"):
+        hb.logistic_regression_rows("score", bad.y2, bad.GT.n_alt_alleles(), [1.0, bad.sep])
+    # the context is usable for the linear path afterwards
+    lin = hb.linear_regression_rows(mt.y2, mt.GT.n_alt_alleles(), [1.0, mt.c1])
+    assert np.isfinite(lin.beta).sum() > 0.9 * M

@@ -1,0 +1,50 @@
+"""The logistic score-test oracle against the reference's R-derived golden values (test_statgen.py:987-1021)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import logreg_oracle as L
+from oracle.linreg_oracle import OracleFatal
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_regression_logistic():
+    doc = json.load(open(os.path.join(GOLDEN, "regression_logistic.json")))
+    s = doc["samples"]
+    x = np.array([[np.nan if v is None else float(v) for v in row] for row in doc["gt_n_alt_alleles"]])
+    y = np.array([np.nan if doc["pheno_table"].get(k) is None else float(doc["pheno_table"][k]) for k in s])
+    cov = np.array([[1.0] + doc["cov_table"].get(k, [np.nan, np.nan]) for k in s])
+    return doc, x, y, cov
+
+
+def test_score_test_matches_r():
+    doc, x, y, cov = load_regression_logistic()
+    out = L.logreg_score(x, y, cov)
+    assert out["n"] == 10                                  # A..J minus W, X (no phenotype / covariates)
+    for pos, want in doc["expected_score"].items():
+        if pos == "constant":
+            continue
+        i = int(pos) - 1
+        assert abs(out["chi_sq_stat"][i] - want["chi_sq_stat"]) < 5e-7, pos
+        assert abs(out["p_value"][i] - want["p_value"]) < 5e-7, pos
+    for pos in doc["expected_score"]["constant"]:
+        c = out["chi_sq_stat"][pos - 1]
+        assert np.isnan(c) or c < 1e-6
+
+
+def test_null_fit_and_fatal_conditions():
+    _, x, y, cov = load_regression_logistic()
+    with pytest.raises(OracleFatal, match="must be non-constant"):
+        L.logreg_score(x, np.where(np.isnan(y), np.nan, 1.0), cov)
+    with pytest.raises(OracleFatal, match="equal to 0 or 1"):
+        L.logreg_score(x, np.where(np.isnan(y), np.nan, y * 2.0), cov)
+    with pytest.raises(OracleFatal, match="degrees of freedom"):
+        L.logreg_score(x, y, np.column_stack([cov] + [np.random.default_rng(i).normal(size=cov.shape[0]) for i in range(7)]))
+    # separable covariate -> the null model explodes / does not converge (LogisticRegression.scala:83-90)
+    sep = np.column_stack([cov[:, 0], np.where(np.nan_to_num(y) > 0, 5.0, -5.0)])
+    with pytest.raises(OracleFatal, match="Failed to fit logistic regression null model"):
+        L.logreg_score(x, y, sep)
+    assert np.allclose(L.chi_sq_tail_1(np.array([0.0, 3.841458820694124])), [1.0, 0.05], atol=1e-12)
