@@ -1,0 +1,152 @@
+// Per-variant statistics shared by the stand-alone epilogue kernel (stats_epilogue.cu) and the fused epilogue of the
+// 4-bit sweep (tc4_kernel.cu).  Restates hail/hail/src/is/hail/methods/LinearRegression.scala:136-160 (same operation
+// order for xxpRec, b, se, t) and the Student-t call 2 * T.cumulative(-|t|, d, true, false) (LR:160): jdistlib's
+// T.cumulative is a port of R's pt(), a regularised incomplete beta I_x(d/2, 1/2), evaluated here with the Lentz continued
+// fraction (direct form in the tail, complement form near the centre).
+#pragma once
+#include "common.cuh"
+
+namespace lrr {
+
+__device__ inline double betacf_dev(double a, double b, double x) {
+  const double tiny = 1e-300, eps = 3e-15;  // a tighter test can bounce a few ulp around 1 for hundreds of iterations
+  const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  double c = 1.0, d = 1.0 - qab * x / qap;
+  if (fabs(d) < tiny) d = tiny;
+  d = 1.0 / d;
+  double h = d;
+  for (int m = 1; m <= 1000; ++m) {
+    const double m2 = 2.0 * m;
+    double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+    d = 1.0 + aa * d;
+    if (fabs(d) < tiny) d = tiny;
+    c = 1.0 + aa / c;
+    if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    h *= d * c;
+    aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+    d = 1.0 + aa * d;
+    if (fabs(d) < tiny) d = tiny;
+    c = 1.0 + aa / c;
+    if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < eps) break;
+  }
+  return h;
+}
+
+// p = 2 P[T_df <= -|t|]; lbeta = log B(df/2, 1/2).  Optionally log10(p), finite where p underflows.
+__device__ inline double two_sided_p_dev(double t, double df, double lbeta, double* log10_p) {
+  const double kInvLn10 = 0.43429448190325182765;
+  if (isnan(t)) {
+    if (log10_p) *log10_p = t;
+    return t;
+  }
+  if (isinf(t)) {
+    if (log10_p) *log10_p = -INFINITY;
+    return 0.0;
+  }
+  const double a = 0.5 * df, b = 0.5;
+  const double t2d = (t / df) * t;
+  const double x = 1.0 / (1.0 + t2d);
+  if (x < (a + 1.0) / (a + b + 2.0)) {
+    const double lf = -a * log1p(t2d) + b * log(t2d / (1.0 + t2d)) - log(a) - lbeta;
+    const double cf = betacf_dev(a, b, x);
+    if (log10_p) *log10_p = (lf + log(cf)) * kInvLn10;
+    return exp(lf) * cf;
+  }
+  const double xc = t2d / (1.0 + t2d);
+  if (xc == 0.0) {
+    if (log10_p) *log10_p = 0.0;
+    return 1.0;
+  }
+  const double lf = b * log(xc) - a * log1p(t2d) - log(b) - lbeta;
+  const double lower = exp(lf) * betacf_dev(b, a, xc);
+  if (log10_p) *log10_p = log1p(-lower) * kInvLn10;
+  return 1.0 - lower;
+}
+
+
+// what the statistics of one group need besides the per-variant sums
+struct StatModel {
+  const double* qty;      // [K][P]
+  const double* yyp;      // [P]
+  int n, K, Kd, P, C, has_intercept, d, weighted;
+  double lbeta;
+  lrr_group_out out;
+};
+
+// statistics of variant v, phenotype p of one group from the exact counts and the dot products dv[0..C)
+__device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n1, int n2, int nm, const double* dv) {
+  const double dRec = 1.0 / (double)a.d;  // LR:51
+  const int64_t idx = v * a.P + p;
+  const double nv = (double)(a.n - nm);
+  const double S = (double)(n1 + 2 * n2);
+  const double xx_int = (double)(n1 + 4 * n2);
+  const double mean = S / nv;                        // RU:52
+  // weighted groups (statgen.py:636-660): the column sum and x.x of the sqrt(w)-scaled imputed x are dot products
+  const double sum_x = a.weighted ? dv[a.Kd + a.P] : S + (double)nm * mean;        // LR:136
+  const double xx_imp = a.weighted ? dv[a.Kd + a.P + 1] : xx_int + (double)nm * mean * mean;
+
+  double qq = 0.0;
+  for (int c = 0; c < a.Kd; ++c) qq += dv[c] * dv[c];
+  double xxp;  // x.x - qtx.qtx  (LR:141-142)
+  if (a.has_intercept) {
+    // constant column handled exactly: x.x - (sum_x)^2/n == xx_int - S^2/nv for the mean-imputed column
+    xxp = (xx_int - S * S / nv) - qq;
+  } else {
+    xxp = xx_imp - qq;
+  }
+  const double xyp = dv[a.Kd + p];                   // y_res . x  == ytx - Qty^T qtx (LR:146)
+  double proj = 0.0;
+  if (a.has_intercept) proj = a.qty[p] * (sum_x / sqrt((double)a.n));
+  for (int c = 0; c < a.Kd; ++c) proj += a.qty[(c + a.has_intercept) * a.P + p] * dv[c];
+  const double ytx = xyp + proj;                     // LR:143
+
+  double b, se, t, pv, l10 = 0.0;
+  // Degenerate (constant / collinear) x: the reference leaves roundoff garbage here (xxp = +-1e-15 and
+  // sqrt of a negative -> NaN se; test_statgen.py:277-284).  Rule: no information -> NaN statistics.
+  const bool degenerate = !(xxp > 1e-11 * xx_imp);
+  if (degenerate && !isnan(xxp)) {
+    b = se = t = pv = l10 = __longlong_as_double(0x7ff8000000000000ll);
+  } else {
+    const double xxpRec = 1.0 / xxp;
+    b = xyp * xxpRec;                                          // LR:150-155
+    se = sqrt(dRec * (a.yyp[p] * xxpRec - b * b));             // LR:157
+    t = b / se;                                                // LR:159
+    pv = two_sided_p_dev(t, (double)a.d, a.lbeta, a.out.log10_p ? &l10 : nullptr);  // LR:160
+  }
+  if (p == 0) {
+    if (a.out.n) a.out.n[v] = a.n;
+    if (a.out.n_missing) a.out.n_missing[v] = nm;
+    if (a.out.sum_x) a.out.sum_x[v] = sum_x;
+  }
+  if (a.out.y_transpose_x) a.out.y_transpose_x[idx] = ytx;
+  if (a.out.beta) a.out.beta[idx] = b;
+  if (a.out.standard_error) a.out.standard_error[idx] = se;
+  if (a.out.t_stat) a.out.t_stat[idx] = t;
+  if (a.out.p_value) a.out.p_value[idx] = pv;
+  if (a.out.log10_p) a.out.log10_p[idx] = l10;
+}
+
+// fill a StatModel from a group (host)
+inline StatModel stat_model_of(const Group& G, const lrr_group_out& out) {
+  StatModel a;
+  a.qty = G.d_qty;
+  a.yyp = G.d_yyp;
+  a.n = G.n;
+  a.K = G.K;
+  a.Kd = G.Kd;
+  a.P = G.P;
+  a.C = G.C;
+  a.has_intercept = G.has_intercept;
+  a.d = G.d;
+  a.weighted = G.weighted;
+  a.lbeta = G.lbeta;
+  a.out = out;
+  return a;
+}
+
+}  // namespace lrr
