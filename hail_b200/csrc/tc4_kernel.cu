@@ -20,6 +20,8 @@
 //   * A ring in units of 64 TMEM columns (one chunk of one plane); a one-plane chunk takes one unit, a two-plane
 //     chunk (tile with missing calls) two consecutive units [plane c | plane m]; every unit has its own
 //     full / empty barrier pair and BOTH sides track the phase parity per barrier, so units may be skipped;
+//   * one-plane tiles use the columns of the unused plane-m accumulators as ring space (6 units instead of 4): the
+//     MMAs of a chunk take ~200 ns plus commit latency and sit inside the unit's reuse loop;
 //   * the scale-factor operands point at 16 TMEM columns filled with 0x7F bytes -- all scales are 1, which makes
 //     the result independent of the scale-factor layout.
 #include <cuda.h>
@@ -42,7 +44,9 @@ constexpr int SLOT = 128;              // samples per unpack warp and chunk (16 
 constexpr int SLOTS = CHUNK / SLOT;    // 4
 constexpr int SLOT_COLS = 16;
 constexpr int UNIT_COLS = SLOTS * SLOT_COLS;   // 64: one chunk of one plane
-constexpr int NU = 4;                  // ring units
+constexpr int MAX_UNITS = 6;           // ring units: 6 (or 4) for one-plane tiles, 4 (two pairs) for two-plane tiles
+constexpr int NU2 = 4;
+constexpr int SF_BASE = 512 - 16;      // scale-factor columns sit at the top of tensor memory in both modes
 constexpr int PANEL = 256;             // samples per basis-panel row (128 bytes of nibbles)
 constexpr int PANELS = CHUNK / PANEL;  // 2
 constexpr int UNPACK_WARPS = 16;       // warp w: TMEM lane quarter w & 3, slot w >> 2 of every chunk
@@ -77,12 +81,14 @@ struct Params {
   int ncols;          // padded to 16
   int n_gstages, n_bstages;
   int n_groups;
-  int sf_base;        // first scale-factor column
-  int ring_base;      // first TMEM column of the A ring (NU units of 64 columns)
+  int ring_base1, nu1;   // one-plane tiles: first TMEM column of the A ring (after D_c) and its units (6 or 4)
+  int ring_base2;        // two-plane tiles: ring after D_c and D_m, NU2 units
   int gstage_bytes, bstage_bytes;
   int mask_bytes;     // n_groups * 128 when any group needs masking, else 0
   const uint8_t* row_flags;  // nullable
   int abl_contig;     // timing ablation: read every genotype box as one contiguous 16 KB block (results are WRONG)
+  int abl;            // timing ablation bits: 1 no tcgen05.st, 2 no MMA, 4 no basis-panel loads, 8 no unpack ALU, 16 no popcount (results are WRONG)
+  int abl_stream;     // timing ablation: genotype stream only -- no unpack, no basis panels, no MMA (results are WRONG)
   GroupMeta g[MAX_GROUPS];
 };
 
@@ -124,8 +130,8 @@ struct Barriers {
   uint64_t gempty[MAX_GSTAGES];  // genotype stage read out by the 16 unpack warps
   uint64_t bfull[MAX_BSTAGES];   // basis-panel stage filled by TMA (both CTAs of a pair complete on the leader's)
   uint64_t bempty[MAX_BSTAGES];  // basis-panel stage consumed (MMA commit)
-  uint64_t a_full[NU];           // ring unit written (16 warps of each CTA)
-  uint64_t a_empty[NU];          // ring unit consumed (MMA commit)
+  uint64_t a_full[MAX_UNITS];    // ring unit written (16 warps of each CTA)
+  uint64_t a_empty[MAX_UNITS];   // ring unit consumed (MMA commit)
   uint64_t d_full;               // accumulators complete (MMA commit)
   uint64_t d_empty;              // accumulators read out (4 epilogue warps of each CTA)
   uint32_t tmem_base;
@@ -169,8 +175,8 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
   auto BFULL = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + s); };
   auto BEMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + MAX_BSTAGES + s); };
   auto AFULL = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + 2 * MAX_BSTAGES + s); };
-  auto AEMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + 2 * MAX_BSTAGES + NU + s); };
-  const uint32_t DFULL = bar0 + 8u * (2 * MAX_GSTAGES + 2 * MAX_BSTAGES + 2 * NU);
+  auto AEMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_GSTAGES + 2 * MAX_BSTAGES + MAX_UNITS + s); };
+  const uint32_t DFULL = bar0 + 8u * (2 * MAX_GSTAGES + 2 * MAX_BSTAGES + 2 * MAX_UNITS);
   const uint32_t DEMPTY = DFULL + 8u;
   const int n_groups = NG ? NG : p.n_groups;
 
@@ -186,7 +192,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
       mbar_init(BFULL(s), 1);
       mbar_init(BEMPTY(s), 1);
     }
-    for (int s = 0; s < NU; ++s) {
+    for (int s = 0; s < MAX_UNITS; ++s) {
       mbar_init(AFULL(s), UNPACK_WARPS * CS);
       mbar_init(AEMPTY(s), 1);
     }
@@ -216,7 +222,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
     uint32_t sf[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) sf[i] = 0x7F7F7F7Fu;
-    tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + p.sf_base, sf);
+    tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + SF_BASE, sf);
     tmem_wait_st();
   }
   tc_fence_before();
@@ -256,6 +262,10 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         if (++gs == p.n_gstages) { gs = 0; g_phase ^= 1; }
       }
     }
+  } else if (warp == WARP_TMA_B && p.abl_stream) {
+    // (ablation: no basis panels)
+  } else if (warp == WARP_MMA && p.abl_stream) {
+    // (ablation: no MMAs)
   } else if (warp == WARP_TMA_B) {
     // ============================== basis-panel producer ==============================
     int bs = 0;
@@ -265,7 +275,9 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         mbar_wait(BEMPTY(bs), b_phase ^ 1);
         const uint32_t sbase = bring0 + bs * p.bstage_bytes;
         if (elect_one()) {
-          if (CS == 1) {
+          if (p.abl & 4) {
+            if (cta_rank == 0) mbar_arrive(BFULL(bs));
+          } else if (CS == 1) {
             mbar_arrive_expect_tx(BFULL(bs), (uint32_t)(PANELS * panel_bytes));
 #pragma unroll
             for (int s = 0; s < PANELS; ++s)
@@ -287,7 +299,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
     // ============================== MMA issuer (pair: the leader only) ==============================
     if (CS == 1 || cta_rank == 0) {
       const uint32_t idesc = make_idesc(p.ncols, TILE_M * CS);
-      const uint32_t sfa = tmem + p.sf_base, sfb = tmem + p.sf_base + 8;
+      const uint32_t sfa = tmem + SF_BASE, sfb = tmem + SF_BASE + 8;
       auto commit = [&](uint32_t bar) {
         if (CS == 1) tc_commit(bar); else tc_commit_pair(bar);
       };
@@ -296,10 +308,11 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
       int ru = 0;               // next ring unit
       uint32_t full_par = 0;    // bit u: parity of the next completion of AFULL(u) this warp waits for
       uint32_t tile_i = 0;
+      bool prev_two_plane = false;
       const uint64_t desc0 = make_kmajor_sw128_desc(bring0);
       const uint32_t stage_d = (uint32_t)p.bstage_bytes >> 4;   // descriptor-address units (16 B)
       const uint32_t panel_d = (uint32_t)panel_bytes >> 4;
-      const uint32_t a_ring = tmem + p.ring_base;
+      uint32_t a_ring = tmem + p.ring_base1;   // set per tile from its mode
 
       // the MMAs of one chunk: unit `u` (+ `u + 1` = plane m), basis stage descriptor `bd`
       auto issue = [&](auto tp_tag, const int u, const uint64_t bd, const uint32_t first_acc) {
@@ -317,23 +330,28 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
       };
       auto generic_chunk = [&](int ch, bool two_plane) {
         mbar_wait(BFULL(bs), b_phase);
-        if (two_plane && (ru & 1)) ru = (ru + 1) & (NU - 1);
+        const int nu = two_plane ? NU2 : p.nu1;
+        if (two_plane && (ru & 1)) { if (++ru >= nu) ru -= nu; }
         mbar_wait(AFULL(ru), (full_par >> ru) & 1u);
         full_par ^= 1u << ru;
         tc_fence_after();
         const uint64_t bd = desc0 + (uint64_t)(bs * stage_d);
         if (elect_one()) {
-          if (two_plane) issue(TrueTag{}, ru, bd, ch ? 1u : 0u); else issue(FalseTag{}, ru, bd, ch ? 1u : 0u);
+          if (p.abl & 2) {
+          } else if (two_plane) issue(TrueTag{}, ru, bd, ch ? 1u : 0u); else issue(FalseTag{}, ru, bd, ch ? 1u : 0u);
           commit(AEMPTY(ru));
           commit(BEMPTY(bs));
         }
         __syncwarp();
-        ru = (ru + (two_plane ? 2 : 1)) & (NU - 1);
+        ru += two_plane ? 2 : 1;
+        if (ru >= nu) ru -= nu;
         if (++bs == p.n_bstages) { bs = 0; b_phase ^= 1; }
       };
       // fast path: UNROLL chunks with every ring position a compile-time constant (entered with bs == 0, ru == 0)
-      auto fast_chunks = [&](auto tp_tag, int& ch) {
+      auto fast_chunks = [&](auto tp_tag, auto nu_tag, int& ch) {
         constexpr bool TP = decltype(tp_tag)::value;
+        constexpr int NU = decltype(nu_tag)::value;
+        static_assert(UNROLL % NU == 0 && UNROLL % NB == 0, "ring positions must repeat every UNROLL chunks");
         for (; ch + UNROLL <= p.n_chunks; ch += UNROLL) {
 #pragma unroll
           for (int k = 0; k < UNROLL; ++k) {
@@ -346,7 +364,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
             tc_fence_after();
             const uint64_t bd = desc0 + (uint64_t)(b * stage_d);
             if (elect_one()) {
-              issue(tp_tag, u, bd, k ? 1u : (ch ? 1u : 0u));
+              if (!(p.abl & 2)) issue(tp_tag, u, bd, k ? 1u : (ch ? 1u : 0u));
               commit(AEMPTY(u));
               commit(BEMPTY(b));
             }
@@ -358,13 +376,18 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
 
       for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
         const bool two_plane = tile_mode(tile);
+        if (tile_i > 0 && two_plane != prev_two_plane) ru = 0;   // the ring is laid out per mode (the unpack warps drain first)
+        prev_two_plane = two_plane;
+        a_ring = tmem + (two_plane ? p.ring_base2 : p.ring_base1);
         mbar_wait(DEMPTY, (tile_i & 1) ^ 1);   // the previous tile's accumulators have been read out (by both CTAs)
         tc_fence_after();
         int ch = 0;
         if (p.n_bstages == NB) {
           while (ch < p.n_chunks && (bs != 0 || ru != 0)) generic_chunk(ch++, two_plane);
           if (ch < p.n_chunks) {
-            if (two_plane) fast_chunks(TrueTag{}, ch); else fast_chunks(FalseTag{}, ch);
+            if (two_plane) fast_chunks(TrueTag{}, IntTag<NU2>{}, ch);
+            else if (p.nu1 == 6) fast_chunks(FalseTag{}, IntTag<6>{}, ch);
+            else fast_chunks(FalseTag{}, IntTag<4>{}, ch);
           }
         }
         for (; ch < p.n_chunks; ++ch) generic_chunk(ch, two_plane);
@@ -390,7 +413,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
     uint32_t empty_par = 0;          // bit u: parity of the last completion of AEMPTY(u) this warp relies on
     uint32_t tile_i = 0;
     bool prev_two_plane = false;
-    const uint32_t a_slot = tmem + lane_addr + p.ring_base + s * SLOT_COLS;
+    uint32_t a_slot = tmem + lane_addr + p.ring_base1 + s * SLOT_COLS;   // set per tile from its mode
     int n2[NG ? NG : MAX_GROUPS];
     const uint32_t afull_leader = (CS == 2) ? mapa_leader(AFULL(0)) : 0u;
     const uint32_t dempty_leader = (CS == 2) ? mapa_leader(DEMPTY) : 0u;
@@ -426,13 +449,18 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         uint32_t rc[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          rc[2 * i + 0] = w[i] & 0x33333333u;
-          rc[2 * i + 1] = (w[i] >> 2) & 0x33333333u;
+          if (p.abl & 8) {
+            rc[2 * i + 0] = w[i];
+            rc[2 * i + 1] = w[i];
+          } else {
+            rc[2 * i + 0] = w[i] & 0x33333333u;
+            rc[2 * i + 1] = (w[i] >> 2) & 0x33333333u;
+          }
         }
         // exact counts for x.x = n1 + 4 n2 (see tc_kernel.cu)
 #pragma unroll
         for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
-          if (NG || g < n_groups) {
+          if ((NG || g < n_groups) && !(p.abl & 16)) {
             int acc = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -448,7 +476,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(gbar + 8u * MAX_GSTAGES);   // genotype stage back to the TMA producer
-        if (pend_u >= 0) {   // retire the previous chunk's TMEM store behind this chunk's arithmetic
+        if (pend_u >= 0 && !(p.abl & 32)) {   // retire the previous chunk's TMEM store behind this chunk's arithmetic
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
@@ -457,7 +485,8 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         mbar_wait(AEMPTY(u), ((empty_par >> u) & 1u) ^ 1u);
         empty_par ^= 1u << u;
         tc_fence_after();
-        tmem_st16(a_slot + u * UNIT_COLS, rc);
+        if (!(p.abl & 1)) tmem_st16(a_slot + u * UNIT_COLS, rc);
+        else if ((rc[0] ^ rc[5] ^ rc[10] ^ rc[15]) == 0x12345678u) n2[0] += 1;   // keep the arithmetic alive
         if (TP) {
           // missing-indicator plane: nibble 0001 (= 0.5) where the call is code 3
 #pragma unroll
@@ -468,20 +497,38 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
           }
           tmem_st16(a_slot + (u + 1) * UNIT_COLS, rc);
         }
+        if (p.abl & 32) {   // experiment: publish the store at once instead of behind the next chunk's arithmetic
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_afull(u);
+        }
         gaddr += p.gstage_bytes;
         gbar += 8u;
         if (gaddr == gaddr_end) { gaddr = smem0; gbar = GFULL(0); g_phase ^= 1; }
       };
+      const int nu = TP ? NU2 : p.nu1;
       auto generic_chunk = [&]() {
-        if (TP && (ru & 1)) ru = (ru + 1) & (NU - 1);
+        if (TP && (ru & 1)) { if (++ru >= nu) ru -= nu; }
         chunk_body(ru, pend);
         pend = ru;
-        ru = (ru + (TP ? 2 : 1)) & (NU - 1);
+        ru += TP ? 2 : 1;
+        if (ru >= nu) ru -= nu;
       };
       int ch = 0;
       // steady state unrolled over the ring (positions become constants): entered with ru == 0
       do { generic_chunk(); ++ch; } while (ch < p.n_chunks && ru != 0);
-      if (!TP) {
+      if (!TP && nu == 6) {
+        for (; ch + 6 <= p.n_chunks; ch += 6) {   // pend == 5 here
+          chunk_body(0, pend);
+          chunk_body(1, 0);
+          chunk_body(2, 1);
+          chunk_body(3, 2);
+          chunk_body(4, 3);
+          chunk_body(5, 4);
+          pend = 5;
+        }
+      } else if (!TP) {
         for (; ch + 4 <= p.n_chunks; ch += 4) {   // pend == 3 here
           chunk_body(0, pend);
           chunk_body(1, 0);
@@ -497,7 +544,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         }
       }
       for (; ch < p.n_chunks; ++ch) generic_chunk();
-      if (pend >= 0) {   // flush the last chunk of the tile
+      if (pend >= 0 && !(p.abl & 32)) {   // flush the last chunk of the tile
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -505,14 +552,34 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
       }
     };
 
+    if (p.abl_stream) {
+      // ablation: consume the genotype stages and nothing else (abl_stream == 2: also LDS the thread's 32 bytes)
+      uint32_t sink = 0;
+      for (int tile = first_tile; tile < tile_end; tile += tile_step)
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          mbar_wait(gbar, g_phase);
+          if (p.abl_stream == 2) { const uint4 w0 = lds128(gaddr + ld0); const uint4 w1 = lds128(gaddr + ld1); sink ^= w0.x ^ w1.w; }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(gbar + 8u * MAX_GSTAGES);
+          gaddr += p.gstage_bytes;
+          gbar += 8u;
+          if (gaddr == gaddr_end) { gaddr = smem0; gbar = GFULL(0); g_phase ^= 1; }
+        }
+      if (sink == 0x12345u) bars->pad = sink;
+    } else
     for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
       const bool two_plane = tile_mode(tile);
       if (tile_i > 0 && two_plane != prev_two_plane) {
         // the ring is laid out differently: wait until every MMA of the previous tile has retired
         mbar_wait(DFULL, (tile_i - 1) & 1);
         tc_fence_after();
+        // ... and until the epilogue warps have read the previous tile's accumulators: the one-plane ring reuses the
+        // plane-m accumulator columns (the epilogue warps arrive here after their tcgen05.ld, in program order)
+        named_bar_sync(2, UNPACK_WARPS * 32);
+        ru = 0;
       }
       prev_two_plane = two_plane;
+      a_slot = tmem + lane_addr + (two_plane ? p.ring_base2 : p.ring_base1) + s * SLOT_COLS;
 #pragma unroll
       for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) n2[g] = 0;
       if (two_plane) {
@@ -741,7 +808,7 @@ struct Pass {
   int64_t bq_row0 = 0;           // first row of this pass in State::d_bq
   std::vector<Segment> segs;
   int gstage_bytes = 0;
-  int sf_base = 0, ring_base = 0, mask_bytes = 0;
+  int ring_base1 = 0, nu1 = 0, ring_base2 = 0, mask_bytes = 0;
   PassShape shape[2];            // [cluster size - 1]
 };
 
@@ -934,9 +1001,12 @@ static int prepare(Ctx* c) {
   for (auto& ps : s->passes) {
     ps.mask_bytes = any_masked ? (int)ps.segs.size() * 128 : 0;
     ps.gstage_bytes = (GENO_BYTES + ps.mask_bytes + 1023) / 1024 * 1024;
-    ps.sf_base = 2 * ps.ncols;
-    ps.ring_base = (2 * ps.ncols + SF_COLS + 31) / 32 * 32;
-    if (ps.ring_base + NU * UNIT_COLS > 512) {
+    // TMEM: accumulators from column 0, scale factors in the top 16 columns, the A ring in between
+    ps.ring_base1 = (ps.ncols + 31) / 32 * 32;
+    ps.ring_base2 = (2 * ps.ncols + 31) / 32 * 32;
+    ps.nu1 = (SF_BASE - ps.ring_base1) / UNIT_COLS >= 6 ? 6 : 4;
+    if (const char* e = getenv("LRR_TC4_NU1")) { if (atoi(e) == 4) ps.nu1 = 4; }
+    if (ps.ring_base2 + NU2 * UNIT_COLS > SF_BASE || ps.ring_base1 + ps.nu1 * UNIT_COLS > SF_BASE) {
       s->why = "not enough tensor memory for the A ring";
       return LRR_OK;
     }
@@ -1037,13 +1107,16 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
     p.n_gstages = sh.n_gstages;
     p.n_bstages = sh.n_bstages;
     p.n_groups = (int)ps.segs.size();
-    p.sf_base = ps.sf_base;
-    p.ring_base = ps.ring_base;
+    p.ring_base1 = ps.ring_base1;
+    p.nu1 = ps.nu1;
+    p.ring_base2 = ps.ring_base2;
     p.gstage_bytes = ps.gstage_bytes;
     p.bstage_bytes = sh.bstage_bytes;
     p.mask_bytes = ps.mask_bytes;
     p.row_flags = d_row_flags;
     p.abl_contig = abl_contig ? 1 : 0;
+    p.abl_stream = getenv("LRR_ABL_STREAM") ? atoi(getenv("LRR_ABL_STREAM")) : 0;
+    p.abl = getenv("LRR_ABL_BITS") ? atoi(getenv("LRR_ABL_BITS")) : 0;
     for (int i = 0; i < p.n_groups; ++i) {
       const Segment& sg = ps.segs[i];
       const Group& gr = c->groups[sg.group];
