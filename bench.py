@@ -121,7 +121,11 @@ def measured_peak():
 
 # =================================================================================================
 def run_ours(a):
-    os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    # rank 0 prints ONE JSON line on stdout: everything else that writes to fd 1 meanwhile (NCCL's version banner comes
+    # from C stdio when NCCL_DEBUG is set in the environment) is sent to stderr until the result is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -313,9 +317,13 @@ def run_ours(a):
     # ---- CPU baseline: the oracle's C restatement of the reference loop, rank 0, bounded sample -------
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(a, gt, y, cov, ctx, dev)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
     if rank == 0:
-        print(json.dumps(result))
+        print(json.dumps(result), flush=True)
     if world > 1:
+        os.dup2(2, 1)   # teardown chatter stays off stdout as well
         dist.destroy_process_group()
 
 
