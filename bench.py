@@ -180,36 +180,68 @@ def run_ours(a):
     n_kept, K, P = bt.n, bt.K, bt.P
     n_kept_all = [b.n for b in bts]
 
-    outs_all = []
-    go = (_lib.GroupOut * G)()
-    for g in range(G):
-        o = {"n": torch.empty(M, dtype=torch.int32, device=dev), "n_missing": torch.empty(M, dtype=torch.int32, device=dev),
-             "sum_x": torch.empty(M, dtype=torch.float64, device=dev)}
-        for f in STAT_FIELDS:
-            o[f] = torch.empty((M, bts[g].P), dtype=torch.float64, device=dev)
-        for k, v in o.items():
-            setattr(go[g], k, v.data_ptr())
-        go[g].log10_p = None
-        outs_all.append(o)
-    out = outs_all[0]
-    rows = torch.cat([out["sum_x"][:, None]] + [out[f] for f in STAT_FIELDS], dim=1)  # result row block for the gather
+    # Result buffers are double-buffered across steps: with N > 1 the all-gather of step i's rows runs on a side stream
+    # (its own communicator) underneath step i + 1's sweep.
+    n_buf = 2 if world > 1 else 1
+    outs_buf, go_buf = [], []
+    for _ in range(n_buf):
+        outs_all = []
+        go = (_lib.GroupOut * G)()
+        for g in range(G):
+            o = {"n": torch.empty(M, dtype=torch.int32, device=dev), "n_missing": torch.empty(M, dtype=torch.int32, device=dev),
+                 "sum_x": torch.empty(M, dtype=torch.float64, device=dev)}
+            for f in STAT_FIELDS:
+                o[f] = torch.empty((M, bts[g].P), dtype=torch.float64, device=dev)
+            for k, v in o.items():
+                setattr(go[g], k, v.data_ptr())
+            go[g].log10_p = None
+            outs_all.append(o)
+        outs_buf.append(outs_all)
+        go_buf.append(go)
+    width = 1 + len(STAT_FIELDS) * bts[0].P
     kid = _lib.KERNELS[a.kernel]
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    main = torch.cuda.current_stream(dev)
+    stream = main.cuda_stream
     ctx.check(lib.lrr_set_timing(ctx.handle, 1))
     launches0 = None
     sweep_ms = []
+    if world > 1:
+        side = torch.cuda.Stream(dev)
+        pg_side = dist.new_group(list(range(world)))   # collectives on `side` need their own communicator
+        rows = [torch.empty((M, width), dtype=torch.float64, device=dev) for _ in range(n_buf)]
+        gathered = [torch.empty((world * M, width), dtype=torch.float64, device=dev) for _ in range(n_buf)]
+        ev_rows = [torch.cuda.Event() for _ in range(n_buf)]
+        ev_done = [torch.cuda.Event() for _ in range(n_buf)]
+        used = [False] * n_buf
+        # what sc.broadcast ships per call (LR:74-78): every basis array of every group, as one flat message
+        basis_flat = torch.cat([x.contiguous().view(torch.uint8).reshape(-1) for bt_ in bts for x in bt_.tensors if x.numel()])
+    step_no = [0]
 
     def step(timed):
-        if world > 1:  # per-step basis broadcast + result gather (tiny next to the sweep)
-            for b in bts:
-                for x in b.tensors:
-                    dist.broadcast(x, 0)
-        ctx.check(lib.lrr_run(ctx.handle, gt.data.data_ptr(), gt.flags_ptr(), M, gt.stride, N, go, G, kid, stream))
+        b = step_no[0] % n_buf
+        step_no[0] += 1
+        out = outs_buf[b][0]
         if world > 1:
-            torch.cat([out["sum_x"][:, None]] + [out[f] for f in STAT_FIELDS], dim=1, out=rows)
-            hd.gather_rows(rows, counts=[M] * world)
+            if used[b]:
+                main.wait_event(ev_done[b])     # the gather that read this buffer two steps ago
+            dist.broadcast(basis_flat, 0)       # per-step basis broadcast, one message (35 MB at C2)
+        ctx.check(lib.lrr_run(ctx.handle, gt.data.data_ptr(), gt.flags_ptr(), M, gt.stride, N, go_buf[b], G, kid, stream))
+        if world > 1:
+            torch.cat([out["sum_x"][:, None]] + [out[f] for f in STAT_FIELDS], dim=1, out=rows[b])
+            ev_rows[b].record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_rows[b])
+                hd.gather_rows(rows[b], counts=[M] * world, out=gathered[b], group=pg_side)
+                ev_done[b].record(side)
+            used[b] = True
         if timed:
             sweep_ms.append(lib.lrr_last_sweep_ms(ctx.handle))
+
+    def drain():
+        if world > 1:   # every outstanding gather is inside the timed region
+            for b in range(n_buf):
+                if used[b]:
+                    main.wait_event(ev_done[b])
 
     def barrier():
         if world > 1:
@@ -218,6 +250,7 @@ def run_ours(a):
 
     for _ in range(a.warmup):
         step(False)
+    drain()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -230,6 +263,7 @@ def run_ours(a):
     e0.record()
     for _ in range(a.steps):
         step(True)
+    drain()
     e1.record()
     barrier()
     t1 = time.time()

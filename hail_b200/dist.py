@@ -73,12 +73,20 @@ def broadcast_bases(bases, device, src=0):
     return out
 
 
-def gather_rows(local_rows: torch.Tensor, counts=None):
-    """All-gather row blocks [m_r, W] (m_r may differ per rank) and concatenate them in rank order."""
+def gather_rows(local_rows: torch.Tensor, counts=None, out=None, group=None):
+    """All-gather row blocks [m_r, W] (m_r may differ per rank) and concatenate them in rank order.
+
+    Equal blocks (the sharded sweep's normal case) go straight into one [world * m, W] tensor (`out`, allocated when
+    None) with all_gather_into_tensor: no per-rank temporaries, no concatenation pass."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local_rows
     world = dist.get_world_size()
     dev = local_rows.device
+    if counts is not None and len(set(counts)) == 1 and counts[0] == local_rows.shape[0]:
+        if out is None:
+            out = torch.empty((world * local_rows.shape[0], local_rows.shape[1]), dtype=local_rows.dtype, device=dev)
+        dist.all_gather_into_tensor(out, local_rows.contiguous(), group=group)
+        return out
     if counts is None:
         c = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=dev)
         cs = [torch.zeros_like(c) for _ in range(world)]
