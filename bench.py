@@ -95,20 +95,20 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, smax, reasons = [], [], set()
+        sm, smax, reasons, watts = [], [], set(), []
         for ts, line in self.samples:
             if ts < t0 - 0.05 or ts > t1 + 0.15:
                 continue
             f = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
+                sm.append(float(f[1])); smax.append(float(f[2])); watts.append(float(f[3]))
             except Exception:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w": float(np.median(watts)) if watts else None}
 
 
 def measured_peak():

@@ -58,7 +58,13 @@ constexpr int MAX_GSTAGES = 10;
 constexpr int NB = 6;                  // basis-panel ring depth the MMA fast path is unrolled for
 constexpr int MAX_BSTAGES = NB;
 constexpr int SF_COLS = 16;            // scale-factor columns (A: first 8, B: last 8), all bytes 0x7F
-constexpr int DIG_Y = 13, DIG_Q = 9;   // base-13 digits per phenotype / covariate column
+#ifndef LRR_TC4_DIG_Y
+#define LRR_TC4_DIG_Y 13
+#endif
+#ifndef LRR_TC4_DIG_Q
+#define LRR_TC4_DIG_Q 9
+#endif
+constexpr int DIG_Y = LRR_TC4_DIG_Y, DIG_Q = LRR_TC4_DIG_Q;   // base-13 digits per phenotype / covariate column
 constexpr int PASS_COLS = 112;         // digit columns per sweep: 2 * 112 accumulators + 16 + ring of 4 * 64 <= 512
 constexpr int UNROLL = 12;             // chunks per unrolled block of the MMA fast path (lcm of NB and NU)
 
