@@ -330,18 +330,24 @@ def run_ours(a):
         for _ in range(2):   # first calls allocate the device arena / page-locked result buffer and load kernels
             e2e_step()
         barrier()
-        t_e = time.time()
-        reps = max(2, min(a.steps, 3))
-        for _ in range(reps):
+        reps = 5
+        times = []
+        for _ in range(reps):     # each repetition is timed on its own: barrier, wall clock around the public call, barrier
+            t_e = time.time()
             ht = e2e_step()
-        barrier()
-        dt = (time.time() - t_e) / reps
-        tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+            barrier()
+            times.append(time.time() - t_e)
+        # the host link is shared with other tenants of the box: single repetitions are occasionally 2x slower.  The
+        # reported value uses the MEDIAN repetition; the mean is kept next to it.
+        tt = torch.tensor(times, dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dt = float(tmax.item())
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)   # slowest rank, repetition by repetition
+        times = [float(v) for v in tt.tolist()]
+        dt = float(np.median(times))
+        dt_mean = float(np.mean(times))
         d2h = Me * (4 + 4 + 8 + 5 * 8 * P)
-        result["e2e"] = {"value": world * Me * float(n_kept) / dt, "unit": "genotypes/s",
+        result["e2e"] = {"value": world * Me * float(n_kept) / dt, "unit": "genotypes/s", "reps": reps,
+                         "mean_value": world * Me * float(n_kept) / dt_mean, "rep_seconds": [round(t, 4) for t in times],
                          "h2d_bytes_per_step": int(Me * bed_stride + 8 * n_kept * (K + P)), "d2h_bytes_per_step": int(d2h),
                          "sample": f"{Me} variants x {N} samples per GPU per step: page-locked host .bed bytes -> "
                                    "HostBedGenotypes -> linear_regression_rows (block-streamed H2D overlapped with the "
