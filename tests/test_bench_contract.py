@@ -1,0 +1,38 @@
+"""The bench line committed under profiles/ carries every key the measurement contract names (CPU test)."""
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_c2_final.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "gpu_launches", "roofline", "clocks", "e2e", "cpu_baseline"):
+        assert k in d, k
+    assert d["unit"] == "genotypes/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["config"]["workload"].startswith("C2") and d["vs_baseline"] is None
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert r["traffic"] is None or r["traffic"] >= r["algorithmic_bytes_per_launch"]
+    # achieved = algorithmic bytes / the sweep kernel's own duration
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["kernel_ms"] / 1e3) / 1e9) < 1.0
+    # value = genotypes of one step / its duration
+    assert abs(d["value"] - 400000 * 1e6 / (d["ms_per_step"] / 1e3)) / d["value"] < 1e-6
+    assert d["gpu_launches"] >= d["steps"]
+    e = d["e2e"]
+    assert e["unit"] == "genotypes/s" and e["h2d_bytes_per_step"] > 1e9 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    for k in ("sm_mhz", "sm_max_mhz", "reasons"):
+        assert k in d["clocks"]
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_algorithmic_bytes_formula_matches_survey():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    # M ceil(N/4) + M G (4 + 8 + 40 P) + G 8 (nK + nP + KP + P)
+    assert b.algorithmic_bytes(1_000_000, 400_000, 1, 10, 1, 400_000) == 100_087_200_088
