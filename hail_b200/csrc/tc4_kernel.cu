@@ -33,6 +33,21 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+// Timing ablations (LRR_ABL_BITS / LRR_ABL_STREAM / LRR_ABL_CONTIG, see Params) are compiled in only with
+// -DLRR_TC4_ABLATIONS=1 (scratch/sustain.sh, scratch/quick.sh); the shipped kernel carries none of their tests.
+#ifndef LRR_TC4_ABLATIONS
+#define LRR_TC4_ABLATIONS 0
+#endif
+#if LRR_TC4_ABLATIONS
+#define ABL(bit) (p.abl & (bit))
+#define ABL_STREAM() (p.abl_stream)
+#define ABL_CONTIG() (p.abl_contig)
+#else
+#define ABL(bit) (0)
+#define ABL_STREAM() (0)
+#define ABL_CONTIG() (0)
+#endif
+
 namespace lrr {
 namespace tc4 {
 
@@ -257,7 +272,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         const uint32_t sbase = smem0 + gs * p.gstage_bytes;
         if (elect_one()) {
           mbar_arrive_expect_tx(GFULL(gs), (uint32_t)(GENO_BYTES + p.mask_bytes));
-          if (p.abl_contig) tma_load_2d(&geno_map, GFULL(gs), sbase, 0, (tile * p.n_chunks + ch) * TILE_M);
+          if (ABL_CONTIG()) tma_load_2d(&geno_map, GFULL(gs), sbase, 0, (tile * p.n_chunks + ch) * TILE_M);
           else tma_load_2d(&geno_map, GFULL(gs), sbase, ch * 128, tile * TILE_M);
           if (p.mask_bytes) {
             for (int g = 0; g < n_groups; ++g)
@@ -268,9 +283,9 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         if (++gs == p.n_gstages) { gs = 0; g_phase ^= 1; }
       }
     }
-  } else if (warp == WARP_TMA_B && p.abl_stream) {
+  } else if (warp == WARP_TMA_B && ABL_STREAM()) {
     // (ablation: no basis panels)
-  } else if (warp == WARP_MMA && p.abl_stream) {
+  } else if (warp == WARP_MMA && ABL_STREAM()) {
     // (ablation: no MMAs)
   } else if (warp == WARP_TMA_B) {
     // ============================== basis-panel producer ==============================
@@ -281,7 +296,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         mbar_wait(BEMPTY(bs), b_phase ^ 1);
         const uint32_t sbase = bring0 + bs * p.bstage_bytes;
         if (elect_one()) {
-          if (p.abl & 4) {
+          if ABL(4) {
             if (cta_rank == 0) mbar_arrive(BFULL(bs));
           } else if (CS == 1) {
             mbar_arrive_expect_tx(BFULL(bs), (uint32_t)(PANELS * panel_bytes));
@@ -343,7 +358,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         tc_fence_after();
         const uint64_t bd = desc0 + (uint64_t)(bs * stage_d);
         if (elect_one()) {
-          if (p.abl & 2) {
+          if ABL(2) {
           } else if (two_plane) issue(TrueTag{}, ru, bd, ch ? 1u : 0u); else issue(FalseTag{}, ru, bd, ch ? 1u : 0u);
           commit(AEMPTY(ru));
           commit(BEMPTY(bs));
@@ -370,7 +385,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
             tc_fence_after();
             const uint64_t bd = desc0 + (uint64_t)(b * stage_d);
             if (elect_one()) {
-              if (!(p.abl & 2)) issue(tp_tag, u, bd, k ? 1u : (ch ? 1u : 0u));
+              if (!ABL(2)) issue(tp_tag, u, bd, k ? 1u : (ch ? 1u : 0u));
               commit(AEMPTY(u));
               commit(BEMPTY(b));
             }
@@ -455,7 +470,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         uint32_t rc[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (p.abl & 8) {
+          if ABL(8) {
             rc[2 * i + 0] = w[i];
             rc[2 * i + 1] = w[i];
           } else {
@@ -466,7 +481,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         // exact counts for x.x = n1 + 4 n2 (see tc_kernel.cu)
 #pragma unroll
         for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
-          if ((NG || g < n_groups) && !(p.abl & 16)) {
+          if ((NG || g < n_groups) && !ABL(16)) {
             int acc = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -482,7 +497,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(gbar + 8u * MAX_GSTAGES);   // genotype stage back to the TMA producer
-        if (pend_u >= 0 && !(p.abl & 32)) {   // retire the previous chunk's TMEM store behind this chunk's arithmetic
+        if (pend_u >= 0 && !ABL(32)) {   // retire the previous chunk's TMEM store behind this chunk's arithmetic
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
@@ -491,7 +506,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         mbar_wait(AEMPTY(u), ((empty_par >> u) & 1u) ^ 1u);
         empty_par ^= 1u << u;
         tc_fence_after();
-        if (!(p.abl & 1)) tmem_st16(a_slot + u * UNIT_COLS, rc);
+        if (!ABL(1)) tmem_st16(a_slot + u * UNIT_COLS, rc);
         else if ((rc[0] ^ rc[5] ^ rc[10] ^ rc[15]) == 0x12345678u) n2[0] += 1;   // keep the arithmetic alive
         if (TP) {
           // missing-indicator plane: nibble 0001 (= 0.5) where the call is code 3
@@ -503,7 +518,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
           }
           tmem_st16(a_slot + (u + 1) * UNIT_COLS, rc);
         }
-        if (p.abl & 32) {   // experiment: publish the store at once instead of behind the next chunk's arithmetic
+        if ABL(32) {   // experiment: publish the store at once instead of behind the next chunk's arithmetic
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
@@ -550,7 +565,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         }
       }
       for (; ch < p.n_chunks; ++ch) generic_chunk();
-      if (pend >= 0 && !(p.abl & 32)) {   // flush the last chunk of the tile
+      if (pend >= 0 && !ABL(32)) {   // flush the last chunk of the tile
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -558,13 +573,13 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
       }
     };
 
-    if (p.abl_stream) {
+    if (ABL_STREAM()) {
       // ablation: consume the genotype stages and nothing else (abl_stream == 2: also LDS the thread's 32 bytes)
       uint32_t sink = 0;
       for (int tile = first_tile; tile < tile_end; tile += tile_step)
         for (int ch = 0; ch < p.n_chunks; ++ch) {
           mbar_wait(gbar, g_phase);
-          if (p.abl_stream == 2) { const uint4 w0 = lds128(gaddr + ld0); const uint4 w1 = lds128(gaddr + ld1); sink ^= w0.x ^ w1.w; }
+          if (ABL_STREAM() == 2) { const uint4 w0 = lds128(gaddr + ld0); const uint4 w1 = lds128(gaddr + ld1); sink ^= w0.x ^ w1.w; }
           __syncwarp();
           if (lane == 0) mbar_arrive(gbar + 8u * MAX_GSTAGES);
           gaddr += p.gstage_bytes;
