@@ -8,15 +8,16 @@
 // -- exactly, no rounding and no dependence on summation order -- and the per-variant epilogue recombines the
 // S exact integers in float64.  With S = 6 the only error is the 2^-47 quantisation of B.
 //
-// Dataflow per CTA (persistent over variant tiles), one CTA per SM:
-//   TMA warp      cp.async.bulk.tensor: packed genotype tile [128 variants x 512 samples] (16 KB, 128B swizzle)
-//                 + the matching basis panels [ncols x 512 samples] int8 -> a ring of shared-memory stages
-//   unpack warps  (8) LDS.128 of the thread's own variant row, 2-bit -> uint8 with shift/mask, exact popcount
-//                 of hom-alt calls, tcgen05.st of the uint8 row into a TMEM ring (A operand lives in TMEM)
-//   MMA warp      one thread issues tcgen05.mma.kind::i8 (M=128, N=ncols, K=32) with A from TMEM, B from the
-//                 swizzled shared-memory panels, D (int32) in TMEM; tcgen05.commit releases ring slots / stages
+// Dataflow per CTA (persistent over variant tiles; CTA pairs with tcgen05.mma.cta_group::2, see the kernel's comment):
+//   TMA warps     cp.async.bulk.tensor: packed genotype tile [128 variants x 512 samples] (16 KB, 128B swizzle) into
+//                 a deep ring; the matching basis panels [this CTA's half of ncols x 512 samples] int8 into a 6-stage ring
+//   unpack warps  (16) LDS.128 of the thread's own variant row, 2-bit -> uint8 with shift/mask, exact popcount,
+//                 tcgen05.st of the uint8 row into a TMEM ring (the A operand lives in TMEM)
+//   MMA warp      one elected lane issues tcgen05.mma.kind::i8 (M=128 or 256, N=ncols, K=32) with A from TMEM, B from
+//                 the swizzled shared-memory panels, D (int32) in TMEM; tcgen05.commit releases ring slots / stages
 //   epilogue      (unpack warps 0-3) tcgen05.ld the int32 accumulators, recombine digits, mean-impute correction
 //                 from the missing-indicator plane, write counts + float64 dot products for the stats epilogue
+// This kernel is the multi-pass path (chained groups, many phenotypes); tc4_kernel.cu is the single-pass 4-bit variant.
 //
 // Missing calls (RegressionUtils.scala:16-58 mean imputation): code 3.  Plane "c" carries the raw code
 // (0..3), plane "m" the indicator [code == 3]; sum_j B (x0 + mean * m) = (Dc - 3 Dm) + mean * Dm.  Tiles whose
@@ -316,7 +317,7 @@ struct FalseTag { static constexpr bool value = false; };
 struct Barriers {
   uint64_t gfull[MAX_GSTAGES];   // genotype stage filled by TMA
   uint64_t gempty[MAX_GSTAGES];  // genotype stage read out by the 16 unpack warps
-  uint64_t bfull[MAX_BSTAGES];   // basis-panel stage filled by TMA (possibly multicast from cluster peers)
+  uint64_t bfull[MAX_BSTAGES];   // basis-panel stage filled by TMA (both CTAs of a pair complete on the leader's)
   uint64_t bempty[MAX_BSTAGES];  // basis-panel stage consumed (MMA commit of every CTA in the cluster)
   uint64_t a_full[MAX_RING];     // A ring slot written (4 quarter-warps)
   uint64_t a_empty[MAX_RING];    // A ring slot consumed (MMA commit)
