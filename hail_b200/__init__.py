@@ -9,7 +9,7 @@ from .statgen import FatalError, linear_regression_rows, _get_regression_row_fie
 
 
 def __getattr__(name):  # lazy: these import torch-side helpers
-    if name in ("PackedGenotypes", "HostBedGenotypes", "packed_stride"):
+    if name in ("PackedGenotypes", "HostBedGenotypes", "DenseDosage", "packed_stride"):
         from . import genotypes
         return getattr(genotypes, name)
     if name in ("import_plink", "export_plink", "import_fam"):

@@ -67,6 +67,8 @@ SIGNATURES = {
     "lrr_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                ctypes.c_int64, ctypes.POINTER(GroupOut), ctypes.c_int32, ctypes.c_int32,
                                ctypes.c_void_p]),
+    "lrr_run_dense": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                     ctypes.POINTER(GroupOut), ctypes.c_int32, ctypes.c_void_p]),
     "lrr_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "lrr_last_kernel": (ctypes.c_int, [ctypes.c_void_p]),
     "lrr_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

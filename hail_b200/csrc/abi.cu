@@ -30,6 +30,7 @@ void free_group(Group& g) {
   cudaFree(g.d_mask);
   cudaFree(g.d_bq);
   cudaFree(g.d_colscale);
+  cudaFree(g.d_basis_t);
   g = Group();
 }
 
@@ -64,7 +65,7 @@ int ensure_workspace(Ctx* c, int64_t M) {
   c->dots_offset.resize(G);
   for (size_t g = 0; g < G; ++g) {
     c->dots_offset[g] = total_c * want;
-    total_c += c->groups[g].C;
+    total_c += c->groups[g].C + 2;   // + 2: column sum and centred squares of the dense-dosage sweep
   }
   LRR_CUDA(c, cudaMalloc(&c->d_counts, sizeof(int32_t) * 4 * (size_t)want * (G ? G : 1)));
   LRR_CUDA(c, cudaMalloc(&c->d_dots, sizeof(double) * (size_t)want * (size_t)(total_c ? total_c : 1)));
@@ -164,6 +165,7 @@ void lrr_destroy(lrr_ctx* ctx) {
   tc_release(c);
   tc4_release(c);
   cudaFree(c->arena);
+  cudaFree(c->d_nanmask);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   delete c;
@@ -376,6 +378,26 @@ int lrr_set_score_model(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_
                              K * K, K + 1))
     return r;
   c->groups.back().score = 1;
+  return LRR_OK;
+}
+
+int lrr_run_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t ldx, int64_t n_samples_total,
+                  const lrr_group_out* outs, int32_t n_outs, void* stream) {
+  CTX_PROLOGUE;
+  if (c->groups.empty()) return fail(c, LRR_ESTATE, "lrr_run_dense: no groups (call lrr_add_group)");
+  if (c->groups[0].score) return fail(c, LRR_ESTATE, "lrr_run_dense: the context holds a logistic score model");
+  for (const Group& g : c->groups)
+    if (g.weighted) return fail(c, LRR_EINVAL, "lrr_run_dense: weighted groups are not supported on dense dosages");
+  if (n_outs != (int32_t)c->groups.size() || !outs) return fail(c, LRR_EINVAL, "lrr_run_dense: need one lrr_group_out per group");
+  if (n_variants < 0 || ldx < n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_dense: bad shape (ldx >= n_samples_total)");
+  if (n_samples_total != c->n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_dense: n_samples_total differs from the groups'");
+  if (n_variants == 0) return LRR_OK;
+  if (!d_x) return fail(c, LRR_EINVAL, "lrr_run_dense: d_x is NULL");
+  if (int r = ensure_workspace(c, n_variants)) return r;
+  if (int r = launch_dense_sweep(c, d_x, n_variants, ldx, st)) return r;
+  c->last_kernel = LRR_KERNEL_FP64;
+  for (size_t g = 0; g < c->groups.size(); ++g)
+    if (int r = launch_stats_epilogue(c, (int)g, n_variants, outs[g], st, true)) return r;
   return LRR_OK;
 }
 

@@ -38,6 +38,9 @@ struct Group {
   double* d_colscale = nullptr;  // [C] value of one unit of the lowest digit
   int ncols_pad = 0;
   int n_slices = 0;
+  // dense-dosage path (filled lazily by launch_dense_sweep)
+  double* d_basis_t = nullptr;   // [ns_pad][C] sample-major copy of d_basis (+ one 64-bit scratch word)
+  int64_t first_sample = 0;      // lowest sample index of the group (pivot of the shifted sums)
 };
 
 struct Ctx {
@@ -63,6 +66,9 @@ struct Ctx {
   void* arena = nullptr;
   size_t arena_bytes = 0;
   int streams_alive = 0;
+  // dense-dosage path: one bit per (variant, sample) "missing and in the group" (dense_kernel.cu), grow-only
+  void* d_nanmask = nullptr;
+  size_t nanmask_bytes = 0;
 };
 
 // make `dev` current for the lifetime of the guard
@@ -96,6 +102,7 @@ int launch_unpack_bed(Ctx*, const uint8_t*, int64_t, int64_t, int64_t, uint8_t*,
 int launch_bn_fill(Ctx*, const uint32_t*, int, const uint8_t*, int64_t, int64_t, int64_t, uint64_t, uint8_t*, int64_t,
                    uint8_t*, cudaStream_t);
 int launch_fp64_sweep(Ctx*, const uint8_t* d_packed, int64_t M, int64_t stride, cudaStream_t);
+int launch_dense_sweep(Ctx*, const double* d_x, int64_t M, int64_t ldx, cudaStream_t);
 int launch_tc_sweep(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, cudaStream_t);
 bool tc_supported(Ctx*, bool may_have_missing);
 void tc_invalidate(Ctx*);
@@ -104,7 +111,7 @@ int launch_tc4_sweep(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, 
 bool tc4_supported(Ctx*, bool single_pass_only);
 void tc4_invalidate(Ctx*);
 void tc4_release(Ctx*);
-int launch_stats_epilogue(Ctx*, int g, int64_t M, const lrr_group_out& out, cudaStream_t);
+int launch_stats_epilogue(Ctx*, int g, int64_t M, const lrr_group_out& out, cudaStream_t, bool dense = false);
 int run_rows(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, int64_t n_samples_total,
              const lrr_group_out* outs, int32_t n_outs, int32_t kernel, cudaStream_t);
 int launch_student_t(Ctx*, const double*, int64_t, double, double*, double*, cudaStream_t);

@@ -78,6 +78,8 @@ struct StatModel {
   const double* qty;      // [K][P]
   const double* yyp;      // [P]
   int n, K, Kd, P, C, has_intercept, d, weighted;
+  int dense;              // dense-dosage sweep: dv has C + 2 entries, dv[C] = sum of the defined entries, dv[C + 1] =
+                          // their centred sum of squares (= that of the mean-imputed column)
   double lbeta;
   lrr_group_out out;
 };
@@ -87,19 +89,21 @@ __device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n
   const double dRec = 1.0 / (double)a.d;  // LR:51
   const int64_t idx = v * a.P + p;
   const double nv = (double)(a.n - nm);
-  const double S = (double)(n1 + 2 * n2);
+  const double S = a.dense ? dv[a.C] : (double)(n1 + 2 * n2);
   const double xx_int = (double)(n1 + 4 * n2);
   const double mean = S / nv;                        // RU:52
   // weighted groups (statgen.py:636-660): the column sum and x.x of the sqrt(w)-scaled imputed x are dot products
   const double sum_x = a.weighted ? dv[a.Kd + a.P] : S + (double)nm * mean;        // LR:136
-  const double xx_imp = a.weighted ? dv[a.Kd + a.P + 1] : xx_int + (double)nm * mean * mean;
+  const double xxc = a.dense ? dv[a.C + 1] : 0.0;   // dense: sum of (x - mean)^2 over the imputed column
+  const double xx_imp = a.dense ? xxc + sum_x * sum_x / (double)a.n
+                                : a.weighted ? dv[a.Kd + a.P + 1] : xx_int + (double)nm * mean * mean;
 
   double qq = 0.0;
   for (int c = 0; c < a.Kd; ++c) qq += dv[c] * dv[c];
   double xxp;  // x.x - qtx.qtx  (LR:141-142)
   if (a.has_intercept) {
     // constant column handled exactly: x.x - (sum_x)^2/n == xx_int - S^2/nv for the mean-imputed column
-    xxp = (xx_int - S * S / nv) - qq;
+    xxp = (a.dense ? xxc : xx_int - S * S / nv) - qq;
   } else {
     xxp = xx_imp - qq;
   }
@@ -148,6 +152,7 @@ inline StatModel stat_model_of(const Group& G, const lrr_group_out& out) {
   a.has_intercept = G.has_intercept;
   a.d = G.d;
   a.weighted = G.weighted;
+  a.dense = 0;
   a.lbeta = G.lbeta;
   a.out = out;
   return a;

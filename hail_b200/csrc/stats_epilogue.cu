@@ -21,7 +21,7 @@ __global__ void stats_epilogue_kernel(EpiArgs a) {
     const int64_t v = idx / a.model.P;
     const int p = (int)(idx - v * a.model.P);
     const int4 cnt = reinterpret_cast<const int4*>(a.counts)[v];
-    variant_stats(a.model, v, p, cnt.x, cnt.y, cnt.z, a.dots + v * a.model.C);
+    variant_stats(a.model, v, p, cnt.x, cnt.y, cnt.z, a.dots + v * (a.model.C + (a.model.dense ? 2 : 0)));
   }
 }
 
@@ -83,7 +83,7 @@ double log_beta_half(double a) {
   return 0.5 * log(3.14159265358979323846) - 0.5 * log(a) + series;
 }
 
-int launch_stats_epilogue(Ctx* c, int g, int64_t M, const lrr_group_out& out, cudaStream_t st) {
+int launch_stats_epilogue(Ctx* c, int g, int64_t M, const lrr_group_out& out, cudaStream_t st, bool dense) {
   if (M == 0) return LRR_OK;
   const Group& G = c->groups[g];
   EpiArgs a;
@@ -91,6 +91,7 @@ int launch_stats_epilogue(Ctx* c, int g, int64_t M, const lrr_group_out& out, cu
   a.dots = c->d_dots + c->dots_offset[g];
   a.M = M;
   a.model = stat_model_of(G, out);
+  a.model.dense = dense ? 1 : 0;
   const int64_t total = M * G.P;
   int64_t grid = (total + 127) / 128;
   if (grid > (int64_t)c->sm_count * 32) grid = (int64_t)c->sm_count * 32;

@@ -171,6 +171,32 @@ class HostBedGenotypes:
         return self.to_device().to_dosage()
 
 
+class DenseDosage:
+    """A dense float64 entry field on the device: [n_variants, n_samples], NaN = missing.
+
+    The general form of `x` in `linear_regression_rows` (any entry-indexed float64 expression, statgen.py:229, 391):
+    PL / GP dosages, imputed dosages, ...  8 bytes per entry instead of 0.25: use PackedGenotypes for hard calls.
+    """
+
+    def __init__(self, values, device=0):
+        dev = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        t = torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64) if isinstance(values, np.ndarray) else values)
+        assert t.dim() == 2
+        self.data = t.to(device=dev, dtype=torch.float64).contiguous()
+        self.n_variants, self.n_samples = int(t.shape[0]), int(t.shape[1])
+
+    @property
+    def device(self):
+        return self.data.device
+
+    @property
+    def nbytes(self):
+        return self.data.numel() * 8
+
+    def to_dosage(self) -> np.ndarray:
+        return self.data.cpu().numpy()
+
+
 def packed_stride(n_samples: int) -> int:
     return int(_lib.load().lrr_packed_stride(int(n_samples)))
 

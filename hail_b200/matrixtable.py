@@ -96,7 +96,7 @@ class EntryExpression(Expression):
 
     def __init__(self, source, kind):
         self.source = source
-        self.kind = kind  # 'n_alt_alleles'
+        self.kind = kind  # 'n_alt_alleles' (packed calls) or 'dosage' (dense float64 entries)
 
 
 class CallExpression(Expression):
@@ -145,7 +145,11 @@ class MatrixTable:
 
     def __getitem__(self, item):
         if item == "GT":
+            if type(self.genotypes).__name__ == "DenseDosage":
+                raise ExpressionException("this MatrixTable holds a dense dosage entry field `x`, not calls")
             return CallExpression(self)
+        if item in ("x", "dosage") and type(self.genotypes).__name__ == "DenseDosage":
+            return EntryExpression(self, "dosage")   # a float64 entry field (statgen.py:229: any float64 x)
         if item in self._entry_aliases:
             return EntryExpression(self, self._entry_aliases[item])
         if item in self._cols:

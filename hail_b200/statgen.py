@@ -332,6 +332,29 @@ class _HostStream:
             self.handle = ctypes.c_void_p()
 
 
+def _run_device_dense(dosage, bases):
+    """lrr_run_dense over a DenseDosage.  Returns per-group dicts of torch CUDA tensors."""
+    dev = dosage.device
+    ctx = _lib.context(dev.index)
+    M, N = dosage.n_variants, dosage.n_samples
+    with torch.cuda.device(dev):
+        _push_groups(ctx, N, bases)
+        outs = []
+        arr = (_lib.GroupOut * len(bases))()
+        for g, b in enumerate(bases):
+            o = {"n": torch.empty(M, dtype=torch.int32, device=dev), "n_missing": torch.empty(M, dtype=torch.int32, device=dev),
+                 "sum_x": torch.empty(M, dtype=torch.float64, device=dev)}
+            for f in STAT_FIELDS:
+                o[f] = torch.empty((M, b.P), dtype=torch.float64, device=dev)
+            for k, v in o.items():
+                setattr(arr[g], k, v.data_ptr())
+            arr[g].log10_p = None
+            outs.append(o)
+        ctx.check(ctx.lib.lrr_run_dense(ctx.handle, dosage.data.data_ptr(), M, N, N, arr, len(bases),
+                                        torch.cuda.current_stream(dev).cuda_stream))
+    return outs
+
+
 def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, weights=None,
                            _kernel="auto", _log10_p=False, _stream_block=0, _stream_depth=0) -> Table:
     """For each row, test an input variable for association with response variables using linear regression.
@@ -378,9 +401,19 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
 
     n_cols = mt.count_cols()
     cov = np.column_stack(cov_vals) if cov_vals else np.empty((n_cols, 0))
-    from .genotypes import HostBedGenotypes
+    from .genotypes import DenseDosage, HostBedGenotypes
 
-    if isinstance(mt.genotypes, HostBedGenotypes):
+    if isinstance(mt.genotypes, DenseDosage) or x.kind == "dosage":
+        if not isinstance(mt.genotypes, DenseDosage) or x.kind != "dosage":
+            raise ExpressionException("'linear_regression_rows/x': a dense dosage field needs a DenseDosage entry matrix")
+        if weights is not None:
+            raise NotImplementedError("linear_regression_rows: weights on dense dosages")
+        bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None)
+                 for i, g in enumerate(y_vals)]
+        outs = _run_device_dense(mt.genotypes, bases)
+        torch.cuda.synchronize(mt.genotypes.device)
+        host = [{k: v.cpu().numpy() for k, v in o.items()} for o in outs]
+    elif isinstance(mt.genotypes, HostBedGenotypes):
         # host-resident .bed rows: stream them through the device; the copies start before the prologue
         stream = _HostStream(mt.genotypes, _stream_block, _stream_depth)
         try:

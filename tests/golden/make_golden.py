@@ -6,9 +6,9 @@ Run in the authoring container only (reads /root/reference, which does not exist
 
 Outputs (committed):
   regression_linear.json   the 8-sample x 10-variant R-lm() golden case
-                           (hail/hail/test/resources/regressionLinear.{vcf,pheno,cov,fam};
+                           (hail/hail/test/resources/regressionLinear.{vcf,gen,sample,pheno,cov,fam};
                            expected values transcribed from
-                           hail/python/test/hail/methods/test_statgen.py:223-234, 262-284, 303-316, 380-424)
+                           hail/python/test/hail/methods/test_statgen.py:223-234, 262-284, 303-316, 334-348, 380-424)
   pt_known_answers.json    hail/python/test/hail/expr/test_expr.py:3564-3568
   fastlmm.npz              PLINK parity data (fastlmmTest.bed/.fam + fastlmmPheno.txt + fastlmmCov.txt)
   bn_4x1024.npz            balding-nichols-1024-variants-4-samples-3-populations.bed (1 % missing)
@@ -51,6 +51,21 @@ def main():
             gt.append(g_row)
             pl.append(pl_row)
 
+    # ---- regressionLinear.gen: GP triples in .sample order (import_gen, methods/impex.py:1354-1490: the array is
+    # missing when |sum - 1| > tolerance = 0.2); gp_dosage = GP[1] + 2 GP[2] (expr/functions.py:1470-1488)
+    with open(f"{RES}/regressionLinear.sample") as f:
+        gen_samples = [line.split()[0] for line in f.read().splitlines()[2:] if line.strip()]
+    gp = []
+    with open(f"{RES}/regressionLinear.gen") as f:
+        for line in f:
+            vals = [float(v) for v in line.split()[6:]]
+            row = []
+            for i in range(0, len(vals), 3):
+                t = vals[i:i + 3]
+                row.append(None if abs(sum(t) - 1.0) > 0.2 else t)
+            gp.append(row)
+    assert gen_samples == samples and len(gp) == len(gt) and all(len(r) == len(samples) for r in gp)
+
     _, ph_rows = read_table(f"{RES}/regressionLinear.pheno")
     pheno = {r[0]: float(r[1]) for r in ph_rows}
     _, cv_rows = read_table(f"{RES}/regressionLinear.cov")
@@ -66,6 +81,7 @@ def main():
         "samples": samples,
         "gt_n_alt_alleles": gt,  # [10 variants][8 samples], None = missing call
         "pl": pl,
+        "gp": gp,  # regressionLinear.gen, None = missing (probabilities do not sum to 1 within 0.2)
         "pheno_table": pheno,  # keyed by sample id; '0' means missing under missing='0' (TS:249-251)
         "cov_table": cov,
         "fam_table": fam,
@@ -85,6 +101,13 @@ def main():
                 "1": {"beta": -0.29166985, "standard_error": 1.2996510, "t_stat": -0.22442167, "p_value": 0.84327106},
                 "2": {"beta": -0.5499320, "standard_error": 0.3401110, "t_stat": -1.616919, "p_value": 0.24728705},
                 "3": {"beta": 1.09536219, "standard_error": 0.6901002, "t_stat": 1.5872510, "p_value": 0.2533675},
+            },
+            # TS:334-348  x = gp_dosage(GP) from regressionLinear.gen: the same numbers, places=4 on beta / standard_error
+            "gp_dosage": {
+                "1": {"beta": -0.29166985, "standard_error": 1.2996510, "t_stat": -0.22442167, "p_value": 0.84327106},
+                "2": {"beta": -0.5499320, "standard_error": 0.3401110, "t_stat": -1.616919, "p_value": 0.24728705},
+                "3": {"beta": 1.09536219, "standard_error": 0.6901002, "t_stat": 1.5872510, "p_value": 0.2533675},
+                "nan_se": [6],
             },
         },
     }

@@ -52,6 +52,11 @@ def pl_dosage(doc):
     return np.array(out)
 
 
+def gp_dosage(doc):
+    """hl.gp_dosage (expr/functions.py:1470-1488): GP[1] + 2 GP[2]; missing where import_gen drops the triple."""
+    return np.array([[np.nan if t is None else t[1] + 2.0 * t[2] for t in row] for row in doc["gp"]])
+
+
 def assert_fields_close(got, want, rel=1e-6, rel_p=1e-5, t_floor=0.0, ctx=""):
     """Parity gate: n exact; sum_x / y_transpose_x / beta / standard_error / t_stat within `rel`
     (the reference's own `_same` comparator, oracle.d_eq); p_value within `rel_p`.

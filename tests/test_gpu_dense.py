@@ -1,0 +1,142 @@
+"""GPU parity of the dense float64 `x` path (lrr_run_dense): `x` may be any entry-indexed float64 expression in the
+reference (methods/statgen.py:229, 391), not only GT.n_alt_alleles() -- PL / GP dosages, imputed DS fields.
+
+Mirrors test_statgen.py:286-316 (pl_dosage), :318-348 (gp_dosage), :350-364 (DS vs GT equivalence); the rest compares
+the CUDA path with the CPU oracle on seeded inputs.
+"""
+import numpy as np
+import pytest
+
+from oracle import linreg_oracle as O
+from tests.helpers import assert_fields_close, gp_dosage, load_regression_linear, pl_dosage
+
+pytestmark = pytest.mark.gpu
+
+
+def _hb():
+    import hail_b200 as hb
+    return hb
+
+
+def _dense_mt(x, **cols):
+    hb = _hb()
+    rows = {"locus": np.array([("1", i + 1) for i in range(x.shape[0])], dtype=object),
+            "alleles": np.array([("C", "T")] * x.shape[0], dtype=object)}
+    return hb.MatrixTable(hb.DenseDosage(x), rows=rows, cols=cols, row_key=("locus", "alleles"))
+
+
+def _as_dict(ht):
+    d = {"n": ht.n}
+    for f in ("sum_x", "y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+        v = np.asarray(ht[f])
+        d[f] = v if (v.ndim == 2 or f == "sum_x") else v[:, None]
+    return d
+
+
+@pytest.mark.parametrize("which", ["pl_dosage", "gp_dosage"])
+def test_reference_golden_dosage(which):  # TS:286-316, TS:318-348
+    hb = _hb()
+    x, y, cov, doc = load_regression_linear()
+    dos = pl_dosage(doc) if which == "pl_dosage" else gp_dosage(doc)
+    mt = _dense_mt(dos, pheno=y, Cov1=cov[:, 0], Cov2=cov[:, 1])
+    ht = hb.linear_regression_rows(y=mt.pheno, x=mt.x, covariates=[1.0, mt.Cov1, mt.Cov2])
+    exp = doc["expected"][which]
+    assert (ht.n == 6).all()
+    for pos in ("1", "2", "3"):
+        for f, v in exp[pos].items():
+            tol = 5e-5 if (which == "gp_dosage" and f in ("beta", "standard_error")) else 5e-7
+            assert abs(ht[f][int(pos) - 1] - v) < tol, (pos, f, ht[f][int(pos) - 1], v)
+    assert np.isnan(ht.standard_error[5])     # TS:348
+    want = O.linreg_group(dos, y[:, None], np.column_stack([np.ones(8), cov]))
+    got = _as_dict(ht)
+    good = slice(0, 5)   # rows 6-10 are degenerate (x in the covariate span): roundoff noise in the reference too
+    assert_fields_close({k: v[good] for k, v in got.items()}, {k: v[good] for k, v in want.items() if k != "_d"},
+                        t_floor=1e-9)
+
+
+def test_ds_equals_gt():  # TS:350-364: a dosage field holding the hard calls gives the hard-call results
+    hb = _hb()
+    N, M = 1500, 200
+    mt = hb.balding_nichols_model(3, N, M, missing_rate=0.03, seed=21)
+    rng = np.random.default_rng(4)
+    y = rng.normal(size=N)
+    dos = mt.genotypes.to_dosage().astype(np.float64)
+    dos[dos < 0] = np.nan
+    mt = mt.annotate_cols(y=y)
+    gt = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=[1.0], _kernel="fp64")
+    dmt = _dense_mt(dos, y=y)
+    ds = hb.linear_regression_rows(y=dmt.y, x=dmt.x, covariates=[1.0])
+    assert np.array_equal(ds.n, gt.n)
+    assert_fields_close(_as_dict(ds), _as_dict(gt), t_floor=1e-9)
+
+
+@pytest.mark.parametrize("N,M,K,P,intercept", [(1000, 70, 3, 1, True), (2049, 33, 10, 3, True), (777, 130, 2, 2, False),
+                                              (515, 40, 0, 1, False), (1200, 37, 4, 14, True)])
+def test_dense_vs_oracle(N, M, K, P, intercept):
+    """Float dosages in [0, 2] with NaN holes, missing phenotypes / covariates; C = K + P above and below one pass (12)."""
+    hb = _hb()
+    rng = np.random.default_rng(N + M)
+    x = rng.beta(0.6, 1.4, size=(M, N)) * 2.0
+    x[rng.random((M, N)) < 0.07] = np.nan
+    cov = rng.normal(size=(N, K))
+    if intercept and K:
+        cov[:, 0] = 1.0
+    ys = rng.normal(size=(N, P)) + 0.4 * np.nan_to_num(x[3])[:, None]
+    ys[rng.random(N) < 0.05, 0] = np.nan
+    if K:
+        cov[rng.random(N) < 0.02, K - 1] = np.nan
+    mt = _dense_mt(x, **{f"y{p}": ys[:, p] for p in range(P)}, **{f"c{k}": cov[:, k] for k in range(K)})
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ht = hb.linear_regression_rows(y=[mt[f"y{p}"] for p in range(P)], x=mt.x,
+                                       covariates=[mt[f"c{k}"] for k in range(K)])
+    want = O.linreg_group(x, ys, cov)
+    assert_fields_close(_as_dict(ht), {k: v for k, v in want.items() if k != "_d"}, t_floor=1e-9)
+    idx = O.complete_samples(ys, cov)[2]
+    assert np.array_equal(ht.n_missing, np.isnan(x[:, idx]).sum(axis=1))
+
+
+def test_dense_chained_and_edges():
+    hb = _hb()
+    rng = np.random.default_rng(9)
+    N, M = 900, 45
+    x = rng.random((M, N)) * 2.0
+    x[rng.random((M, N)) < 0.25] = np.nan
+    x[0] = np.nan            # all-missing variant: every statistic NaN (RU:52: 0 / 0)
+    x[1] = 0.75              # constant column: degenerate
+    y1 = rng.normal(size=N); y2 = rng.normal(size=N)
+    y1[rng.random(N) < 0.1] = np.nan
+    y2[rng.random(N) < 0.3] = np.nan
+    c = rng.normal(size=N)
+    mt = _dense_mt(x, y1=y1, y2=y2, c=c)
+    ht = hb.linear_regression_rows(y=[[mt.y1], [mt.y2]], x=mt.x, covariates=[1.0, mt.c])
+    cov = np.column_stack([np.ones(N), c])
+    want = O.linreg_chained(x, [y1[:, None], y2[:, None]], cov)
+    for g in range(2):
+        got = {"n": ht.n[:, g], "sum_x": ht.sum_x[:, g]}
+        for f in ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+            got[f] = ht[f][g]
+        assert np.isnan(got["sum_x"][0]) and np.isnan(got["beta"][0]).all() and np.isnan(got["p_value"][0]).all()
+        assert np.isnan(got["standard_error"][1]).all() or (np.abs(got["t_stat"][1]) < 1e-3).all()
+        assert_fields_close({k: v[2:] for k, v in got.items()}, {k: v[2:] for k, v in want[g].items() if k != "_d"},
+                            t_floor=1e-9, ctx=f"g={g}")
+    # empty row range; filtered columns
+    e = _dense_mt(np.empty((0, N)), y=y1)
+    assert hb.linear_regression_rows(y=e.y, x=e.x, covariates=[1.0]).count() == 0
+    keep = rng.random(N) < 0.6
+    sub = mt.filter_cols(keep)
+    hs = hb.linear_regression_rows(y=sub.y1, x=sub.x, covariates=[1.0, sub.c])
+    ws = O.linreg_group(x[:, keep], y1[keep][:, None], cov[keep])
+    got = _as_dict(hs)
+    assert_fields_close({k: v[2:] for k, v in got.items()}, {k: v[2:] for k, v in ws.items() if k != "_d"}, t_floor=1e-9)
+
+
+def test_dense_rejects_mismatched_sources():
+    hb = _hb()
+    rng = np.random.default_rng(0)
+    mt = _dense_mt(rng.random((4, 30)), y=rng.normal(size=30))
+    with pytest.raises(hb.ExpressionException):
+        mt.GT
+    with pytest.raises(NotImplementedError):
+        hb.linear_regression_rows(y=mt.y, x=mt.x, covariates=[1.0], weights=mt.y)

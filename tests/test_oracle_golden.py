@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from oracle import linreg_oracle as O
-from tests.helpers import GOLDEN, load_regression_linear, pl_dosage
+from tests.helpers import GOLDEN, gp_dosage, load_regression_linear, pl_dosage
 
 
 def _check(res, expected, places=6):
@@ -88,6 +88,18 @@ def test_linear_regression_pl():  # TS:286-316
     covs = np.column_stack([np.ones(8), cov])
     res = O.linreg_group(pl_dosage(doc), y[:, None], covs)
     _check(res, doc["expected"]["pl_dosage"])
+
+
+def test_linear_regression_gp_dosage():  # TS:318-348 (places=4 on beta / standard_error, 6 on t / p)
+    x, y, cov, doc = load_regression_linear()
+    res = O.linreg_group(gp_dosage(doc), y[:, None], np.column_stack([np.ones(8), cov]))
+    exp = doc["expected"]["gp_dosage"]
+    for pos in ("1", "2", "3"):
+        for f, v in exp[pos].items():
+            tol = 5e-5 if f in ("beta", "standard_error") else 5e-7
+            assert abs(res[f][int(pos) - 1, 0] - v) < tol, (pos, f)
+    for v in exp["nan_se"]:
+        assert np.isnan(res["standard_error"][v - 1, 0])
 
 
 @pytest.mark.parametrize("kind", ["is_case", "quant"])
