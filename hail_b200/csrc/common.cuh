@@ -39,8 +39,7 @@ struct Group {
   int ncols_pad = 0;
   int n_slices = 0;
   // dense-dosage path (filled lazily by launch_dense_sweep)
-  double* d_basis_t = nullptr;   // [ns_pad][C] sample-major copy of d_basis (+ one 64-bit scratch word)
-  int64_t first_sample = 0;      // lowest sample index of the group (pivot of the shifted sums)
+  double* d_basis_t = nullptr;   // [ns_pad][C] sample-major copy of d_basis, then [ns_pad] the 0 / 1 group indicator
 };
 
 struct Ctx {

@@ -7,14 +7,14 @@
 //   dense_sweep_kernel   a CTA owns VT = 8 variants, its 8 warps stride over 64-sample chunks (one 128-bit load per lane
 //                        per variant, the basis columns [Q' | Y_res] read as 128-bit loads from L2 where they stay
 //                        resident: 32 MB at 400k samples x 10 columns).  Per variant it accumulates, over the DEFINED
-//                        entries of the group's samples: the count, the pivot-shifted sum and sum of squares, and the
+//                        entries of the group's samples: the count, the sum and the sum of squares, and the
 //                        dot product with every basis column (missing entries contribute 0 here), and it writes one bit
 //                        per (variant, sample) saying "missing and in the group" (1/64 of the traffic of x).
 //   dense_impute_kernel  the mean-imputed column is x + mean * [missing]: a warp per variant walks the set bits and adds
 //                        mean * sum_{missing} basis[c] to every dot product, reading a sample-major copy of the basis
 //                        (one sample's C values are contiguous).  Cost is proportional to the number of missing entries.
 // The statistics epilogue (stats_device.cuh, `dense`) then uses dots[C] = sum of the defined entries and
-// dots[C + 1] = their centred sum of squares instead of the exact genotype counts of the packed kernels.
+// dots[C + 1] = their sum of squares instead of the exact genotype counts of the packed kernels.
 #include <type_traits>
 
 #include "common.cuh"
@@ -23,11 +23,14 @@ namespace lrr {
 
 namespace {
 
-constexpr int VW = 4;        // variants per warp
-constexpr int WARPS = 8;     // warps per CTA
-constexpr int VT = VW * WARPS;  // variants per CTA
-constexpr int CHUNK = 64;    // samples per step (two per lane)
-constexpr int STAGES = 6;    // cp.async ring depth: (STAGES - 1) x 16 KB of x in flight per SM
+constexpr int VW = 4;            // variants per dot warp
+constexpr int DOT_WARPS = 8;     // warps that accumulate the dot products
+constexpr int STAT_WARPS = 8;    // warps that count / sum the defined entries, write the missing bits, zero the holes
+constexpr int SVW = 4;           // variants per stat warp
+constexpr int VT = VW * DOT_WARPS;  // variants per CTA (= SVW * STAT_WARPS)
+constexpr int THREADS = (DOT_WARPS + STAT_WARPS) * 32;
+constexpr int CHUNK = 64;        // samples per step (two per lane)
+constexpr int STAGES = 8;        // cp.async ring depth (16 KB of x + 5 KB of basis per stage)
 
 struct DenseArgs {
   const double* x;       // [M][ldx]
@@ -35,12 +38,12 @@ struct DenseArgs {
   int64_t ns_pad;
   const double* basis;   // [C][ns_pad]
   const uint32_t* mask;  // [ns_pad / 16], bit sample_shift(j & 15) of word j >> 4 set iff sample j is in the group
-  int64_t first_sample;  // lowest sample index of the group: its entry is the pivot of the shifted sums
+  const double* indicator;  // [ns_pad] 1.0 for the group's samples, else 0.0
   int n;
   int C;                 // all dot columns of the group
   int c0;                // first column of this pass
   int32_t* counts;       // [M][4]: (0, 0, n_missing, 0)
-  double* dots;          // [M][C + 2]: C dot products, sum of the defined entries, their centred sum of squares
+  double* dots;          // [M][C + 2]: C dot products, sum of the defined entries, their sum of squares
   uint2* nanmask;        // [M][n_chunks]: .x bit l = sample 64 k + 2 l missing (and in the group), .y = sample 64 k + 2 l + 1
   int64_t n_chunks;
 };
@@ -52,147 +55,220 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // 16- / 8-byte asynchronous global -> shared copies; `bytes` < size zero-fills the rest (samples past the last one)
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem),
-               "r"(bytes) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t smem, const void* gmem, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem), "l"(gmem), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem),
-               "r"(bytes) : "memory");
+__device__ __forceinline__ void cp_async16_full(uint32_t smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t smem, const void* gmem, int bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8_full(uint32_t smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// exponent all ones: NaN (missing) or +-Inf.  Both count as "missing" here: an infinite entry has no meaningful
+// regression in the reference either (every statistic NaN); mean-imputing it keeps the other rows of the CTA clean.
+__device__ __forceinline__ bool not_finite(double v) { return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000; }
+
 // CB = basis columns of this pass (compile-time: the accumulators live in registers), FIRST = this pass also produces
-// the counts / sums / missing bits, VEC = rows are 16-byte aligned (128-bit copies of x)
+// the counts / sums / missing bits, VEC = rows are 16-byte aligned (128-bit copies of x).
+// Warp-specialised, one barrier per 64-sample step:
+//   stat warps     (8 x 4 variants) issue every cp.async copy (stage k + 7) and run one stage AHEAD of the dot warps: on
+//                  stage k + 1 they ballot the "missing and in the group" bits, count them, and overwrite every
+//                  non-finite entry with 0 in shared memory
+//   dot warps      (8 x 4 variants) then read clean data on stage k: acc[r][c] += basis[c][j] * x[r][j] and, with the
+//                  group's 0 / 1 indicator column staged next to the basis, sum += ind[j] * x[r][j] and
+//                  squares += (ind[j] * x[r][j]) * x[r][j]  (samples outside the group have zero basis rows)
 template <int CB, bool FIRST, bool VEC>
-__global__ void __launch_bounds__(WARPS * 32, 1) dense_sweep_kernel(DenseArgs a) {
-  extern __shared__ __align__(16) double s_ring[];   // STAGES x { x [VT][CHUNK], basis [CB][CHUNK] }
-  constexpr int STAGE_DOUBLES = (VT + CB) * CHUNK;
+__global__ void __launch_bounds__(THREADS, 1) dense_sweep_kernel(DenseArgs a) {
+  extern __shared__ __align__(16) double s_ring[];   // STAGES x { x [VT][CHUNK], indicator [CHUNK], basis [CB][CHUNK] }
+  constexpr int STAGE_DOUBLES = (VT + 1 + CB) * CHUNK;
+  constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * 8;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int64_t v0 = (int64_t)blockIdx.x * VT;
   const int cb = min(CB, a.C - a.c0);
+  const int sw = warp - DOT_WARPS;
 
-  auto issue = [&](int64_t chunk) {   // one stage: 64 samples of the CTA's 32 variants and of this pass's columns
-    double* st = s_ring + (chunk % STAGES) * STAGE_DOUBLES;
-    const int64_t j0 = chunk * CHUNK;
-    if (VEC) {
-#pragma unroll
-      for (int i = 0; i < VT * (CHUNK / 2) / (WARPS * 32); ++i) {
-        const int idx = threadIdx.x + i * WARPS * 32;
-        const int r = idx >> 5, l2 = (idx & 31) * 2;
-        int64_t vv = v0 + r;
-        if (vv >= a.M) vv = a.M - 1;   // clamp: copies stay in bounds, stores are skipped
-        const int64_t left = a.n_total - (j0 + l2);
-        const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
-        cp_async16(st + r * CHUNK + l2, a.x + vv * a.ldx + (bytes ? j0 + l2 : 0), bytes);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < VT * CHUNK / (WARPS * 32); ++i) {
-        const int idx = threadIdx.x + i * WARPS * 32;
-        const int r = idx >> 6, l = idx & 63;
-        int64_t vv = v0 + r;
-        if (vv >= a.M) vv = a.M - 1;
-        const int bytes = (j0 + l < a.n_total) ? 8 : 0;
-        cp_async8(st + r * CHUNK + l, a.x + vv * a.ldx + (bytes ? j0 + l : 0), bytes);
-      }
-    }
-    for (int idx = threadIdx.x; idx < cb * (CHUNK / 2); idx += WARPS * 32) {   // ns_pad >= 64 n_chunks: in bounds
-      const int c = idx >> 5, l2 = (idx & 31) * 2;
-      cp_async16(st + (VT + c) * CHUNK + l2, a.basis + (int64_t)(a.c0 + c) * a.ns_pad + j0 + l2, 16);
-    }
-  };
-
-  double piv[VW];
-#pragma unroll
-  for (int r = 0; r < VW; ++r) {
-    piv[r] = 0.0;
-    if (FIRST) {
-      int64_t vv = v0 + warp * VW + r;
-      if (vv >= a.M) vv = a.M - 1;
-      const double p = a.x[vv * a.ldx + a.first_sample];
-      piv[r] = (p == p && fabs(p) <= 1.7e308) ? p : 0.0;
-    }
-  }
-  double acc[VW][CB];
-  double s[VW], ss[VW];
-  int n_miss = 0;   // lane r counts variant r's missing entries
-#pragma unroll
-  for (int r = 0; r < VW; ++r) {
-    s[r] = ss[r] = 0.0;
-#pragma unroll
-    for (int c = 0; c < CB; ++c) acc[r][c] = 0.0;
-  }
   if (cb < CB) {   // unused columns of the last pass: zero once, never copied into
     for (int st = 0; st < STAGES; ++st)
-      for (int i = threadIdx.x; i < (CB - cb) * CHUNK; i += WARPS * 32) s_ring[st * STAGE_DOUBLES + (VT + cb) * CHUNK + i] = 0.0;
+      for (int i = threadIdx.x; i < (CB - cb) * CHUNK; i += THREADS)
+        s_ring[st * STAGE_DOUBLES + (VT + 1 + cb) * CHUNK + i] = 0.0;
   }
 
-  const int sh0 = sample_shift((lane & 7) * 2), sh1 = sample_shift((lane & 7) * 2 + 1);
-#pragma unroll
-  for (int k = 0; k < STAGES - 1; ++k) {
-    if (k < a.n_chunks) issue(k);
-    cp_async_commit();
-  }
-  for (int64_t chunk = 0; chunk < a.n_chunks; ++chunk) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();   // stage `chunk` has landed for every thread; stage chunk - 1 is free again
-    if (chunk + STAGES - 1 < a.n_chunks) issue(chunk + STAGES - 1);
-    cp_async_commit();
-    const double* st = s_ring + (chunk % STAGES) * STAGE_DOUBLES;
-    const uint32_t mw = __ldg(a.mask + chunk * 4 + (lane >> 3));
-    const bool g0 = (mw >> sh0) & 1u, g1 = (mw >> sh1) & 1u;
-    double2 xv[VW];
-#pragma unroll
-    for (int r = 0; r < VW; ++r) xv[r] = *reinterpret_cast<const double2*>(st + (warp * VW + r) * CHUNK + lane * 2);
-    double x0[VW], x1[VW];
+  if (sw < 0) {
+    // =================== dot warps ===================
+    double acc[VW][CB];
+    double s[VW], ss[VW];
 #pragma unroll
     for (int r = 0; r < VW; ++r) {
-      const bool m0 = xv[r].x != xv[r].x, m1 = xv[r].y != xv[r].y;
-      const bool u0 = g0 && !m0, u1 = g1 && !m1;      // entries that enter the sums
-      x0[r] = u0 ? xv[r].x : 0.0;
-      x1[r] = u1 ? xv[r].y : 0.0;
+      s[r] = ss[r] = 0.0;
+#pragma unroll
+      for (int c = 0; c < CB; ++c) acc[r][c] = 0.0;
+    }
+    __syncthreads();   // (the stat warps clean stage 0 now)
+    int slot = 0;      // ring slot of stage `chunk`
+    for (int64_t chunk = 0; chunk < a.n_chunks; ++chunk) {
+      __syncthreads();   // stage chunk is complete and clean
+      const double* st = s_ring + slot * STAGE_DOUBLES + lane * 2;
+      double2 xv[VW];
+#pragma unroll
+      for (int r = 0; r < VW; ++r) xv[r] = *reinterpret_cast<const double2*>(st + (warp * VW + r) * CHUNK);
       if (FIRST) {
-        const double d0 = u0 ? x0[r] - piv[r] : 0.0, d1 = u1 ? x1[r] - piv[r] : 0.0;
-        s[r] += d0 + d1;
-        ss[r] = fma(d0, d0, fma(d1, d1, ss[r]));
-        const uint32_t b0 = __ballot_sync(0xffffffffu, g0 && m0), b1 = __ballot_sync(0xffffffffu, g1 && m1);
-        if (lane == r) {
-          n_miss += __popc(b0) + __popc(b1);
-          const int64_t vv = v0 + warp * VW + r;
-          if (vv < a.M) a.nanmask[vv * a.n_chunks + chunk] = make_uint2(b0, b1);
+        const double2 g = *reinterpret_cast<const double2*>(st + VT * CHUNK);
+#pragma unroll
+        for (int r = 0; r < VW; ++r) {
+          const double t0 = g.x * xv[r].x, t1 = g.y * xv[r].y;
+          s[r] += t0 + t1;
+          ss[r] = fma(t0, xv[r].x, fma(t1, xv[r].y, ss[r]));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CB; ++c) {
+        const double2 q = *reinterpret_cast<const double2*>(st + (VT + 1 + c) * CHUNK);
+#pragma unroll
+        for (int r = 0; r < VW; ++r) acc[r][c] = fma(q.x, xv[r].x, fma(q.y, xv[r].y, acc[r][c]));
+      }
+      slot = slot == STAGES - 1 ? 0 : slot + 1;
+    }
+#pragma unroll
+    for (int r = 0; r < VW; ++r) {
+      const int64_t vv = v0 + warp * VW + r;
+      double* d = a.dots + vv * (a.C + 2);
+#pragma unroll
+      for (int c = 0; c < CB; ++c) {
+        const double t = warp_sum(acc[r][c]);
+        if (lane == 0 && c < cb && vv < a.M) d[a.c0 + c] = t;
+      }
+      if (FIRST) {
+        const double rs = warp_sum(s[r]), rss = warp_sum(ss[r]);
+        if (lane == 0 && vv < a.M) {
+          d[a.C] = rs;        // sum of the defined entries of the group's samples
+          d[a.C + 1] = rss;   // their sum of squares
         }
       }
     }
+  } else {
+    // =================== stat warps: loader + missing bits + hole filling ===================
+    const int t = threadIdx.x - DOT_WARPS * 32;
+    constexpr int LT = STAT_WARPS * 32;   // loader threads
+    const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(s_ring);
+    constexpr int X_ELEMS = VEC ? VT * CHUNK / 2 : VT * CHUNK;         // x copies per stage
+    static_assert(X_ELEMS % LT == 0, "every loader thread issues the same number of x copies");
+    constexpr int XI = X_ELEMS / LT;
+    const double* xsrc[XI];
+    uint32_t xdst[XI];   // byte offset inside a stage
 #pragma unroll
-    for (int c = 0; c < CB; ++c) {
-      const double2 q = *reinterpret_cast<const double2*>(st + (VT + c) * CHUNK + lane * 2);
-#pragma unroll
-      for (int r = 0; r < VW; ++r) acc[r][c] = fma(q.x, x0[r], fma(q.y, x1[r], acc[r][c]));
+    for (int i = 0; i < XI; ++i) {
+      const int idx = t + i * LT;
+      const int r = VEC ? idx >> 5 : idx >> 6;
+      const int l = VEC ? (idx & 31) * 2 : idx & 63;
+      int64_t vv = v0 + r;
+      if (vv >= a.M) vv = a.M - 1;   // clamp: copies stay in bounds, stores are skipped
+      xsrc[i] = a.x + vv * a.ldx + l;
+      xdst[i] = (uint32_t)(r * CHUNK + l) * 8u;
     }
-  }
+    // column copies: slot 0 = the group indicator, slot 1 + c = basis column c0 + c (all 128-bit, ns_pad is padded)
+    constexpr int BI = ((1 + CB) * (CHUNK / 2) + LT - 1) / LT;
+    const double* bsrc[BI];
+    uint32_t bdst[BI];
+    bool bok[BI];
+#pragma unroll
+    for (int i = 0; i < BI; ++i) {
+      const int idx = t + i * LT;
+      const int col = idx >> 5, l2 = (idx & 31) * 2;
+      bok[i] = col < 1 + cb;
+      bsrc[i] = (col == 0 || !bok[i] ? a.indicator : a.basis + (int64_t)(a.c0 + col - 1) * a.ns_pad) + l2;
+      bdst[i] = (uint32_t)((VT + col) * CHUNK + l2) * 8u;
+    }
+    const int64_t n_full = a.n_total / CHUNK;
+    // copies of stage `chunk` into ring slot `slot`; the source pointers advance with every call (calls are in order)
+    auto issue = [&](int64_t chunk, int slot) {
+      const uint32_t st = ring_base + (uint32_t)slot * STAGE_BYTES;
+      if (chunk < n_full) {
+#pragma unroll
+        for (int i = 0; i < XI; ++i) {
+          if (VEC) cp_async16_full(st + xdst[i], xsrc[i]);
+          else cp_async8_full(st + xdst[i], xsrc[i]);
+        }
+      } else {   // the last, partial chunk: zero-fill past the last sample
+#pragma unroll
+        for (int i = 0; i < XI; ++i) {
+          const int64_t left = a.n_total - (chunk * CHUNK + (int64_t)((xdst[i] >> 3) & (CHUNK - 1)));
+          if (VEC) {
+            const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+            cp_async16(st + xdst[i], bytes ? xsrc[i] : a.x, bytes);
+          } else {
+            const int bytes = left >= 1 ? 8 : 0;
+            cp_async8(st + xdst[i], bytes ? xsrc[i] : a.x, bytes);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < BI; ++i)
+        if (bok[i]) cp_async16_full(st + bdst[i], bsrc[i]);
+#pragma unroll
+      for (int i = 0; i < XI; ++i) xsrc[i] += CHUNK;
+#pragma unroll
+      for (int i = 0; i < BI; ++i) bsrc[i] += CHUNK;
+    };
+#pragma unroll
+    for (int k = 0; k < STAGES - 1; ++k) {
+      if (k < a.n_chunks) issue(k, k);
+      cp_async_commit();
+    }
 
-  // ---- reduce over the lanes: every warp owns its variants ----
+    int nm[SVW];
 #pragma unroll
-  for (int r = 0; r < VW; ++r) {
-    const int64_t vv = v0 + warp * VW + r;
-    double* d = a.dots + vv * (a.C + 2);
+    for (int r = 0; r < SVW; ++r) nm[r] = 0;
+    // one step on the stage in `slot`: missing bits of chunk `chunk`, then zero the holes in place
+    auto stat_step = [&](int64_t chunk, int slot) {
+      double* st = s_ring + slot * STAGE_DOUBLES + (sw * SVW) * CHUNK + lane * 2;
+      bool g0 = false, g1 = false;
+      if (FIRST) {   // the staged indicator column (no global load on the per-step critical path)
+        const double2 g = *reinterpret_cast<const double2*>(s_ring + slot * STAGE_DOUBLES + VT * CHUNK + lane * 2);
+        g0 = g.x != 0.0;
+        g1 = g.y != 0.0;
+      }
 #pragma unroll
-    for (int c = 0; c < CB; ++c) {
-      const double t = warp_sum(acc[r][c]);
-      if (lane == 0 && c < cb && vv < a.M) d[a.c0 + c] = t;
+      for (int r = 0; r < SVW; ++r) {
+        double2 xv = *reinterpret_cast<const double2*>(st + r * CHUNK);
+        const bool m0 = not_finite(xv.x), m1 = not_finite(xv.y);
+        if (m0 || m1) {
+          if (m0) xv.x = 0.0;
+          if (m1) xv.y = 0.0;
+          *reinterpret_cast<double2*>(st + r * CHUNK) = xv;
+        }
+        if (FIRST) {
+          const uint32_t b0 = __ballot_sync(0xffffffffu, g0 && m0), b1 = __ballot_sync(0xffffffffu, g1 && m1);
+          nm[r] += __popc(b0) + __popc(b1);
+          const int64_t vv = v0 + sw * SVW + r;
+          if (lane == 0 && vv < a.M) a.nanmask[vv * a.n_chunks + chunk] = make_uint2(b0, b1);
+        }
+      }
+    };
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();   // stage 0 has landed for every loader thread
+    if (a.n_chunks > 0) stat_step(0, 0);
+    int slot = 0;
+    for (int64_t chunk = 0; chunk < a.n_chunks; ++chunk) {
+      cp_async_wait<STAGES - 3>();
+      __syncthreads();   // stage chunk + 1 has landed, stage chunk is clean, stage chunk - 1 is free again
+      if (chunk + STAGES - 1 < a.n_chunks) issue(chunk + STAGES - 1, slot == 0 ? STAGES - 1 : slot - 1);
+      cp_async_commit();
+      slot = slot == STAGES - 1 ? 0 : slot + 1;
+      if (chunk + 1 < a.n_chunks) stat_step(chunk + 1, slot);
     }
     if (FIRST) {
-      const double rs = warp_sum(s[r]), rss = warp_sum(ss[r]);
-      const int nm = __shfl_sync(0xffffffffu, n_miss, r);
-      if (lane == 0 && vv < a.M) {
-        const int ndv = a.n - nm;
-        d[a.C] = rs + (double)ndv * piv[r];                    // sum of the defined entries
-        d[a.C + 1] = rss - rs * rs / (double)ndv;              // centred squares (the mean-imputed entries add 0)
-        reinterpret_cast<int4*>(a.counts)[vv] = make_int4(0, 0, nm, 0);
+#pragma unroll
+      for (int r = 0; r < SVW; ++r) {
+        const int64_t vv = v0 + sw * SVW + r;
+        if (lane == 0 && vv < a.M) reinterpret_cast<int4*>(a.counts)[vv] = make_int4(0, 0, nm[r], 0);
       }
     }
   }
@@ -210,11 +286,13 @@ struct ImputeArgs {
 };
 
 // dots[v][c] += mean_v * sum over the missing in-group samples j of basis[c][j]   (RU:52-57: those slots hold the mean)
-__global__ void __launch_bounds__(256) dense_impute_kernel(ImputeArgs a) {
+// One CTA per variant with missing entries; threads stride over the 64-sample mask words.
+constexpr int IMPUTE_THREADS = 128;
+__global__ void __launch_bounds__(IMPUTE_THREADS) dense_impute_kernel(ImputeArgs a) {
   constexpr int CP = 12;
-  const int lane = threadIdx.x & 31;
-  const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (v >= a.M) return;
+  __shared__ double s_corr[IMPUTE_THREADS / 32][CP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t v = blockIdx.x;
   const int nm = a.counts[v * 4 + 2];
   if (nm == 0) return;
   double* d = a.dots + v * (a.C + 2);
@@ -225,7 +303,7 @@ __global__ void __launch_bounds__(256) dense_impute_kernel(ImputeArgs a) {
 #pragma unroll
     for (int c = 0; c < CP; ++c) corr[c] = 0.0;
     const int cb = min(CP, a.C - c0);
-    for (int64_t k = lane; k < a.n_chunks; k += 32) {
+    for (int64_t k = threadIdx.x; k < a.n_chunks; k += IMPUTE_THREADS) {
       const uint2 w = mk[k];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -243,8 +321,16 @@ __global__ void __launch_bounds__(256) dense_impute_kernel(ImputeArgs a) {
 #pragma unroll
     for (int c = 0; c < CP; ++c) {
       const double r = warp_sum(corr[c]);
-      if (lane == 0 && c < cb) d[c0 + c] += mean * r;
+      if (lane == 0) s_corr[warp][c] = r;
     }
+    __syncthreads();
+    if ((int)threadIdx.x < cb) {
+      double r = 0.0;
+#pragma unroll
+      for (int w = 0; w < IMPUTE_THREADS / 32; ++w) r += s_corr[w][threadIdx.x];
+      d[c0 + threadIdx.x] += mean * r;
+    }
+    __syncthreads();
   }
 }
 
@@ -257,27 +343,21 @@ __global__ void transpose_basis_kernel(const double* __restrict__ basis, int C, 
   }
 }
 
-__global__ void first_sample_kernel(const uint32_t* __restrict__ mask, int64_t n_words, unsigned long long* out) {
-  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t m = mask[w];
-    if (!m) continue;
-    for (int j = 0; j < 16; ++j)
-      if ((m >> sample_shift(j)) & 1u) {
-        atomicMin(out, (unsigned long long)(w * 16 + j));
-        break;
-      }
-  }
+// 0 / 1 indicator of the group's samples as float64 (a staged "basis column" for the sums of the defined entries)
+__global__ void indicator_kernel(const uint32_t* __restrict__ mask, int64_t ns_pad, double* __restrict__ out) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ns_pad; j += (int64_t)gridDim.x * blockDim.x)
+    out[j] = ((mask[j >> 4] >> sample_shift((int)(j & 15))) & 1u) ? 1.0 : 0.0;
 }
 
 template <int CB, bool FIRST, bool VEC>
 void launch_pass_v(const DenseArgs& a, int grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (VT + CB) * CHUNK * (int)sizeof(double);
+  constexpr int smem = STAGES * (VT + 1 + CB) * CHUNK * (int)sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(dense_sweep_kernel<CB, FIRST, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_set = true;
   }
-  dense_sweep_kernel<CB, FIRST, VEC><<<grid, WARPS * 32, smem, st>>>(a);
+  dense_sweep_kernel<CB, FIRST, VEC><<<grid, THREADS, smem, st>>>(a);
 }
 
 template <int CB, bool FIRST>
@@ -288,8 +368,11 @@ void launch_pass(const DenseArgs& a, bool vec, int grid, cudaStream_t st) {
 
 template <bool FIRST>
 void launch_pass_cb(const DenseArgs& a, int cb, bool vec, int grid, cudaStream_t st) {
-  if (cb <= 4) launch_pass<4, FIRST>(a, vec, grid, st);
+  if (cb <= 2) launch_pass<2, FIRST>(a, vec, grid, st);
+  else if (cb <= 4) launch_pass<4, FIRST>(a, vec, grid, st);
+  else if (cb <= 6) launch_pass<6, FIRST>(a, vec, grid, st);
   else if (cb <= 8) launch_pass<8, FIRST>(a, vec, grid, st);
+  else if (cb <= 10) launch_pass<10, FIRST>(a, vec, grid, st);
   else launch_pass<12, FIRST>(a, vec, grid, st);
 }
 
@@ -310,17 +393,12 @@ int launch_dense_sweep(Ctx* c, const double* d_x, int64_t M, int64_t ldx, cudaSt
       LRR_CUDA(c, cudaMalloc(&c->d_nanmask, need));
       c->nanmask_bytes = need;
     }
-    if (!G.d_basis_t) {   // sample-major copy of the basis for the imputation pass + the pivot sample, once per group
-      LRR_CUDA(c, cudaMalloc(&G.d_basis_t, sizeof(double) * (size_t)G.C * (size_t)G.ns_pad + sizeof(unsigned long long)));
-      unsigned long long* d_first = reinterpret_cast<unsigned long long*>(G.d_basis_t + (size_t)G.C * (size_t)G.ns_pad);
-      LRR_CUDA(c, cudaMemsetAsync(d_first, 0xff, sizeof(unsigned long long), st));
+    if (!G.d_basis_t) {   // once per group: sample-major copy of the basis (imputation pass) + the indicator column
+      LRR_CUDA(c, cudaMalloc(&G.d_basis_t, sizeof(double) * ((size_t)G.C + 1) * (size_t)G.ns_pad));
       transpose_basis_kernel<<<c->sm_count * 8, 256, 0, st>>>(G.d_basis, G.C, G.ns_pad, G.d_basis_t);
-      first_sample_kernel<<<c->sm_count, 256, 0, st>>>(G.d_mask, G.ns_pad / 16, d_first);
+      indicator_kernel<<<c->sm_count * 2, 256, 0, st>>>(G.d_mask, G.ns_pad, G.d_basis_t + (size_t)G.C * (size_t)G.ns_pad);
       c->launches += 2;
-      unsigned long long h_first = 0;
-      LRR_CUDA(c, cudaMemcpyAsync(&h_first, d_first, sizeof(h_first), cudaMemcpyDeviceToHost, st));
-      LRR_CUDA(c, cudaStreamSynchronize(st));
-      G.first_sample = (h_first < (unsigned long long)n_total) ? (int64_t)h_first : 0;
+      LRR_CUDA(c, cudaGetLastError());
     }
     DenseArgs a;
     a.x = d_x;
@@ -330,7 +408,7 @@ int launch_dense_sweep(Ctx* c, const double* d_x, int64_t M, int64_t ldx, cudaSt
     a.ns_pad = G.ns_pad;
     a.basis = G.d_basis;
     a.mask = G.d_mask;
-    a.first_sample = G.first_sample;
+    a.indicator = G.d_basis_t + (size_t)G.C * (size_t)G.ns_pad;
     a.n = G.n;
     a.C = G.C;
     a.counts = c->d_counts + (int64_t)g * c->reserved_variants * 4;
@@ -359,7 +437,7 @@ int launch_dense_sweep(Ctx* c, const double* d_x, int64_t M, int64_t ldx, cudaSt
     ia.dots = a.dots;
     ia.nanmask = a.nanmask;
     ia.n_chunks = n_chunks;
-    dense_impute_kernel<<<(int)((M + 7) / 8), 256, 0, st>>>(ia);
+    dense_impute_kernel<<<(unsigned)M, IMPUTE_THREADS, 0, st>>>(ia);
     c->launches++;
     LRR_CUDA(c, cudaGetLastError());
   }

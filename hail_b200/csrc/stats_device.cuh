@@ -79,7 +79,7 @@ struct StatModel {
   const double* yyp;      // [P]
   int n, K, Kd, P, C, has_intercept, d, weighted;
   int dense;              // dense-dosage sweep: dv has C + 2 entries, dv[C] = sum of the defined entries, dv[C + 1] =
-                          // their centred sum of squares (= that of the mean-imputed column)
+                          // their sum of squares
   double lbeta;
   lrr_group_out out;
 };
@@ -94,7 +94,8 @@ __device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n
   const double mean = S / nv;                        // RU:52
   // weighted groups (statgen.py:636-660): the column sum and x.x of the sqrt(w)-scaled imputed x are dot products
   const double sum_x = a.weighted ? dv[a.Kd + a.P] : S + (double)nm * mean;        // LR:136
-  const double xxc = a.dense ? dv[a.C + 1] : 0.0;   // dense: sum of (x - mean)^2 over the imputed column
+  // dense: centred sum of squares of the imputed column (the imputed entries sit at the mean and add nothing)
+  const double xxc = a.dense ? dv[a.C + 1] - S * S / nv : 0.0;
   const double xx_imp = a.dense ? xxc + sum_x * sum_x / (double)a.n
                                 : a.weighted ? dv[a.Kd + a.P + 1] : xx_int + (double)nm * mean * mean;
 
