@@ -48,3 +48,44 @@ def test_null_fit_and_fatal_conditions():
     with pytest.raises(OracleFatal, match="Failed to fit logistic regression null model"):
         L.logreg_score(x, y, sep)
     assert np.allclose(L.chi_sq_tail_1(np.array([0.0, 3.841458820694124])), [1.0, 0.05], atol=1e-12)
+
+
+# ---- wald / lrt / firth (per-variant Newton fits) ------------------------------------------------------------
+def test_wald_and_lrt_match_r():   # test_statgen.py:719-756, 940-985
+    doc, x, y, cov = load_regression_logistic()
+    for test, key in (("wald", "expected_wald"), ("lrt", "expected_lrt")):
+        out = L.logreg_rows(test, x, y, cov)
+        exp = doc[key]
+        for pos in ("1", "2"):
+            for f, v in exp[pos].items():
+                assert abs(out[f][int(pos) - 1] - v) < 5e-7, (test, pos, f)
+        for pos in exp["not_converged"]:
+            assert not out["converged"][pos - 1]                # separable
+        for pos in exp["constant"]:
+            i = pos - 1
+            assert (not out["converged"][i]) or np.isnan(out["p_value"][i]) or abs(out["p_value"][i] - 1) < 1e-4
+
+
+def load_epacts():
+    z = np.load(os.path.join(GOLDEN, "logistic_epacts.npz"))
+    x = z["gt"].astype(np.float64)
+    x[x < 0] = np.nan
+    cov = np.column_stack([np.ones(x.shape[1]), z["is_female"], z["pc1"], z["pc2"]])
+    return z, x, z["is_case"], cov
+
+
+def test_epacts_all_four_tests():  # test_statgen.py:1722-1862
+    z, x, y, cov = load_epacts()
+    w = L.logreg_rows("wald", x, y, cov)
+    for i in range(5):
+        for j, f in enumerate(("beta", "standard_error", "z_stat", "p_value")):
+            assert w[f][i] == pytest.approx(z["wald"][i, j], rel=z["wald_rel"][i, j]), (i, f)
+    lrt = L.logreg_rows("lrt", x, y, cov)
+    assert lrt["p_value"] == pytest.approx(z["lrt_p"], rel=1e-4)
+    sc = L.logreg_score(x, y, cov)
+    assert sc["chi_sq_stat"] == pytest.approx(z["score"][:, 0], rel=1e-5)
+    assert sc["p_value"] == pytest.approx(z["score"][:, 1], rel=1e-5)
+    fi = L.logreg_rows("firth", x, y, cov)
+    assert fi["beta"] == pytest.approx(z["firth"][:, 0], rel=1e-4)
+    assert fi["p_value"] == pytest.approx(z["firth"][:, 1], rel=1e-4)
+    assert fi["converged"].all() and w["converged"].all()
