@@ -37,6 +37,13 @@ class ScoreOut(ctypes.Structure):
     _fields_ = [("chi_sq_stat", ctypes.c_void_p), ("p_value", ctypes.c_void_p), ("n_missing", ctypes.c_void_p)]
 
 
+class LogitOut(ctypes.Structure):
+    """lrr_logit_out"""
+
+    _fields_ = [(k, ctypes.c_void_p) for k in ("beta", "standard_error", "z_stat", "chi_sq_stat", "p_value",
+                                               "n_iterations", "converged", "exploded")]
+
+
 # name -> (restype, argtypes); must list every symbol include/lrr_b200.h declares (tests check this)
 SIGNATURES = {
     "lrr_version": (ctypes.c_char_p, []),
@@ -69,6 +76,12 @@ SIGNATURES = {
                                ctypes.c_void_p]),
     "lrr_run_dense": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.POINTER(GroupOut), ctypes.c_int32, ctypes.c_void_p]),
+    "lrr_set_logit_model": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_double]),
+    "lrr_run_logit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                     ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.POINTER(LogitOut),
+                                     ctypes.c_void_p]),
     "lrr_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "lrr_last_kernel": (ctypes.c_int, [ctypes.c_void_p]),
     "lrr_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

@@ -164,6 +164,7 @@ void lrr_destroy(lrr_ctx* ctx) {
   free_workspace(c);
   tc_release(c);
   tc4_release(c);
+  logit_release(c);
   cudaFree(c->arena);
   cudaFree(c->d_nanmask);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -417,6 +418,23 @@ int lrr_run_score(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_fl
   if (int r = launch_fp64_sweep(c, d_packed, n_variants, packed_stride, st)) return r;
   c->last_kernel = LRR_KERNEL_FP64;
   return launch_score_epilogue(c, n_variants, *out, st);
+}
+
+int lrr_set_logit_model(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, const int32_t* complete_idx,
+                        const double* cov, const double* y, const double* b0, const double* score0, const double* fisher0,
+                        double loglik0) {
+  if (!ctx) return LRR_EINVAL;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  DeviceGuard guard(c->device);
+  return logit_set_model(c, n_samples_total, n, K, complete_idx, cov, y, b0, score0, fisher0, loglik0);
+}
+
+int lrr_run_logit(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int64_t packed_stride, int64_t n_samples_total,
+                  int32_t test, int32_t max_iterations, double tolerance, const lrr_logit_out* out, void* stream) {
+  CTX_PROLOGUE;
+  if (!out) return fail(c, LRR_EINVAL, "lrr_run_logit: out is NULL");
+  if (int r = check_packed(c, n_samples_total, packed_stride)) return r;
+  return logit_run(c, d_packed, n_variants, packed_stride, n_samples_total, test, max_iterations, tolerance, *out, st);
 }
 
 int lrr_reserve(lrr_ctx* ctx, int64_t max_variants) {

@@ -57,6 +57,7 @@ struct Ctx {
   int sm_count = 148;
   void* tc_state = nullptr;  // opaque, owned by tc_kernel.cu
   void* tc4_state = nullptr; // opaque, owned by tc4_kernel.cu
+  void* logit_state = nullptr; // opaque, owned by logit_kernel.cu (Wald / LRT / Firth model)
   // optional device timing of the sweep kernel(s) of the last lrr_run (bench roofline)
   int timing = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -115,6 +116,11 @@ int run_rows(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t 
              const lrr_group_out* outs, int32_t n_outs, int32_t kernel, cudaStream_t);
 int launch_student_t(Ctx*, const double*, int64_t, double, double*, double*, cudaStream_t);
 int launch_score_epilogue(Ctx*, int64_t M, const lrr_score_out& out, cudaStream_t);
+int logit_set_model(Ctx*, int64_t n_samples_total, int32_t n, int32_t K, const int32_t* idx, const double* cov, const double* y,
+                    const double* b0, const double* score0, const double* fisher0, double loglk0);
+int logit_run(Ctx*, const uint8_t* d_packed, int64_t M, int64_t stride, int64_t n_samples_total, int test, int max_iter,
+              double tol, const lrr_logit_out& out, cudaStream_t);
+void logit_release(Ctx*);
 
 // position of sample `j` (0..15 within its word) in the packed word: bits [8i+2s, 8i+2s+1], j = 4s+i
 __host__ __device__ inline int sample_shift(int j) { return 8 * (j & 3) + 2 * (j >> 2); }

@@ -1,0 +1,514 @@
+// Kernel 5: per-variant logistic regression fits -- the Wald, likelihood-ratio and Firth tests of
+// `hl.logistic_regression_rows`.  One CTA per variant; Newton iterations in float64.
+//
+// Reference, per row (hail/hail/src/is/hail/methods/LogisticRegression.scala:115-157): x is mean-imputed over the complete
+// samples into the last column of the design matrix X = [covariates | x] (RegressionUtils.scala:16-58), then
+//   WaldTest / LikelihoodRatioTest   stats/LogisticRegressionModel.scala:55-145: model.fit(Some(nullFit)) (:294-370) -- start
+//                                    at b = [b_null, 0]; the covariate blocks of the first score / Fisher matrix are the
+//                                    null fit's (:311-325); iterate delta = fisher \ score until max|delta| < tol;
+//                                    Wald: se = sqrt(diag(inv(fisher))), z = b / se, p = 2 pnorm(-|z|);
+//                                    LRT: chi2 = 2 (logLkhd - logLkhd_null), p = pchisqtail(chi2, 1)
+//   LogisticFirthTest                :155-199 with fitFirth (:372-408): a null fit (K free coefficients) and a full fit
+//                                    (K + 1), both with the hat diagonal of the FULL design; the reference takes it from a
+//                                    QR of sqrt(W) X, here it comes from the normal equations: h_i = w_i x_i' F^-1 x_i,
+//                                    delta = F_00^-1 X_0' (y - mu + h (1/2 - mu)), sum log|diag R| = 1/2 log det F.
+// Every evaluation is one pass over the n complete samples: the CTA's 256 threads stride over them (covariate planes
+// [K][n] are L2-resident and read coalesced, genotype codes are gathered from the packed row through the complete-sample
+// index), each thread keeps the m + m (m + 1) / 2 partial sums of the score and the Fisher matrix in registers
+// (compile-time MM >= m), then a warp-shuffle + shared-memory reduction; thread 0 solves the m x m system (LU with
+// partial pivoting, singular = an exactly zero pivot, as LAPACK dgesv under breeze's `\`).
+#include "common.cuh"
+
+namespace lrr {
+
+namespace {
+
+constexpr int LT = 256;   // threads per CTA
+
+struct LogitModel {
+  int n = 0, K = 0;
+  int64_t n_samples_total = 0;
+  int32_t* d_idx = nullptr;   // [n] stored-sample index of each complete sample
+  double* d_cov = nullptr;    // [K][n]
+  double* d_y = nullptr;      // [n]
+  double* d_null = nullptr;   // [K] b0 | [K] score0 | [K*K] fisher0 | loglk0
+};
+
+struct LogitArgs {
+  const uint8_t* packed;
+  int64_t M, stride;
+  int n, K;
+  const int32_t* idx;
+  const double* cov;
+  const double* y;
+  const double* null_fit;
+  int test;        // 1 wald, 2 lrt, 3 firth
+  int max_iter;
+  double tol;
+  lrr_logit_out out;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double nan_value() { return __longlong_as_double(0x7ff8000000000000ll); }
+
+// Solve A z = rhs in place (A [m][MM] row-major in shared memory, destroyed).  Returns false when a pivot is exactly 0.
+template <int MM>
+__device__ bool lu_solve(double (*A)[MM], double* rhs, int m) {
+  for (int k = 0; k < m; ++k) {
+    int p = k;
+    double best = fabs(A[k][k]);
+    for (int i = k + 1; i < m; ++i) {
+      const double v = fabs(A[i][k]);
+      if (v > best) { best = v; p = i; }
+    }
+    if (A[p][k] == 0.0) return false;
+    if (p != k) {
+      for (int j = 0; j < m; ++j) { const double t = A[k][j]; A[k][j] = A[p][j]; A[p][j] = t; }
+      const double t = rhs[k]; rhs[k] = rhs[p]; rhs[p] = t;
+    }
+    const double inv = 1.0 / A[k][k];
+    for (int i = k + 1; i < m; ++i) {
+      const double f = A[i][k] * inv;
+      if (f != 0.0) {
+        for (int j = k + 1; j < m; ++j) A[i][j] -= f * A[k][j];
+        rhs[i] -= f * rhs[k];
+      }
+    }
+  }
+  for (int k = m - 1; k >= 0; --k) {
+    double s = rhs[k];
+    for (int j = k + 1; j < m; ++j) s -= A[k][j] * rhs[j];
+    rhs[k] = s / A[k][k];
+  }
+  return true;
+}
+
+// Inverse of A (destroyed) into Inv by Gauss-Jordan with partial pivoting; also log|det A|.  false = singular.
+template <int MM>
+__device__ bool invert(double (*A)[MM], double (*Inv)[MM], int m, double* logdet) {
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) Inv[i][j] = (i == j) ? 1.0 : 0.0;
+  double ld = 0.0;
+  for (int k = 0; k < m; ++k) {
+    int p = k;
+    double best = fabs(A[k][k]);
+    for (int i = k + 1; i < m; ++i) {
+      const double v = fabs(A[i][k]);
+      if (v > best) { best = v; p = i; }
+    }
+    if (A[p][k] == 0.0) return false;
+    if (p != k)
+      for (int j = 0; j < m; ++j) {
+        double t = A[k][j]; A[k][j] = A[p][j]; A[p][j] = t;
+        t = Inv[k][j]; Inv[k][j] = Inv[p][j]; Inv[p][j] = t;
+      }
+    ld += log(fabs(A[k][k]));
+    const double inv = 1.0 / A[k][k];
+    for (int j = 0; j < m; ++j) { A[k][j] *= inv; Inv[k][j] *= inv; }
+    for (int i = 0; i < m; ++i) {
+      if (i == k) continue;
+      const double f = A[i][k];
+      if (f != 0.0)
+        for (int j = 0; j < m; ++j) { A[i][j] -= f * A[k][j]; Inv[i][j] -= f * Inv[k][j]; }
+    }
+  }
+  *logdet = ld;
+  return true;
+}
+
+template <int MM>
+struct Shared {
+  double red[LT / 32][MM + MM * (MM + 1) / 2 + 1];
+  double F[MM][MM];      // Fisher matrix (symmetric, full)
+  double W[MM][MM];      // work copy for the solves
+  double Inv[MM][MM];
+  double score[MM], b[MM], delta[MM];
+  double loglik, logdet, mean;
+  int counts[3];
+  int status;            // 0 continue, 1 converged, 2 exploded
+};
+
+// One pass over the complete samples at coefficients b[0..m0) (columns m0..m-1 of X do not enter eta).
+//   MODE 0: score[a] = sum x_a (y - mu), F[a][b] = sum w x_a x_b, loglik = sum log(y mu + (1 - y)(1 - mu))   (all m columns)
+//   MODE 1: Firth second pass: score[a] = sum x_a (y - mu + h (1/2 - mu)) with h = w x' Inv x
+template <int MM, int MODE>
+__device__ void eval_pass(const LogitArgs& a, Shared<MM>& sh, const uint32_t* row, int m, int m0, bool want_loglik) {
+  constexpr int NF = MM * (MM + 1) / 2;
+  double sc[MM], fi[NF];
+  double ll = 0.0;
+#pragma unroll
+  for (int i = 0; i < MM; ++i) sc[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NF; ++i) fi[i] = 0.0;
+  if (MODE == 1) {   // the symmetric inverse, off-diagonal entries doubled
+#pragma unroll
+    for (int p = 0, q = 0; p < MM; ++p)
+#pragma unroll
+      for (int r = 0; r <= p; ++r, ++q) fi[q] = (p < m && r < m) ? (p == r ? sh.Inv[p][r] : 2.0 * sh.Inv[p][r]) : 0.0;
+  }
+  double bb[MM];
+#pragma unroll
+  for (int i = 0; i < MM; ++i) bb[i] = (i < m0) ? sh.b[i] : 0.0;
+  const double mean = sh.mean;
+  const int K = a.K;
+  for (int i = threadIdx.x; i < a.n; i += LT) {
+    double xa[MM];
+#pragma unroll
+    for (int k = 0; k < MM; ++k) xa[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < MM - 1; ++k)
+      if (k < K) xa[k] = __ldg(a.cov + (int64_t)k * a.n + i);
+    const int s = __ldg(a.idx + i);
+    const uint32_t code = (__ldg(row + (s >> 4)) >> sample_shift(s & 15)) & 3u;
+    const double x = (code == 3u) ? mean : (double)code;
+#pragma unroll
+    for (int k = 0; k < MM; ++k)
+      if (k == K) xa[k] = x;
+    double eta = 0.0;
+#pragma unroll
+    for (int k = 0; k < MM; ++k) eta = fma(bb[k], xa[k], eta);
+    const double mu = 1.0 / (1.0 + exp(-eta));
+    const double w = mu * (1.0 - mu);
+    const double yi = __ldg(a.y + i);
+    double r = yi - mu;
+    if (MODE == 0) {
+      if (want_loglik) ll += log(yi * mu + (1.0 - yi) * (1.0 - mu));
+#pragma unroll
+      for (int p = 0, q = 0; p < MM; ++p) {
+        const double wx = w * xa[p];
+#pragma unroll
+        for (int c = 0; c <= p; ++c, ++q) fi[q] = fma(wx, xa[c], fi[q]);
+      }
+    } else {
+      double h = 0.0;
+#pragma unroll
+      for (int p = 0, q = 0; p < MM; ++p) {
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c <= p; ++c, ++q) t = fma(fi[q], xa[c], t);
+        h = fma(t, xa[p], h);
+      }
+      r += w * h * (0.5 - mu);
+    }
+#pragma unroll
+    for (int k = 0; k < MM; ++k) sc[k] = fma(xa[k], r, sc[k]);
+  }
+  // ---- reduce ----
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < MM; ++k) {
+    const double t = warp_sum(sc[k]);
+    if (lane == 0) sh.red[warp][k] = t;
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int q = 0; q < NF; ++q) {
+      const double t = warp_sum(fi[q]);
+      if (lane == 0) sh.red[warp][MM + q] = t;
+    }
+    const double t = warp_sum(ll);
+    if (lane == 0) sh.red[warp][MM + NF] = t;
+  }
+  __syncthreads();
+  const int total = (MODE == 0) ? MM + NF + 1 : MM;
+  for (int q = threadIdx.x; q < total; q += LT) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < LT / 32; ++w) t += sh.red[w][q];
+    if (q < MM) {
+      sh.score[q] = t;
+    } else if (q < MM + NF) {
+      int p = 0, rem = q - MM;
+      while (rem > p) { rem -= p + 1; ++p; }
+      sh.F[p][rem] = t;
+      sh.F[rem][p] = t;
+    } else {
+      sh.loglik = t;
+    }
+  }
+  __syncthreads();
+}
+
+template <int MM>
+__global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
+  __shared__ Shared<MM> sh;
+  const int K = a.K, m = K + 1;
+  const double* b0 = a.null_fit;
+  const double* score0 = a.null_fit + K;
+  const double* fisher0 = a.null_fit + 2 * K;
+  const double loglk0 = a.null_fit[2 * K + K * K];
+  for (int64_t v = blockIdx.x; v < a.M; v += gridDim.x) {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(a.packed + v * a.stride);
+    // ---- exact genotype counts over the complete samples -> mean of the defined calls (RU:33-52) ----
+    if (threadIdx.x < 3) sh.counts[threadIdx.x] = 0;
+    __syncthreads();
+    {
+      int n1 = 0, n2 = 0, nm = 0;
+      for (int i = threadIdx.x; i < a.n; i += LT) {
+        const int s = __ldg(a.idx + i);
+        const uint32_t code = (__ldg(row + (s >> 4)) >> sample_shift(s & 15)) & 3u;
+        n1 += code == 1u;
+        n2 += code == 2u;
+        nm += code == 3u;
+      }
+      n1 = __reduce_add_sync(0xffffffffu, n1);
+      n2 = __reduce_add_sync(0xffffffffu, n2);
+      nm = __reduce_add_sync(0xffffffffu, nm);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sh.counts[0], n1);
+        atomicAdd(&sh.counts[1], n2);
+        atomicAdd(&sh.counts[2], nm);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      sh.mean = (double)(sh.counts[0] + 2 * sh.counts[1]) / (double)(a.n - sh.counts[2]);
+      sh.status = 0;
+    }
+    if (threadIdx.x < MM) sh.b[threadIdx.x] = ((int)threadIdx.x < K) ? b0[threadIdx.x] : 0.0;
+    __syncthreads();
+
+    int iter = 0;
+    double beta = nan_value(), se = nan_value(), z = nan_value(), chi2 = nan_value(), pv = nan_value();
+    bool converged = false, exploded = false;
+
+    if (a.test != 3) {
+      // =============== Wald / LRT: LogisticRegressionModel.fit(Some(nullFit)) ===============
+      eval_pass<MM, 0>(a, sh, row, m, m, false);
+      if (threadIdx.x == 0) {   // the covariate blocks of the first step are the null fit's (:311-325)
+        for (int i = 0; i < K; ++i) {
+          sh.score[i] = score0[i];
+          for (int j = 0; j < K; ++j) sh.F[i][j] = fisher0[i * K + j];
+        }
+      }
+      __syncthreads();
+      while (true) {
+        if (iter >= a.max_iter) break;
+        ++iter;
+        if (threadIdx.x == 0) {
+          for (int i = 0; i < m; ++i) {
+            sh.delta[i] = sh.score[i];
+            for (int j = 0; j < m; ++j) sh.W[i][j] = sh.F[i][j];
+          }
+          int st = 0;
+          if (!lu_solve<MM>(sh.W, sh.delta, m)) {
+            st = 2;                                   // MatrixSingularException -> exploded (:360-361)
+          } else if (isnan(sh.delta[0])) {
+            st = 2;
+          } else {
+            double mx = 0.0;
+            bool any_nan = false;
+            for (int i = 0; i < m; ++i) {
+              mx = fmax(mx, fabs(sh.delta[i]));   // breeze max(abs(.)): NaN entries other than [0] compare false
+              any_nan |= isnan(sh.delta[i]);
+            }
+            if (mx < a.tol && !any_nan) st = 1;
+            else
+              for (int i = 0; i < m; ++i) sh.b[i] += sh.delta[i];
+          }
+          sh.status = st;
+        }
+        __syncthreads();
+        const int st = sh.status;
+        if (st == 1) { converged = true; break; }
+        if (st == 2) { exploded = true; break; }
+        eval_pass<MM, 0>(a, sh, row, m, m, false);
+      }
+      if (converged) {
+        if (a.test == 1) {
+          if (threadIdx.x == 0) {
+            for (int i = 0; i < m; ++i)
+              for (int j = 0; j < m; ++j) sh.W[i][j] = sh.F[i][j];
+            sh.status = invert<MM>(sh.W, sh.Inv, m, &sh.logdet) ? 1 : 2;
+          }
+          __syncthreads();
+          if (sh.status == 1) {
+            beta = sh.b[K];
+            se = sqrt(sh.Inv[K][K]);
+            z = beta / se;
+            pv = erfc(fabs(z) * 0.70710678118654752440);   // 2 pnorm(-|z|)
+          }
+        } else {
+          eval_pass<MM, 0>(a, sh, row, m, m, true);         // logLkhd at the final mu (:365)
+          beta = sh.b[K];
+          chi2 = 2.0 * (sh.loglik - loglk0);
+          pv = chi2 > 0.0 ? erfc(sqrt(0.5 * chi2)) : (chi2 == chi2 ? 1.0 : chi2);   // pchisqtail(chi2, 1)
+        }
+      }
+    } else {
+      // =============== Firth: fitFirth with K, then K + 1 free coefficients (:155-199, :372-408) ===============
+      double ll_null = 0.0;
+      for (int stage = 0; stage < 2; ++stage) {
+        const int m0 = K + stage;
+        iter = 0;
+        converged = exploded = false;
+        while (!converged && !exploded && iter < a.max_iter) {
+          ++iter;
+          eval_pass<MM, 0>(a, sh, row, m, m0, true);         // F = X' W X over all m columns at mu(b[0..m0))
+          if (threadIdx.x == 0) {
+            for (int i = 0; i < m; ++i)
+              for (int j = 0; j < m; ++j) sh.W[i][j] = sh.F[i][j];
+            sh.status = invert<MM>(sh.W, sh.Inv, m, &sh.logdet) ? 0 : 2;
+          }
+          __syncthreads();
+          if (sh.status == 2) { exploded = true; break; }
+          const double ll_here = sh.loglik + 0.5 * sh.logdet;   // + sum log|diag R| (:397-399)
+          eval_pass<MM, 1>(a, sh, row, m, m0, false);
+          if (threadIdx.x == 0) {
+            for (int i = 0; i < m0; ++i) {
+              sh.delta[i] = sh.score[i];
+              for (int j = 0; j < m0; ++j) sh.W[i][j] = sh.F[i][j];
+            }
+            int st = 0;
+            if (!lu_solve<MM>(sh.W, sh.delta, m0)) {
+              st = 2;
+            } else if (isnan(sh.delta[0])) {
+              st = 2;
+            } else {
+              double mx = 0.0;
+              bool any_nan = false;
+              for (int i = 0; i < m0; ++i) {
+                mx = fmax(mx, fabs(sh.delta[i]));
+                any_nan |= isnan(sh.delta[i]);
+              }
+              if (mx < a.tol && !any_nan && iter > 1) st = 1;
+              else
+                for (int i = 0; i < m0; ++i) sh.b[i] += sh.delta[i];
+            }
+            sh.status = st;
+          }
+          __syncthreads();
+          if (sh.status == 1) {
+            converged = true;
+            if (stage == 0) ll_null = ll_here;
+            else {
+              beta = sh.b[K];
+              chi2 = 2.0 * (ll_here - ll_null);
+              pv = chi2 > 0.0 ? erfc(sqrt(0.5 * chi2)) : (chi2 == chi2 ? 1.0 : chi2);
+            }
+          } else if (sh.status == 2) {
+            exploded = true;
+          }
+          __syncthreads();
+        }
+        if (!converged) break;   // the null Firth fit did not converge: its fit record is reported (:196-197)
+        if (stage == 0 && threadIdx.x == 0) sh.b[K] = 0.0;
+        __syncthreads();
+      }
+    }
+
+    if (threadIdx.x == 0) {
+      if (a.out.beta) a.out.beta[v] = beta;
+      if (a.out.standard_error) a.out.standard_error[v] = se;
+      if (a.out.z_stat) a.out.z_stat[v] = z;
+      if (a.out.chi_sq_stat) a.out.chi_sq_stat[v] = chi2;
+      if (a.out.p_value) a.out.p_value[v] = pv;
+      if (a.out.n_iterations) a.out.n_iterations[v] = iter;
+      if (a.out.converged) a.out.converged[v] = converged ? 1 : 0;
+      if (a.out.exploded) a.out.exploded[v] = exploded ? 1 : 0;
+    }
+    __syncthreads();
+  }
+}
+
+template <int MM>
+void launch_mm(const LogitArgs& a, int grid, cudaStream_t st) {
+  logit_fit_kernel<MM><<<grid, LT, 0, st>>>(a);
+}
+
+void free_model(LogitModel* m) {
+  if (!m) return;
+  cudaFree(m->d_idx);
+  cudaFree(m->d_cov);
+  cudaFree(m->d_y);
+  cudaFree(m->d_null);
+  delete m;
+}
+
+}  // namespace
+
+void logit_release(Ctx* c) {
+  free_model(reinterpret_cast<LogitModel*>(c->logit_state));
+  c->logit_state = nullptr;
+}
+
+int logit_set_model(Ctx* c, int64_t n_samples_total, int32_t n, int32_t K, const int32_t* idx, const double* cov,
+                    const double* y, const double* b0, const double* score0, const double* fisher0, double loglk0) {
+  if (n_samples_total <= 0 || n <= 0 || n > n_samples_total) return fail(c, LRR_EINVAL, "lrr_set_logit_model: bad sample counts");
+  if (K < 1) return fail(c, LRR_EINVAL, "logistic regression requires at least one covariate expression");
+  if (K + 1 > 12) return fail(c, LRR_EINVAL, "lrr_set_logit_model: at most 11 covariates (the Fisher matrix lives in registers)");
+  if (n - K - 1 < 1) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "%d samples and %d %s (including x) implies %d degrees of freedom.", n, K + 1,
+             K == 1 ? "covariate" : "covariates", n - K - 1);
+    return fail(c, LRR_EINVAL, buf);
+  }
+  if (!idx || !cov || !y || !b0 || !score0 || !fisher0) return fail(c, LRR_EINVAL, "lrr_set_logit_model: NULL input array");
+  logit_release(c);
+  LogitModel* m = new LogitModel();
+  c->logit_state = m;
+  m->n = n;
+  m->K = K;
+  m->n_samples_total = n_samples_total;
+  std::vector<double> nf(2 * (size_t)K + (size_t)K * K + 1);
+  for (int i = 0; i < K; ++i) nf[i] = b0[i];
+  for (int i = 0; i < K; ++i) nf[K + i] = score0[i];
+  for (int i = 0; i < K * K; ++i) nf[2 * K + i] = fisher0[i];
+  nf[2 * K + K * K] = loglk0;
+  LRR_CUDA(c, cudaMalloc(&m->d_idx, sizeof(int32_t) * (size_t)n));
+  LRR_CUDA(c, cudaMemcpy(m->d_idx, idx, sizeof(int32_t) * (size_t)n, cudaMemcpyDefault));
+  LRR_CUDA(c, cudaMalloc(&m->d_cov, sizeof(double) * (size_t)K * n));
+  LRR_CUDA(c, cudaMemcpy(m->d_cov, cov, sizeof(double) * (size_t)K * n, cudaMemcpyDefault));
+  LRR_CUDA(c, cudaMalloc(&m->d_y, sizeof(double) * (size_t)n));
+  LRR_CUDA(c, cudaMemcpy(m->d_y, y, sizeof(double) * (size_t)n, cudaMemcpyDefault));
+  LRR_CUDA(c, cudaMalloc(&m->d_null, sizeof(double) * nf.size()));
+  LRR_CUDA(c, cudaMemcpy(m->d_null, nf.data(), sizeof(double) * nf.size(), cudaMemcpyHostToDevice));
+  return LRR_OK;
+}
+
+int logit_run(Ctx* c, const uint8_t* d_packed, int64_t M, int64_t stride, int64_t n_samples_total, int test, int max_iter,
+              double tol, const lrr_logit_out& out, cudaStream_t st) {
+  LogitModel* m = reinterpret_cast<LogitModel*>(c->logit_state);
+  if (!m) return fail(c, LRR_ESTATE, "lrr_run_logit: call lrr_set_logit_model first");
+  if (test < 1 || test > 3) return fail(c, LRR_EINVAL, "lrr_run_logit: test must be LRR_LOGIT_WALD, _LRT or _FIRTH");
+  if (M < 0 || max_iter < 0 || !(tol > 0.0)) return fail(c, LRR_EINVAL, "lrr_run_logit: bad arguments");
+  if (n_samples_total != m->n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_logit: n_samples_total differs from the model's");
+  if (stride % 4 != 0 || stride * 4 < n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_logit: bad packed_stride");
+  if (M == 0) return LRR_OK;
+  if (!d_packed) return fail(c, LRR_EINVAL, "lrr_run_logit: d_packed is NULL");
+  LogitArgs a;
+  a.packed = d_packed;
+  a.M = M;
+  a.stride = stride;
+  a.n = m->n;
+  a.K = m->K;
+  a.idx = m->d_idx;
+  a.cov = m->d_cov;
+  a.y = m->d_y;
+  a.null_fit = m->d_null;
+  a.test = test;
+  a.max_iter = max_iter;
+  a.tol = tol;
+  a.out = out;
+  const int64_t want = M < (int64_t)c->sm_count * 8 ? M : (int64_t)c->sm_count * 8;
+  const int grid = (int)want;
+  const int mm = m->K + 1;
+  if (mm <= 2) launch_mm<2>(a, grid, st);
+  else if (mm <= 3) launch_mm<3>(a, grid, st);
+  else if (mm <= 4) launch_mm<4>(a, grid, st);
+  else if (mm <= 5) launch_mm<5>(a, grid, st);
+  else if (mm <= 6) launch_mm<6>(a, grid, st);
+  else if (mm <= 8) launch_mm<8>(a, grid, st);
+  else if (mm <= 10) launch_mm<10>(a, grid, st);
+  else launch_mm<12>(a, grid, st);
+  c->launches++;
+  LRR_CUDA(c, cudaGetLastError());
+  return LRR_OK;
+}
+
+}  // namespace lrr

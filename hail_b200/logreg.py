@@ -1,16 +1,19 @@
-"""`logistic_regression_rows` (score test) -- host side of the B200 path.
+"""`logistic_regression_rows` (wald / lrt / score / firth) -- host side of the B200 path.
 
-Mirrors, for test='score',
+Mirrors
   * Python API + validation   hail/python/hail/methods/statgen.py:731-1012 (defaults max_iterations=25, tolerance=1e-6;
                               ValueError for no covariates / empty y; same pass_through rules as the linear path)
   * driver prologue           hail/hail/src/is/hail/methods/LogisticRegression.scala:38-100: complete samples over ALL
                               phenotypes and covariates, 0/1 and non-constant checks, d >= 1, one null model fit per
                               phenotype (fatal when Newton does not converge), stats/LogisticRegressionModel.scala:279-370
-  * output schema             key, pass_through, `chi_sq_stat`, `p_value` (scalars for one y; for a list of y the
-                              reference nests them in `logistic_regression: array<struct>` -- here arrays [M, P])
-The per-row loop (LogisticRegression.scala:115-157 with LogisticScoreTest, LogisticRegressionModel.scala:211-264) runs in
-the CUDA library behind lrr_set_score_model / lrr_run_score.  'wald', 'lrt' and 'firth' need per-variant Newton
-iterations and are not implemented.
+  * output schema             key, pass_through, then the test's fields (stats/LogisticRegressionModel.scala:56-62, 111-116,
+                              156-161, 212-215): wald `beta, standard_error, z_stat, p_value, fit`; lrt / firth `beta,
+                              chi_sq_stat, p_value, fit`; score `chi_sq_stat, p_value`; `fit` = struct{n_iterations,
+                              converged, exploded} (scalars for one y; for a list of y the reference nests them in
+                              `logistic_regression: array<struct>` -- here arrays [M, P])
+The per-row loop (LogisticRegression.scala:115-157) runs in the CUDA library: the score test on the float64 sweep
+(lrr_set_score_model / lrr_run_score), the Wald / LRT / Firth tests as per-variant Newton fits, one CTA per variant
+(lrr_set_logit_model / lrr_run_logit, csrc/logit_kernel.cu).
 """
 from __future__ import annotations
 
@@ -61,15 +64,21 @@ def _fit_null(C, y, max_iter, tol):
     return b, mu, score, fisher, it, converged, exploded
 
 
+def _fit_null_checked(C, y, max_iter, tol):
+    fit = _fit_null(C, y, max_iter, tol)
+    it, converged, exploded = fit[4], fit[5], fit[6]
+    if not converged:   # LogisticRegression.scala:83-90
+        raise FatalError("Failed to fit logistic regression null model (standard MLE with covariates only): " +
+                         (f"exploded at Newton iteration {it}" if exploded else "Newton iteration failed to converge"))
+    return fit
+
+
 def logistic_regression_rows(test, y, x, covariates, pass_through=(), *, max_iterations=None, tolerance=None) -> Table:
     """For each row, test an input variable for association with a binary response using logistic regression
     (drop-in for `hl.logistic_regression_rows(test='score', ...)`, statgen.py:731)."""
     if test not in ("wald", "lrt", "score", "firth"):
         raise TypeError("logistic_regression_rows: parameter 'test': expected one of 'wald', 'lrt', 'score', 'firth', "
                         f"found {test!r}")
-    if test != "score":
-        raise NotImplementedError(f"logistic_regression_rows: test={test!r} needs per-variant Newton iterations; only the "
-                                  "score test runs on the B200 path")
     if max_iterations is None:
         max_iterations = 25
     if tolerance is None:
@@ -116,36 +125,70 @@ def logistic_regression_rows(test, y, x, covariates, pass_through=(), *, max_ite
     dev = g.device
     ctx = _lib.context(dev.index)
     M, N, P = g.n_variants, g.n_samples, yk.shape[1]
-    chi = np.empty((M, P))
-    pv = np.empty((M, P))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    results = OrderedDict()
     with torch.cuda.device(dev):
-        d_chi = torch.empty(M, dtype=torch.float64, device=dev)
-        d_p = torch.empty(M, dtype=torch.float64, device=dev)
-        out = _lib.ScoreOut(d_chi.data_ptr(), d_p.data_ptr(), None)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        for col in range(P):
-            b, mu, score, fisher, it, converged, exploded = _fit_null(C, yk[:, col], max_iterations, tolerance)
-            if not converged:   # LogisticRegression.scala:83-90
-                raise FatalError("Failed to fit logistic regression null model (standard MLE with covariates only): " +
-                                 (f"exploded at Newton iteration {it}" if exploded else "Newton iteration failed to converge"))
-            w = mu * (1.0 - mu)
-            wc = np.ascontiguousarray((C * w[:, None]).T)        # [K, n]
-            resid = np.ascontiguousarray(yk[:, col] - mu)
-            finv = np.ascontiguousarray(np.linalg.inv(fisher))
-            ctx.check(ctx.lib.lrr_set_score_model(ctx.handle, N, n, k, idx.ctypes.data, wc.ctypes.data, resid.ctypes.data,
-                                                  np.ascontiguousarray(w).ctypes.data, finv.ctypes.data,
-                                                  np.ascontiguousarray(score).ctypes.data))
-            ctx.check(ctx.lib.lrr_run_score(ctx.handle, g.data.data_ptr(), g.flags_ptr(), M, g.stride, N,
-                                            ctypes.byref(out), stream))
-            torch.cuda.synchronize(dev)
-            chi[:, col] = d_chi.cpu().numpy()
-            pv[:, col] = d_p.cpu().numpy()
-        ctx.check(ctx.lib.lrr_clear_groups(ctx.handle))
+        if test == "score":
+            chi = np.empty((M, P))
+            pv = np.empty((M, P))
+            d_chi = torch.empty(M, dtype=torch.float64, device=dev)
+            d_p = torch.empty(M, dtype=torch.float64, device=dev)
+            out = _lib.ScoreOut(d_chi.data_ptr(), d_p.data_ptr(), None)
+            for col in range(P):
+                b, mu, score, fisher, it, converged, exploded = _fit_null_checked(C, yk[:, col], max_iterations, tolerance)
+                w = mu * (1.0 - mu)
+                wc = np.ascontiguousarray((C * w[:, None]).T)        # [K, n]
+                resid = np.ascontiguousarray(yk[:, col] - mu)
+                finv = np.ascontiguousarray(np.linalg.inv(fisher))
+                ctx.check(ctx.lib.lrr_set_score_model(ctx.handle, N, n, k, idx.ctypes.data, wc.ctypes.data, resid.ctypes.data,
+                                                      np.ascontiguousarray(w).ctypes.data, finv.ctypes.data,
+                                                      np.ascontiguousarray(score).ctypes.data))
+                ctx.check(ctx.lib.lrr_run_score(ctx.handle, g.data.data_ptr(), g.flags_ptr(), M, g.stride, N,
+                                                ctypes.byref(out), stream))
+                torch.cuda.synchronize(dev)
+                chi[:, col] = d_chi.cpu().numpy()
+                pv[:, col] = d_p.cpu().numpy()
+            ctx.check(ctx.lib.lrr_clear_groups(ctx.handle))
+            results["chi_sq_stat"] = chi
+            results["p_value"] = pv
+        else:
+            names = {"wald": ("beta", "standard_error", "z_stat", "p_value"), "lrt": ("beta", "chi_sq_stat", "p_value"),
+                     "firth": ("beta", "chi_sq_stat", "p_value")}[test]
+            code = {"wald": 1, "lrt": 2, "firth": 3}[test]
+            dev_out = {f: torch.empty(M, dtype=torch.float64, device=dev) for f in names}
+            dev_out["n_iterations"] = torch.empty(M, dtype=torch.int32, device=dev)
+            dev_out["converged"] = torch.empty(M, dtype=torch.uint8, device=dev)
+            dev_out["exploded"] = torch.empty(M, dtype=torch.uint8, device=dev)
+            out = _lib.LogitOut()
+            for f, t in dev_out.items():
+                setattr(out, f, t.data_ptr())
+            host = {f: np.empty((M, P), dtype={"n_iterations": np.int32, "converged": bool, "exploded": bool}.get(f, np.float64))
+                    for f in dev_out}
+            Ct = np.ascontiguousarray(C.T)                              # [K, n]
+            for col in range(P):
+                b, mu, score, fisher, it, converged, exploded = _fit_null_checked(C, yk[:, col], max_iterations, tolerance)
+                yc = np.ascontiguousarray(yk[:, col])
+                with np.errstate(divide="ignore"):
+                    loglik0 = float(np.sum(np.log(yc * mu + (1.0 - yc) * (1.0 - mu))))
+                b_c, s_c, f_c = (np.ascontiguousarray(v, dtype=np.float64) for v in (b, score, fisher))
+                ctx.check(ctx.lib.lrr_set_logit_model(ctx.handle, N, n, k, idx.ctypes.data, Ct.ctypes.data, yc.ctypes.data,
+                                                      b_c.ctypes.data, s_c.ctypes.data, f_c.ctypes.data, loglik0))
+                ctx.check(ctx.lib.lrr_run_logit(ctx.handle, g.data.data_ptr(), M, g.stride, N, code, int(max_iterations),
+                                                float(tolerance), ctypes.byref(out), stream))
+                torch.cuda.synchronize(dev)
+                for f, t in dev_out.items():
+                    host[f][:, col] = t.cpu().numpy()
+            for f in names:
+                results[f] = host[f]
+            results["fit"] = {f: host[f] for f in ("n_iterations", "converged", "exploded")}
     fields = OrderedDict()
     for kf in mt.row_key:
         fields[kf] = mt.row[kf]
     for kf, v in row_fields.items():
         fields[kf] = v
-    fields["chi_sq_stat"] = chi if y_is_list else chi[:, 0]
-    fields["p_value"] = pv if y_is_list else pv[:, 0]
+    for kf, v in results.items():
+        if isinstance(v, dict):
+            fields[kf] = {kk: (vv if y_is_list else vv[:, 0]) for kk, vv in v.items()}
+        else:
+            fields[kf] = v if y_is_list else v[:, 0]
     return Table(fields, key=mt.row_key, n_rows=mt.count_rows())

@@ -188,6 +188,35 @@ int lrr_set_score_model(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_
 int lrr_run_score(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
                   int64_t n_samples_total, const lrr_score_out* out, void* stream);
 
+/* ---- logistic regression, Wald / likelihood-ratio / Firth tests (`hl.logistic_regression_rows(test='wald'|'lrt'|'firth')`)
+ * The per-row loop of hail/hail/src/is/hail/methods/LogisticRegression.scala:115-157 with WaldTest, LikelihoodRatioTest and
+ * LogisticFirthTest (stats/LogisticRegressionModel.scala:55-199; the Newton fits :294-408): one CTA per variant iterates
+ * in float64 on the mean-imputed genotype column.  The host fits the null model once (LogisticRegression.scala:67-91)
+ * and passes, for the n complete samples (ascending complete_idx): cov [K, n], y [n] (0 / 1), the null coefficients
+ * b0 [K], and the null fit's last score [K], Fisher matrix [K, K] and log-likelihood (the first Newton step of the full
+ * model reuses them, LogisticRegressionModel.scala:311-325).  K <= 11.
+ * lrr_run_logit writes, per variant, the fields of the test's schema (`standard_error`, `z_stat`: Wald only;
+ * `chi_sq_stat`: LRT / Firth only; NaN where the reference leaves them missing: fit not converged or singular) and the
+ * `fit` struct (n_iterations, converged, exploded).  NULL output pointers are skipped. */
+#define LRR_LOGIT_WALD 1
+#define LRR_LOGIT_LRT 2
+#define LRR_LOGIT_FIRTH 3
+typedef struct {
+  double* beta;
+  double* standard_error;
+  double* z_stat;
+  double* chi_sq_stat;
+  double* p_value;
+  int32_t* n_iterations;
+  uint8_t* converged;
+  uint8_t* exploded;
+} lrr_logit_out;
+int lrr_set_logit_model(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, const int32_t* complete_idx,
+                        const double* cov, const double* y, const double* b0, const double* score0, const double* fisher0,
+                        double loglik0);
+int lrr_run_logit(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int64_t packed_stride, int64_t n_samples_total,
+                  int32_t test, int32_t max_iterations, double tolerance, const lrr_logit_out* out, void* stream);
+
 /* two-sided Student-t p-value on the device, exposed for unit tests of the epilogue:
  * p[i] = 2 * P[T_df <= -|t[i]|]  (jdistlib T.cumulative call sites LR:160, LR:344) */
 int lrr_student_t_two_sided(lrr_ctx* ctx, const double* d_t, int64_t count, double df, double* d_p, double* d_log10_p,

@@ -59,6 +59,7 @@ def chi_sq_tail_1(chi2):
     out = np.full(chi2.shape, np.nan)
     ok = chi2 >= 0
     out[ok] = [math.erfc(math.sqrt(v / 2.0)) for v in chi2[ok]]
+    out[chi2 < 0] = 1.0          # a roundoff-negative statistic: the upper tail is the whole distribution (R: pchisq)
     return out
 
 

@@ -650,8 +650,6 @@ def test_logistic_score_vs_oracle_and_errors():
         hb.logistic_regression_rows("score", [], mt.GT.n_alt_alleles(), [1.0])
     with pytest.raises(TypeError):
         hb.logistic_regression_rows("rao", mt.y2, mt.GT.n_alt_alleles(), [1.0])
-    with pytest.raises(NotImplementedError):
-        hb.logistic_regression_rows("wald", mt.y2, mt.GT.n_alt_alleles(), [1.0])
     bad = mt.annotate_cols(q=rng.normal(size=N), one=np.ones(N), sep=np.where(y2 > 0, 9.0, -9.0))
     with pytest.raises(hb.FatalError, match="equal to 0 or 1"):
         hb.logistic_regression_rows("score", bad.q, bad.GT.n_alt_alleles(), [1.0])
