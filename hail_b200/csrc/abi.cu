@@ -434,7 +434,14 @@ int lrr_run_logit(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int
   CTX_PROLOGUE;
   if (!out) return fail(c, LRR_EINVAL, "lrr_run_logit: out is NULL");
   if (int r = check_packed(c, n_samples_total, packed_stride)) return r;
-  return logit_run(c, d_packed, n_variants, packed_stride, n_samples_total, test, max_iterations, tolerance, *out, st);
+  return logit_run(c, d_packed, nullptr, n_variants, packed_stride, n_samples_total, test, max_iterations, tolerance, *out, st);
+}
+
+int lrr_run_logit_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t ldx, int64_t n_samples_total, int32_t test,
+                        int32_t max_iterations, double tolerance, const lrr_logit_out* out, void* stream) {
+  CTX_PROLOGUE;
+  if (!out) return fail(c, LRR_EINVAL, "lrr_run_logit_dense: out is NULL");
+  return logit_run(c, nullptr, d_x, n_variants, ldx, n_samples_total, test, max_iterations, tolerance, *out, st);
 }
 
 int lrr_reserve(lrr_ctx* ctx, int64_t max_variants) {

@@ -118,8 +118,8 @@ int launch_student_t(Ctx*, const double*, int64_t, double, double*, double*, cud
 int launch_score_epilogue(Ctx*, int64_t M, const lrr_score_out& out, cudaStream_t);
 int logit_set_model(Ctx*, int64_t n_samples_total, int32_t n, int32_t K, const int32_t* idx, const double* cov, const double* y,
                     const double* b0, const double* score0, const double* fisher0, double loglk0);
-int logit_run(Ctx*, const uint8_t* d_packed, int64_t M, int64_t stride, int64_t n_samples_total, int test, int max_iter,
-              double tol, const lrr_logit_out& out, cudaStream_t);
+int logit_run(Ctx*, const uint8_t* d_packed, const double* d_dense, int64_t M, int64_t stride, int64_t n_samples_total,
+              int test, int max_iter, double tol, const lrr_logit_out& out, cudaStream_t);
 void logit_release(Ctx*);
 
 // position of sample `j` (0..15 within its word) in the packed word: bits [8i+2s, 8i+2s+1], j = 4s+i

@@ -35,7 +35,9 @@ struct LogitModel {
 };
 
 struct LogitArgs {
-  const uint8_t* packed;
+  const uint8_t* packed;   // 2-bit rows, or
+  const double* dense;     // [M][ldx] float64 entries over all stored samples, NaN = missing (packed == nullptr)
+  int64_t ldx;
   int64_t M, stride;
   int n, K;
   const int32_t* idx;
@@ -137,7 +139,8 @@ struct Shared {
 //   MODE 0: score[a] = sum x_a (y - mu), F[a][b] = sum w x_a x_b, loglik = sum log(y mu + (1 - y)(1 - mu))   (all m columns)
 //   MODE 1: Firth second pass: score[a] = sum x_a (y - mu + h (1/2 - mu)) with h = w x' Inv x
 template <int MM, int MODE>
-__device__ void eval_pass(const LogitArgs& a, Shared<MM>& sh, const uint32_t* row, int m, int m0, bool want_loglik) {
+__device__ void eval_pass(const LogitArgs& a, Shared<MM>& sh, const uint32_t* row, const double* drow, int m, int m0,
+                          bool want_loglik) {
   constexpr int NF = MM * (MM + 1) / 2;
   double sc[MM], fi[NF];
   double ll = 0.0;
@@ -164,8 +167,14 @@ __device__ void eval_pass(const LogitArgs& a, Shared<MM>& sh, const uint32_t* ro
     for (int k = 0; k < MM - 1; ++k)
       if (k < K) xa[k] = __ldg(a.cov + (int64_t)k * a.n + i);
     const int s = __ldg(a.idx + i);
-    const uint32_t code = (__ldg(row + (s >> 4)) >> sample_shift(s & 15)) & 3u;
-    const double x = (code == 3u) ? mean : (double)code;
+    double x;
+    if (drow) {
+      x = __ldg(drow + s);
+      if (x != x) x = mean;
+    } else {
+      const uint32_t code = (__ldg(row + (s >> 4)) >> sample_shift(s & 15)) & 3u;
+      x = (code == 3u) ? mean : (double)code;
+    }
 #pragma unroll
     for (int k = 0; k < MM; ++k)
       if (k == K) xa[k] = x;
@@ -243,11 +252,32 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
   const double* fisher0 = a.null_fit + 2 * K;
   const double loglk0 = a.null_fit[2 * K + K * K];
   for (int64_t v = blockIdx.x; v < a.M; v += gridDim.x) {
-    const uint32_t* row = reinterpret_cast<const uint32_t*>(a.packed + v * a.stride);
+    const uint32_t* row = a.packed ? reinterpret_cast<const uint32_t*>(a.packed + v * a.stride) : nullptr;
+    const double* drow = a.packed ? nullptr : a.dense + v * a.ldx;
     // ---- exact genotype counts over the complete samples -> mean of the defined calls (RU:33-52) ----
     if (threadIdx.x < 3) sh.counts[threadIdx.x] = 0;
+    if (threadIdx.x == 0) sh.loglik = 0.0;
     __syncthreads();
-    {
+    if (drow) {   // dense entries: sum and count of the defined ones
+      double sum = 0.0;
+      int nd = 0;
+      for (int i = threadIdx.x; i < a.n; i += LT) {
+        const double xv = __ldg(drow + __ldg(a.idx + i));
+        if (xv == xv) { sum += xv; ++nd; }
+      }
+      sum = warp_sum(sum);
+      nd = __reduce_add_sync(0xffffffffu, nd);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sh.counts[0], nd);
+        sh.red[threadIdx.x >> 5][0] = sum;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < LT / 32; ++w) t += sh.red[w][0];
+        sh.loglik = t;   // scratch: the sum of the defined entries
+      }
+    } else {
       int n1 = 0, n2 = 0, nm = 0;
       for (int i = threadIdx.x; i < a.n; i += LT) {
         const int s = __ldg(a.idx + i);
@@ -267,7 +297,8 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      sh.mean = (double)(sh.counts[0] + 2 * sh.counts[1]) / (double)(a.n - sh.counts[2]);
+      sh.mean = drow ? sh.loglik / (double)sh.counts[0]
+                     : (double)(sh.counts[0] + 2 * sh.counts[1]) / (double)(a.n - sh.counts[2]);
       sh.status = 0;
     }
     if (threadIdx.x < MM) sh.b[threadIdx.x] = ((int)threadIdx.x < K) ? b0[threadIdx.x] : 0.0;
@@ -279,7 +310,7 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
 
     if (a.test != 3) {
       // =============== Wald / LRT: LogisticRegressionModel.fit(Some(nullFit)) ===============
-      eval_pass<MM, 0>(a, sh, row, m, m, false);
+      eval_pass<MM, 0>(a, sh, row, drow, m, m, false);
       if (threadIdx.x == 0) {   // the covariate blocks of the first step are the null fit's (:311-325)
         for (int i = 0; i < K; ++i) {
           sh.score[i] = score0[i];
@@ -317,7 +348,7 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
         const int st = sh.status;
         if (st == 1) { converged = true; break; }
         if (st == 2) { exploded = true; break; }
-        eval_pass<MM, 0>(a, sh, row, m, m, false);
+        eval_pass<MM, 0>(a, sh, row, drow, m, m, false);
       }
       if (converged) {
         if (a.test == 1) {
@@ -334,7 +365,7 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
             pv = erfc(fabs(z) * 0.70710678118654752440);   // 2 pnorm(-|z|)
           }
         } else {
-          eval_pass<MM, 0>(a, sh, row, m, m, true);         // logLkhd at the final mu (:365)
+          eval_pass<MM, 0>(a, sh, row, drow, m, m, true);         // logLkhd at the final mu (:365)
           beta = sh.b[K];
           chi2 = 2.0 * (sh.loglik - loglk0);
           pv = chi2 > 0.0 ? erfc(sqrt(0.5 * chi2)) : (chi2 == chi2 ? 1.0 : chi2);   // pchisqtail(chi2, 1)
@@ -349,7 +380,7 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
         converged = exploded = false;
         while (!converged && !exploded && iter < a.max_iter) {
           ++iter;
-          eval_pass<MM, 0>(a, sh, row, m, m0, true);         // F = X' W X over all m columns at mu(b[0..m0))
+          eval_pass<MM, 0>(a, sh, row, drow, m, m0, true);         // F = X' W X over all m columns at mu(b[0..m0))
           if (threadIdx.x == 0) {
             for (int i = 0; i < m; ++i)
               for (int j = 0; j < m; ++j) sh.W[i][j] = sh.F[i][j];
@@ -358,7 +389,7 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
           __syncthreads();
           if (sh.status == 2) { exploded = true; break; }
           const double ll_here = sh.loglik + 0.5 * sh.logdet;   // + sum log|diag R| (:397-399)
-          eval_pass<MM, 1>(a, sh, row, m, m0, false);
+          eval_pass<MM, 1>(a, sh, row, drow, m, m0, false);
           if (threadIdx.x == 0) {
             for (int i = 0; i < m0; ++i) {
               sh.delta[i] = sh.score[i];
@@ -471,18 +502,21 @@ int logit_set_model(Ctx* c, int64_t n_samples_total, int32_t n, int32_t K, const
   return LRR_OK;
 }
 
-int logit_run(Ctx* c, const uint8_t* d_packed, int64_t M, int64_t stride, int64_t n_samples_total, int test, int max_iter,
-              double tol, const lrr_logit_out& out, cudaStream_t st) {
+int logit_run(Ctx* c, const uint8_t* d_packed, const double* d_dense, int64_t M, int64_t stride, int64_t n_samples_total,
+              int test, int max_iter, double tol, const lrr_logit_out& out, cudaStream_t st) {
   LogitModel* m = reinterpret_cast<LogitModel*>(c->logit_state);
   if (!m) return fail(c, LRR_ESTATE, "lrr_run_logit: call lrr_set_logit_model first");
   if (test < 1 || test > 3) return fail(c, LRR_EINVAL, "lrr_run_logit: test must be LRR_LOGIT_WALD, _LRT or _FIRTH");
   if (M < 0 || max_iter < 0 || !(tol > 0.0)) return fail(c, LRR_EINVAL, "lrr_run_logit: bad arguments");
   if (n_samples_total != m->n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_logit: n_samples_total differs from the model's");
-  if (stride % 4 != 0 || stride * 4 < n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_logit: bad packed_stride");
+  if (d_dense ? stride < n_samples_total : (stride % 4 != 0 || stride * 4 < n_samples_total))
+    return fail(c, LRR_EINVAL, "lrr_run_logit: bad row stride");
   if (M == 0) return LRR_OK;
-  if (!d_packed) return fail(c, LRR_EINVAL, "lrr_run_logit: d_packed is NULL");
+  if (!d_packed && !d_dense) return fail(c, LRR_EINVAL, "lrr_run_logit: the row pointer is NULL");
   LogitArgs a;
-  a.packed = d_packed;
+  a.packed = d_dense ? nullptr : d_packed;
+  a.dense = d_dense;
+  a.ldx = stride;
   a.M = M;
   a.stride = stride;
   a.n = m->n;

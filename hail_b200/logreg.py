@@ -118,8 +118,13 @@ def logistic_regression_rows(test, y, x, covariates, pass_through=(), *, max_ite
     log.info("logistic_regression_rows: running %s on %d samples for response variable y,\n"
              "    with input variable x, and %d additional %s...", test, n, k, _plural(k, "covariate"))
 
-    from .genotypes import HostBedGenotypes
+    from .genotypes import DenseDosage, HostBedGenotypes
     g = mt.genotypes
+    dense = isinstance(g, DenseDosage)
+    if dense != (x.kind == "dosage"):
+        raise ExpressionException("'logistic_regression_rows/x': a dense dosage field needs a DenseDosage entry matrix")
+    if dense and test == "score":
+        raise NotImplementedError("logistic_regression_rows: test='score' on dense dosages")
     if isinstance(g, HostBedGenotypes):   # the score path sweeps a resident store
         g = g.to_device()
     dev = g.device
@@ -173,8 +178,12 @@ def logistic_regression_rows(test, y, x, covariates, pass_through=(), *, max_ite
                 b_c, s_c, f_c = (np.ascontiguousarray(v, dtype=np.float64) for v in (b, score, fisher))
                 ctx.check(ctx.lib.lrr_set_logit_model(ctx.handle, N, n, k, idx.ctypes.data, Ct.ctypes.data, yc.ctypes.data,
                                                       b_c.ctypes.data, s_c.ctypes.data, f_c.ctypes.data, loglik0))
-                ctx.check(ctx.lib.lrr_run_logit(ctx.handle, g.data.data_ptr(), M, g.stride, N, code, int(max_iterations),
-                                                float(tolerance), ctypes.byref(out), stream))
+                if dense:
+                    ctx.check(ctx.lib.lrr_run_logit_dense(ctx.handle, g.data.data_ptr(), M, N, N, code, int(max_iterations),
+                                                          float(tolerance), ctypes.byref(out), stream))
+                else:
+                    ctx.check(ctx.lib.lrr_run_logit(ctx.handle, g.data.data_ptr(), M, g.stride, N, code,
+                                                    int(max_iterations), float(tolerance), ctypes.byref(out), stream))
                 torch.cuda.synchronize(dev)
                 for f, t in dev_out.items():
                     host[f][:, col] = t.cpu().numpy()

@@ -216,6 +216,10 @@ int lrr_set_logit_model(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_
                         double loglik0);
 int lrr_run_logit(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int64_t packed_stride, int64_t n_samples_total,
                   int32_t test, int32_t max_iterations, double tolerance, const lrr_logit_out* out, void* stream);
+/* the same fits for a dense float64 x ([n_variants, ldx] on the device, NaN = missing): pl_dosage / gp_dosage inputs,
+ * hail/python/test/hail/methods/test_statgen.py:851-938 */
+int lrr_run_logit_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t ldx, int64_t n_samples_total, int32_t test,
+                        int32_t max_iterations, double tolerance, const lrr_logit_out* out, void* stream);
 
 /* two-sided Student-t p-value on the device, exposed for unit tests of the epilogue:
  * p[i] = 2 * P[T_df <= -|t[i]|]  (jdistlib T.cumulative call sites LR:160, LR:344) */

@@ -15,7 +15,7 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 
 
 def main():
-    samples, gt = None, []
+    samples, gt, pl = None, [], []
     with open(f"{RES}/regressionLogistic.vcf") as f:
         for line in f:
             if line.startswith("##"):
@@ -24,11 +24,25 @@ def main():
             if line.startswith("#"):
                 samples = parts[9:]
                 continue
-            row = []
+            row, pl_row = [], []
+            fmt = parts[8].split(":")
             for cell in parts[9:]:
-                g = cell.split(":")[0]
+                fields = dict(zip(fmt, cell.split(":")))
+                g = fields["GT"]
                 row.append(None if "." in g else sum(int(a) for a in g.replace("|", "/").split("/")))
+                p = fields.get("PL", ".")
+                pl_row.append(None if p == "." else [int(v) for v in p.split(",")])
             gt.append(row)
+            pl.append(pl_row)
+    # regressionLogistic.gen: GP triples in .sample order; missing when |sum - 1| > 0.2 (methods/impex.py import_gen)
+    with open(f"{RES}/regressionLogistic.sample") as f:
+        gen_samples = [line.split()[0] for line in f.read().splitlines()[2:] if line.strip()]
+    gp = []
+    with open(f"{RES}/regressionLogistic.gen") as f:
+        for line in f:
+            vals = [float(v) for v in line.split()[6:]]
+            gp.append([None if abs(sum(vals[i:i + 3]) - 1.0) > 0.2 else vals[i:i + 3] for i in range(0, len(vals), 3)])
+    assert gen_samples == samples and len(gp) == len(gt), (gen_samples, samples)
     cov = {}
     with open(f"{RES}/regressionLogistic.cov") as f:
         f.readline()
@@ -47,6 +61,8 @@ def main():
         "source": "hail/hail/test/resources/regressionLogistic.{vcf,cov}, regressionLogisticBoolean.pheno",
         "samples": samples,
         "gt_n_alt_alleles": gt,
+        "pl": pl,
+        "gp": gp,
         "cov_table": cov,
         "pheno_table": pheno,
         "expected_score": {   # test_statgen.py:1007-1021, places=6
@@ -60,6 +76,12 @@ def main():
             "2": {"beta": -0.43659460858, "standard_error": 1.0296902941, "z_stat": -0.4240057531, "p_value": 0.6715616176},
             "not_converged": [3],
             "constant": [6, 7, 8, 9, 10],   # not converged, p NaN or |p - 1| < 1e-4
+        },
+        "expected_wald_dosage": {   # test_statgen.py:851-938: x = pl_dosage(PL) (places=6) and gp_dosage(GP) (places=4)
+            "1": {"beta": -0.8286774, "standard_error": 2.151145, "z_stat": -0.3852261, "p_value": 0.7000699},
+            "2": {"beta": -0.4431764, "standard_error": 1.045213, "z_stat": -0.4240058, "p_value": 0.6715616},
+            "not_converged": [3],
+            "constant": [6, 7, 8, 9, 10],
         },
         "expected_lrt": {     # test_statgen.py:958-985
             "1": {"beta": -0.81226793796, "chi_sq_stat": 0.1503349167, "p_value": 0.6982155052},

@@ -133,3 +133,31 @@ def test_multi_pheno_shapes_and_errors():
     with pytest.raises(Exception, match="at most 11 covariates"):
         many = mt.annotate_cols(**{f"k{i}": rng.normal(size=N) for i in range(12)})
         hb.logistic_regression_rows("wald", many.y1, many.GT.n_alt_alleles(), [1.0] + [many[f"k{i}"] for i in range(12)])
+
+
+@pytest.mark.parametrize("which", ["pl", "gp"])
+def test_wald_on_dense_dosages(which):   # TS:851-938, through DenseDosage -> lrr_run_logit_dense
+    hb = _hb()
+    from tests.helpers import gp_dosage, pl_dosage
+    doc, x, y, cov = load_regression_logistic()
+    dos = pl_dosage(doc) if which == "pl" else gp_dosage(doc)
+    mt = hb.MatrixTable(hb.DenseDosage(dos), cols={"y": y, "c1": cov[:, 1], "c2": cov[:, 2]})
+    exp = doc["expected_wald_dosage"]
+    tol = 5e-7 if which == "pl" else 5e-5
+    ht = hb.logistic_regression_rows("wald", mt.y, mt.x, [1.0, mt.c1, mt.c2])
+    for pos in ("1", "2"):
+        for f, v in exp[pos].items():
+            assert abs(ht[f][int(pos) - 1] - v) < tol, (which, pos, f, ht[f][int(pos) - 1])
+    assert not ht.fit["converged"][2]
+    for test in ("wald", "lrt", "firth"):
+        got = hb.logistic_regression_rows(test, mt.y, mt.x, [1.0, mt.c1, mt.c2])
+        want = L.logreg_rows(test, dos, y, cov)
+        conv = want["converged"] & got.fit["converged"]
+        info = (test, got.fit["converged"].tolist(), want["converged"].tolist(), got.fit["n_iterations"].tolist(),
+                want["n_iterations"].tolist())
+        assert np.array_equal(got.fit["converged"][:2], want["converged"][:2]), info
+        assert conv[:2].all() or test == "firth", info
+        for f in ("beta", "p_value"):
+            _close(np.asarray(got[f])[:2][conv[:2]], want[f][:2][conv[:2]], 1e-5, f"{test} {f}")   # rows 6-10 are degenerate
+    with pytest.raises(NotImplementedError):
+        hb.logistic_regression_rows("score", mt.y, mt.x, [1.0, mt.c1, mt.c2])

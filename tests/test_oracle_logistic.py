@@ -89,3 +89,20 @@ def test_epacts_all_four_tests():  # test_statgen.py:1722-1862
     assert fi["beta"] == pytest.approx(z["firth"][:, 0], rel=1e-4)
     assert fi["p_value"] == pytest.approx(z["firth"][:, 1], rel=1e-4)
     assert fi["converged"].all() and w["converged"].all()
+
+
+@pytest.mark.parametrize("which", ["pl", "gp"])
+def test_wald_on_dosages(which):   # test_statgen.py:851-938
+    from tests.helpers import gp_dosage, pl_dosage
+    doc, x, y, cov = load_regression_logistic()
+    dos = pl_dosage(doc) if which == "pl" else gp_dosage(doc)
+    out = L.logreg_rows("wald", dos, y, cov)
+    exp = doc["expected_wald_dosage"]
+    tol = 5e-7 if which == "pl" else 5e-5
+    for pos in ("1", "2"):
+        for f, v in exp[pos].items():
+            assert abs(out[f][int(pos) - 1] - v) < tol, (which, pos, f, out[f][int(pos) - 1])
+    assert not out["converged"][2]
+    for pos in exp["constant"]:
+        i = pos - 1
+        assert (not out["converged"][i]) or np.isnan(out["p_value"][i]) or abs(out["p_value"][i] - 1) < 1e-4
