@@ -5,7 +5,7 @@ and fails loudly if it is missing -- there is no CPU fallback.
 """
 from .matrixtable import (ColumnExpression, EntryExpression, ExpressionException, MatrixTable, RowExpression, Struct,
                           Table)
-from .statgen import FatalError, linear_regression_rows, _get_regression_row_fields, _warn_if_no_intercept
+from .statgen import FatalError, lambda_gc, linear_regression_rows, _get_regression_row_fields, _warn_if_no_intercept
 
 
 def __getattr__(name):  # lazy: these import torch-side helpers
@@ -24,5 +24,5 @@ def __getattr__(name):  # lazy: these import torch-side helpers
     raise AttributeError(name)
 
 
-__all__ = ["linear_regression_rows", "logistic_regression_rows", "MatrixTable", "Table", "FatalError", "ExpressionException", "PackedGenotypes",
+__all__ = ["linear_regression_rows", "lambda_gc", "logistic_regression_rows", "MatrixTable", "Table", "FatalError", "ExpressionException", "PackedGenotypes",
            "HostBedGenotypes", "import_plink", "export_plink", "import_fam", "balding_nichols_model"]

@@ -85,6 +85,7 @@ SIGNATURES = {
     "lrr_run_logit_dense": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.POINTER(LogitOut),
                                            ctypes.c_void_p]),
+    "lrr_qchisqtail1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "lrr_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "lrr_last_kernel": (ctypes.c_int, [ctypes.c_void_p]),
     "lrr_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

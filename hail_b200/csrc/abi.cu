@@ -488,4 +488,10 @@ int lrr_student_t_two_sided(lrr_ctx* ctx, const double* d_t, int64_t count, doub
   return launch_student_t(c, d_t, count, df, d_p, d_log10_p, st);
 }
 
+int lrr_qchisqtail1(lrr_ctx* ctx, const double* d_p, int64_t count, double* d_chi2, void* stream) {
+  CTX_PROLOGUE;
+  if (count < 0 || (count > 0 && (!d_p || !d_chi2))) return fail(c, LRR_EINVAL, "lrr_qchisqtail1: bad arguments");
+  return launch_qchisqtail1(c, d_p, count, d_chi2, st);
+}
+
 }  // extern "C"

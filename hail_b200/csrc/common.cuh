@@ -115,6 +115,7 @@ int launch_stats_epilogue(Ctx*, int g, int64_t M, const lrr_group_out& out, cuda
 int run_rows(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, int64_t n_samples_total,
              const lrr_group_out* outs, int32_t n_outs, int32_t kernel, cudaStream_t);
 int launch_student_t(Ctx*, const double*, int64_t, double, double*, double*, cudaStream_t);
+int launch_qchisqtail1(Ctx*, const double* d_p, int64_t count, double* d_out, cudaStream_t);
 int launch_score_epilogue(Ctx*, int64_t M, const lrr_score_out& out, cudaStream_t);
 int logit_set_model(Ctx*, int64_t n_samples_total, int32_t n, int32_t K, const int32_t* idx, const double* cov, const double* y,
                     const double* b0, const double* score0, const double* fisher0, double loglk0);

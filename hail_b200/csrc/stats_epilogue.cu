@@ -120,6 +120,24 @@ int launch_score_epilogue(Ctx* c, int64_t M, const lrr_score_out& out, cudaStrea
   return LRR_OK;
 }
 
+// chi2[i] = qchisqtail(p[i], 1) = 2 erfcinv(p)^2: the statistic whose upper tail is p (lambda_gc, statgen.py:3121-3128)
+__global__ void qchisqtail1_kernel(const double* __restrict__ p, int64_t count, double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const double e = erfcinv(p[i]);
+    out[i] = 2.0 * e * e;
+  }
+}
+
+int launch_qchisqtail1(Ctx* c, const double* d_p, int64_t count, double* d_out, cudaStream_t st) {
+  if (count == 0) return LRR_OK;
+  int64_t grid = (count + 255) / 256;
+  if (grid > 4096) grid = 4096;
+  qchisqtail1_kernel<<<(int)grid, 256, 0, st>>>(d_p, count, d_out);
+  c->launches++;
+  LRR_CUDA(c, cudaGetLastError());
+  return LRR_OK;
+}
+
 int launch_student_t(Ctx* c, const double* d_t, int64_t count, double df, double* d_p, double* d_l10,
                      cudaStream_t st) {
   if (count == 0) return LRR_OK;

@@ -450,3 +450,24 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
     t = Table(fields, key=mt.row_key, n_rows=mt.count_rows())
     t.n_missing = [h["n_missing"] for h in host] if is_chained else host[0]["n_missing"]
     return t
+
+
+def lambda_gc(p_value, approximate=True, device=0) -> float:
+    """Genomic inflation factor of a set of p-values: median(qchisqtail(p, 1)) / qchisqtail(0.5, 1) over the non-NaN
+    p-values (drop-in for `hl.lambda_gc`, statgen.py:3096-3128; `approximate` is accepted and ignored -- the median is
+    exact here).  The quantile function runs on the device (lrr_qchisqtail1), the order statistic in torch."""
+    p = np.ascontiguousarray(np.asarray(p_value, dtype=np.float64).reshape(-1))
+    dev = torch.device("cuda", device)
+    ctx = _lib.context(dev.index)
+    with torch.cuda.device(dev):
+        d_p = torch.from_numpy(p).to(dev)
+        d_p = d_p[~torch.isnan(d_p)].contiguous()
+        if d_p.numel() == 0:
+            return float("nan")
+        chi = torch.empty_like(d_p)
+        ctx.check(ctx.lib.lrr_qchisqtail1(ctx.handle, d_p.data_ptr(), d_p.numel(), chi.data_ptr(),
+                                          torch.cuda.current_stream(dev).cuda_stream))
+        srt = torch.sort(chi).values
+        n = srt.numel()
+        med = srt[n // 2] if n % 2 else 0.5 * (srt[n // 2 - 1] + srt[n // 2])
+        return float(med) / 0.454936423119572   # qchisqtail(0.5, 1)

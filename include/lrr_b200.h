@@ -225,6 +225,9 @@ int lrr_run_logit_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int
  * p[i] = 2 * P[T_df <= -|t[i]|]  (jdistlib T.cumulative call sites LR:160, LR:344) */
 int lrr_student_t_two_sided(lrr_ctx* ctx, const double* d_t, int64_t count, double df, double* d_p, double* d_log10_p,
                             void* stream);
+/* chi2[i] = qchisqtail(p[i], 1), the 1-d.o.f. chi-squared statistic whose upper tail is p: the per-row half of
+ * `hl.lambda_gc` (hail/python/hail/methods/statgen.py:3096-3128), a downstream consumer of `p_value` */
+int lrr_qchisqtail1(lrr_ctx* ctx, const double* d_p, int64_t count, double* d_chi2, void* stream);
 
 #ifdef __cplusplus
 }

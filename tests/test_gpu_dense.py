@@ -140,3 +140,19 @@ def test_dense_rejects_mismatched_sources():
         mt.GT
     with pytest.raises(NotImplementedError):
         hb.linear_regression_rows(y=mt.y, x=mt.x, covariates=[1.0], weights=mt.y)
+
+
+def test_lambda_gc():   # statgen.py:3096-3128
+    hb = _hb()
+    import scipy.stats as st
+    rng = np.random.default_rng(8)
+    p = rng.random(10001)
+    p[::50] = np.nan
+    p[3] = 1e-300
+    ok = p[~np.isnan(p)]
+    want = np.median(st.chi2.isf(ok, 1)) / st.chi2.isf(0.5, 1)
+    assert hb.lambda_gc(p) == pytest.approx(want, rel=1e-10)
+    assert hb.lambda_gc(p[:-1]) == pytest.approx(np.median(st.chi2.isf(p[:-1][~np.isnan(p[:-1])], 1)) / st.chi2.isf(0.5, 1), rel=1e-10)
+    assert np.isnan(hb.lambda_gc(np.array([np.nan])))
+    # uniform p-values: no inflation
+    assert abs(hb.lambda_gc(rng.random(200001)) - 1.0) < 0.02
