@@ -18,11 +18,14 @@ def __getattr__(name):  # lazy: these import torch-side helpers
     if name == "logistic_regression_rows":
         from .logreg import logistic_regression_rows
         return logistic_regression_rows
+    if name == "hwe_normalized_pca":
+        from .pca import hwe_normalized_pca
+        return hwe_normalized_pca
     if name in ("balding_nichols_model", "bn_parameters", "bn_fill"):
         from . import bn
         return getattr(bn, name)
     raise AttributeError(name)
 
 
-__all__ = ["linear_regression_rows", "lambda_gc", "logistic_regression_rows", "MatrixTable", "Table", "FatalError", "ExpressionException", "PackedGenotypes",
+__all__ = ["linear_regression_rows", "lambda_gc", "hwe_normalized_pca", "logistic_regression_rows", "MatrixTable", "Table", "FatalError", "ExpressionException", "PackedGenotypes",
            "HostBedGenotypes", "import_plink", "export_plink", "import_fam", "balding_nichols_model"]

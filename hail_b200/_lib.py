@@ -86,6 +86,9 @@ SIGNATURES = {
                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.POINTER(LogitOut),
                                            ctypes.c_void_p]),
     "lrr_qchisqtail1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "lrr_at_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                    ctypes.c_void_p]),
     "lrr_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "lrr_last_kernel": (ctypes.c_int, [ctypes.c_void_p]),
     "lrr_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["abi.cu", "pack.cu", "fp64_kernel.cu", "dense_kernel.cu", "logit_kernel.cu", "stats_epilogue.cu", "tc_kernel.cu", "tc4_kernel.cu", "stream.cu"]
+SOURCES = ["abi.cu", "pack.cu", "fp64_kernel.cu", "dense_kernel.cu", "logit_kernel.cu", "gram_kernel.cu", "stats_epilogue.cu", "tc_kernel.cu", "tc4_kernel.cu", "stream.cu"]
 LIB = os.path.join(HERE, "liblrr_b200.so")
 
 NVCC_FLAGS = [

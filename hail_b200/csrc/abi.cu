@@ -494,4 +494,13 @@ int lrr_qchisqtail1(lrr_ctx* ctx, const double* d_p, int64_t count, double* d_ch
   return launch_qchisqtail1(c, d_p, count, d_chi2, st);
 }
 
+int lrr_at_times(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int64_t packed_stride, int64_t n_samples_total,
+                 const double* d_coef, const double* d_t, int32_t L, int32_t n_splits, double* d_out, void* stream) {
+  CTX_PROLOGUE;
+  if (n_variants < 0 || n_samples_total <= 0) return fail(c, LRR_EINVAL, "lrr_at_times: bad shape");
+  if (int r = check_packed(c, n_samples_total, packed_stride)) return r;
+  if (!d_out || (n_variants > 0 && (!d_packed || !d_coef || !d_t))) return fail(c, LRR_EINVAL, "lrr_at_times: NULL array");
+  return launch_at_times(c, d_packed, n_variants, packed_stride, n_samples_total, d_coef, d_t, L, n_splits, d_out, st);
+}
+
 }  // extern "C"

@@ -122,6 +122,8 @@ int logit_set_model(Ctx*, int64_t n_samples_total, int32_t n, int32_t K, const i
 int logit_run(Ctx*, const uint8_t* d_packed, const double* d_dense, int64_t M, int64_t stride, int64_t n_samples_total,
               int test, int max_iter, double tol, const lrr_logit_out& out, cudaStream_t);
 void logit_release(Ctx*);
+int launch_at_times(Ctx*, const uint8_t* d_packed, int64_t M, int64_t stride, int64_t n_total, const double* d_coef,
+                    const double* d_t, int L, int n_splits, double* d_out, cudaStream_t);
 
 // position of sample `j` (0..15 within its word) in the packed word: bits [8i+2s, 8i+2s+1], j = 4s+i
 __host__ __device__ inline int sample_shift(int j) { return 8 * (j & 3) + 2 * (j >> 2); }

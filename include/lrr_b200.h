@@ -229,6 +229,16 @@ int lrr_student_t_two_sided(lrr_ctx* ctx, const double* d_t, int64_t count, doub
  * `hl.lambda_gc` (hail/python/hail/methods/statgen.py:3096-3128), a downstream consumer of `p_value` */
 int lrr_qchisqtail1(lrr_ctx* ctx, const double* d_p, int64_t count, double* d_chi2, void* stream);
 
+/* ---- PCA building block (`hl.hwe_normalized_pca`, hail/python/hail/methods/pca.py:15-33, 345-372) ----
+ * The power iteration G <- A' (A G) needs, next to the per-variant sweep A G (lrr_run with the columns of G as
+ * phenotypes: y_transpose_x), the TRANSPOSED product over the same packed rows:
+ *     out[s][j][c] = sum over the variants v of split s of  coef[v][code(v, j)] * t[v][c]
+ * coef [n_variants][4] tabulates the entry value of call codes 0, 1, 2 and missing per variant (HWE normalisation:
+ * (code - mean_v) / sd_v and 0), t is [n_variants][L] (L <= 24), out is [n_splits][n_samples_total][L]; the variant range
+ * is cut into n_splits contiguous parts whose partial sums the caller adds (deterministic). */
+int lrr_at_times(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int64_t packed_stride, int64_t n_samples_total,
+                 const double* d_coef, const double* d_t, int32_t L, int32_t n_splits, double* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
