@@ -21,7 +21,7 @@ eigenproblem) runs in torch on the device.  Iterations stop when the top-k Ritz 
 """
 from __future__ import annotations
 
-import ctypes
+import logging
 from collections import OrderedDict
 from types import SimpleNamespace
 
@@ -32,15 +32,30 @@ from . import _lib
 from .matrixtable import CallExpression, ExpressionException, Table
 from .statgen import FatalError, _run_device
 
+log = logging.getLogger("hail_b200")
+
+
+class _DeviceColumns:
+    """Quacks like the numpy arrays `statgen._add_group` hands to lrr_add_group (`.ctypes.data`, `.size`), but the
+    pointer is a device pointer: the library copies with cudaMemcpyDefault, so the columns never visit the host."""
+
+    def __init__(self, t):
+        self.tensor = t.contiguous()
+        self.size = self.tensor.numel()
+        self.ctypes = SimpleNamespace(data=self.tensor.data_ptr())
+
 
 def _sweep_basis(idx32, cols):
-    """A `linear_regression_rows` group with no covariates whose phenotypes are the given columns [P, n]."""
+    """A `linear_regression_rows` group with no covariates whose phenotypes are the given columns [P, n]
+    (a numpy array or a float64 CUDA tensor)."""
     P, n = cols.shape
+    y = _DeviceColumns(cols) if isinstance(cols, torch.Tensor) else np.ascontiguousarray(cols, dtype=np.float64)
     return SimpleNamespace(n=n, K=0, P=P, has_intercept=False, complete_idx=idx32, q_cols=np.empty(0), qty=np.empty(0),
-                           y_res=np.ascontiguousarray(cols, dtype=np.float64), yyp=np.ones(P), weighted=False)
+                           y_res=y, yyp=np.ones(P), weighted=False)
 
 
-def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8, _tol=1e-10, _max_iterations=60, _seed=0):
+def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8, _tol=1e-9, _max_iterations=60,
+                       _restart_blocks=6, _seed=0):
     """Run principal component analysis (PCA) on the Hardy-Weinberg-normalized genotype call matrix
     (drop-in for `hl.hwe_normalized_pca`, pca.py:35).  Returns (eigenvalues, scores, loadings)."""
     if not isinstance(call_expr, CallExpression):
@@ -81,7 +96,7 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
         n_splits = int(max(1, min(64, -(-4 * 148 // strips), M // 32 or 1)))
 
         def a_times(V):            # [n, L] -> [M, L]
-            ytx = _run_device(g, [_sweep_basis(idx, V.t().contiguous().cpu().numpy())])[0]["y_transpose_x"]
+            ytx = _run_device(g, [_sweep_basis(idx, V.t().contiguous())])[0]["y_transpose_x"]
             T = (ytx - mean[:, None] * V.sum(dim=0)[None, :]) * inv_sd[:, None]
             return torch.where(keep[:, None], T, torch.zeros_like(T))
 
@@ -104,14 +119,19 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
         Ts = []
         prev = None
         n_cols = L
+        n_restarts = n_sweeps = 0
+        converged = False
         for it in range(int(_max_iterations)):
             Ts.append(a_times(Vs[-1]))
+            n_sweeps += 1
             Tall = torch.cat(Ts, dim=1)
             ritz = torch.linalg.eigvalsh(Tall.t() @ Tall).flip(0)[:k]
             if prev is not None and bool(((ritz - prev).abs() <= _tol * ritz.abs().clamp(min=1e-300)).all()):
+                converged = True
                 break
             prev = ritz
-            if n_cols >= n:                            # the subspace is the whole sample space: Rayleigh-Ritz is exact
+            if n_cols >= n and n_restarts == 0:        # the subspace is the whole sample space: Rayleigh-Ritz is exact
+                converged = True
                 break
             W = at_times(Ts[-1])
             scale = float(W.norm()) / max(W.shape[1], 1) ** 0.5
@@ -122,9 +142,24 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
             good = R.diagonal().abs() > 1e-10 * max(scale, 1e-300)   # directions that are new (not roundoff of old ones)
             n_new = int(min(int(good.sum()), n - n_cols))
             if n_new == 0:                             # invariant subspace: the Krylov space is exhausted
+                converged = True
                 break
             Vs.append(Q[:, good][:, :n_new].contiguous())
             n_cols += n_new
+            if len(Vs) > _restart_blocks and n_cols < n:
+                # thick restart: keep the leading Ritz vectors of everything but the newest block (A Vr = Tall Wm needs
+                # no sweep) so that the Rayleigh-Ritz problem and the re-orthogonalisation stay small
+                Vold, Told = torch.cat(Vs[:-1], dim=1), torch.cat(Ts, dim=1)
+                _, Wr = torch.linalg.eigh(Told.t() @ Told)
+                Wr = Wr.flip(1)[:, :L]
+                Vs = [Vold @ Wr, Vs[-1]]
+                Ts = [Told @ Wr]
+                n_cols = Vs[0].shape[1] + Vs[1].shape[1]
+                n_restarts += 1
+        if not converged:
+            # components inside the noise bulk (eigenvalues a fraction of a percent apart) converge slowly in any Lanczos
+            # method (Spark's ARPACK allows 300 iterations, mllib RowMatrix.computeSVD); the Ritz pairs are returned
+            log.warning("hwe_normalized_pca: top-%d Ritz values still moving by more than %g after %d sweeps", k, _tol, n_sweeps)
         Vall = torch.cat(Vs[:len(Ts)], dim=1)
         Tall = torch.cat(Ts, dim=1)
         evals, Wm = torch.linalg.eigh(Tall.t() @ Tall)
@@ -146,7 +181,8 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
         sf[kf] = mt.col[kf]
     sf["scores"] = scores_h
     scores_t = Table(sf, key=mt.col_key, n_rows=n)
-    scores_t.n_iterations = len(Ts)
+    scores_t.n_iterations = n_sweeps
+    scores_t.converged = converged
     loadings_t = None
     if compute_loadings:
         lf = OrderedDict()
