@@ -92,8 +92,8 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
         coef[:, :3] = (codes[None, :] - mean[:, None]) * inv_sd[:, None]       # missing call -> 0 (pca.py:30)
         d_idx = torch.from_numpy(idx.astype(np.int64)).to(dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        strips = (g.stride + 255) // 256
-        n_splits = int(max(1, min(64, -(-4 * 148 // strips), M // 32 or 1)))
+        strips = (g.stride + 127) // 128
+        n_splits = int(max(1, min(64, -(-8 * 148 // strips), M // 32 or 1)))
 
         def a_times(V):            # [n, L] -> [M, L]
             ytx = _run_device(g, [_sweep_basis(idx, V.t().contiguous())])[0]["y_transpose_x"]
