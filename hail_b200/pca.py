@@ -54,6 +54,23 @@ def _sweep_basis(idx32, cols):
                            y_res=y, yyp=np.ones(P), weighted=False)
 
 
+def _qr(W):
+    """Thin QR of a tall block.  Cholesky-QR applied twice (two small Gram matrices and triangular solves: the
+    Householder QR of a 400k x 16 block costs more than a pass over the genotypes); falls back to Householder QR when
+    the block is numerically rank deficient."""
+    try:
+        R1 = torch.linalg.cholesky(W.t() @ W, upper=True)
+        Q = torch.linalg.solve_triangular(R1, W, upper=True, left=False)
+        R2 = torch.linalg.cholesky(Q.t() @ Q, upper=True)
+        Q = torch.linalg.solve_triangular(R2, Q, upper=True, left=False)
+        R = R2 @ R1
+        if bool(torch.isfinite(R).all()) and float(R.diagonal().abs().min()) > 1e-8 * float(R.diagonal().abs().max()):
+            return Q, R
+    except Exception:   # not positive definite: rank deficient block
+        pass
+    return torch.linalg.qr(W)
+
+
 def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8, _tol=1e-9, _max_iterations=60,
                        _restart_blocks=6, _seed=0):
     """Run principal component analysis (PCA) on the Hardy-Weinberg-normalized genotype call matrix
@@ -115,7 +132,7 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
                              "principal components.")
         gen = torch.Generator(device=dev)
         gen.manual_seed(int(_seed))
-        Vs = [torch.linalg.qr(torch.randn((n, L), generator=gen, **f64))[0]]
+        Vs = [_qr(torch.randn((n, L), generator=gen, **f64))[0]]
         Ts = []
         prev = None
         n_cols = L
@@ -138,7 +155,7 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
             Vall = torch.cat(Vs, dim=1)
             for _ in range(2):
                 W = W - Vall @ (Vall.t() @ W)
-            Q, R = torch.linalg.qr(W)
+            Q, R = _qr(W)
             good = R.diagonal().abs() > 1e-10 * max(scale, 1e-300)   # directions that are new (not roundoff of old ones)
             n_new = int(min(int(good.sum()), n - n_cols))
             if n_new == 0:                             # invariant subspace: the Krylov space is exhausted
