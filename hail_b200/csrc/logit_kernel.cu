@@ -15,7 +15,7 @@
 // Every evaluation is one pass over the n complete samples: the CTA's 256 threads stride over them (covariate planes
 // [K][n] are L2-resident and read coalesced, genotype codes are gathered from the packed row through the complete-sample
 // index), each thread keeps the m + m (m + 1) / 2 partial sums of the score and the Fisher matrix in registers
-// (compile-time MM >= m), then a warp-shuffle + shared-memory reduction; thread 0 solves the m x m system (LU with
+// (compile-time MM >= m; in 2 / 4 slices with one pass each for m > 12), then a warp-shuffle + shared-memory reduction; thread 0 solves the m x m system (LU with
 // partial pivoting, singular = an exactly zero pivot, as LAPACK dgesv under breeze's `\`).
 #include "common.cuh"
 
@@ -135,93 +135,119 @@ struct Shared {
   int status;            // 0 continue, 1 converged, 2 exploded
 };
 
-// One pass over the complete samples at coefficients b[0..m0) (columns m0..m-1 of X do not enter eta).
+// One evaluation over the complete samples at coefficients b[0..m0) (columns m0..m-1 of X do not enter eta).
 //   MODE 0: score[a] = sum x_a (y - mu), F[a][b] = sum w x_a x_b, loglik = sum log(y mu + (1 - y)(1 - mu))   (all m columns)
 //   MODE 1: Firth second pass: score[a] = sum x_a (y - mu + h (1/2 - mu)) with h = w x' Inv x
+// The partial sums live in registers.  For MM <= 12 the whole lower triangle of F fits (one pass over the samples); for
+// MM = 16 / 20 it is accumulated in 2 / 4 slices, one pass each (eta and mu are recomputed), and MODE 1 reads the inverse
+// from shared memory instead of holding it in registers.
+template <int MM>
+struct Slices {
+  static constexpr int value = MM <= 12 ? 1 : MM <= 16 ? 2 : 4;
+};
+
 template <int MM, int MODE>
 __device__ void eval_pass(const LogitArgs& a, Shared<MM>& sh, const uint32_t* row, const double* drow, int m, int m0,
                           bool want_loglik) {
   constexpr int NF = MM * (MM + 1) / 2;
-  double sc[MM], fi[NF];
-  double ll = 0.0;
-#pragma unroll
-  for (int i = 0; i < MM; ++i) sc[i] = 0.0;
-#pragma unroll
-  for (int i = 0; i < NF; ++i) fi[i] = 0.0;
-  if (MODE == 1) {   // the symmetric inverse, off-diagonal entries doubled
-#pragma unroll
-    for (int p = 0, q = 0; p < MM; ++p)
-#pragma unroll
-      for (int r = 0; r <= p; ++r, ++q) fi[q] = (p < m && r < m) ? (p == r ? sh.Inv[p][r] : 2.0 * sh.Inv[p][r]) : 0.0;
-  }
-  double bb[MM];
-#pragma unroll
-  for (int i = 0; i < MM; ++i) bb[i] = (i < m0) ? sh.b[i] : 0.0;
+  constexpr int PARTS = (MODE == 0) ? Slices<MM>::value : 1;
+  constexpr int NFP = (NF + PARTS - 1) / PARTS;
+  constexpr bool INV_SMEM = (MODE == 1) && (MM > 12);
+  constexpr int NFI = (MODE == 0) ? NFP : (INV_SMEM ? 1 : NF);
   const double mean = sh.mean;
   const int K = a.K;
-  for (int i = threadIdx.x; i < a.n; i += LT) {
-    double xa[MM];
-#pragma unroll
-    for (int k = 0; k < MM; ++k) xa[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < MM - 1; ++k)
-      if (k < K) xa[k] = __ldg(a.cov + (int64_t)k * a.n + i);
-    const int s = __ldg(a.idx + i);
-    double x;
-    if (drow) {
-      x = __ldg(drow + s);
-      if (x != x) x = mean;
-    } else {
-      const uint32_t code = (__ldg(row + (s >> 4)) >> sample_shift(s & 15)) & 3u;
-      x = (code == 3u) ? mean : (double)code;
-    }
-#pragma unroll
-    for (int k = 0; k < MM; ++k)
-      if (k == K) xa[k] = x;
-    double eta = 0.0;
-#pragma unroll
-    for (int k = 0; k < MM; ++k) eta = fma(bb[k], xa[k], eta);
-    const double mu = 1.0 / (1.0 + exp(-eta));
-    const double w = mu * (1.0 - mu);
-    const double yi = __ldg(a.y + i);
-    double r = yi - mu;
-    if (MODE == 0) {
-      if (want_loglik) ll += log(yi * mu + (1.0 - yi) * (1.0 - mu));
-#pragma unroll
-      for (int p = 0, q = 0; p < MM; ++p) {
-        const double wx = w * xa[p];
-#pragma unroll
-        for (int c = 0; c <= p; ++c, ++q) fi[q] = fma(wx, xa[c], fi[q]);
-      }
-    } else {
-      double h = 0.0;
-#pragma unroll
-      for (int p = 0, q = 0; p < MM; ++p) {
-        double t = 0.0;
-#pragma unroll
-        for (int c = 0; c <= p; ++c, ++q) t = fma(fi[q], xa[c], t);
-        h = fma(t, xa[p], h);
-      }
-      r += w * h * (0.5 - mu);
-    }
-#pragma unroll
-    for (int k = 0; k < MM; ++k) sc[k] = fma(xa[k], r, sc[k]);
-  }
-  // ---- reduce ----
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < MM; ++k) {
-    const double t = warp_sum(sc[k]);
-    if (lane == 0) sh.red[warp][k] = t;
-  }
-  if (MODE == 0) {
+  for (int part = 0; part < PARTS; ++part) {
+    double sc[MM], fi[NFI];
+    double ll = 0.0;
 #pragma unroll
-    for (int q = 0; q < NF; ++q) {
-      const double t = warp_sum(fi[q]);
-      if (lane == 0) sh.red[warp][MM + q] = t;
+    for (int i = 0; i < MM; ++i) sc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NFI; ++i) fi[i] = 0.0;
+    if (MODE == 1 && !INV_SMEM) {   // the symmetric inverse, off-diagonal entries doubled
+#pragma unroll
+      for (int p = 0, q = 0; p < MM; ++p)
+#pragma unroll
+        for (int r = 0; r <= p; ++r, ++q)
+          fi[INV_SMEM ? 0 : q] = (p < m && r < m) ? (p == r ? sh.Inv[p][r] : 2.0 * sh.Inv[p][r]) : 0.0;
     }
-    const double t = warp_sum(ll);
-    if (lane == 0) sh.red[warp][MM + NF] = t;
+    double bb[MM];
+#pragma unroll
+    for (int i = 0; i < MM; ++i) bb[i] = (i < m0) ? sh.b[i] : 0.0;
+    for (int i = threadIdx.x; i < a.n; i += LT) {
+      double xa[MM];
+#pragma unroll
+      for (int k = 0; k < MM; ++k) xa[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < MM - 1; ++k)
+        if (k < K) xa[k] = __ldg(a.cov + (int64_t)k * a.n + i);
+      const int s = __ldg(a.idx + i);
+      double x;
+      if (drow) {
+        x = __ldg(drow + s);
+        if (x != x) x = mean;
+      } else {
+        const uint32_t code = (__ldg(row + (s >> 4)) >> sample_shift(s & 15)) & 3u;
+        x = (code == 3u) ? mean : (double)code;
+      }
+#pragma unroll
+      for (int k = 0; k < MM; ++k)
+        if (k == K) xa[k] = x;
+      double eta = 0.0;
+#pragma unroll
+      for (int k = 0; k < MM; ++k) eta = fma(bb[k], xa[k], eta);
+      const double mu = 1.0 / (1.0 + exp(-eta));
+      const double w = mu * (1.0 - mu);
+      const double yi = __ldg(a.y + i);
+      double r = yi - mu;
+      if (MODE == 0) {
+        if (part == 0 && want_loglik) ll += log(yi * mu + (1.0 - yi) * (1.0 - mu));
+#pragma unroll
+        for (int p = 0, q = 0; p < MM; ++p) {
+          const double wx = w * xa[p];
+#pragma unroll
+          for (int c = 0; c <= p; ++c, ++q)
+            if (q >= part * NFP && q < (part + 1) * NFP) fi[(q - part * NFP) % NFI] = fma(wx, xa[c], fi[(q - part * NFP) % NFI]);
+        }
+      } else {
+        double h = 0.0;
+#pragma unroll
+        for (int p = 0, q = 0; p < MM; ++p) {
+          double t = 0.0;
+#pragma unroll
+          for (int c = 0; c <= p; ++c, ++q)
+            t = fma(INV_SMEM ? ((p < m) ? (p == c ? sh.Inv[p][c] : 2.0 * sh.Inv[p][c]) : 0.0) : fi[INV_SMEM ? 0 : q], xa[c], t);
+          h = fma(t, xa[p], h);
+        }
+        r += w * h * (0.5 - mu);
+      }
+      if (part == 0) {
+#pragma unroll
+        for (int k = 0; k < MM; ++k) sc[k] = fma(xa[k], r, sc[k]);
+      }
+    }
+    // ---- reduce over the lanes ----
+    if (part == 0) {
+#pragma unroll
+      for (int k = 0; k < MM; ++k) {
+        const double t = warp_sum(sc[k]);
+        if (lane == 0) sh.red[warp][k] = t;
+      }
+    }
+    if (MODE == 0) {
+#pragma unroll
+      for (int q = 0; q < NFP; ++q) {
+        if (part * NFP + q < NF) {
+          const double t = warp_sum(fi[q % NFI]);
+          if (lane == 0) sh.red[warp][MM + part * NFP + q] = t;
+        }
+      }
+      if (part == 0) {
+        const double t = warp_sum(ll);
+        if (lane == 0) sh.red[warp][MM + NF] = t;
+      }
+    }
   }
   __syncthreads();
   const int total = (MODE == 0) ? MM + NF + 1 : MM;
@@ -472,7 +498,7 @@ int logit_set_model(Ctx* c, int64_t n_samples_total, int32_t n, int32_t K, const
                     const double* y, const double* b0, const double* score0, const double* fisher0, double loglk0) {
   if (n_samples_total <= 0 || n <= 0 || n > n_samples_total) return fail(c, LRR_EINVAL, "lrr_set_logit_model: bad sample counts");
   if (K < 1) return fail(c, LRR_EINVAL, "logistic regression requires at least one covariate expression");
-  if (K + 1 > 12) return fail(c, LRR_EINVAL, "lrr_set_logit_model: at most 11 covariates (the Fisher matrix lives in registers)");
+  if (K + 1 > 20) return fail(c, LRR_EINVAL, "lrr_set_logit_model: at most 19 covariates (the Fisher matrix lives in registers)");
   if (n - K - 1 < 1) {
     char buf[160];
     snprintf(buf, sizeof buf, "%d samples and %d %s (including x) implies %d degrees of freedom.", n, K + 1,
@@ -539,7 +565,9 @@ int logit_run(Ctx* c, const uint8_t* d_packed, const double* d_dense, int64_t M,
   else if (mm <= 6) launch_mm<6>(a, grid, st);
   else if (mm <= 8) launch_mm<8>(a, grid, st);
   else if (mm <= 10) launch_mm<10>(a, grid, st);
-  else launch_mm<12>(a, grid, st);
+  else if (mm <= 12) launch_mm<12>(a, grid, st);
+  else if (mm <= 16) launch_mm<16>(a, grid, st);
+  else launch_mm<20>(a, grid, st);
   c->launches++;
   LRR_CUDA(c, cudaGetLastError());
   return LRR_OK;
