@@ -194,9 +194,10 @@ __device__ void eval_pass(const LogitArgs& a, Shared<MM>& sh, const uint32_t* ro
 #pragma unroll
       for (int k = 0; k < MM; ++k)
         if (k == K) xa[k] = x;
-      double eta = 0.0;
+      double e4[4] = {0.0, 0.0, 0.0, 0.0};   // four short chains instead of one of length MM (FP64 latency)
 #pragma unroll
-      for (int k = 0; k < MM; ++k) eta = fma(bb[k], xa[k], eta);
+      for (int k = 0; k < MM; ++k) e4[k & 3] = fma(bb[k], xa[k], e4[k & 3]);
+      const double eta = (e4[0] + e4[1]) + (e4[2] + e4[3]);
       const double mu = 1.0 / (1.0 + exp(-eta));
       const double w = mu * (1.0 - mu);
       const double yi = __ldg(a.y + i);
