@@ -71,10 +71,23 @@ def _qr(W):
     return torch.linalg.qr(W)
 
 
+def _allreduce(t, sharded):
+    """Sum over the ranks of a variant-sharded run (NCCL all-reduce over NVLink); identity otherwise."""
+    if sharded:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
 def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8, _tol=1e-9, _max_iterations=60,
-                       _restart_blocks=6, _seed=0):
+                       _restart_blocks=6, _seed=0, _sharded=False):
     """Run principal component analysis (PCA) on the Hardy-Weinberg-normalized genotype call matrix
-    (drop-in for `hl.hwe_normalized_pca`, pca.py:35).  Returns (eigenvalues, scores, loadings)."""
+    (drop-in for `hl.hwe_normalized_pca`, pca.py:35).  Returns (eigenvalues, scores, loadings).
+
+    `_sharded=True` (one process per GPU, torch.distributed initialised): every rank passes its own contiguous range of
+    VARIANTS over the same samples.  Unlike the regression sweep this algorithm has a real exchange step: the
+    transposed product A' T and the small Gram matrices T' T are sums over variants, so they are all-reduced (n x L
+    and L x L float64 per iteration); eigenvalues and scores come out identical on every rank, loadings stay sharded."""
     if not isinstance(call_expr, CallExpression):
         raise ExpressionException("'hwe_normalized_pca/call_expr': expected a call expression (e.g. mt.GT)")
     if not isinstance(k, int) or isinstance(k, bool):
@@ -99,7 +112,7 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
         n_called = (n - o["n_missing"]).to(torch.float64)
         mean = o["sum_x"] / float(n)                  # the mean-imputed column sums to n * mean
         keep = (mean > 0.0) & (mean < 2.0) & (n_called > 0)
-        m = int(keep.sum())
+        m = int(_allreduce(keep.sum().to(torch.int64).reshape(1), _sharded).item())
         if m == 0:
             raise FatalError("hwe_normalize: found 0 variants after filtering out monomorphic sites.")
         mean = torch.where(keep, mean, torch.zeros_like(mean))
@@ -123,7 +136,10 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
             Tc = T.contiguous()
             ctx.check(ctx.lib.lrr_at_times(ctx.handle, g.data.data_ptr(), M, g.stride, N, coef.data_ptr(), Tc.data_ptr(), L,
                                            n_splits, out.data_ptr(), stream))
-            return out.sum(dim=0)[d_idx]
+            return _allreduce(out.sum(dim=0)[d_idx].contiguous(), _sharded)
+
+        def gram(T):               # T' T summed over every rank's variants
+            return _allreduce(T.t() @ T, _sharded)
 
         # ---- block Lanczos with full re-orthogonalisation, Rayleigh-Ritz over the accumulated Krylov space ----
         L = int(min(n, max(k + _oversample, k), 24))
@@ -132,7 +148,11 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
                              "principal components.")
         gen = torch.Generator(device=dev)
         gen.manual_seed(int(_seed))
-        Vs = [_qr(torch.randn((n, L), generator=gen, **f64))[0]]
+        V0 = _qr(torch.randn((n, L), generator=gen, **f64))[0].contiguous()
+        if _sharded:
+            import torch.distributed as dist
+            dist.broadcast(V0, 0)
+        Vs = [V0]
         Ts = []
         prev = None
         n_cols = L
@@ -142,7 +162,7 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
             Ts.append(a_times(Vs[-1]))
             n_sweeps += 1
             Tall = torch.cat(Ts, dim=1)
-            ritz = torch.linalg.eigvalsh(Tall.t() @ Tall).flip(0)[:k]
+            ritz = torch.linalg.eigvalsh(gram(Tall)).flip(0)[:k]
             if prev is not None and bool(((ritz - prev).abs() <= _tol * ritz.abs().clamp(min=1e-300)).all()):
                 converged = True
                 break
@@ -167,7 +187,7 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
                 # thick restart: keep the leading Ritz vectors of everything but the newest block (A Vr = Tall Wm needs
                 # no sweep) so that the Rayleigh-Ritz problem and the re-orthogonalisation stay small
                 Vold, Told = torch.cat(Vs[:-1], dim=1), torch.cat(Ts, dim=1)
-                _, Wr = torch.linalg.eigh(Told.t() @ Told)
+                _, Wr = torch.linalg.eigh(gram(Told))
                 Wr = Wr.flip(1)[:, :L]
                 Vs = [Vold @ Wr, Vs[-1]]
                 Ts = [Told @ Wr]
@@ -179,7 +199,7 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
             log.warning("hwe_normalized_pca: top-%d Ritz values still moving by more than %g after %d sweeps", k, _tol, n_sweeps)
         Vall = torch.cat(Vs[:len(Ts)], dim=1)
         Tall = torch.cat(Ts, dim=1)
-        evals, Wm = torch.linalg.eigh(Tall.t() @ Tall)
+        evals, Wm = torch.linalg.eigh(gram(Tall))
         evals, Wm = evals.flip(0)[:k], Wm.flip(1)[:, :k]
         if evals.numel() < k or bool((evals[:k] <= 1e-12 * evals[0].clamp(min=1e-300)).any()):   # PCA.scala:47-51
             nz = int((evals > 1e-12 * evals[0]).sum())
@@ -207,6 +227,6 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
             v = mt.row[kf]
             lf[kf] = v[keep_h] if isinstance(v, np.ndarray) else [x for x, kp in zip(v, keep_h) if kp]
         lf["loadings"] = loadings_h
-        loadings_t = Table(lf, key=mt.row_key, n_rows=m)
+        loadings_t = Table(lf, key=mt.row_key, n_rows=int(keep_h.sum()))   # this rank's kept variants when sharded
         loadings_t.kept_variants = keep_h
     return eigenvalues, scores_t, loadings_t

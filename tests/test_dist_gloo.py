@@ -52,6 +52,18 @@ def _worker(rank, world, port, tmp):
         assert np.array_equal(allrows[:, 0], want[:, 0], equal_nan=True)  # sum_x: exact, order preserved
         covered = [hd.variant_range(r, world, M) for r in range(world)]
         assert covered[0][0] == 0 and covered[-1][1] == M and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+        # the one path with a real exchange step: variant-sharded PCA all-reduces A' (A V) and the Gram matrices
+        # (hail_b200/pca.py `_sharded`); the per-shard products are stood in by the numpy oracle
+        from hail_b200 import pca as hpca
+        from oracle import pca_oracle as PO
+        a, keep = PO.hwe_normalize(x)                       # [m, N] with the GLOBAL variant count in the scaling
+        kept_rows = np.nonzero(keep)[0]
+        local = a[(kept_rows >= lo) & (kept_rows < hi)]
+        V = np.random.default_rng(5).normal(size=(N, 4))
+        T = local @ V
+        W = hpca._allreduce(torch.from_numpy(local.T @ T), True).numpy()
+        G = hpca._allreduce(torch.from_numpy(T.T @ T), True).numpy()
+        assert np.allclose(W, a.T @ (a @ V), rtol=1e-11, atol=1e-12) and np.allclose(G, (a @ V).T @ (a @ V), rtol=1e-11)
         with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:
