@@ -142,7 +142,7 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
             return _allreduce(T.t() @ T, _sharded)
 
         # ---- block Lanczos with full re-orthogonalisation, Rayleigh-Ritz over the accumulated Krylov space ----
-        L = int(min(n, max(k + _oversample, k), 24))
+        L = int(min(n, -(-max(k + _oversample, k) // 4) * 4, 24))   # block width: a multiple of 4 (the kernels' column tiles)
         if min(n, m) < k:   # PCA.scala:47-51
             raise FatalError(f"Found only {min(n, m)} non-zero (or nearly zero) eigenvalues, but user requested {k} "
                              "principal components.")
