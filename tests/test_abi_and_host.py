@@ -159,3 +159,35 @@ def test_bn_mirror_distribution():
     assert d.min() >= 0 and d.max() == 2
     freq = d.mean(axis=1) / 2.0
     assert np.abs(freq - af[:, pop].mean(axis=1)).max() < 0.03
+
+
+def test_neighbour_calls_validate_before_any_device_work():
+    """logistic_regression_rows / hwe_normalized_pca raise the reference's errors on the host (no GPU needed):
+    statgen.py:960-984, LogisticRegression.scala:44-61, PCA.scala:35-37."""
+    import hail_b200 as hb
+
+    mt = _fake_mt()
+    x = mt.GT.n_alt_alleles()
+    yb = (mt.pheno.values > 0).astype(np.float64)
+    mt2 = mt.annotate_cols(yb=yb, q=mt.pheno.values, one=np.ones(8))
+    x2 = mt2.GT.n_alt_alleles()
+    with pytest.raises(TypeError):
+        hb.logistic_regression_rows("rao", mt2.yb, x2, [1.0])
+    with pytest.raises(ValueError, match="at least one covariate"):
+        hb.logistic_regression_rows("wald", mt2.yb, x2, [])
+    with pytest.raises(ValueError, match="found no values for 'y'"):
+        hb.logistic_regression_rows("lrt", [], x2, [1.0])
+    with pytest.raises(hb.ExpressionException):
+        hb.logistic_regression_rows("firth", mt2.yb, mt2.yb, [1.0])
+    with pytest.raises(hb.FatalError, match="equal to 0 or 1"):
+        hb.logistic_regression_rows("wald", mt2.q, x2, [1.0])
+    with pytest.raises(hb.FatalError, match="must be non-constant"):
+        hb.logistic_regression_rows("wald", mt2.one, x2, [1.0])
+    with pytest.raises(hb.FatalError, match="degrees of freedom"):
+        hb.logistic_regression_rows("wald", mt2.yb, x2, [1.0] + [mt2.c1] * 7)
+    with pytest.raises(hb.FatalError, match="requested invalid number of components"):
+        hb.hwe_normalized_pca(mt.GT, k=0)
+    with pytest.raises(hb.ExpressionException):
+        hb.hwe_normalized_pca(x, k=2)
+    with pytest.raises(TypeError):
+        hb.hwe_normalized_pca(mt.GT, k=2.0)
