@@ -10,7 +10,7 @@ Mirrors
                               156-161, 212-215): wald `beta, standard_error, z_stat, p_value, fit`; lrt / firth `beta,
                               chi_sq_stat, p_value, fit`; score `chi_sq_stat, p_value`; `fit` = struct{n_iterations,
                               converged, exploded} (scalars for one y; for a list of y the reference nests them in
-                              `logistic_regression: array<struct>` -- here arrays [M, P])
+                              `logistic_regression: array<struct>` -- provided, next to flat [M, P] arrays)
 The per-row loop (LogisticRegression.scala:115-157) runs in the CUDA library: the score test on the float64 sweep
 (lrr_set_score_model / lrr_run_score), the Wald / LRT / Firth tests as per-variant Newton fits, one CTA per variant
 (lrr_set_logit_model / lrr_run_logit, csrc/logit_kernel.cu).
@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .matrixtable import EntryExpression, ExpressionException, Table
+from .matrixtable import ChainedField, EntryExpression, ExpressionException, Table
 from .statgen import FatalError, _column_values, _get_regression_row_fields, _plural, _warn_if_no_intercept
 
 log = logging.getLogger("hail_b200")
@@ -200,4 +200,11 @@ def logistic_regression_rows(test, y, x, covariates, pass_through=(), *, max_ite
             fields[kf] = {kk: (vv if y_is_list else vv[:, 0]) for kk, vv in v.items()}
         else:
             fields[kf] = v if y_is_list else v[:, 0]
+    if y_is_list:
+        # the reference's schema for a list of y: `logistic_regression: array<struct{...test fields...}>`, one struct per
+        # phenotype (statgen.py:1003-1011); the flat [M, P] arrays above carry the same numbers
+        fields["logistic_regression"] = ChainedField(
+            OrderedDict((kf, ({kk: vv[:, p] for kk, vv in v.items()} if isinstance(v, dict) else v[:, p]))
+                        for kf, v in results.items())
+            for p in range(P))
     return Table(fields, key=mt.row_key, n_rows=mt.count_rows())

@@ -122,6 +122,12 @@ def test_multi_pheno_shapes_and_errors():
     mt = hb.MatrixTable(hb.PackedGenotypes.from_bed_rows(rows, N), rows={"rsid": np.arange(M)}, cols={"y1": y1, "y2": y2, "c1": c1})
     ht = hb.logistic_regression_rows("wald", [mt.y1, mt.y2], mt.GT.n_alt_alleles(), [1.0, mt.c1], pass_through=["rsid"])
     assert ht.beta.shape == (M, 2) and ht.fit["n_iterations"].shape == (M, 2) and list(ht.rsid) == list(range(M))
+    r7 = ht.collect()[7]      # the reference's nested schema (TS:758-803): one struct per phenotype
+    assert len(r7.logistic_regression) == 2
+    for p in range(2):
+        lr = r7.logistic_regression[p]
+        assert (lr.beta == ht.beta[7, p] or np.isnan(lr.beta)) and lr.fit.n_iterations == ht.fit["n_iterations"][7, p]
+        assert lr.fit.converged == bool(ht.fit["converged"][7, p])
     cov = np.column_stack([np.ones(N), c1])
     for col, yy in enumerate((y1, y2)):
         want = L.logreg_rows("wald", x, yy, cov)
