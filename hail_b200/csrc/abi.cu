@@ -387,8 +387,6 @@ int lrr_run_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t l
   CTX_PROLOGUE;
   if (c->groups.empty()) return fail(c, LRR_ESTATE, "lrr_run_dense: no groups (call lrr_add_group)");
   if (c->groups[0].score) return fail(c, LRR_ESTATE, "lrr_run_dense: the context holds a logistic score model");
-  for (const Group& g : c->groups)
-    if (g.weighted) return fail(c, LRR_EINVAL, "lrr_run_dense: weighted groups are not supported on dense dosages");
   if (n_outs != (int32_t)c->groups.size() || !outs) return fail(c, LRR_EINVAL, "lrr_run_dense: need one lrr_group_out per group");
   if (n_variants < 0 || ldx < n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_dense: bad shape (ldx >= n_samples_total)");
   if (n_samples_total != c->n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_dense: n_samples_total differs from the groups'");

@@ -42,6 +42,7 @@ struct DenseArgs {
   int n;
   int C;                 // all dot columns of the group
   int c0;                // first column of this pass
+  int sq_col;            // weighted groups: the column accumulated against x^2 (sum_j w_j x_j^2, statgen.py:646), else -1
   int32_t* counts;       // [M][4]: (0, 0, n_missing, 0)
   double* dots;          // [M][C + 2]: C dot products, sum of the defined entries, their sum of squares
   uint2* nanmask;        // [M][n_chunks]: .x bit l = sample 64 k + 2 l missing (and in the group), .y = sample 64 k + 2 l + 1
@@ -84,7 +85,7 @@ __device__ __forceinline__ bool not_finite(double v) { return (__double2hiint(v)
 //   dot warps      (8 x 4 variants) then read clean data on stage k: acc[r][c] += basis[c][j] * x[r][j] and, with the
 //                  group's 0 / 1 indicator column staged next to the basis, sum += ind[j] * x[r][j] and
 //                  squares += (ind[j] * x[r][j]) * x[r][j]  (samples outside the group have zero basis rows)
-template <int CB, bool FIRST, bool VEC>
+template <int CB, bool FIRST, bool VEC, bool SQ>
 __global__ void __launch_bounds__(THREADS, 1) dense_sweep_kernel(DenseArgs a) {
   extern __shared__ __align__(16) double s_ring[];   // STAGES x { x [VT][CHUNK], indicator [CHUNK], basis [CB][CHUNK] }
   constexpr int STAGE_DOUBLES = (VT + 1 + CB) * CHUNK;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_sweep_kernel(DenseArgs a) {
 #pragma unroll
       for (int c = 0; c < CB; ++c) acc[r][c] = 0.0;
     }
+    const int sqc = SQ ? a.sq_col - a.c0 : -1;
     __syncthreads();   // (the stat warps clean stage 0 now)
     int slot = 0;      // ring slot of stage `chunk`
     for (int64_t chunk = 0; chunk < a.n_chunks; ++chunk) {
@@ -131,8 +133,13 @@ __global__ void __launch_bounds__(THREADS, 1) dense_sweep_kernel(DenseArgs a) {
 #pragma unroll
       for (int c = 0; c < CB; ++c) {
         const double2 q = *reinterpret_cast<const double2*>(st + (VT + 1 + c) * CHUNK);
+        if (SQ && c == sqc) {   // the w column of a weighted group meets x^2
 #pragma unroll
-        for (int r = 0; r < VW; ++r) acc[r][c] = fma(q.x, xv[r].x, fma(q.y, xv[r].y, acc[r][c]));
+          for (int r = 0; r < VW; ++r) acc[r][c] = fma(q.x, xv[r].x * xv[r].x, fma(q.y, xv[r].y * xv[r].y, acc[r][c]));
+        } else {
+#pragma unroll
+          for (int r = 0; r < VW; ++r) acc[r][c] = fma(q.x, xv[r].x, fma(q.y, xv[r].y, acc[r][c]));
+        }
       }
       slot = slot == STAGES - 1 ? 0 : slot + 1;
     }
@@ -278,6 +285,7 @@ struct ImputeArgs {
   int64_t M;
   int C;
   int n;
+  int sq_col;             // column whose imputed entries contribute mean^2 (weighted groups), else -1
   const double* basis_t;  // [ns_pad][C] sample-major copy
   const int32_t* counts;
   double* dots;
@@ -328,7 +336,7 @@ __global__ void __launch_bounds__(IMPUTE_THREADS) dense_impute_kernel(ImputeArgs
       double r = 0.0;
 #pragma unroll
       for (int w = 0; w < IMPUTE_THREADS / 32; ++w) r += s_corr[w][threadIdx.x];
-      d[c0 + threadIdx.x] += mean * r;
+      d[c0 + threadIdx.x] += ((c0 + (int)threadIdx.x == a.sq_col) ? mean * mean : mean) * r;
     }
     __syncthreads();
   }
@@ -349,25 +357,31 @@ __global__ void indicator_kernel(const uint32_t* __restrict__ mask, int64_t ns_p
     out[j] = ((mask[j >> 4] >> sample_shift((int)(j & 15))) & 1u) ? 1.0 : 0.0;
 }
 
-template <int CB, bool FIRST, bool VEC>
+template <int CB, bool FIRST, bool VEC, bool SQ>
 void launch_pass_v(const DenseArgs& a, int grid, cudaStream_t st) {
   constexpr int smem = STAGES * (VT + 1 + CB) * CHUNK * (int)sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(dense_sweep_kernel<CB, FIRST, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(dense_sweep_kernel<CB, FIRST, VEC, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_set = true;
   }
-  dense_sweep_kernel<CB, FIRST, VEC><<<grid, THREADS, smem, st>>>(a);
+  dense_sweep_kernel<CB, FIRST, VEC, SQ><<<grid, THREADS, smem, st>>>(a);
 }
 
-template <int CB, bool FIRST>
+template <int CB, bool FIRST, bool SQ = false>
 void launch_pass(const DenseArgs& a, bool vec, int grid, cudaStream_t st) {
-  if (vec) launch_pass_v<CB, FIRST, true>(a, grid, st);
-  else launch_pass_v<CB, FIRST, false>(a, grid, st);
+  if (vec) launch_pass_v<CB, FIRST, true, SQ>(a, grid, st);
+  else launch_pass_v<CB, FIRST, false, SQ>(a, grid, st);
 }
 
 template <bool FIRST>
 void launch_pass_cb(const DenseArgs& a, int cb, bool vec, int grid, cudaStream_t st) {
+  if (a.sq_col >= 0) {   // weighted groups: fewer column-tile sizes (each is one more kernel to build)
+    if (cb <= 4) launch_pass<4, FIRST, true>(a, vec, grid, st);
+    else if (cb <= 8) launch_pass<8, FIRST, true>(a, vec, grid, st);
+    else launch_pass<12, FIRST, true>(a, vec, grid, st);
+    return;
+  }
   if (cb <= 2) launch_pass<2, FIRST>(a, vec, grid, st);
   else if (cb <= 4) launch_pass<4, FIRST>(a, vec, grid, st);
   else if (cb <= 6) launch_pass<6, FIRST>(a, vec, grid, st);
@@ -411,6 +425,7 @@ int launch_dense_sweep(Ctx* c, const double* d_x, int64_t M, int64_t ldx, cudaSt
     a.indicator = G.d_basis_t + (size_t)G.C * (size_t)G.ns_pad;
     a.n = G.n;
     a.C = G.C;
+    a.sq_col = G.weighted ? G.C - 1 : -1;
     a.counts = c->d_counts + (int64_t)g * c->reserved_variants * 4;
     a.dots = c->d_dots + c->dots_offset[g];
     a.nanmask = reinterpret_cast<uint2*>(c->d_nanmask);
@@ -432,6 +447,7 @@ int launch_dense_sweep(Ctx* c, const double* d_x, int64_t M, int64_t ldx, cudaSt
     ia.M = M;
     ia.C = G.C;
     ia.n = G.n;
+    ia.sq_col = G.weighted ? G.C - 1 : -1;
     ia.basis_t = G.d_basis_t;
     ia.counts = a.counts;
     ia.dots = a.dots;

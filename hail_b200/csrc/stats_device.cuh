@@ -96,8 +96,8 @@ __device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n
   const double sum_x = a.weighted ? dv[a.Kd + a.P] : S + (double)nm * mean;        // LR:136
   // dense: centred sum of squares of the imputed column (the imputed entries sit at the mean and add nothing)
   const double xxc = a.dense ? dv[a.C + 1] - S * S / nv : 0.0;
-  const double xx_imp = a.dense ? xxc + sum_x * sum_x / (double)a.n
-                                : a.weighted ? dv[a.Kd + a.P + 1] : xx_int + (double)nm * mean * mean;
+  const double xx_imp = a.weighted ? dv[a.Kd + a.P + 1]
+                                   : a.dense ? xxc + sum_x * sum_x / (double)a.n : xx_int + (double)nm * mean * mean;
 
   double qq = 0.0;
   for (int c = 0; c < a.Kd; ++c) qq += dv[c] * dv[c];

@@ -406,9 +406,7 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
     if isinstance(mt.genotypes, DenseDosage) or x.kind == "dosage":
         if not isinstance(mt.genotypes, DenseDosage) or x.kind != "dosage":
             raise ExpressionException("'linear_regression_rows/x': a dense dosage field needs a DenseDosage entry matrix")
-        if weights is not None:
-            raise NotImplementedError("linear_regression_rows: weights on dense dosages")
-        bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None)
+        bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None, w_vals[i])
                  for i, g in enumerate(y_vals)]
         outs = _run_device_dense(mt.genotypes, bases)
         torch.cuda.synchronize(mt.genotypes.device)

@@ -138,7 +138,7 @@ int lrr_run(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_flags, i
 /* The same hot call for a DENSE float64 x: `x` may be any entry-indexed float64 expression in the reference
  * (methods/statgen.py:229, 391; e.g. PL / GP dosages, test_statgen.py:286-364), not only GT.n_alt_alleles().
  * d_x is [n_variants, ldx] row-major on the device, one double per entry over ALL n_samples_total columns, NaN =
- * missing (mean-imputed per group as RU:16-58).  Float64 CUDA-core kernel; weighted groups are not supported here. */
+ * missing (mean-imputed per group as RU:16-58).  Float64 CUDA-core kernel; weighted groups (lrr_add_group_weighted) too. */
 int lrr_run_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t ldx, int64_t n_samples_total,
                   const lrr_group_out* outs, int32_t n_outs, void* stream);
 /* number of kernel launches issued by this context since creation (for bench accounting) */

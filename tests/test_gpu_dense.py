@@ -138,8 +138,31 @@ def test_dense_rejects_mismatched_sources():
     mt = _dense_mt(rng.random((4, 30)), y=rng.normal(size=30))
     with pytest.raises(hb.ExpressionException):
         mt.GT
-    with pytest.raises(NotImplementedError):
-        hb.linear_regression_rows(y=mt.y, x=mt.x, covariates=[1.0], weights=mt.y)
+
+
+@pytest.mark.parametrize("N,P,K", [(900, 2, 3), (1301, 1, 10)])
+def test_dense_weighted_vs_oracle(N, P, K):
+    """`weights` on a dense float64 x (statgen.py:557-581, 636-660): x is mean-imputed, then scaled by sqrt(w)."""
+    hb = _hb()
+    rng = np.random.default_rng(N)
+    M = 60
+    x = rng.beta(0.7, 1.3, size=(M, N)) * 2.0
+    x[rng.random((M, N)) < 0.06] = np.nan
+    cov = np.column_stack([np.ones(N)] + [rng.normal(size=N) for _ in range(K - 1)])
+    ys = rng.normal(size=(N, P)) + 0.3 * np.nan_to_num(x[2])[:, None]
+    ys[rng.random(N) < 0.04, 0] = np.nan
+    w = rng.uniform(0.2, 4.0, size=N)
+    w[rng.random(N) < 0.03] = np.nan                    # missing weights drop the sample (TS:610-660)
+    mt = _dense_mt(x, w=w, **{f"y{p}": ys[:, p] for p in range(P)}, **{f"c{k}": cov[:, k] for k in range(1, K)})
+    covs = [1.0] + [mt[f"c{k}"] for k in range(1, K)]
+    ht = hb.linear_regression_rows(y=[mt[f"y{p}"] for p in range(P)], x=mt.x, covariates=covs, weights=mt.w)
+    want = O.linreg_group_weighted(x, ys, cov, w)
+    assert_fields_close(_as_dict(ht), {k: v for k, v in want.items() if k != "_d"}, t_floor=1e-9, ctx="dense weighted")
+    # unit weights reproduce the unweighted statistics
+    mt1 = mt.annotate_cols(one=np.ones(N))
+    hu = hb.linear_regression_rows(y=mt1.y0, x=mt1.x, covariates=[1.0] + [mt1[f"c{k}"] for k in range(1, K)], weights=mt1.one)
+    h0 = hb.linear_regression_rows(y=mt1.y0, x=mt1.x, covariates=[1.0] + [mt1[f"c{k}"] for k in range(1, K)])
+    assert np.allclose(hu.beta, h0.beta, rtol=1e-7) and np.allclose(hu.p_value, h0.p_value, rtol=1e-6)
 
 
 def test_lambda_gc():   # statgen.py:3096-3128
