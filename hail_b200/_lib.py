@@ -89,6 +89,8 @@ SIGNATURES = {
     "lrr_at_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                     ctypes.c_void_p]),
+    "lrr_set_guard": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "lrr_last_recomputed": (ctypes.c_int64, [ctypes.c_void_p]),
     "lrr_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "lrr_last_kernel": (ctypes.c_int, [ctypes.c_void_p]),
     "lrr_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -165,6 +167,11 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    @property
+    def last_recomputed(self) -> int:
+        """Rows of the last lrr_run that the tolerance guard sent to the float64 recompute (synchronises)."""
+        return int(self.lib.lrr_last_recomputed(self.handle))
 
     @property
     def launch_count(self) -> int:

@@ -2,6 +2,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -21,6 +22,15 @@ int cuda_fail(Ctx* c, cudaError_t e, const char* what) {
   return fail(c, LRR_ECUDA, m);
 }
 
+int abi_caught(void* ctx, int code, const char* what) noexcept {
+  try {
+    std::string m = std::string("internal error: ") + (what ? what : "?");
+    if (ctx) reinterpret_cast<Ctx*>(ctx)->err = m; else g_create_error = m;
+  } catch (...) {
+  }
+  return code;
+}
+
 namespace {
 
 void free_group(Group& g) {
@@ -37,8 +47,13 @@ void free_group(Group& g) {
 void free_workspace(Ctx* c) {
   cudaFree(c->d_counts);
   cudaFree(c->d_dots);
+  cudaFree(c->d_flag_mark);
+  cudaFree(c->d_flag_list);
+  cudaFree(c->d_flag_count);
   c->d_counts = nullptr;
   c->d_dots = nullptr;
+  c->d_flag_mark = c->d_flag_list = c->d_flag_count = nullptr;
+  c->flag_pending = false;
   c->reserved_variants = 0;
   c->dots_offset.clear();
 }
@@ -69,6 +84,16 @@ int ensure_workspace(Ctx* c, int64_t M) {
   }
   LRR_CUDA(c, cudaMalloc(&c->d_counts, sizeof(int32_t) * 4 * (size_t)want * (G ? G : 1)));
   LRR_CUDA(c, cudaMalloc(&c->d_dots, sizeof(double) * (size_t)want * (size_t)(total_c ? total_c : 1)));
+  LRR_CUDA(c, cudaMalloc(&c->d_flag_mark, sizeof(int32_t) * (size_t)want * (G ? G : 1)));
+  LRR_CUDA(c, cudaMalloc(&c->d_flag_list, sizeof(int32_t) * (size_t)want * (G ? G : 1)));
+  LRR_CUDA(c, cudaMalloc(&c->d_flag_count, sizeof(int32_t) * (G ? G : 1)));
+  if ((int)G > c->h_flag_groups) {
+    if (c->h_flag_count) cudaFreeHost(c->h_flag_count);
+    c->h_flag_count = nullptr;
+    LRR_CUDA(c, cudaMallocHost(&c->h_flag_count, sizeof(int32_t) * G));
+    c->h_flag_groups = (int)G;
+  }
+  if (!c->flag_ev) LRR_CUDA(c, cudaEventCreateWithFlags(&c->flag_ev, cudaEventDisableTiming));
   c->reserved_variants = want;
   return LRR_OK;
 }
@@ -97,12 +122,28 @@ int run_rows(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_
     }
     LRR_CUDA(c, cudaEventRecord(c->ev0, st));
   }
+  // Adaptive precision: when more than 2 % of the previous run's rows left the tolerance guard (structured or badly
+  // scaled covariates), the covariate / fitted columns get more digits from now on.  Never blocks: the count is read
+  // only if its copy has already completed.
+  if (c->flag_pending && cudaEventQuery(c->flag_ev) == cudaSuccess) {
+    c->flag_pending = false;
+    int64_t worst = 0;
+    for (size_t g = 0; g < c->groups.size() && (int)g < c->h_flag_groups; ++g) worst = std::max<int64_t>(worst, c->h_flag_count[g]);
+    if (c->flag_rows >= 1024 && worst * 50 > c->flag_rows && c->digit_boost < 6) {
+      c->digit_boost += 2;
+      tc4_invalidate(c);
+    }
+  }
   int k = kernel;
   const bool may_miss = true;  // the column budget is checked for the general (two-plane) mode
-  // AUTO: the 4-bit tensor-core sweep when one sweep covers every column and its exactness bound holds, else the
-  // int8 tensor-core sweep (multi-pass for many phenotypes), else the float64 CUDA-core kernel
-  if (k == LRR_KERNEL_AUTO)
-    k = tc4_supported(c, true) ? LRR_KERNEL_TC4 : tc_supported(c, may_miss) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
+  // AUTO: tiny problems go straight to the float64 CUDA-core kernel (quantising the basis would cost more than the
+  // sweep); otherwise the 4-bit tensor-core sweep (as many passes as the columns need) when its exactness bound holds,
+  // else the int8 tensor-core sweep, else the float64 kernel
+  if (k == LRR_KERNEL_AUTO) {
+    const double work = (double)n_variants * (double)c->groups[0].ns_pad;
+    if (work <= 2.5e8) k = LRR_KERNEL_FP64;
+    else k = tc4_supported(c, false) ? LRR_KERNEL_TC4 : tc_supported(c, may_miss) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
+  }
   if (k == LRR_KERNEL_TC4) {
     if (!tc4_supported(c, false))
       return fail(c, LRR_EINVAL, "lrr_run: 4-bit tensor-core kernel does not support this configuration: " + c->err);
@@ -121,8 +162,43 @@ int run_rows(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_
     LRR_CUDA(c, cudaEventRecord(c->ev1, st));
     c->ev_valid = true;
   }
-  for (size_t g = 0; g < c->groups.size(); ++g)
-    if (int r = launch_stats_epilogue(c, (int)g, n_variants, outs[g], st)) return r;
+  const size_t G = c->groups.size();
+  const bool quantised = (k == LRR_KERNEL_TC4 || k == LRR_KERNEL_TC);
+  const bool guarded = quantised && c->guard;
+  if (guarded) {
+    LRR_CUDA(c, cudaMemsetAsync(c->d_flag_count, 0, sizeof(int32_t) * G, st));
+    for (size_t g = 0; g < G; ++g)
+      LRR_CUDA(c, cudaMemsetAsync(c->d_flag_mark + (int64_t)g * c->reserved_variants, 0, sizeof(int32_t) * (size_t)n_variants, st));
+  }
+  for (size_t g = 0; g < G; ++g) {
+    const double* quantum = nullptr;
+    int n_fit = 0, stride = c->groups[g].C;
+    double qscale = 1.0;
+    if (k == LRR_KERNEL_TC4) {
+      quantum = tc4_quantum(c, (int)g, &n_fit);
+      stride = c->groups[g].C + 2;
+    } else if (k == LRR_KERNEL_TC) {
+      quantum = tc_quantum(c, (int)g);
+      qscale = 4.0;
+    }
+    if (int r = launch_stats_epilogue(c, (int)g, n_variants, outs[g], st, false, quantum, n_fit, stride, qscale)) return r;
+    if (guarded && !c->groups[g].weighted) {
+      // rows the guard listed: float64 recompute of their counts and dot products, then their statistics once more
+      const int32_t* list = c->d_flag_list + (int64_t)g * c->reserved_variants;
+      if (int r = launch_fp64_recompute(c, (int)g, d_packed, packed_stride, list, c->d_flag_count + g, stride, st)) return r;
+      if (int r = launch_stats_epilogue_listed(c, (int)g, outs[g], stride, st)) return r;
+    }
+  }
+  if (guarded) {
+    LRR_CUDA(c, cudaMemcpyAsync(c->h_flag_count, c->d_flag_count, sizeof(int32_t) * G, cudaMemcpyDeviceToHost, st));
+    LRR_CUDA(c, cudaEventRecord(c->flag_ev, st));
+    c->flag_pending = true;
+    c->flag_rows = n_variants;
+  } else {
+    c->flag_pending = false;
+    c->flag_rows = 0;
+    for (int g = 0; g < c->h_flag_groups; ++g) c->h_flag_count[g] = 0;
+  }
   return LRR_OK;
 }
 
@@ -134,7 +210,7 @@ extern "C" {
 
 const char* lrr_version(void) { return "lrr_b200 0.1 (sm_100a)"; }
 
-int lrr_create(lrr_ctx** out, int device) {
+int lrr_create(lrr_ctx** out, int device) try {
   if (!out) return fail(nullptr, LRR_EINVAL, "lrr_create: out is NULL");
   *out = nullptr;
   int count = 0;
@@ -155,8 +231,9 @@ int lrr_create(lrr_ctx** out, int device) {
   *out = reinterpret_cast<lrr_ctx*>(c);
   return LRR_OK;
 }
+LRR_ABI_CATCH(nullptr)
 
-void lrr_destroy(lrr_ctx* ctx) {
+void lrr_destroy(lrr_ctx* ctx) try {
   if (!ctx) return;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   DeviceGuard guard(c->device);
@@ -167,9 +244,12 @@ void lrr_destroy(lrr_ctx* ctx) {
   logit_release(c);
   cudaFree(c->arena);
   cudaFree(c->d_nanmask);
+  if (c->h_flag_count) cudaFreeHost(c->h_flag_count);
+  if (c->flag_ev) cudaEventDestroy(c->flag_ev);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   delete c;
+} catch (...) {
 }
 
 const char* lrr_last_error(const lrr_ctx* ctx) {
@@ -196,50 +276,55 @@ static int check_packed(Ctx* c, int64_t n_samples, int64_t packed_stride) {
 }
 
 int lrr_pack_bed(lrr_ctx* ctx, const uint8_t* d_bed, int64_t n_variants, int64_t bed_stride, int64_t n_samples,
-                 uint8_t* d_packed, int64_t packed_stride, uint8_t* d_row_flags, void* stream) {
+                 uint8_t* d_packed, int64_t packed_stride, uint8_t* d_row_flags, void* stream) try {
   CTX_PROLOGUE;
   if (n_variants < 0 || n_samples <= 0 || bed_stride < (n_samples + 3) / 4)
     return fail(c, LRR_EINVAL, "lrr_pack_bed: bed_stride must be >= ceil(n_samples/4) (LoadPlink.scala:240-251)");
   if (int r = check_packed(c, n_samples, packed_stride)) return r;
   return launch_pack_bed(c, d_bed, n_variants, bed_stride, n_samples, d_packed, packed_stride, d_row_flags, st);
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_pack_dosage_i8(lrr_ctx* ctx, const int8_t* d_dosage, int64_t n_variants, int64_t n_samples, uint8_t* d_packed,
-                       int64_t packed_stride, uint8_t* d_row_flags, void* stream) {
+                       int64_t packed_stride, uint8_t* d_row_flags, void* stream) try {
   CTX_PROLOGUE;
   if (n_variants < 0 || n_samples <= 0) return fail(c, LRR_EINVAL, "lrr_pack_dosage_i8: bad shape");
   if (int r = check_packed(c, n_samples, packed_stride)) return r;
   return launch_pack_i8(c, d_dosage, n_variants, n_samples, d_packed, packed_stride, d_row_flags, st);
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_unpack_dosage_i8(lrr_ctx* ctx, const uint8_t* d_packed, int64_t packed_stride, int64_t n_variants,
-                         int64_t n_samples, int8_t* d_dosage, void* stream) {
+                         int64_t n_samples, int8_t* d_dosage, void* stream) try {
   CTX_PROLOGUE;
   if (n_variants < 0 || n_samples <= 0) return fail(c, LRR_EINVAL, "lrr_unpack_dosage_i8: bad shape");
   if (int r = check_packed(c, n_samples, packed_stride)) return r;
   return launch_unpack_i8(c, d_packed, packed_stride, n_variants, n_samples, d_dosage, st);
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_unpack_bed(lrr_ctx* ctx, const uint8_t* d_packed, int64_t packed_stride, int64_t n_variants, int64_t n_samples,
-                   uint8_t* d_bed, int64_t bed_stride, void* stream) {
+                   uint8_t* d_bed, int64_t bed_stride, void* stream) try {
   CTX_PROLOGUE;
   if (n_variants < 0 || n_samples <= 0 || bed_stride < (n_samples + 3) / 4)
     return fail(c, LRR_EINVAL, "lrr_unpack_bed: bed_stride must be >= ceil(n_samples/4)");
   if (int r = check_packed(c, n_samples, packed_stride)) return r;
   return launch_unpack_bed(c, d_packed, packed_stride, n_variants, n_samples, d_bed, bed_stride, st);
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_bn_fill(lrr_ctx* ctx, const uint32_t* d_thresholds, int n_pops, const uint8_t* d_pop, int64_t n_variants,
                 int64_t first_variant, int64_t n_samples, uint64_t seed, uint8_t* d_packed, int64_t packed_stride,
-                uint8_t* d_row_flags, void* stream) {
+                uint8_t* d_row_flags, void* stream) try {
   CTX_PROLOGUE;
   if (n_variants < 0 || n_samples <= 0 || n_pops <= 0 || n_pops > 255) return fail(c, LRR_EINVAL, "lrr_bn_fill: bad shape");
   if (int r = check_packed(c, n_samples, packed_stride)) return r;
   return launch_bn_fill(c, d_thresholds, n_pops, d_pop, n_variants, first_variant, n_samples, seed, d_packed,
                         packed_stride, d_row_flags, st);
 }
+LRR_ABI_CATCH(ctx)
 
-int lrr_clear_groups(lrr_ctx* ctx) {
+int lrr_clear_groups(lrr_ctx* ctx) try {
   if (!ctx) return LRR_EINVAL;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   DeviceGuard guard(c->device);
@@ -252,6 +337,7 @@ int lrr_clear_groups(lrr_ctx* ctx) {
   c->n_samples_total = 0;
   return LRR_OK;
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_num_groups(const lrr_ctx* ctx) {
   return ctx ? (int)reinterpret_cast<const Ctx*>(ctx)->groups.size() : 0;
@@ -351,19 +437,21 @@ static int add_group_impl(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int3
 
 int lrr_add_group(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, int32_t P, int32_t has_intercept,
                   const int32_t* complete_idx, const double* q_cols, const double* y_res, const double* qty,
-                  const double* yyp) {
+                  const double* yyp) try {
   return add_group_impl(ctx, n_samples_total, n, K, P, has_intercept, complete_idx, q_cols, y_res, qty, yyp, nullptr);
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_add_group_weighted(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, int32_t P,
                            const int32_t* complete_idx, const double* q_cols, const double* y_res, const double* qty,
-                           const double* yyp, const double* sqrt_w) {
+                           const double* yyp, const double* sqrt_w) try {
   if (ctx && !sqrt_w) return fail(reinterpret_cast<Ctx*>(ctx), LRR_EINVAL, "lrr_add_group_weighted: sqrt_w is NULL");
   return add_group_impl(ctx, n_samples_total, n, K, P, 0, complete_idx, q_cols, y_res, qty, yyp, sqrt_w);
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_set_score_model(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, const int32_t* complete_idx,
-                        const double* wc, const double* resid, const double* w, const double* finv, const double* score0) {
+                        const double* wc, const double* resid, const double* w, const double* finv, const double* score0) try {
   if (!ctx) return LRR_EINVAL;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (K < 1) return fail(c, LRR_EINVAL, "logistic regression requires at least one covariate expression");
@@ -381,9 +469,10 @@ int lrr_set_score_model(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_
   c->groups.back().score = 1;
   return LRR_OK;
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_run_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t ldx, int64_t n_samples_total,
-                  const lrr_group_out* outs, int32_t n_outs, void* stream) {
+                  const lrr_group_out* outs, int32_t n_outs, void* stream) try {
   CTX_PROLOGUE;
   if (c->groups.empty()) return fail(c, LRR_ESTATE, "lrr_run_dense: no groups (call lrr_add_group)");
   if (c->groups[0].score) return fail(c, LRR_ESTATE, "lrr_run_dense: the context holds a logistic score model");
@@ -399,9 +488,10 @@ int lrr_run_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t l
     if (int r = launch_stats_epilogue(c, (int)g, n_variants, outs[g], st, true)) return r;
   return LRR_OK;
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_run_score(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
-                  int64_t n_samples_total, const lrr_score_out* out, void* stream) {
+                  int64_t n_samples_total, const lrr_score_out* out, void* stream) try {
   CTX_PROLOGUE;
   (void)d_row_flags;
   if (c->groups.size() != 1 || !c->groups[0].score) return fail(c, LRR_ESTATE, "lrr_run_score: call lrr_set_score_model first");
@@ -417,32 +507,36 @@ int lrr_run_score(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_fl
   c->last_kernel = LRR_KERNEL_FP64;
   return launch_score_epilogue(c, n_variants, *out, st);
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_set_logit_model(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_t K, const int32_t* complete_idx,
                         const double* cov, const double* y, const double* b0, const double* score0, const double* fisher0,
-                        double loglik0) {
+                        double loglik0) try {
   if (!ctx) return LRR_EINVAL;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   DeviceGuard guard(c->device);
   return logit_set_model(c, n_samples_total, n, K, complete_idx, cov, y, b0, score0, fisher0, loglik0);
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_run_logit(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int64_t packed_stride, int64_t n_samples_total,
-                  int32_t test, int32_t max_iterations, double tolerance, const lrr_logit_out* out, void* stream) {
+                  int32_t test, int32_t max_iterations, double tolerance, const lrr_logit_out* out, void* stream) try {
   CTX_PROLOGUE;
   if (!out) return fail(c, LRR_EINVAL, "lrr_run_logit: out is NULL");
   if (int r = check_packed(c, n_samples_total, packed_stride)) return r;
   return logit_run(c, d_packed, nullptr, n_variants, packed_stride, n_samples_total, test, max_iterations, tolerance, *out, st);
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_run_logit_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t ldx, int64_t n_samples_total, int32_t test,
-                        int32_t max_iterations, double tolerance, const lrr_logit_out* out, void* stream) {
+                        int32_t max_iterations, double tolerance, const lrr_logit_out* out, void* stream) try {
   CTX_PROLOGUE;
   if (!out) return fail(c, LRR_EINVAL, "lrr_run_logit_dense: out is NULL");
   return logit_run(c, nullptr, d_x, n_variants, ldx, n_samples_total, test, max_iterations, tolerance, *out, st);
 }
+LRR_ABI_CATCH(ctx)
 
-int lrr_reserve(lrr_ctx* ctx, int64_t max_variants) {
+int lrr_reserve(lrr_ctx* ctx, int64_t max_variants) try {
   if (!ctx) return LRR_EINVAL;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   DeviceGuard guard(c->device);
@@ -450,23 +544,42 @@ int lrr_reserve(lrr_ctx* ctx, int64_t max_variants) {
   if (max_variants < 0) return fail(c, LRR_EINVAL, "lrr_reserve: negative size");
   return ensure_workspace(c, max_variants);
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_run(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
-            int64_t n_samples_total, const lrr_group_out* outs, int32_t n_outs, int32_t kernel, void* stream) {
+            int64_t n_samples_total, const lrr_group_out* outs, int32_t n_outs, int32_t kernel, void* stream) try {
   CTX_PROLOGUE;
   return run_rows(c, d_packed, d_row_flags, n_variants, packed_stride, n_samples_total, outs, n_outs, kernel, st);
+}
+LRR_ABI_CATCH(ctx)
+
+int lrr_set_guard(lrr_ctx* ctx, int enabled) {
+  if (!ctx) return LRR_EINVAL;
+  reinterpret_cast<Ctx*>(ctx)->guard = enabled ? 1 : 0;
+  return LRR_OK;
+}
+
+int64_t lrr_last_recomputed(lrr_ctx* ctx) {
+  if (!ctx) return -1;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  DeviceGuard guard(c->device);
+  if (c->flag_pending && cudaEventSynchronize(c->flag_ev) != cudaSuccess) return -1;
+  int64_t total = 0;
+  for (size_t g = 0; g < c->groups.size() && (int)g < c->h_flag_groups; ++g) total += c->h_flag_count[g];
+  return total;
 }
 
 int64_t lrr_launch_count(const lrr_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->launches : 0; }
 int lrr_last_kernel(const lrr_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->last_kernel : 0; }
 
-int lrr_set_timing(lrr_ctx* ctx, int enabled) {
+int lrr_set_timing(lrr_ctx* ctx, int enabled) try {
   if (!ctx) return LRR_EINVAL;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   c->timing = enabled ? 1 : 0;
   if (!enabled) c->ev_valid = false;
   return LRR_OK;
 }
+LRR_ABI_CATCH(ctx)
 
 float lrr_last_sweep_ms(lrr_ctx* ctx) {
   if (!ctx) return -1.f;
@@ -480,25 +593,28 @@ float lrr_last_sweep_ms(lrr_ctx* ctx) {
 }
 
 int lrr_student_t_two_sided(lrr_ctx* ctx, const double* d_t, int64_t count, double df, double* d_p, double* d_log10_p,
-                            void* stream) {
+                            void* stream) try {
   CTX_PROLOGUE;
   if (count < 0 || !(df > 0)) return fail(c, LRR_EINVAL, "lrr_student_t_two_sided: bad arguments");
   return launch_student_t(c, d_t, count, df, d_p, d_log10_p, st);
 }
+LRR_ABI_CATCH(ctx)
 
-int lrr_qchisqtail1(lrr_ctx* ctx, const double* d_p, int64_t count, double* d_chi2, void* stream) {
+int lrr_qchisqtail1(lrr_ctx* ctx, const double* d_p, int64_t count, double* d_chi2, void* stream) try {
   CTX_PROLOGUE;
   if (count < 0 || (count > 0 && (!d_p || !d_chi2))) return fail(c, LRR_EINVAL, "lrr_qchisqtail1: bad arguments");
   return launch_qchisqtail1(c, d_p, count, d_chi2, st);
 }
+LRR_ABI_CATCH(ctx)
 
 int lrr_at_times(lrr_ctx* ctx, const uint8_t* d_packed, int64_t n_variants, int64_t packed_stride, int64_t n_samples_total,
-                 const double* d_coef, const double* d_t, int32_t L, int32_t n_splits, double* d_out, void* stream) {
+                 const double* d_coef, const double* d_t, int32_t L, int32_t n_splits, double* d_out, void* stream) try {
   CTX_PROLOGUE;
   if (n_variants < 0 || n_samples_total <= 0) return fail(c, LRR_EINVAL, "lrr_at_times: bad shape");
   if (int r = check_packed(c, n_samples_total, packed_stride)) return r;
   if (!d_out || (n_variants > 0 && (!d_packed || !d_coef || !d_t))) return fail(c, LRR_EINVAL, "lrr_at_times: NULL array");
   return launch_at_times(c, d_packed, n_variants, packed_stride, n_samples_total, d_coef, d_t, L, n_splits, d_out, st);
 }
+LRR_ABI_CATCH(ctx)
 
 }  // extern "C"

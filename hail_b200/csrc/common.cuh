@@ -2,13 +2,31 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../../include/lrr_b200.h"
 
+// Tuning switches read from the environment exist only in tuning builds (scratch/build_abl.sh passes -DLRR_TUNING=1):
+// the shipped library never consults the environment, so no variable can change its results.
+#ifndef LRR_TUNING
+#define LRR_TUNING 0
+#endif
+
 namespace lrr {
+
+inline const char* tuning_env(const char* name) {
+#if LRR_TUNING
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
 
 constexpr int kSamplesPerWord = 16;    // 2 bits per call, 32-bit words
 constexpr int kRowAlignBytes = 128;    // packed row stride granularity (TMA boxes, 128-bit loads)
@@ -69,6 +87,18 @@ struct Ctx {
   // dense-dosage path: one bit per (variant, sample) "missing and in the group" (dense_kernel.cu), grow-only
   void* d_nanmask = nullptr;
   size_t nanmask_bytes = 0;
+  // tolerance guard of the quantised (tensor-core) sweeps: rows whose rigorous error bound leaves the tolerance are
+  // listed by the statistics epilogue and recomputed in float64 (stats_device.cuh, fp64_kernel.cu)
+  int32_t* d_flag_mark = nullptr;   // [G][reserved] 1 = row already listed
+  int32_t* d_flag_list = nullptr;   // [G][reserved] listed rows
+  int32_t* d_flag_count = nullptr;  // [G]
+  int32_t* h_flag_count = nullptr;  // page-locked mirror of d_flag_count after the last run (see lrr_last_recomputed)
+  int h_flag_groups = 0;
+  cudaEvent_t flag_ev = nullptr;    // the mirror is valid once this has completed
+  bool flag_pending = false;
+  int64_t flag_rows = 0;            // rows of the run the mirror belongs to
+  int guard = 1;                    // 0: no tolerance guard (kernel tuning / tests of the raw quantised path)
+  int digit_boost = 0;              // extra base-13 digits for covariate / fitted columns (raised when > 2 % of a run was recomputed)
 };
 
 // make `dev` current for the lifetime of the guard
@@ -87,6 +117,13 @@ struct DeviceGuard {
 
 int fail(Ctx* c, int code, const std::string& msg);
 int cuda_fail(Ctx* c, cudaError_t e, const char* what);
+// No C++ exception crosses the C ABI: every extern "C" entry point is a function-try-block ending in
+// LRR_ABI_CATCH, which turns std::bad_alloc into LRR_ENOMEM and anything else into LRR_ESTATE with the message kept.
+int abi_caught(void* ctx, int code, const char* what) noexcept;
+#define LRR_ABI_CATCH(ctx)                                                                              \
+  catch (const std::bad_alloc&) { return lrr::abi_caught((void*)(ctx), LRR_ENOMEM, "out of host memory"); } \
+  catch (const std::exception& e) { return lrr::abi_caught((void*)(ctx), LRR_ESTATE, e.what()); }          \
+  catch (...) { return lrr::abi_caught((void*)(ctx), LRR_ESTATE, "unknown C++ exception"); }
 
 #define LRR_CUDA(ctx, call)                                  \
   do {                                                       \
@@ -105,13 +142,22 @@ int launch_fp64_sweep(Ctx*, const uint8_t* d_packed, int64_t M, int64_t stride, 
 int launch_dense_sweep(Ctx*, const double* d_x, int64_t M, int64_t ldx, cudaStream_t);
 int launch_tc_sweep(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, cudaStream_t);
 bool tc_supported(Ctx*, bool may_have_missing);
+const double* tc_quantum(Ctx*, int g);
+const double* tc4_quantum(Ctx*, int g, int* n_fit);
+int launch_fp64_recompute(Ctx*, int g, const uint8_t* d_packed, int64_t stride, const int32_t* d_list, const int32_t* d_count,
+                          int dots_stride, cudaStream_t);
 void tc_invalidate(Ctx*);
 void tc_release(Ctx*);
 int launch_tc4_sweep(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, cudaStream_t);
 bool tc4_supported(Ctx*, bool single_pass_only);
 void tc4_invalidate(Ctx*);
 void tc4_release(Ctx*);
-int launch_stats_epilogue(Ctx*, int g, int64_t M, const lrr_group_out& out, cudaStream_t, bool dense = false);
+// `quantum` != NULL: per-column quantisation step of the sweep that produced the dots (tolerance guard on); `n_fit`:
+// fitted-value dot products behind the C dot columns; `stride`: doubles per dots row
+int launch_stats_epilogue(Ctx*, int g, int64_t M, const lrr_group_out& out, cudaStream_t, bool dense = false,
+                          const double* quantum = nullptr, int n_fit = 0, int stride = 0, double qscale = 1.0);
+// the same statistics for the rows listed in d_flag_list (after launch_fp64_recompute)
+int launch_stats_epilogue_listed(Ctx*, int g, const lrr_group_out& out, int stride, cudaStream_t);
 int run_rows(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, int64_t n_samples_total,
              const lrr_group_out* outs, int32_t n_outs, int32_t kernel, cudaStream_t);
 int launch_student_t(Ctx*, const double*, int64_t, double, double*, double*, cudaStream_t);

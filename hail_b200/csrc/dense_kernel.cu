@@ -72,8 +72,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// exponent all ones: NaN (missing) or +-Inf.  Both count as "missing" here: an infinite entry has no meaningful
-// regression in the reference either (every statistic NaN); mean-imputing it keeps the other rows of the CTA clean.
+// exponent all ones: NaN (missing) or +-Inf.  Both are zeroed in shared memory so that the other rows of the CTA stay
+// clean, but only NaN is a missing entry (RU:16-58): an infinite entry is a DEFINED value in the reference and turns
+// every statistic of its row into NaN (sum_x into +-Inf); the row is marked in counts[v].w (bit 0: +Inf seen,
+// bit 1: -Inf seen) and the statistics epilogue emits exactly that.
 __device__ __forceinline__ bool not_finite(double v) { return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000; }
 
 // CB = basis columns of this pass (compile-time: the accumulators live in registers), FIRST = this pass also produces
@@ -230,9 +232,9 @@ __global__ void __launch_bounds__(THREADS, 1) dense_sweep_kernel(DenseArgs a) {
       cp_async_commit();
     }
 
-    int nm[SVW];
+    int nm[SVW], inf_seen[SVW];
 #pragma unroll
-    for (int r = 0; r < SVW; ++r) nm[r] = 0;
+    for (int r = 0; r < SVW; ++r) nm[r] = inf_seen[r] = 0;
     // one step on the stage in `slot`: missing bits of chunk `chunk`, then zero the holes in place
     auto stat_step = [&](int64_t chunk, int slot) {
       double* st = s_ring + slot * STAGE_DOUBLES + (sw * SVW) * CHUNK + lane * 2;
@@ -245,10 +247,14 @@ __global__ void __launch_bounds__(THREADS, 1) dense_sweep_kernel(DenseArgs a) {
 #pragma unroll
       for (int r = 0; r < SVW; ++r) {
         double2 xv = *reinterpret_cast<const double2*>(st + r * CHUNK);
-        const bool m0 = not_finite(xv.x), m1 = not_finite(xv.y);
+        bool m0 = not_finite(xv.x), m1 = not_finite(xv.y);
         if (m0 || m1) {
-          if (m0) xv.x = 0.0;
-          if (m1) xv.y = 0.0;
+          if (FIRST) {   // +-Inf inside the group: a defined value, not a missing one
+            if (m0 && isinf(xv.x)) { if (g0) inf_seen[r] |= xv.x > 0.0 ? 1 : 2; m0 = false; }
+            if (m1 && isinf(xv.y)) { if (g1) inf_seen[r] |= xv.y > 0.0 ? 1 : 2; m1 = false; }
+          }
+          if (not_finite(xv.x)) xv.x = 0.0;
+          if (not_finite(xv.y)) xv.y = 0.0;
           *reinterpret_cast<double2*>(st + r * CHUNK) = xv;
         }
         if (FIRST) {
@@ -275,7 +281,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_sweep_kernel(DenseArgs a) {
 #pragma unroll
       for (int r = 0; r < SVW; ++r) {
         const int64_t vv = v0 + sw * SVW + r;
-        if (lane == 0 && vv < a.M) reinterpret_cast<int4*>(a.counts)[vv] = make_int4(0, 0, nm[r], 0);
+        const int inf_bits = (int)__reduce_or_sync(0xffffffffu, (unsigned)inf_seen[r]);
+        if (lane == 0 && vv < a.M) reinterpret_cast<int4*>(a.counts)[vv] = make_int4(0, 0, nm[r], inf_bits);
       }
     }
   }
@@ -358,36 +365,33 @@ __global__ void indicator_kernel(const uint32_t* __restrict__ mask, int64_t ns_p
 }
 
 template <int CB, bool FIRST, bool VEC, bool SQ>
-void launch_pass_v(const DenseArgs& a, int grid, cudaStream_t st) {
+cudaError_t launch_pass_v(const DenseArgs& a, int grid, cudaStream_t st) {
   constexpr int smem = STAGES * (VT + 1 + CB) * CHUNK * (int)sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(dense_sweep_kernel<CB, FIRST, VEC, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
-  }
+  // the attribute is per device: set it on every launch (a host-side table write) instead of caching one flag per process
+  const cudaError_t e = cudaFuncSetAttribute(dense_sweep_kernel<CB, FIRST, VEC, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
   dense_sweep_kernel<CB, FIRST, VEC, SQ><<<grid, THREADS, smem, st>>>(a);
+  return cudaSuccess;
 }
 
 template <int CB, bool FIRST, bool SQ = false>
-void launch_pass(const DenseArgs& a, bool vec, int grid, cudaStream_t st) {
-  if (vec) launch_pass_v<CB, FIRST, true, SQ>(a, grid, st);
-  else launch_pass_v<CB, FIRST, false, SQ>(a, grid, st);
+cudaError_t launch_pass(const DenseArgs& a, bool vec, int grid, cudaStream_t st) {
+  return vec ? launch_pass_v<CB, FIRST, true, SQ>(a, grid, st) : launch_pass_v<CB, FIRST, false, SQ>(a, grid, st);
 }
 
 template <bool FIRST>
-void launch_pass_cb(const DenseArgs& a, int cb, bool vec, int grid, cudaStream_t st) {
+cudaError_t launch_pass_cb(const DenseArgs& a, int cb, bool vec, int grid, cudaStream_t st) {
   if (a.sq_col >= 0) {   // weighted groups: fewer column-tile sizes (each is one more kernel to build)
-    if (cb <= 4) launch_pass<4, FIRST, true>(a, vec, grid, st);
-    else if (cb <= 8) launch_pass<8, FIRST, true>(a, vec, grid, st);
-    else launch_pass<12, FIRST, true>(a, vec, grid, st);
-    return;
+    if (cb <= 4) return launch_pass<4, FIRST, true>(a, vec, grid, st);
+    if (cb <= 8) return launch_pass<8, FIRST, true>(a, vec, grid, st);
+    return launch_pass<12, FIRST, true>(a, vec, grid, st);
   }
-  if (cb <= 2) launch_pass<2, FIRST>(a, vec, grid, st);
-  else if (cb <= 4) launch_pass<4, FIRST>(a, vec, grid, st);
-  else if (cb <= 6) launch_pass<6, FIRST>(a, vec, grid, st);
-  else if (cb <= 8) launch_pass<8, FIRST>(a, vec, grid, st);
-  else if (cb <= 10) launch_pass<10, FIRST>(a, vec, grid, st);
-  else launch_pass<12, FIRST>(a, vec, grid, st);
+  if (cb <= 2) return launch_pass<2, FIRST>(a, vec, grid, st);
+  if (cb <= 4) return launch_pass<4, FIRST>(a, vec, grid, st);
+  if (cb <= 6) return launch_pass<6, FIRST>(a, vec, grid, st);
+  if (cb <= 8) return launch_pass<8, FIRST>(a, vec, grid, st);
+  if (cb <= 10) return launch_pass<10, FIRST>(a, vec, grid, st);
+  return launch_pass<12, FIRST>(a, vec, grid, st);
 }
 
 }  // namespace
@@ -437,8 +441,7 @@ int launch_dense_sweep(Ctx* c, const double* d_x, int64_t M, int64_t ldx, cudaSt
     do {
       a.c0 = c0;
       const int cb = G.C - c0;
-      if (c0 == 0) launch_pass_cb<true>(a, cb, vec, grid, st);
-      else launch_pass_cb<false>(a, cb, vec, grid, st);
+      LRR_CUDA(c, c0 == 0 ? launch_pass_cb<true>(a, cb, vec, grid, st) : launch_pass_cb<false>(a, cb, vec, grid, st));
       c->launches++;
       LRR_CUDA(c, cudaGetLastError());
       c0 += 12;

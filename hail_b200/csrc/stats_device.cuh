@@ -78,14 +78,24 @@ struct StatModel {
   const double* qty;      // [K][P]
   const double* yyp;      // [P]
   int n, K, Kd, P, C, has_intercept, d, weighted;
-  int dense;              // dense-dosage sweep: dv has C + 2 entries, dv[C] = sum of the defined entries, dv[C + 1] =
-                          // their sum of squares
+  int dense;              // dense-dosage sweep: dv[C] = sum of the defined entries, dv[C + 1] = their sum of squares
+  int stride;             // doubles per dots row
+  int n_fit;              // > 0: dv[C + p] = (fitted-value column of phenotype p) . x, the covariate part of y_transpose_x
+  // tolerance guard of the quantised sweeps (NULL = the dots are float64 sums, nothing to guard)
+  const double* quantum;  // [C + n_fit] quantisation step of every dot column
+  double qscale;          // the per-sample error is at most qscale * quantum / 2 (int8 sweep: 4, its shifted fields)
+  double tol, tol_p;      // relative bounds that pass (half of BASELINE's 1e-6 / 1e-5: the other half is the reference's own roundoff)
+  double t_floor;         // an absolute error bound of t (of beta in units of its standard error) below this passes too
+  int32_t* flag_mark;     // [M]
+  int32_t* flag_list;     // [M]
+  int32_t* flag_count;
   double lbeta;
   lrr_group_out out;
 };
 
-// statistics of variant v, phenotype p of one group from the exact counts and the dot products dv[0..C)
-__device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n1, int n2, int nm, const double* dv) {
+// statistics of variant v, phenotype p of one group from the exact counts and the dot products dv[0..stride).
+// `aux` = counts[v].w: dense sweep only, bit 0 / 1 = a +Inf / -Inf entry inside the group.
+__device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n1, int n2, int nm, int aux, const double* dv) {
   const double dRec = 1.0 / (double)a.d;  // LR:51
   const int64_t idx = v * a.P + p;
   const double nv = (double)(a.n - nm);
@@ -93,7 +103,7 @@ __device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n
   const double xx_int = (double)(n1 + 4 * n2);
   const double mean = S / nv;                        // RU:52
   // weighted groups (statgen.py:636-660): the column sum and x.x of the sqrt(w)-scaled imputed x are dot products
-  const double sum_x = a.weighted ? dv[a.Kd + a.P] : S + (double)nm * mean;        // LR:136
+  double sum_x = a.weighted ? dv[a.Kd + a.P] : S + (double)nm * mean;        // LR:136
   // dense: centred sum of squares of the imputed column (the imputed entries sit at the mean and add nothing)
   const double xxc = a.dense ? dv[a.C + 1] - S * S / nv : 0.0;
   const double xx_imp = a.weighted ? dv[a.Kd + a.P + 1]
@@ -111,15 +121,21 @@ __device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n
   const double xyp = dv[a.Kd + p];                   // y_res . x  == ytx - Qty^T qtx (LR:146)
   double proj = 0.0;
   if (a.has_intercept) proj = a.qty[p] * (sum_x / sqrt((double)a.n));
-  for (int c = 0; c < a.Kd; ++c) proj += a.qty[(c + a.has_intercept) * a.P + p] * dv[c];
-  const double ytx = xyp + proj;                     // LR:143
+  if (a.n_fit) {
+    proj += dv[a.C + p];
+  } else {
+    for (int c = 0; c < a.Kd; ++c) proj += a.qty[(c + a.has_intercept) * a.P + p] * dv[c];
+  }
+  double ytx = xyp + proj;                           // LR:143
 
   double b, se, t, pv, l10 = 0.0;
   // Degenerate (constant / collinear) x: the reference leaves roundoff garbage here (xxp = +-1e-15 and
   // sqrt of a negative -> NaN se; test_statgen.py:277-284).  Rule: no information -> NaN statistics.
-  const bool degenerate = !(xxp > 1e-11 * xx_imp);
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  const double thr = 1e-11 * xx_imp;
+  const bool degenerate = !(xxp > thr);
   if (degenerate && !isnan(xxp)) {
-    b = se = t = pv = l10 = __longlong_as_double(0x7ff8000000000000ll);
+    b = se = t = pv = l10 = nan;
   } else {
     const double xxpRec = 1.0 / xxp;
     b = xyp * xxpRec;                                          // LR:150-155
@@ -127,6 +143,52 @@ __device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n
     t = b / se;                                                // LR:159
     pv = two_sided_p_dev(t, (double)a.d, a.lbeta, a.out.log10_p ? &l10 : nullptr);  // LR:160
   }
+  if (a.dense && (aux & 3)) {
+    // an infinite entry is a defined value in the reference: sum_x = +-Inf (NaN when both signs occur), x.x = Inf and every
+    // statistic NaN (Inf - Inf); the sweep zeroed the entry to keep its other sums finite
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    sum_x = (aux & 3) == 1 ? inf : (aux & 3) == 2 ? -inf : nan;
+    ytx = b = se = t = pv = l10 = nan;
+  }
+
+  // ---- tolerance guard (quantised sweeps): rigorous bounds on what the digit quantisation can have changed ----
+  if (a.quantum && nv > 0.0) {
+    // every stored basis value is within quantum / 2 of the true one and the imputed column is non-negative, so a dot
+    // product is off by at most (quantum / 2) * sum_j x_j, whatever the genotypes are
+    const double h = 0.5 * a.qscale * (S + (double)nm * mean) * (1.0 + 1e-9);
+    double Eq = 0.0, Eproj = 0.0;
+    for (int c = 0; c < a.Kd; ++c) {
+      const double e = h * a.quantum[c];
+      Eq += (2.0 * fabs(dv[c]) + e) * e;
+      if (!a.n_fit) Eproj += fabs(a.qty[(c + a.has_intercept) * a.P + p]) * e;
+    }
+    const double Ey = h * a.quantum[a.Kd + p];
+    const double Eytx = Ey + (a.n_fit ? h * a.quantum[a.C + p] : Eproj);
+    bool flag;
+    if (fabs(xxp - thr) <= Eq) {
+      flag = true;                        // the degenerate-or-not decision itself is in doubt
+    } else if (degenerate) {
+      flag = false;                       // NaN statistics either way
+    } else {
+      const double inv = 1.0 / xxp;
+      const double rx = Eq / (xxp - Eq);                                   // relative bound of 1 / xxp
+      const double Eb = inv * (Ey * (1.0 + rx) + fabs(xyp) * rx);
+      const double se2 = dRec * (a.yyp[p] * inv - b * b);
+      const double Ese2 = dRec * (a.yyp[p] * inv * rx + (2.0 * fabs(b) + Eb) * Eb);
+      const double Ese = Ese2 / (se + sqrt(fmax(se2 - Ese2, 0.0)));
+      const double Et = (Eb + fabs(t) * Ese) / (se - Ese);
+      const bool ok_b = Eb <= a.tol * fabs(b) || Eb <= a.t_floor * se;
+      const bool ok_se = se2 > Ese2 && Ese <= a.tol * se;
+      const bool ok_t = Et <= a.tol * fabs(t) || Et <= a.t_floor;
+      // |d log p / d t| <= |t| + 2.7 for the two-sided Student-t tail (Mills-ratio bound; 2 f(t) / p <= 2.7 for |t| <= 1)
+      const bool ok_p = Et * (fabs(t) + 2.7) <= a.tol_p || Et <= a.t_floor;
+      // wide profile: the same absolute floor, expressed on the dot-product scale (d beta = d xyp / xxp)
+      const bool ok_ytx = Eytx <= a.tol * fabs(ytx) || (a.P > 2 && Eytx <= a.t_floor * se * xxp);
+      flag = !(ok_b && ok_se && ok_t && ok_p && ok_ytx);   // a NaN anywhere fails its test
+    }
+    if (flag && atomicExch(a.flag_mark + v, 1) == 0) a.flag_list[atomicAdd(a.flag_count, 1)] = (int32_t)v;
+  }
+
   if (p == 0) {
     if (a.out.n) a.out.n[v] = a.n;
     if (a.out.n_missing) a.out.n_missing[v] = nm;
@@ -154,6 +216,16 @@ inline StatModel stat_model_of(const Group& G, const lrr_group_out& out) {
   a.d = G.d;
   a.weighted = G.weighted;
   a.dense = 0;
+  a.stride = G.C;
+  a.n_fit = 0;
+  a.quantum = nullptr;
+  a.qscale = 1.0;
+  a.tol = 0.5e-6;
+  a.tol_p = 0.5e-5;
+  // strict profile: |dt| <= 5e-10 passes (the float64 floor the parity tests allow); wide profile (P > 2, the
+  // dense-contraction configuration with its stated tolerance): |dt| <= 5e-7
+  a.t_floor = G.P > 2 ? 0.5e-6 : 0.5e-9;
+  a.flag_mark = a.flag_list = a.flag_count = nullptr;
   a.lbeta = G.lbeta;
   a.out = out;
   return a;

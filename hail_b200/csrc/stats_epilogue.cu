@@ -21,7 +21,20 @@ __global__ void stats_epilogue_kernel(EpiArgs a) {
     const int64_t v = idx / a.model.P;
     const int p = (int)(idx - v * a.model.P);
     const int4 cnt = reinterpret_cast<const int4*>(a.counts)[v];
-    variant_stats(a.model, v, p, cnt.x, cnt.y, cnt.z, a.dots + v * (a.model.C + (a.model.dense ? 2 : 0)));
+    variant_stats(a.model, v, p, cnt.x, cnt.y, cnt.z, cnt.w, a.dots + v * a.model.stride);
+  }
+}
+
+// the same statistics for the rows the guard listed, after their float64 recompute (a.model.quantum == NULL here)
+__global__ void stats_epilogue_listed_kernel(EpiArgs a, const int32_t* __restrict__ list, const int32_t* __restrict__ count) {
+  const int64_t total = (int64_t)(*count) * a.model.P;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / a.model.P;
+    const int p = (int)(idx - i * a.model.P);
+    const int64_t v = list[i];
+    const int4 cnt = reinterpret_cast<const int4*>(a.counts)[v];
+    variant_stats(a.model, v, p, cnt.x, cnt.y, cnt.z, cnt.w, a.dots + v * a.model.stride);
   }
 }
 
@@ -83,7 +96,8 @@ double log_beta_half(double a) {
   return 0.5 * log(3.14159265358979323846) - 0.5 * log(a) + series;
 }
 
-int launch_stats_epilogue(Ctx* c, int g, int64_t M, const lrr_group_out& out, cudaStream_t st, bool dense) {
+int launch_stats_epilogue(Ctx* c, int g, int64_t M, const lrr_group_out& out, cudaStream_t st, bool dense,
+                          const double* quantum, int n_fit, int stride, double qscale) {
   if (M == 0) return LRR_OK;
   const Group& G = c->groups[g];
   EpiArgs a;
@@ -92,10 +106,34 @@ int launch_stats_epilogue(Ctx* c, int g, int64_t M, const lrr_group_out& out, cu
   a.M = M;
   a.model = stat_model_of(G, out);
   a.model.dense = dense ? 1 : 0;
+  a.model.stride = stride > 0 ? stride : G.C + (dense ? 2 : 0);
+  a.model.n_fit = n_fit;
+  if (quantum && c->guard && !G.weighted) {
+    a.model.quantum = quantum;
+    a.model.qscale = qscale;
+    a.model.flag_mark = c->d_flag_mark + (int64_t)g * c->reserved_variants;
+    a.model.flag_list = c->d_flag_list + (int64_t)g * c->reserved_variants;
+    a.model.flag_count = c->d_flag_count + g;
+  }
   const int64_t total = M * G.P;
   int64_t grid = (total + 127) / 128;
   if (grid > (int64_t)c->sm_count * 32) grid = (int64_t)c->sm_count * 32;
   stats_epilogue_kernel<<<(int)grid, 128, 0, st>>>(a);
+  c->launches++;
+  LRR_CUDA(c, cudaGetLastError());
+  return LRR_OK;
+}
+
+int launch_stats_epilogue_listed(Ctx* c, int g, const lrr_group_out& out, int stride, cudaStream_t st) {
+  const Group& G = c->groups[g];
+  EpiArgs a;
+  a.counts = c->d_counts + (int64_t)g * c->reserved_variants * 4;
+  a.dots = c->d_dots + c->dots_offset[g];
+  a.M = 0;
+  a.model = stat_model_of(G, out);
+  a.model.stride = stride;
+  stats_epilogue_listed_kernel<<<c->sm_count, 128, 0, st>>>(a, c->d_flag_list + (int64_t)g * c->reserved_variants,
+                                                          c->d_flag_count + g);
   c->launches++;
   LRR_CUDA(c, cudaGetLastError());
   return LRR_OK;

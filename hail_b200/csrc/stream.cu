@@ -145,7 +145,7 @@ using namespace lrr;
 extern "C" {
 
 int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64_t n_variants, int64_t bed_stride,
-                     int64_t n_samples, int64_t block_variants, int32_t depth) {
+                     int64_t n_samples, int64_t block_variants, int32_t depth) try {
   if (!ctx) return LRR_EINVAL;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!out) return fail(c, LRR_EINVAL, "lrr_stream_begin: out is NULL");
@@ -227,8 +227,9 @@ int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64
   *out = reinterpret_cast<lrr_stream*>(s);
   return LRR_OK;
 }
+LRR_ABI_CATCH(ctx)
 
-int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs, int32_t n_outs, int32_t kernel) {
+int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs, int32_t n_outs, int32_t kernel) try {
   if (!ctx || !stream) return LRR_EINVAL;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   Stream* s = reinterpret_cast<Stream*>(stream);
@@ -291,10 +292,12 @@ int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs
   if (rc == LRR_OK && e2 != cudaSuccess) rc = cuda_fail(c, e2, "cudaStreamSynchronize(comp)");
   return rc;
 }
+LRR_ABI_CATCH(ctx)
 
-void lrr_stream_end(lrr_ctx* ctx, lrr_stream* stream) {
+void lrr_stream_end(lrr_ctx* ctx, lrr_stream* stream) try {
   (void)ctx;
   destroy(reinterpret_cast<Stream*>(stream));
+} catch (...) {
 }
 
 }  // extern "C"

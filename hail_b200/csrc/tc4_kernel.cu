@@ -5,8 +5,11 @@
 // restated), but both operands are E2M1 (4-bit float) elements:
 //   A  call code c in {0..3} as the nibble 00cc = c / 2 (exactly representable: 0, .5, 1, 1.5), 64 samples per MMA;
 //   B  every basis column as balanced base-13 digits u in {0, +-1, +-2, +-3, +-4, +-6, +-8} stored as u / 2 (the E2M1
-//      values 0, .5, 1, 1.5, 2, 3, 4): a complete residue system mod 13, 13 digits (46.5 bits) for phenotype
-//      columns, 9 digits (31.7 bits) for covariate columns; block scales are all 1 (UE8M0 0x7F).
+//      values 0, .5, 1, 1.5, 2, 3, 4): a complete residue system mod 13.  The number of digits is chosen PER COLUMN by
+//      the host (digit_policy below: 13 digits = 46.5 bits for the residualised phenotype columns, 6 for well-scaled
+//      covariate columns plus one 11-digit "fitted value" column per phenotype that carries y_transpose_x, more for
+//      heavy-tailed columns); what the chosen quantum costs is bounded per variant in the statistics epilogue
+//      (stats_device.cuh) and rows outside the tolerance are recomputed in float64.  Block scales are all 1 (UE8M0 0x7F).
 // Every product is a multiple of 1/4 and the f32 accumulator holds sum c u / 4 EXACTLY as long as |sum c u| <= 2^24;
 // the host checks the worst case over all possible genotypes for every column (acc_bound_kernel) and refuses the
 // kernel otherwise, so the result is independent of tiling and summation order, like the int8 kernel's INT32 sums.
@@ -34,7 +37,8 @@
 #include "tc_ptx.cuh"
 
 // Timing ablations (LRR_ABL_BITS / LRR_ABL_STREAM / LRR_ABL_CONTIG, see Params) are compiled in only with
-// -DLRR_TC4_ABLATIONS=1 (scratch/sustain.sh, scratch/quick.sh); the shipped kernel carries none of their tests.
+// -DLRR_TC4_ABLATIONS=1 -DLRR_TUNING=1 (scratch/build_abl.sh); the shipped kernel carries none of their tests and the
+// shipped library never reads the environment (common.cuh tuning_env).
 #ifndef LRR_TC4_ABLATIONS
 #define LRR_TC4_ABLATIONS 0
 #endif
@@ -73,26 +77,21 @@ constexpr int MAX_GSTAGES = 10;
 constexpr int NB = 6;                  // basis-panel ring depth the MMA fast path is unrolled for
 constexpr int MAX_BSTAGES = NB;
 constexpr int SF_COLS = 16;            // scale-factor columns (A: first 8, B: last 8), all bytes 0x7F
-#ifndef LRR_TC4_DIG_Y
-#define LRR_TC4_DIG_Y 13
-#endif
-#ifndef LRR_TC4_DIG_Q
-#define LRR_TC4_DIG_Q 9
-#endif
-constexpr int DIG_Y = LRR_TC4_DIG_Y, DIG_Q = LRR_TC4_DIG_Q;   // base-13 digits per phenotype / covariate column
+constexpr int MAX_DIGITS = 13;         // base-13 digits per column: 13^13 / 3 < 2^53 / 3, recombined in two int64 halves
 constexpr int PASS_COLS = 112;         // digit columns per sweep: 2 * 112 accumulators + 16 + ring of 4 * 64 <= 512
 constexpr int UNROLL = 12;             // chunks per unrolled block of the MMA fast path (lcm of NB and NU)
 
 struct GroupMeta {
   int col_off;        // first digit column of this group in B
-  int C;              // dot-product columns (Kd + P)
-  int Kd;             // of which covariate columns (DIG_Q digits each; the rest have DIG_Y)
+  int C;              // dot-product columns of this segment
+  int n_digit_cols;   // sum of nd[0..C): the "ones" column follows them
   int n;              // complete samples
   int32_t* counts;    // [M][4]
   double* dots;       // [M][dots_stride], already offset to this segment's first dot column
   int dots_stride;
   const double* colscale;   // [C]
   const uint32_t* mask_hi;  // [ns_pad/16], high bit of each kept field
+  uint8_t nd[PASS_COLS];    // base-13 digits of each dot column of the segment
 };
 
 struct Params {
@@ -627,9 +626,8 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
           const GroupMeta& G = p.g[g];
           const int cnt = n2[g] + bars->n2_xchg[tile_i & 1][0][g][row] + bars->n2_xchg[tile_i & 1][1][g][row] +
                           bars->n2_xchg[tile_i & 1][2][g][row];
-          // the group's columns: Kd x DIG_Q then P x DIG_Y digit columns, then one "ones" column (digit value 1.0)
-          const int n_digit_cols = G.Kd * DIG_Q + (G.C - G.Kd) * DIG_Y;
-          const int ones_col = G.col_off + n_digit_cols;
+          // the group's columns: nd[c] digit columns per dot column c, then one "ones" column (digit value 1.0)
+          const int ones_col = G.col_off + G.n_digit_cols;
           uint32_t r16[16];
           tmem_ld16(d_c + (ones_col & ~15), r16);
           tmem_wait_ld();
@@ -656,7 +654,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
           const int c_lo = G.col_off, c_hi = ones_col;
           long long hi = 0, lo = 0, mhi = 0, mlo = 0;
           long long pw = 1;   // 13^sl (sl < 6) or 13^(sl - 6)
-          int c = 0, sl = 0, nd = G.Kd > 0 ? DIG_Q : DIG_Y;
+          int c = 0, sl = 0, nd = G.nd[0];
           for (int base = c_lo & ~15; base < c_hi; base += 16) {
             uint32_t dc[16], dm[16];
             tmem_ld16(d_c + base, dc);
@@ -687,7 +685,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
                   sl = 0;
                   pw = 1;
                   ++c;
-                  nd = c < G.Kd ? DIG_Q : DIG_Y;
+                  nd = c < G.C ? G.nd[c] : MAX_DIGITS;
                 }
               }
             }
@@ -714,13 +712,39 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // basis quantisation: float64 column -> balanced base-13 digits as E2M1 nibbles, in the A operand's element order
 // ------------------------------------------------------------------------------------------------
-__global__ void colmax_kernel(const double* __restrict__ basis, int C, int64_t ns_pad, unsigned long long* colmax_bits) {
-  const int c = blockIdx.y;
-  double m = 0.0;
-  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ns_pad; j += (int64_t)gridDim.x * blockDim.x)
-    m = fmax(m, fabs(basis[(int64_t)c * ns_pad + j]));
-  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(colmax_bits + c, (unsigned long long)__double_as_longlong(m));
+// max |v| and sum v^2 of one column per CTA (fixed reduction order: the digit policy below must not depend on atomics)
+__global__ void __launch_bounds__(1024) colstat_kernel(const double* __restrict__ col, int64_t ns_pad, double* __restrict__ colmax,
+                                                       double* __restrict__ sumsq) {
+  __shared__ double s_m[32], s_q[32];
+  double m = 0.0, q = 0.0;
+  for (int64_t j = threadIdx.x; j < ns_pad; j += blockDim.x) {
+    const double v = col[j];
+    m = fmax(m, fabs(v));
+    q = fma(v, v, q);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_m[threadIdx.x >> 5] = m; s_q[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { m = fmax(m, s_m[w]); q += s_q[w]; }
+    *colmax = m;
+    *sumsq = q;
+  }
+}
+
+// the "fitted value" column of phenotype p: fit[j] = sum_c q_c[j] * Qty[c + has_intercept][p] over the Kd dot-product
+// covariate columns, so that y_transpose_x = xyp + Qty[0][p] sum_x / sqrt(n) + fit . x (LR:143-146) needs no
+// high-precision covariate projections
+__global__ void fitted_kernel(const double* __restrict__ basis, const double* __restrict__ qty, int Kd, int P, int has_intercept,
+                              int p, int64_t ns_pad, double* __restrict__ fit) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ns_pad; j += (int64_t)gridDim.x * blockDim.x) {
+    double f = 0.0;
+    for (int c = 0; c < Kd; ++c) f = fma(basis[(int64_t)c * ns_pad + j], qty[(c + has_intercept) * P + p], f);
+    fit[j] = f;
+  }
 }
 
 // digit of residue r = I mod 13, chosen from {0, +-1, +-2, +-3, +-4, +-6, +-8} (complete residue system mod 13)
@@ -742,38 +766,43 @@ __host__ __device__ inline double imax13(int nd) {   // floor(13^nd / 3): every 
   return floor(p13 / 3.0);
 }
 
-// One thread per byte of a panel row.  Byte b of a row covers word wd = b / 8 of the packed genotype row (16 samples):
-// with r = (b % 8) / 4 and i = b % 4 its low nibble is sample 16 wd + 4 r + i, its high nibble sample 16 wd + 4 (r + 2) + i
-// -- the order in which the unpack warps emit the calls of a word.
-__global__ void quantize_kernel(const double* __restrict__ basis, const uint32_t* __restrict__ mask, int C, int Kd,
-                                int64_t ns_pad, const unsigned long long* __restrict__ colmax_bits, int col_off,
-                                uint8_t* __restrict__ bq, double* __restrict__ colscale) {
-  const int c = blockIdx.y;  // 0..C-1 data columns, C = ones column
-  const int nd = c < Kd ? DIG_Q : DIG_Y;
-  const int first = col_off + (c < Kd ? c * DIG_Q : Kd * DIG_Q + (c - Kd) * DIG_Y);
+// One column -> its nd digit rows.  One thread per byte of a panel row.  Byte b of a row covers word wd = b / 8 of the
+// packed genotype row (16 samples): with r = (b % 8) / 4 and i = b % 4 its low nibble is sample 16 wd + 4 r + i, its high
+// nibble sample 16 wd + 4 (r + 2) + i -- the order in which the unpack warps emit the calls of a word.
+// The stored value of sample j is I_j * colscale with I_j = rn(v_j / colscale), |I_j| <= imax: |v_j - I_j colscale| <=
+// colscale / 2 (plus 2^-52 |v_j| of the division), the per-sample quantum the statistics epilogue bounds.
+__global__ void quantize_kernel(const double* __restrict__ col, int nd, int64_t ns_pad, const double* __restrict__ colmax,
+                                int first_row, uint8_t* __restrict__ bq, double* __restrict__ colscale) {
   const double imax = imax13(nd);
+  const int64_t row_bytes = ns_pad / 2;
+  const double cm = *colmax;
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < row_bytes; b += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t wd = b >> 3;
+    const int r = (int)((b >> 2) & 1), i = (int)(b & 3);
+    const int64_t j_lo = 16 * wd + 4 * r + i, j_hi = j_lo + 8;
+    long long I_lo = 0, I_hi = 0;
+    if (cm > 0.0) {
+      I_lo = __double2ll_rn(col[j_lo] / cm * imax);
+      I_hi = __double2ll_rn(col[j_hi] / cm * imax);
+    }
+    for (int s = 0; s < nd; ++s) {
+      const uint32_t lo = e2m1_code(digit13(I_lo)), hi = e2m1_code(digit13(I_hi));
+      bq[(int64_t)(first_row + s) * row_bytes + b] = (uint8_t)(lo | (hi << 4));
+    }
+    if (b == 0) *colscale = cm > 0.0 ? cm / imax : 0.0;
+  }
+}
+
+// the "ones" row of a segment: digit value 1.0 for the samples of the group
+__global__ void ones_row_kernel(const uint32_t* __restrict__ mask, int64_t ns_pad, int row, uint8_t* __restrict__ bq) {
   const int64_t row_bytes = ns_pad / 2;
   for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < row_bytes; b += (int64_t)gridDim.x * blockDim.x) {
     const int64_t wd = b >> 3;
     const int r = (int)((b >> 2) & 1), i = (int)(b & 3);
     const int64_t j_lo = 16 * wd + 4 * r + i, j_hi = j_lo + 8;
-    if (c == C) {
-      const uint32_t mw = mask[wd];
-      const uint32_t in_lo = (mw >> sample_shift((int)(j_lo & 15))) & 1u, in_hi = (mw >> sample_shift((int)(j_hi & 15))) & 1u;
-      bq[(int64_t)first * row_bytes + b] = (uint8_t)((in_lo ? 2u : 0u) | ((in_hi ? 2u : 0u) << 4));   // digit value 1.0
-      continue;
-    }
-    const double cm = __longlong_as_double((long long)colmax_bits[c]);
-    long long I_lo = 0, I_hi = 0;
-    if (cm > 0.0) {
-      I_lo = __double2ll_rn(basis[(int64_t)c * ns_pad + j_lo] / cm * imax);
-      I_hi = __double2ll_rn(basis[(int64_t)c * ns_pad + j_hi] / cm * imax);
-    }
-    for (int s = 0; s < nd; ++s) {
-      const uint32_t lo = e2m1_code(digit13(I_lo)), hi = e2m1_code(digit13(I_hi));
-      bq[(int64_t)(first + s) * row_bytes + b] = (uint8_t)(lo | (hi << 4));
-    }
-    if (b == 0) colscale[c] = cm > 0.0 ? cm / imax : 0.0;
+    const uint32_t mw = mask[wd];
+    const uint32_t in_lo = (mw >> sample_shift((int)(j_lo & 15))) & 1u, in_hi = (mw >> sample_shift((int)(j_hi & 15))) & 1u;
+    bq[(int64_t)row * row_bytes + b] = (uint8_t)((in_lo ? 2u : 0u) | ((in_hi ? 2u : 0u) << 4));
   }
 }
 
@@ -813,9 +842,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct Segment {
   int group;     // index into Ctx::groups
-  int c_first;   // first dot column of the group in this segment
+  int c_first;   // first (extended) dot column of the group in this segment
   int n_cols;    // dot columns in this segment
-  int kd_in;     // of which (leading) covariate columns
+  int n_digit_cols;   // their digit rows
   int row0;      // first row of this segment in the pass's panel matrix (digit rows, then the ones row)
 };
 
@@ -833,15 +862,24 @@ struct Pass {
   PassShape shape[2];            // [cluster size - 1]
 };
 
+// Per group: the dot columns the sweep produces.  Columns [0, C) are the group's basis planes ([Kd covariate | P
+// residualised phenotype] columns); columns [C, C + n_fit) are fitted-value columns (one per phenotype, P <= 2 only).
+struct GroupCols {
+  int n_fit = 0;
+  double* d_fit = nullptr;       // [n_fit][ns_pad]
+  std::vector<uint8_t> nd;       // [C + n_fit] base-13 digits per column
+};
+
 struct State {
   bool prepared = false;
   bool usable = false;
   std::string why;
   EncodeTiledFn encode = nullptr;
   std::vector<Pass> passes;
+  std::vector<GroupCols> cols;
   uint8_t* d_bq = nullptr;
   double* d_colscale = nullptr;
-  unsigned long long* d_colmax = nullptr;
+  double* d_colstat = nullptr;   // [2][nscale]: column maxima, sums of squares
   uint32_t* d_mask_hi = nullptr;
   std::vector<int> scale_off;
   int cluster = 2;
@@ -856,12 +894,14 @@ static State* state(Ctx* c) {
 static void free_prepared(State* s) {
   cudaFree(s->d_bq);
   cudaFree(s->d_colscale);
-  cudaFree(s->d_colmax);
+  cudaFree(s->d_colstat);
   cudaFree(s->d_mask_hi);
+  for (auto& gc : s->cols) cudaFree(gc.d_fit);
+  s->cols.clear();
   s->d_mask_hi = nullptr;
   s->d_bq = nullptr;
   s->d_colscale = nullptr;
-  s->d_colmax = nullptr;
+  s->d_colstat = nullptr;
   s->passes.clear();
   s->prepared = false;
   s->usable = false;
@@ -875,14 +915,48 @@ static int encode_2d(State* s, CUtensorMap* map, const void* ptr, uint64_t inner
   cuuint32_t estr[2] = {1, 1};
   CUresult r = s->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         getenv("LRR_ABL_L2P128") ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
-                         : getenv("LRR_ABL_L2PNONE") ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         tuning_env("LRR_ABL_L2P128") ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                         : tuning_env("LRR_ABL_L2PNONE") ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Digit policy.  The quantisation error of a dot product is at most (colscale / 2) * sum_j |x_j| for ANY genotype row
+// (stats_device.cuh checks exactly that per variant), colscale = colmax / floor(13^nd / 3).  The digit counts below
+// keep that bound inside the tolerance for well-scaled columns at any allele frequency (DESIGN.md 5.1 "precision"):
+//   strict profile (P <= 2)   residualised phenotype 13 digits (|dt| <= 1e-10), covariate columns 6 digits (they only
+//                             enter x.x - |Q'x|^2, relative error ~1e-7), and y_transpose_x comes from one 11-digit
+//                             fitted-value column per phenotype instead of the covariate projections;
+//   wide profile (P > 2)      phenotype columns 10 digits (|dt| <= 1.5e-7 worst case, ~1e-10 typical: the "stated
+//                             tolerance" of the dense-contraction configuration), covariate columns 13 digits (shared by
+//                             all phenotypes; they carry y_transpose_x).
+// A column whose maximum is far above 4.5 rms (heavy tails, outliers) gets one more digit per factor 13, up to 13;
+// `boost` (Ctx::digit_boost, raised when too many rows had to be recomputed) adds digits to the covariate / fitted columns.
+// ------------------------------------------------------------------------------------------------
+static int tail_digits(double colmax, double sumsq, int64_t n) {
+  if (!(colmax > 0.0) || !(sumsq > 0.0) || n <= 0) return 0;
+  const double ratio = colmax / (4.5 * sqrt(sumsq / (double)n));
+  if (!(ratio > 1.0)) return 0;
+  return (int)ceil(log(ratio) / log(13.0) - 1e-9);
+}
+
+static void digit_policy(const Group& gr, int n_fit, const double* colmax, const double* sumsq, int boost, std::vector<uint8_t>& nd) {
+  const bool wide = gr.P > 2;
+  const int Cx = gr.C + n_fit;
+  nd.resize(Cx);
+  for (int c = 0; c < Cx; ++c) {
+    int base;
+    if (c < gr.Kd) base = (wide || n_fit == 0 ? 13 : 6 + boost);
+    else if (c < gr.C) base = wide ? 10 + boost : 13;
+    else base = 11 + boost;
+    const int d = base + tail_digits(colmax[c], sumsq[c], gr.n);
+    nd[c] = (uint8_t)std::min(MAX_DIGITS, std::max(1, d));
+  }
+}
+
 // split every group's dot columns into passes of at most PASS_COLS panel rows
-static void plan_passes(const Ctx* c, std::vector<Pass>& passes) {
+static void plan_passes(const Ctx* c, const std::vector<GroupCols>& cols, std::vector<Pass>& passes) {
   passes.clear();
   Pass cur;
   int used = 0;
@@ -895,29 +969,27 @@ static void plan_passes(const Ctx* c, std::vector<Pass>& passes) {
     used = 0;
   };
   for (size_t g = 0; g < c->groups.size(); ++g) {
-    const Group& gr = c->groups[g];
+    const std::vector<uint8_t>& nd = cols[g].nd;
+    const int Cx = (int)nd.size();
     int col = 0;
-    while (col < gr.C) {
-      const int nd0 = col < gr.Kd ? DIG_Q : DIG_Y;
-      if (used + nd0 + 1 > PASS_COLS || (int)cur.segs.size() == MAX_GROUPS) close();
+    while (col < Cx) {
+      if (used + nd[col] + 1 > PASS_COLS || (int)cur.segs.size() == MAX_GROUPS) close();
       Segment sg;
       sg.group = (int)g;
       sg.c_first = col;
       sg.n_cols = 0;
-      sg.kd_in = 0;
       sg.row0 = used;
       int rows = 0;
-      while (col < gr.C) {
-        const int nd = col < gr.Kd ? DIG_Q : DIG_Y;
-        if (used + rows + nd + 1 > PASS_COLS) break;
-        rows += nd;
-        if (col < gr.Kd) sg.kd_in++;
+      while (col < Cx) {
+        if (used + rows + nd[col] + 1 > PASS_COLS) break;
+        rows += nd[col];
         sg.n_cols++;
         col++;
       }
+      sg.n_digit_cols = rows;
       used += rows + 1;   // + ones row
       cur.segs.push_back(sg);
-      if (col < gr.C) close();
+      if (col < Cx) close();
     }
   }
   close();
@@ -950,48 +1022,75 @@ static int prepare(Ctx* c) {
       s->why = "weighted groups (x.x is not linear in the call codes) run on the float64 kernel";
       return LRR_OK;
     }
+  const int64_t ns_pad = c->groups[0].ns_pad;
+  const int64_t row_bytes = ns_pad / 2;
+  const unsigned gx = (unsigned)std::min<int64_t>((ns_pad + 255) / 256, 1024);
+  const unsigned gxb = (unsigned)std::min<int64_t>((row_bytes + 255) / 256, 1024);
+  // ---- fitted-value columns, column statistics, digit policy ----
   int nscale = 0;
   s->scale_off.assign(G, 0);
+  s->cols.assign(G, GroupCols());
   for (size_t g = 0; g < G; ++g) {
+    const Group& gr = c->groups[g];
+    GroupCols& gc = s->cols[g];
+    gc.n_fit = (gr.P <= 2 && gr.Kd > 0) ? gr.P : 0;   // the spare two slots of a dots row hold their dot products
     s->scale_off[g] = nscale;
-    nscale += c->groups[g].C;
+    nscale += gr.C + gc.n_fit;
+    if (gc.n_fit) {
+      LRR_CUDA(c, cudaMalloc(&gc.d_fit, sizeof(double) * (size_t)gc.n_fit * (size_t)ns_pad));
+      for (int p = 0; p < gc.n_fit; ++p)
+        fitted_kernel<<<gx, 256>>>(gr.d_basis, gr.d_qty, gr.Kd, gr.P, gr.has_intercept, p, ns_pad, gc.d_fit + (int64_t)p * ns_pad);
+      c->launches += gc.n_fit;
+    }
   }
-  plan_passes(c, s->passes);
+  auto column_ptr = [&](size_t g, int col) -> const double* {
+    const Group& gr = c->groups[g];
+    return col < gr.C ? gr.d_basis + (int64_t)col * ns_pad : s->cols[g].d_fit + (int64_t)(col - gr.C) * ns_pad;
+  };
+  LRR_CUDA(c, cudaMalloc(&s->d_colstat, sizeof(double) * 2 * (size_t)nscale));
+  LRR_CUDA(c, cudaMalloc(&s->d_colscale, sizeof(double) * (size_t)nscale));
+  for (size_t g = 0; g < G; ++g)
+    for (int col = 0; col < c->groups[g].C + s->cols[g].n_fit; ++col) {
+      const int k = s->scale_off[g] + col;
+      colstat_kernel<<<1, 1024>>>(column_ptr(g, col), ns_pad, s->d_colstat + k, s->d_colstat + nscale + k);
+      c->launches++;
+    }
+  LRR_CUDA(c, cudaGetLastError());
+  std::vector<double> h_stat(2 * (size_t)nscale);
+  LRR_CUDA(c, cudaMemcpy(h_stat.data(), s->d_colstat, sizeof(double) * h_stat.size(), cudaMemcpyDeviceToHost));
+  for (size_t g = 0; g < G; ++g)
+    digit_policy(c->groups[g], s->cols[g].n_fit, h_stat.data() + s->scale_off[g], h_stat.data() + nscale + s->scale_off[g],
+                 c->digit_boost, s->cols[g].nd);
+  plan_passes(c, s->cols, s->passes);
   int64_t total_rows = 0;
   for (auto& ps : s->passes) {
     ps.bq_row0 = total_rows;
     total_rows += ps.ncols;
   }
-  const int64_t ns_pad = c->groups[0].ns_pad;
-  const int64_t row_bytes = ns_pad / 2;
   LRR_CUDA(c, cudaMalloc(&s->d_bq, (size_t)total_rows * row_bytes));
   LRR_CUDA(c, cudaMemset(s->d_bq, 0, (size_t)total_rows * row_bytes));
-  LRR_CUDA(c, cudaMalloc(&s->d_colscale, sizeof(double) * (size_t)nscale));
-  LRR_CUDA(c, cudaMalloc(&s->d_colmax, sizeof(unsigned long long) * (size_t)nscale));
-  LRR_CUDA(c, cudaMemset(s->d_colmax, 0, sizeof(unsigned long long) * (size_t)nscale));
   const int64_t mask_words = ns_pad / 16;
   LRR_CUDA(c, cudaMalloc(&s->d_mask_hi, sizeof(uint32_t) * (size_t)mask_words * G));
   bool any_masked = false;
-  const unsigned gx = (unsigned)std::min<int64_t>((ns_pad + 255) / 256, 1024);
-  const unsigned gxb = (unsigned)std::min<int64_t>((row_bytes + 255) / 256, 1024);
   for (size_t g = 0; g < G; ++g) {
     const Group& gr = c->groups[g];
     if ((int64_t)gr.n != c->n_samples_total) any_masked = true;
     mask_hi_kernel<<<(unsigned)std::min<int64_t>((mask_words + 255) / 256, 1024), 256>>>(gr.d_mask, mask_words,
                                                                                         s->d_mask_hi + g * mask_words);
-    for (int c0 = 0; c0 < gr.C; c0 += 65535)
-      colmax_kernel<<<dim3(gx, (unsigned)std::min(gr.C - c0, 65535)), 256>>>(gr.d_basis + (int64_t)c0 * ns_pad,
-                                                                            std::min(gr.C - c0, 65535), ns_pad,
-                                                                            s->d_colmax + s->scale_off[g] + c0);
-    c->launches += 2;
+    c->launches++;
   }
   for (auto& ps : s->passes) {
     for (const Segment& sg : ps.segs) {
       const Group& gr = c->groups[sg.group];
-      quantize_kernel<<<dim3(gxb, (unsigned)(sg.n_cols + 1)), 256>>>(
-          gr.d_basis + (int64_t)sg.c_first * ns_pad, gr.d_mask, sg.n_cols, sg.kd_in, ns_pad,
-          s->d_colmax + s->scale_off[sg.group] + sg.c_first, (int)(ps.bq_row0 + sg.row0), s->d_bq,
-          s->d_colscale + s->scale_off[sg.group] + sg.c_first);
+      int row = (int)ps.bq_row0 + sg.row0;
+      for (int i = 0; i < sg.n_cols; ++i) {
+        const int col = sg.c_first + i, k = s->scale_off[sg.group] + col;
+        const int nd = s->cols[sg.group].nd[col];
+        quantize_kernel<<<gxb, 256>>>(column_ptr(sg.group, col), nd, ns_pad, s->d_colstat + k, row, s->d_bq, s->d_colscale + k);
+        row += nd;
+        c->launches++;
+      }
+      ones_row_kernel<<<gxb, 256>>>(gr.d_mask, ns_pad, row, s->d_bq);
       c->launches++;
     }
   }
@@ -1017,7 +1116,6 @@ static int prepare(Ctx* c) {
       return LRR_OK;
     }
   }
-  LRR_CUDA(c, cudaDeviceSynchronize());
   const int budget = 227 * 1024 - (int)sizeof(Barriers) - 1024;
   for (auto& ps : s->passes) {
     ps.mask_bytes = any_masked ? (int)ps.segs.size() * 128 : 0;
@@ -1026,7 +1124,7 @@ static int prepare(Ctx* c) {
     ps.ring_base1 = (ps.ncols + 31) / 32 * 32;
     ps.ring_base2 = (2 * ps.ncols + 31) / 32 * 32;
     ps.nu1 = (SF_BASE - ps.ring_base1) / UNIT_COLS >= 6 ? 6 : 4;
-    if (const char* e = getenv("LRR_TC4_NU1")) { if (atoi(e) == 4) ps.nu1 = 4; }
+    if (const char* e = tuning_env("LRR_TC4_NU1")) { if (atoi(e) == 4) ps.nu1 = 4; }
     if (ps.ring_base2 + NU2 * UNIT_COLS > SF_BASE || ps.ring_base1 + ps.nu1 * UNIT_COLS > SF_BASE) {
       s->why = "not enough tensor memory for the A ring";
       return LRR_OK;
@@ -1062,7 +1160,7 @@ static int prepare(Ctx* c) {
 #undef LRR_SET_SMEM
     s->attr_set = true;
   }
-  if (const char* e = getenv("LRR_TC_CLUSTER")) {
+  if (const char* e = tuning_env("LRR_TC_CLUSTER")) {
     const int v = atoi(e);
     if (v == 1 || v == 2) s->cluster = v;
   }
@@ -1088,6 +1186,14 @@ bool tc4_supported(Ctx* c, bool single_pass_only) {
   return true;
 }
 
+// per-column quantum (value of one unit of the lowest digit) of group g's dot columns [C + n_fit], after tc4_supported
+const double* tc4_quantum(Ctx* c, int g, int* n_fit) {
+  tc4::State* s = tc4::state(c);
+  if (!s->usable) return nullptr;
+  if (n_fit) *n_fit = s->cols[g].n_fit;
+  return s->d_colscale + s->scale_off[g];
+}
+
 void tc4_invalidate(Ctx* c) {
   if (!c->tc4_state) return;
   tc4::free_prepared(static_cast<tc4::State*>(c->tc4_state));
@@ -1109,7 +1215,7 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
   State* s = state(c);
   if (!s->usable) return fail(c, LRR_EINVAL, "4-bit tensor-core kernel unavailable: " + s->why);
   CUtensorMap geno_map;
-  const bool abl_contig = getenv("LRR_ABL_CONTIG") != nullptr;   // timing ablation only
+  const bool abl_contig = tuning_env("LRR_ABL_CONTIG") != nullptr;   // timing ablation only
   if (abl_contig) {
     if (encode_2d(s, &geno_map, d_packed, 128, (uint64_t)(M * stride / 128), 128, 128, TILE_M))
       return fail(c, LRR_ECUDA, "cuTensorMapEncodeTiled failed (contiguous ablation)");
@@ -1136,18 +1242,19 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
     p.mask_bytes = ps.mask_bytes;
     p.row_flags = d_row_flags;
     p.abl_contig = abl_contig ? 1 : 0;
-    p.abl_stream = getenv("LRR_ABL_STREAM") ? atoi(getenv("LRR_ABL_STREAM")) : 0;
-    p.abl = getenv("LRR_ABL_BITS") ? atoi(getenv("LRR_ABL_BITS")) : 0;
+    p.abl_stream = tuning_env("LRR_ABL_STREAM") ? atoi(tuning_env("LRR_ABL_STREAM")) : 0;
+    p.abl = tuning_env("LRR_ABL_BITS") ? atoi(tuning_env("LRR_ABL_BITS")) : 0;
     for (int i = 0; i < p.n_groups; ++i) {
       const Segment& sg = ps.segs[i];
       const Group& gr = c->groups[sg.group];
       p.g[i].col_off = sg.row0;
       p.g[i].C = sg.n_cols;
-      p.g[i].Kd = sg.kd_in;
+      p.g[i].n_digit_cols = sg.n_digit_cols;
+      memcpy(p.g[i].nd, s->cols[sg.group].nd.data() + sg.c_first, (size_t)sg.n_cols);
       p.g[i].n = gr.n;
       p.g[i].counts = c->d_counts + (int64_t)sg.group * c->reserved_variants * 4;
       p.g[i].dots = c->d_dots + c->dots_offset[sg.group] + sg.c_first;
-      p.g[i].dots_stride = gr.C;
+      p.g[i].dots_stride = gr.C + 2;   // [C dot products | fitted-value dot products (<= 2)]
       p.g[i].colscale = s->d_colscale + s->scale_off[sg.group] + sg.c_first;
       p.g[i].mask_hi = s->d_mask_hi + (int64_t)sg.group * (gr.ns_pad / 16);
     }

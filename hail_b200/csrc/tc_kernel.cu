@@ -79,12 +79,12 @@ constexpr int MAX_GSTAGES = 10;        // genotype ring (16 KB per stage)
 constexpr int MAX_BSTAGES = 6;         // basis-panel ring (4 * ncols * 128 B per stage)
 constexpr int MAX_RING = 4;            // A ring groups (GROUP_COLS TMEM columns each)
 constexpr int GROUP_COLS = 128;        // one-plane: 4 slots of plane c; two-plane: 2 slots of plane c + 2 of plane m
-// Balanced base-256 digits per basis column.  The residualised phenotype columns feed beta directly and get 48
-// bits (error 2^-47 of the column max, the float64 roundoff class of the reference's own dgemm); the centred
-// covariate columns only enter through |Q^T x|^2 and the y_transpose_x reconstruction, where 32 bits already
-// leave a relative error below 1e-10 (DESIGN.md "precision").
+// Balanced base-256 digits per basis column: 48 bits for every column (error 2^-47 of the column max, 2^-45 for the
+// samples whose field reaches the MMA as 4c -- the quantum the tolerance guard of stats_device.cuh is given is
+// therefore 4 colscale).  The covariate columns carry y_transpose_x = xyp + Qty . qtx, whose RIGOROUS bound needs the
+// same class of precision as the phenotype columns (32-bit covariate digits left 1 % of the rows outside it).
 constexpr int N_SLICES_Y = 6;
-constexpr int N_SLICES_Q = 4;
+constexpr int N_SLICES_Q = 6;
 // TMEM column map (512 columns x 128 lanes x 32 bit), ncols = digit columns padded to 16:
 //   [0, ncols)            accumulators of plane c (raw call code)
 //   [ncols, 2 ncols)      accumulators of plane m (missing indicator), two-plane tiles only
@@ -1222,13 +1222,13 @@ static int prepare(Ctx* c) {
       sh.bstage_bytes = SLOTS * rows * 128;
       // basis-panel ring: 6 stages if at least 6 genotype stages still fit, else 3, else whatever fits (generic path)
       int bst = LRR_TC_NB;
-      if (const char* e = getenv("LRR_TC_BSTAGES")) bst = atoi(e);
+      if (const char* e = tuning_env("LRR_TC_BSTAGES")) bst = atoi(e);
       if (bst > MAX_BSTAGES) bst = MAX_BSTAGES;
       if (bst > 3 && budget - bst * sh.bstage_bytes < 6 * ps.gstage_bytes) bst = 3;
       while (bst > 2 && budget - bst * sh.bstage_bytes < 3 * ps.gstage_bytes) --bst;
       int gst = (budget - bst * sh.bstage_bytes) / ps.gstage_bytes;
       if (gst > MAX_GSTAGES) gst = MAX_GSTAGES;
-      if (const char* e = getenv("LRR_TC_GSTAGES")) { const int v = atoi(e); if (v >= 2 && v < gst) gst = v; }
+      if (const char* e = tuning_env("LRR_TC_GSTAGES")) { const int v = atoi(e); if (v >= 2 && v < gst) gst = v; }
       if (bst < 2 || gst < 2) {
         s->why = "not enough shared memory for the genotype / basis-panel rings";
         return LRR_OK;
@@ -1246,7 +1246,7 @@ static int prepare(Ctx* c) {
 #undef LRR_SET_SMEM
     s->attr_set = true;
   }
-  if (const char* e = getenv("LRR_TC_CLUSTER")) {
+  if (const char* e = tuning_env("LRR_TC_CLUSTER")) {
     const int v = atoi(e);
     if (v == 1 || v == 2) s->cluster = v;
   }
@@ -1265,6 +1265,12 @@ bool tc_supported(Ctx* c, bool /*may_have_missing*/) {
     return false;
   }
   return true;
+}
+
+// per-column quantum (value of one unit of the lowest digit) of group g's dot columns, after tc_supported
+const double* tc_quantum(Ctx* c, int g) {
+  tc::State* s = tc::state(c);
+  return s->d_colscale ? s->d_colscale + s->scale_off[g] : nullptr;
 }
 
 void tc_invalidate(Ctx* c) {

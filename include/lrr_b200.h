@@ -38,7 +38,8 @@ extern "C" {
 #define LRR_ESTATE 3   /* call order / missing groups */
 #define LRR_ENOMEM 4
 
-/* kernels selectable in lrr_run */
+/* kernels selectable in lrr_run.  AUTO: FP64 for tiny inputs (n_variants * n_samples <= 2.5e8), else TC4 (as many
+ * sweeps as the digit columns need) when its exactness bound holds (<= 699k samples guaranteed), else TC, else FP64. */
 #define LRR_KERNEL_AUTO 0
 #define LRR_KERNEL_FP64 1  /* CUDA-core float64 reference-order kernel */
 #define LRR_KERNEL_TC 2    /* tcgen05 int8-sliced exact-integer kernel (INT32 accumulators) */
@@ -141,6 +142,16 @@ int lrr_run(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_flags, i
  * missing (mean-imputed per group as RU:16-58).  Float64 CUDA-core kernel; weighted groups (lrr_add_group_weighted) too. */
 int lrr_run_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t ldx, int64_t n_samples_total,
                   const lrr_group_out* outs, int32_t n_outs, void* stream);
+/* Tolerance guard of the quantised (TC / TC4) sweeps.  The basis columns are stored as exact digits of a fixed-point
+ * value, so a dot product is off by at most (quantum / 2) * sum_j x_j for ANY genotype row; the per-variant epilogue
+ * propagates that bound through xxp, beta, standard_error, t_stat, p_value and y_transpose_x and lists every row whose
+ * bound leaves half of the parity tolerance (relative 1e-6, p-values 1e-5; an absolute |dt| <= 5e-10 also passes, 5e-7
+ * for groups of more than two phenotypes).  Listed rows are recomputed in float64 inside the same lrr_run (asynchronous,
+ * same stream).  lrr_last_recomputed returns how many rows of the last lrr_run were recomputed, summed over the groups
+ * (it synchronises on that run); when more than 2 % were, the next lrr_run re-quantises the basis with more digits.
+ * lrr_set_guard(ctx, 0) switches the guard off (kernel tuning, tests of the raw quantised path). */
+int lrr_set_guard(lrr_ctx* ctx, int enabled);
+int64_t lrr_last_recomputed(lrr_ctx* ctx);
 /* number of kernel launches issued by this context since creation (for bench accounting) */
 int64_t lrr_launch_count(const lrr_ctx* ctx);
 /* which kernel LRR_KERNEL_AUTO resolved to on the last lrr_run */
@@ -194,7 +205,7 @@ int lrr_run_score(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_fl
  * in float64 on the mean-imputed genotype column.  The host fits the null model once (LogisticRegression.scala:67-91)
  * and passes, for the n complete samples (ascending complete_idx): cov [K, n], y [n] (0 / 1), the null coefficients
  * b0 [K], and the null fit's last score [K], Fisher matrix [K, K] and log-likelihood (the first Newton step of the full
- * model reuses them, LogisticRegressionModel.scala:311-325).  K <= 11.
+ * model reuses them, LogisticRegressionModel.scala:311-325).  K <= 19.
  * lrr_run_logit writes, per variant, the fields of the test's schema (`standard_error`, `z_stat`: Wald only;
  * `chi_sq_stat`: LRT / Firth only; NaN where the reference leaves them missing: fit not converged or singular) and the
  * `fit` struct (n_iterations, converged, exploded).  NULL output pointers are skipped. */
