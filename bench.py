@@ -29,6 +29,8 @@ sys.path.insert(0, ROOT)
 N_SAMPLES, N_VARIANTS, N_COV, N_PHENO = 400_000, 1_000_000, 10, 1
 WORKLOAD = "C2: BN(3 pops) 400k samples x 1M variants, P=1, K=10 (intercept + 9 PCs)"
 METRIC = "genotypes/sec (variants x samples) for linear_regression_rows"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE tc4 sweep launch on the headline workload (ncu --set full)
+TRAFFIC_C2_TC4 = {"bytes": 103306471048, "source": "constant from profiles/r01_tc4_full_c2_ncu_full.txt (ncu --set full, one launch)"}
 
 
 def parse():
@@ -49,6 +51,14 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling (BASELINE config 5): --variants is the TOTAL, split over the ranks; a range larger "
+                         "than --chunk-variants is swept in regenerated chunks")
+    ap.add_argument("--chunk-variants", type=int, default=250_000)
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: result-row gather through peer copies on the copy engines (symmetric memory) or NCCL")
+    ap.add_argument("--no-gather", action="store_true", help="A/B: skip the per-step result gather")
+    ap.add_argument("--no-broadcast", action="store_true", help="A/B: skip the per-step basis broadcast")
     return ap.parse_args()
 
 
@@ -119,6 +129,18 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def config_of(a, N, M, P, K, G, world):
+    """The `config` object: the SAME keys and values on both arms for the same command line (the driver compares them)."""
+    headline = (N, M, P, G, a.missing_rate, a.strong) == (N_SAMPLES, N_VARIANTS, N_PHENO, 1, 0.0, False)
+    return {"workload": WORKLOAD if headline
+            else f"NON-HEADLINE {N} samples x {M} variants" + (" in total (strong scaling)" if a.strong else " per GPU")
+                 + f", P={P}, groups={G}, missing={a.missing_rate}",
+            "samples": N, "variants_per_gpu": M if not a.strong else -(-M // world), "phenotypes": P, "covariates": K,
+            "missing_rate": a.missing_rate, "groups": G, "parallelism": f"variant-sharded x{world}",
+            "l2": "inputs larger than L2 (packed genotypes of one step: %.1f GB per GPU)"
+                  % ((M if not a.strong else min(-(-M // world), a.chunk_variants)) * ((N + 3) // 4 + 127) // 128 * 128 / 1e9)}
+
+
 # =================================================================================================
 def run_ours(a):
     # rank 0 prints ONE JSON line on stdout: everything else that writes to fd 1 meanwhile (NCCL's version banner comes
@@ -131,7 +153,8 @@ def run_ours(a):
 
     import hail_b200 as hb
     from hail_b200 import _lib, bn
-    from hail_b200.statgen import GroupBasis, STAT_FIELDS
+    from hail_b200 import dist as hd
+    from hail_b200.statgen import GroupBasis
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -140,21 +163,32 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    N, M = a.samples, a.variants
+    N = a.samples
     seed = 0
-
-    # ---- synthetic input, generated directly in HBM (not timed) --------------------------------
-    first = rank * M
-    pop, th, _ = bn.bn_parameters(3, N, M, missing_rate=a.missing_rate, seed=seed, first_variant=first)
-    gt = bn.bn_fill(hb.PackedGenotypes.empty(M, N, dev), pop, th, seed=seed, first_variant=first)
-    del th
-    y, cov = phenotypes_and_covariates(N, n_pheno=a.phenotypes)
     ctx = _lib.context(local)
     lib = ctx.lib
+    y, cov = phenotypes_and_covariates(N, n_pheno=a.phenotypes)
 
-    # ---- basis: host prologue on rank 0, NCCL broadcast (the analogue of sc.broadcast, LR:74-78) ---------
-    from hail_b200 import dist as hd
+    # ---- the variant range of this rank and its synthetic input, generated directly in HBM (not timed) ----
+    if a.strong:
+        # BASELINE config 5: a.variants in TOTAL, split into contiguous ranges; a range larger than what stays resident is
+        # swept in chunks regenerated from the seeded generator (it stands in for the storage the rows arrive from)
+        lo_r, hi_r = hd.variant_range(rank, world, a.variants)
+        M = hi_r - lo_r
+        chunk = min(M, a.chunk_variants)
+        first = lo_r
+    else:
+        M = chunk = a.variants
+        first = rank * M
+    gt = hb.PackedGenotypes.empty(chunk, N, dev)
 
+    def generate(first_variant, rows):
+        pop, th, _ = bn.bn_parameters(3, N, rows, missing_rate=a.missing_rate, seed=seed, first_variant=first_variant)
+        bn.bn_fill(gt.rows(0, rows), pop, th, seed=seed, first_variant=first_variant)
+
+    generate(first, chunk)
+
+    # ---- basis: host prologue on rank 0, one NCCL broadcast per call (the analogue of sc.broadcast, LR:74-78) ---------
     if a.chained:
         rng_m = np.random.Generator(np.random.Philox(key=[2, 0xC3]))
         y1 = np.where(rng_m.random(N) < 0.10, np.nan, y[:, 0])
@@ -163,79 +197,74 @@ def run_ours(a):
     else:
         y_groups = [y]
     bases = [GroupBasis(yg, cov, np.arange(N), i if a.chained else None) for i, yg in enumerate(y_groups)] if rank == 0 else None
-    bts = hd.broadcast_bases(bases, dev)
-    bt = bts[0]
+    sr = hd.ShardedRegression(gt)          # the product path: hail_b200.linear_regression_rows(_sharded=True) runs on it
+    bts = sr.set_bases(bases)
     G = len(bts)
-
-    def push_basis(bl):
-        ctx.check(lib.lrr_clear_groups(ctx.handle))
-        for b in bl:
-            t = b.tensors
-            ctx.check(lib.lrr_add_group(ctx.handle, N, b.n, b.K, b.P, b.has_intercept, t[0].data_ptr(),
-                                        t[1].data_ptr() if t[1].numel() else None, t[2].data_ptr(), t[3].data_ptr(),
-                                        t[4].data_ptr()))
-        ctx.check(lib.lrr_reserve(ctx.handle, M))
-
-    push_basis(bts)
-    n_kept, K, P = bt.n, bt.K, bt.P
+    n_kept, K, P = bts[0].n, bts[0].K, bts[0].P
     n_kept_all = [b.n for b in bts]
 
-    # Result buffers are double-buffered across steps: with N > 1 the all-gather of step i's rows runs on a side stream
-    # (its own communicator) underneath step i + 1's sweep.
+    # Result buffers are double-buffered across steps: with N > 1 the gather of step i's rows runs on a side stream
+    # underneath step i + 1's sweep.
     n_buf = 2 if world > 1 else 1
-    outs_buf, go_buf = [], []
-    for _ in range(n_buf):
-        outs_all = []
-        go = (_lib.GroupOut * G)()
-        for g in range(G):
-            o = {"n": torch.empty(M, dtype=torch.int32, device=dev), "n_missing": torch.empty(M, dtype=torch.int32, device=dev),
-                 "sum_x": torch.empty(M, dtype=torch.float64, device=dev)}
-            for f in STAT_FIELDS:
-                o[f] = torch.empty((M, bts[g].P), dtype=torch.float64, device=dev)
-            for k, v in o.items():
-                setattr(go[g], k, v.data_ptr())
-            go[g].log10_p = None
-            outs_all.append(o)
-        outs_buf.append(outs_all)
-        go_buf.append(go)
-    width = 1 + len(STAT_FIELDS) * bts[0].P
-    kid = _lib.KERNELS[a.kernel]
+    bufs = [sr.alloc_outputs() for _ in range(n_buf)]
+    width = 3 + len(sr.FIELDS) * P
     main = torch.cuda.current_stream(dev)
-    stream = main.cuda_stream
     ctx.check(lib.lrr_set_timing(ctx.handle, 1))
-    launches0 = None
     sweep_ms = []
+    gather_mode = None
     if world > 1:
         side = torch.cuda.Stream(dev)
-        pg_side = dist.new_group(list(range(world)))   # collectives on `side` need their own communicator
-        rows = [torch.empty((M, width), dtype=torch.float64, device=dev) for _ in range(n_buf)]
-        gathered = [torch.empty((world * M, width), dtype=torch.float64, device=dev) for _ in range(n_buf)]
+        gatherer = hd.RowGather(chunk, width * G, dev, n_buf, mode=a.gather)
+        gather_mode = gatherer.mode
+        rows = [torch.empty((chunk, width * G), dtype=torch.float64, device=dev) for _ in range(n_buf)]
         ev_rows = [torch.cuda.Event() for _ in range(n_buf)]
         ev_done = [torch.cuda.Event() for _ in range(n_buf)]
         used = [False] * n_buf
-        # what sc.broadcast ships per call (LR:74-78): every basis array of every group, as one flat message
-        basis_flat = torch.cat([x.contiguous().view(torch.uint8).reshape(-1) for bt_ in bts for x in bt_.tensors if x.numel()])
     step_no = [0]
+    chunk_events = []
 
-    def step(timed):
+    def sweep_chunk(timed):
+        """One lrr_run over the resident chunk (+ its share of the result gather)."""
         b = step_no[0] % n_buf
         step_no[0] += 1
-        out = outs_buf[b][0]
-        if world > 1:
-            if used[b]:
-                main.wait_event(ev_done[b])     # the gather that read this buffer two steps ago
-            dist.broadcast(basis_flat, 0)       # per-step basis broadcast, one message (35 MB at C2)
-        ctx.check(lib.lrr_run(ctx.handle, gt.data.data_ptr(), gt.flags_ptr(), M, gt.stride, N, go_buf[b], G, kid, stream))
-        if world > 1:
-            torch.cat([out["sum_x"][:, None]] + [out[f] for f in STAT_FIELDS], dim=1, out=rows[b])
+        outs, arr = bufs[b]
+        if world > 1 and used[b]:
+            main.wait_event(ev_done[b])     # the gather that read this buffer two steps ago
+        sr.run(kernel=a.kernel, outs=outs, arr=arr)
+        if world > 1 and not a.no_gather:
+            if G == 1:
+                sr.pack_rows(outs[0], out=rows[b])
+            else:
+                for g in range(G):
+                    rows[b][:, g * width:(g + 1) * width].copy_(sr.pack_rows(outs[g]))
             ev_rows[b].record(main)
             with torch.cuda.stream(side):
                 side.wait_event(ev_rows[b])
-                hd.gather_rows(rows[b], counts=[M] * world, out=gathered[b], group=pg_side)
+                gatherer.gather(rows[b], b)
                 ev_done[b].record(side)
             used[b] = True
         if timed:
             sweep_ms.append(lib.lrr_last_sweep_ms(ctx.handle))
+
+    def step(timed):
+        """One call of the hot path: the per-call basis broadcast (LR:74-78), then the sweep of this rank's range."""
+        if world > 1 and not a.no_broadcast:
+            sr.rebroadcast()                # one flat message (35 MB at C2), on the compute stream
+        if not a.strong or chunk == M:
+            sweep_chunk(timed)
+            return
+        for lo in range(0, M, chunk):       # strong scaling over a range larger than the resident chunk
+            rows_c = min(chunk, M - lo)
+            if lo:
+                generate(first + lo, rows_c)   # regenerated in place; ordered after the previous sweep on this stream
+            ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ec0.record(main)
+            sweep_chunk(timed)
+            ec1.record(main)
+            if timed:
+                chunk_events.append((ec0, ec1))
+        if M > chunk:
+            generate(first, chunk)
 
     def drain():
         if world > 1:   # every outstanding gather is inside the timed region
@@ -253,9 +282,8 @@ def run_ours(a):
     drain()
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
+    sampler.start()
+    time.sleep(0.3)
     barrier()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -268,48 +296,66 @@ def run_ours(a):
     barrier()
     t1 = time.time()
     launches = ctx.launch_count - launches0
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    recomputed = ctx.last_recomputed
+    my_ms = float(e0.elapsed_time(e1))
+    if a.strong and chunk < M:
+        # chunked strong scaling: the regeneration between chunks stands in for the storage the rows arrive from and is not
+        # part of the metric; the time of a step is the sum of its chunks' event-timed sweep + statistics (+ row packing)
+        my_ms = float(sum(c0.elapsed_time(c1) for c0, c1 in chunk_events))
+    ms = torch.tensor([my_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    clocks = sampler.stop(t0, t1)
     kernel_used = ctx.last_kernel
     ms_per_step = total_ms / a.steps
     # genotypes = variants x samples kept, summed over the groups regressed (reference: one imputed column per group)
-    value = world * M * float(sum(n_kept_all)) / (ms_per_step / 1e3)
+    total_variants = a.variants if a.strong else world * M
+    value = total_variants * float(sum(n_kept_all)) / (ms_per_step / 1e3)
 
     # ---- roofline of the dominant (sweep) kernel: algorithmic bytes / its own event-timed duration ----
     peak, peak_src = measured_peak()
-    abytes = algorithmic_bytes(M, N, G, K, P, n_kept)
+    launch_rows = chunk
+    abytes = algorithmic_bytes(launch_rows, N, G, K, P, n_kept)
     sweep = float(np.mean(sweep_ms))
     achieved = abytes / (sweep / 1e3) / 1e9
-    # DRAM bytes of one sweep launch from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum), captured on
-    # this exact workload: profiles/r01_tc4_full_c2_ncu_full.txt (103.105 GB + 0.201 GB).  Only valid for the headline.
-    headline = (N, M, P, G, a.missing_rate) == (N_SAMPLES, N_VARIANTS, N_PHENO, 1, 0.0)
-    traffic = 103306471048 if (headline and kernel_used == "tc4") else None
+    # DRAM bytes of one sweep launch: a CONSTANT from one `ncu --set full` capture of this exact workload and kernel
+    # (dram__bytes_read.sum + dram__bytes_write.sum), not a measurement of this run; null for any other workload
+    headline = (N, M, P, G, a.missing_rate, a.strong) == (N_SAMPLES, N_VARIANTS, N_PHENO, 1, 0.0, False)
+    traffic = TRAFFIC_C2_TC4["bytes"] if (headline and kernel_used == "tc4") else None
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": f"{kernel_used} sweep",
+                "frac": round(achieved / peak, 4), "traffic": traffic,
+                "traffic_source": TRAFFIC_C2_TC4["source"] if traffic else None,
+                "kernel": f"{kernel_used} sweep",
                 "kernel_ms": round(sweep, 3), "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src,
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4)}
+    # every rank's own sweep-kernel time and clocks (which rank limits the step, and why)
+    mine = {"rank": rank, "kernel_ms_min": round(float(np.min(sweep_ms)), 3), "kernel_ms_median": round(float(np.median(sweep_ms)), 3),
+            "kernel_ms_max": round(float(np.max(sweep_ms)), 3), "region_ms_per_step": round(my_ms / a.steps, 3),
+            "sm_mhz": clocks.get("sm_mhz"), "power_w": clocks.get("power_w"), "reasons": clocks.get("reasons")}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
 
     result = {
         "metric": METRIC, "value": value, "unit": "genotypes/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if a.strong else "weak", "vs_baseline": None,
         "dtype": "f64 epilogue; sweep " + {"tc": "u8 x s8 digits -> s32 exact (tcgen05 kind::i8)",
                                            "tc4": "e2m1 x e2m1 digits -> f32 exact within 2^24 (tcgen05 kind::mxf4)"}.get(kernel_used, "f64 FMA"),
         "data": "synthetic (seeded Balding-Nichols style, generated in HBM)",
-        "config": {"workload": WORKLOAD if (N, M, P, G, a.missing_rate) == (N_SAMPLES, N_VARIANTS, N_PHENO, 1, 0.0)
-                   else f"NON-HEADLINE {N} samples x {M} variants, P={P}, groups={G}, missing={a.missing_rate}",
-                   "samples": N, "variants_per_gpu": M, "phenotypes": P, "covariates": K, "missing_rate": a.missing_rate, "groups": G,
-                   "kernel": kernel_used, "parallelism": f"variant-sharded x{world}",
-                   "l2": "inputs larger than L2 (packed genotypes %.1f GB per GPU)" % (gt.nbytes / 1e9)},
-        "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+        "config": config_of(a, N, a.variants if a.strong else M, P, K, G, world), "kernel": kernel_used,
+        "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "ranks": per_rank,
+        "recomputed_rows_last_step": int(recomputed),
+        "multi_gpu": None if world == 1 else {"gather": gather_mode, "broadcast_per_step": not a.no_broadcast,
+                                              "gather_per_step": not a.no_gather, "row_bytes_per_rank": chunk * width * G * 8},
     }
 
     # ---- e2e: public API, host buffers, H2D + ingest + sweep + D2H inside the timed region -----------
-    if not a.no_e2e:
+    if not a.no_e2e and not a.strong:
         Me = min(a.e2e_variants, M)
         bed_stride = (N + 3) // 4
+        stream = main.cuda_stream
         d_bed = torch.empty((Me, bed_stride), dtype=torch.uint8, device=dev)
         ctx.check(lib.lrr_unpack_bed(ctx.handle, gt.data.data_ptr(), gt.stride, Me, N, d_bed.data_ptr(), bed_stride, stream))
         h_bed = torch.empty((Me, bed_stride), dtype=torch.uint8, pin_memory=True)
@@ -329,6 +375,19 @@ def run_ours(a):
 
         for _ in range(2):   # first calls allocate the device arena / page-locked result buffer and load kernels
             e2e_step()
+        # the H2D leg alone (the same bytes, one cudaMemcpyAsync per 256 MB block): what the host link gives this process
+        d_probe = torch.empty((min(Me, 4096), bed_stride), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)
+        t_h = time.time()
+        for lo in range(0, Me, d_probe.shape[0]):
+            d_probe[: min(d_probe.shape[0], Me - lo)].copy_(h_bed[lo:lo + d_probe.shape[0]], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        h2d_alone = Me * bed_stride / (time.time() - t_h) / 1e9
+        del d_probe
+        # the host prologue alone (complete samples + covariate QR; overlapped with the first copies inside the call)
+        t_p = time.time()
+        GroupBasis(y[:, :1], cov, np.arange(N))
+        prologue_s = time.time() - t_p
         barrier()
         reps = 5
         times = []
@@ -346,16 +405,22 @@ def run_ours(a):
         dt = float(np.median(times))
         dt_mean = float(np.mean(times))
         d2h = Me * (4 + 4 + 8 + 5 * 8 * P)
+        h2d = int(Me * bed_stride + 8 * n_kept * (K + P))
+        device_s = Me / M * ms_per_step / 1e3
+        stages = {"h2d_at_link_rate_s": round(Me * bed_stride / (h2d_alone * 1e9), 4), "host_prologue_s": round(prologue_s, 4),
+                  "device_sweep_s": round(device_s, 4)}
         result["e2e"] = {"value": world * Me * float(n_kept) / dt, "unit": "genotypes/s", "reps": reps,
                          "mean_value": world * Me * float(n_kept) / dt_mean, "rep_seconds": [round(t, 4) for t in times],
-                         "h2d_bytes_per_step": int(Me * bed_stride + 8 * n_kept * (K + P)), "d2h_bytes_per_step": int(d2h),
+                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+                         "h2d_gbps_achieved": round(h2d / dt / 1e9, 2), "h2d_gbps_link_alone": round(h2d_alone, 2),
+                         "stage_seconds": stages, "slowest_stage": max(stages, key=stages.get),
                          "sample": f"{Me} variants x {N} samples per GPU per step: page-locked host .bed bytes -> "
                                    "HostBedGenotypes -> linear_regression_rows (block-streamed H2D overlapped with the "
                                    "host QR prologue and the sweep; result rows D2H to numpy), PCIe-bound"}
         del h_bed
 
     # ---- CPU baseline: the oracle's C restatement of the reference loop, rank 0, bounded sample -------
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and not a.strong:
         result["cpu_baseline"] = cpu_baseline(a, gt, y, cov, ctx, dev)
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
@@ -427,8 +492,7 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "genotypes/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (same seeded generator, CPU mirror)",
-        "config": {"workload": WORKLOAD if (N, a.variants) == (N_SAMPLES, N_VARIANTS) else f"REDUCED {N} samples x {a.variants} variants",
-                   "samples": N, "phenotypes": N_PHENO, "covariates": N_COV, "missing_rate": a.missing_rate},
+        "config": config_of(a, N, a.variants, N_PHENO, N_COV, 1, max(a.gpus, 1)), "kernel": "reference (C restatement, OpenMP)",
         "cpu_baseline": {"value": value, "unit": "genotypes/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "genotypes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

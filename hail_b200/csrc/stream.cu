@@ -167,8 +167,17 @@ int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64
   if (block_variants <= 0) block_variants = std::max<int64_t>(128, (256ll << 20) / bed_stride / 128 * 128);
   s->block = std::max<int64_t>(1, std::min<int64_t>(block_variants, std::max<int64_t>(n_variants, 1)));
   s->n_blocks = (n_variants + s->block - 1) / s->block;
-  // default depth: up to 16 GB of packed rows in flight (covers the host prologue at PCIe rate), at least 3 slots
-  if (depth <= 0) depth = (int)std::max<int64_t>(3, (16ll << 30) / (s->block * s->stride));
+  // default depth: up to 16 GB of packed rows in flight (covers the host prologue at PCIe rate) but never more than
+  // half of what the device has free (the cached arena counts as free: it is reused), at least 3 slots
+  if (depth <= 0) {
+    size_t free_b = 0, total_b = 0;
+    int64_t budget = 16ll << 30;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+      budget = std::min<int64_t>(budget, (int64_t)((free_b + c->arena_bytes) / 2));
+    else
+      cudaGetLastError();
+    depth = (int)std::max<int64_t>(3, budget / (s->block * s->stride));
+  }
   s->depth = (int)std::max<int64_t>(1, std::min<int64_t>(depth, std::max<int64_t>(s->n_blocks, 1)));
   auto bail = [&](int code) {
     destroy(s);
@@ -256,17 +265,19 @@ int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs
     if (rb.used && (e = cudaStreamWaitEvent(s->s_comp, rb.copied, 0)) != cudaSuccess) { rc = cuda_fail(c, e, "wait copied"); break; }
     rc = run_rows(c, s->d_packed[slot], s->d_flags[slot], rows, s->stride, s->N, rb.outs.data(), n_outs, kernel, s->s_comp);
     if (rc != LRR_OK) break;
-    cudaEventRecord(s->swept[slot], s->s_comp);
+#define STEP(call) if ((e = (call)) != cudaSuccess) { rc = cuda_fail(c, e, #call); break; }
+    STEP(cudaEventRecord(s->swept[slot], s->s_comp));
     s->slot_swept_valid[slot] = 1;
-    cudaEventRecord(rb.ready, s->s_comp);
-    cudaStreamWaitEvent(s->s_d2h, rb.ready, 0);
+    STEP(cudaEventRecord(rb.ready, s->s_comp));
+    STEP(cudaStreamWaitEvent(s->s_d2h, rb.ready, 0));
     for (size_t g = 0; g < c->groups.size(); ++g) {
       const int P = c->groups[g].P;
       const lrr_group_out& d = rb.outs[g];
       const lrr_group_out& h = h_outs[g];
       auto copy = [&](void* dst, const void* src, size_t elem, int64_t per_row) {
-        if (dst) cudaMemcpyAsync(static_cast<char*>(dst) + (size_t)row0 * per_row * elem, src, (size_t)rows * per_row * elem,
-                                 cudaMemcpyDeviceToHost, s->s_d2h);
+        if (!dst || e != cudaSuccess) return;   // the first failed enqueue is kept in `e` and reported below
+        e = cudaMemcpyAsync(static_cast<char*>(dst) + (size_t)row0 * per_row * elem, src, (size_t)rows * per_row * elem,
+                            cudaMemcpyDeviceToHost, s->s_d2h);
       };
       copy(h.n, d.n, sizeof(int32_t), 1);
       copy(h.n_missing, d.n_missing, sizeof(int32_t), 1);
@@ -278,7 +289,9 @@ int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs
       copy(h.p_value, d.p_value, sizeof(double), P);
       copy(h.log10_p, d.log10_p, sizeof(double), P);
     }
-    cudaEventRecord(rb.copied, s->s_d2h);
+    if (e != cudaSuccess) { rc = cuda_fail(c, e, "cudaMemcpyAsync(result rows, device -> host)"); break; }
+    STEP(cudaEventRecord(rb.copied, s->s_d2h));
+#undef STEP
     rb.used = true;
     if (s->next_load < s->n_blocks) {
       rc = issue_load(s, s->next_load);
@@ -291,6 +304,22 @@ int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs
   if (rc == LRR_OK && e != cudaSuccess) rc = cuda_fail(c, e, "cudaStreamSynchronize(d2h)");
   if (rc == LRR_OK && e2 != cudaSuccess) rc = cuda_fail(c, e2, "cudaStreamSynchronize(comp)");
   return rc;
+}
+LRR_ABI_CATCH(ctx)
+
+int lrr_trim(lrr_ctx* ctx) try {
+  if (!ctx) return LRR_EINVAL;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (c->streams_alive) return fail(c, LRR_ESTATE, "lrr_trim: a stream of this context is still open");
+  DeviceGuard guard(c->device);
+  LRR_CUDA(c, cudaDeviceSynchronize());
+  cudaFree(c->arena);
+  c->arena = nullptr;
+  c->arena_bytes = 0;
+  cudaFree(c->d_nanmask);
+  c->d_nanmask = nullptr;
+  c->nanmask_bytes = 0;
+  return LRR_OK;
 }
 LRR_ABI_CATCH(ctx)
 

@@ -33,6 +33,9 @@ class BasisTensors:
 
     @classmethod
     def from_group_basis(cls, b, device):
+        if getattr(b, "weighted", False):
+            # a weighted group also carries sqrt(w) and must reach lrr_add_group_weighted: not part of this message
+            raise NotImplementedError("BasisTensors: weighted groups (weights=) are not broadcast; run them on one device")
         t = [torch.from_numpy(np.ascontiguousarray(getattr(b, f))).to(device) for f in BASIS_FIELDS]
         return cls((b.n, b.K, b.P, int(b.has_intercept)), t)
 
@@ -41,36 +44,143 @@ class BasisTensors:
         return self.n - self.K - 1
 
 
-def broadcast_bases(bases, device, src=0):
-    """Rank `src` passes its list of GroupBasis (others pass None); every rank returns the list of BasisTensors."""
-    rank = dist.get_rank() if dist.is_initialized() else 0
-    world = dist.get_world_size() if dist.is_initialized() else 1
+MAX_GROUPS_MSG = 63   # groups one broadcast header can describe
+
+
+def _basis_shapes(n, K, P, hi):
+    """(dtype, shape) of BASIS_FIELDS for a group with these counts."""
+    return [(torch.int32, (n,)), (torch.float64, (K - hi, n)), (torch.float64, (P, n)), (torch.float64, (K, P)),
+            (torch.float64, (P,))]
+
+
+def broadcast_bases(bases, device, src=0, group=None, message=None):
+    """Rank `src` passes its list of GroupBasis (others pass None); every rank returns the list of BasisTensors.
+
+    What `sc.broadcast` ships per call (LR:74-78, LR:257) travels as ONE flat message: a fixed-size header (group count and
+    the four counts of every group) and one byte payload holding every array of every group; the receivers' tensors
+    are views into that payload."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return [BasisTensors.from_group_basis(b, device) for b in bases]
-    count = torch.tensor([len(bases) if rank == src else 0], dtype=torch.int64, device=device)
-    dist.broadcast(count, src)
+    header = torch.zeros(1 + 4 * MAX_GROUPS_MSG, dtype=torch.int64, device=device)
+    mine = None
+    if rank == src:
+        if len(bases) > MAX_GROUPS_MSG:
+            raise ValueError(f"broadcast_bases: at most {MAX_GROUPS_MSG} groups per call")
+        mine = [BasisTensors.from_group_basis(b, device) for b in bases]
+        header[0] = len(mine)
+        for g, bt in enumerate(mine):
+            header[1 + 4 * g: 5 + 4 * g] = torch.tensor([bt.n, bt.K, bt.P, bt.has_intercept], dtype=torch.int64)
+    dist.broadcast(header, src, group=group)
+    h = header.tolist()
+    metas = [tuple(int(v) for v in h[1 + 4 * g: 5 + 4 * g]) for g in range(int(h[0]))]
+    layout, total = [], 0
+    for meta in metas:
+        offs = []
+        for dt, shape in _basis_shapes(*meta):
+            nbytes = int(np.prod(shape)) * (4 if dt == torch.int32 else 8)
+            offs.append((total, nbytes, dt, shape))
+            total += (nbytes + 7) // 8 * 8
+        layout.append(offs)
+    payload = torch.zeros(max(total, 8), dtype=torch.uint8, device=device)
+    if rank == src:
+        for bt, offs in zip(mine, layout):
+            for t, (off, nbytes, _, _) in zip(bt.tensors, offs):
+                if nbytes:
+                    payload[off:off + nbytes] = t.contiguous().view(torch.uint8).reshape(-1)
+    dist.broadcast(payload, src, group=group)
     out = []
-    for g in range(int(count.item())):
-        if rank == src:
-            bt = BasisTensors.from_group_basis(bases[g], device)
-            meta = torch.tensor([bt.n, bt.K, bt.P, bt.has_intercept], dtype=torch.int64, device=device)
-        else:
-            meta = torch.zeros(4, dtype=torch.int64, device=device)
-        dist.broadcast(meta, src)
-        n, K, P, hi = (int(v) for v in meta.tolist())
-        if rank != src:
-            bt = BasisTensors((n, K, P, hi), [
-                torch.empty(n, dtype=torch.int32, device=device),
-                torch.empty((K - hi, n), dtype=torch.float64, device=device),
-                torch.empty((P, n), dtype=torch.float64, device=device),
-                torch.empty((K, P), dtype=torch.float64, device=device),
-                torch.empty(P, dtype=torch.float64, device=device),
-            ])
-        for x in bt.tensors:
-            if x.numel():
-                dist.broadcast(x, src)
-        out.append(bt)
+    for meta, offs in zip(metas, layout):
+        ts = [payload[off:off + nbytes].view(dt).reshape(shape) for off, nbytes, dt, shape in offs]
+        out.append(BasisTensors(meta, ts))
+    if message is not None:
+        message.extend([header, payload])
     return out
+
+
+class ShardedRegression:
+    """`linear_regression_rows` over variant shards: one process per GPU, rank r holds a contiguous range of the
+    variants (LinearRegression.scala:95 / :274: one task per partition).  Per call: ONE basis broadcast from rank 0
+    (LR:74-78 / :257), the sweep of the local rows with no collective inside, and -- only on request -- an all-gather of
+    the fixed-width result rows in rank order (= row order).  Results are bit-identical to the single-device run: every
+    row's arithmetic is independent of where the row sits."""
+
+    FIELDS = ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value")
+
+    def __init__(self, genotypes, group=None):
+        from . import _lib
+        self.g = genotypes
+        self.dev = genotypes.device
+        self.ctx = _lib.context(self.dev.index)
+        self.group = group
+        self.bts = None
+
+    def set_bases(self, bases, src=0):
+        """Collective.  Rank `src` passes the list of GroupBasis (the driver prologue ran there), the others None."""
+        ctx, N = self.ctx, self.g.n_samples
+        self._message, self._src = [], src
+        self.bts = broadcast_bases(bases, self.dev, src, self.group, message=self._message)
+        with torch.cuda.device(self.dev):
+            ctx.check(ctx.lib.lrr_clear_groups(ctx.handle))
+            for b in self.bts:
+                t = b.tensors
+                ctx.check(ctx.lib.lrr_add_group(ctx.handle, N, b.n, b.K, b.P, b.has_intercept, t[0].data_ptr(),
+                                                t[1].data_ptr() if t[1].numel() else None, t[2].data_ptr(),
+                                                t[3].data_ptr() if t[3].numel() else None, t[4].data_ptr()))
+            ctx.check(ctx.lib.lrr_reserve(ctx.handle, self.g.n_variants))
+        return self.bts
+
+    def rebroadcast(self):
+        """The per-call message once more (header + payload, asynchronous on the current stream): what a repeated call
+        with the same phenotypes costs on the wire (bench.py)."""
+        for t in self._message:
+            dist.broadcast(t, self._src, group=self.group)
+
+    def alloc_outputs(self, want_log10_p=False):
+        from . import _lib
+        M, dev = self.g.n_variants, self.dev
+        outs, arr = [], (_lib.GroupOut * len(self.bts))()
+        for g, b in enumerate(self.bts):
+            o = {"n": torch.empty(M, dtype=torch.int32, device=dev), "n_missing": torch.empty(M, dtype=torch.int32, device=dev),
+                 "sum_x": torch.empty(M, dtype=torch.float64, device=dev)}
+            for f in self.FIELDS + (("log10_p",) if want_log10_p else ()):
+                o[f] = torch.empty((M, b.P), dtype=torch.float64, device=dev)
+            for k, v in o.items():
+                setattr(arr[g], k, v.data_ptr())
+            if not want_log10_p:
+                arr[g].log10_p = None
+            outs.append(o)
+        return outs, arr
+
+    def run(self, kernel="auto", outs=None, arr=None, want_log10_p=False):
+        """The local sweep + statistics (asynchronous on torch's current stream).  Returns the per-group output dicts."""
+        from . import _lib
+        if outs is None:
+            outs, arr = self.alloc_outputs(want_log10_p)
+        g, ctx = self.g, self.ctx
+        with torch.cuda.device(self.dev):
+            ctx.check(ctx.lib.lrr_run(ctx.handle, g.data.data_ptr(), g.flags_ptr(), g.n_variants, g.stride, g.n_samples, arr,
+                                      len(self.bts), _lib.KERNELS[kernel], torch.cuda.current_stream(self.dev).cuda_stream))
+        return outs
+
+    @staticmethod
+    def pack_rows(o, out=None):
+        """One group's result fields as fixed-width float64 rows [M, 3 + 5 P] (n, n_missing, sum_x, then the P-wide fields)."""
+        cols = [o["n"].to(torch.float64)[:, None], o["n_missing"].to(torch.float64)[:, None], o["sum_x"][:, None]]
+        cols += [o[f] for f in ShardedRegression.FIELDS]
+        return torch.cat(cols, dim=1, out=out)
+
+    @staticmethod
+    def unpack_rows(rows, P):
+        o = {"n": rows[:, 0].to(torch.int32), "n_missing": rows[:, 1].to(torch.int32), "sum_x": rows[:, 2].contiguous()}
+        for i, f in enumerate(ShardedRegression.FIELDS):
+            o[f] = rows[:, 3 + i * P: 3 + (i + 1) * P].contiguous()
+        return o
+
+    def gather(self, outs):
+        """All ranks' rows of every group, concatenated in rank order (collective)."""
+        return [self.unpack_rows(gather_rows(self.pack_rows(o), group=self.group), b.P) for o, b in zip(outs, self.bts)]
 
 
 def gather_rows(local_rows: torch.Tensor, counts=None, out=None, group=None):
@@ -78,9 +188,9 @@ def gather_rows(local_rows: torch.Tensor, counts=None, out=None, group=None):
 
     Equal blocks (the sharded sweep's normal case) go straight into one [world * m, W] tensor (`out`, allocated when
     None) with all_gather_into_tensor: no per-rank temporaries, no concatenation pass."""
-    if not dist.is_initialized() or dist.get_world_size() == 1:
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local_rows
-    world = dist.get_world_size()
+    world = dist.get_world_size(group)
     dev = local_rows.device
     if counts is not None and len(set(counts)) == 1 and counts[0] == local_rows.shape[0]:
         if out is None:
@@ -90,7 +200,7 @@ def gather_rows(local_rows: torch.Tensor, counts=None, out=None, group=None):
     if counts is None:
         c = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=dev)
         cs = [torch.zeros_like(c) for _ in range(world)]
-        dist.all_gather(cs, c)
+        dist.all_gather(cs, c, group=group)
         counts = [int(x.item()) for x in cs]
     width = local_rows.shape[1]
     mmax = max(counts)
@@ -99,5 +209,54 @@ def gather_rows(local_rows: torch.Tensor, counts=None, out=None, group=None):
         padded = torch.zeros((mmax, width), dtype=local_rows.dtype, device=dev)
         padded[: local_rows.shape[0]] = local_rows
     parts = [torch.empty((mmax, width), dtype=local_rows.dtype, device=dev) for _ in range(world)]
-    dist.all_gather(parts, padded.contiguous())
+    dist.all_gather(parts, padded.contiguous(), group=group)
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+class RowGather:
+    """All-gather of fixed-width result rows [m, W] float64 (same m on every rank) into [world * m, W], rank order.
+
+    `peer` mode: the output buffers live in symmetric memory (torch.distributed._symmetric_memory: every rank maps every
+    peer's buffer over NVLink); a rank PUSHES its rows into its slot of every peer's buffer with plain device-to-device
+    copies -- they run on the copy engines, so the gather takes no SM from a persistent sweep kernel running next to it
+    (an NCCL all-gather's CTAs do: +0.8 ms on the 8-GPU step of round 1) -- and a symmetric-memory barrier publishes
+    them.  `nccl` mode: all_gather_into_tensor on the caller's stream (own communicator).  `auto` tries peer first."""
+
+    def __init__(self, m, width, device, n_buffers=2, mode="auto", group=None):
+        self.m, self.width, self.dev = int(m), int(width), device
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.mode = None
+        self.why = None
+        if mode in ("auto", "peer"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                pg = group if group is not None else dist.group.WORLD
+                self.bufs, self.hdls, self.peers = [], [], []
+                for _ in range(n_buffers):
+                    t = symm.empty((self.world * self.m, self.width), dtype=torch.float64, device=device)
+                    h = symm.rendezvous(t, pg.group_name if hasattr(pg, "group_name") else pg)
+                    self.bufs.append(t)
+                    self.hdls.append(h)
+                    self.peers.append([h.get_buffer(r, t.shape, t.dtype) for r in range(self.world)])
+                self.mode = "peer (copy engines over symmetric memory)"
+            except Exception as e:   # symmetric memory unavailable on this box / build
+                self.why = f"{type(e).__name__}: {e}"
+                if mode == "peer":
+                    raise
+        if self.mode is None:
+            self.pg = dist.new_group(list(range(self.world))) if group is None else group
+            self.bufs = [torch.empty((self.world * self.m, self.width), dtype=torch.float64, device=device) for _ in range(n_buffers)]
+            self.mode = "nccl all_gather_into_tensor" + (f" (peer mode unavailable: {self.why})" if self.why else "")
+
+    def gather(self, rows, b=0):
+        """Asynchronous on the current stream; returns buffer b holding every rank's rows once the stream reaches here."""
+        if self.mode.startswith("peer"):
+            lo, hi = self.rank * self.m, (self.rank + 1) * self.m
+            self.hdls[b].barrier(channel=0)          # every peer is done reading buffer b from its previous use
+            for r in range(self.world):
+                self.peers[b][(self.rank + r) % self.world][lo:hi].copy_(rows, non_blocking=True)
+            self.hdls[b].barrier(channel=1)          # every push has landed everywhere
+        else:
+            dist.all_gather_into_tensor(self.bufs[b], rows.contiguous(), group=self.pg)
+        return self.bufs[b]

@@ -167,6 +167,9 @@ def import_plink(bed, bim, fam, n_partitions=None, block_size=None, min_partitio
     if not a2_reference:
         import torch
         host.rows.copy_(torch.from_numpy(_SWAP_HOM[host.rows.numpy()]))
+        pad = (-n_samples) % 4     # the pad calls of the last byte of a row are 00 in the file and must stay 00
+        if pad:
+            host.rows[:, -1] &= 0xFF >> (2 * pad)
     if resident:
         gt = host.to_device()
         if not identity:
@@ -286,8 +289,9 @@ def _bed_rows_of(mt: MatrixTable) -> np.ndarray:
         stride = (n_cols + 3) // 4
         out = torch.empty((g.n_variants, stride), dtype=torch.uint8, device=g.device)
         with torch.cuda.device(g.device):
+            # on torch's current stream: `g.data` was packed there, and .cpu() below synchronises with it
             ctx.check(ctx.lib.lrr_unpack_bed(ctx.handle, g.data.data_ptr(), g.stride, g.n_variants, g.n_samples,
-                                             out.data_ptr(), stride, None))
+                                             out.data_ptr(), stride, torch.cuda.current_stream(g.device).cuda_stream))
         return out.cpu().numpy()
     # filtered columns: re-encode the kept samples on the host (export is not on the hot path)
     dos = g.to_dosage()[:, mt.col_index]

@@ -283,6 +283,44 @@ class Table:
                 cols[k] = [_row_value(v, i) for i in range(self.n_rows)]
         return pd.DataFrame(cols)
 
+    def gather(self):
+        """For the Table of a `_sharded=True` call: every rank's rows concatenated in rank order (= the row order of
+        the unsharded dataset) on every rank.  Collective over the default torch.distributed group; numeric fields
+        travel as tensors (NCCL on GPUs), row keys / pass-through fields as pickled objects."""
+        import torch
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return self
+        backend = dist.get_backend()
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        counts = [None] * dist.get_world_size()
+        dist.all_gather_object(counts, int(self.n_rows))
+
+        def cat_array(v):
+            a = np.asarray(v)
+            if a.dtype.kind in "fiub":
+                t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+                flat = t.reshape(a.shape[0], -1)
+                from .dist import gather_rows
+                out = gather_rows(flat, counts=counts)
+                return out.cpu().numpy().reshape((sum(counts),) + a.shape[1:])
+            parts = [None] * len(counts)
+            dist.all_gather_object(parts, a)
+            return np.concatenate(parts, axis=0)
+
+        def cat(v):
+            if isinstance(v, ChainedField):
+                return ChainedField(cat(g) for g in v)
+            if isinstance(v, dict):
+                return {k: cat(x) for k, x in v.items()}
+            return cat_array(v)
+
+        t = Table(OrderedDict((k, cat(v)) for k, v in self._fields.items()), self.key, sum(counts))
+        if hasattr(self, "n_missing"):
+            t.n_missing = [cat_array(g) for g in self.n_missing] if isinstance(self.n_missing, list) else cat_array(self.n_missing)
+        return t
+
     def _same(self, other, tolerance=1e-6):
         """Table._same (hail/python/hail/table.py:4384): same fields, floats equal within the D_== comparator."""
         if list(self._fields) != list(other._fields) or self.n_rows != other.n_rows:

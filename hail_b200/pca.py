@@ -108,7 +108,7 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
 
     with torch.cuda.device(dev):
         # ---- hwe_normalize (pca.py:15-33): counts from one sweep against a constant column ----
-        o = _run_device(g, [_sweep_basis(idx, np.ones((1, n)))])[0]
+        o = _run_device(g, [_sweep_basis(idx, np.ones((1, n)))], guard=False)[0]
         n_called = (n - o["n_missing"]).to(torch.float64)
         mean = o["sum_x"] / float(n)                  # the mean-imputed column sums to n * mean
         keep = (mean > 0.0) & (mean < 2.0) & (n_called > 0)
@@ -126,7 +126,7 @@ def hwe_normalized_pca(call_expr, k=10, compute_loadings=False, *, _oversample=8
         n_splits = int(max(1, min(64, -(-8 * 148 // strips), M // 32 or 1)))
 
         def a_times(V):            # [n, L] -> [M, L]
-            ytx = _run_device(g, [_sweep_basis(idx, V.t().contiguous())])[0]["y_transpose_x"]
+            ytx = _run_device(g, [_sweep_basis(idx, V.t().contiguous())], guard=False)[0]["y_transpose_x"]
             T = (ytx - mean[:, None] * V.sum(dim=0)[None, :]) * inv_sd[:, None]
             return torch.where(keep[:, None], T, torch.zeros_like(T))
 

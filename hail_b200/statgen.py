@@ -222,12 +222,16 @@ def orthonormal_basis(c):
     return np.column_stack([one, rest]), True
 
 
-def _run_device(genotypes, bases, kernel="auto", want_log10_p=False, chunk_variants=None):
-    """Push the group bases and sweep all rows.  Returns per-group dicts of torch CUDA tensors."""
+def _run_device(genotypes, bases, kernel="auto", want_log10_p=False, chunk_variants=None, guard=True):
+    """Push the group bases and sweep all rows.  Returns per-group dicts of torch CUDA tensors.
+
+    `guard=False` switches the tolerance guard of the quantised sweeps off for this call (the PCA's power iteration
+    only consumes y_transpose_x and corrects itself; include/lrr_b200.h lrr_set_guard)."""
     dev = genotypes.device
     ctx = _lib.context(dev.index)
     M, N = genotypes.n_variants, genotypes.n_samples
     with torch.cuda.device(dev):
+        ctx.check(ctx.lib.lrr_set_guard(ctx.handle, 1 if guard else 0))
         _push_groups(ctx, N, bases)
         outs = []
         for b in bases:
@@ -257,6 +261,8 @@ def _run_device(genotypes, bases, kernel="auto", want_log10_p=False, chunk_varia
                 arr[g].log10_p = o["log10_p"][lo:hi].data_ptr() if want_log10_p else None
             ctx.check(ctx.lib.lrr_run(ctx.handle, genotypes.data[lo:hi].data_ptr(), genotypes.flags_ptr(lo), hi - lo,
                                       genotypes.stride, N, arr, len(bases), kid, stream))
+        if not guard:
+            ctx.check(ctx.lib.lrr_set_guard(ctx.handle, 1))
     return outs
 
 
@@ -356,7 +362,8 @@ def _run_device_dense(dosage, bases):
 
 
 def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, weights=None,
-                           _kernel="auto", _log10_p=False, _stream_block=0, _stream_depth=0) -> Table:
+                           _kernel="auto", _log10_p=False, _stream_block=0, _stream_depth=0, _guard=True,
+                           _sharded=False) -> Table:
     """For each row, test an input variable for association with response variables using linear regression.
 
     Drop-in for `hl.linear_regression_rows` (statgen.py:235): same arguments, same validation, same output
@@ -365,6 +372,12 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
     a list of lists).  `block_size` is accepted and numerically inert on the GPU.  `weights` (one expression, or one
     per group of a chained `y`): weighted least squares as the reference's `_linear_regression_rows_nd` does it
     (statgen.py:557-581, 636-660): samples without a weight are dropped, x is mean-imputed and then scaled by sqrt(w).
+
+    `_sharded=True` (one process per GPU, torch.distributed initialised): every rank passes a MatrixTable holding its own
+    contiguous range of the ROWS (variants) over the same columns -- the reference's one task per partition (LR:95,
+    :274).  Rank 0 runs the driver prologue and its bases are broadcast once per call (LR:74-78, :257); every rank
+    sweeps its rows and returns the Table of ITS rows (bit-identical to the same rows of a single-device run);
+    `Table.gather()` concatenates all ranks' rows in rank order on every rank.
     """
     if not isinstance(block_size, int):
         raise TypeError("linear_regression_rows: 'block_size' must be int")
@@ -420,10 +433,23 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
             host = stream.run(bases, kernel=_kernel, want_log10_p=_log10_p)
         finally:
             stream.close()
+    elif _sharded:
+        import torch.distributed as tdist
+
+        from .dist import ShardedRegression
+        if weights is not None:
+            raise NotImplementedError("linear_regression_rows: weights= with _sharded=True")
+        sr = ShardedRegression(mt.genotypes)
+        bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None)
+                 for i, g in enumerate(y_vals)] if tdist.get_rank() == 0 else None
+        sr.set_bases(bases)
+        outs = sr.run(kernel=_kernel, want_log10_p=_log10_p)
+        torch.cuda.synchronize(mt.genotypes.device)
+        host = [{k: v.cpu().numpy() for k, v in o.items()} for o in outs]
     else:
         bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None, w_vals[i])
                  for i, g in enumerate(y_vals)]
-        outs = _run_device(mt.genotypes, bases, kernel=_kernel, want_log10_p=_log10_p)
+        outs = _run_device(mt.genotypes, bases, kernel=_kernel, want_log10_p=_log10_p, guard=_guard)
         torch.cuda.synchronize(mt.genotypes.device)
         host = [{k: v.cpu().numpy() for k, v in o.items()} for o in outs]
 
@@ -447,6 +473,7 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
             fields[f] = h[f] if y_is_list else h[f][:, 0]  # SG:404-406
     t = Table(fields, key=mt.row_key, n_rows=mt.count_rows())
     t.n_missing = [h["n_missing"] for h in host] if is_chained else host[0]["n_missing"]
+    t.sharded = bool(_sharded)
     return t
 
 

@@ -50,6 +50,17 @@ def _worker(rank, world, port, tmp):
         # (the stand-in oracle blocks rows by 16, so shard boundaries move its BLAS block shapes: last-bit differences)
         assert np.allclose(allrows, want, rtol=1e-10, atol=1e-13, equal_nan=True)
         assert np.array_equal(allrows[:, 0], want[:, 0], equal_nan=True)  # sum_x: exact, order preserved
+        # Table.gather(): the sharded call's per-rank Tables concatenated in rank order (numeric fields as tensors,
+        # object-valued row keys pickled)
+        import hail_b200 as hb
+        from collections import OrderedDict
+        keys = np.array([("1", i + 1) for i in range(M)] + [None], dtype=object)[:-1]
+        local = hb.Table(OrderedDict(locus=keys[lo:hi], n=np.full(hi - lo, 7, dtype=np.int32), sum_x=part["sum_x"],
+                                     beta=part["beta"]), key=("locus",), n_rows=hi - lo)
+        local.n_missing = np.arange(lo, hi, dtype=np.int32)
+        full = local.gather()
+        assert full.n_rows == M and list(full.locus) == list(keys) and np.array_equal(full.n_missing, np.arange(M))
+        assert np.array_equal(full.sum_x, allrows[:, 0], equal_nan=True) and full.beta.shape == (M, 2)
         covered = [hd.variant_range(r, world, M) for r in range(world)]
         assert covered[0][0] == 0 and covered[-1][1] == M and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
         # the one path with a real exchange step: variant-sharded PCA all-reduces A' (A V) and the Gram matrices
