@@ -44,6 +44,17 @@ void free_group(Group& g) {
   g = Group();
 }
 
+// a retired group keeps its four input buffers for the next lrr_add_group (everything derived from them goes)
+void retire_group(Ctx* c, Group& g) {
+  if (g.d_bq) cudaFree(g.d_bq);
+  if (g.d_colscale) cudaFree(g.d_colscale);
+  if (g.d_basis_t) cudaFree(g.d_basis_t);
+  g.d_bq = nullptr;
+  g.d_colscale = nullptr;
+  g.d_basis_t = nullptr;
+  if (c->spare.size() < 8) c->spare.push_back(g); else free_group(g);
+}
+
 void free_workspace(Ctx* c) {
   cudaFree(c->d_counts);
   cudaFree(c->d_dots);
@@ -55,6 +66,7 @@ void free_workspace(Ctx* c) {
   c->d_flag_mark = c->d_flag_list = c->d_flag_count = nullptr;
   c->flag_pending = false;
   c->reserved_variants = 0;
+  c->ws_groups = c->ws_cols = 0;
   c->dots_offset.clear();
 }
 
@@ -71,33 +83,63 @@ __global__ void scatter_basis_kernel(const double* __restrict__ cols, int C, int
   }
 }
 
+// grow-only: [G][rows] counts / flag arrays and [sum_g (C_g + 2)][rows] dot products
 int ensure_workspace(Ctx* c, int64_t M) {
-  if (M <= c->reserved_variants && c->dots_offset.size() == c->groups.size()) return LRR_OK;
-  const int64_t want = M > c->reserved_variants ? M : c->reserved_variants;
-  free_workspace(c);
-  const size_t G = c->groups.size();
+  const int64_t G = (int64_t)c->groups.size();
   int64_t total_c = 0;
-  c->dots_offset.resize(G);
-  for (size_t g = 0; g < G; ++g) {
-    c->dots_offset[g] = total_c * want;
-    total_c += c->groups[g].C + 2;   // + 2: column sum and centred squares of the dense-dosage sweep
+  for (const Group& g : c->groups) total_c += g.C + 2;   // + 2: fitted-value dots (tc4) / column sum and squares (dense)
+  if (M > c->reserved_variants || G > c->ws_groups || total_c > c->ws_cols) {
+    const int64_t rows = std::max<int64_t>(M, c->reserved_variants);
+    const int64_t groups = std::max<int64_t>(std::max<int64_t>(G, c->ws_groups), 1);
+    const int64_t cols = std::max<int64_t>(std::max<int64_t>(total_c, c->ws_cols), 1);
+    LRR_CUDA(c, cudaDeviceSynchronize());   // (growing only: a run may still be using the old buffers)
+    free_workspace(c);
+    LRR_CUDA(c, cudaMalloc(&c->d_counts, sizeof(int32_t) * 4 * (size_t)rows * (size_t)groups));
+    LRR_CUDA(c, cudaMalloc(&c->d_dots, sizeof(double) * (size_t)rows * (size_t)cols));
+    LRR_CUDA(c, cudaMalloc(&c->d_flag_mark, sizeof(int32_t) * (size_t)rows * (size_t)groups));
+    LRR_CUDA(c, cudaMalloc(&c->d_flag_list, sizeof(int32_t) * (size_t)rows * (size_t)groups));
+    LRR_CUDA(c, cudaMalloc(&c->d_flag_count, sizeof(int32_t) * (size_t)groups));
+    if ((int)groups > c->h_flag_groups) {
+      if (c->h_flag_count) cudaFreeHost(c->h_flag_count);
+      c->h_flag_count = nullptr;
+      c->h_flag_groups = 0;
+      LRR_CUDA(c, cudaMallocHost(&c->h_flag_count, sizeof(int32_t) * (size_t)groups));
+      c->h_flag_groups = (int)groups;
+    }
+    if (!c->flag_ev) LRR_CUDA(c, cudaEventCreateWithFlags(&c->flag_ev, cudaEventDisableTiming));
+    c->reserved_variants = rows;
+    c->ws_groups = groups;
+    c->ws_cols = cols;
   }
-  LRR_CUDA(c, cudaMalloc(&c->d_counts, sizeof(int32_t) * 4 * (size_t)want * (G ? G : 1)));
-  LRR_CUDA(c, cudaMalloc(&c->d_dots, sizeof(double) * (size_t)want * (size_t)(total_c ? total_c : 1)));
-  LRR_CUDA(c, cudaMalloc(&c->d_flag_mark, sizeof(int32_t) * (size_t)want * (G ? G : 1)));
-  LRR_CUDA(c, cudaMalloc(&c->d_flag_list, sizeof(int32_t) * (size_t)want * (G ? G : 1)));
-  LRR_CUDA(c, cudaMalloc(&c->d_flag_count, sizeof(int32_t) * (G ? G : 1)));
-  if ((int)G > c->h_flag_groups) {
-    if (c->h_flag_count) cudaFreeHost(c->h_flag_count);
-    c->h_flag_count = nullptr;
-    LRR_CUDA(c, cudaMallocHost(&c->h_flag_count, sizeof(int32_t) * G));
-    c->h_flag_groups = (int)G;
+  if (c->dots_offset.size() != (size_t)G) {
+    c->dots_offset.resize((size_t)G);
+    int64_t off = 0;
+    for (int64_t g = 0; g < G; ++g) {
+      c->dots_offset[(size_t)g] = off * c->reserved_variants;
+      off += c->groups[(size_t)g].C + 2;
+    }
   }
-  if (!c->flag_ev) LRR_CUDA(c, cudaEventCreateWithFlags(&c->flag_ev, cudaEventDisableTiming));
-  c->reserved_variants = want;
   return LRR_OK;
 }
 
+}  // namespace
+
+int run_begin(Ctx* c, cudaStream_t st) {
+  if (c->ready_valid) LRR_CUDA(c, cudaStreamWaitEvent(st, c->ready_ev, 0));
+  return LRR_OK;
+}
+
+int run_end(Ctx* c, cudaStream_t st) {
+  if (!c->busy_ev) LRR_CUDA(c, cudaEventCreateWithFlags(&c->busy_ev, cudaEventDisableTiming));
+  LRR_CUDA(c, cudaEventRecord(c->busy_ev, st));
+  c->busy_valid = true;
+  return LRR_OK;
+}
+
+namespace {
+constexpr int64_t kPilotRows = 8192;   // rows of the precision pilot (64 tiles)
+int run_rows_once(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
+                  const lrr_group_out* outs, int k, cudaStream_t st);
 }  // namespace
 
 // the hot call behind lrr_run and the streaming loop (stream.cu): sweep + per-variant statistics of one row block
@@ -114,35 +156,54 @@ int run_rows(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_
   if (n_variants == 0) return LRR_OK;
   if (!d_packed) return fail(c, LRR_EINVAL, "lrr_run: d_packed is NULL");
   if (int r = ensure_workspace(c, n_variants)) return r;
+  if (int r = run_begin(c, st)) return r;
 
+  int k = kernel;
+  const bool may_miss = true;  // the column budget is checked for the general (two-plane) mode
+  // AUTO: small problems go straight to the float64 CUDA-core kernel (quantising the basis would cost more than the
+  // sweep: ~4e12 genotype-columns / s against ~0.5 ms of preparation); otherwise the 4-bit tensor-core sweep (as many
+  // passes as the columns need) when its exactness bound holds, else the int8 tensor-core sweep, else the float64 kernel
+  if (k == LRR_KERNEL_AUTO) {
+    double cols = 0.0;
+    for (const Group& g : c->groups) cols += g.C;
+    const double work = (double)n_variants * (double)c->groups[0].ns_pad * cols;
+    if (work <= 2e9) k = LRR_KERNEL_FP64;
+    else k = tc4_supported(c, false) ? LRR_KERNEL_TC4 : tc_supported(c, may_miss) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
+  }
+  // Adaptive precision (4-bit sweep), once per group set and deterministic: the first kPilotRows rows run as a pilot;
+  // when more than 2 % of them leave the tolerance guard (structured or badly scaled covariates: |Q'x| is large for
+  // every row), the covariate / fitted-value columns are re-quantised with two more digits, up to three times.  This
+  // is the only place the hot call waits for the device, and only on the first call after the groups changed.
+  if (k == LRR_KERNEL_TC4 && c->guard && !c->pilot_done && n_variants >= 2 * kPilotRows) {
+    c->pilot_done = true;
+    const int timing = c->timing;
+    c->timing = 0;
+    for (;;) {
+      if (!tc4_supported(c, false))
+        return fail(c, LRR_EINVAL, "lrr_run: 4-bit tensor-core kernel does not support this configuration: " + c->err);
+      if (int r = run_rows_once(c, d_packed, d_row_flags, kPilotRows, packed_stride, outs, k, st)) return r;
+      LRR_CUDA(c, cudaStreamSynchronize(st));
+      int64_t worst = 0;
+      for (size_t g = 0; g < c->groups.size(); ++g) worst = std::max<int64_t>(worst, c->h_flag_count[g]);
+      if (worst * 50 <= kPilotRows || c->digit_boost >= 6) break;
+      c->digit_boost += 2;
+      tc4_invalidate(c);
+    }
+    c->timing = timing;
+  }
+  return run_rows_once(c, d_packed, d_row_flags, n_variants, packed_stride, outs, k, st);
+}
+
+namespace {
+int run_rows_once(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
+                  const lrr_group_out* outs, int k, cudaStream_t st) {
+  const bool may_miss = true;
   if (c->timing) {
     if (!c->ev0) {
       LRR_CUDA(c, cudaEventCreate(&c->ev0));
       LRR_CUDA(c, cudaEventCreate(&c->ev1));
     }
     LRR_CUDA(c, cudaEventRecord(c->ev0, st));
-  }
-  // Adaptive precision: when more than 2 % of the previous run's rows left the tolerance guard (structured or badly
-  // scaled covariates), the covariate / fitted columns get more digits from now on.  Never blocks: the count is read
-  // only if its copy has already completed.
-  if (c->flag_pending && cudaEventQuery(c->flag_ev) == cudaSuccess) {
-    c->flag_pending = false;
-    int64_t worst = 0;
-    for (size_t g = 0; g < c->groups.size() && (int)g < c->h_flag_groups; ++g) worst = std::max<int64_t>(worst, c->h_flag_count[g]);
-    if (c->flag_rows >= 1024 && worst * 50 > c->flag_rows && c->digit_boost < 6) {
-      c->digit_boost += 2;
-      tc4_invalidate(c);
-    }
-  }
-  int k = kernel;
-  const bool may_miss = true;  // the column budget is checked for the general (two-plane) mode
-  // AUTO: tiny problems go straight to the float64 CUDA-core kernel (quantising the basis would cost more than the
-  // sweep); otherwise the 4-bit tensor-core sweep (as many passes as the columns need) when its exactness bound holds,
-  // else the int8 tensor-core sweep, else the float64 kernel
-  if (k == LRR_KERNEL_AUTO) {
-    const double work = (double)n_variants * (double)c->groups[0].ns_pad;
-    if (work <= 2.5e8) k = LRR_KERNEL_FP64;
-    else k = tc4_supported(c, false) ? LRR_KERNEL_TC4 : tc_supported(c, may_miss) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
   }
   if (k == LRR_KERNEL_TC4) {
     if (!tc4_supported(c, false))
@@ -199,8 +260,9 @@ int run_rows(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_
     c->flag_rows = 0;
     for (int g = 0; g < c->h_flag_groups; ++g) c->h_flag_count[g] = 0;
   }
-  return LRR_OK;
+  return run_end(c, st);
 }
+}  // namespace
 
 }  // namespace lrr
 
@@ -238,6 +300,11 @@ void lrr_destroy(lrr_ctx* ctx) try {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   DeviceGuard guard(c->device);
   for (auto& g : c->groups) free_group(g);
+  for (auto& g : c->spare) free_group(g);
+  cudaFree(c->d_scratch);
+  cudaFree(c->d_recompute);
+  if (c->busy_ev) cudaEventDestroy(c->busy_ev);
+  if (c->ready_ev) cudaEventDestroy(c->ready_ev);
   free_workspace(c);
   tc_release(c);
   tc4_release(c);
@@ -328,12 +395,16 @@ int lrr_clear_groups(lrr_ctx* ctx) try {
   if (!ctx) return LRR_EINVAL;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   DeviceGuard guard(c->device);
-  cudaDeviceSynchronize();
-  for (auto& g : c->groups) free_group(g);
+  // no device synchronisation: the buffers are kept (retire_group) and their next writer, lrr_add_group, is ordered
+  // behind the runs still in flight through busy_ev
+  for (auto& g : c->groups) retire_group(c, g);
   c->groups.clear();
   tc_invalidate(c);
   tc4_invalidate(c);
-  free_workspace(c);
+  c->dots_offset.clear();
+  c->flag_pending = false;
+  c->digit_boost = 0;
+  c->pilot_done = false;
   c->n_samples_total = 0;
   return LRR_OK;
 }
@@ -380,24 +451,55 @@ static int add_group_impl(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int3
   g.lbeta = log_beta_half(0.5 * (double)d);
   g.ns_pad = lrr_packed_stride(n_samples_total) * 4;
 
-  int32_t* d_idx = nullptr;
-  double* d_cols = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(d_idx);
-    cudaFree(d_cols);
-  };
+  // steady state: no cudaMalloc and no device synchronisation here.  The staging scratch is grow-only, the four group
+  // buffers come from a retired group when one is large enough, and the copies / kernels below run on the default
+  // stream behind busy_ev (the last run that may still read those buffers on another stream).
+  const size_t idx_bytes = (sizeof(int32_t) * (size_t)n + 255) / 256 * 256;
+  const size_t cols_bytes = sizeof(double) * (size_t)g.C * (size_t)n;
+  const size_t basis_bytes = sizeof(double) * (size_t)g.C * (size_t)g.ns_pad;
+  const size_t mask_bytes = sizeof(uint32_t) * (size_t)(g.ns_pad / 16);
+  const size_t n_qty = qty_len >= 0 ? (size_t)qty_len : (size_t)K * P;
+  const size_t n_yyp = yyp_len >= 0 ? (size_t)yyp_len : (size_t)P;
+  const size_t qty_bytes = sizeof(double) * (n_qty ? n_qty : 1), yyp_bytes = sizeof(double) * (n_yyp ? n_yyp : 1);
+  bool pooled = false;
   auto bail = [&](cudaError_t e, const char* what) {
-    cleanup();
     free_group(g);
     return cuda_fail(c, e, what);
   };
   cudaError_t e;
 #define TRY(call) if ((e = (call)) != cudaSuccess) return bail(e, #call)
-  TRY(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)n));
-  TRY(cudaMemcpy(d_idx, complete_idx, sizeof(int32_t) * (size_t)n, cudaMemcpyDefault));
-  TRY(cudaMalloc(&d_cols, sizeof(double) * (size_t)g.C * n));
-  if (g.Kd > 0) TRY(cudaMemcpy(d_cols, q_cols, sizeof(double) * (size_t)g.Kd * n, cudaMemcpyDefault));
-  TRY(cudaMemcpy(d_cols + (size_t)g.Kd * n, y_res, sizeof(double) * (size_t)P * n, cudaMemcpyDefault));
+  if (c->busy_valid) TRY(cudaStreamWaitEvent(0, c->busy_ev, 0));
+  if (idx_bytes + cols_bytes > c->scratch_bytes) {
+    TRY(cudaDeviceSynchronize());
+    cudaFree(c->d_scratch);
+    c->d_scratch = nullptr;
+    c->scratch_bytes = 0;
+    TRY(cudaMalloc(&c->d_scratch, idx_bytes + cols_bytes));
+    c->scratch_bytes = idx_bytes + cols_bytes;
+  }
+  int32_t* d_idx = static_cast<int32_t*>(c->d_scratch);
+  double* d_cols = reinterpret_cast<double*>(static_cast<char*>(c->d_scratch) + idx_bytes);
+  for (size_t i = 0; i < c->spare.size(); ++i) {
+    const Group& sp = c->spare[i];
+    if (sp.cap_basis >= basis_bytes && sp.cap_mask >= mask_bytes && sp.cap_qty >= qty_bytes && sp.cap_yyp >= yyp_bytes &&
+        sp.cap_basis <= 2 * basis_bytes + (1u << 20)) {   // (do not pin a huge buffer under a tiny group)
+      g.d_basis = sp.d_basis; g.d_mask = sp.d_mask; g.d_qty = sp.d_qty; g.d_yyp = sp.d_yyp;
+      g.cap_basis = sp.cap_basis; g.cap_mask = sp.cap_mask; g.cap_qty = sp.cap_qty; g.cap_yyp = sp.cap_yyp;
+      c->spare.erase(c->spare.begin() + (long)i);
+      pooled = true;
+      break;
+    }
+  }
+  if (!pooled) {
+    TRY(cudaMalloc(&g.d_basis, basis_bytes));
+    TRY(cudaMalloc(&g.d_mask, mask_bytes));
+    TRY(cudaMalloc(&g.d_qty, qty_bytes));
+    TRY(cudaMalloc(&g.d_yyp, yyp_bytes));
+    g.cap_basis = basis_bytes; g.cap_mask = mask_bytes; g.cap_qty = qty_bytes; g.cap_yyp = yyp_bytes;
+  }
+  TRY(cudaMemcpyAsync(d_idx, complete_idx, sizeof(int32_t) * (size_t)n, cudaMemcpyDefault, 0));
+  if (g.Kd > 0) TRY(cudaMemcpyAsync(d_cols, q_cols, sizeof(double) * (size_t)g.Kd * n, cudaMemcpyDefault, 0));
+  TRY(cudaMemcpyAsync(d_cols + (size_t)g.Kd * n, y_res, sizeof(double) * (size_t)P * n, cudaMemcpyDefault, 0));
   if (sqrt_w) {   // column C-2 = sqrt(w), column C-1 = w
     std::vector<double> sw(n), w(n);
     TRY(cudaMemcpy(sw.data(), sqrt_w, sizeof(double) * (size_t)n, cudaMemcpyDefault));
@@ -406,16 +508,10 @@ static int add_group_impl(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int3
     TRY(cudaMemcpy(d_cols + (size_t)(g.Kd + P) * n, sw.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
     TRY(cudaMemcpy(d_cols + (size_t)(g.Kd + P + 1) * n, w.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
   }
-  TRY(cudaMalloc(&g.d_basis, sizeof(double) * (size_t)g.C * g.ns_pad));
-  TRY(cudaMemset(g.d_basis, 0, sizeof(double) * (size_t)g.C * g.ns_pad));
-  TRY(cudaMalloc(&g.d_mask, sizeof(uint32_t) * (size_t)(g.ns_pad / 16)));
-  TRY(cudaMemset(g.d_mask, 0, sizeof(uint32_t) * (size_t)(g.ns_pad / 16)));
-  const size_t n_qty = qty_len >= 0 ? (size_t)qty_len : (size_t)K * P;
-  const size_t n_yyp = yyp_len >= 0 ? (size_t)yyp_len : (size_t)P;
-  TRY(cudaMalloc(&g.d_qty, sizeof(double) * (n_qty ? n_qty : 1)));
-  if (n_qty) TRY(cudaMemcpy(g.d_qty, qty, sizeof(double) * n_qty, cudaMemcpyDefault));
-  TRY(cudaMalloc(&g.d_yyp, sizeof(double) * n_yyp));
-  TRY(cudaMemcpy(g.d_yyp, yyp, sizeof(double) * n_yyp, cudaMemcpyDefault));
+  TRY(cudaMemsetAsync(g.d_basis, 0, basis_bytes, 0));
+  TRY(cudaMemsetAsync(g.d_mask, 0, mask_bytes, 0));
+  if (n_qty) TRY(cudaMemcpyAsync(g.d_qty, qty, sizeof(double) * n_qty, cudaMemcpyDefault, 0));
+  TRY(cudaMemcpyAsync(g.d_yyp, yyp, sizeof(double) * n_yyp, cudaMemcpyDefault, 0));
   {
     const int64_t total = (int64_t)g.C * n;
     int grid = (int)((total + 255) / 256);
@@ -423,15 +519,17 @@ static int add_group_impl(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int3
     scatter_basis_kernel<<<grid, 256>>>(d_cols, g.C, n, d_idx, g.ns_pad, g.d_basis, g.d_mask);
     c->launches++;
     TRY(cudaGetLastError());
-    TRY(cudaDeviceSynchronize());
   }
+  if (!c->ready_ev) TRY(cudaEventCreateWithFlags(&c->ready_ev, cudaEventDisableTiming));
+  TRY(cudaEventRecord(c->ready_ev, 0));
+  c->ready_valid = true;
 #undef TRY
-  cleanup();
   c->groups.push_back(g);
   tc_invalidate(c);
   tc4_invalidate(c);
   c->n_samples_total = n_samples_total;
   c->dots_offset.clear();  // workspace layout depends on the group list
+  c->pilot_done = false;
   return LRR_OK;
 }
 

@@ -58,6 +58,8 @@ struct Group {
   int n_slices = 0;
   // dense-dosage path (filled lazily by launch_dense_sweep)
   double* d_basis_t = nullptr;   // [ns_pad][C] sample-major copy of d_basis, then [ns_pad] the 0 / 1 group indicator
+  // capacities (bytes) of d_basis / d_mask / d_qty / d_yyp: a retired group's buffers are reused by the next lrr_add_group
+  size_t cap_basis = 0, cap_mask = 0, cap_qty = 0, cap_yyp = 0;
 };
 
 struct Ctx {
@@ -97,8 +99,21 @@ struct Ctx {
   cudaEvent_t flag_ev = nullptr;    // the mirror is valid once this has completed
   bool flag_pending = false;
   int64_t flag_rows = 0;            // rows of the run the mirror belongs to
+  // per-call latency: nothing on the lrr_clear_groups / lrr_add_group / lrr_run path synchronises the device or calls
+  // cudaMalloc in the steady state.  Retired groups keep their buffers for the next lrr_add_group, the workspaces are
+  // grow-only, and ordering against kernels still in flight on the caller's streams is done with two events.
+  std::vector<Group> spare;         // retired groups (buffers only)
+  void* d_scratch = nullptr;        // add_group staging: kept sample indices + compact columns
+  size_t scratch_bytes = 0;
+  cudaEvent_t busy_ev = nullptr;    // recorded on the caller's stream after the last run that read the group buffers
+  cudaEvent_t ready_ev = nullptr;   // recorded on the default stream after the last lrr_add_group's device work
+  bool busy_valid = false, ready_valid = false;
+  int64_t ws_groups = 0, ws_cols = 0;   // workspace capacities next to reserved_variants
+  void* d_recompute = nullptr;      // split-row partial sums + arrival counters of fp64_recompute_kernel (grow-only)
+  size_t recompute_bytes = 0;
   int guard = 1;                    // 0: no tolerance guard (kernel tuning / tests of the raw quantised path)
-  int digit_boost = 0;              // extra base-13 digits for covariate / fitted columns (raised when > 2 % of a run was recomputed)
+  int digit_boost = 0;              // extra base-13 digits for covariate / fitted columns (raised by the pilot of run_rows)
+  bool pilot_done = false;          // the precision pilot ran for the current group set
 };
 
 // make `dev` current for the lifetime of the guard
@@ -115,6 +130,10 @@ struct DeviceGuard {
   }
 };
 
+// order the caller's stream behind the last lrr_add_group (call at the start of every run that reads group buffers) and
+// mark the group buffers as in use by that stream (call at its end)
+int run_begin(Ctx* c, cudaStream_t st);
+int run_end(Ctx* c, cudaStream_t st);
 int fail(Ctx* c, int code, const std::string& msg);
 int cuda_fail(Ctx* c, cudaError_t e, const char* what);
 // No C++ exception crosses the C ABI: every extern "C" entry point is a function-try-block ending in

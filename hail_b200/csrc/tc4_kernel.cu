@@ -77,8 +77,12 @@ constexpr int MAX_GSTAGES = 10;
 constexpr int NB = 6;                  // basis-panel ring depth the MMA fast path is unrolled for
 constexpr int MAX_BSTAGES = NB;
 constexpr int SF_COLS = 16;            // scale-factor columns (A: first 8, B: last 8), all bytes 0x7F
+#ifndef LRR_TC4_TP_EAGER
+#define LRR_TC4_TP_EAGER 1
+#endif
 constexpr int MAX_DIGITS = 13;         // base-13 digits per column: 13^13 / 3 < 2^53 / 3, recombined in two int64 halves
 constexpr int PASS_COLS = 112;         // digit columns per sweep: 2 * 112 accumulators + 16 + ring of 4 * 64 <= 512
+constexpr int PASS_COLS_WIDE = 224;    // one-plane-only sweeps (no missing call in the whole input): 224 + 16 + 4 * 64 <= 512
 constexpr int UNROLL = 12;             // chunks per unrolled block of the MMA fast path (lcm of NB and NU)
 
 struct GroupMeta {
@@ -91,7 +95,7 @@ struct GroupMeta {
   int dots_stride;
   const double* colscale;   // [C]
   const uint32_t* mask_hi;  // [ns_pad/16], high bit of each kept field
-  uint8_t nd[PASS_COLS];    // base-13 digits of each dot column of the segment
+  uint8_t nd[PASS_COLS_WIDE];   // base-13 digits of each dot column of the segment
 };
 
 struct Params {
@@ -105,6 +109,7 @@ struct Params {
   int ring_base2;        // two-plane tiles: ring after D_c and D_m, NU2 units
   int gstage_bytes, bstage_bytes;
   int mask_bytes;     // n_groups * 128 when any group needs masking, else 0
+  int one_plane_only; // wide passes: the host has checked that no row holds a missing call
   const uint8_t* row_flags;  // nullable
   int abl_contig;     // timing ablation: read every genotype box as one contiguous 16 KB block (results are WRONG)
   int abl;            // timing ablation bits: 1 no tcgen05.st, 2 no MMA, 4 no basis-panel loads, 8 no unpack ALU, 16 no popcount (results are WRONG)
@@ -161,7 +166,7 @@ struct Barriers {
 
 __device__ __forceinline__ bool tile_has_missing(const Params& p, int tile) {
   const int64_t r0 = (int64_t)tile * TILE_M;
-  if (r0 >= p.M) return false;   // padding tile of a pair
+  if (r0 >= p.M || p.one_plane_only) return false;   // padding tile of a pair; wide passes
   if (!p.row_flags) return true;
   uint32_t any = 0;
   if (r0 + TILE_M <= p.M && ((reinterpret_cast<uintptr_t>(p.row_flags + r0) & 15) == 0)) {
@@ -368,10 +373,12 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         if (++bs == p.n_bstages) { bs = 0; b_phase ^= 1; }
       };
       // fast path: UNROLL chunks with every ring position a compile-time constant (entered with bs == 0, ru == 0)
-      auto fast_chunks = [&](auto tp_tag, auto nu_tag, int& ch) {
+      auto fast_chunks = [&](auto tp_tag, auto nu_tag, auto nb_tag, int& ch) {
         constexpr bool TP = decltype(tp_tag)::value;
         constexpr int NU = decltype(nu_tag)::value;
-        static_assert(UNROLL % NU == 0 && UNROLL % NB == 0, "ring positions must repeat every UNROLL chunks");
+        constexpr int NB = decltype(nb_tag)::value;   // basis-panel ring depth: 6, or 3 for the wide passes
+        static_assert(UNROLL % NU == 0 && UNROLL % NB == 0 && (UNROLL / NB) % 2 == 0,
+                      "ring positions and the basis ring's parity must repeat every UNROLL chunks");
         for (; ch + UNROLL <= p.n_chunks; ch += UNROLL) {
 #pragma unroll
           for (int k = 0; k < UNROLL; ++k) {
@@ -390,7 +397,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
             }
             __syncwarp();
           }
-          // UNROLL / NB = 2 passes over the basis ring: its parity is unchanged
+          // UNROLL / NB is even: the parity of the basis ring is unchanged
         }
       };
 
@@ -402,12 +409,18 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         mbar_wait(DEMPTY, (tile_i & 1) ^ 1);   // the previous tile's accumulators have been read out (by both CTAs)
         tc_fence_after();
         int ch = 0;
-        if (p.n_bstages == NB) {
+        if (p.n_bstages == NB || p.n_bstages == 3) {
           while (ch < p.n_chunks && (bs != 0 || ru != 0)) generic_chunk(ch++, two_plane);
           if (ch < p.n_chunks) {
-            if (two_plane) fast_chunks(TrueTag{}, IntTag<NU2>{}, ch);
-            else if (p.nu1 == 6) fast_chunks(FalseTag{}, IntTag<6>{}, ch);
-            else fast_chunks(FalseTag{}, IntTag<4>{}, ch);
+            if (p.n_bstages == NB) {
+              if (two_plane) fast_chunks(TrueTag{}, IntTag<NU2>{}, IntTag<NB>{}, ch);
+              else if (p.nu1 == 6) fast_chunks(FalseTag{}, IntTag<6>{}, IntTag<NB>{}, ch);
+              else fast_chunks(FalseTag{}, IntTag<4>{}, IntTag<NB>{}, ch);
+            } else {
+              if (two_plane) fast_chunks(TrueTag{}, IntTag<NU2>{}, IntTag<3>{}, ch);
+              else if (p.nu1 == 6) fast_chunks(FalseTag{}, IntTag<6>{}, IntTag<3>{}, ch);
+              else fast_chunks(FalseTag{}, IntTag<4>{}, IntTag<3>{}, ch);
+            }
           }
         }
         for (; ch < p.n_chunks; ++ch) generic_chunk(ch, two_plane);
@@ -446,6 +459,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
     auto run_chunks = [&](auto tp_tag, auto ma_tag) {
       constexpr bool TP = decltype(tp_tag)::value;
       constexpr bool MA = decltype(ma_tag)::value;
+      constexpr bool EAGER = TP && (LRR_TC4_TP_EAGER != 0);
       int pend = -1;    // unit whose TMEM store is issued but not yet published to the MMA warp
       auto chunk_body = [&](const int u, const int pend_u) {
         mbar_wait(gbar, g_phase);
@@ -496,7 +510,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(gbar + 8u * MAX_GSTAGES);   // genotype stage back to the TMA producer
-        if (pend_u >= 0 && !ABL(32)) {   // retire the previous chunk's TMEM store behind this chunk's arithmetic
+        if (pend_u >= 0 && !EAGER) {   // retire the previous chunk's TMEM store behind this chunk's arithmetic
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
@@ -517,7 +531,9 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
           }
           tmem_st16(a_slot + (u + 1) * UNIT_COLS, rc);
         }
-        if ABL(32) {   // experiment: publish the store at once instead of behind the next chunk's arithmetic
+        if (EAGER) {
+          // two-plane tiles: the ring holds only two chunks (4 units), so a store published one chunk late would leave the
+          // MMA warp nothing to overlap with -- publish at once (measured: 35 -> see profiles/README.md ms per C3 pass)
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
@@ -564,7 +580,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         }
       }
       for (; ch < p.n_chunks; ++ch) generic_chunk();
-      if (pend >= 0 && !ABL(32)) {   // flush the last chunk of the tile
+      if (pend >= 0 && !EAGER) {   // flush the last chunk of the tile
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -873,6 +889,9 @@ struct GroupCols {
 struct State {
   bool prepared = false;
   bool usable = false;
+  bool wide = false;             // the prepared plan uses wide one-plane-only passes
+  int32_t* d_any = nullptr;      // scratch of any_flag_kernel
+  int32_t* h_any = nullptr;      // page-locked
   std::string why;
   EncodeTiledFn encode = nullptr;
   std::vector<Pass> passes;
@@ -956,7 +975,7 @@ static void digit_policy(const Group& gr, int n_fit, const double* colmax, const
 }
 
 // split every group's dot columns into passes of at most PASS_COLS panel rows
-static void plan_passes(const Ctx* c, const std::vector<GroupCols>& cols, std::vector<Pass>& passes) {
+static void plan_passes(const Ctx* c, const std::vector<GroupCols>& cols, std::vector<Pass>& passes, int pass_cols) {
   passes.clear();
   Pass cur;
   int used = 0;
@@ -973,7 +992,7 @@ static void plan_passes(const Ctx* c, const std::vector<GroupCols>& cols, std::v
     const int Cx = (int)nd.size();
     int col = 0;
     while (col < Cx) {
-      if (used + nd[col] + 1 > PASS_COLS || (int)cur.segs.size() == MAX_GROUPS) close();
+      if (used + nd[col] + 1 > pass_cols || (int)cur.segs.size() == MAX_GROUPS) close();
       Segment sg;
       sg.group = (int)g;
       sg.c_first = col;
@@ -981,7 +1000,7 @@ static void plan_passes(const Ctx* c, const std::vector<GroupCols>& cols, std::v
       sg.row0 = used;
       int rows = 0;
       while (col < Cx) {
-        if (used + rows + nd[col] + 1 > PASS_COLS) break;
+        if (used + rows + nd[col] + 1 > pass_cols) break;
         rows += nd[col];
         sg.n_cols++;
         col++;
@@ -995,11 +1014,18 @@ static void plan_passes(const Ctx* c, const std::vector<GroupCols>& cols, std::v
   close();
 }
 
-static int prepare(Ctx* c) {
+__global__ void any_flag_kernel(const uint8_t* __restrict__ flags, int64_t M, int32_t* __restrict__ any) {
+  int f = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) f |= flags[i];
+  if (__any_sync(0xffffffffu, f != 0) && (threadIdx.x & 31) == 0) atomicOr(any, 1);
+}
+
+static int prepare(Ctx* c, bool wide) {
   State* s = state(c);
-  if (s->prepared) return LRR_OK;
+  if (s->prepared && s->wide == wide) return LRR_OK;
   free_prepared(s);
   s->prepared = true;
+  s->wide = wide;
   s->usable = false;
   if (!s->encode) {
     void* fn = nullptr;
@@ -1061,7 +1087,9 @@ static int prepare(Ctx* c) {
   for (size_t g = 0; g < G; ++g)
     digit_policy(c->groups[g], s->cols[g].n_fit, h_stat.data() + s->scale_off[g], h_stat.data() + nscale + s->scale_off[g],
                  c->digit_boost, s->cols[g].nd);
-  plan_passes(c, s->cols, s->passes);
+  int wide_cols = PASS_COLS_WIDE;
+  if (const char* e = tuning_env("LRR_TC4_WIDE")) { const int v = atoi(e); if (v >= PASS_COLS && v <= PASS_COLS_WIDE) wide_cols = v / 16 * 16; }
+  plan_passes(c, s->cols, s->passes, wide ? wide_cols : PASS_COLS);
   int64_t total_rows = 0;
   for (auto& ps : s->passes) {
     ps.bq_row0 = total_rows;
@@ -1125,7 +1153,7 @@ static int prepare(Ctx* c) {
     ps.ring_base2 = (2 * ps.ncols + 31) / 32 * 32;
     ps.nu1 = (SF_BASE - ps.ring_base1) / UNIT_COLS >= 6 ? 6 : 4;
     if (const char* e = tuning_env("LRR_TC4_NU1")) { if (atoi(e) == 4) ps.nu1 = 4; }
-    if (ps.ring_base2 + NU2 * UNIT_COLS > SF_BASE || ps.ring_base1 + ps.nu1 * UNIT_COLS > SF_BASE) {
+    if ((!wide && ps.ring_base2 + NU2 * UNIT_COLS > SF_BASE) || ps.ring_base1 + ps.nu1 * UNIT_COLS > SF_BASE) {
       s->why = "not enough tensor memory for the A ring";
       return LRR_OK;
     }
@@ -1173,7 +1201,8 @@ static int prepare(Ctx* c) {
 
 // usable at all; `single_pass_only`: only when one sweep covers every column (what LRR_KERNEL_AUTO asks)
 bool tc4_supported(Ctx* c, bool single_pass_only) {
-  if (tc4::prepare(c) != LRR_OK) return false;
+  tc4::State* s0 = tc4::state(c);
+  if (tc4::prepare(c, s0->prepared ? s0->wide : false) != LRR_OK) return false;
   tc4::State* s = tc4::state(c);
   if (!s->usable) {
     c->err = s->why;
@@ -1203,6 +1232,8 @@ void tc4_release(Ctx* c) {
   if (!c->tc4_state) return;
   tc4::State* s = static_cast<tc4::State*>(c->tc4_state);
   tc4::free_prepared(s);
+  cudaFree(s->d_any);
+  if (s->h_any) cudaFreeHost(s->h_any);
   delete s;
   c->tc4_state = nullptr;
 }
@@ -1211,9 +1242,31 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
                      cudaStream_t st) {
   using namespace tc4;
   if (M == 0) return LRR_OK;
-  if (int r = prepare(c)) return r;
   State* s = state(c);
+  if (int r = prepare(c, s->prepared ? s->wide : false)) return r;
   if (!s->usable) return fail(c, LRR_EINVAL, "4-bit tensor-core kernel unavailable: " + s->why);
+  // More digit columns than one sweep holds: every pass re-reads the genotypes, so fewer, wider passes win -- but a pass of
+  // up to 224 columns has no tensor memory for the missing-indicator plane.  It is used when the input's row flags say
+  // that no row holds a missing call (one small reduction + a 4-byte read per call, only in multi-pass configurations).
+  if (s->passes.size() > 1 || s->wide) {
+    bool want_wide = false;
+    if (d_row_flags) {
+      if (!s->d_any) {
+        LRR_CUDA(c, cudaMalloc(&s->d_any, sizeof(int32_t)));
+        LRR_CUDA(c, cudaMallocHost(&s->h_any, sizeof(int32_t)));
+      }
+      LRR_CUDA(c, cudaMemsetAsync(s->d_any, 0, sizeof(int32_t), st));
+      any_flag_kernel<<<(unsigned)std::min<int64_t>((M + 255) / 256, 1184), 256, 0, st>>>(d_row_flags, M, s->d_any);
+      c->launches++;
+      LRR_CUDA(c, cudaMemcpyAsync(s->h_any, s->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      LRR_CUDA(c, cudaStreamSynchronize(st));
+      want_wide = *s->h_any == 0;
+    }
+    if (want_wide != s->wide) {
+      if (int r = prepare(c, want_wide)) return r;
+      if (!s->usable) return fail(c, LRR_EINVAL, "4-bit tensor-core kernel unavailable: " + s->why);
+    }
+  }
   CUtensorMap geno_map;
   const bool abl_contig = tuning_env("LRR_ABL_CONTIG") != nullptr;   // timing ablation only
   if (abl_contig) {
@@ -1241,6 +1294,7 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
     p.bstage_bytes = sh.bstage_bytes;
     p.mask_bytes = ps.mask_bytes;
     p.row_flags = d_row_flags;
+    p.one_plane_only = s->wide ? 1 : 0;
     p.abl_contig = abl_contig ? 1 : 0;
     p.abl_stream = tuning_env("LRR_ABL_STREAM") ? atoi(tuning_env("LRR_ABL_STREAM")) : 0;
     p.abl = tuning_env("LRR_ABL_BITS") ? atoi(tuning_env("LRR_ABL_BITS")) : 0;

@@ -148,7 +148,9 @@ int lrr_run_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t l
  * bound leaves half of the parity tolerance (relative 1e-6, p-values 1e-5; an absolute |dt| <= 5e-10 also passes, 5e-7
  * for groups of more than two phenotypes).  Listed rows are recomputed in float64 inside the same lrr_run (asynchronous,
  * same stream).  lrr_last_recomputed returns how many rows of the last lrr_run were recomputed, summed over the groups
- * (it synchronises on that run); when more than 2 % were, the next lrr_run re-quantises the basis with more digits.
+ * (it synchronises on that run).  Precision is adaptive and deterministic: on the first lrr_run after the groups
+ * changed, the first 8,192 rows run as a pilot and, when more than 2 % of them were listed (structured or badly scaled
+ * covariates), the covariate columns are re-quantised with two more base-13 digits, up to three times.
  * lrr_set_guard(ctx, 0) switches the guard off (kernel tuning, tests of the raw quantised path). */
 int lrr_set_guard(lrr_ctx* ctx, int enabled);
 int64_t lrr_last_recomputed(lrr_ctx* ctx);

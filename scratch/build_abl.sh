@@ -4,6 +4,7 @@
 #   scratch/build_abl.sh && LRR_B200_LIB=$PWD/scratch/abl/tc4_abl.so LRR_ABL_BITS=2 scratch/sustain.sh noMMA
 cd "$(dirname "$0")/.."
 mkdir -p scratch/abl
-SRC="hail_b200/csrc/abi.cu hail_b200/csrc/pack.cu hail_b200/csrc/fp64_kernel.cu hail_b200/csrc/stats_epilogue.cu hail_b200/csrc/tc_kernel.cu hail_b200/csrc/tc4_kernel.cu hail_b200/csrc/stream.cu"
+SRC="$(ls hail_b200/csrc/*.cu | tr '
+' ' ')"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared"
 nvcc $FLAGS -DLRR_TC4_ABLATIONS=1 -DLRR_TUNING=1 "$@" -o scratch/abl/tc4_abl.so $SRC && ls -la scratch/abl
