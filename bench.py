@@ -30,7 +30,7 @@ N_SAMPLES, N_VARIANTS, N_COV, N_PHENO = 400_000, 1_000_000, 10, 1
 WORKLOAD = "C2: BN(3 pops) 400k samples x 1M variants, P=1, K=10 (intercept + 9 PCs)"
 METRIC = "genotypes/sec (variants x samples) for linear_regression_rows"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE tc4 sweep launch on the headline workload (ncu --set full)
-TRAFFIC_C2_TC4 = {"bytes": 103306471048, "source": "constant from profiles/r01_tc4_full_c2_ncu_full.txt (ncu --set full, one launch)"}
+TRAFFIC_C2_TC4 = {"bytes": 102427254560, "source": "constant from profiles/r02_c2_tc4_ncu_full.txt (ncu --set full, one launch: 102.164 GB read + 0.263 GB written)"}
 
 
 def parse():
@@ -197,7 +197,8 @@ def run_ours(a):
     else:
         y_groups = [y]
     bases = [GroupBasis(yg, cov, np.arange(N), i if a.chained else None) for i, yg in enumerate(y_groups)] if rank == 0 else None
-    sr = hd.ShardedRegression(gt)          # the product path: hail_b200.linear_regression_rows(_sharded=True) runs on it
+    # the product path: hail_b200.linear_regression_rows(_sharded=True) runs on the same class
+    sr = hd.ShardedRegression(gt, transport="peer" if a.gather in ("auto", "peer") else "nccl")
     bts = sr.set_bases(bases)
     G = len(bts)
     n_kept, K, P = bts[0].n, bts[0].K, bts[0].P
@@ -347,7 +348,7 @@ def run_ours(a):
         "config": config_of(a, N, a.variants if a.strong else M, P, K, G, world), "kernel": kernel_used,
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "ranks": per_rank,
         "recomputed_rows_last_step": int(recomputed),
-        "multi_gpu": None if world == 1 else {"gather": gather_mode, "broadcast_per_step": not a.no_broadcast,
+        "multi_gpu": None if world == 1 else {"gather": gather_mode, "broadcast": sr.transport, "broadcast_per_step": not a.no_broadcast,
                                               "gather_per_step": not a.no_gather, "row_bytes_per_rank": chunk * width * G * 8},
     }
 

@@ -168,7 +168,7 @@ int run_rows(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_
     for (const Group& g : c->groups) cols += g.C;
     const double work = (double)n_variants * (double)c->groups[0].ns_pad * cols;
     if (work <= 2e9) k = LRR_KERNEL_FP64;
-    else k = tc4_supported(c, false) ? LRR_KERNEL_TC4 : tc_supported(c, may_miss) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
+    else k = tc4_supported(c, false, d_row_flags, n_variants, st) ? LRR_KERNEL_TC4 : tc_supported(c, may_miss) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
   }
   // Adaptive precision (4-bit sweep), once per group set and deterministic: the first kPilotRows rows run as a pilot;
   // when more than 2 % of them leave the tolerance guard (structured or badly scaled covariates: |Q'x| is large for
@@ -179,7 +179,7 @@ int run_rows(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_
     const int timing = c->timing;
     c->timing = 0;
     for (;;) {
-      if (!tc4_supported(c, false))
+      if (!tc4_supported(c, false, d_row_flags, n_variants, st))
         return fail(c, LRR_EINVAL, "lrr_run: 4-bit tensor-core kernel does not support this configuration: " + c->err);
       if (int r = run_rows_once(c, d_packed, d_row_flags, kPilotRows, packed_stride, outs, k, st)) return r;
       LRR_CUDA(c, cudaStreamSynchronize(st));
@@ -206,7 +206,7 @@ int run_rows_once(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, i
     LRR_CUDA(c, cudaEventRecord(c->ev0, st));
   }
   if (k == LRR_KERNEL_TC4) {
-    if (!tc4_supported(c, false))
+    if (!tc4_supported(c, false, d_row_flags, n_variants, st))
       return fail(c, LRR_EINVAL, "lrr_run: 4-bit tensor-core kernel does not support this configuration: " + c->err);
     if (int r = launch_tc4_sweep(c, d_packed, d_row_flags, n_variants, packed_stride, st)) return r;
   } else if (k == LRR_KERNEL_TC) {

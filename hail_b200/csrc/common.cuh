@@ -168,7 +168,8 @@ int launch_fp64_recompute(Ctx*, int g, const uint8_t* d_packed, int64_t stride, 
 void tc_invalidate(Ctx*);
 void tc_release(Ctx*);
 int launch_tc4_sweep(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, cudaStream_t);
-bool tc4_supported(Ctx*, bool single_pass_only);
+// (d_row_flags, M, st: lets the first quantisation of a group set pick the wide one-plane plan when no row has a missing call)
+bool tc4_supported(Ctx*, bool single_pass_only, const uint8_t* d_row_flags = nullptr, int64_t M = 0, cudaStream_t st = nullptr);
 void tc4_invalidate(Ctx*);
 void tc4_release(Ctx*);
 // `quantum` != NULL: per-column quantisation step of the sweep that produced the dots (tolerance guard on); `n_fit`:

@@ -729,9 +729,12 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
 // basis quantisation: float64 column -> balanced base-13 digits as E2M1 nibbles, in the A operand's element order
 // ------------------------------------------------------------------------------------------------
 // max |v| and sum v^2 of one column per CTA (fixed reduction order: the digit policy below must not depend on atomics)
-__global__ void __launch_bounds__(1024) colstat_kernel(const double* __restrict__ col, int64_t ns_pad, double* __restrict__ colmax,
-                                                       double* __restrict__ sumsq) {
+__global__ void __launch_bounds__(1024) colstat_kernel(const double* __restrict__ cols, int64_t ns_pad, double* __restrict__ colmax_out,
+                                                       double* __restrict__ sumsq_out) {
   __shared__ double s_m[32], s_q[32];
+  const double* col = cols + (int64_t)blockIdx.x * ns_pad;   // one CTA per column
+  double* colmax = colmax_out + blockIdx.x;
+  double* sumsq = sumsq_out + blockIdx.x;
   double m = 0.0, q = 0.0;
   for (int64_t j = threadIdx.x; j < ns_pad; j += blockDim.x) {
     const double v = col[j];
@@ -827,15 +830,22 @@ __global__ void ones_row_kernel(const uint32_t* __restrict__ mask, int64_t ns_pa
 __global__ void acc_bound_kernel(const uint8_t* __restrict__ bq, int64_t row_bytes, unsigned long long* __restrict__ bound) {
   const int64_t r = blockIdx.y;
   unsigned long long pos = 0, neg = 0;
-  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < row_bytes; b += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t byte = bq[r * row_bytes + b];
+  const uint4* row = reinterpret_cast<const uint4*>(bq + r * row_bytes);   // row_bytes is a multiple of 256
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < row_bytes / 16; q += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(row + q);
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    uint32_t p32 = 0, n32 = 0;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint32_t code = (byte >> (4 * h)) & 15u;
-      const uint32_t m = code & 7u;
-      const unsigned long long u = m <= 4 ? m : (m == 5 ? 6ull : (m == 6 ? 8ull : 12ull));
-      if (code & 8u) neg += 3ull * u; else pos += 3ull * u;
-    }
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        const uint32_t code = (w4[k] >> (4 * h)) & 15u;
+        const uint32_t m = code & 7u;
+        const uint32_t u = m <= 4 ? m : (m == 5 ? 6u : (m == 6 ? 8u : 12u));
+        if (code & 8u) n32 += 3u * u; else p32 += 3u * u;
+      }
+    pos += p32;
+    neg += n32;
   }
   for (int o = 16; o > 0; o >>= 1) {
     pos += __shfl_xor_sync(0xffffffffu, pos, o);
@@ -1075,12 +1085,16 @@ static int prepare(Ctx* c, bool wide) {
   };
   LRR_CUDA(c, cudaMalloc(&s->d_colstat, sizeof(double) * 2 * (size_t)nscale));
   LRR_CUDA(c, cudaMalloc(&s->d_colscale, sizeof(double) * (size_t)nscale));
-  for (size_t g = 0; g < G; ++g)
-    for (int col = 0; col < c->groups[g].C + s->cols[g].n_fit; ++col) {
-      const int k = s->scale_off[g] + col;
-      colstat_kernel<<<1, 1024>>>(column_ptr(g, col), ns_pad, s->d_colstat + k, s->d_colstat + nscale + k);
+  for (size_t g = 0; g < G; ++g) {
+    const Group& gr = c->groups[g];
+    const int k = s->scale_off[g];
+    colstat_kernel<<<(unsigned)gr.C, 1024>>>(gr.d_basis, ns_pad, s->d_colstat + k, s->d_colstat + nscale + k);
+    c->launches++;
+    if (s->cols[g].n_fit) {
+      colstat_kernel<<<(unsigned)s->cols[g].n_fit, 1024>>>(s->cols[g].d_fit, ns_pad, s->d_colstat + k + gr.C, s->d_colstat + nscale + k + gr.C);
       c->launches++;
     }
+  }
   LRR_CUDA(c, cudaGetLastError());
   std::vector<double> h_stat(2 * (size_t)nscale);
   LRR_CUDA(c, cudaMemcpy(h_stat.data(), s->d_colstat, sizeof(double) * h_stat.size(), cudaMemcpyDeviceToHost));
@@ -1128,8 +1142,9 @@ static int prepare(Ctx* c, bool wide) {
     unsigned long long* d_bound = nullptr;
     LRR_CUDA(c, cudaMalloc(&d_bound, sizeof(unsigned long long) * 2 * (size_t)total_rows));
     LRR_CUDA(c, cudaMemset(d_bound, 0, sizeof(unsigned long long) * 2 * (size_t)total_rows));
+    const unsigned gxq = (unsigned)std::max<int64_t>(1, std::min<int64_t>((row_bytes / 16 + 255) / 256, 64));
     for (int64_t r0 = 0; r0 < total_rows; r0 += 65535)
-      acc_bound_kernel<<<dim3(gxb, (unsigned)std::min<int64_t>(total_rows - r0, 65535)), 256>>>(s->d_bq + r0 * row_bytes,
+      acc_bound_kernel<<<dim3(gxq, (unsigned)std::min<int64_t>(total_rows - r0, 65535)), 256>>>(s->d_bq + r0 * row_bytes,
                                                                                              row_bytes, d_bound + 2 * r0);
     c->launches++;
     std::vector<unsigned long long> h_bound(2 * (size_t)total_rows);
@@ -1197,12 +1212,36 @@ static int prepare(Ctx* c, bool wide) {
   return LRR_OK;
 }
 
+// Before the first quantisation of a group set: when the column count makes a multi-pass plan certain (every column has
+// at least 6 digits), ask the row flags first so that the basis is quantised once, for the right plan.
+static int first_plan_is_wide(Ctx* c, const uint8_t* d_row_flags, int64_t M, cudaStream_t st, bool* wide) {
+  State* s = state(c);
+  *wide = false;
+  if (s->prepared || !d_row_flags || M <= 0) return LRR_OK;
+  int64_t dot_cols = 0;
+  for (const Group& gr : c->groups) dot_cols += gr.C;
+  if (6 * dot_cols <= PASS_COLS) return LRR_OK;
+  if (!s->d_any) {
+    LRR_CUDA(c, cudaMalloc(&s->d_any, sizeof(int32_t)));
+    LRR_CUDA(c, cudaMallocHost(&s->h_any, sizeof(int32_t)));
+  }
+  LRR_CUDA(c, cudaMemsetAsync(s->d_any, 0, sizeof(int32_t), st));
+  any_flag_kernel<<<(unsigned)std::min<int64_t>((M + 255) / 256, 1184), 256, 0, st>>>(d_row_flags, M, s->d_any);
+  c->launches++;
+  LRR_CUDA(c, cudaMemcpyAsync(s->h_any, s->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  LRR_CUDA(c, cudaStreamSynchronize(st));
+  *wide = *s->h_any == 0;
+  return LRR_OK;
+}
+
 }  // namespace tc4
 
 // usable at all; `single_pass_only`: only when one sweep covers every column (what LRR_KERNEL_AUTO asks)
-bool tc4_supported(Ctx* c, bool single_pass_only) {
+bool tc4_supported(Ctx* c, bool single_pass_only, const uint8_t* d_row_flags, int64_t M, cudaStream_t st) {
   tc4::State* s0 = tc4::state(c);
-  if (tc4::prepare(c, s0->prepared ? s0->wide : false) != LRR_OK) return false;
+  bool first_wide = false;
+  if (tc4::first_plan_is_wide(c, d_row_flags, M, st, &first_wide) != LRR_OK) return false;
+  if (tc4::prepare(c, s0->prepared ? s0->wide : first_wide) != LRR_OK) return false;
   tc4::State* s = tc4::state(c);
   if (!s->usable) {
     c->err = s->why;
@@ -1243,7 +1282,9 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
   using namespace tc4;
   if (M == 0) return LRR_OK;
   State* s = state(c);
-  if (int r = prepare(c, s->prepared ? s->wide : false)) return r;
+  bool first_wide = false;
+  if (int r = first_plan_is_wide(c, d_row_flags, M, st, &first_wide)) return r;
+  if (int r = prepare(c, s->prepared ? s->wide : first_wide)) return r;
   if (!s->usable) return fail(c, LRR_EINVAL, "4-bit tensor-core kernel unavailable: " + s->why);
   // More digit columns than one sweep holds: every pass re-reads the genotypes, so fewer, wider passes win -- but a pass of
   // up to 224 columns has no tensor memory for the missing-indicator plane.  It is used when the input's row flags say

@@ -53,7 +53,7 @@ def _basis_shapes(n, K, P, hi):
             (torch.float64, (P,))]
 
 
-def broadcast_bases(bases, device, src=0, group=None, message=None):
+def broadcast_bases(bases, device, src=0, group=None, message=None, payload_transport=None):
     """Rank `src` passes its list of GroupBasis (others pass None); every rank returns the list of BasisTensors.
 
     What `sc.broadcast` ships per call (LR:74-78, LR:257) travels as ONE flat message: a fixed-size header (group count and
@@ -89,7 +89,10 @@ def broadcast_bases(bases, device, src=0, group=None, message=None):
             for t, (off, nbytes, _, _) in zip(bt.tensors, offs):
                 if nbytes:
                     payload[off:off + nbytes] = t.contiguous().view(torch.uint8).reshape(-1)
-    dist.broadcast(payload, src, group=group)
+    if payload_transport is not None:
+        payload = payload_transport(payload)     # e.g. PeerBroadcast: pulled over NVLink by the copy engines
+    else:
+        dist.broadcast(payload, src, group=group)
     out = []
     for meta, offs in zip(metas, layout):
         ts = [payload[off:off + nbytes].view(dt).reshape(shape) for off, nbytes, dt, shape in offs]
@@ -108,20 +111,27 @@ class ShardedRegression:
 
     FIELDS = ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value")
 
-    def __init__(self, genotypes, group=None):
+    def __init__(self, genotypes, group=None, transport="nccl"):
+        """`transport`: how the per-call basis message travels -- "nccl" (dist.broadcast) or "peer" (PeerBroadcast: pulled
+        over NVLink by the copy engines; needs torch symmetric memory, falls back to NCCL when it is unavailable)."""
         from . import _lib
         self.g = genotypes
         self.dev = genotypes.device
         self.ctx = _lib.context(self.dev.index)
         self.group = group
         self.bts = None
+        self.transport = transport
+        self._peer = None
 
     def set_bases(self, bases, src=0):
         """Collective.  Rank `src` passes the list of GroupBasis (the driver prologue ran there), the others None."""
         ctx, N = self.ctx, self.g.n_samples
         self._message, self._src = [], src
-        self.bts = broadcast_bases(bases, self.dev, src, self.group, message=self._message)
+        self.bts = broadcast_bases(bases, self.dev, src, self.group, message=self._message,
+                                   payload_transport=self._peer_payload if self.transport == "peer" else None)
         with torch.cuda.device(self.dev):
+            # lrr_add_group copies on the library's default stream: the message must have landed (one host wait per call)
+            torch.cuda.current_stream(self.dev).synchronize()
             ctx.check(ctx.lib.lrr_clear_groups(ctx.handle))
             for b in self.bts:
                 t = b.tensors
@@ -131,11 +141,30 @@ class ShardedRegression:
             ctx.check(ctx.lib.lrr_reserve(ctx.handle, self.g.n_variants))
         return self.bts
 
+    def _peer_payload(self, payload):
+        """The payload of the per-call message through PeerBroadcast (created, or re-created larger, collectively: every
+        rank knows the size from the header)."""
+        nbytes = payload.numel()
+        if self._peer is None or self._peer.capacity < nbytes:
+            try:
+                self._peer = PeerBroadcast(nbytes, self.dev, self._src, self.group)
+            except Exception as e:   # symmetric memory unavailable on this box / build
+                self.transport = f"nccl (peer transport unavailable: {type(e).__name__}: {e})"
+                dist.broadcast(payload, self._src, group=self.group)
+                return payload
+        return self._peer.send(payload, nbytes)
+
     def rebroadcast(self):
         """The per-call message once more (header + payload, asynchronous on the current stream): what a repeated call
         with the same phenotypes costs on the wire (bench.py)."""
-        for t in self._message:
-            dist.broadcast(t, self._src, group=self.group)
+        header, payload = self._message
+        if self._peer is not None and self.transport == "peer":
+            if getattr(self, "_staged", None) is None:
+                self._staged = payload.clone()   # (the received payload IS the symmetric buffer: send from a copy)
+            self._peer.send(self._staged, self._staged.numel())
+            return
+        dist.broadcast(header, self._src, group=self.group)
+        dist.broadcast(payload, self._src, group=self.group)
 
     def alloc_outputs(self, want_log10_p=False):
         from . import _lib
@@ -260,3 +289,42 @@ class RowGather:
         else:
             dist.all_gather_into_tensor(self.bufs[b], rows.contiguous(), group=self.pg)
         return self.bufs[b]
+
+
+class PeerBroadcast:
+    """One-to-all copy of a byte message through symmetric memory: the root stages the message in its own symmetric buffer
+    and signals every peer (point to point); a peer waits for that signal only, PULLS the bytes over NVLink with a plain
+    device-to-device copy (copy engines) and signals the root back, which the root collects before it overwrites the
+    buffer with the next message.  No rank ever waits for a rank other than the root, and no SM spins inside a collective
+    kernel next to the sweep (the per-call NCCL broadcast cost the 8-GPU step of round 2 1.4 ms: it acts as a barrier over
+    ranks whose sweep times differ by 15 %, and its polling CTAs draw from the same power budget)."""
+
+    def __init__(self, nbytes, device, src=0, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.src, self.dev = src, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        pg = group if group is not None else dist.group.WORLD
+        self.capacity = int(max(nbytes, 1 << 20))
+        self.buf = symm.empty(self.capacity, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, pg.group_name if hasattr(pg, "group_name") else pg)
+        self.root_view = self.hdl.get_buffer(src, (self.capacity,), torch.uint8)
+        self.sent = 0
+
+    def send(self, message, nbytes):
+        """Collective, asynchronous on the current stream.  `message` (uint8, >= nbytes) is read on the root only; returns
+        a uint8 view of the local copy (valid until the next send)."""
+        if self.rank == self.src:
+            if self.sent:
+                for r in range(self.world):
+                    if r != self.src:
+                        self.hdl.wait_signal(r, channel=3)     # peer r has pulled the previous message
+            self.buf[:nbytes].copy_(message[:nbytes], non_blocking=True)
+            for r in range(self.world):
+                if r != self.src:
+                    self.hdl.put_signal(r, channel=2)
+        else:
+            self.hdl.wait_signal(self.src, channel=2)
+            self.buf[:nbytes].copy_(self.root_view[:nbytes], non_blocking=True)
+            self.hdl.put_signal(self.src, channel=3)
+        self.sent += 1
+        return self.buf[:nbytes]

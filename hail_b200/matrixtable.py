@@ -263,6 +263,16 @@ class Table:
         f.update(named)
         return Table(f, self.key, self.n_rows)
 
+    def annotate(self, **named):
+        """Replace / append fields (statgen.py:404-406 uses it to unwrap the single-phenotype arrays)."""
+        f = OrderedDict(self._fields)
+        f.update(named)
+        t = Table(f, self.key, self.n_rows)
+        for extra in ("n_missing", "sharded"):
+            if extra in self.__dict__:
+                setattr(t, extra, self.__dict__[extra])
+        return t
+
     def collect(self):
         rows = []
         for i in range(self.n_rows):
@@ -317,7 +327,7 @@ class Table:
             return cat_array(v)
 
         t = Table(OrderedDict((k, cat(v)) for k, v in self._fields.items()), self.key, sum(counts))
-        if hasattr(self, "n_missing"):
+        if "n_missing" in self.__dict__:
             t.n_missing = [cat_array(g) for g in self.n_missing] if isinstance(self.n_missing, list) else cat_array(self.n_missing)
         return t
 

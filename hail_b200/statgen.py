@@ -373,11 +373,17 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
     per group of a chained `y`): weighted least squares as the reference's `_linear_regression_rows_nd` does it
     (statgen.py:557-581, 636-660): samples without a weight are dropped, x is mean-imputed and then scaled by sqrt(w).
 
+    Like the reference (statgen.py:370-401) the call selects its inputs into uniquely named fields, builds the config
+    `{'name': 'LinearRegressionRowsSingle' | '...Chained', 'yFields', 'xField', 'covFields', 'rowBlockSize',
+    'passThrough'}` and applies the relational function registered under that name (hail_b200/plugin.py, the
+    analogue of `MatrixToTableApply` + RelationalFunctions.scala:112-138).
+
     `_sharded=True` (one process per GPU, torch.distributed initialised): every rank passes a MatrixTable holding its own
     contiguous range of the ROWS (variants) over the same columns -- the reference's one task per partition (LR:95,
     :274).  Rank 0 runs the driver prologue and its bases are broadcast once per call (LR:74-78, :257); every rank
     sweeps its rows and returns the Table of ITS rows (bit-identical to the same rows of a single-device run);
-    `Table.gather()` concatenates all ranks' rows in rank order on every rank.
+    `Table.gather()` concatenates all ranks' rows in rank order on every rank.  `_sharded="peer"` sends the broadcast
+    through symmetric memory (pulled over NVLink by the copy engines, hail_b200/dist.py PeerBroadcast) instead of NCCL.
     """
     if not isinstance(block_size, int):
         raise TypeError("linear_regression_rows: 'block_size' must be int")
@@ -407,74 +413,113 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
     groups = [list(g) for g in y] if is_chained else [list(y) if y_is_list else [y]]
     y_vals = [[_column_values(e, mt, "linear_regression_rows/y") for e in g] for g in groups]
     cov_vals = [_column_values(e, mt, "linear_regression_rows/covariates") for e in covariates]
-    w_vals = [None] * len(groups) if weights is None else \
-        [_column_values(e, mt, "linear_regression_rows/weights") for e in weights]
+    w_vals = None if weights is None else [_column_values(e, mt, "linear_regression_rows/weights") for e in weights]
     _warn_if_no_intercept("linear_regression_rows", covariates)
     row_fields = _get_regression_row_fields(mt, pass_through, "linear_regression_rows")
 
+    # SG:370-392: select the inputs into uniquely named column / entry fields ...
+    x_field_name = f"__uid_x_{next(_uid)}"
+    if is_chained:
+        y_field_names = [[f"__y_{i}_{j}" for j in range(len(g))] for i, g in enumerate(y_vals)]
+    else:
+        y_field_names = [f"__y_{i}" for i in range(len(y_vals[0]))]
+    cov_field_names = [f"__cov{i}" for i in range(len(cov_vals))]
+    flat_names = list(itertools.chain.from_iterable(y_field_names)) if is_chained else y_field_names
+    selected = mt._copy(cols=OrderedDict(itertools.chain(zip(flat_names, itertools.chain.from_iterable(y_vals)),
+                                                         zip(cov_field_names, cov_vals))),
+                        rows=OrderedDict(itertools.chain(((k, mt.row[k]) for k in mt.row_key), row_fields.items())),
+                        col_key=()).annotate_entries(**{x_field_name: x})
+    # ... SG:394-401: and hand the config to the relational function registered under its name
+    config = {
+        "name": "LinearRegressionRowsChained" if is_chained else "LinearRegressionRowsSingle",
+        "yFields": y_field_names,
+        "xField": x_field_name,
+        "covFields": cov_field_names,
+        "rowBlockSize": block_size,
+        "passThrough": [f for f in row_fields if f not in mt.row_key],
+    }
+    from . import plugin
+    ht = plugin.matrix_to_table_apply(selected, config, weights=w_vals, kernel=_kernel, log10_p=_log10_p,
+                                      stream_block=_stream_block, stream_depth=_stream_depth, guard=_guard, sharded=_sharded)
+    if not y_is_list:   # SG:404-406
+        fields = STAT_FIELDS + (["log10_p"] if _log10_p else [])
+        ht = ht.annotate(**{f: ht[f][:, 0] for f in fields})
+    return ht
+
+
+_uid = itertools.count()
+
+
+def _execute(mt, x, y_vals, cov_vals, is_chained, pass_through_names, *, weights=None, kernel="auto", log10_p=False,
+             stream_block=0, stream_depth=0, guard=True, sharded=False) -> Table:
+    """The body of LinearRegressionRowsSingle / Chained `execute` (LR:46-195 / 226-407): driver prologue on the host,
+    the per-partition loop on the device.  `y_vals` is a list of groups, each a list of float64 column arrays; returns
+    the Table with array-valued statistics ([M, P] per group; a ChainedField over groups when `is_chained`)."""
     n_cols = mt.count_cols()
     cov = np.column_stack(cov_vals) if cov_vals else np.empty((n_cols, 0))
+    w_vals = [None] * len(y_vals) if weights is None else weights
     from .genotypes import DenseDosage, HostBedGenotypes
+
+    def make_bases():
+        return [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None, w_vals[i])
+                for i, g in enumerate(y_vals)]
 
     if isinstance(mt.genotypes, DenseDosage) or x.kind == "dosage":
         if not isinstance(mt.genotypes, DenseDosage) or x.kind != "dosage":
             raise ExpressionException("'linear_regression_rows/x': a dense dosage field needs a DenseDosage entry matrix")
-        bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None, w_vals[i])
-                 for i, g in enumerate(y_vals)]
-        outs = _run_device_dense(mt.genotypes, bases)
+        outs = _run_device_dense(mt.genotypes, make_bases())
         torch.cuda.synchronize(mt.genotypes.device)
         host = [{k: v.cpu().numpy() for k, v in o.items()} for o in outs]
-    elif isinstance(mt.genotypes, HostBedGenotypes):
+    elif isinstance(mt.genotypes, HostBedGenotypes) and mt.genotypes.nbytes >= _STREAM_MIN_BYTES:
         # host-resident .bed rows: stream them through the device; the copies start before the prologue
-        stream = _HostStream(mt.genotypes, _stream_block, _stream_depth)
+        stream = _HostStream(mt.genotypes, stream_block, stream_depth)
         try:
-            bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None, w_vals[i])
-                     for i, g in enumerate(y_vals)]
-            host = stream.run(bases, kernel=_kernel, want_log10_p=_log10_p)
+            host = stream.run(make_bases(), kernel=kernel, want_log10_p=log10_p)
         finally:
             stream.close()
-    elif _sharded:
+    elif sharded:
         import torch.distributed as tdist
 
         from .dist import ShardedRegression
         if weights is not None:
             raise NotImplementedError("linear_regression_rows: weights= with _sharded=True")
-        sr = ShardedRegression(mt.genotypes)
-        bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None)
-                 for i, g in enumerate(y_vals)] if tdist.get_rank() == 0 else None
-        sr.set_bases(bases)
-        outs = sr.run(kernel=_kernel, want_log10_p=_log10_p)
+        sr = ShardedRegression(mt.genotypes, transport="peer" if sharded == "peer" else "nccl")
+        sr.set_bases(make_bases() if tdist.get_rank() == 0 else None)
+        outs = sr.run(kernel=kernel, want_log10_p=log10_p)
         torch.cuda.synchronize(mt.genotypes.device)
         host = [{k: v.cpu().numpy() for k, v in o.items()} for o in outs]
     else:
-        bases = [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None, w_vals[i])
-                 for i, g in enumerate(y_vals)]
-        outs = _run_device(mt.genotypes, bases, kernel=_kernel, want_log10_p=_log10_p, guard=_guard)
-        torch.cuda.synchronize(mt.genotypes.device)
+        # (a small host-resident .bed goes to the device in one piece: the streaming machinery -- four streams, a slot
+        # ring, a page-locked result buffer -- costs more than a sweep of a few megabytes)
+        g = mt.genotypes.to_device() if isinstance(mt.genotypes, HostBedGenotypes) else mt.genotypes
+        outs = _run_device(g, make_bases(), kernel=kernel, want_log10_p=log10_p, guard=guard)
+        torch.cuda.synchronize(g.device)
         host = [{k: v.cpu().numpy() for k, v in o.items()} for o in outs]
 
     fields = OrderedDict()
     for k in mt.row_key:
         fields[k] = mt.row[k]
-    for k, v in row_fields.items():
-        fields[k] = v
+    for k in pass_through_names:
+        fields[k] = mt.row[k]
+    stat_names = STAT_FIELDS + (["log10_p"] if log10_p else [])
     if is_chained:  # LR:208-216
         fields["n"] = np.stack([h["n"] for h in host], axis=1)
         fields["sum_x"] = np.stack([h["sum_x"] for h in host], axis=1)
-        for f in STAT_FIELDS:
+        for f in stat_names:
             fields[f] = ChainedField(h[f] for h in host)
-        if _log10_p:
-            fields["log10_p"] = ChainedField(h["log10_p"] for h in host)
-    else:
+    else:           # LR:26-34: array<float64> of length P per row
         h = host[0]
         fields["n"] = h["n"]
         fields["sum_x"] = h["sum_x"]
-        for f in STAT_FIELDS + (["log10_p"] if _log10_p else []):
-            fields[f] = h[f] if y_is_list else h[f][:, 0]  # SG:404-406
+        for f in stat_names:
+            fields[f] = h[f]
     t = Table(fields, key=mt.row_key, n_rows=mt.count_rows())
     t.n_missing = [h["n_missing"] for h in host] if is_chained else host[0]["n_missing"]
-    t.sharded = bool(_sharded)
+    t.sharded = bool(sharded)
     return t
+
+
+_STREAM_MIN_BYTES = 64 << 20
 
 
 def lambda_gc(p_value, approximate=True, device=0) -> float:

@@ -191,3 +191,35 @@ def test_neighbour_calls_validate_before_any_device_work():
         hb.hwe_normalized_pca(x, k=2)
     with pytest.raises(TypeError):
         hb.hwe_normalized_pca(mt.GT, k=2.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# the plugin entry: config dict -> relational function, by name (RelationalFunctions.scala:112-138)
+def test_plugin_lookup_by_config_name_and_schema():
+    import json
+
+    import pytest
+
+    from hail_b200 import plugin
+
+    cfg = {"name": "LinearRegressionRowsSingle", "yFields": ["__y_0", "__y_1"], "xField": "__uid_x", "covFields": ["__cov0"],
+           "rowBlockSize": 16, "passThrough": ["rsid"]}
+    f = plugin.lookup_matrix_to_table(cfg)
+    assert isinstance(f, plugin.LinearRegressionRowsSingle) and f.preserves_partition_counts()
+    assert isinstance(plugin.lookup_matrix_to_table(json.dumps(cfg)), plugin.LinearRegressionRowsSingle)   # the JSON the JVM sees
+
+    class _G:   # a MatrixTable needs only its shape here
+        n_variants, n_samples = 3, 4
+    mt = plugin.MatrixTable(_G(), rows={"locus": [1, 2, 3], "rsid": ["a", "b", "c"]}, row_key=("locus",))
+    # result schema: key, pass-through, then the statistics in the reference's order (LR:26-42)
+    assert f.typ(mt) == ["locus", "rsid", "n", "sum_x", "y_transpose_x", "beta", "standard_error", "t_stat", "p_value"]
+    ch = plugin.lookup_matrix_to_table({**cfg, "name": "LinearRegressionRowsChained", "yFields": [["__y_0_0"], ["__y_1_0", "__y_1_1"]]})
+    assert isinstance(ch, plugin.LinearRegressionRowsChained) and ch.chained
+    with pytest.raises(ValueError, match="no MatrixToTableFunction registered"):
+        plugin.lookup_matrix_to_table({**cfg, "name": "PoissonRegression"})
+    with pytest.raises(ValueError, match="bad config"):
+        plugin.lookup_matrix_to_table({k: v for k, v in cfg.items() if k != "covFields"})
+    with pytest.raises(ValueError, match="yFields"):
+        plugin.lookup_matrix_to_table({**cfg, "name": "LinearRegressionRowsChained"})   # chained needs lists of lists
+    with pytest.raises(KeyError, match="no column field"):
+        f.execute(mt)

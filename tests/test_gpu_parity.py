@@ -660,3 +660,26 @@ def test_logistic_score_vs_oracle_and_errors():
     # the context is usable for the linear path afterwards
     lin = hb.linear_regression_rows(mt.y2, mt.GT.n_alt_alleles(), [1.0, mt.c1])
     assert np.isfinite(lin.beta).sum() > 0.9 * M
+
+
+def test_plugin_config_entry_equals_the_public_call():
+    """the config dict of statgen.py:394-401, applied through the registry (plugin.matrix_to_table_apply),
+    gives the rows of the public call; Single returns array-valued statistics (LR:26-34), the wrapper unwraps them."""
+    hb = _hb()
+    from hail_b200 import plugin
+    N, M = 500, 40
+    rng = np.random.default_rng(21)
+    x = rng.integers(0, 3, size=(M, N)).astype(np.float64)
+    x[rng.random(x.shape) < 0.05] = np.nan
+    mt = _mt_from_dosage(x, y=rng.normal(size=N), y2=rng.normal(size=N), c=rng.normal(size=N))
+    ht = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=[1.0, mt.c], pass_through=["qual"])
+    sel = mt.annotate_cols(__y_0=mt.y, __cov0=1.0, __cov1=mt.c).annotate_entries(__x=mt.GT.n_alt_alleles())
+    cfg = {"name": "LinearRegressionRowsSingle", "yFields": ["__y_0"], "xField": "__x", "covFields": ["__cov0", "__cov1"],
+           "rowBlockSize": 16, "passThrough": ["qual"]}
+    raw = plugin.matrix_to_table_apply(sel, cfg)
+    assert raw.row == plugin.lookup_matrix_to_table(cfg).typ(sel) == ht.row
+    assert raw.beta.shape == (M, 1) and np.array_equal(raw.beta[:, 0], ht.beta, equal_nan=True)
+    assert np.array_equal(raw.p_value[:, 0], ht.p_value, equal_nan=True) and np.array_equal(raw.n, ht.n)
+    ch = plugin.matrix_to_table_apply(sel.annotate_cols(__y_1_0=mt.y2, __y_0_0=mt.y),
+                                      {**cfg, "name": "LinearRegressionRowsChained", "yFields": [["__y_0_0"], ["__y_1_0"]]})
+    assert ch.n.shape == (M, 2) and np.array_equal(ch.beta[0][:, 0], ht.beta, equal_nan=True)
