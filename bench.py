@@ -392,11 +392,13 @@ def run_ours(a):
         barrier()
         reps = 5
         times = []
+        h2d_in_call = []
         for _ in range(reps):     # each repetition is timed on its own: barrier, wall clock around the public call, barrier
             t_e = time.time()
             ht = e2e_step()
             barrier()
             times.append(time.time() - t_e)
+            h2d_in_call.append(float(lib.lrr_last_stream_h2d_ms(ctx.handle)))
         # the host link is shared with other tenants of the box: single repetitions are occasionally 2x slower.  The
         # reported value uses the MEDIAN repetition; the mean is kept next to it.
         tt = torch.tensor(times, dtype=torch.float64, device=dev)
@@ -414,6 +416,8 @@ def run_ours(a):
                          "mean_value": world * Me * float(n_kept) / dt_mean, "rep_seconds": [round(t, 4) for t in times],
                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                          "h2d_gbps_achieved": round(h2d / dt / 1e9, 2), "h2d_gbps_link_alone": round(h2d_alone, 2),
+                         "h2d_window_ms_in_call": [round(v, 1) for v in h2d_in_call],
+                         "h2d_gbps_in_call": round(Me * bed_stride / (float(np.median(h2d_in_call)) / 1e3) / 1e9, 2) if min(h2d_in_call) > 0 else None,
                          "stage_seconds": stages, "slowest_stage": max(stages, key=stages.get),
                          "sample": f"{Me} variants x {N} samples per GPU per step: page-locked host .bed bytes -> "
                                    "HostBedGenotypes -> linear_regression_rows (block-streamed H2D overlapped with the "

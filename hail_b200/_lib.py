@@ -101,6 +101,7 @@ SIGNATURES = {
                                       ctypes.c_int32]),
     "lrr_stream_end": (None, [ctypes.c_void_p, ctypes.c_void_p]),
     "lrr_trim": (ctypes.c_int, [ctypes.c_void_p]),
+    "lrr_last_stream_h2d_ms": (ctypes.c_float, [ctypes.c_void_p]),
     "lrr_set_score_model": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_void_p]),

@@ -86,6 +86,7 @@ struct Ctx {
   void* arena = nullptr;
   size_t arena_bytes = 0;
   int streams_alive = 0;
+  float last_stream_h2d_ms = -1.f;   // first block copy issued -> last block copy done, of the last lrr_stream_run
   // dense-dosage path: one bit per (variant, sample) "missing and in the group" (dense_kernel.cu), grow-only
   void* d_nanmask = nullptr;
   size_t nanmask_bytes = 0;

@@ -50,6 +50,7 @@ struct Stream {
   ResultBuf res[N_RES];
   int64_t next_load = 0;   // next block to copy + pack
   bool ran = false;
+  cudaEvent_t h2d_first = nullptr, h2d_last = nullptr;   // timing events around the first / last block copy (measurement)
 };
 
 namespace {
@@ -62,8 +63,10 @@ int issue_load(Stream* s, int64_t b) {
   const int k = (int)(b % std::min<int64_t>(N_STAGE, s->n_blocks)), slot = (int)(b % s->depth);
   const int64_t rows = rows_of(s, b);
   if (s->stage_used[k]) LRR_CUDA(c, cudaStreamWaitEvent(s->s_h2d, s->stage_free[k], 0));
+  if (b == 0 && s->h2d_first) LRR_CUDA(c, cudaEventRecord(s->h2d_first, s->s_h2d));
   LRR_CUDA(c, cudaMemcpyAsync(s->d_stage[k], s->h_bed + b * s->block * s->bed_stride, (size_t)(rows * s->bed_stride),
                               cudaMemcpyHostToDevice, s->s_h2d));
+  if (b == s->n_blocks - 1 && s->h2d_last) LRR_CUDA(c, cudaEventRecord(s->h2d_last, s->s_h2d));
   LRR_CUDA(c, cudaEventRecord(s->stage_loaded[k], s->s_h2d));
   LRR_CUDA(c, cudaStreamWaitEvent(s->s_pack, s->stage_loaded[k], 0));
   if (s->slot_swept_valid[slot]) LRR_CUDA(c, cudaStreamWaitEvent(s->s_pack, s->swept[slot], 0));   // slot still being read
@@ -88,6 +91,8 @@ void destroy(Stream* s) {
     if (s->stage_free[k]) cudaEventDestroy(s->stage_free[k]);
   }
   // the staging / slot memory is the context's arena: it stays allocated for the next stream (lrr_destroy frees it)
+  if (s->h2d_first) cudaEventDestroy(s->h2d_first);
+  if (s->h2d_last) cudaEventDestroy(s->h2d_last);
   for (auto e : s->packed) if (e) cudaEventDestroy(e);
   for (auto e : s->swept) if (e) cudaEventDestroy(e);
   for (auto& r : s->res) {
@@ -192,6 +197,8 @@ int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64
   TRY(cudaStreamCreateWithFlags(&s->s_pack, cudaStreamNonBlocking));
   TRY(cudaStreamCreateWithFlags(&s->s_comp, cudaStreamNonBlocking));
   TRY(cudaStreamCreateWithFlags(&s->s_d2h, cudaStreamNonBlocking));
+  TRY(cudaEventCreate(&s->h2d_first));
+  TRY(cudaEventCreate(&s->h2d_last));
   // one arena for the staging buffers and the slots, cached on the context across streams (cudaMalloc / cudaFree of
   // tens of GB would otherwise sit in front of the first copy of every call)
   const int n_stage = (int)std::min<int64_t>(N_STAGE, s->n_blocks);
@@ -301,11 +308,19 @@ int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs
   c->timing = timing;
   cudaError_t e = cudaStreamSynchronize(s->s_d2h);
   cudaError_t e2 = cudaStreamSynchronize(s->s_comp);
+  c->last_stream_h2d_ms = -1.f;
+  if (rc == LRR_OK && s->h2d_first && s->h2d_last && cudaEventSynchronize(s->h2d_last) == cudaSuccess) {
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, s->h2d_first, s->h2d_last) == cudaSuccess) c->last_stream_h2d_ms = ms;
+    else cudaGetLastError();
+  }
   if (rc == LRR_OK && e != cudaSuccess) rc = cuda_fail(c, e, "cudaStreamSynchronize(d2h)");
   if (rc == LRR_OK && e2 != cudaSuccess) rc = cuda_fail(c, e2, "cudaStreamSynchronize(comp)");
   return rc;
 }
 LRR_ABI_CATCH(ctx)
+
+float lrr_last_stream_h2d_ms(const lrr_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->last_stream_h2d_ms : -1.f; }
 
 int lrr_trim(lrr_ctx* ctx) try {
   if (!ctx) return LRR_EINVAL;

@@ -900,6 +900,8 @@ struct State {
   bool prepared = false;
   bool usable = false;
   bool wide = false;             // the prepared plan uses wide one-plane-only passes
+  unsigned long long* d_bound = nullptr;   // scratch of acc_bound_kernel (grow-only)
+  size_t bound_bytes = 0;
   int32_t* d_any = nullptr;      // scratch of any_flag_kernel
   int32_t* h_any = nullptr;      // page-locked
   std::string why;
@@ -1139,9 +1141,17 @@ static int prepare(Ctx* c, bool wide) {
   LRR_CUDA(c, cudaGetLastError());
   {
     // exactness guard: no f32 accumulator can leave the exactly-representable range, whatever the genotypes are
-    unsigned long long* d_bound = nullptr;
-    LRR_CUDA(c, cudaMalloc(&d_bound, sizeof(unsigned long long) * 2 * (size_t)total_rows));
-    LRR_CUDA(c, cudaMemset(d_bound, 0, sizeof(unsigned long long) * 2 * (size_t)total_rows));
+    // (grow-only scratch kept on the state: a cudaFree here would wait for every copy the streaming loop has in flight)
+    const size_t bound_bytes = sizeof(unsigned long long) * 2 * (size_t)total_rows;
+    if (bound_bytes > s->bound_bytes) {
+      cudaFree(s->d_bound);
+      s->d_bound = nullptr;
+      s->bound_bytes = 0;
+      LRR_CUDA(c, cudaMalloc(&s->d_bound, bound_bytes));
+      s->bound_bytes = bound_bytes;
+    }
+    unsigned long long* d_bound = s->d_bound;
+    LRR_CUDA(c, cudaMemsetAsync(d_bound, 0, bound_bytes, 0));
     const unsigned gxq = (unsigned)std::max<int64_t>(1, std::min<int64_t>((row_bytes / 16 + 255) / 256, 64));
     for (int64_t r0 = 0; r0 < total_rows; r0 += 65535)
       acc_bound_kernel<<<dim3(gxq, (unsigned)std::min<int64_t>(total_rows - r0, 65535)), 256>>>(s->d_bq + r0 * row_bytes,
@@ -1149,7 +1159,6 @@ static int prepare(Ctx* c, bool wide) {
     c->launches++;
     std::vector<unsigned long long> h_bound(2 * (size_t)total_rows);
     cudaError_t e = cudaMemcpy(h_bound.data(), d_bound, sizeof(unsigned long long) * h_bound.size(), cudaMemcpyDeviceToHost);
-    cudaFree(d_bound);
     if (e != cudaSuccess) return cuda_fail(c, e, "tc4 acc_bound_kernel");
     unsigned long long worst = 0;
     for (unsigned long long v : h_bound) worst = std::max(worst, v);
@@ -1272,6 +1281,7 @@ void tc4_release(Ctx* c) {
   tc4::State* s = static_cast<tc4::State*>(c->tc4_state);
   tc4::free_prepared(s);
   cudaFree(s->d_any);
+  cudaFree(s->d_bound);
   if (s->h_any) cudaFreeHost(s->h_any);
   delete s;
   c->tc4_state = nullptr;

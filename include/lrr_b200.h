@@ -181,6 +181,9 @@ int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64
                      int64_t n_samples, int64_t block_variants, int32_t depth);
 int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs, int32_t n_outs, int32_t kernel);
 void lrr_stream_end(lrr_ctx* ctx, lrr_stream* stream);
+/* measurement hook: device time from the start of the first block's host-to-device copy to the end of the last one, of
+ * the last lrr_stream_run (milliseconds; negative if none) -- what the host link gave the call */
+float lrr_last_stream_h2d_ms(const lrr_ctx* ctx);
 /* The streaming arena (staging buffers + slots, up to 16 GB and never more than half of the free device memory) and the
  * dense path's missing-bit plane stay cached on the context between calls; lrr_trim gives them back to the device
  * (synchronises; LRR_ESTATE while a stream is open).  lrr_destroy frees everything. */

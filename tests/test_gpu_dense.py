@@ -179,3 +179,36 @@ def test_lambda_gc():   # statgen.py:3096-3128
     assert np.isnan(hb.lambda_gc(np.array([np.nan])))
     # uniform p-values: no inflation
     assert abs(hb.lambda_gc(rng.random(200001)) - 1.0) < 0.02
+
+
+def test_dense_infinite_entries_follow_the_reference():
+    """An infinite entry is a DEFINED value in the reference (RU:16-58 only imputes missing ones): sum_x = +-Inf (NaN when
+    both signs occur), x.x = Inf and every statistic NaN (Inf - Inf).  The other rows of the same CTA are untouched, and
+    an infinite entry of a sample OUTSIDE the group (missing phenotype) changes nothing."""
+    hb = _hb()
+    rng = np.random.default_rng(31)
+    N, M = 900, 70
+    x = rng.uniform(0, 2, size=(M, N))
+    x[rng.random(x.shape) < 0.02] = np.nan
+    y = rng.normal(size=N)
+    y[5] = np.nan                      # sample 5 is outside the group
+    base = hb.linear_regression_rows(y=_dense_mt(x, y=y, c=np.arange(N) / N).y, x=_dense_mt(x, y=y, c=np.arange(N) / N).x,
+                                     covariates=[1.0, _dense_mt(x, y=y, c=np.arange(N) / N).c])
+    xi = x.copy()
+    xi[3, 17] = np.inf
+    xi[9, 100] = -np.inf
+    xi[20, 40], xi[20, 41] = np.inf, -np.inf
+    xi[33, 5] = np.inf                 # outside the group: ignored
+    mt = _dense_mt(xi, y=y, c=np.arange(N) / N)
+    ht = hb.linear_regression_rows(y=mt.y, x=mt.x, covariates=[1.0, mt.c])
+    assert ht.sum_x[3] == np.inf and ht.sum_x[9] == -np.inf and np.isnan(ht.sum_x[20])
+    for row in (3, 9, 20):
+        for f in ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+            assert np.isnan(ht[f][row]), (row, f)
+    assert np.array_equal(ht.n_missing, np.isnan(x[:, np.arange(N) != 5]).sum(axis=1))   # Inf is not a missing entry
+    others = np.setdiff1d(np.arange(M), [3, 9, 20])
+    for f in ("sum_x", "y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+        assert np.array_equal(ht[f][others], base[f][others], equal_nan=True), f
+    # what the reference's float64 algebra gives for such a row (oracle, same semantics)
+    want = O.linreg_group(xi, y[:, None], np.column_stack([np.ones(N), np.arange(N) / N]))
+    assert np.isnan(want["beta"][[3, 9, 20], 0]).all() and want["sum_x"][3] == np.inf

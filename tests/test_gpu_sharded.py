@@ -86,3 +86,26 @@ def test_sharded_call_equals_single_device_bit_for_bit(tmp_path):
         for g in range(2):
             for f in ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
                 assert np.array_equal(z[f"{f}{g}"], one[f][g], equal_nan=True), (kernel, f, g)
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_dense_and_packed_paths_on_a_second_device_in_one_process():
+    """Kernel attributes (dynamic shared memory limits) are per device: after device 0 has run every path, device 1 must
+    run them too inside the same process (the dense sweep needs 143-184 KB of dynamic shared memory)."""
+    import hail_b200 as hb
+    rng = np.random.default_rng(2)
+    N, M = 3000, 600
+    x = rng.integers(0, 3, size=(M, N)).astype(np.float64)
+    x[rng.random(x.shape) < 0.03] = np.nan
+    y, c = rng.normal(size=N), rng.normal(size=N)
+    res = []
+    for dev in (0, 1):
+        d = hb.MatrixTable(hb.DenseDosage(x, device=dev), cols={"y": y, "c": c})
+        hd = hb.linear_regression_rows(y=d.y, x=d.x, covariates=[1.0, d.c])
+        g = hb.MatrixTable(hb.PackedGenotypes.from_dosage(np.where(np.isnan(x), -1, x).astype(np.int8), device=dev), cols={"y": y, "c": c})
+        hp = [hb.linear_regression_rows(y=g.y, x=g.GT.n_alt_alleles(), covariates=[1.0, g.c], _kernel=k) for k in ("fp64", "tc4", "tc")]
+        res.append((hd, hp))
+    for f in ("beta", "standard_error", "p_value", "sum_x"):
+        assert np.array_equal(res[0][0][f], res[1][0][f], equal_nan=True), f
+        for a, b in zip(res[0][1], res[1][1]):
+            assert np.array_equal(a[f], b[f], equal_nan=True), f
