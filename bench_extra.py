@@ -32,18 +32,29 @@ def covariates(n, k, seed=0):
     return np.column_stack([np.ones(n)] + [rng.normal(size=n) for _ in range(k - 1)]), rng
 
 
-def bench_dense(N, M, K, missing):
+def bench_dense(N, M, K, missing, compact=False):
     import hail_b200 as hb
     from hail_b200 import _lib, statgen
     from hail_b200.statgen import GroupBasis
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev)
     g.manual_seed(1)
-    x = torch.rand((M, N), device=dev, dtype=torch.float64, generator=g) * 2
-    x[torch.rand((M, N), device=dev, generator=g) < missing] = float("nan")
     cov, rng = covariates(N, K)
     y = rng.normal(size=(N, 1))
-    dd = hb.DenseDosage(x, 0)
+    if compact:   # uniform dosages as uint16 entries (value = q * scale, 0xFFFF = missing), drawn on the device row block by row block
+        scale = 2.0 / 65534.0
+        ld = (N + 7) // 8 * 8
+        xq = torch.zeros((M, ld), dtype=torch.int16, device=dev)
+        for lo in range(0, M, 1024):
+            hi = min(M, lo + 1024)
+            q = torch.randint(0, 65535, (hi - lo, N), device=dev, generator=g, dtype=torch.int32)
+            q[torch.rand((hi - lo, N), device=dev, generator=g) < missing] = 65535
+            xq[lo:hi, :N] = torch.where(q >= 32768, q - 65536, q).to(torch.int16)    # the bits of the uint16 value
+        del q
+    else:
+        x = torch.rand((M, N), device=dev, dtype=torch.float64, generator=g) * 2
+        x[torch.rand((M, N), device=dev, generator=g) < missing] = float("nan")
+        dd = hb.DenseDosage(x, 0)
     ctx = _lib.context(0)
     statgen._push_groups(ctx, N, [GroupBasis(y, cov, np.arange(N), None)])
     o = {"n": torch.empty(M, dtype=torch.int32, device=dev), "n_missing": torch.empty(M, dtype=torch.int32, device=dev),
@@ -57,7 +68,10 @@ def bench_dense(N, M, K, missing):
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def run():
-        ctx.check(ctx.lib.lrr_run_dense(ctx.handle, dd.data.data_ptr(), M, N, N, arr, 1, stream))
+        if compact:
+            ctx.check(ctx.lib.lrr_run_dense_u16(ctx.handle, xq.data_ptr(), M, ld, N, scale, arr, 1, stream))
+        else:
+            ctx.check(ctx.lib.lrr_run_dense(ctx.handle, dd.data.data_ptr(), M, N, N, arr, 1, stream))
 
     for _ in range(3):
         run()
@@ -71,14 +85,15 @@ def bench_dense(N, M, K, missing):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    bytes_alg = M * N * 8 + M * (4 + 4 + 8 + 5 * 8)
+    bytes_alg = M * N * (2 if compact else 8) + M * (4 + 4 + 8 + 5 * 8)
     peak, src = hbm_peak()
     ach = bytes_alg / ms / 1e6
-    return {"metric": "entries/sec (variants x samples) for linear_regression_rows on a dense float64 x", "value": M * N / ms * 1e3,
+    return {"metric": "entries/sec (variants x samples) for linear_regression_rows on a dense " + ("uint16 (compact)" if compact else "float64") + " x",
+            "value": M * N / ms * 1e3,
             "unit": "entries/s", "n_gpus": 1, "steps": reps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True,
-            "dtype": "f64", "data": "synthetic (uniform dosages in [0, 2], generated in HBM)",
-            "config": {"workload": f"dense x: {N} samples x {M} variants, P=1, K={K}", "missing_rate": missing,
-                       "l2": "inputs larger than L2 (%.1f GB)" % (M * N * 8 / 1e9)},
+            "dtype": "f64 arithmetic" + (", u16 storage" if compact else ""), "data": "synthetic (uniform dosages in [0, 2], generated in HBM)",
+            "config": {"workload": f"dense x ({'uint16' if compact else 'float64'} entries): {N} samples x {M} variants, P=1, K={K}", "missing_rate": missing,
+                       "l2": "inputs larger than L2 (%.1f GB)" % (M * N * (2 if compact else 8) / 1e9)},
             "gpu_launches": int(ctx.launch_count - l0),
             "roofline": {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                          "traffic": None, "kernel": "dense sweep + imputation + statistics (whole call)",
@@ -132,6 +147,8 @@ def main():
     if "dense" in which:
         for miss in (0.0, 0.01):
             print(json.dumps(bench_dense(N, 4736, 10, miss)), flush=True)
+        for miss in (0.0, 0.01):
+            print(json.dumps(bench_dense(N, 4736 * 4, 10, miss, compact=True)), flush=True)
     if "logistic" in which:
         for test in ("score", "wald", "lrt", "firth"):
             print(json.dumps(bench_logistic(N, 2048, 10, test)), flush=True)

@@ -9,7 +9,7 @@ from .statgen import FatalError, lambda_gc, linear_regression_rows, _get_regress
 
 
 def __getattr__(name):  # lazy: these import torch-side helpers
-    if name in ("PackedGenotypes", "HostBedGenotypes", "DenseDosage", "packed_stride"):
+    if name in ("PackedGenotypes", "HostBedGenotypes", "DenseDosage", "CompactDosage", "packed_stride"):
         from . import genotypes
         return getattr(genotypes, name)
     if name in ("import_plink", "export_plink", "import_fam"):

@@ -76,6 +76,8 @@ SIGNATURES = {
                                ctypes.c_void_p]),
     "lrr_run_dense": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.POINTER(GroupOut), ctypes.c_int32, ctypes.c_void_p]),
+    "lrr_run_dense_u16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                         ctypes.c_double, ctypes.POINTER(GroupOut), ctypes.c_int32, ctypes.c_void_p]),
     "lrr_set_logit_model": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_double]),
@@ -102,11 +104,14 @@ SIGNATURES = {
     "lrr_stream_end": (None, [ctypes.c_void_p, ctypes.c_void_p]),
     "lrr_trim": (ctypes.c_int, [ctypes.c_void_p]),
     "lrr_last_stream_h2d_ms": (ctypes.c_float, [ctypes.c_void_p]),
+    "lrr_last_stream_timeline": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "lrr_set_score_model": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_void_p]),
     "lrr_run_score": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "lrr_run_score_dense": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                           ctypes.c_void_p, ctypes.c_void_p]),
     "lrr_student_t_two_sided": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double,
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 }

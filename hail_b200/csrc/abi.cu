@@ -70,17 +70,69 @@ void free_workspace(Ctx* c) {
   c->dots_offset.clear();
 }
 
-// scatter compact per-kept-sample columns into zero-initialised full-width planes and build the sample mask
-__global__ void scatter_basis_kernel(const double* __restrict__ cols, int C, int n, const int32_t* __restrict__ idx,
-                                     int64_t ns_pad, double* __restrict__ basis, uint32_t* __restrict__ mask) {
+// scatter compact per-kept-sample columns into zero-initialised full-width planes and build the sample mask.  The
+// columns come from up to four sources (covariate block, phenotype block, and the two extra columns of weighted /
+// score groups); a source may be device memory or page-locked host memory mapped into the device's address space.
+struct ScatterSrc {
+  const double* ptr[4];
+  int first[5];   // source k holds columns [first[k], first[k + 1])
+};
+
+__global__ void scatter_basis_kernel(ScatterSrc src, int C, int n, const int32_t* __restrict__ idx, int64_t ns_pad,
+                                     double* __restrict__ basis, uint32_t* __restrict__ mask) {
   const int64_t total = (int64_t)C * n;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i / n);
     const int j = (int)(i - (int64_t)c * n);
     const int64_t s = idx[j];
-    basis[(int64_t)c * ns_pad + s] = cols[i];
+    const int k = c < src.first[1] ? 0 : c < src.first[2] ? 1 : c < src.first[3] ? 2 : 3;
+    basis[(int64_t)c * ns_pad + s] = src.ptr[k][(int64_t)(c - src.first[k]) * n + j];
     if (c == 0) atomicOr(mask + (s >> 4), 1u << sample_shift((int)(s & 15)));
   }
+}
+
+__global__ void copy_doubles_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// Where lrr_add_group's input arrays are read from.  HOST arrays are copied (by the CPU) into a page-locked buffer that is
+// mapped into the device's address space, and the kernels above read it over PCIe directly: a cudaMemcpy would queue behind
+// every host-to-device copy the streaming loop has in flight on the same copy engine (lrr_stream_begin runs first) and the
+// first sweep could not start before the last genotype block had arrived.  DEVICE arrays are read in place.
+struct Staging {
+  Ctx* c;
+  size_t off = 0;
+  explicit Staging(Ctx* ctx) : c(ctx) {}
+  static bool on_device(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+  }
+  // device-readable pointer to `bytes` at `p` (NULL on allocation failure; *err is set then)
+  const void* in(const void* p, size_t bytes, cudaError_t* err) {
+    if (!p || bytes == 0 || on_device(p)) return p;
+    const size_t at = (off + 255) / 256 * 256;
+    memcpy(static_cast<char*>(c->h_stage) + at, p, bytes);
+    off = at + bytes;
+    (void)err;
+    return static_cast<const char*>(c->d_stage_view) + at;
+  }
+};
+
+int ensure_staging(Ctx* c, size_t bytes) {
+  // the previous lrr_add_group's kernels may still be reading the buffer
+  if (c->stage_ev_valid) LRR_CUDA(c, cudaEventSynchronize(c->stage_ev));
+  if (bytes <= c->h_stage_bytes) return LRR_OK;
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  c->h_stage = nullptr;
+  c->h_stage_bytes = 0;
+  LRR_CUDA(c, cudaHostAlloc(&c->h_stage, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+  LRR_CUDA(c, cudaHostGetDevicePointer(&c->d_stage_view, c->h_stage, 0));
+  c->h_stage_bytes = bytes;
+  return LRR_OK;
 }
 
 // grow-only: [G][rows] counts / flag arrays and [sum_g (C_g + 2)][rows] dot products
@@ -301,7 +353,8 @@ void lrr_destroy(lrr_ctx* ctx) try {
   DeviceGuard guard(c->device);
   for (auto& g : c->groups) free_group(g);
   for (auto& g : c->spare) free_group(g);
-  cudaFree(c->d_scratch);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->stage_ev) cudaEventDestroy(c->stage_ev);
   cudaFree(c->d_recompute);
   if (c->busy_ev) cudaEventDestroy(c->busy_ev);
   if (c->ready_ev) cudaEventDestroy(c->ready_ev);
@@ -451,11 +504,9 @@ static int add_group_impl(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int3
   g.lbeta = log_beta_half(0.5 * (double)d);
   g.ns_pad = lrr_packed_stride(n_samples_total) * 4;
 
-  // steady state: no cudaMalloc and no device synchronisation here.  The staging scratch is grow-only, the four group
-  // buffers come from a retired group when one is large enough, and the copies / kernels below run on the default
-  // stream behind busy_ev (the last run that may still read those buffers on another stream).
-  const size_t idx_bytes = (sizeof(int32_t) * (size_t)n + 255) / 256 * 256;
-  const size_t cols_bytes = sizeof(double) * (size_t)g.C * (size_t)n;
+  // steady state: no cudaMalloc, no cudaMemcpy and no device synchronisation here.  The four group buffers come from a
+  // retired group when one is large enough, host inputs travel through the mapped staging buffer (Staging above), and the
+  // kernels below run on the default stream behind busy_ev (the last run that may still read those buffers elsewhere).
   const size_t basis_bytes = sizeof(double) * (size_t)g.C * (size_t)g.ns_pad;
   const size_t mask_bytes = sizeof(uint32_t) * (size_t)(g.ns_pad / 16);
   const size_t n_qty = qty_len >= 0 ? (size_t)qty_len : (size_t)K * P;
@@ -468,17 +519,35 @@ static int add_group_impl(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int3
   };
   cudaError_t e;
 #define TRY(call) if ((e = (call)) != cudaSuccess) return bail(e, #call)
-  if (c->busy_valid) TRY(cudaStreamWaitEvent(0, c->busy_ev, 0));
-  if (idx_bytes + cols_bytes > c->scratch_bytes) {
-    TRY(cudaDeviceSynchronize());
-    cudaFree(c->d_scratch);
-    c->d_scratch = nullptr;
-    c->scratch_bytes = 0;
-    TRY(cudaMalloc(&c->d_scratch, idx_bytes + cols_bytes));
-    c->scratch_bytes = idx_bytes + cols_bytes;
+  // weighted / score groups: column C-2 = sqrt(w), column C-1 = w (host arithmetic on n values)
+  std::vector<double> sw, w;
+  if (sqrt_w) {
+    sw.resize((size_t)n);
+    w.resize((size_t)n);
+    TRY(cudaMemcpy(sw.data(), sqrt_w, sizeof(double) * (size_t)n, cudaMemcpyDefault));
+    for (int i = 0; i < n; ++i) w[(size_t)i] = sw[(size_t)i] * sw[(size_t)i];
+    if (w_col) TRY(cudaMemcpy(w.data(), w_col, sizeof(double) * (size_t)n, cudaMemcpyDefault));
   }
-  int32_t* d_idx = static_cast<int32_t*>(c->d_scratch);
-  double* d_cols = reinterpret_cast<double*>(static_cast<char*>(c->d_scratch) + idx_bytes);
+  const size_t stage_need = sizeof(int32_t) * (size_t)n + sizeof(double) * ((size_t)g.C * (size_t)n + n_qty + n_yyp) + 8 * 256;
+  if (int r = ensure_staging(c, stage_need)) {
+    free_group(g);
+    return r;
+  }
+  Staging stage(c);
+  const int32_t* v_idx = static_cast<const int32_t*>(stage.in(complete_idx, sizeof(int32_t) * (size_t)n, &e));
+  ScatterSrc src;
+  src.ptr[0] = static_cast<const double*>(stage.in(q_cols, sizeof(double) * (size_t)g.Kd * (size_t)n, &e));
+  src.ptr[1] = static_cast<const double*>(stage.in(y_res, sizeof(double) * (size_t)P * (size_t)n, &e));
+  src.ptr[2] = sqrt_w ? static_cast<const double*>(stage.in(sw.data(), sizeof(double) * (size_t)n, &e)) : nullptr;
+  src.ptr[3] = sqrt_w ? static_cast<const double*>(stage.in(w.data(), sizeof(double) * (size_t)n, &e)) : nullptr;
+  src.first[0] = 0;
+  src.first[1] = g.Kd;
+  src.first[2] = g.Kd + P;
+  src.first[3] = g.Kd + P + (sqrt_w ? 1 : 0);
+  src.first[4] = g.C;
+  const double* v_qty = static_cast<const double*>(stage.in(qty, sizeof(double) * n_qty, &e));
+  const double* v_yyp = static_cast<const double*>(stage.in(yyp, sizeof(double) * n_yyp, &e));
+  if (c->busy_valid) TRY(cudaStreamWaitEvent(0, c->busy_ev, 0));
   for (size_t i = 0; i < c->spare.size(); ++i) {
     const Group& sp = c->spare[i];
     if (sp.cap_basis >= basis_bytes && sp.cap_mask >= mask_bytes && sp.cap_qty >= qty_bytes && sp.cap_yyp >= yyp_bytes &&
@@ -497,29 +566,21 @@ static int add_group_impl(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int3
     TRY(cudaMalloc(&g.d_yyp, yyp_bytes));
     g.cap_basis = basis_bytes; g.cap_mask = mask_bytes; g.cap_qty = qty_bytes; g.cap_yyp = yyp_bytes;
   }
-  TRY(cudaMemcpyAsync(d_idx, complete_idx, sizeof(int32_t) * (size_t)n, cudaMemcpyDefault, 0));
-  if (g.Kd > 0) TRY(cudaMemcpyAsync(d_cols, q_cols, sizeof(double) * (size_t)g.Kd * n, cudaMemcpyDefault, 0));
-  TRY(cudaMemcpyAsync(d_cols + (size_t)g.Kd * n, y_res, sizeof(double) * (size_t)P * n, cudaMemcpyDefault, 0));
-  if (sqrt_w) {   // column C-2 = sqrt(w), column C-1 = w
-    std::vector<double> sw(n), w(n);
-    TRY(cudaMemcpy(sw.data(), sqrt_w, sizeof(double) * (size_t)n, cudaMemcpyDefault));
-    for (int i = 0; i < n; ++i) w[i] = sw[i] * sw[i];
-    if (w_col) TRY(cudaMemcpy(w.data(), w_col, sizeof(double) * (size_t)n, cudaMemcpyDefault));
-    TRY(cudaMemcpy(d_cols + (size_t)(g.Kd + P) * n, sw.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
-    TRY(cudaMemcpy(d_cols + (size_t)(g.Kd + P + 1) * n, w.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
-  }
   TRY(cudaMemsetAsync(g.d_basis, 0, basis_bytes, 0));
   TRY(cudaMemsetAsync(g.d_mask, 0, mask_bytes, 0));
-  if (n_qty) TRY(cudaMemcpyAsync(g.d_qty, qty, sizeof(double) * n_qty, cudaMemcpyDefault, 0));
-  TRY(cudaMemcpyAsync(g.d_yyp, yyp, sizeof(double) * n_yyp, cudaMemcpyDefault, 0));
+  if (n_qty) copy_doubles_kernel<<<(unsigned)std::min<size_t>((n_qty + 255) / 256, 1024), 256>>>(g.d_qty, v_qty, (int64_t)n_qty);
+  copy_doubles_kernel<<<(unsigned)std::min<size_t>((n_yyp + 255) / 256, 1024), 256>>>(g.d_yyp, v_yyp, (int64_t)n_yyp);
   {
     const int64_t total = (int64_t)g.C * n;
     int grid = (int)((total + 255) / 256);
     if (grid > 65535) grid = 65535;
-    scatter_basis_kernel<<<grid, 256>>>(d_cols, g.C, n, d_idx, g.ns_pad, g.d_basis, g.d_mask);
-    c->launches++;
+    scatter_basis_kernel<<<grid, 256>>>(src, g.C, n, v_idx, g.ns_pad, g.d_basis, g.d_mask);
+    c->launches += 3;
     TRY(cudaGetLastError());
   }
+  if (!c->stage_ev) TRY(cudaEventCreateWithFlags(&c->stage_ev, cudaEventDisableTiming));
+  TRY(cudaEventRecord(c->stage_ev, 0));
+  c->stage_ev_valid = true;
   if (!c->ready_ev) TRY(cudaEventCreateWithFlags(&c->ready_ev, cudaEventDisableTiming));
   TRY(cudaEventRecord(c->ready_ev, 0));
   c->ready_valid = true;
@@ -580,11 +641,33 @@ int lrr_run_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t l
   if (n_variants == 0) return LRR_OK;
   if (!d_x) return fail(c, LRR_EINVAL, "lrr_run_dense: d_x is NULL");
   if (int r = ensure_workspace(c, n_variants)) return r;
+  if (int r = run_begin(c, st)) return r;
   if (int r = launch_dense_sweep(c, d_x, n_variants, ldx, st)) return r;
   c->last_kernel = LRR_KERNEL_FP64;
   for (size_t g = 0; g < c->groups.size(); ++g)
     if (int r = launch_stats_epilogue(c, (int)g, n_variants, outs[g], st, true)) return r;
-  return LRR_OK;
+  return run_end(c, st);
+}
+LRR_ABI_CATCH(ctx)
+
+int lrr_run_dense_u16(lrr_ctx* ctx, const uint16_t* d_xq, int64_t n_variants, int64_t ldx, int64_t n_samples_total, double scale,
+                      const lrr_group_out* outs, int32_t n_outs, void* stream) try {
+  CTX_PROLOGUE;
+  if (c->groups.empty()) return fail(c, LRR_ESTATE, "lrr_run_dense_u16: no groups (call lrr_add_group)");
+  if (c->groups[0].score) return fail(c, LRR_ESTATE, "lrr_run_dense_u16: the context holds a logistic score model");
+  if (n_outs != (int32_t)c->groups.size() || !outs) return fail(c, LRR_EINVAL, "lrr_run_dense_u16: need one lrr_group_out per group");
+  if (n_variants < 0 || ldx < n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_dense_u16: bad shape (ldx >= n_samples_total)");
+  if (!(scale > 0.0)) return fail(c, LRR_EINVAL, "lrr_run_dense_u16: scale must be positive");
+  if (n_samples_total != c->n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_dense_u16: n_samples_total differs from the groups'");
+  if (n_variants == 0) return LRR_OK;
+  if (!d_xq) return fail(c, LRR_EINVAL, "lrr_run_dense_u16: d_xq is NULL");
+  if (int r = ensure_workspace(c, n_variants)) return r;
+  if (int r = run_begin(c, st)) return r;
+  if (int r = launch_dense_sweep(c, nullptr, n_variants, ldx, st, d_xq, scale)) return r;
+  c->last_kernel = LRR_KERNEL_FP64;
+  for (size_t g = 0; g < c->groups.size(); ++g)
+    if (int r = launch_stats_epilogue(c, (int)g, n_variants, outs[g], st, true)) return r;
+  return run_end(c, st);
 }
 LRR_ABI_CATCH(ctx)
 
@@ -601,9 +684,29 @@ int lrr_run_score(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_fl
   if (n_variants == 0) return LRR_OK;
   if (!d_packed) return fail(c, LRR_EINVAL, "lrr_run_score: d_packed is NULL");
   if (int r = ensure_workspace(c, n_variants)) return r;
+  if (int r = run_begin(c, st)) return r;
   if (int r = launch_fp64_sweep(c, d_packed, n_variants, packed_stride, st)) return r;
   c->last_kernel = LRR_KERNEL_FP64;
-  return launch_score_epilogue(c, n_variants, *out, st);
+  if (int r = launch_score_epilogue(c, n_variants, *out, st)) return r;
+  return run_end(c, st);
+}
+LRR_ABI_CATCH(ctx)
+
+int lrr_run_score_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t ldx, int64_t n_samples_total,
+                        const lrr_score_out* out, void* stream) try {
+  CTX_PROLOGUE;
+  if (c->groups.size() != 1 || !c->groups[0].score) return fail(c, LRR_ESTATE, "lrr_run_score_dense: call lrr_set_score_model first");
+  if (!out) return fail(c, LRR_EINVAL, "lrr_run_score_dense: out is NULL");
+  if (n_variants < 0 || ldx < n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_score_dense: bad shape (ldx >= n_samples_total)");
+  if (n_samples_total != c->n_samples_total) return fail(c, LRR_EINVAL, "lrr_run_score_dense: n_samples_total differs from the model's");
+  if (n_variants == 0) return LRR_OK;
+  if (!d_x) return fail(c, LRR_EINVAL, "lrr_run_score_dense: d_x is NULL");
+  if (int r = ensure_workspace(c, n_variants)) return r;
+  if (int r = run_begin(c, st)) return r;
+  if (int r = launch_dense_sweep(c, d_x, n_variants, ldx, st)) return r;
+  c->last_kernel = LRR_KERNEL_FP64;
+  if (int r = launch_score_epilogue(c, n_variants, *out, st, true)) return r;
+  return run_end(c, st);
 }
 LRR_ABI_CATCH(ctx)
 

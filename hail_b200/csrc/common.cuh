@@ -86,6 +86,8 @@ struct Ctx {
   void* arena = nullptr;
   size_t arena_bytes = 0;
   int streams_alive = 0;
+  std::vector<float> stream_timeline;   // lrr_set_timing(1): per block of the last lrr_stream_run, ms since the first copy
+                                        // started: [copy done, sweep started, statistics done]
   float last_stream_h2d_ms = -1.f;   // first block copy issued -> last block copy done, of the last lrr_stream_run
   // dense-dosage path: one bit per (variant, sample) "missing and in the group" (dense_kernel.cu), grow-only
   void* d_nanmask = nullptr;
@@ -104,8 +106,11 @@ struct Ctx {
   // cudaMalloc in the steady state.  Retired groups keep their buffers for the next lrr_add_group, the workspaces are
   // grow-only, and ordering against kernels still in flight on the caller's streams is done with two events.
   std::vector<Group> spare;         // retired groups (buffers only)
-  void* d_scratch = nullptr;        // add_group staging: kept sample indices + compact columns
-  size_t scratch_bytes = 0;
+  void* h_stage = nullptr;          // add_group staging: page-locked host buffer mapped into the device (see abi.cu Staging)
+  void* d_stage_view = nullptr;     // its device address
+  size_t h_stage_bytes = 0;
+  cudaEvent_t stage_ev = nullptr;   // the kernels reading the staging buffer have finished
+  bool stage_ev_valid = false;
   cudaEvent_t busy_ev = nullptr;    // recorded on the caller's stream after the last run that read the group buffers
   cudaEvent_t ready_ev = nullptr;   // recorded on the default stream after the last lrr_add_group's device work
   bool busy_valid = false, ready_valid = false;
@@ -159,7 +164,9 @@ int launch_unpack_bed(Ctx*, const uint8_t*, int64_t, int64_t, int64_t, uint8_t*,
 int launch_bn_fill(Ctx*, const uint32_t*, int, const uint8_t*, int64_t, int64_t, int64_t, uint64_t, uint8_t*, int64_t,
                    uint8_t*, cudaStream_t);
 int launch_fp64_sweep(Ctx*, const uint8_t* d_packed, int64_t M, int64_t stride, cudaStream_t);
-int launch_dense_sweep(Ctx*, const double* d_x, int64_t M, int64_t ldx, cudaStream_t);
+// d_xq != NULL: compact uint16 entries (value = q * xscale, 0xFFFF = missing) instead of the float64 d_x
+int launch_dense_sweep(Ctx*, const double* d_x, int64_t M, int64_t ldx, cudaStream_t, const uint16_t* d_xq = nullptr,
+                       double xscale = 0.0);
 int launch_tc_sweep(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, cudaStream_t);
 bool tc_supported(Ctx*, bool may_have_missing);
 const double* tc_quantum(Ctx*, int g);
@@ -183,7 +190,7 @@ int run_rows(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t 
              const lrr_group_out* outs, int32_t n_outs, int32_t kernel, cudaStream_t);
 int launch_student_t(Ctx*, const double*, int64_t, double, double*, double*, cudaStream_t);
 int launch_qchisqtail1(Ctx*, const double* d_p, int64_t count, double* d_out, cudaStream_t);
-int launch_score_epilogue(Ctx*, int64_t M, const lrr_score_out& out, cudaStream_t);
+int launch_score_epilogue(Ctx*, int64_t M, const lrr_score_out& out, cudaStream_t, bool dense = false);
 int logit_set_model(Ctx*, int64_t n_samples_total, int32_t n, int32_t K, const int32_t* idx, const double* cov, const double* y,
                     const double* b0, const double* score0, const double* fisher0, double loglk0);
 int logit_run(Ctx*, const uint8_t* d_packed, const double* d_dense, int64_t M, int64_t stride, int64_t n_samples_total,

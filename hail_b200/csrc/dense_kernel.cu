@@ -33,7 +33,9 @@ constexpr int CHUNK = 64;        // samples per step (two per lane)
 constexpr int STAGES = 8;        // cp.async ring depth (16 KB of x + 5 KB of basis per stage)
 
 struct DenseArgs {
-  const double* x;       // [M][ldx]
+  const double* x;       // [M][ldx]  (float64 input)
+  const uint16_t* xq;    // [M][ldx]  (compact input: entry = xq * xscale, 0xFFFF = missing), exclusive with x
+  double xscale;
   int64_t M, ldx, n_total;
   int64_t ns_pad;
   const double* basis;   // [C][ns_pad]
@@ -87,11 +89,18 @@ __device__ __forceinline__ bool not_finite(double v) { return (__double2hiint(v)
 //   dot warps      (8 x 4 variants) then read clean data on stage k: acc[r][c] += basis[c][j] * x[r][j] and, with the
 //                  group's 0 / 1 indicator column staged next to the basis, sum += ind[j] * x[r][j] and
 //                  squares += (ind[j] * x[r][j]) * x[r][j]  (samples outside the group have zero basis rows)
-template <int CB, bool FIRST, bool VEC, bool SQ>
+// XK: how x arrives -- 0: float64, 8-byte copies; 1: float64, 16-byte copies (aligned rows); 2: compact uint16 entries
+// (value = q * xscale, 0xFFFF = missing; 16-byte copies of 8 entries into a raw region of the stage, converted to float64
+// by the stat warps one stage ahead of the dot warps, which never see the difference).
+template <int CB, bool FIRST, int XK, bool SQ>
 __global__ void __launch_bounds__(THREADS, 1) dense_sweep_kernel(DenseArgs a) {
-  extern __shared__ __align__(16) double s_ring[];   // STAGES x { x [VT][CHUNK], indicator [CHUNK], basis [CB][CHUNK] }
-  constexpr int STAGE_DOUBLES = (VT + 1 + CB) * CHUNK;
+  extern __shared__ __align__(16) double s_ring[];   // STAGES x { x [VT][CHUNK], indicator [CHUNK], basis [CB][CHUNK], raw u16 }
+  constexpr bool VEC = XK == 1;
+  constexpr bool U16 = XK == 2;
+  constexpr int RAW_DOUBLES = U16 ? VT * CHUNK / 4 : 0;
+  constexpr int STAGE_DOUBLES = (VT + 1 + CB) * CHUNK + RAW_DOUBLES;
   constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * 8;
+  constexpr uint32_t RAW_OFF = (uint32_t)((VT + 1 + CB) * CHUNK) * 8u;   // byte offset of the raw region inside a stage
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int64_t v0 = (int64_t)blockIdx.x * VT;
@@ -167,21 +176,25 @@ __global__ void __launch_bounds__(THREADS, 1) dense_sweep_kernel(DenseArgs a) {
     const int t = threadIdx.x - DOT_WARPS * 32;
     constexpr int LT = STAT_WARPS * 32;   // loader threads
     const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(s_ring);
-    constexpr int X_ELEMS = VEC ? VT * CHUNK / 2 : VT * CHUNK;         // x copies per stage
+    constexpr int X_ELEMS = U16 ? VT * CHUNK / 8 : VEC ? VT * CHUNK / 2 : VT * CHUNK;         // x copies per stage
     static_assert(X_ELEMS % LT == 0, "every loader thread issues the same number of x copies");
     constexpr int XI = X_ELEMS / LT;
-    const double* xsrc[XI];
+    constexpr int XBYTES = U16 ? 2 : 8;   // bytes per entry in global memory
+    const char* xsrc[XI];
     uint32_t xdst[XI];   // byte offset inside a stage
+    int xl[XI];          // first entry of the copy within its chunk
 #pragma unroll
     for (int i = 0; i < XI; ++i) {
       const int idx = t + i * LT;
-      const int r = VEC ? idx >> 5 : idx >> 6;
-      const int l = VEC ? (idx & 31) * 2 : idx & 63;
+      const int r = U16 ? idx >> 3 : VEC ? idx >> 5 : idx >> 6;
+      const int l = U16 ? (idx & 7) * 8 : VEC ? (idx & 31) * 2 : idx & 63;
       int64_t vv = v0 + r;
       if (vv >= a.M) vv = a.M - 1;   // clamp: copies stay in bounds, stores are skipped
-      xsrc[i] = a.x + vv * a.ldx + l;
-      xdst[i] = (uint32_t)(r * CHUNK + l) * 8u;
+      xsrc[i] = (U16 ? reinterpret_cast<const char*>(a.xq) : reinterpret_cast<const char*>(a.x)) + (vv * a.ldx + l) * XBYTES;
+      xdst[i] = U16 ? RAW_OFF + (uint32_t)(r * CHUNK + l) * 2u : (uint32_t)(r * CHUNK + l) * 8u;
+      xl[i] = l;
     }
+    const char* const xbase = U16 ? reinterpret_cast<const char*>(a.xq) : reinterpret_cast<const char*>(a.x);
     // column copies: slot 0 = the group indicator, slot 1 + c = basis column c0 + c (all 128-bit, ns_pad is padded)
     constexpr int BI = ((1 + CB) * (CHUNK / 2) + LT - 1) / LT;
     const double* bsrc[BI];
@@ -202,19 +215,22 @@ __global__ void __launch_bounds__(THREADS, 1) dense_sweep_kernel(DenseArgs a) {
       if (chunk < n_full) {
 #pragma unroll
         for (int i = 0; i < XI; ++i) {
-          if (VEC) cp_async16_full(st + xdst[i], xsrc[i]);
+          if (VEC || U16) cp_async16_full(st + xdst[i], xsrc[i]);
           else cp_async8_full(st + xdst[i], xsrc[i]);
         }
       } else {   // the last, partial chunk: zero-fill past the last sample
 #pragma unroll
         for (int i = 0; i < XI; ++i) {
-          const int64_t left = a.n_total - (chunk * CHUNK + (int64_t)((xdst[i] >> 3) & (CHUNK - 1)));
-          if (VEC) {
+          const int64_t left = a.n_total - (chunk * CHUNK + (int64_t)xl[i]);
+          if (U16) {
+            const int bytes = left >= 8 ? 16 : (left > 0 ? (int)left * 2 : 0);
+            cp_async16(st + xdst[i], bytes ? xsrc[i] : xbase, bytes);
+          } else if (VEC) {
             const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
-            cp_async16(st + xdst[i], bytes ? xsrc[i] : a.x, bytes);
+            cp_async16(st + xdst[i], bytes ? xsrc[i] : xbase, bytes);
           } else {
             const int bytes = left >= 1 ? 8 : 0;
-            cp_async8(st + xdst[i], bytes ? xsrc[i] : a.x, bytes);
+            cp_async8(st + xdst[i], bytes ? xsrc[i] : xbase, bytes);
           }
         }
       }
@@ -222,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_sweep_kernel(DenseArgs a) {
       for (int i = 0; i < BI; ++i)
         if (bok[i]) cp_async16_full(st + bdst[i], bsrc[i]);
 #pragma unroll
-      for (int i = 0; i < XI; ++i) xsrc[i] += CHUNK;
+      for (int i = 0; i < XI; ++i) xsrc[i] += CHUNK * XBYTES;
 #pragma unroll
       for (int i = 0; i < BI; ++i) bsrc[i] += CHUNK;
     };
@@ -246,6 +262,21 @@ __global__ void __launch_bounds__(THREADS, 1) dense_sweep_kernel(DenseArgs a) {
       }
 #pragma unroll
       for (int r = 0; r < SVW; ++r) {
+        if (U16) {
+          // compact entries: convert this lane's two entries to float64 (missing -> 0 + its bit), always written
+          const uint32_t q2 = *reinterpret_cast<const uint32_t*>(
+              reinterpret_cast<const char*>(s_ring + slot * STAGE_DOUBLES) + RAW_OFF + ((sw * SVW + r) * CHUNK + lane * 2) * 2);
+          const uint32_t q0 = q2 & 0xFFFFu, q1 = q2 >> 16;
+          const bool m0 = q0 == 0xFFFFu, m1 = q1 == 0xFFFFu;
+          *reinterpret_cast<double2*>(st + r * CHUNK) = make_double2(m0 ? 0.0 : (double)q0 * a.xscale, m1 ? 0.0 : (double)q1 * a.xscale);
+          if (FIRST) {
+            const uint32_t b0 = __ballot_sync(0xffffffffu, g0 && m0), b1 = __ballot_sync(0xffffffffu, g1 && m1);
+            nm[r] += __popc(b0) + __popc(b1);
+            const int64_t vv = v0 + sw * SVW + r;
+            if (lane == 0 && vv < a.M) a.nanmask[vv * a.n_chunks + chunk] = make_uint2(b0, b1);
+          }
+          continue;
+        }
         double2 xv = *reinterpret_cast<const double2*>(st + r * CHUNK);
         bool m0 = not_finite(xv.x), m1 = not_finite(xv.y);
         if (m0 || m1) {
@@ -364,40 +395,50 @@ __global__ void indicator_kernel(const uint32_t* __restrict__ mask, int64_t ns_p
     out[j] = ((mask[j >> 4] >> sample_shift((int)(j & 15))) & 1u) ? 1.0 : 0.0;
 }
 
-template <int CB, bool FIRST, bool VEC, bool SQ>
+template <int CB, bool FIRST, int XK, bool SQ>
 cudaError_t launch_pass_v(const DenseArgs& a, int grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (VT + 1 + CB) * CHUNK * (int)sizeof(double);
+  constexpr int smem = STAGES * ((VT + 1 + CB) * CHUNK + (XK == 2 ? VT * CHUNK / 4 : 0)) * (int)sizeof(double);
   // the attribute is per device: set it on every launch (a host-side table write) instead of caching one flag per process
-  const cudaError_t e = cudaFuncSetAttribute(dense_sweep_kernel<CB, FIRST, VEC, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const cudaError_t e = cudaFuncSetAttribute(dense_sweep_kernel<CB, FIRST, XK, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  dense_sweep_kernel<CB, FIRST, VEC, SQ><<<grid, THREADS, smem, st>>>(a);
+  dense_sweep_kernel<CB, FIRST, XK, SQ><<<grid, THREADS, smem, st>>>(a);
   return cudaSuccess;
 }
 
 template <int CB, bool FIRST, bool SQ = false>
-cudaError_t launch_pass(const DenseArgs& a, bool vec, int grid, cudaStream_t st) {
-  return vec ? launch_pass_v<CB, FIRST, true, SQ>(a, grid, st) : launch_pass_v<CB, FIRST, false, SQ>(a, grid, st);
+cudaError_t launch_pass(const DenseArgs& a, int xk, int grid, cudaStream_t st) {
+  if (xk == 2) {
+    if constexpr (SQ) return cudaErrorNotSupported;   // (weighted groups take float64 x)
+    else return launch_pass_v<CB, FIRST, 2, false>(a, grid, st);
+  }
+  return xk == 1 ? launch_pass_v<CB, FIRST, 1, SQ>(a, grid, st) : launch_pass_v<CB, FIRST, 0, SQ>(a, grid, st);
 }
 
 template <bool FIRST>
-cudaError_t launch_pass_cb(const DenseArgs& a, int cb, bool vec, int grid, cudaStream_t st) {
+cudaError_t launch_pass_cb(const DenseArgs& a, int cb, int xk, int grid, cudaStream_t st) {
   if (a.sq_col >= 0) {   // weighted groups: fewer column-tile sizes (each is one more kernel to build)
-    if (cb <= 4) return launch_pass<4, FIRST, true>(a, vec, grid, st);
-    if (cb <= 8) return launch_pass<8, FIRST, true>(a, vec, grid, st);
-    return launch_pass<12, FIRST, true>(a, vec, grid, st);
+    if (cb <= 4) return launch_pass<4, FIRST, true>(a, xk, grid, st);
+    if (cb <= 8) return launch_pass<8, FIRST, true>(a, xk, grid, st);
+    return launch_pass<12, FIRST, true>(a, xk, grid, st);
   }
-  if (cb <= 2) return launch_pass<2, FIRST>(a, vec, grid, st);
-  if (cb <= 4) return launch_pass<4, FIRST>(a, vec, grid, st);
-  if (cb <= 6) return launch_pass<6, FIRST>(a, vec, grid, st);
-  if (cb <= 8) return launch_pass<8, FIRST>(a, vec, grid, st);
-  if (cb <= 10) return launch_pass<10, FIRST>(a, vec, grid, st);
-  return launch_pass<12, FIRST>(a, vec, grid, st);
+  if (cb <= 2) return launch_pass<2, FIRST>(a, xk, grid, st);
+  if (cb <= 4) return launch_pass<4, FIRST>(a, xk, grid, st);
+  if (cb <= 6) return launch_pass<6, FIRST>(a, xk, grid, st);
+  if (cb <= 8) return launch_pass<8, FIRST>(a, xk, grid, st);
+  if (cb <= 10) return launch_pass<10, FIRST>(a, xk, grid, st);
+  return launch_pass<12, FIRST>(a, xk, grid, st);
 }
 
 }  // namespace
 
-int launch_dense_sweep(Ctx* c, const double* d_x, int64_t M, int64_t ldx, cudaStream_t st) {
+int launch_dense_sweep(Ctx* c, const double* d_x, int64_t M, int64_t ldx, cudaStream_t st, const uint16_t* d_xq, double xscale) {
   if (M == 0) return LRR_OK;
+  if (d_xq) {
+    if (ldx % 8 != 0 || reinterpret_cast<uintptr_t>(d_xq) % 16 != 0)
+      return fail(c, LRR_EINVAL, "compact dosage rows must be 16-byte aligned (ldx a multiple of 8 entries)");
+    for (const Group& G : c->groups)
+      if (G.weighted) return fail(c, LRR_EINVAL, "weighted groups take float64 x (lrr_run_dense)");
+  }
   const int64_t n_total = c->n_samples_total;
   for (size_t g = 0; g < c->groups.size(); ++g) {
     Group& G = c->groups[g];
@@ -420,6 +461,8 @@ int launch_dense_sweep(Ctx* c, const double* d_x, int64_t M, int64_t ldx, cudaSt
     }
     DenseArgs a;
     a.x = d_x;
+    a.xq = d_xq;
+    a.xscale = xscale;
     a.M = M;
     a.ldx = ldx;
     a.n_total = n_total;
@@ -434,7 +477,7 @@ int launch_dense_sweep(Ctx* c, const double* d_x, int64_t M, int64_t ldx, cudaSt
     a.dots = c->d_dots + c->dots_offset[g];
     a.nanmask = reinterpret_cast<uint2*>(c->d_nanmask);
     a.n_chunks = n_chunks;
-    const bool vec = (ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0);
+    const int vec = d_xq ? 2 : ((ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0)) ? 1 : 0;
     const int grid = (int)((M + VT - 1) / VT);
     // column passes: one when C <= 12 (x is read once); otherwise passes of 12 re-read x
     int c0 = 0;

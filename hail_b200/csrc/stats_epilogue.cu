@@ -48,12 +48,13 @@ struct ScoreArgs {
   const double* aux;      // [K + 1]: u, a0
   int64_t M;
   int K;
+  int stride;             // doubles per dots row: K + 3 (packed sweep) or K + 5 (dense sweep)
   lrr_score_out out;
 };
 
 __global__ void score_epilogue_kernel(ScoreArgs a) {
   for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < a.M; v += (int64_t)gridDim.x * blockDim.x) {
-    const double* dv = a.dots + v * (a.K + 3);
+    const double* dv = a.dots + v * a.stride;
     const double s1 = dv[a.K], f11 = dv[a.K + 2];
     double quad = 0.0, fu = 0.0;
     for (int i = 0; i < a.K; ++i) {
@@ -139,7 +140,7 @@ int launch_stats_epilogue_listed(Ctx* c, int g, const lrr_group_out& out, int st
   return LRR_OK;
 }
 
-int launch_score_epilogue(Ctx* c, int64_t M, const lrr_score_out& out, cudaStream_t st) {
+int launch_score_epilogue(Ctx* c, int64_t M, const lrr_score_out& out, cudaStream_t st, bool dense) {
   if (M == 0) return LRR_OK;
   const Group& G = c->groups[0];
   ScoreArgs a;
@@ -149,6 +150,7 @@ int launch_score_epilogue(Ctx* c, int64_t M, const lrr_score_out& out, cudaStrea
   a.aux = G.d_yyp;
   a.M = M;
   a.K = G.K;
+  a.stride = G.C + (dense ? 2 : 0);
   a.out = out;
   int64_t grid = (M + 127) / 128;
   if (grid > (int64_t)c->sm_count * 32) grid = (int64_t)c->sm_count * 32;

@@ -51,6 +51,7 @@ struct Stream {
   int64_t next_load = 0;   // next block to copy + pack
   bool ran = false;
   cudaEvent_t h2d_first = nullptr, h2d_last = nullptr;   // timing events around the first / last block copy (measurement)
+  std::vector<cudaEvent_t> t_loaded, t_comp0, t_comp1;     // per block: copy done, sweep started, statistics done (c->timing only)
 };
 
 namespace {
@@ -67,6 +68,11 @@ int issue_load(Stream* s, int64_t b) {
   LRR_CUDA(c, cudaMemcpyAsync(s->d_stage[k], s->h_bed + b * s->block * s->bed_stride, (size_t)(rows * s->bed_stride),
                               cudaMemcpyHostToDevice, s->s_h2d));
   if (b == s->n_blocks - 1 && s->h2d_last) LRR_CUDA(c, cudaEventRecord(s->h2d_last, s->s_h2d));
+  if (c->timing && b < 4096) {
+    if ((int64_t)s->t_loaded.size() <= b) s->t_loaded.resize((size_t)b + 1, nullptr);
+    LRR_CUDA(c, cudaEventCreate(&s->t_loaded[(size_t)b]));
+    LRR_CUDA(c, cudaEventRecord(s->t_loaded[(size_t)b], s->s_h2d));
+  }
   LRR_CUDA(c, cudaEventRecord(s->stage_loaded[k], s->s_h2d));
   LRR_CUDA(c, cudaStreamWaitEvent(s->s_pack, s->stage_loaded[k], 0));
   if (s->slot_swept_valid[slot]) LRR_CUDA(c, cudaStreamWaitEvent(s->s_pack, s->swept[slot], 0));   // slot still being read
@@ -91,6 +97,8 @@ void destroy(Stream* s) {
     if (s->stage_free[k]) cudaEventDestroy(s->stage_free[k]);
   }
   // the staging / slot memory is the context's arena: it stays allocated for the next stream (lrr_destroy frees it)
+  for (auto* v : {&s->t_loaded, &s->t_comp0, &s->t_comp1})
+    for (auto e : *v) if (e) cudaEventDestroy(e);
   if (s->h2d_first) cudaEventDestroy(s->h2d_first);
   if (s->h2d_last) cudaEventDestroy(s->h2d_last);
   for (auto e : s->packed) if (e) cudaEventDestroy(e);
@@ -270,8 +278,17 @@ int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs
     cudaError_t e;
     if ((e = cudaStreamWaitEvent(s->s_comp, s->packed[slot], 0)) != cudaSuccess) { rc = cuda_fail(c, e, "wait packed"); break; }
     if (rb.used && (e = cudaStreamWaitEvent(s->s_comp, rb.copied, 0)) != cudaSuccess) { rc = cuda_fail(c, e, "wait copied"); break; }
+    if (timing && b < 4096) {
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
+        s->t_comp0.push_back(e0);
+        s->t_comp1.push_back(e1);
+        cudaEventRecord(e0, s->s_comp);
+      }
+    }
     rc = run_rows(c, s->d_packed[slot], s->d_flags[slot], rows, s->stride, s->N, rb.outs.data(), n_outs, kernel, s->s_comp);
     if (rc != LRR_OK) break;
+    if (timing && b < 4096 && (int64_t)s->t_comp1.size() == b + 1) cudaEventRecord(s->t_comp1[(size_t)b], s->s_comp);
 #define STEP(call) if ((e = (call)) != cudaSuccess) { rc = cuda_fail(c, e, #call); break; }
     STEP(cudaEventRecord(s->swept[slot], s->s_comp));
     s->slot_swept_valid[slot] = 1;
@@ -308,6 +325,18 @@ int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs
   c->timing = timing;
   cudaError_t e = cudaStreamSynchronize(s->s_d2h);
   cudaError_t e2 = cudaStreamSynchronize(s->s_comp);
+  c->stream_timeline.clear();
+  if (timing && rc == LRR_OK && s->h2d_first) {   // per block, milliseconds since the first copy started: copy done, sweep started, statistics done
+    cudaStreamSynchronize(s->s_comp);
+    for (size_t b = 0; b < s->t_comp1.size() && b < s->t_loaded.size(); ++b) {
+      float t[3] = {-1.f, -1.f, -1.f};
+      cudaEventElapsedTime(&t[0], s->h2d_first, s->t_loaded[b]);
+      cudaEventElapsedTime(&t[1], s->h2d_first, s->t_comp0[b]);
+      cudaEventElapsedTime(&t[2], s->h2d_first, s->t_comp1[b]);
+      c->stream_timeline.insert(c->stream_timeline.end(), t, t + 3);
+    }
+    cudaGetLastError();
+  }
   c->last_stream_h2d_ms = -1.f;
   if (rc == LRR_OK && s->h2d_first && s->h2d_last && cudaEventSynchronize(s->h2d_last) == cudaSuccess) {
     float ms = -1.f;
@@ -319,6 +348,14 @@ int lrr_stream_run(lrr_ctx* ctx, lrr_stream* stream, const lrr_group_out* h_outs
   return rc;
 }
 LRR_ABI_CATCH(ctx)
+
+int lrr_last_stream_timeline(const lrr_ctx* ctx, float* out, int capacity) {
+  if (!ctx) return 0;
+  const Ctx* c = reinterpret_cast<const Ctx*>(ctx);
+  const int n = (int)std::min<size_t>(c->stream_timeline.size(), capacity > 0 ? (size_t)capacity : 0);
+  if (out) memcpy(out, c->stream_timeline.data(), sizeof(float) * (size_t)n);
+  return (int)c->stream_timeline.size();
+}
 
 float lrr_last_stream_h2d_ms(const lrr_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->last_stream_h2d_ms : -1.f; }
 

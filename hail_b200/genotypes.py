@@ -197,6 +197,50 @@ class DenseDosage:
         return self.data.cpu().numpy()
 
 
+class CompactDosage:
+    """A dosage entry field stored as one uint16 per entry on the device: value = q * scale, q = 0xFFFF = missing
+    (include/lrr_b200.h lrr_run_dense_u16).  The compact form of `DenseDosage` for imputed data: BGEN's 8-bit genotype
+    probabilities give dosages that are exact multiples of 1/255 (`scale=1/255`, the default when every defined value
+    is one); otherwise `scale = 2/65534` stores any dosage in [0, 2] to 1.5e-5.  2 bytes of HBM per entry instead of 8.
+    The regression sees the DEQUANTISED values: `to_dosage()` returns exactly them."""
+
+    MISSING = 0xFFFF
+
+    def __init__(self, values, scale=None, device=0):
+        dev = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        v = np.asarray(values, dtype=np.float64)
+        assert v.ndim == 2
+        miss = np.isnan(v)
+        if scale is None:
+            q255 = np.where(miss, 0.0, v) * 255.0
+            scale = 1.0 / 255.0 if np.all(np.abs(q255 - np.rint(q255)) < 1e-9) else 2.0 / 65534.0
+        q = np.rint(np.where(miss, 0.0, v) / scale)
+        if q.min(initial=0.0) < 0 or q.max(initial=0.0) > 65534:
+            raise ValueError("CompactDosage: values must lie in [0, 65534 * scale]")
+        q = np.where(miss, self.MISSING, q).astype(np.uint16)
+        M, N = q.shape
+        ld = (N + 7) // 8 * 8
+        buf = np.zeros((M, ld), dtype=np.uint16)
+        buf[:, :N] = q
+        # (torch has no uint16 arithmetic, but it can hold the bytes: int16 view of the same bits)
+        self.data = torch.from_numpy(buf.view(np.int16)).to(dev).contiguous()
+        self.scale = float(scale)
+        self.ld = ld
+        self.n_variants, self.n_samples = int(M), int(N)
+
+    @property
+    def device(self):
+        return self.data.device
+
+    @property
+    def nbytes(self):
+        return self.data.numel() * 2
+
+    def to_dosage(self) -> np.ndarray:
+        q = self.data.cpu().numpy().view(np.uint16)[:, : self.n_samples].astype(np.float64)
+        return np.where(q == self.MISSING, np.nan, q * self.scale)
+
+
 def packed_stride(n_samples: int) -> int:
     return int(_lib.load().lrr_packed_stride(int(n_samples)))
 

@@ -123,8 +123,6 @@ def logistic_regression_rows(test, y, x, covariates, pass_through=(), *, max_ite
     dense = isinstance(g, DenseDosage)
     if dense != (x.kind == "dosage"):
         raise ExpressionException("'logistic_regression_rows/x': a dense dosage field needs a DenseDosage entry matrix")
-    if dense and test == "score":
-        raise NotImplementedError("logistic_regression_rows: test='score' on dense dosages")
     if isinstance(g, HostBedGenotypes):   # the score path sweeps a resident store
         g = g.to_device()
     dev = g.device
@@ -148,8 +146,11 @@ def logistic_regression_rows(test, y, x, covariates, pass_through=(), *, max_ite
                 ctx.check(ctx.lib.lrr_set_score_model(ctx.handle, N, n, k, idx.ctypes.data, wc.ctypes.data, resid.ctypes.data,
                                                       np.ascontiguousarray(w).ctypes.data, finv.ctypes.data,
                                                       np.ascontiguousarray(score).ctypes.data))
-                ctx.check(ctx.lib.lrr_run_score(ctx.handle, g.data.data_ptr(), g.flags_ptr(), M, g.stride, N,
-                                                ctypes.byref(out), stream))
+                if dense:
+                    ctx.check(ctx.lib.lrr_run_score_dense(ctx.handle, g.data.data_ptr(), M, N, N, ctypes.byref(out), stream))
+                else:
+                    ctx.check(ctx.lib.lrr_run_score(ctx.handle, g.data.data_ptr(), g.flags_ptr(), M, g.stride, N,
+                                                    ctypes.byref(out), stream))
                 torch.cuda.synchronize(dev)
                 chi[:, col] = d_chi.cpu().numpy()
                 pv[:, col] = d_p.cpu().numpy()

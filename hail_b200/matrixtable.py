@@ -145,10 +145,10 @@ class MatrixTable:
 
     def __getitem__(self, item):
         if item == "GT":
-            if type(self.genotypes).__name__ == "DenseDosage":
+            if type(self.genotypes).__name__ in ("DenseDosage", "CompactDosage"):
                 raise ExpressionException("this MatrixTable holds a dense dosage entry field `x`, not calls")
             return CallExpression(self)
-        if item in ("x", "dosage") and type(self.genotypes).__name__ == "DenseDosage":
+        if item in ("x", "dosage") and type(self.genotypes).__name__ in ("DenseDosage", "CompactDosage"):
             return EntryExpression(self, "dosage")   # a float64 entry field (statgen.py:229: any float64 x)
         if item in self._entry_aliases:
             return EntryExpression(self, self._entry_aliases[item])

@@ -339,7 +339,7 @@ class _HostStream:
 
 
 def _run_device_dense(dosage, bases):
-    """lrr_run_dense over a DenseDosage.  Returns per-group dicts of torch CUDA tensors."""
+    """lrr_run_dense over a DenseDosage (lrr_run_dense_u16 over a CompactDosage).  Returns per-group dicts of torch CUDA tensors."""
     dev = dosage.device
     ctx = _lib.context(dev.index)
     M, N = dosage.n_variants, dosage.n_samples
@@ -356,8 +356,12 @@ def _run_device_dense(dosage, bases):
                 setattr(arr[g], k, v.data_ptr())
             arr[g].log10_p = None
             outs.append(o)
-        ctx.check(ctx.lib.lrr_run_dense(ctx.handle, dosage.data.data_ptr(), M, N, N, arr, len(bases),
-                                        torch.cuda.current_stream(dev).cuda_stream))
+        if hasattr(dosage, "scale"):   # CompactDosage: uint16 entries
+            ctx.check(ctx.lib.lrr_run_dense_u16(ctx.handle, dosage.data.data_ptr(), M, dosage.ld, N, dosage.scale, arr, len(bases),
+                                                torch.cuda.current_stream(dev).cuda_stream))
+        else:
+            ctx.check(ctx.lib.lrr_run_dense(ctx.handle, dosage.data.data_ptr(), M, N, N, arr, len(bases),
+                                            torch.cuda.current_stream(dev).cuda_stream))
     return outs
 
 
@@ -458,7 +462,8 @@ def _execute(mt, x, y_vals, cov_vals, is_chained, pass_through_names, *, weights
     n_cols = mt.count_cols()
     cov = np.column_stack(cov_vals) if cov_vals else np.empty((n_cols, 0))
     w_vals = [None] * len(y_vals) if weights is None else weights
-    from .genotypes import DenseDosage, HostBedGenotypes
+    from .genotypes import CompactDosage, DenseDosage, HostBedGenotypes
+    DenseDosage = (DenseDosage, CompactDosage)   # both are dense entry fields; the device call differs (_run_device_dense)
 
     def make_bases():
         return [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None, w_vals[i])

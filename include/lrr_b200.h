@@ -154,6 +154,13 @@ int lrr_run_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t l
  * lrr_set_guard(ctx, 0) switches the guard off (kernel tuning, tests of the raw quantised path). */
 int lrr_set_guard(lrr_ctx* ctx, int enabled);
 int64_t lrr_last_recomputed(lrr_ctx* ctx);
+/* The dense call for a COMPACT dosage store (the 8 / 16-bit dosages of imputed data, io/bgen/): one
+ * uint16 per entry, entry value = q * scale, q = 0xFFFF = missing.  BGEN's 8-bit genotype probabilities give dosages that
+ * are exact multiples of 1/255 (q <= 510, scale = 1/255); any other float dosage is stored to 2/65534 (scale = 2/65534).
+ * d_xq is [n_variants, ldx] row-major with ldx a multiple of 8 entries and 16-byte aligned rows.  2 bytes of HBM per entry
+ * instead of 8; the results are those of lrr_run_dense on the dequantised values q * scale, bit for bit. */
+int lrr_run_dense_u16(lrr_ctx* ctx, const uint16_t* d_xq, int64_t n_variants, int64_t ldx, int64_t n_samples_total, double scale,
+                      const lrr_group_out* outs, int32_t n_outs, void* stream);
 /* number of kernel launches issued by this context since creation (for bench accounting) */
 int64_t lrr_launch_count(const lrr_ctx* ctx);
 /* which kernel LRR_KERNEL_AUTO resolved to on the last lrr_run */
@@ -184,6 +191,9 @@ void lrr_stream_end(lrr_ctx* ctx, lrr_stream* stream);
 /* measurement hook: device time from the start of the first block's host-to-device copy to the end of the last one, of
  * the last lrr_stream_run (milliseconds; negative if none) -- what the host link gave the call */
 float lrr_last_stream_h2d_ms(const lrr_ctx* ctx);
+/* with lrr_set_timing(ctx, 1): the block timeline of the last lrr_stream_run, three floats per block (milliseconds since
+ * the first copy started: copy done, sweep started, statistics done); copies up to `capacity` floats, returns the total */
+int lrr_last_stream_timeline(const lrr_ctx* ctx, float* out, int capacity);
 /* The streaming arena (staging buffers + slots, up to 16 GB and never more than half of the free device memory) and the
  * dense path's missing-bit plane stay cached on the context between calls; lrr_trim gives them back to the device
  * (synchronises; LRR_ESTATE while a stream is open).  lrr_destroy frees everything. */
@@ -207,6 +217,9 @@ int lrr_set_score_model(lrr_ctx* ctx, int64_t n_samples_total, int32_t n, int32_
                         const double* wc, const double* resid, const double* w, const double* finv, const double* score0);
 int lrr_run_score(lrr_ctx* ctx, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t n_variants, int64_t packed_stride,
                   int64_t n_samples_total, const lrr_score_out* out, void* stream);
+/* the same test for a dense float64 x ([n_variants, ldx] on the device, NaN = missing; pl_dosage / gp_dosage inputs) */
+int lrr_run_score_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int64_t ldx, int64_t n_samples_total,
+                        const lrr_score_out* out, void* stream);
 
 /* ---- logistic regression, Wald / likelihood-ratio / Firth tests (`hl.logistic_regression_rows(test='wald'|'lrt'|'firth')`)
  * The per-row loop of hail/hail/src/is/hail/methods/LogisticRegression.scala:115-157 with WaldTest, LikelihoodRatioTest and

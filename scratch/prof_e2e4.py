@@ -23,9 +23,13 @@ cov = np.column_stack([np.ones(N)] + [rng.standard_normal(N) for _ in range(K - 
 y = rng.standard_normal((N, 1))
 g = hb.HostBedGenotypes(h_bed, N, dev)
 out = []
-for rep in range(5):
+blocks = [int(v) for v in os.environ.get("BLOCKS", "0").split(",")]
+ctx.check(ctx.lib.lrr_set_timing(ctx.handle, 1))
+import ctypes
+for rep in range(3 * len(blocks) + 2):
+    blk = blocks[max(rep - 2, 0) // 3]
     t0 = time.perf_counter()
-    st = _HostStream(g)
+    st = _HostStream(g, block_variants=blk)
     t1 = time.perf_counter()
     bases = [GroupBasis(y, cov, np.arange(N))]
     t2 = time.perf_counter()
@@ -33,6 +37,11 @@ for rep in range(5):
     t3 = time.perf_counter()
     st.close()
     t4 = time.perf_counter()
-    out.append({"stream_begin_ms": 1e3 * (t1 - t0), "prologue_ms": 1e3 * (t2 - t1), "run_ms": 1e3 * (t3 - t2), "close_ms": 1e3 * (t4 - t3),
+    buf = (ctypes.c_float * 12288)()
+    nt = ctx.lib.lrr_last_stream_timeline(ctx.handle, buf, 12288)
+    tl = np.array(buf[:min(nt, 12288)]).reshape(-1, 3)
+    if rep == 3:
+        print("timeline (copy done, sweep started, statistics done) every 5th block:\n", np.round(tl[::5], 1))
+    out.append({"block": blk, "last_block_done_ms": float(tl[-1, 2]) if len(tl) else -1.0, "first_sweep_start_ms": float(tl[0, 1]) if len(tl) else -1.0, "stream_begin_ms": 1e3 * (t1 - t0), "prologue_ms": 1e3 * (t2 - t1), "run_ms": 1e3 * (t3 - t2), "close_ms": 1e3 * (t4 - t3),
                 "total_ms": 1e3 * (t4 - t0), "h2d_window_ms": float(ctx.lib.lrr_last_stream_h2d_ms(ctx.handle))})
-print(json.dumps(out, indent=1))
+print("\n".join(json.dumps({k: (round(v, 1) if isinstance(v, float) else v) for k, v in o.items()}) for o in out))

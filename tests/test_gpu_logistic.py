@@ -165,5 +165,66 @@ def test_wald_on_dense_dosages(which):   # TS:851-938, through DenseDosage -> lr
         assert conv[:2].all() or test == "firth", info
         for f in ("beta", "p_value"):
             _close(np.asarray(got[f])[:2][conv[:2]], want[f][:2][conv[:2]], 1e-5, f"{test} {f}")   # rows 6-10 are degenerate
-    with pytest.raises(NotImplementedError):
-        hb.logistic_regression_rows("score", mt.y, mt.x, [1.0, mt.c1, mt.c2])
+    # the score test on the same dense dosages (lrr_run_score_dense; LogisticRegressionModel.scala:211-264)
+    hs = hb.logistic_regression_rows("score", mt.y, mt.x, [1.0, mt.c1, mt.c2])
+    ws = L.logreg_score(dos, y, cov)
+    ok = np.isfinite(ws["chi_sq_stat"][:5])
+    _close(hs.chi_sq_stat[:5][ok], ws["chi_sq_stat"][:5][ok], 1e-6, "score chi2 dense")
+    _close(hs.p_value[:5][ok], ws["p_value"][:5][ok], 1e-5, "score p dense")
+
+
+def test_score_on_dense_dosages_vs_packed_and_oracle():
+    """The score test gives the same rows for a dense float64 field holding the hard calls as for the packed store, and
+    matches the oracle on real-valued dosages with missing entries."""
+    hb = _hb()
+    rng = np.random.default_rng(8)
+    N, M = 2500, 300
+    mt = hb.balding_nichols_model(3, N, M, missing_rate=0.03, seed=19)
+    dos = mt.genotypes.to_dosage().astype(np.float64)
+    dos[dos < 0] = np.nan
+    c1 = rng.normal(size=N)
+    yb = (rng.random(N) < 1 / (1 + np.exp(-(0.4 * np.nan_to_num(dos[3]) - 0.3 + 0.2 * c1)))).astype(np.float64)
+    mt = mt.annotate_cols(y=yb, c1=c1)
+    packed = hb.logistic_regression_rows("score", mt.y, mt.GT.n_alt_alleles(), [1.0, mt.c1])
+    dmt = hb.MatrixTable(hb.DenseDosage(dos), cols={"y": yb, "c1": c1})
+    dense = hb.logistic_regression_rows("score", dmt.y, dmt.x, [1.0, dmt.c1])
+    _close(dense.chi_sq_stat, packed.chi_sq_stat, 1e-9, "dense vs packed chi2")
+    soft = np.clip(dos + 0.05 * rng.normal(size=dos.shape), 0, 2)
+    smt = hb.MatrixTable(hb.DenseDosage(soft), cols={"y": yb, "c1": c1})
+    got = hb.logistic_regression_rows("score", smt.y, smt.x, [1.0, smt.c1])
+    want = L.logreg_score(soft, yb, np.column_stack([np.ones(N), c1]))
+    _close(got.chi_sq_stat, want["chi_sq_stat"], 1e-6, "soft dosage chi2")
+    _close(got.p_value, want["p_value"], 1e-5, "soft dosage p")
+
+
+def test_logistic_at_400k_samples_vs_oracle():
+    """The 256-thread float64 reductions of logit_fit_kernel and the score sweep at the BASELINE sample count."""
+    hb = _hb()
+    from hail_b200 import bn
+    N, M, K = 400_000, 24, 4
+    pop, th, _ = bn.bn_parameters(3, N, M, missing_rate=0.01, seed=23)
+    gt = bn.bn_fill(hb.PackedGenotypes.empty(M, N), pop, th, seed=23)
+    dos = gt.to_dosage().astype(np.float64)
+    dos[dos < 0] = np.nan
+    rng = np.random.default_rng(24)
+    cov = np.column_stack([np.ones(N)] + [rng.standard_normal(N) for _ in range(K - 1)])
+    eta = -0.5 + 0.03 * np.nan_to_num(dos[2]) + 0.2 * cov[:, 1]
+    yb = (rng.random(N) < 1 / (1 + np.exp(-eta))).astype(np.float64)
+    yb[rng.random(N) < 0.02] = np.nan
+    mt = hb.MatrixTable(gt, cols={"y": yb, **{f"c{i}": cov[:, i] for i in range(1, K)}})
+    covs = [1.0] + [mt[f"c{i}"] for i in range(1, K)]
+    for test in ("wald", "lrt", "score", "firth"):
+        ht = hb.logistic_regression_rows(test, mt.y, mt.GT.n_alt_alleles(), covs)
+        want = L.logreg_score(dos, yb, cov) if test == "score" else L.logreg_rows(test, dos, yb, cov)
+        conv = np.ones(M, dtype=bool) if test == "score" else (want["converged"] & ht.fit["converged"])
+        assert conv.sum() >= M - 1, test
+        for f in ("beta", "standard_error", "z_stat", "chi_sq_stat", "p_value"):
+            if f in want:
+                a, b = np.asarray(ht[f])[conv], np.asarray(want[f])[conv]
+                # (the LRT statistic is 2 (l1 - l0) with |l| ~ 2.7e5: below 1e-3 it is float64 roundoff in any implementation)
+                floor = 1e-3 if f == "chi_sq_stat" else 1e-6
+                big = np.abs(b) > floor if f in ("beta", "z_stat", "chi_sq_stat") else np.ones_like(b, dtype=bool)
+                if f == "p_value" and test in ("lrt", "firth"):
+                    big = np.asarray(want["chi_sq_stat"])[conv] > 1e-3
+                _close(a[big], b[big], 2e-6 if test != "firth" else 2e-5, f"400k {test} {f}")
+        assert int(np.nanargmin(ht.p_value)) == 2
