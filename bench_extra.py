@@ -114,8 +114,19 @@ def bench_logistic(N, M, K, test):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
     it = float(ht.fit["n_iterations"].mean()) if test != "score" else 0.0
+    # CPU baseline: the oracle's numpy restatement of the reference's per-row loop (LogisticRegression.scala:115-157) on a
+    # bounded sample of the same rows, host BLAS threads as configured ("port": the JVM reference cannot run here)
+    from oracle import logreg_oracle as LO
+    Ms = 8 if test != "score" else 32
+    dos = mt.genotypes.rows(0, Ms).to_dosage().astype(np.float64)
+    dos[dos < 0] = np.nan
+    t0 = time.perf_counter()
+    LO.logreg_score(dos, y, cov) if test == "score" else LO.logreg_rows(test, dos, y, cov)
+    dt_cpu = time.perf_counter() - t0
     return {"metric": f"genotypes/sec for logistic_regression_rows(test='{test}') through the public call (host null fit included)",
             "value": N * M / dt, "unit": "genotypes/s", "variants_per_s": M / dt, "n_gpus": 1, "seconds": dt, "higher_is_better": True,
+            "cpu_baseline": {"value": N * Ms / dt_cpu, "unit": "genotypes/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{Ms} variants x {N} samples, {dt_cpu:.1f} s, oracle/logreg_oracle.py (numpy, null fit included)"},
             "dtype": "f64", "data": "synthetic (seeded Balding-Nichols style, 1 % missing)", "mean_newton_iterations": it,
             "config": {"workload": f"logistic {test}: {N} samples x {M} variants, K={K}"}}
 

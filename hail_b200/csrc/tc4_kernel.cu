@@ -34,6 +34,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "tc_ptx.cuh"
 
 // Timing ablations (LRR_ABL_BITS / LRR_ABL_STREAM / LRR_ABL_CONTIG, see Params) are compiled in only with
@@ -56,6 +57,10 @@ namespace lrr {
 namespace tc4 {
 
 using namespace ptx;
+using tcc::IntTag;
+using tcc::TrueTag;
+using tcc::FalseTag;
+using tcc::EncodeTiledFn;
 
 constexpr int TILE_M = 128;            // variants per tile == TMEM lanes
 constexpr int CHUNK = 512;             // samples per genotype stage (128 packed bytes per row)
@@ -146,9 +151,6 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int m) {
   return d;                       // scale-factor ids 0
 }
 
-template <int V> struct IntTag { static constexpr int value = V; };
-struct TrueTag { static constexpr bool value = true; };
-struct FalseTag { static constexpr bool value = false; };
 
 struct Barriers {
   uint64_t gfull[MAX_GSTAGES];   // genotype stage filled by TMA
@@ -165,21 +167,8 @@ struct Barriers {
 };
 
 __device__ __forceinline__ bool tile_has_missing(const Params& p, int tile) {
-  const int64_t r0 = (int64_t)tile * TILE_M;
-  if (r0 >= p.M || p.one_plane_only) return false;   // padding tile of a pair; wide passes
-  if (!p.row_flags) return true;
-  uint32_t any = 0;
-  if (r0 + TILE_M <= p.M && ((reinterpret_cast<uintptr_t>(p.row_flags + r0) & 15) == 0)) {
-    const uint4* f = reinterpret_cast<const uint4*>(p.row_flags + r0);
-#pragma unroll
-    for (int i = 0; i < TILE_M / 16; ++i) {
-      const uint4 v = __ldg(f + i);
-      any |= v.x | v.y | v.z | v.w;
-    }
-  } else {
-    for (int64_t r = r0; r < p.M && r < r0 + TILE_M; ++r) any |= p.row_flags[r];
-  }
-  return any != 0;
+  if (p.one_plane_only) return false;   // wide passes: the host has checked the row flags
+  return tcc::tile_flags_any(p.row_flags, p.M, tile, TILE_M);
 }
 
 // NG = number of groups known at compile time (1, 2) or 0 = run-time p.n_groups; CS = 1 (one CTA per tile) or 2 (CTA
@@ -857,15 +846,6 @@ __global__ void acc_bound_kernel(const uint8_t* __restrict__ bq, int64_t row_byt
   }
 }
 
-__global__ void mask_hi_kernel(const uint32_t* __restrict__ mask_lo, int64_t words, uint32_t* __restrict__ mask_hi) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x)
-    mask_hi[i] = mask_lo[i] << 1;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 struct Segment {
   int group;     // index into Ctx::groups
   int c_first;   // first (extended) dot column of the group in this segment
@@ -940,16 +920,7 @@ static void free_prepared(State* s) {
 
 static int encode_2d(State* s, CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride,
                      uint32_t box_inner, uint32_t box_outer) {
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {row_stride};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = s->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         tuning_env("LRR_ABL_L2P128") ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
-                         : tuning_env("LRR_ABL_L2PNONE") ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : (int)r;
+  return tcc::encode_2d_u8(s->encode, map, ptr, inner, outer, row_stride, box_inner, box_outer);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1039,17 +1010,7 @@ static int prepare(Ctx* c, bool wide) {
   s->prepared = true;
   s->wide = wide;
   s->usable = false;
-  if (!s->encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
-      cudaGetLastError();
-      s->why = "cuTensorMapEncodeTiled is not available from the driver";
-      return LRR_OK;
-    }
-    s->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  }
+  if (!s->encode && !(s->encode = tcc::get_encode_fn(&s->why))) return LRR_OK;
   const size_t G = c->groups.size();
   if (G == 0) {
     s->why = "no groups";
@@ -1119,7 +1080,7 @@ static int prepare(Ctx* c, bool wide) {
   for (size_t g = 0; g < G; ++g) {
     const Group& gr = c->groups[g];
     if ((int64_t)gr.n != c->n_samples_total) any_masked = true;
-    mask_hi_kernel<<<(unsigned)std::min<int64_t>((mask_words + 255) / 256, 1024), 256>>>(gr.d_mask, mask_words,
+    tcc::mask_hi_kernel<<<(unsigned)std::min<int64_t>((mask_words + 255) / 256, 1024), 256>>>(gr.d_mask, mask_words,
                                                                                         s->d_mask_hi + g * mask_words);
     c->launches++;
   }
@@ -1193,6 +1154,7 @@ static int prepare(Ctx* c, bool wide) {
       int bst = NB;
       if (bst > 3 && budget - bst * sh.bstage_bytes < 6 * ps.gstage_bytes) bst = 3;
       while (bst > 2 && budget - bst * sh.bstage_bytes < 3 * ps.gstage_bytes) --bst;
+      if (const char* e = tuning_env("LRR_TC4_BST")) { const int v = atoi(e); if (v >= 2 && v <= NB && budget - v * sh.bstage_bytes >= 2 * ps.gstage_bytes) bst = v; }
       int gst = (budget - bst * sh.bstage_bytes) / ps.gstage_bytes;
       if (gst > MAX_GSTAGES) gst = MAX_GSTAGES;
       if (bst < 2 || gst < 2) {
@@ -1367,33 +1329,8 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
 #define LRR_PICK(NG_) (cs == 2 ? (void*)tc4_sweep_kernel<NG_, 2> : (void*)tc4_sweep_kernel<NG_, 1>)
     kfn = p.n_groups == 1 ? LRR_PICK(1) : p.n_groups == 2 ? LRR_PICK(2) : LRR_PICK(0);
 #undef LRR_PICK
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = (size_t)sh.smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int max_clusters = c->sm_count / cs;
-    if (cs > 1) {
-      cfg.gridDim = dim3((unsigned)(c->sm_count / cs * cs));
-      int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, kfn, &cfg) == cudaSuccess && nc > 0) max_clusters = nc;
-      else cudaGetLastError();
-    }
-    int n_cta = max_clusters * cs;
-    const int need = (p.n_tiles + cs - 1) / cs * cs;
-    if (n_cta > need) n_cta = need;
-    cfg.gridDim = dim3((unsigned)n_cta);
     void* args[3] = {(void*)&geno_map, (void*)&sh.b_map, (void*)&p};
-    LRR_CUDA(c, cudaLaunchKernelExC(&cfg, kfn, args));
-    c->launches++;
-    LRR_CUDA(c, cudaGetLastError());
+    if (int r = tcc::launch_persistent_clusters(c, kfn, cs, THREADS, sh.smem_bytes, p.n_tiles, args, st)) return r;
   }
   return LRR_OK;
 }

@@ -5,8 +5,21 @@ import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_committed_bench_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_c2_end.json")))
+import pytest
+
+
+@pytest.mark.parametrize("line", ["r01_bench_c2_end.json", "r02_bench_default_final.json"])
+def test_committed_bench_line_has_the_contract_keys(line):
+    d = json.load(open(os.path.join(ROOT, "profiles", line)))
+    if line.startswith("r02"):
+        # round 2: the DRAM traffic is labelled as the constant it is, every rank reports its own sweep time and clocks, and
+        # the end-to-end leg says what the host link gave inside the call
+        assert d["roofline"]["traffic_source"].startswith("constant from profiles/") and d["kernel"] == "tc4"
+        assert d["ranks"][0]["kernel_ms_median"] > 0 and "sm_mhz" in d["ranks"][0]
+        e = d["e2e"]
+        assert e["h2d_gbps_in_call"] > 0 and e["h2d_gbps_link_alone"] > 0 and e["slowest_stage"] in e["stage_seconds"]
+        assert set(d["config"]) == {"workload", "samples", "variants_per_gpu", "phenotypes", "covariates", "missing_rate", "groups",
+                                    "parallelism", "l2"}
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "gpu_launches", "roofline", "clocks", "e2e", "cpu_baseline"):
         assert k in d, k
