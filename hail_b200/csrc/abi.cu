@@ -176,6 +176,20 @@ int ensure_workspace(Ctx* c, int64_t M) {
 
 }  // namespace
 
+void release_caches(Ctx* c) {
+  for (auto& g : c->spare) free_group(g);
+  c->spare.clear();
+  cudaFree(c->d_recompute);
+  c->d_recompute = nullptr;
+  c->recompute_bytes = 0;
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  c->h_stage = nullptr;
+  c->d_stage_view = nullptr;
+  c->h_stage_bytes = 0;
+  c->stage_ev_valid = false;
+  if (c->groups.empty()) free_workspace(c);
+}
+
 int run_begin(Ctx* c, cudaStream_t st) {
   if (c->ready_valid) LRR_CUDA(c, cudaStreamWaitEvent(st, c->ready_ev, 0));
   return LRR_OK;
@@ -222,26 +236,37 @@ int run_rows(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_
     if (work <= 2e9) k = LRR_KERNEL_FP64;
     else k = tc4_supported(c, false, d_row_flags, n_variants, st) ? LRR_KERNEL_TC4 : tc_supported(c, may_miss) ? LRR_KERNEL_TC : LRR_KERNEL_FP64;
   }
-  // Adaptive precision (4-bit sweep), once per group set and deterministic: the first kPilotRows rows run as a pilot;
+  // Adaptive precision (4-bit sweep), once per group set and deterministic: the first kPilotRows rows (or the whole of
+  // a shorter run, e.g. one block of the streaming loop) run as a pilot;
   // when more than 2 % of them leave the tolerance guard (structured or badly scaled covariates: |Q'x| is large for
   // every row), the covariate / fitted-value columns are re-quantised with two more digits, up to three times.  This
   // is the only place the hot call waits for the device, and only on the first call after the groups changed.
-  if (k == LRR_KERNEL_TC4 && c->guard && !c->pilot_done && n_variants >= 2 * kPilotRows) {
+  if (k == LRR_KERNEL_TC4 && c->guard && !c->pilot_done && n_variants >= 1024) {
     c->pilot_done = true;
-    const int timing = c->timing;
-    c->timing = 0;
+    const int64_t pilot_rows = std::min<int64_t>(kPilotRows, n_variants);   // (a short block of the streaming loop: all of it)
+    const int saved_timing = c->timing;
+    if (pilot_rows != n_variants) c->timing = 0;   // (the sweep timer brackets the run proper)
     for (;;) {
+      int r = LRR_OK;
       if (!tc4_supported(c, false, d_row_flags, n_variants, st))
-        return fail(c, LRR_EINVAL, "lrr_run: 4-bit tensor-core kernel does not support this configuration: " + c->err);
-      if (int r = run_rows_once(c, d_packed, d_row_flags, kPilotRows, packed_stride, outs, k, st)) return r;
-      LRR_CUDA(c, cudaStreamSynchronize(st));
+        r = fail(c, LRR_EINVAL, "lrr_run: 4-bit tensor-core kernel does not support this configuration: " + c->err);
+      if (!r) r = run_rows_once(c, d_packed, d_row_flags, pilot_rows, packed_stride, outs, k, st);
+      if (!r) {
+        const cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) r = cuda_fail(c, e, "cudaStreamSynchronize (precision pilot)");
+      }
+      if (r) {
+        c->timing = saved_timing;
+        return r;
+      }
       int64_t worst = 0;
       for (size_t g = 0; g < c->groups.size(); ++g) worst = std::max<int64_t>(worst, c->h_flag_count[g]);
-      if (worst * 50 <= kPilotRows || c->digit_boost >= 6) break;
+      if (worst * 50 <= pilot_rows || c->digit_boost >= 6) break;
       c->digit_boost += 2;
       tc4_invalidate(c);
     }
-    c->timing = timing;
+    c->timing = saved_timing;
+    if (pilot_rows == n_variants) return LRR_OK;   // the pilot was the run
   }
   return run_rows_once(c, d_packed, d_row_flags, n_variants, packed_stride, outs, k, st);
 }

@@ -138,6 +138,7 @@ struct DeviceGuard {
 
 // order the caller's stream behind the last lrr_add_group (call at the start of every run that reads group buffers) and
 // mark the group buffers as in use by that stream (call at its end)
+void release_caches(Ctx* c);   // lrr_trim: everything the context keeps between calls that no live group needs
 int run_begin(Ctx* c, cudaStream_t st);
 int run_end(Ctx* c, cudaStream_t st);
 int fail(Ctx* c, int code, const std::string& msg);

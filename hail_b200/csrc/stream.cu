@@ -371,6 +371,7 @@ int lrr_trim(lrr_ctx* ctx) try {
   cudaFree(c->d_nanmask);
   c->d_nanmask = nullptr;
   c->nanmask_bytes = 0;
+  release_caches(c);   // retired groups' buffers, workspaces of the hot call, staging (abi.cu)
   return LRR_OK;
 }
 LRR_ABI_CATCH(ctx)

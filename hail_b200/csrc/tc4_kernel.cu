@@ -99,7 +99,7 @@ struct GroupMeta {
   double* dots;       // [M][dots_stride], already offset to this segment's first dot column
   int dots_stride;
   const double* colscale;   // [C]
-  const uint32_t* mask_hi;  // [ns_pad/16], high bit of each kept field
+  const uint32_t* mask_hi;  // [ns_pad/16], both bits of each kept sample's field
   uint8_t nd[PASS_COLS_WIDE];   // base-13 digits of each dot column of the segment
 };
 
@@ -480,23 +480,21 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
             rc[2 * i + 1] = (w[i] >> 2) & 0x33333333u;
           }
         }
-        // exact counts for x.x = n1 + 4 n2 (see tc_kernel.cu)
+        // exact counts for x.x = n1 + 4 n2: the number of set bits among the group's fields, T = n1 + n2 + 2 n_miss (one
+        // POPC per word, one AND more under a sample mask); with S = n1 + 2 n2 and n_miss from the "ones" column of the
+        // two planes the epilogue solves n2 = S - (T - 2 n_miss), n1 = S - 2 n2
+        auto count_bits = [&]() {
 #pragma unroll
-        for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
-          if ((NG || g < n_groups) && !ABL(16)) {
-            int acc = 0;
+          for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
+            if ((NG || g < n_groups) && !ABL(16)) {
+              int acc = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (MA && !TP) {
-                acc += __popc(w[i]);
-              } else {
-                const uint32_t m = MA ? 0xAAAAAAAAu : mm[g][i];
-                acc += TP ? __popc(w[i] & ~(w[i] << 1) & m) : __popc(w[i] & m);
-              }
+              for (int i = 0; i < 8; ++i) acc += MA ? __popc(w[i]) : __popc(w[i] & mm[g][i]);
+              n2[g] += acc;
             }
-            n2[g] += acc;
           }
-        }
+        };
+        if (!EAGER) count_bits();   // (two-plane tiles count behind their TMEM stores, see below)
         __syncwarp();
         if (lane == 0) mbar_arrive(gbar + 8u * MAX_GSTAGES);   // genotype stage back to the TMA producer
         if (pend_u >= 0 && !EAGER) {   // retire the previous chunk's TMEM store behind this chunk's arithmetic
@@ -522,7 +520,9 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         }
         if (EAGER) {
           // two-plane tiles: the ring holds only two chunks (4 units), so a store published one chunk late would leave the
-          // MMA warp nothing to overlap with -- publish at once (measured: 35 -> see profiles/README.md ms per C3 pass)
+          // MMA warp nothing to overlap with -- publish at once (35.4 -> 32.4 ms per C3 pass), with the population counts
+          // in the shadow of the stores
+          count_bits();
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
@@ -651,7 +651,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
           const int sc = __float2int_rn(2.f * sc_f);   // sum of codes: A = c / 2, ones digit = 1.0
           const int nm = __float2int_rn(2.f * nm_f);   // missing calls: A = 1 / 2
           const int S = sc - 3 * nm;                   // n1 + 2 n2
-          const int n2g = (!two_plane && p.mask_bytes == 0) ? S - cnt : cnt;
+          const int n2g = S - (cnt - 2 * nm);          // cnt = set bits among the group's fields = n1 + n2 + 2 n_miss
           const int n1 = S - 2 * n2g;
           const double mean = (double)S / (double)(G.n - nm);
           if (v < p.M) reinterpret_cast<int4*>(G.counts)[v] = make_int4(n1, n2g, nm, 0);
@@ -891,7 +891,7 @@ struct State {
   uint8_t* d_bq = nullptr;
   double* d_colscale = nullptr;
   double* d_colstat = nullptr;   // [2][nscale]: column maxima, sums of squares
-  uint32_t* d_mask_hi = nullptr;
+  uint32_t* d_mask_hi = nullptr;   // per group: both bits of every kept field
   std::vector<int> scale_off;
   int cluster = 2;
   bool attr_set = false;
@@ -997,6 +997,12 @@ static void plan_passes(const Ctx* c, const std::vector<GroupCols>& cols, std::v
   close();
 }
 
+// both bits of every kept sample's field (Group::d_mask has the low bit): what the unpack warps AND the packed words with
+__global__ void mask_full_kernel(const uint32_t* __restrict__ mask_lo, int64_t words, uint32_t* __restrict__ mask_full) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x)
+    mask_full[i] = mask_lo[i] | (mask_lo[i] << 1);
+}
+
 __global__ void any_flag_kernel(const uint8_t* __restrict__ flags, int64_t M, int32_t* __restrict__ any) {
   int f = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) f |= flags[i];
@@ -1080,8 +1086,8 @@ static int prepare(Ctx* c, bool wide) {
   for (size_t g = 0; g < G; ++g) {
     const Group& gr = c->groups[g];
     if ((int64_t)gr.n != c->n_samples_total) any_masked = true;
-    tcc::mask_hi_kernel<<<(unsigned)std::min<int64_t>((mask_words + 255) / 256, 1024), 256>>>(gr.d_mask, mask_words,
-                                                                                        s->d_mask_hi + g * mask_words);
+    mask_full_kernel<<<(unsigned)std::min<int64_t>((mask_words + 255) / 256, 1024), 256>>>(gr.d_mask, mask_words,
+                                                                                          s->d_mask_hi + g * mask_words);
     c->launches++;
   }
   for (auto& ps : s->passes) {

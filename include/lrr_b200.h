@@ -195,8 +195,10 @@ float lrr_last_stream_h2d_ms(const lrr_ctx* ctx);
  * the first copy started: copy done, sweep started, statistics done); copies up to `capacity` floats, returns the total */
 int lrr_last_stream_timeline(const lrr_ctx* ctx, float* out, int capacity);
 /* The streaming arena (staging buffers + slots, up to 16 GB and never more than half of the free device memory) and the
- * dense path's missing-bit plane stay cached on the context between calls; lrr_trim gives them back to the device
- * (synchronises; LRR_ESTATE while a stream is open).  lrr_destroy frees everything. */
+ * dense path's missing-bit plane stay cached on the context between calls, and so do the buffers of retired groups, the
+ * workspaces of the hot call and the host staging buffer (that is what keeps lrr_clear_groups / lrr_add_group / lrr_run
+ * free of cudaMalloc and device synchronisation); lrr_trim gives all of it back (synchronises; LRR_ESTATE while a stream
+ * is open).  lrr_destroy frees everything. */
 int lrr_trim(lrr_ctx* ctx);
 
 /* ---- logistic regression, score test (`hl.logistic_regression_rows(test='score', ...)`) --------

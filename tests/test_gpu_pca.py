@@ -123,3 +123,25 @@ def test_filtered_columns_and_errors():
         hb.hwe_normalized_pca(mono.GT, k=2)
     with pytest.raises(hb.ExpressionException):
         hb.hwe_normalized_pca(mt.GT.n_alt_alleles(), k=2)
+
+
+def test_pca_at_400k_samples_vs_exact_eigensystem():
+    """The BASELINE sample count: 400k samples x 1,536 variants from four populations.  The oracle's exact SVD of a
+    1,536 x 400k matrix is replaced by the eigensystem of the small Gram matrix A A' (same eigenvalues; loadings = its
+    eigenvectors, scores = A' U) built from the oracle's own hwe_normalize."""
+    hb = _hb()
+    N, M, k = 400_000, 1536, 3
+    mt = hb.balding_nichols_model(4, N, M, missing_rate=0.01, seed=29)
+    dos = mt.genotypes.to_dosage().astype(np.float32)
+    dos[dos < 0] = np.nan
+    a, keep = P.hwe_normalize(dos)                       # float64 [m, N]
+    w, u = np.linalg.eigh(a @ a.T)
+    order = np.argsort(w)[::-1][:k]
+    want_ev, want_load = w[order], u[:, order]
+    want_scores = a.T @ want_load
+    ev, scores, loadings = hb.hwe_normalized_pca(mt.GT, k=k, compute_loadings=True)
+    np.testing.assert_allclose(ev, want_ev, rtol=1e-6)
+    assert want_ev[k - 1] > 3 * w[np.argsort(w)[::-1][k]]          # k structure components, well separated from the bulk
+    _same_up_to_sign(scores.scores, want_scores, rtol=1e-5, atol=1e-5 * np.abs(want_scores).max())
+    got_load = np.asarray(loadings.loadings)[keep] if np.asarray(loadings.loadings).shape[0] == M else np.asarray(loadings.loadings)
+    _same_up_to_sign(got_load, want_load, rtol=1e-5, atol=1e-5 * np.abs(want_load).max())
