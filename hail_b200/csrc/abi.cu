@@ -163,6 +163,21 @@ int ensure_workspace(Ctx* c, int64_t M) {
     c->ws_groups = groups;
     c->ws_cols = cols;
   }
+  {
+    // the deferred-tail list of the statistics epilogue: 1/16 of the largest group's (variant, phenotype) entries
+    int64_t maxP = 1;
+    for (const Group& g : c->groups) maxP = std::max<int64_t>(maxP, g.P);
+    const int64_t want = M * maxP / 16 + 4096;
+    if (want > c->tail_capacity) {
+      LRR_CUDA(c, cudaDeviceSynchronize());
+      cudaFree(c->d_tail);
+      c->d_tail = nullptr;
+      c->tail_capacity = 0;
+      LRR_CUDA(c, cudaMalloc(&c->d_tail, sizeof(int64_t) * 2 * (size_t)want));
+      if (!c->d_tail_count) LRR_CUDA(c, cudaMalloc(&c->d_tail_count, sizeof(int32_t)));
+      c->tail_capacity = want;
+    }
+  }
   if (c->dots_offset.size() != (size_t)G) {
     c->dots_offset.resize((size_t)G);
     int64_t off = 0;
@@ -182,6 +197,9 @@ void release_caches(Ctx* c) {
   cudaFree(c->d_recompute);
   c->d_recompute = nullptr;
   c->recompute_bytes = 0;
+  cudaFree(c->d_tail);
+  c->d_tail = nullptr;
+  c->tail_capacity = 0;
   if (c->h_stage) cudaFreeHost(c->h_stage);
   c->h_stage = nullptr;
   c->d_stage_view = nullptr;
@@ -380,6 +398,8 @@ void lrr_destroy(lrr_ctx* ctx) try {
   for (auto& g : c->spare) free_group(g);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->stage_ev) cudaEventDestroy(c->stage_ev);
+  cudaFree(c->d_tail);
+  cudaFree(c->d_tail_count);
   cudaFree(c->d_recompute);
   if (c->busy_ev) cudaEventDestroy(c->busy_ev);
   if (c->ready_ev) cudaEventDestroy(c->ready_ev);

@@ -115,6 +115,9 @@ struct Ctx {
   cudaEvent_t ready_ev = nullptr;   // recorded on the default stream after the last lrr_add_group's device work
   bool busy_valid = false, ready_valid = false;
   int64_t ws_groups = 0, ws_cols = 0;   // workspace capacities next to reserved_variants
+  void* d_tail = nullptr;           // deferred tail p-values of the statistics epilogue: (entry, t) pairs (grow-only)
+  int32_t* d_tail_count = nullptr;
+  int64_t tail_capacity = 0;
   void* d_recompute = nullptr;      // split-row partial sums + arrival counters of fp64_recompute_kernel (grow-only)
   size_t recompute_bytes = 0;
   int guard = 1;                    // 0: no tolerance guard (kernel tuning / tests of the raw quantised path)

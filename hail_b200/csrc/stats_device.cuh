@@ -73,6 +73,19 @@ __device__ inline double two_sided_p_dev(double t, double df, double lbeta, doub
 }
 
 
+// the tail region of two_sided_p_dev: the direct continued fraction, ~50 iterations for large df (the centre takes ~8)
+__device__ inline bool p_value_is_tail(double t, double df) {
+  if (!(fabs(t) < INFINITY)) return false;   // NaN / Inf are answered at once
+  const double a = 0.5 * df, b = 0.5;
+  const double x = 1.0 / (1.0 + (t / df) * t);
+  return x < (a + 1.0) / (a + b + 2.0) && t * t >= 6.76;
+}
+
+struct TailEntry {
+  int64_t idx;   // v * P + p
+  double t;
+};
+
 // what the statistics of one group need besides the per-variant sums
 struct StatModel {
   const double* qty;      // [K][P]
@@ -89,6 +102,11 @@ struct StatModel {
   int32_t* flag_mark;     // [M]
   int32_t* flag_list;     // [M]
   int32_t* flag_count;
+  // the p-values of the tail region are deferred to a compacted second kernel (one slow lane would otherwise hold its whole
+  // warp for ~50 iterations: under the null a quarter of the warps hold one); NULL = compute every p-value in place
+  TailEntry* tail_list;
+  int32_t* tail_count;
+  int32_t tail_capacity;
   double lbeta;
   lrr_group_out out;
 };
@@ -141,7 +159,16 @@ __device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n
     b = xyp * xxpRec;                                          // LR:150-155
     se = sqrt(dRec * (a.yyp[p] * xxpRec - b * b));             // LR:157
     t = b / se;                                                // LR:159
-    pv = two_sided_p_dev(t, (double)a.d, a.lbeta, a.out.log10_p ? &l10 : nullptr);  // LR:160
+    bool deferred = false;
+    if (a.tail_list && (a.out.p_value || a.out.log10_p) && p_value_is_tail(t, (double)a.d)) {
+      const int k = atomicAdd(a.tail_count, 1);
+      if (k < a.tail_capacity) {
+        a.tail_list[k].idx = idx;
+        a.tail_list[k].t = t;
+        deferred = true;
+      }
+    }
+    pv = deferred ? 0.0 : two_sided_p_dev(t, (double)a.d, a.lbeta, a.out.log10_p ? &l10 : nullptr);  // LR:160
   }
   if (a.dense && (aux & 3)) {
     // an infinite entry is a defined value in the reference: sum_x = +-Inf (NaN when both signs occur), x.x = Inf and every
@@ -226,6 +253,9 @@ inline StatModel stat_model_of(const Group& G, const lrr_group_out& out) {
   // dense-contraction configuration with its stated tolerance): |dt| <= 5e-7
   a.t_floor = G.P > 2 ? 0.5e-6 : 0.5e-9;
   a.flag_mark = a.flag_list = a.flag_count = nullptr;
+  a.tail_list = nullptr;
+  a.tail_count = nullptr;
+  a.tail_capacity = 0;
   a.lbeta = G.lbeta;
   a.out = out;
   return a;

@@ -1,6 +1,8 @@
 // Per-variant epilogue kernels: from exact genotype counts and the projected dot products to
 // (sum_x, y_transpose_x, beta, standard_error, t_stat, p_value) -- the mathematics lives in stats_device.cuh -- and the
 // logistic score-test epilogue.
+#include <algorithm>
+
 #include "stats_device.cuh"
 
 namespace lrr {
@@ -35,6 +37,19 @@ __global__ void stats_epilogue_listed_kernel(EpiArgs a, const int32_t* __restric
     const int64_t v = list[i];
     const int4 cnt = reinterpret_cast<const int4*>(a.counts)[v];
     variant_stats(a.model, v, p, cnt.x, cnt.y, cnt.z, cnt.w, a.dots + v * a.model.stride);
+  }
+}
+
+// the deferred p-values: every lane runs the long continued fraction
+__global__ void stats_tail_kernel(const TailEntry* __restrict__ list, const int32_t* __restrict__ count, int capacity, double df,
+                                  double lbeta, double* __restrict__ p_value, double* __restrict__ log10_p) {
+  const int n = min(*count, capacity);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const TailEntry e = list[i];
+    double l = 0.0;
+    const double pv = two_sided_p_dev(e.t, df, lbeta, log10_p ? &l : nullptr);
+    if (p_value) p_value[e.idx] = pv;
+    if (log10_p) log10_p[e.idx] = l;
   }
 }
 
@@ -117,11 +132,24 @@ int launch_stats_epilogue(Ctx* c, int g, int64_t M, const lrr_group_out& out, cu
     a.model.flag_count = c->d_flag_count + g;
   }
   const int64_t total = M * G.P;
+  const bool defer = c->d_tail && total >= 4096 && (out.p_value || out.log10_p);
+  if (defer) {
+    a.model.tail_list = static_cast<TailEntry*>(c->d_tail);
+    a.model.tail_count = c->d_tail_count;
+    a.model.tail_capacity = (int32_t)std::min<int64_t>(c->tail_capacity, 1 << 30);
+    LRR_CUDA(c, cudaMemsetAsync(c->d_tail_count, 0, sizeof(int32_t), st));
+  }
   int64_t grid = (total + 127) / 128;
   if (grid > (int64_t)c->sm_count * 32) grid = (int64_t)c->sm_count * 32;
   stats_epilogue_kernel<<<(int)grid, 128, 0, st>>>(a);
   c->launches++;
   LRR_CUDA(c, cudaGetLastError());
+  if (defer) {
+    stats_tail_kernel<<<c->sm_count * 4, 128, 0, st>>>(a.model.tail_list, a.model.tail_count, a.model.tail_capacity, (double)G.d, G.lbeta,
+                                                      out.p_value, out.log10_p);
+    c->launches++;
+    LRR_CUDA(c, cudaGetLastError());
+  }
   return LRR_OK;
 }
 
