@@ -843,6 +843,8 @@ struct State {
   double* d_colscale = nullptr;   // concatenated per group
   unsigned long long* d_colmax = nullptr;
   uint32_t* d_mask_hi = nullptr;  // [G][ns_pad/16] group masks shifted to the high bit of each field
+  unsigned long long* d_bound = nullptr;   // scratch of acc_bound_kernel (grow-only)
+  size_t bound_bytes = 0;
   std::vector<int> scale_off;
   int cluster = 2;
   bool attr_set = false;
@@ -979,16 +981,23 @@ static int prepare(Ctx* c) {
   LRR_CUDA(c, cudaGetLastError());
   {
     // exactness guard: no INT32 accumulator can overflow, whatever the genotypes are
-    unsigned long long* d_bound = nullptr;
-    LRR_CUDA(c, cudaMalloc(&d_bound, sizeof(unsigned long long) * 2 * (size_t)total_rows));
-    LRR_CUDA(c, cudaMemset(d_bound, 0, sizeof(unsigned long long) * 2 * (size_t)total_rows));
+    // (grow-only scratch kept on the state: a cudaFree here would wait for every copy the streaming loop has in flight)
+    const size_t bound_bytes = sizeof(unsigned long long) * 2 * (size_t)total_rows;
+    if (bound_bytes > s->bound_bytes) {
+      cudaFree(s->d_bound);
+      s->d_bound = nullptr;
+      s->bound_bytes = 0;
+      LRR_CUDA(c, cudaMalloc(&s->d_bound, bound_bytes));
+      s->bound_bytes = bound_bytes;
+    }
+    unsigned long long* d_bound = s->d_bound;
+    LRR_CUDA(c, cudaMemsetAsync(d_bound, 0, bound_bytes, 0));
     for (int64_t r0 = 0; r0 < total_rows; r0 += 65535)
       acc_bound_kernel<<<dim3(gx, (unsigned)std::min<int64_t>(total_rows - r0, 65535)), 256>>>(s->d_bq + r0 * ns_pad, ns_pad,
                                                                                             d_bound + 2 * r0);
     c->launches++;
     std::vector<unsigned long long> h_bound(2 * (size_t)total_rows);
     cudaError_t e = cudaMemcpy(h_bound.data(), d_bound, sizeof(unsigned long long) * h_bound.size(), cudaMemcpyDeviceToHost);
-    cudaFree(d_bound);
     if (e != cudaSuccess) return cuda_fail(c, e, "acc_bound_kernel");
     unsigned long long worst = 0;
     for (unsigned long long v : h_bound) worst = std::max(worst, v);
@@ -1083,6 +1092,7 @@ void tc_release(Ctx* c) {
   if (!c->tc_state) return;
   tc::State* s = static_cast<tc::State*>(c->tc_state);
   tc::free_prepared(s);
+  cudaFree(s->d_bound);
   delete s;
   c->tc_state = nullptr;
 }

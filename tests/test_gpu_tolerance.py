@@ -255,3 +255,20 @@ def test_environment_cannot_change_results(monkeypatch):
     again = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=[1.0, mt.c], _kernel="tc4")
     for f in ("beta", "standard_error", "t_stat", "p_value", "sum_x"):
         assert np.array_equal(base[f], again[f], equal_nan=True), f
+
+
+def test_structured_covariates_streamed_from_host_blocks():
+    """The precision pilot also runs when the rows arrive block by block (lrr_stream_*: every block is a short lrr_run):
+    genotype-like covariates from host-resident .bed bytes, results within tolerance of the oracle."""
+    hb = _hb()
+    from oracle import c_oracle
+    N, M = 100_000, 6144
+    gt, bed_rows, _, rng = _big_case(N, M, 2, 0.0, seed=47)
+    x = obed.decode_rows(bed_rows[:4], N)
+    cov = np.column_stack([np.ones(N)] + [x[i] + 0.3 * rng.standard_normal(N) for i in range(3)] + [rng.standard_normal(N)])
+    y = rng.standard_normal(N)
+    host = hb.MatrixTable(hb.HostBedGenotypes(bed_rows, N), cols={"y": y, **{f"c{i}": cov[:, i] for i in range(1, 5)}})
+    ht = hb.linear_regression_rows(y=host.y, x=host.GT.n_alt_alleles(), covariates=[1.0] + [host[f"c{i}"] for i in range(1, 5)],
+                                   _stream_block=4096)   # (blocks large enough for AUTO to take the tensor-core sweep)
+    want = c_oracle.linreg_group_bed(bed_rows, N, y[:, None], cov)
+    assert_fields_close(_as_oracle_dict(ht), _strip(want), t_floor=1e-9, ctx="streamed, structured covariates")
