@@ -115,6 +115,9 @@ struct Params {
   int gstage_bytes, bstage_bytes;
   int mask_bytes;     // n_groups * 128 when any group needs masking, else 0
   int one_plane_only; // wide passes: the host has checked that no row holds a missing call
+  int plane_mode;     // 0: one sweep, both planes where a tile pair holds a missing call;  split sweeps (wide passes over
+                      // data WITH missing calls): 1 = plane c of every tile (raw sums for flagged pairs), 2 = plane m of the
+                      // flagged pairs only, which also finishes their rows from the sums of the plane-c sweep
   const uint8_t* row_flags;  // nullable
   int abl_contig;     // timing ablation: read every genotype box as one contiguous 16 KB block (results are WRONG)
   int abl;            // timing ablation bits: 1 no tcgen05.st, 2 no MMA, 4 no basis-panel loads, 8 no unpack ALU, 16 no popcount (results are WRONG)
@@ -249,17 +252,22 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
   const int tile_step = CS > 1 ? (int)n_clusters_x() * CS : (int)gridDim.x;
   const int tile_end = CS > 1 ? p.n_tiles + cta_rank : p.n_tiles;   // (tile - rank) < n_tiles for every CTA alike
   const int panel_bytes = p.ncols / CS * 128;   // this CTA's rows of one basis panel (256 samples)
-  auto tile_mode = [&](int tile) {
+  auto pair_flag = [&](int tile) {   // does the tile (pair) hold a missing call, as far as the row flags know?
     if (CS == 1) return tile_has_missing(p, tile);
     const int t0 = tile - cta_rank;
     return tile_has_missing(p, t0) || tile_has_missing(p, t0 + 1);
   };
+  // two planes in one sweep only in mode 0; the split sweeps run every tile as a one-plane tile
+  auto tile_mode = [&](int tile) { return p.plane_mode == 0 && pair_flag(tile); };
+  // the plane-m sweep visits the flagged pairs only (every role skips the others alike)
+  auto tile_skipped = [&](int tile) { return p.plane_mode == 2 && !pair_flag(tile); };
 
   if (warp == WARP_TMA_G) {
     // ============================== genotype producer ==============================
     int gs = 0;
     uint32_t g_phase = 0;
     for (int tile = first_tile; tile < tile_end; tile += tile_step) {
+      if (tile_skipped(tile)) continue;
       for (int ch = 0; ch < p.n_chunks; ++ch) {
         mbar_wait(GEMPTY(gs), g_phase ^ 1);
         const uint32_t sbase = smem0 + gs * p.gstage_bytes;
@@ -285,6 +293,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
     int bs = 0;
     uint32_t b_phase = 0;
     for (int tile = first_tile; tile < tile_end; tile += tile_step) {
+      if (tile_skipped(tile)) continue;
       for (int ch = 0; ch < p.n_chunks; ++ch) {
         mbar_wait(BEMPTY(bs), b_phase ^ 1);
         const uint32_t sbase = bring0 + bs * p.bstage_bytes;
@@ -390,7 +399,8 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         }
       };
 
-      for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
+      for (int tile = first_tile; tile < tile_end; tile += tile_step) {
+        if (tile_skipped(tile)) continue;
         const bool two_plane = tile_mode(tile);
         if (tile_i > 0 && two_plane != prev_two_plane) ru = 0;   // the ring is laid out per mode (the unpack warps drain first)
         prev_two_plane = two_plane;
@@ -415,6 +425,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         for (; ch < p.n_chunks; ++ch) generic_chunk(ch, two_plane);
         if (elect_one()) commit(DFULL);
         __syncwarp();
+        ++tile_i;
       }
     }
   } else {
@@ -445,10 +456,13 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
 
     // The chunk loop of one tile, specialised on the tile's mode (TP: two planes) and on whether any group needs its
     // sample mask for the hom-alt count (MA: none does).
-    auto run_chunks = [&](auto tp_tag, auto ma_tag) {
+    // MO: the plane-m sweep of a split pass -- the A operand is the missing indicator alone, nothing is counted.
+    auto run_chunks = [&](auto tp_tag, auto ma_tag, auto mo_tag) {
       constexpr bool TP = decltype(tp_tag)::value;
-      constexpr bool MA = decltype(ma_tag)::value;
+      constexpr bool MO = decltype(mo_tag)::value;
+      constexpr bool MA = decltype(ma_tag)::value || MO;
       constexpr bool EAGER = TP && (LRR_TC4_TP_EAGER != 0);
+      static_assert(!(TP && MO), "the plane-m sweep runs one-plane tiles");
       int pend = -1;    // unit whose TMEM store is issued but not yet published to the MMA warp
       auto chunk_body = [&](const int u, const int pend_u) {
         mbar_wait(gbar, g_phase);
@@ -475,6 +489,10 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
           if ABL(8) {
             rc[2 * i + 0] = w[i];
             rc[2 * i + 1] = w[i];
+          } else if (MO) {
+            const uint32_t mw = w[i] & (w[i] >> 1);   // bit 2f set iff field f is code 3: nibble 0001 (= 0.5)
+            rc[2 * i + 0] = mw & 0x11111111u;
+            rc[2 * i + 1] = (mw >> 2) & 0x11111111u;
           } else {
             rc[2 * i + 0] = w[i] & 0x33333333u;
             rc[2 * i + 1] = (w[i] >> 2) & 0x33333333u;
@@ -486,7 +504,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         auto count_bits = [&]() {
 #pragma unroll
           for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
-            if ((NG || g < n_groups) && !ABL(16)) {
+            if ((NG || g < n_groups) && !ABL(16) && !MO) {
               int acc = 0;
 #pragma unroll
               for (int i = 0; i < 8; ++i) acc += MA ? __popc(w[i]) : __popc(w[i] & mm[g][i]);
@@ -592,7 +610,8 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         }
       if (sink == 0x12345u) bars->pad = sink;
     } else
-    for (int tile = first_tile; tile < tile_end; tile += tile_step, ++tile_i) {
+    for (int tile = first_tile; tile < tile_end; tile += tile_step) {
+      if (tile_skipped(tile)) continue;
       const bool two_plane = tile_mode(tile);
       if (tile_i > 0 && two_plane != prev_two_plane) {
         // the ring is laid out differently: wait until every MMA of the previous tile has retired
@@ -607,10 +626,12 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
       a_slot = tmem + lane_addr + (two_plane ? p.ring_base2 : p.ring_base1) + s * SLOT_COLS;
 #pragma unroll
       for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) n2[g] = 0;
-      if (two_plane) {
-        if (p.mask_bytes == 0) run_chunks(TrueTag{}, TrueTag{}); else run_chunks(TrueTag{}, FalseTag{});
+      if (p.plane_mode == 2) {
+        run_chunks(FalseTag{}, TrueTag{}, TrueTag{});
+      } else if (two_plane) {
+        if (p.mask_bytes == 0) run_chunks(TrueTag{}, TrueTag{}, FalseTag{}); else run_chunks(TrueTag{}, FalseTag{}, FalseTag{});
       } else {
-        if (p.mask_bytes == 0) run_chunks(FalseTag{}, TrueTag{}); else run_chunks(FalseTag{}, FalseTag{});
+        if (p.mask_bytes == 0) run_chunks(FalseTag{}, TrueTag{}, FalseTag{}); else run_chunks(FalseTag{}, FalseTag{}, FalseTag{});
       }
 
       // ------------------------------ per-tile epilogue ------------------------------
@@ -625,6 +646,10 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
         tc_fence_after();
         const int64_t v = (int64_t)tile * TILE_M + row;
         const uint32_t d_c = tmem + lane_addr, d_m = tmem + lane_addr + p.ncols;
+        // split sweeps: the plane-c sweep leaves RAW sums for the flagged pairs (sum of codes, set bits, D_c); the
+        // plane-m sweep, which visits exactly those pairs, finishes them: counts, mean, (D_c - 3 D_m) + mean D_m
+        const bool raw_c = p.plane_mode == 1 && pair_flag(tile);
+        const bool m_only = p.plane_mode == 2;
 #pragma unroll
         for (int g = 0; g < (NG ? NG : MAX_GROUPS); ++g) {
           if (!(NG || g < n_groups)) continue;
@@ -648,13 +673,20 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
             for (int i = 0; i < 16; ++i)
               if (i == (ones_col & 15)) nm_f = __uint_as_float(r16[i]);
           }
-          const int sc = __float2int_rn(2.f * sc_f);   // sum of codes: A = c / 2, ones digit = 1.0
-          const int nm = __float2int_rn(2.f * nm_f);   // missing calls: A = 1 / 2
+          int sc = __float2int_rn(2.f * sc_f);         // sum of codes: A = c / 2, ones digit = 1.0
+          int nm = __float2int_rn(2.f * nm_f);         // missing calls: A = 1 / 2
+          int bits = cnt;                              // set bits among the group's fields = n1 + n2 + 2 n_miss
+          if (m_only) {
+            nm = sc;                                   // this sweep's accumulators hold the indicator plane
+            const int4 raw = v < p.M ? reinterpret_cast<const int4*>(G.counts)[v] : make_int4(0, 0, 0, 0);
+            sc = raw.x;
+            bits = raw.y;
+          }
           const int S = sc - 3 * nm;                   // n1 + 2 n2
-          const int n2g = S - (cnt - 2 * nm);          // cnt = set bits among the group's fields = n1 + n2 + 2 n_miss
+          const int n2g = S - (bits - 2 * nm);
           const int n1 = S - 2 * n2g;
           const double mean = (double)S / (double)(G.n - nm);
-          if (v < p.M) reinterpret_cast<int4*>(G.counts)[v] = make_int4(n1, n2g, nm, 0);
+          if (v < p.M) reinterpret_cast<int4*>(G.counts)[v] = raw_c ? make_int4(sc, cnt, -1, 0) : make_int4(n1, n2g, nm, 0);
           // digit columns, 16 TMEM columns at a time: accumulator = sum c u / 4 with u the base-13 digit
           const int c_lo = G.col_off, c_hi = ones_col;
           long long hi = 0, lo = 0, mhi = 0, mlo = 0;
@@ -685,6 +717,10 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
                   const double scale = G.colscale[c];
                   double dot = fma((double)hi, 4826809.0, (double)lo) * scale;
                   if (two_plane && nm > 0) dot += mean * (fma((double)mhi, 4826809.0, (double)mlo) * scale);
+                  if (m_only && v < p.M) {   // `dot` is D_m here; the plane-c sweep left D_c
+                    const double d_raw = G.dots[v * G.dots_stride + c];
+                    dot = nm > 0 ? (d_raw - 3.0 * dot) + mean * dot : d_raw;
+                  }
                   if (v < p.M) G.dots[v * G.dots_stride + c] = dot;
                   hi = lo = mhi = mlo = 0;
                   sl = 0;
@@ -702,6 +738,7 @@ tc4_sweep_kernel(const __grid_constant__ CUtensorMap geno_map, const __grid_cons
           if (CS == 1) mbar_arrive(DEMPTY); else mbar_arrive_cluster(dempty_leader);
         }
       }
+      ++tile_i;
     }
   }
 
@@ -1190,24 +1227,15 @@ static int prepare(Ctx* c, bool wide) {
 }
 
 // Before the first quantisation of a group set: when the column count makes a multi-pass plan certain (every column has
-// at least 6 digits), ask the row flags first so that the basis is quantised once, for the right plan.
+// at least 6 digits) the basis is quantised once, for the wide plan.
 static int first_plan_is_wide(Ctx* c, const uint8_t* d_row_flags, int64_t M, cudaStream_t st, bool* wide) {
+  (void)d_row_flags; (void)M; (void)st;
   State* s = state(c);
   *wide = false;
-  if (s->prepared || !d_row_flags || M <= 0) return LRR_OK;
+  if (s->prepared) return LRR_OK;
   int64_t dot_cols = 0;
   for (const Group& gr : c->groups) dot_cols += gr.C;
-  if (6 * dot_cols <= PASS_COLS) return LRR_OK;
-  if (!s->d_any) {
-    LRR_CUDA(c, cudaMalloc(&s->d_any, sizeof(int32_t)));
-    LRR_CUDA(c, cudaMallocHost(&s->h_any, sizeof(int32_t)));
-  }
-  LRR_CUDA(c, cudaMemsetAsync(s->d_any, 0, sizeof(int32_t), st));
-  any_flag_kernel<<<(unsigned)std::min<int64_t>((M + 255) / 256, 1184), 256, 0, st>>>(d_row_flags, M, s->d_any);
-  c->launches++;
-  LRR_CUDA(c, cudaMemcpyAsync(s->h_any, s->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  LRR_CUDA(c, cudaStreamSynchronize(st));
-  *wide = *s->h_any == 0;
+  *wide = 6 * dot_cols > PASS_COLS;   // more than one narrow pass for certain: wide passes (clean input: one plane; else split)
   return LRR_OK;
 }
 
@@ -1267,8 +1295,14 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
   // More digit columns than one sweep holds: every pass re-reads the genotypes, so fewer, wider passes win -- but a pass of
   // up to 224 columns has no tensor memory for the missing-indicator plane.  It is used when the input's row flags say
   // that no row holds a missing call (one small reduction + a 4-byte read per call, only in multi-pass configurations).
+  // More digit columns than one sweep holds: every pass re-reads the genotypes, so the passes are WIDE (up to 224 columns,
+  // one accumulator set).  When the row flags say that no row holds a missing call (one small reduction + a 4-byte read per
+  // call) a wide pass is one one-plane sweep; otherwise it is SPLIT into two one-plane sweeps -- plane c of every tile, then
+  // plane m of the flagged tile pairs, which finishes their rows -- instead of twice as many narrow two-plane sweeps (a
+  // two-plane tile has tensor memory for two chunks of A operand only and runs 1.6x slower than two one-plane tiles).
+  bool split = false;
   if (s->passes.size() > 1 || s->wide) {
-    bool want_wide = false;
+    split = true;   // unknown flags: every tile may hold a missing call
     if (d_row_flags) {
       if (!s->d_any) {
         LRR_CUDA(c, cudaMalloc(&s->d_any, sizeof(int32_t)));
@@ -1279,10 +1313,10 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
       c->launches++;
       LRR_CUDA(c, cudaMemcpyAsync(s->h_any, s->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
       LRR_CUDA(c, cudaStreamSynchronize(st));
-      want_wide = *s->h_any == 0;
+      split = *s->h_any != 0;
     }
-    if (want_wide != s->wide) {
-      if (int r = prepare(c, want_wide)) return r;
+    if (!s->wide) {
+      if (int r = prepare(c, true)) return r;
       if (!s->usable) return fail(c, LRR_EINVAL, "4-bit tensor-core kernel unavailable: " + s->why);
     }
   }
@@ -1293,9 +1327,11 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
       return fail(c, LRR_ECUDA, "cuTensorMapEncodeTiled failed (contiguous ablation)");
   } else if (encode_2d(s, &geno_map, d_packed, (uint64_t)stride, (uint64_t)M, (uint64_t)stride, 128, TILE_M))
     return fail(c, LRR_ECUDA, "cuTensorMapEncodeTiled failed for the genotype store (pointer must be 16-byte aligned)");
-  for (const Pass& ps : s->passes) {
+  for (const Pass& ps : s->passes)
+  for (int mode = split ? 1 : 0; mode <= (split ? 2 : 0); ++mode) {
     Params p;
     memset(&p, 0, sizeof p);
+    p.plane_mode = mode;
     p.M = M;
     p.n_tiles = (int)((M + TILE_M - 1) / TILE_M);
     p.n_chunks = (int)(stride / 128);
@@ -1313,7 +1349,7 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
     p.bstage_bytes = sh.bstage_bytes;
     p.mask_bytes = ps.mask_bytes;
     p.row_flags = d_row_flags;
-    p.one_plane_only = s->wide ? 1 : 0;
+    p.one_plane_only = (s->wide && !split) ? 1 : 0;
     p.abl_contig = abl_contig ? 1 : 0;
     p.abl_stream = tuning_env("LRR_ABL_STREAM") ? atoi(tuning_env("LRR_ABL_STREAM")) : 0;
     p.abl = tuning_env("LRR_ABL_BITS") ? atoi(tuning_env("LRR_ABL_BITS")) : 0;
