@@ -57,19 +57,24 @@ def gp_dosage(doc):
     return np.array([[np.nan if t is None else t[1] + 2.0 * t[2] for t in row] for row in doc["gp"]])
 
 
-def assert_fields_close(got, want, rel=1e-6, rel_p=1e-5, t_floor=0.0, ctx=""):
+def assert_fields_close(got, want, rel=1e-6, rel_p=1e-5, t_floor=0.0, ctx="", ytx_abs=None):
     """Parity gate: n exact; sum_x / y_transpose_x / beta / standard_error / t_stat within `rel`
     (the reference's own `_same` comparator, oracle.d_eq); p_value within `rel_p`.
 
     `t_floor` > 0 additionally accepts |delta t| <= t_floor (FP64 roundoff floor on a statistic whose
     true value is ~0: beta/se relative error is unbounded there in ANY float64 implementation,
-    the reference included).
+    the reference included).  `ytx_abs` (array, optional) additionally accepts |delta y_transpose_x| <= ytx_abs: the
+    many-phenotype precision profile's stated floor for dot products that cancel to ~0, 5e-7 standard errors of x.y
+    (`ytx_floor_of` below computes it).
     """
     from oracle.linreg_oracle import d_eq
 
     assert np.array_equal(np.asarray(got["n"]), np.asarray(want["n"])), ctx + " n differs"
     for f in ("sum_x", "y_transpose_x", "standard_error"):
         ok = d_eq(got[f], want[f], rel)
+        if f == "y_transpose_x" and ytx_abs is not None:
+            with np.errstate(invalid="ignore"):
+                ok |= np.abs(np.asarray(got[f]) - np.asarray(want[f])) <= ytx_abs
         assert ok.all(), f"{ctx} {f}: {np.count_nonzero(~ok)} mismatches, first at {np.argwhere(~ok)[:3].tolist()}"
     se = np.asarray(want["standard_error"], dtype=np.float64)
     for f, scale in (("beta", se), ("t_stat", np.ones_like(se))):
@@ -83,3 +88,17 @@ def assert_fields_close(got, want, rel=1e-6, rel_p=1e-5, t_floor=0.0, ctx=""):
         with np.errstate(invalid="ignore"):
             ok |= np.abs(np.asarray(got["t_stat"]) - np.asarray(want["t_stat"])) <= t_floor
     assert ok.all(), f"{ctx} p_value: {np.count_nonzero(~ok)} mismatches, first at {np.argwhere(~ok)[:3].tolist()}"
+
+
+def ytx_floor_of(x, cov, se, floor=5e-7):
+    """`floor` standard errors of x.y per (variant, phenotype): floor * se * xxp with xxp = x.x - |Q'x|^2 of the
+    mean-imputed rows `x` [M, n] (NaN = missing) over the kept samples' covariates `cov` [n, K]."""
+    x = np.array(x, dtype=np.float64)
+    miss = np.isnan(x)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean = np.where(miss, 0.0, x).sum(axis=1) / (~miss).sum(axis=1)
+    x[miss] = np.broadcast_to(mean[:, None], x.shape)[miss]
+    q = np.linalg.qr(cov)[0] if cov.shape[1] else np.zeros((cov.shape[0], 0))
+    qtx = x @ q
+    xxp = (x * x).sum(axis=1) - (qtx * qtx).sum(axis=1)
+    return floor * np.asarray(se) * xxp[:, None]

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 from oracle import bed as obed
 from oracle import linreg_oracle as O
 from tests.bn_mirror import bn_fill_numpy
-from tests.helpers import GOLDEN, assert_fields_close, load_regression_linear
+from tests.helpers import GOLDEN, assert_fields_close, load_regression_linear, ytx_floor_of
 
 KERNELS = ["fp64", "tc", "tc4"]
 TC_KERNELS = ["tc", "tc4"]   # the exact-integer tensor-core sweeps: int8 digits / INT32 sums, E2M1 digits / f32 sums
@@ -444,6 +444,56 @@ def test_many_phenotypes_multi_pass(kernel):
     want = O.linreg_group(dos, ys, cov)
     assert ht.beta.shape == (M, P)
     assert_fields_close(_as_oracle_dict(ht), {k: v for k, v in want.items() if k != "_d"}, t_floor=1e-9, ctx=kernel)
+
+
+def test_multi_pass_with_sparse_missing_tiles():
+    """Several wide passes over data where only SOME tile pairs hold missing calls, > 2 tiles per CTA: the split
+    plane-c / plane-m sweeps (raw sums left by the first, rows finished by the second, untouched pairs skipped) must
+    give the rows of the oracle, the exact counts, and the same rows as the int8 kernel's two-plane passes."""
+    hb = _hb()
+    rng = np.random.default_rng(21)
+    N, M, P, K = 1500, 148 * 128 * 2 + 128 * 5 + 37, 20, 4
+    x = rng.integers(0, 3, size=(M, N)).astype(np.int8)
+    pair = np.arange(M) // 256
+    miss_rows = (pair % 3 == 1) | (pair % 11 == 0)
+    miss_rows[-20:] = True                       # the ragged last tile too
+    mask = (rng.random((M, N)) < 0.05) & miss_rows[:, None]
+    x[mask] = -1
+    x[300] = -1                                   # an all-missing variant inside a flagged pair
+    gt = hb.PackedGenotypes.from_dosage(x)
+    cov = np.column_stack([np.ones(N), rng.normal(size=(N, K - 1))])
+    ys = rng.normal(size=(N, P))
+    cols = {f"y{i}": ys[:, i] for i in range(P)}
+    cols.update({f"c{i}": cov[:, i] for i in range(1, K)})
+    mt = hb.MatrixTable(gt, cols=cols)
+    xf = np.where(x < 0, np.nan, x).astype(np.float64)
+    want = O.linreg_group(xf, ys, cov)
+    floor = ytx_floor_of(xf, cov, want["standard_error"])
+    rows = {}
+    for kernel in ("tc4", "auto", "tc"):
+        ht = hb.linear_regression_rows(y=[mt[f"y{i}"] for i in range(P)], x=mt.GT.n_alt_alleles(),
+                                       covariates=[1.0] + [mt[f"c{i}"] for i in range(1, K)], _kernel=kernel)
+        assert np.array_equal(ht.n_missing, (x < 0).sum(axis=1)), kernel
+        # 770k dot products: a few cancel to ~1e-5 of their scale; P > 2 is the many-phenotype profile (its stated floor)
+        assert_fields_close(_as_oracle_dict(ht), {k: v for k, v in want.items() if k != "_d"}, t_floor=1e-9, ctx=kernel,
+                            ytx_abs=None if kernel == "tc" else floor)
+        rows[kernel] = ht
+    assert np.array_equal(rows["tc4"].sum_x, rows["tc"].sum_x, equal_nan=True)
+    # chained groups on the same data (different complete-sample sets per group), still more columns than one pass
+    y2 = ys.copy()
+    y2[rng.random(N) < 0.1] = np.nan
+    mt2 = mt.annotate_cols(**{f"z{i}": y2[:, i] for i in range(P)})
+    ht = hb.linear_regression_rows(y=[[mt2[f"y{i}"] for i in range(P)], [mt2[f"z{i}"] for i in range(P)]],
+                                   x=mt2.GT.n_alt_alleles(), covariates=[1.0] + [mt2[f"c{i}"] for i in range(1, K)])
+    wantc = O.linreg_chained(xf, [ys, y2], cov)
+    for g in range(2):
+        got = {"n": ht.n[:, g], "sum_x": ht.sum_x[:, g]}
+        for f in ("y_transpose_x", "beta", "standard_error", "t_stat", "p_value"):
+            got[f] = ht[f][g]
+        idx = O.complete_samples([ys, y2][g], cov)[2]
+        assert_fields_close(got, {k: v for k, v in wantc[g].items() if k != "_d"}, t_floor=1e-9, ctx=f"chained g={g}",
+                            ytx_abs=ytx_floor_of(xf[:, idx], cov[idx], wantc[g]["standard_error"]))
+        assert np.array_equal(ht.n_missing[g], (x[:, idx] < 0).sum(axis=1))
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
