@@ -129,6 +129,18 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_tensor_peak():
+    """Tensor-pipe roof of the digit sweeps, in TFLOP/s of the kind the kernel issues: MEASURED_PEAKS.json holds cuBLAS bf16
+    (burst and sustained under the power cap); the 4-bit (mxf4) pipe is nominally 4x bf16 and the int8 pipe 2x
+    (B200_PROFILING.md: 2.25 / 4.5 / 9 PFLOP/s dense), so the roof used is that ratio times the MEASURED sustained bf16 figure."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        return float(m.get("bf16_tflops_sustained") or m["bf16_tflops"]), "measured cuBLAS bf16, sustained (MEASURED_PEAKS.json)"
+    except Exception:
+        return 2250.0, "fallback (B200_PROFILING.md nominal 2.25 PFLOP/s bf16)"
+
+
 def config_of(a, N, M, P, K, G, world):
     """The `config` object: the SAME keys and values on both arms for the same command line (the driver compares them)."""
     headline = (N, M, P, G, a.missing_rate, a.strong) == (N_SAMPLES, N_VARIANTS, N_PHENO, 1, 0.0, False)
@@ -330,6 +342,27 @@ def run_ours(a):
                 "kernel": f"{kernel_used} sweep",
                 "kernel_ms": round(sweep, 3), "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src,
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4)}
+    # The same launches against the TENSOR roof (only the many-column configurations are dense contractions):
+    # multiply-adds the sweeps issue = variants x padded samples x MMA columns (x 2 planes on tiles with a missing call),
+    # from the library's own record of the passes it launched.  The roof that takes longer is the binding one.
+    shape = ctx.last_sweep_shape
+    if kernel_used in ("tc", "tc4") and shape[1] > 0:
+        two_plane_share = 1.0 if a.missing_rate > 0 else 0.0   # >= 1 % missing: every 256-variant tile pair holds one
+        col_planes = shape[1] + shape[2] * two_plane_share
+        samples_padded = gt.stride * 4
+        ratio, kind = (4.0, "mxf4 (e2m1 x e2m1)") if kernel_used == "tc4" else (2.0, "int8")
+        bf16, bf16_src = measured_tensor_peak()
+        tflop = 2.0 * launch_rows * samples_padded * col_planes / 1e12
+        t_ach = tflop / (sweep / 1e3)
+        t_peak = ratio * bf16
+        tensor = {"bound": "tensor", "achieved": round(t_ach, 1), "peak": round(t_peak, 1), "unit": "TFLOP/s",
+                  "frac": round(t_ach / t_peak, 4), "kind": kind, "sweep_launches": shape[0], "mma_columns": shape[1],
+                  "two_plane_columns": shape[2], "digit_columns_in_use": shape[3], "two_plane_share_assumed": two_plane_share,
+                  "flop_per_launch": 2.0 * launch_rows * samples_padded * col_planes,
+                  "peak_source": f"{ratio:g} x {bf16_src}; nominal dense {2250.0 * ratio:g} TFLOP/s",
+                  "frac_of_nominal": round(t_ach / (2250.0 * ratio), 4)}
+        roofline["tensor"] = tensor
+        roofline["binding"] = "tensor" if tflop / t_peak > abytes / 1e9 / peak else "hbm"
     # every rank's own sweep-kernel time and clocks (which rank limits the step, and why)
     mine = {"rank": rank, "kernel_ms_min": round(float(np.min(sweep_ms)), 3), "kernel_ms_median": round(float(np.median(sweep_ms)), 3),
             "kernel_ms_max": round(float(np.max(sweep_ms)), 3), "region_ms_per_step": round(my_ms / a.steps, 3),

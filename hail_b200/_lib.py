@@ -97,6 +97,7 @@ SIGNATURES = {
     "lrr_last_kernel": (ctypes.c_int, [ctypes.c_void_p]),
     "lrr_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "lrr_last_sweep_ms": (ctypes.c_float, [ctypes.c_void_p]),
+    "lrr_last_sweep_shape": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "lrr_stream_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int64,
                                         ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32]),
     "lrr_stream_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(GroupOut), ctypes.c_int32,
@@ -183,6 +184,13 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.lrr_launch_count(self.handle))
+
+    @property
+    def last_sweep_shape(self):
+        """(sweep launches, MMA columns over them, columns of two-plane-capable launches, digit columns in use) of the last lrr_run."""
+        out = (ctypes.c_int64 * 4)()
+        self.check(self.lib.lrr_last_sweep_shape(self.handle, out))
+        return tuple(int(v) for v in out)
 
     @property
     def last_kernel(self) -> str:

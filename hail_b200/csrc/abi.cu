@@ -300,6 +300,7 @@ int run_rows_once(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, i
     }
     LRR_CUDA(c, cudaEventRecord(c->ev0, st));
   }
+  c->sweep_shape[0] = c->sweep_shape[1] = c->sweep_shape[2] = c->sweep_shape[3] = 0;
   if (k == LRR_KERNEL_TC4) {
     if (!tc4_supported(c, false, d_row_flags, n_variants, st))
       return fail(c, LRR_EINVAL, "lrr_run: 4-bit tensor-core kernel does not support this configuration: " + c->err);
@@ -328,16 +329,18 @@ int run_rows_once(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags, i
   }
   for (size_t g = 0; g < G; ++g) {
     const double* quantum = nullptr;
+    const double* err_sum = nullptr;
     int n_fit = 0, stride = c->groups[g].C;
     double qscale = 1.0;
     if (k == LRR_KERNEL_TC4) {
       quantum = tc4_quantum(c, (int)g, &n_fit);
+      err_sum = tc4_errsum(c, (int)g);
       stride = c->groups[g].C + 2;
     } else if (k == LRR_KERNEL_TC) {
       quantum = tc_quantum(c, (int)g);
       qscale = 4.0;
     }
-    if (int r = launch_stats_epilogue(c, (int)g, n_variants, outs[g], st, false, quantum, n_fit, stride, qscale)) return r;
+    if (int r = launch_stats_epilogue(c, (int)g, n_variants, outs[g], st, false, quantum, n_fit, stride, qscale, err_sum)) return r;
     if (guarded && !c->groups[g].weighted) {
       // rows the guard listed: float64 recompute of their counts and dot products, then their statistics once more
       const int32_t* list = c->d_flag_list + (int64_t)g * c->reserved_variants;
@@ -817,6 +820,13 @@ int64_t lrr_last_recomputed(lrr_ctx* ctx) {
 
 int64_t lrr_launch_count(const lrr_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->launches : 0; }
 int lrr_last_kernel(const lrr_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->last_kernel : 0; }
+
+int lrr_last_sweep_shape(const lrr_ctx* ctx, int64_t* out4) {
+  if (!ctx || !out4) return LRR_EINVAL;
+  const Ctx* c = reinterpret_cast<const Ctx*>(ctx);
+  for (int i = 0; i < 4; ++i) out4[i] = c->sweep_shape[i];
+  return LRR_OK;
+}
 
 int lrr_set_timing(lrr_ctx* ctx, int enabled) try {
   if (!ctx) return LRR_EINVAL;

@@ -82,6 +82,10 @@ struct Ctx {
   int timing = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
+  // shape of the last lrr_run's tensor-core sweep(s), for the bench's tensor roofline: launches, MMA columns summed over
+  // the launches (N of every pass, padded), the part of them issued by launches whose tiles may also run the
+  // missing-indicator plane (narrow two-plane sweeps), and the digit columns actually used (unpadded)
+  int64_t sweep_shape[4] = {0, 0, 0, 0};
   // device arena of the streaming loop (staging + slots), kept between streams (stream.cu)
   void* arena = nullptr;
   size_t arena_bytes = 0;
@@ -175,6 +179,7 @@ int launch_tc_sweep(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, i
 bool tc_supported(Ctx*, bool may_have_missing);
 const double* tc_quantum(Ctx*, int g);
 const double* tc4_quantum(Ctx*, int g, int* n_fit);
+const double* tc4_errsum(Ctx*, int g);
 int launch_fp64_recompute(Ctx*, int g, const uint8_t* d_packed, int64_t stride, const int32_t* d_list, const int32_t* d_count,
                           int dots_stride, cudaStream_t);
 void tc_invalidate(Ctx*);
@@ -185,9 +190,11 @@ bool tc4_supported(Ctx*, bool single_pass_only, const uint8_t* d_row_flags = nul
 void tc4_invalidate(Ctx*);
 void tc4_release(Ctx*);
 // `quantum` != NULL: per-column quantisation step of the sweep that produced the dots (tolerance guard on); `n_fit`:
-// fitted-value dot products behind the C dot columns; `stride`: doubles per dots row
+// fitted-value dot products behind the C dot columns; `stride`: doubles per dots row; `err_sum`: per-column totals of the
+// basis rounding errors (4-bit sweep), added to the dot products times the row's centring constant
 int launch_stats_epilogue(Ctx*, int g, int64_t M, const lrr_group_out& out, cudaStream_t, bool dense = false,
-                          const double* quantum = nullptr, int n_fit = 0, int stride = 0, double qscale = 1.0);
+                          const double* quantum = nullptr, int n_fit = 0, int stride = 0, double qscale = 1.0,
+                          const double* err_sum = nullptr);
 // the same statistics for the rows listed in d_flag_list (after launch_fp64_recompute)
 int launch_stats_epilogue_listed(Ctx*, int g, const lrr_group_out& out, int stride, cudaStream_t);
 int run_rows(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, int64_t M, int64_t stride, int64_t n_samples_total,

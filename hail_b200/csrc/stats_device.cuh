@@ -96,6 +96,7 @@ struct StatModel {
   int n_fit;              // > 0: dv[C + p] = (fitted-value column of phenotype p) . x, the covariate part of y_transpose_x
   // tolerance guard of the quantised sweeps (NULL = the dots are float64 sums, nothing to guard)
   const double* quantum;  // [C + n_fit] quantisation step of every dot column
+  const double* err_sum;  // [C + n_fit] sum over the samples of (true - stored) basis value, or NULL (4-bit sweep only)
   double qscale;          // the per-sample error is at most qscale * quantum / 2 (int8 sweep: 4, its shifted fields)
   double tol, tol_p;      // relative bounds that pass (half of BASELINE's 1e-6 / 1e-5: the other half is the reference's own roundoff)
   double t_floor;         // an absolute error bound of t (of beta in units of its standard error) below this passes too
@@ -127,8 +128,23 @@ __device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n
   const double xx_imp = a.weighted ? dv[a.Kd + a.P + 1]
                                    : a.dense ? xxc + sum_x * sum_x / (double)a.n : xx_int + (double)nm * mean * mean;
 
+  // Centring (quantised 4-bit sweep): with e_j = true - stored basis value, sum_j e_j x_j = ac sum_j e_j + sum_j e_j (x_j - ac)
+  // for any constant ac.  The first term is known (err_sum) and is added to the dot product; the second is bounded by
+  // (quantum / 2) sum_j |x_j - ac| -- with ac = the call that makes that L1 distance smallest (the row's prevailing
+  // genotype) instead of (quantum / 2) sum_j x_j: 2 x tighter at allele frequency 1/2 (ac = 1), ~1 / (1 - p) x near p = 1.
+  double ac = 0.0;
+  double l1 = S + (double)nm * mean;   // sum_j |x_j - 0| of the imputed column
+  if (a.err_sum && !a.dense) {
+    const double n0 = nv - (double)(n1 + n2);
+    const double l1_1 = n0 + (double)n2 + (double)nm * fabs(mean - 1.0);
+    const double l1_2 = 2.0 * n0 + (double)n1 + (double)nm * (2.0 - mean);
+    if (l1_1 < l1) { l1 = l1_1; ac = 1.0; }
+    if (l1_2 < l1) { l1 = l1_2; ac = 2.0; }
+  }
+  auto dot = [&](int c) { return ac != 0.0 ? fma(ac, a.err_sum[c], dv[c]) : dv[c]; };
+
   double qq = 0.0;
-  for (int c = 0; c < a.Kd; ++c) qq += dv[c] * dv[c];
+  for (int c = 0; c < a.Kd; ++c) qq += dot(c) * dot(c);
   double xxp;  // x.x - qtx.qtx  (LR:141-142)
   if (a.has_intercept) {
     // constant column handled exactly: x.x - (sum_x)^2/n == xx_int - S^2/nv for the mean-imputed column
@@ -136,13 +152,13 @@ __device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n
   } else {
     xxp = xx_imp - qq;
   }
-  const double xyp = dv[a.Kd + p];                   // y_res . x  == ytx - Qty^T qtx (LR:146)
+  const double xyp = dot(a.Kd + p);                  // y_res . x  == ytx - Qty^T qtx (LR:146)
   double proj = 0.0;
   if (a.has_intercept) proj = a.qty[p] * (sum_x / sqrt((double)a.n));
   if (a.n_fit) {
-    proj += dv[a.C + p];
+    proj += dot(a.C + p);
   } else {
-    for (int c = 0; c < a.Kd; ++c) proj += a.qty[(c + a.has_intercept) * a.P + p] * dv[c];
+    for (int c = 0; c < a.Kd; ++c) proj += a.qty[(c + a.has_intercept) * a.P + p] * dot(c);
   }
   double ytx = xyp + proj;                           // LR:143
 
@@ -180,13 +196,14 @@ __device__ inline void variant_stats(const StatModel& a, int64_t v, int p, int n
 
   // ---- tolerance guard (quantised sweeps): rigorous bounds on what the digit quantisation can have changed ----
   if (a.quantum && nv > 0.0) {
-    // every stored basis value is within quantum / 2 of the true one and the imputed column is non-negative, so a dot
-    // product is off by at most (quantum / 2) * sum_j x_j, whatever the genotypes are
-    const double h = 0.5 * a.qscale * (S + (double)nm * mean) * (1.0 + 1e-9);
+    // every stored basis value is within quantum / 2 of the true one, so a (centred, see above) dot product is off by at
+    // most (quantum / 2) * sum_j |x_j - ac|, whatever the genotypes are (ac = 0: sum_j x_j, the imputed column is
+    // non-negative); + the 2^-41 per sample of the fixed-point error total that ac multiplies
+    const double h = 0.5 * a.qscale * l1 * (1.0 + 1e-9) + ac * (double)a.n * 9.1e-13;
     double Eq = 0.0, Eproj = 0.0;
     for (int c = 0; c < a.Kd; ++c) {
       const double e = h * a.quantum[c];
-      Eq += (2.0 * fabs(dv[c]) + e) * e;
+      Eq += (2.0 * fabs(dot(c)) + e) * e;
       if (!a.n_fit) Eproj += fabs(a.qty[(c + a.has_intercept) * a.P + p]) * e;
     }
     const double Ey = h * a.quantum[a.Kd + p];
@@ -246,6 +263,7 @@ inline StatModel stat_model_of(const Group& G, const lrr_group_out& out) {
   a.stride = G.C;
   a.n_fit = 0;
   a.quantum = nullptr;
+  a.err_sum = nullptr;
   a.qscale = 1.0;
   a.tol = 0.5e-6;
   a.tol_p = 0.5e-5;

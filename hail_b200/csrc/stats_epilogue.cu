@@ -113,7 +113,7 @@ double log_beta_half(double a) {
 }
 
 int launch_stats_epilogue(Ctx* c, int g, int64_t M, const lrr_group_out& out, cudaStream_t st, bool dense,
-                          const double* quantum, int n_fit, int stride, double qscale) {
+                          const double* quantum, int n_fit, int stride, double qscale, const double* err_sum) {
   if (M == 0) return LRR_OK;
   const Group& G = c->groups[g];
   EpiArgs a;
@@ -124,6 +124,7 @@ int launch_stats_epilogue(Ctx* c, int g, int64_t M, const lrr_group_out& out, cu
   a.model.dense = dense ? 1 : 0;
   a.model.stride = stride > 0 ? stride : G.C + (dense ? 2 : 0);
   a.model.n_fit = n_fit;
+  if (err_sum && !dense && !G.weighted) a.model.err_sum = err_sum;
   if (quantum && c->guard && !G.weighted) {
     a.model.quantum = quantum;
     a.model.qscale = qscale;

@@ -87,7 +87,7 @@ constexpr int SF_COLS = 16;            // scale-factor columns (A: first 8, B: l
 #endif
 constexpr int MAX_DIGITS = 13;         // base-13 digits per column: 13^13 / 3 < 2^53 / 3, recombined in two int64 halves
 constexpr int PASS_COLS = 112;         // digit columns per sweep: 2 * 112 accumulators + 16 + ring of 4 * 64 <= 512
-constexpr int PASS_COLS_WIDE = 224;    // one-plane-only sweeps (no missing call in the whole input): 224 + 16 + 4 * 64 <= 512
+constexpr int PASS_COLS_WIDE = 240;    // one-plane sweeps of multi-pass configurations: 240 accumulators | ring of 4 * 64 | 16 = 512
 constexpr int UNROLL = 12;             // chunks per unrolled block of the MMA fast path (lcm of NB and NU)
 
 struct GroupMeta {
@@ -816,26 +816,46 @@ __host__ __device__ inline double imax13(int nd) {   // floor(13^nd / 3): every 
 // nibble sample 16 wd + 4 (r + 2) + i -- the order in which the unpack warps emit the calls of a word.
 // The stored value of sample j is I_j * colscale with I_j = rn(v_j / colscale), |I_j| <= imax: |v_j - I_j colscale| <=
 // colscale / 2 (plus 2^-52 |v_j| of the division), the per-sample quantum the statistics epilogue bounds.
+// It also accumulates errfx += sum_j (v_j - I_j colscale) / colscale in 2^-40 fixed point (integer atomics: the sum does
+// not depend on the order), the column's TOTAL rounding error: sum_j e_j x_j = a sum_j e_j + sum_j e_j (x_j - a) for any
+// constant a, so the statistics epilogue adds a * sum_j e_j to the dot product and bounds the rest by
+// (colscale / 2) sum_j |x_j - a| with a = the row's most frequent call (stats_device.cuh).
 __global__ void quantize_kernel(const double* __restrict__ col, int nd, int64_t ns_pad, const double* __restrict__ colmax,
-                                int first_row, uint8_t* __restrict__ bq, double* __restrict__ colscale) {
+                                int first_row, uint8_t* __restrict__ bq, double* __restrict__ colscale,
+                                unsigned long long* __restrict__ errfx) {
   const double imax = imax13(nd);
   const int64_t row_bytes = ns_pad / 2;
   const double cm = *colmax;
+  const double cs = cm > 0.0 ? cm / imax : 0.0;
+  long long err = 0;
   for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < row_bytes; b += (int64_t)gridDim.x * blockDim.x) {
     const int64_t wd = b >> 3;
     const int r = (int)((b >> 2) & 1), i = (int)(b & 3);
     const int64_t j_lo = 16 * wd + 4 * r + i, j_hi = j_lo + 8;
     long long I_lo = 0, I_hi = 0;
     if (cm > 0.0) {
-      I_lo = __double2ll_rn(col[j_lo] / cm * imax);
-      I_hi = __double2ll_rn(col[j_hi] / cm * imax);
+      const double v_lo = col[j_lo], v_hi = col[j_hi];
+      I_lo = __double2ll_rn(v_lo / cm * imax);
+      I_hi = __double2ll_rn(v_hi / cm * imax);
+      // v - I cs with one rounding (fma), in units of cs: within [-1/2, 1/2] up to the roundoff of the division above
+      err += __double2ll_rn(fma(-(double)I_lo, cs, v_lo) / cs * 1099511627776.0);
+      err += __double2ll_rn(fma(-(double)I_hi, cs, v_hi) / cs * 1099511627776.0);
     }
     for (int s = 0; s < nd; ++s) {
       const uint32_t lo = e2m1_code(digit13(I_lo)), hi = e2m1_code(digit13(I_hi));
       bq[(int64_t)(first_row + s) * row_bytes + b] = (uint8_t)(lo | (hi << 4));
     }
-    if (b == 0) *colscale = cm > 0.0 ? cm / imax : 0.0;
+    if (b == 0) *colscale = cs;
   }
+  for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+  if ((threadIdx.x & 31) == 0 && err != 0) atomicAdd(errfx, (unsigned long long)err);
+}
+
+// errsum[k] = (fixed-point total of column k) * 2^-40 * colscale[k]
+__global__ void errsum_kernel(const unsigned long long* __restrict__ errfx, const double* __restrict__ colscale, int n,
+                              double* __restrict__ errsum) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) errsum[k] = (double)(long long)errfx[k] * (1.0 / 1099511627776.0) * colscale[k];
 }
 
 // the "ones" row of a segment: digit value 1.0 for the samples of the group
@@ -926,7 +946,9 @@ struct State {
   std::vector<Pass> passes;
   std::vector<GroupCols> cols;
   uint8_t* d_bq = nullptr;
-  double* d_colscale = nullptr;
+  double* d_colscale = nullptr;   // [2 * nscale]: quantum of every dot column, then the sum of its rounding errors
+  int nscale = 0;
+  unsigned long long* d_errfx = nullptr;   // [nscale] fixed-point accumulators of quantize_kernel
   double* d_colstat = nullptr;   // [2][nscale]: column maxima, sums of squares
   uint32_t* d_mask_hi = nullptr;   // per group: both bits of every kept field
   std::vector<int> scale_off;
@@ -942,6 +964,8 @@ static State* state(Ctx* c) {
 static void free_prepared(State* s) {
   cudaFree(s->d_bq);
   cudaFree(s->d_colscale);
+  cudaFree(s->d_errfx);
+  s->d_errfx = nullptr;
   cudaFree(s->d_colstat);
   cudaFree(s->d_mask_hi);
   for (auto& gc : s->cols) cudaFree(gc.d_fit);
@@ -968,28 +992,44 @@ static int encode_2d(State* s, CUtensorMap* map, const void* ptr, uint64_t inner
 //                             enter x.x - |Q'x|^2, relative error ~1e-7), and y_transpose_x comes from one 11-digit
 //                             fitted-value column per phenotype instead of the covariate projections;
 //   wide profile (P > 2)      phenotype columns 10 digits (|dt| <= 1.5e-7 worst case, ~1e-10 typical: the "stated
-//                             tolerance" of the dense-contraction configuration), covariate columns 13 digits (shared by
-//                             all phenotypes; they carry y_transpose_x).
+//                             tolerance" of the dense-contraction configuration), covariate columns 12 digits (shared by
+//                             all phenotypes; they carry y_transpose_x: error bound ~1e-8 in dot-product units, far inside
+//                             that profile's 5e-7 floor.  12 rather than 13 is what lets BASELINE's 128 phenotypes + 9
+//                             covariates fill exactly six 240-column passes: 1 + 9 * 12 + 13 * 10 and 5 x (1 + 23 * 10)).
 // A column whose maximum is far above 4.5 rms (heavy tails, outliers) gets one more digit per factor 13, up to 13;
 // `boost` (Ctx::digit_boost, raised when too many rows had to be recomputed) adds digits to the covariate / fitted columns.
 // ------------------------------------------------------------------------------------------------
-static int tail_digits(double colmax, double sumsq, int64_t n) {
+static int tail_digits(double colmax, double sumsq, int64_t n, double slack) {
   if (!(colmax > 0.0) || !(sumsq > 0.0) || n <= 0) return 0;
-  const double ratio = colmax / (4.5 * sqrt(sumsq / (double)n));
+  const double ratio = colmax / (slack * 4.5 * sqrt(sumsq / (double)n));
   if (!(ratio > 1.0)) return 0;
   return (int)ceil(log(ratio) / log(13.0) - 1e-9);
 }
 
+// `slack`: how far above 4.5 rms a column's maximum may lie before it costs a digit.  The strict profile's digit counts were
+// sized for exactly that scale with the bound (quantum / 2) sum_j x_j; the centred bound of the statistics epilogue
+// ((quantum / 2) sum_j |x_j - ac|, stats_device.cuh) is 1.57 x tighter at its own worst allele frequency (0.3) than the
+// old one at its design point (0.5) -- relative to x.x - |Q'x|^2 ~ 2 p (1 - p) n -- and no longer grows towards p = 1, so a
+// factor 1.5 is free (a Gaussian column of 400k samples peaks at ~5 rms = 1.1 x).  The wide profile's bounds leave room under its 5e-7 floor: a 10-digit phenotype
+// column is bounded by |dt| <= 1.5e-7 at 4.5 rms, so up to 3 x that scale stays inside; the 12-digit covariate columns
+// (~1e-8 in dot-product units) have a factor 13 = one whole digit.  A Gaussian column of 400k samples peaks at ~5 rms --
+// without the slack every such column paid an eleventh digit (1,526 instead of 1,394 digit columns for BASELINE's
+// 128-phenotype configuration: 7 passes instead of 6).  The per-variant guard enforces the tolerance either way.
 static void digit_policy(const Group& gr, int n_fit, const double* colmax, const double* sumsq, int boost, std::vector<uint8_t>& nd) {
   const bool wide = gr.P > 2;
+  int wide_cov_digits = 12;
+  double y_slack = wide ? 3.0 : 1.5, cov_slack = wide ? 13.0 : 1.5;
+  if (const char* e = tuning_env("LRR_TC4_WIDE_COVD")) { const int v = atoi(e); if (v >= 6 && v <= MAX_DIGITS) wide_cov_digits = v; }
+  if (const char* e = tuning_env("LRR_TC4_SLACK")) { if (atof(e) >= 1.0) { y_slack = atof(e); cov_slack = wide ? 13.0 * atof(e) / 3.0 : atof(e); } }
   const int Cx = gr.C + n_fit;
   nd.resize(Cx);
   for (int c = 0; c < Cx; ++c) {
     int base;
-    if (c < gr.Kd) base = (wide || n_fit == 0 ? 13 : 6 + boost);
-    else if (c < gr.C) base = wide ? 10 + boost : 13;
-    else base = 11 + boost;
-    const int d = base + tail_digits(colmax[c], sumsq[c], gr.n);
+    double slack;
+    if (c < gr.Kd) { base = wide ? wide_cov_digits : (n_fit == 0 ? 13 : 6 + boost); slack = cov_slack; }
+    else if (c < gr.C) { base = wide ? 10 + boost : 13; slack = y_slack; }
+    else { base = 11 + boost; slack = y_slack; }
+    const int d = base + tail_digits(colmax[c], sumsq[c], gr.n, slack);
     nd[c] = (uint8_t)std::min(MAX_DIGITS, std::max(1, d));
   }
 }
@@ -1090,7 +1130,10 @@ static int prepare(Ctx* c, bool wide) {
     return col < gr.C ? gr.d_basis + (int64_t)col * ns_pad : s->cols[g].d_fit + (int64_t)(col - gr.C) * ns_pad;
   };
   LRR_CUDA(c, cudaMalloc(&s->d_colstat, sizeof(double) * 2 * (size_t)nscale));
-  LRR_CUDA(c, cudaMalloc(&s->d_colscale, sizeof(double) * (size_t)nscale));
+  LRR_CUDA(c, cudaMalloc(&s->d_colscale, sizeof(double) * 2 * (size_t)nscale));
+  LRR_CUDA(c, cudaMalloc(&s->d_errfx, sizeof(unsigned long long) * (size_t)nscale));
+  LRR_CUDA(c, cudaMemset(s->d_errfx, 0, sizeof(unsigned long long) * (size_t)nscale));
+  s->nscale = (int)nscale;
   for (size_t g = 0; g < G; ++g) {
     const Group& gr = c->groups[g];
     const int k = s->scale_off[g];
@@ -1134,7 +1177,8 @@ static int prepare(Ctx* c, bool wide) {
       for (int i = 0; i < sg.n_cols; ++i) {
         const int col = sg.c_first + i, k = s->scale_off[sg.group] + col;
         const int nd = s->cols[sg.group].nd[col];
-        quantize_kernel<<<gxb, 256>>>(column_ptr(sg.group, col), nd, ns_pad, s->d_colstat + k, row, s->d_bq, s->d_colscale + k);
+        quantize_kernel<<<gxb, 256>>>(column_ptr(sg.group, col), nd, ns_pad, s->d_colstat + k, row, s->d_bq, s->d_colscale + k,
+                                      s->d_errfx + k);
         row += nd;
         c->launches++;
       }
@@ -1142,6 +1186,8 @@ static int prepare(Ctx* c, bool wide) {
       c->launches++;
     }
   }
+  errsum_kernel<<<(unsigned)((nscale + 255) / 256), 256>>>(s->d_errfx, s->d_colscale, (int)nscale, s->d_colscale + nscale);
+  c->launches++;
   LRR_CUDA(c, cudaGetLastError());
   {
     // exactness guard: no f32 accumulator can leave the exactly-representable range, whatever the genotypes are
@@ -1177,7 +1223,7 @@ static int prepare(Ctx* c, bool wide) {
     ps.mask_bytes = any_masked ? (int)ps.segs.size() * 128 : 0;
     ps.gstage_bytes = (GENO_BYTES + ps.mask_bytes + 1023) / 1024 * 1024;
     // TMEM: accumulators from column 0, scale factors in the top 16 columns, the A ring in between
-    ps.ring_base1 = (ps.ncols + 31) / 32 * 32;
+    ps.ring_base1 = ps.ncols > 224 ? ps.ncols : (ps.ncols + 31) / 32 * 32;   // 240 columns: the ring starts right behind them
     ps.ring_base2 = (2 * ps.ncols + 31) / 32 * 32;
     ps.nu1 = (SF_BASE - ps.ring_base1) / UNIT_COLS >= 6 ? 6 : 4;
     if (const char* e = tuning_env("LRR_TC4_NU1")) { if (atoi(e) == 4) ps.nu1 = 4; }
@@ -1267,6 +1313,13 @@ const double* tc4_quantum(Ctx* c, int g, int* n_fit) {
   return s->d_colscale + s->scale_off[g];
 }
 
+// per-column sum of the rounding errors of the stored basis values (same layout as tc4_quantum)
+const double* tc4_errsum(Ctx* c, int g) {
+  tc4::State* s = tc4::state(c);
+  if (!s->usable) return nullptr;
+  return s->d_colscale + s->nscale + s->scale_off[g];
+}
+
 void tc4_invalidate(Ctx* c) {
   if (!c->tc4_state) return;
   tc4::free_prepared(static_cast<tc4::State*>(c->tc4_state));
@@ -1292,10 +1345,7 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
   if (int r = first_plan_is_wide(c, d_row_flags, M, st, &first_wide)) return r;
   if (int r = prepare(c, s->prepared ? s->wide : first_wide)) return r;
   if (!s->usable) return fail(c, LRR_EINVAL, "4-bit tensor-core kernel unavailable: " + s->why);
-  // More digit columns than one sweep holds: every pass re-reads the genotypes, so fewer, wider passes win -- but a pass of
-  // up to 224 columns has no tensor memory for the missing-indicator plane.  It is used when the input's row flags say
-  // that no row holds a missing call (one small reduction + a 4-byte read per call, only in multi-pass configurations).
-  // More digit columns than one sweep holds: every pass re-reads the genotypes, so the passes are WIDE (up to 224 columns,
+  // More digit columns than one sweep holds: every pass re-reads the genotypes, so the passes are WIDE (up to 240 columns,
   // one accumulator set).  When the row flags say that no row holds a missing call (one small reduction + a 4-byte read per
   // call) a wide pass is one one-plane sweep; otherwise it is SPLIT into two one-plane sweeps -- plane c of every tile, then
   // plane m of the flagged tile pairs, which finishes their rows -- instead of twice as many narrow two-plane sweeps (a
@@ -1373,6 +1423,12 @@ int launch_tc4_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags
 #undef LRR_PICK
     void* args[3] = {(void*)&geno_map, (void*)&sh.b_map, (void*)&p};
     if (int r = tcc::launch_persistent_clusters(c, kfn, cs, THREADS, sh.smem_bytes, p.n_tiles, args, st)) return r;
+    int used = 0;
+    for (const Segment& sg : ps.segs) used += sg.n_digit_cols + 1;
+    c->sweep_shape[0] += 1;
+    c->sweep_shape[1] += ps.ncols;
+    if (mode == 0 && !p.one_plane_only) c->sweep_shape[2] += ps.ncols;   // narrow sweep: flagged tile pairs run plane m too
+    c->sweep_shape[3] += used;
   }
   return LRR_OK;
 }

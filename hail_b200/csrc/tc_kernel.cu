@@ -1148,6 +1148,10 @@ int launch_tc_sweep(Ctx* c, const uint8_t* d_packed, const uint8_t* d_row_flags,
 #undef LRR_PICK
     void* args[3] = {(void*)&geno_map, (void*)&sh.b_map, (void*)&p};
     if (int r = tcc::launch_persistent_clusters(c, kfn, cs, THREADS, sh.smem_bytes, p.n_tiles, args, st)) return r;
+    c->sweep_shape[0] += 1;
+    c->sweep_shape[1] += ps.ncols;
+    c->sweep_shape[2] += ps.ncols;   // every int8 sweep is two-plane capable
+    c->sweep_shape[3] += ps.ncols;
   }
   return LRR_OK;
 }

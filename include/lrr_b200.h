@@ -171,6 +171,12 @@ int lrr_last_kernel(const lrr_ctx* ctx);
  * last lrr_run's sweep (negative if none was recorded). */
 int lrr_set_timing(lrr_ctx* ctx, int enabled);
 float lrr_last_sweep_ms(lrr_ctx* ctx);
+/* measurement hook: shape of the last lrr_run's tensor-core sweep(s) -- out4[0] = sweep launches (passes x planes),
+ * out4[1] = MMA columns N summed over those launches (padded to 16), out4[2] = the part of out4[1] issued by launches whose
+ * tile pairs ALSO run the missing-indicator plane when they hold a missing call (narrow two-plane sweeps; split wide passes
+ * count each plane as its own launch instead), out4[3] = digit columns in use, summed like out4[1].  Tensor work of the run =
+ * variants x padded samples x (out4[1] + out4[2] x share of two-plane tiles) multiply-adds.  All zero after a float64 run. */
+int lrr_last_sweep_shape(const lrr_ctx* ctx, int64_t* out4);
 
 /* ---- the hot call on HOST-resident input: the streaming loop ------------------------------------------
  * The reference's loop consumes each partition's rows as they are decoded from storage (LinearRegression.scala:95,

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 from oracle import bed as obed
 from oracle import linreg_oracle as O
-from tests.helpers import assert_fields_close
+from tests.helpers import assert_fields_close, ytx_floor_of
 from tests.test_gpu_parity import _as_oracle_dict, _big_case, _hb
 
 
@@ -79,8 +79,55 @@ def test_c4_at_its_own_shape(kernel):
         assert _ctx().last_kernel == "tc4"
     want = c_oracle.linreg_group_bed(bed_rows, N, ys, cov)
     assert ht.beta.shape == (M, P)
-    assert_fields_close(_as_oracle_dict(ht), _strip(want), t_floor=1e-9, ctx=f"C4 {kernel}")
+    # P > 2 is the many-phenotype profile: 10-digit phenotype columns, so a y_transpose_x that cancels to ~1e-5 of its scale
+    # is held to that profile's stated floor (5e-7 standard errors of x.y) instead of 1e-6 of itself
+    floor = None
+    if kernel != "tc":
+        floor = ytx_floor_of(obed.decode_rows(bed_rows, N).astype(np.float64), cov, want["standard_error"])
+    assert_fields_close(_as_oracle_dict(ht), _strip(want), t_floor=1e-9, ctx=f"C4 {kernel}", ytx_abs=floor)
     assert int(np.nanargmin(ht.p_value[:, 0])) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("missing_rate", [0.0, 0.02])
+def test_centred_bound_at_extreme_allele_frequencies(missing_rate):
+    """Rows at allele frequency 0.5, ~1 and ~0 (sum x up to 2 n next to a small x.x - |Q'x|^2): the 4-bit sweep's 6-digit
+    covariate columns stay inside the tolerance because the epilogue centres every dot product on the row's prevailing call
+    (adds ac * sum of the basis rounding errors, bounds the rest by (quantum / 2) sum |x - ac|); such rows must neither
+    leave the tolerance nor be sent to the float64 recompute wholesale."""
+    hb = _hb()
+    from oracle import c_oracle
+    N, M, K = 400_000, 512, 10
+    rng = np.random.Generator(np.random.Philox(key=[91, 3]))
+    p = np.concatenate([np.full(64, 0.5), rng.uniform(0.95, 0.9995, 192), rng.uniform(0.0005, 0.05, 192),
+                        rng.uniform(0.3, 0.7, 64)])
+    x = np.empty((M, N), dtype=np.int8)
+    for lo in range(0, M, 64):
+        x[lo:lo + 64] = rng.binomial(2, p[lo:lo + 64, None], size=(min(64, M - lo), N)).astype(np.int8)
+    if missing_rate > 0:
+        for lo in range(0, M, 64):
+            x[lo:lo + 64][rng.random((min(64, M - lo), N)) < missing_rate] = -1
+    gt = hb.PackedGenotypes.from_dosage(x)
+    bed_rows = obed.encode_rows(x)
+    cov = np.column_stack([np.ones(N)] + [rng.standard_normal(N) for _ in range(K - 1)])
+    y = rng.standard_normal(N) + 0.05 * (x[300] == 1)
+    mt = hb.MatrixTable(gt, cols={"y": y, **{f"c{i}": cov[:, i] for i in range(1, K)}})
+    covs = [1.0] + [mt[f"c{i}"] for i in range(1, K)]
+    want = c_oracle.linreg_group_bed(bed_rows, N, y[:, None], cov)
+    ht = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=covs, _kernel="tc4")
+    assert_fields_close(_as_oracle_dict(ht), _strip(want), t_floor=1e-9, ctx=f"extreme AF miss={missing_rate}")
+    # a handful of rows whose y_transpose_x cancels may be listed; the high-frequency rows as a class must not be
+    assert _ctx().last_recomputed <= 8, _ctx().last_recomputed
+    # and with the guard off the centred dot products alone are already inside the tolerance
+    _ctx().check(_ctx().lib.lrr_set_guard(_ctx().handle, 0))
+    try:
+        raw = hb.linear_regression_rows(y=mt.y, x=mt.GT.n_alt_alleles(), covariates=covs, _kernel="tc4")
+    finally:
+        _ctx().check(_ctx().lib.lrr_set_guard(_ctx().handle, 1))
+    rawd = _as_oracle_dict(raw)
+    for f in ("beta", "standard_error", "t_stat"):
+        w = np.asarray(want[f]).reshape(-1)
+        assert O.d_eq(np.asarray(rawd[f]).reshape(-1), w, 1e-6)[np.isfinite(w)].mean() > 0.99, f
 
 
 # ---------------------------------------------------------------------------------------------
