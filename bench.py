@@ -30,7 +30,7 @@ N_SAMPLES, N_VARIANTS, N_COV, N_PHENO = 400_000, 1_000_000, 10, 1
 WORKLOAD = "C2: BN(3 pops) 400k samples x 1M variants, P=1, K=10 (intercept + 9 PCs)"
 METRIC = "genotypes/sec (variants x samples) for linear_regression_rows"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE tc4 sweep launch on the headline workload (ncu --set full)
-TRAFFIC_C2_TC4 = {"bytes": 102427254560, "source": "constant from profiles/r02_c2_tc4_ncu_full.txt (ncu --set full, one launch: 102.164 GB read + 0.263 GB written)"}
+TRAFFIC_C2_TC4 = {"bytes": 103273221120, "source": "constant from profiles/r02b_c2_ncu_full.txt (ncu --set full, one launch of the 80-column sweep: 103.020 GB read + 0.253 GB written)"}
 
 
 def parse():
