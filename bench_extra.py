@@ -117,7 +117,7 @@ def bench_logistic(N, M, K, test):
     # CPU baseline: the oracle's numpy restatement of the reference's per-row loop (LogisticRegression.scala:115-157) on a
     # bounded sample of the same rows, host BLAS threads as configured ("port": the JVM reference cannot run here)
     from oracle import logreg_oracle as LO
-    Ms = 8 if test != "score" else 32
+    Ms = (8 if K <= 12 else 2) if test != "score" else 32
     dos = mt.genotypes.rows(0, Ms).to_dosage().astype(np.float64)
     dos[dos < 0] = np.nan
     t0 = time.perf_counter()
@@ -163,6 +163,9 @@ def main():
     if "logistic" in which:
         for test in ("score", "wald", "lrt", "firth"):
             print(json.dumps(bench_logistic(N, 2048, 10, test)), flush=True)
+    if "logistic_wide" in which:   # wide models: the register form's last size (19 covariates) and the tiled form (32 / 48 / 64 columns)
+        for K in (19, 24, 40, 63):
+            print(json.dumps(bench_logistic(N, 592, K, "wald")), flush=True)
     if "pca" in which:
         print(json.dumps(bench_pca(N, 100000, 5)), flush=True)
 

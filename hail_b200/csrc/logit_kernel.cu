@@ -123,9 +123,12 @@ __device__ bool invert(double (*A)[MM], double (*Inv)[MM], int m, double* logdet
   return true;
 }
 
+constexpr int TS = 32;   // samples per tile of the tiled form (MM > 20)
+
 template <int MM>
 struct Shared {
-  double red[LT / 32][MM + MM * (MM + 1) / 2 + 1];
+  // register form: per-warp partial sums of the score, the Fisher triangle and the log-likelihood; tiled form: scratch only
+  double red[LT / 32][MM <= 20 ? MM + MM * (MM + 1) / 2 + 1 : 4];
   double F[MM][MM];      // Fisher matrix (symmetric, full)
   double W[MM][MM];      // work copy for the solves
   double Inv[MM][MM];
@@ -133,6 +136,13 @@ struct Shared {
   double loglik, logdet, mean;
   int counts[3];
   int status;            // 0 continue, 1 converged, 2 exploded
+};
+
+// tiled form (MM > 20): one tile of the design matrix [TS samples][MM columns] with the samples' weights and residuals
+template <int MM>
+struct Tile {
+  double X[TS][MM + 2];   // row stride a multiple of 16 bytes (128-bit loads of four columns), +2: rows start on different banks
+  double w[TS], r[TS];
 };
 
 // One evaluation over the complete samples at coefficients b[0..m0) (columns m0..m-1 of X do not enter eta).
@@ -270,9 +280,165 @@ __device__ void eval_pass(const LogitArgs& a, Shared<MM>& sh, const uint32_t* ro
   __syncthreads();
 }
 
+// The same evaluation for wide models (20 < m <= MM = 32 / 48 / 64): the (m + 1) m / 2 sums no longer fit the registers of
+// one thread, so the CTA walks the samples in tiles of TS: the tile of X = [covariates | x] is staged in shared memory (the
+// next tile's values travel in registers meanwhile), eight threads per sample form eta -> mu, w, the residual (MODE 1: and
+// the hat value x' Inv x), then the weighted Gram update F += X' diag(w) X runs as 4 x 4 register blocks: thread `tid` owns
+// block (bi >= bj) of the lower triangle for ALL samples, so F needs no reduction and its sum order is fixed; threads
+// nblk .. nblk + MM - 1 own one score entry each.
+template <int MM, int MODE>
+__device__ void eval_pass_tiled(const LogitArgs& a, Shared<MM>& sh, Tile<MM>& tl, const uint32_t* row, const double* drow, int m,
+                                int m0, bool want_loglik) {
+  constexpr int NB = MM / 4, NBLK = NB * (NB + 1) / 2;
+  constexpr int PER = TS * MM / LT;   // staged values per thread and tile
+  static_assert(TS * MM % LT == 0 && NBLK + MM <= LT && LT / TS == 8, "thread mapping of the tiled form");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = a.K;
+  const double mean = sh.mean;
+  int bi = 0, bj = 0;
+  if (tid < NBLK) {
+    int p = 0, rem = tid;
+    while (rem > p) { rem -= p + 1; ++p; }
+    bi = p;
+    bj = rem;
+  }
+  const int sk = tid - NBLK;   // score entry of this thread (0 <= sk < MM)
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  double sc = 0.0, ll = 0.0;
+  // value (k, t) of the tile starting at sample i0: covariate k, the imputed x (k == K), or 0 (padding)
+  auto fetch = [&](int q, int i0) -> double {
+    const int idx = tid + q * LT;
+    const int k = idx / TS, t = idx % TS;
+    const int i = i0 + t;
+    if (i >= a.n || k > K) return 0.0;
+    if (k < K) return __ldg(a.cov + (int64_t)k * a.n + i);
+    const int smp = __ldg(a.idx + i);
+    if (drow) {
+      const double x = __ldg(drow + smp);
+      return x != x ? mean : x;
+    }
+    const uint32_t code = (__ldg(row + (smp >> 4)) >> sample_shift(smp & 15)) & 3u;
+    return code == 3u ? mean : (double)code;
+  };
+  double nxt[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) nxt[q] = fetch(q, 0);
+  for (int i0 = 0; i0 < a.n; i0 += TS) {
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int idx = tid + q * LT;
+      tl.X[idx % TS][idx / TS] = nxt[q];
+    }
+    __syncthreads();
+    if (i0 + TS < a.n) {
+#pragma unroll
+      for (int q = 0; q < PER; ++q) nxt[q] = fetch(q, i0 + TS);
+    }
+    {   // eta, mu, w, residual: eight threads per sample
+      const int t = tid >> 3, part = tid & 7;
+      const double* xr = tl.X[t];
+      double e = 0.0;
+      for (int k = part; k < m0; k += 8) e = fma(sh.b[k], xr[k], e);
+      e += __shfl_xor_sync(0xffffffffu, e, 1);
+      e += __shfl_xor_sync(0xffffffffu, e, 2);
+      e += __shfl_xor_sync(0xffffffffu, e, 4);
+      double h = 0.0;
+      if (MODE == 1) {   // hat value x' Inv x (Inv symmetric)
+        for (int p = part; p < m; p += 8) {
+          double tp = 0.0;
+          for (int c = 0; c < m; ++c) tp = fma(sh.Inv[p][c], xr[c], tp);
+          h = fma(tp, xr[p], h);
+        }
+        h += __shfl_xor_sync(0xffffffffu, h, 1);
+        h += __shfl_xor_sync(0xffffffffu, h, 2);
+        h += __shfl_xor_sync(0xffffffffu, h, 4);
+      }
+      if (part == 0) {
+        const int i = i0 + t;
+        double w = 0.0, r = 0.0;
+        if (i < a.n) {
+          const double mu = 1.0 / (1.0 + exp(-e));
+          const double yi = __ldg(a.y + i);
+          w = mu * (1.0 - mu);
+          r = yi - mu;
+          if (MODE == 0 && want_loglik) ll += log(yi * mu + (1.0 - yi) * (1.0 - mu));
+          if (MODE == 1) r += w * h * (0.5 - mu);
+        }
+        tl.w[t] = w;
+        tl.r[t] = r;
+      }
+    }
+    __syncthreads();
+    if (MODE == 0 && tid < NBLK) {
+#pragma unroll 4
+      for (int t = 0; t < TS; ++t) {
+        const double2 a01 = *reinterpret_cast<const double2*>(&tl.X[t][4 * bi]), a23 = *reinterpret_cast<const double2*>(&tl.X[t][4 * bi + 2]);
+        const double2 b01 = *reinterpret_cast<const double2*>(&tl.X[t][4 * bj]), b23 = *reinterpret_cast<const double2*>(&tl.X[t][4 * bj + 2]);
+        const double wt = tl.w[t];
+        const double av[4] = {a01.x * wt, a01.y * wt, a23.x * wt, a23.y * wt};
+        const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+      }
+    } else if (sk >= 0 && sk < MM) {
+#pragma unroll 8
+      for (int t = 0; t < TS; ++t) sc = fma(tl.X[t][sk], tl.r[t], sc);
+    }
+    __syncthreads();
+  }
+  if (MODE == 0 && tid < NBLK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = 4 * bi + i, c = 4 * bj + j;
+        if (c <= p) {
+          sh.F[p][c] = acc[i][j];
+          sh.F[c][p] = acc[i][j];
+        }
+      }
+  }
+  if (sk >= 0 && sk < MM) sh.score[sk] = sc;
+  if (MODE == 0) {
+    ll = warp_sum(ll);
+    if (lane == 0) sh.red[warp][0] = ll;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < LT / 32; ++w) t += sh.red[w][0];
+      sh.loglik = t;
+    }
+  }
+  __syncthreads();
+}
+
+template <int MM, int MODE>
+__device__ __forceinline__ void eval_any(const LogitArgs& a, Shared<MM>& sh, const uint32_t* row, const double* drow, int m, int m0,
+                                         bool want_loglik) {
+  if constexpr (MM <= 20) {
+    eval_pass<MM, MODE>(a, sh, row, drow, m, m0, want_loglik);
+  } else {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    Tile<MM>& tl = *reinterpret_cast<Tile<MM>*>(s_dyn + (sizeof(Shared<MM>) + 15) / 16 * 16);
+    eval_pass_tiled<MM, MODE>(a, sh, tl, row, drow, m, m0, want_loglik);
+  }
+}
+
+template <int MM>
+constexpr size_t logit_smem_bytes() {
+  return (sizeof(Shared<MM>) + 15) / 16 * 16 + (MM > 20 ? sizeof(Tile<MM>) : 0);
+}
+
 template <int MM>
 __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
-  __shared__ Shared<MM> sh;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  Shared<MM>& sh = *reinterpret_cast<Shared<MM>*>(s_dyn);
   const int K = a.K, m = K + 1;
   const double* b0 = a.null_fit;
   const double* score0 = a.null_fit + K;
@@ -337,7 +503,7 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
 
     if (a.test != 3) {
       // =============== Wald / LRT: LogisticRegressionModel.fit(Some(nullFit)) ===============
-      eval_pass<MM, 0>(a, sh, row, drow, m, m, false);
+      eval_any<MM, 0>(a, sh, row, drow, m, m, false);
       if (threadIdx.x == 0) {   // the covariate blocks of the first step are the null fit's (:311-325)
         for (int i = 0; i < K; ++i) {
           sh.score[i] = score0[i];
@@ -375,7 +541,7 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
         const int st = sh.status;
         if (st == 1) { converged = true; break; }
         if (st == 2) { exploded = true; break; }
-        eval_pass<MM, 0>(a, sh, row, drow, m, m, false);
+        eval_any<MM, 0>(a, sh, row, drow, m, m, false);
       }
       if (converged) {
         if (a.test == 1) {
@@ -392,7 +558,7 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
             pv = erfc(fabs(z) * 0.70710678118654752440);   // 2 pnorm(-|z|)
           }
         } else {
-          eval_pass<MM, 0>(a, sh, row, drow, m, m, true);         // logLkhd at the final mu (:365)
+          eval_any<MM, 0>(a, sh, row, drow, m, m, true);         // logLkhd at the final mu (:365)
           beta = sh.b[K];
           chi2 = 2.0 * (sh.loglik - loglk0);
           pv = chi2 > 0.0 ? erfc(sqrt(0.5 * chi2)) : (chi2 == chi2 ? 1.0 : chi2);   // pchisqtail(chi2, 1)
@@ -407,7 +573,7 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
         converged = exploded = false;
         while (!converged && !exploded && iter < a.max_iter) {
           ++iter;
-          eval_pass<MM, 0>(a, sh, row, drow, m, m0, true);         // F = X' W X over all m columns at mu(b[0..m0))
+          eval_any<MM, 0>(a, sh, row, drow, m, m0, true);         // F = X' W X over all m columns at mu(b[0..m0))
           if (threadIdx.x == 0) {
             for (int i = 0; i < m; ++i)
               for (int j = 0; j < m; ++j) sh.W[i][j] = sh.F[i][j];
@@ -416,7 +582,7 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
           __syncthreads();
           if (sh.status == 2) { exploded = true; break; }
           const double ll_here = sh.loglik + 0.5 * sh.logdet;   // + sum log|diag R| (:397-399)
-          eval_pass<MM, 1>(a, sh, row, drow, m, m0, false);
+          eval_any<MM, 1>(a, sh, row, drow, m, m0, false);
           if (threadIdx.x == 0) {
             for (int i = 0; i < m0; ++i) {
               sh.delta[i] = sh.score[i];
@@ -475,8 +641,14 @@ __global__ void __launch_bounds__(LT) logit_fit_kernel(LogitArgs a) {
 }
 
 template <int MM>
-void launch_mm(const LogitArgs& a, int grid, cudaStream_t st) {
-  logit_fit_kernel<MM><<<grid, LT, 0, st>>>(a);
+cudaError_t launch_mm(const LogitArgs& a, int grid, cudaStream_t st) {
+  constexpr size_t smem = logit_smem_bytes<MM>();
+  if (smem > 48 * 1024) {   // per device, so set on every launch (a second GPU in the same process has its own attribute)
+    const cudaError_t e = cudaFuncSetAttribute(logit_fit_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  logit_fit_kernel<MM><<<grid, LT, smem, st>>>(a);
+  return cudaSuccess;
 }
 
 void free_model(LogitModel* m) {
@@ -499,7 +671,7 @@ int logit_set_model(Ctx* c, int64_t n_samples_total, int32_t n, int32_t K, const
                     const double* y, const double* b0, const double* score0, const double* fisher0, double loglk0) {
   if (n_samples_total <= 0 || n <= 0 || n > n_samples_total) return fail(c, LRR_EINVAL, "lrr_set_logit_model: bad sample counts");
   if (K < 1) return fail(c, LRR_EINVAL, "logistic regression requires at least one covariate expression");
-  if (K + 1 > 20) return fail(c, LRR_EINVAL, "lrr_set_logit_model: at most 19 covariates (the Fisher matrix lives in registers)");
+  if (K + 1 > 64) return fail(c, LRR_EINVAL, "lrr_set_logit_model: at most 63 covariates");
   if (n - K - 1 < 1) {
     char buf[160];
     snprintf(buf, sizeof buf, "%d samples and %d %s (including x) implies %d degrees of freedom.", n, K + 1,
@@ -559,16 +731,21 @@ int logit_run(Ctx* c, const uint8_t* d_packed, const double* d_dense, int64_t M,
   const int64_t want = M < (int64_t)c->sm_count * 8 ? M : (int64_t)c->sm_count * 8;
   const int grid = (int)want;
   const int mm = m->K + 1;
-  if (mm <= 2) launch_mm<2>(a, grid, st);
-  else if (mm <= 3) launch_mm<3>(a, grid, st);
-  else if (mm <= 4) launch_mm<4>(a, grid, st);
-  else if (mm <= 5) launch_mm<5>(a, grid, st);
-  else if (mm <= 6) launch_mm<6>(a, grid, st);
-  else if (mm <= 8) launch_mm<8>(a, grid, st);
-  else if (mm <= 10) launch_mm<10>(a, grid, st);
-  else if (mm <= 12) launch_mm<12>(a, grid, st);
-  else if (mm <= 16) launch_mm<16>(a, grid, st);
-  else launch_mm<20>(a, grid, st);
+  cudaError_t le;
+  if (mm <= 2) le = launch_mm<2>(a, grid, st);
+  else if (mm <= 3) le = launch_mm<3>(a, grid, st);
+  else if (mm <= 4) le = launch_mm<4>(a, grid, st);
+  else if (mm <= 5) le = launch_mm<5>(a, grid, st);
+  else if (mm <= 6) le = launch_mm<6>(a, grid, st);
+  else if (mm <= 8) le = launch_mm<8>(a, grid, st);
+  else if (mm <= 10) le = launch_mm<10>(a, grid, st);
+  else if (mm <= 12) le = launch_mm<12>(a, grid, st);
+  else if (mm <= 16) le = launch_mm<16>(a, grid, st);
+  else if (mm <= 20) le = launch_mm<20>(a, grid, st);
+  else if (mm <= 32) le = launch_mm<32>(a, grid, st);   // tiled form: Fisher blocks in registers, X tiles in shared memory
+  else if (mm <= 48) le = launch_mm<48>(a, grid, st);
+  else le = launch_mm<64>(a, grid, st);
+  LRR_CUDA(c, le);
   c->launches++;
   LRR_CUDA(c, cudaGetLastError());
   return LRR_OK;

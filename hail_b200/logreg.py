@@ -171,8 +171,8 @@ def logistic_regression_rows(test, y, x, covariates, pass_through=(), *, max_ite
             host = {f: np.empty((M, P), dtype={"n_iterations": np.int32, "converged": bool, "exploded": bool}.get(f, np.float64))
                     for f in dev_out}
             Ct = np.ascontiguousarray(C.T)                              # [K, n]
-            if k > 19:   # the per-variant Newton fits keep the (K + 1)^2 Fisher triangle in registers (csrc/logit_kernel.cu)
-                raise ValueError(f"logistic_regression_rows: test={test!r} supports at most 19 covariates on the device "
+            if k > 63:   # csrc/logit_kernel.cu: register form up to 19 covariates, tiled form (32 / 48 / 64 columns) up to 63
+                raise ValueError(f"logistic_regression_rows: test={test!r} supports at most 63 covariates on the device "
                                  f"(found {k}); use test='score' for wider models")
             for col in range(P):
                 b, mu, score, fisher, it, converged, exploded = _fit_null_checked(C, yk[:, col], max_iterations, tolerance)

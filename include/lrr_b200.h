@@ -235,7 +235,8 @@ int lrr_run_score_dense(lrr_ctx* ctx, const double* d_x, int64_t n_variants, int
  * in float64 on the mean-imputed genotype column.  The host fits the null model once (LogisticRegression.scala:67-91)
  * and passes, for the n complete samples (ascending complete_idx): cov [K, n], y [n] (0 / 1), the null coefficients
  * b0 [K], and the null fit's last score [K], Fisher matrix [K, K] and log-likelihood (the first Newton step of the full
- * model reuses them, LogisticRegressionModel.scala:311-325).  K <= 19.
+ * model reuses them, LogisticRegressionModel.scala:311-325).  K <= 63 (up to 19 covariates the per-thread register form,
+ * above that the Fisher matrix is accumulated as 4 x 4 register blocks over shared-memory tiles of the design matrix).
  * lrr_run_logit writes, per variant, the fields of the test's schema (`standard_error`, `z_stat`: Wald only;
  * `chi_sq_stat`: LRT / Firth only; NaN where the reference leaves them missing: fit not converged or singular) and the
  * `fit` struct (n_iterations, converged, exploded).  NULL output pointers are skipped. */
