@@ -166,6 +166,9 @@ def main():
     if "logistic_wide" in which:   # wide models: the register form's last size (19 covariates) and the tiled form (32 / 48 / 64 columns)
         for K in (19, 24, 40, 63):
             print(json.dumps(bench_logistic(N, 592, K, "wald")), flush=True)
+    if "logistic_mid" in which:   # 12 - 19 covariates: register form (2 / 4 slices) against the tiled form (tuning builds: LRR_LOGIT_TILED_FROM)
+        for K in (10, 12, 15, 19):
+            print(json.dumps(bench_logistic(N, 592, K, "wald")), flush=True)
     if "pca" in which:
         print(json.dumps(bench_pca(N, 100000, 5)), flush=True)
 

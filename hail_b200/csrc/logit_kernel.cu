@@ -732,7 +732,10 @@ int logit_run(Ctx* c, const uint8_t* d_packed, const double* d_dense, int64_t M,
   const int grid = (int)want;
   const int mm = m->K + 1;
   cudaError_t le;
-  if (mm <= 2) le = launch_mm<2>(a, grid, st);
+  int tiled_from = 21;   // smallest m that takes the tiled form
+  if (const char* e = tuning_env("LRR_LOGIT_TILED_FROM")) tiled_from = atoi(e);
+  if (mm >= tiled_from && mm <= 32) le = launch_mm<32>(a, grid, st);
+  else if (mm <= 2) le = launch_mm<2>(a, grid, st);
   else if (mm <= 3) le = launch_mm<3>(a, grid, st);
   else if (mm <= 4) le = launch_mm<4>(a, grid, st);
   else if (mm <= 5) le = launch_mm<5>(a, grid, st);
