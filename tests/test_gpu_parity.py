@@ -361,6 +361,11 @@ def test_full_sample_size_parity_vs_c_oracle(N, missing_rate):
         assert_fields_close(got, {k: v for k, v in want.items() if k != "_d"}, t_floor=1e-9,
                             ctx=f"{kernel} N={N} miss={missing_rate}")
         res[kernel] = ht
+        if kernel == "tc4" and missing_rate == 0.0:
+            # BASELINE's headline shape runs 80 MMA columns: 9 six-digit covariate columns + 13 + 11 digits for the phenotype
+            # and its fitted-value column + the "ones" row (Gaussian columns must not cost a tail digit: DESIGN.md 5.1c)
+            from hail_b200 import _lib
+            assert _lib.context(0).last_sweep_shape == (1, 80, 80, 79), _lib.context(0).last_sweep_shape
         # the causal variant is by far the strongest signal and its log10 p is finite
         assert int(np.nanargmin(ht.p_value)) == 0 and np.isfinite(ht.log10_p[0]) and ht.log10_p[0] < -6
     # the kernels agree far below the tolerance (exact integer paths vs float64 FMA path)

@@ -77,6 +77,10 @@ def test_c4_at_its_own_shape(kernel):
                                    covariates=[1.0] + [mt[f"c{i}"] for i in range(1, K)], _kernel=kernel)
     if kernel == "auto":
         assert _ctx().last_kernel == "tc4"
+        # the digit policy is part of the contract (it silently cost a seventh pass for most of round 2): 128 ten-digit
+        # phenotype columns + 9 twelve-digit covariate columns + one "ones" row per pass fill SIX 240-column passes
+        launches, mma_cols, _, digit_cols = _ctx().last_sweep_shape
+        assert (launches, mma_cols, digit_cols) == (6, 1440, 128 * 10 + 9 * 12 + 6), _ctx().last_sweep_shape
     want = c_oracle.linreg_group_bed(bed_rows, N, ys, cov)
     assert ht.beta.shape == (M, P)
     # P > 2 is the many-phenotype profile: 10-digit phenotype columns, so a y_transpose_x that cancels to ~1e-5 of its scale
