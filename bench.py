@@ -48,6 +48,7 @@ def parse():
                     help="BASELINE config 3: y=[[y1],[y2]] with 10 %% / 20 %% phenotype missingness (use with --missing-rate 0.25)")
     ap.add_argument("--e2e-variants", type=int, default=131072,
                     help="variants per GPU and step of the end-to-end leg (host .bed bytes; 131072 x 400k samples = 13.1 GB)")
+    ap.add_argument("--e2e-reps", type=int, default=5, help="timed repetitions of the end-to-end leg (the median is reported)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -166,6 +167,7 @@ def run_ours(a):
     import hail_b200 as hb
     from hail_b200 import _lib, bn
     from hail_b200 import dist as hd
+    from hail_b200 import statgen
     from hail_b200.statgen import GroupBasis
 
     rank = int(os.environ.get("RANK", 0))
@@ -423,15 +425,17 @@ def run_ours(a):
         GroupBasis(y[:, :1], cov, np.arange(N))
         prologue_s = time.time() - t_p
         barrier()
-        reps = 5
+        reps = max(1, a.e2e_reps)
         times = []
         h2d_in_call = []
+        phases = []
         for _ in range(reps):     # each repetition is timed on its own: barrier, wall clock around the public call, barrier
             t_e = time.time()
             ht = e2e_step()
             barrier()
             times.append(time.time() - t_e)
             h2d_in_call.append(float(lib.lrr_last_stream_h2d_ms(ctx.handle)))
+            phases.append({k: round(v, 1) for k, v in statgen.LAST_STREAM_PHASES.items()})
         # the host link is shared with other tenants of the box: single repetitions are occasionally 2x slower.  The
         # reported value uses the MEDIAN repetition; the mean is kept next to it.
         tt = torch.tensor(times, dtype=torch.float64, device=dev)
@@ -452,6 +456,7 @@ def run_ours(a):
                          "h2d_window_ms_in_call": [round(v, 1) for v in h2d_in_call],
                          "h2d_gbps_in_call": round(Me * bed_stride / (float(np.median(h2d_in_call)) / 1e3) / 1e9, 2) if min(h2d_in_call) > 0 else None,
                          "stage_seconds": stages, "slowest_stage": max(stages, key=stages.get),
+                         "host_phase_ms_per_rep": phases,
                          "sample": f"{Me} variants x {N} samples per GPU per step: page-locked host .bed bytes -> "
                                    "HostBedGenotypes -> linear_regression_rows (block-streamed H2D overlapped with the "
                                    "host QR prologue and the sweep; result rows D2H to numpy), PCIe-bound"}

@@ -5,6 +5,9 @@
 #include <algorithm>
 #include <vector>
 
+#include <chrono>
+#include <cstdio>
+
 #include "common.cuh"
 
 namespace lrr {
@@ -205,7 +208,10 @@ void release_caches(Ctx* c) {
   c->d_stage_view = nullptr;
   c->h_stage_bytes = 0;
   c->stage_ev_valid = false;
-  if (c->groups.empty()) free_workspace(c);
+  if (c->groups.empty()) {
+    free_workspace(c);
+    tc4_trim(c);
+  }
 }
 
 int run_begin(Ctx* c, cudaStream_t st) {
@@ -498,10 +504,14 @@ int lrr_clear_groups(lrr_ctx* ctx) try {
   DeviceGuard guard(c->device);
   // no device synchronisation: the buffers are kept (retire_group) and their next writer, lrr_add_group, is ordered
   // behind the runs still in flight through busy_ev
+  const bool trace = tuning_env("LRR_TRACE") != nullptr;
+  auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tr0 = trace ? now_us() : 0.0;
   for (auto& g : c->groups) retire_group(c, g);
   c->groups.clear();
   tc_invalidate(c);
   tc4_invalidate(c);
+  if (trace) fprintf(stderr, "[lrr trace] clear_groups: %.0f us\n", now_us() - tr0);
   c->dots_offset.clear();
   c->flag_pending = false;
   c->digit_boost = 0;

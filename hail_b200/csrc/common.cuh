@@ -189,6 +189,7 @@ int launch_tc4_sweep(Ctx*, const uint8_t* d_packed, const uint8_t* d_row_flags, 
 bool tc4_supported(Ctx*, bool single_pass_only, const uint8_t* d_row_flags = nullptr, int64_t M = 0, cudaStream_t st = nullptr);
 void tc4_invalidate(Ctx*);
 void tc4_release(Ctx*);
+void tc4_trim(Ctx*);
 // `quantum` != NULL: per-column quantisation step of the sweep that produced the dots (tolerance guard on); `n_fit`:
 // fitted-value dot products behind the C dot columns; `stride`: doubles per dots row; `err_sum`: per-column totals of the
 // basis rounding errors (4-bit sweep), added to the dot products times the row's centring constant

@@ -15,6 +15,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <vector>
 
 #include "common.cuh"
@@ -168,6 +170,10 @@ int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64
   if (n_variants > 0 && !h_bed) return fail(c, LRR_EINVAL, "lrr_stream_begin: h_bed is NULL");
   if (c->streams_alive) return fail(c, LRR_ESTATE, "lrr_stream_begin: another stream of this context is still open (lrr_stream_end it first)");
   DeviceGuard guard(c->device);
+  const bool trace = tuning_env("LRR_TRACE") != nullptr;   // tuning builds only: where lrr_stream_begin spends host time
+  auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tr0 = trace ? now_us() : 0.0;
+  double tr1 = 0, tr2 = 0, tr3 = 0, tr4 = 0;
   Stream* s = new Stream();
   c->streams_alive++;
   s->ctx = c;
@@ -192,6 +198,7 @@ int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64
     depth = (int)std::max<int64_t>(3, budget / (s->block * s->stride));
   }
   s->depth = (int)std::max<int64_t>(1, std::min<int64_t>(depth, std::max<int64_t>(s->n_blocks, 1)));
+  if (trace) tr1 = now_us();
   auto bail = [&](int code) {
     destroy(s);
     return code;
@@ -207,6 +214,7 @@ int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64
   TRY(cudaStreamCreateWithFlags(&s->s_d2h, cudaStreamNonBlocking));
   TRY(cudaEventCreate(&s->h2d_first));
   TRY(cudaEventCreate(&s->h2d_last));
+  if (trace) tr2 = now_us();
   // one arena for the staging buffers and the slots, cached on the context across streams (cudaMalloc / cudaFree of
   // tens of GB would otherwise sit in front of the first copy of every call)
   const int n_stage = (int)std::min<int64_t>(N_STAGE, s->n_blocks);
@@ -244,9 +252,15 @@ int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64
     a += flag_bytes;
   }
 #undef TRY
+  if (trace) tr3 = now_us();
   for (int64_t b = 0; b < s->n_blocks && b < s->depth; ++b) {
     if (int r = issue_load(s, b)) return bail(r);
     s->next_load = b + 1;
+  }
+  if (trace) {
+    tr4 = now_us();
+    fprintf(stderr, "[lrr trace] stream_begin: mem info %.0f us, streams %.0f us, arena + events %.0f us, first loads %.0f us\n",
+            tr1 - tr0, tr2 - tr1, tr3 - tr2, tr4 - tr3);
   }
   *out = reinterpret_cast<lrr_stream*>(s);
   return LRR_OK;

@@ -954,21 +954,36 @@ struct State {
   std::vector<int> scale_off;
   int cluster = 2;
   bool attr_set = false;
+  // The buffers above live in grow-only pools that survive free_prepared: lrr_clear_groups runs at the start of every public
+  // call, and a cudaFree there is a device synchronisation plus a trip through the kernel driver that took 20 - 570 ms in one
+  // call out of four on a shared box (profiles/r02b_e2e_clear_groups_trace.txt).  Reuse is ordered like the group buffers:
+  // prepare() writes them on the default stream behind lrr_add_group, which waits for the runs still in flight (busy_ev).
+  struct Pool {
+    void* p = nullptr;
+    size_t cap = 0;
+  };
+  Pool pool_bq, pool_colscale, pool_errfx, pool_colstat, pool_mask, pool_fit;
 };
+
+static int pool_take(Ctx* c, State::Pool& pl, size_t need, void** out) {
+  if (need > pl.cap) {
+    cudaFree(pl.p);
+    pl.p = nullptr;
+    pl.cap = 0;
+    LRR_CUDA(c, cudaMalloc(&pl.p, need));
+    pl.cap = need;
+  }
+  *out = pl.p;
+  return LRR_OK;
+}
 
 static State* state(Ctx* c) {
   if (!c->tc4_state) c->tc4_state = new State();
   return static_cast<State*>(c->tc4_state);
 }
 
-static void free_prepared(State* s) {
-  cudaFree(s->d_bq);
-  cudaFree(s->d_colscale);
-  cudaFree(s->d_errfx);
+static void free_prepared(State* s) {   // forgets the plan; the device buffers stay in their pools
   s->d_errfx = nullptr;
-  cudaFree(s->d_colstat);
-  cudaFree(s->d_mask_hi);
-  for (auto& gc : s->cols) cudaFree(gc.d_fit);
   s->cols.clear();
   s->d_mask_hi = nullptr;
   s->d_bq = nullptr;
@@ -977,6 +992,14 @@ static void free_prepared(State* s) {
   s->passes.clear();
   s->prepared = false;
   s->usable = false;
+}
+
+static void free_pools(State* s) {
+  for (State::Pool* pl : {&s->pool_bq, &s->pool_colscale, &s->pool_errfx, &s->pool_colstat, &s->pool_mask, &s->pool_fit}) {
+    cudaFree(pl->p);
+    pl->p = nullptr;
+    pl->cap = 0;
+  }
 }
 
 static int encode_2d(State* s, CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride,
@@ -1118,8 +1141,20 @@ static int prepare(Ctx* c, bool wide) {
     gc.n_fit = (gr.P <= 2 && gr.Kd > 0) ? gr.P : 0;   // the spare two slots of a dots row hold their dot products
     s->scale_off[g] = nscale;
     nscale += gr.C + gc.n_fit;
-    if (gc.n_fit) {
-      LRR_CUDA(c, cudaMalloc(&gc.d_fit, sizeof(double) * (size_t)gc.n_fit * (size_t)ns_pad));
+  }
+  {
+    size_t fit_cols = 0;
+    for (size_t g = 0; g < G; ++g) fit_cols += (size_t)s->cols[g].n_fit;
+    void* fit_base = nullptr;
+    if (fit_cols)
+      if (int r = pool_take(c, s->pool_fit, sizeof(double) * fit_cols * (size_t)ns_pad, &fit_base)) return r;
+    size_t at = 0;
+    for (size_t g = 0; g < G; ++g) {
+      const Group& gr = c->groups[g];
+      GroupCols& gc = s->cols[g];
+      if (!gc.n_fit) continue;
+      gc.d_fit = static_cast<double*>(fit_base) + at * (size_t)ns_pad;
+      at += (size_t)gc.n_fit;
       for (int p = 0; p < gc.n_fit; ++p)
         fitted_kernel<<<gx, 256>>>(gr.d_basis, gr.d_qty, gr.Kd, gr.P, gr.has_intercept, p, ns_pad, gc.d_fit + (int64_t)p * ns_pad);
       c->launches += gc.n_fit;
@@ -1129,9 +1164,9 @@ static int prepare(Ctx* c, bool wide) {
     const Group& gr = c->groups[g];
     return col < gr.C ? gr.d_basis + (int64_t)col * ns_pad : s->cols[g].d_fit + (int64_t)(col - gr.C) * ns_pad;
   };
-  LRR_CUDA(c, cudaMalloc(&s->d_colstat, sizeof(double) * 2 * (size_t)nscale));
-  LRR_CUDA(c, cudaMalloc(&s->d_colscale, sizeof(double) * 2 * (size_t)nscale));
-  LRR_CUDA(c, cudaMalloc(&s->d_errfx, sizeof(unsigned long long) * (size_t)nscale));
+  if (int r = pool_take(c, s->pool_colstat, sizeof(double) * 2 * (size_t)nscale, reinterpret_cast<void**>(&s->d_colstat))) return r;
+  if (int r = pool_take(c, s->pool_colscale, sizeof(double) * 2 * (size_t)nscale, reinterpret_cast<void**>(&s->d_colscale))) return r;
+  if (int r = pool_take(c, s->pool_errfx, sizeof(unsigned long long) * (size_t)nscale, reinterpret_cast<void**>(&s->d_errfx))) return r;
   LRR_CUDA(c, cudaMemset(s->d_errfx, 0, sizeof(unsigned long long) * (size_t)nscale));
   s->nscale = (int)nscale;
   for (size_t g = 0; g < G; ++g) {
@@ -1158,10 +1193,10 @@ static int prepare(Ctx* c, bool wide) {
     ps.bq_row0 = total_rows;
     total_rows += ps.ncols;
   }
-  LRR_CUDA(c, cudaMalloc(&s->d_bq, (size_t)total_rows * row_bytes));
+  if (int r = pool_take(c, s->pool_bq, (size_t)total_rows * row_bytes, reinterpret_cast<void**>(&s->d_bq))) return r;
   LRR_CUDA(c, cudaMemset(s->d_bq, 0, (size_t)total_rows * row_bytes));
   const int64_t mask_words = ns_pad / 16;
-  LRR_CUDA(c, cudaMalloc(&s->d_mask_hi, sizeof(uint32_t) * (size_t)mask_words * G));
+  if (int r = pool_take(c, s->pool_mask, sizeof(uint32_t) * (size_t)mask_words * G, reinterpret_cast<void**>(&s->d_mask_hi))) return r;
   bool any_masked = false;
   for (size_t g = 0; g < G; ++g) {
     const Group& gr = c->groups[g];
@@ -1325,10 +1360,18 @@ void tc4_invalidate(Ctx* c) {
   tc4::free_prepared(static_cast<tc4::State*>(c->tc4_state));
 }
 
+// lrr_trim: give the pools back once no plan uses them
+void tc4_trim(Ctx* c) {
+  if (!c->tc4_state) return;
+  tc4::State* s = static_cast<tc4::State*>(c->tc4_state);
+  if (!s->prepared) tc4::free_pools(s);
+}
+
 void tc4_release(Ctx* c) {
   if (!c->tc4_state) return;
   tc4::State* s = static_cast<tc4::State*>(c->tc4_state);
   tc4::free_prepared(s);
+  tc4::free_pools(s);
   cudaFree(s->d_any);
   cudaFree(s->d_bound);
   if (s->h_any) cudaFreeHost(s->h_any);

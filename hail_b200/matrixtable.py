@@ -225,7 +225,7 @@ def _as_float_col(v):
     a = np.asarray(v)
     if a.dtype == object:  # None -> missing
         return np.array([np.nan if e is None else float(e) for e in a], dtype=np.float64)
-    return a.astype(np.float64)
+    return a.astype(np.float64, copy=False)   # float64 columns are used as they are (expressions never write into them)
 
 
 class Struct(dict):

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import itertools
+import time
 import logging
 import warnings
 from collections import OrderedDict
@@ -124,11 +125,16 @@ class GroupBasis:
                  "    with input variable x, and %d additional %s...", tag, n, P, _plural(P, "variable"), K,
                  _plural(K, "covariate"))  # LR:60-63 / 241-244
         self.weighted = weights is not None
+        col_index = np.asarray(col_index)
+        if n < n_cols:   # (every sample complete: no 32 MB copies of what is already there)
+            ys, cov, col_index = ys[keep], cov[keep], col_index[keep]
+            if self.weighted:
+                weights = weights[keep]
         with _blas_limits(limits=1):
             if self.weighted:
-                self._build_weighted(ys[keep], cov[keep], np.sqrt(weights[keep]), np.asarray(col_index)[keep], n, K, P, d)
+                self._build_weighted(ys, cov, np.sqrt(weights), col_index, n, K, P, d)
             else:
-                self._build(ys[keep], cov[keep], np.asarray(col_index)[keep], n, K, P, d)
+                self._build(ys, cov, col_index, n, K, P, d)
 
     def _build_weighted(self, y, c, sw, kept_index, n, K, P, d):
         """statgen.py:557-581: y and the covariates are scaled by sqrt(w) before the QR; x is scaled on the device
@@ -156,19 +162,21 @@ class GroupBasis:
     def _build(self, y, c, kept_index, n, K, P, d):
         self.n, self.K, self.P, self.d = n, K, P, d
         self.complete_idx = np.ascontiguousarray(kept_index, dtype=np.int32)  # into the packed store
+        # everything below works on TRANSPOSED planes ([K, n], [P, n]: what the device consumes), so that no n x K array is
+        # ever transposed or re-stacked: the prologue runs next to a host -> device copy that takes the memory bus
         if K > 0:
-            q, has_intercept = orthonormal_basis(c)    # LR:67 (only Q Q^T enters the results)
+            q_t, has_intercept = orthonormal_basis_t(c)    # LR:67 (only Q Q^T enters the results)
         else:
-            q, has_intercept = np.zeros((n, 0)), False
-        qty = q.T @ y                                  # LR:71
+            q_t, has_intercept = np.zeros((0, n)), False
+        qty = q_t @ y                                  # LR:71  [K, P]
         self.has_intercept = has_intercept
-        self.qty = np.ascontiguousarray(qty)           # [K, P]
+        self.qty = np.ascontiguousarray(qty)
         self.yyp = np.ascontiguousarray(np.einsum("ij,ij->j", y, y) - np.einsum("ij,ij->j", qty, qty))  # LR:78
-        y_res = y - q @ qty                            # so that y_res . x == ytx - Qty^T qtx (LR:146)
-        y_res -= q @ (q.T @ y_res)                     # one re-orthogonalisation pass
+        y_res_t = y.T - qty.T @ q_t                    # so that y_res . x == ytx - Qty^T qtx (LR:146)  [P, n]
+        y_res_t -= (q_t @ y_res_t.T).T @ q_t           # one re-orthogonalisation pass
         kd0 = 1 if has_intercept else 0
-        self.q_cols = np.ascontiguousarray(q[:, kd0:].T)   # [Kd, n]
-        self.y_res = np.ascontiguousarray(y_res.T)          # [P, n]
+        self.q_cols = np.ascontiguousarray(q_t[kd0:])       # [Kd, n] (rows of a C-ordered array: no copy)
+        self.y_res = np.ascontiguousarray(y_res_t)          # [P, n]
 
 
 def _gram_orthonormalise(a, rank_tol=1e-11):
@@ -220,6 +228,59 @@ def orthonormal_basis(c):
             return q_all, False
     rest = rest - np.outer(one, one @ rest)                  # exact-zero column sums up to roundoff
     return np.column_stack([one, rest]), True
+
+
+def orthonormal_basis_t(c):
+    """`orthonormal_basis` in transposed form: returns (Q^T [K, n] C-contiguous, has_intercept).
+
+    Same construction -- two Gram (CholeskyQR2-style) passes, then a rotation inside the span that makes row 0 exactly
+    1/sqrt(n) and the other rows orthogonal to it -- but every step after the first pass is composed in K x K algebra
+    and applied to the n-long planes ONCE: with q_all = q1 T2 orthonormal and the constant in its span, the centred
+    columns cc = q_all - one u^T have the Gram matrix I - u u^T, whose range is u-perp, so rest = q_all V with V any
+    orthonormal basis of u-perp (a Householder reflector) -- no Gram pass over the samples is needed for it.  9 passes
+    over the n x K data instead of ~30.  Ill-conditioned or rank-deficient covariates take the general route.
+    """
+    n, K = c.shape
+    fast = None
+    g = c.T @ c
+    w, v = np.linalg.eigh(g)
+    wmax = w.max() if w.size else 0.0
+    if np.isfinite(wmax) and wmax > 0.0 and w.min() > 1e-7 * wmax:
+        q1_t = (v / np.sqrt(w)).T @ c.T                       # [K, n]
+        w2, v2 = np.linalg.eigh(q1_t @ q1_t.T)                # second pass: removes the O(cond^2 eps) loss of orthogonality
+        if w2.min() > 0.5:
+            t2 = (v2 / np.sqrt(w2)) @ v2.T                    # q_all = q1 t2 (never formed)
+            inv_sqrt_n = 1.0 / np.sqrt(n)
+            u = t2.T @ (q1_t.sum(axis=1) * inv_sqrt_n)        # q_all^T one
+            resid = inv_sqrt_n - (t2 @ u) @ q1_t              # one - q_all u, explicitly (1 - |u|^2 cannot resolve 1e-9)
+            if np.linalg.norm(resid) > 1e-9:
+                return np.ascontiguousarray(t2.T @ q1_t), False
+            un = u / np.linalg.norm(u)
+            e0 = np.zeros(K)
+            e0[0] = -1.0 if un[0] > 0 else 1.0                # reflect s e0 <-> un with |un - s e0| >= 1
+            hv = un - e0
+            h = np.eye(K) - 2.0 * np.outer(hv, hv) / (hv @ hv)
+            q_t = np.empty((K, n))
+            q_t[0] = inv_sqrt_n
+            if K > 1:
+                rest = q_t[1:]
+                np.matmul((t2 @ h[:, 1:]).T, q1_t, out=rest)  # columns 1.. of the reflector span u-perp
+                rest -= rest.mean(axis=1, keepdims=True)      # exact-zero sums up to roundoff
+                g3 = rest @ rest.T
+                if np.abs(g3 - np.eye(K - 1)).max() > 1e-12:  # (not expected: one more symmetric orthonormalisation)
+                    w3, v3 = np.linalg.eigh(g3)
+                    if w3.min() > 0.5:
+                        rest[:] = ((v3 / np.sqrt(w3)) @ v3.T) @ rest
+                        rest -= rest.mean(axis=1, keepdims=True)
+                        fast = (q_t, True)
+                else:
+                    fast = (q_t, True)
+            else:
+                fast = (q_t, True)
+    if fast is not None:
+        return fast
+    q, has_intercept = orthonormal_basis(c)
+    return np.ascontiguousarray(q.T), has_intercept
 
 
 def _run_device(genotypes, bases, kernel="auto", want_log10_p=False, chunk_variants=None, guard=True):
@@ -452,6 +513,7 @@ def linear_regression_rows(y, x, covariates, block_size=16, pass_through=(), *, 
 
 
 _uid = itertools.count()
+LAST_STREAM_PHASES = {}   # host-side phase times of the last call that streamed host-resident rows (measurement aid)
 
 
 def _execute(mt, x, y_vals, cov_vals, is_chained, pass_through_names, *, weights=None, kernel="auto", log10_p=False,
@@ -477,11 +539,19 @@ def _execute(mt, x, y_vals, cov_vals, is_chained, pass_through_names, *, weights
         host = [{k: v.cpu().numpy() for k, v in o.items()} for o in outs]
     elif isinstance(mt.genotypes, HostBedGenotypes) and mt.genotypes.nbytes >= _STREAM_MIN_BYTES:
         # host-resident .bed rows: stream them through the device; the copies start before the prologue
+        t0 = time.perf_counter()
         stream = _HostStream(mt.genotypes, stream_block, stream_depth)
         try:
-            host = stream.run(make_bases(), kernel=kernel, want_log10_p=log10_p)
+            t1 = time.perf_counter()
+            bases = make_bases()
+            t2 = time.perf_counter()
+            host = stream.run(bases, kernel=kernel, want_log10_p=log10_p)
+            t3 = time.perf_counter()
         finally:
             stream.close()
+        # where the wall time of the last streamed call went (host side; the copies run underneath all of it)
+        LAST_STREAM_PHASES.update(stream_begin_ms=1e3 * (t1 - t0), host_prologue_ms=1e3 * (t2 - t1),
+                                  add_groups_and_stream_run_ms=1e3 * (t3 - t2), close_ms=1e3 * (time.perf_counter() - t3))
     elif sharded:
         import torch.distributed as tdist
 
