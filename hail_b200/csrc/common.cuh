@@ -90,6 +90,7 @@ struct Ctx {
   void* arena = nullptr;
   size_t arena_bytes = 0;
   int streams_alive = 0;
+  int64_t stream_budget = 0;   // device bytes the default stream depth may take, asked from the driver when the arena is (re)built
   std::vector<float> stream_timeline;   // lrr_set_timing(1): per block of the last lrr_stream_run, ms since the first copy
                                         // started: [copy done, sweep started, statistics done]
   float last_stream_h2d_ms = -1.f;   // first block copy issued -> last block copy done, of the last lrr_stream_run

@@ -188,13 +188,28 @@ int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64
   s->n_blocks = (n_variants + s->block - 1) / s->block;
   // default depth: up to 16 GB of packed rows in flight (covers the host prologue at PCIe rate) but never more than
   // half of what the device has free (the cached arena counts as free: it is reused), at least 3 slots
+  const int n_stage = (int)std::min<int64_t>(N_STAGE, s->n_blocks);
+  const size_t stage_bytes = ((size_t)(s->block * bed_stride) + 255) / 256 * 256;
+  const size_t slot_bytes = (size_t)(s->block * s->stride);
+  const size_t flag_bytes = ((size_t)s->block + 255) / 256 * 256;
+  auto arena_need = [&](int64_t dep) {
+    const int64_t d = std::max<int64_t>(1, std::min<int64_t>(dep, std::max<int64_t>(s->n_blocks, 1)));
+    return n_stage * stage_bytes + (size_t)d * (slot_bytes + flag_bytes);
+  };
   if (depth <= 0) {
-    size_t free_b = 0, total_b = 0;
-    int64_t budget = 16ll << 30;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
-      budget = std::min<int64_t>(budget, (int64_t)((free_b + c->arena_bytes) / 2));
-    else
-      cudaGetLastError();
+    // The budget is asked from the driver when the arena has to be (re)built and remembered with it: cudaMemGetInfo goes
+    // through the kernel driver and took up to 80 ms in one call out of five on a shared box.
+    int64_t budget = c->arena ? c->stream_budget : 0;
+    if (budget > 0 && arena_need(std::max<int64_t>(3, budget / (s->block * s->stride))) > c->arena_bytes) budget = 0;
+    if (budget <= 0) {
+      size_t free_b = 0, total_b = 0;
+      budget = 16ll << 30;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+        budget = std::min<int64_t>(budget, (int64_t)((free_b + c->arena_bytes) / 2));
+      else
+        cudaGetLastError();
+      c->stream_budget = budget;
+    }
     depth = (int)std::max<int64_t>(3, budget / (s->block * s->stride));
   }
   s->depth = (int)std::max<int64_t>(1, std::min<int64_t>(depth, std::max<int64_t>(s->n_blocks, 1)));
@@ -217,11 +232,7 @@ int lrr_stream_begin(lrr_ctx* ctx, lrr_stream** out, const uint8_t* h_bed, int64
   if (trace) tr2 = now_us();
   // one arena for the staging buffers and the slots, cached on the context across streams (cudaMalloc / cudaFree of
   // tens of GB would otherwise sit in front of the first copy of every call)
-  const int n_stage = (int)std::min<int64_t>(N_STAGE, s->n_blocks);
-  const size_t stage_bytes = ((size_t)(s->block * bed_stride) + 255) / 256 * 256;
-  const size_t slot_bytes = (size_t)(s->block * s->stride);
-  const size_t flag_bytes = ((size_t)s->block + 255) / 256 * 256;
-  const size_t need = n_stage * stage_bytes + (size_t)s->depth * (slot_bytes + flag_bytes);
+  const size_t need = arena_need(s->depth);
   if (need > c->arena_bytes) {
     cudaFree(c->arena);
     c->arena = nullptr;
@@ -382,6 +393,7 @@ int lrr_trim(lrr_ctx* ctx) try {
   cudaFree(c->arena);
   c->arena = nullptr;
   c->arena_bytes = 0;
+  c->stream_budget = 0;
   cudaFree(c->d_nanmask);
   c->d_nanmask = nullptr;
   c->nanmask_bytes = 0;

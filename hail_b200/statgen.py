@@ -522,12 +522,14 @@ def _execute(mt, x, y_vals, cov_vals, is_chained, pass_through_names, *, weights
     the per-partition loop on the device.  `y_vals` is a list of groups, each a list of float64 column arrays; returns
     the Table with array-valued statistics ([M, P] per group; a ChainedField over groups when `is_chained`)."""
     n_cols = mt.count_cols()
-    cov = np.column_stack(cov_vals) if cov_vals else np.empty((n_cols, 0))
     w_vals = [None] * len(y_vals) if weights is None else weights
     from .genotypes import CompactDosage, DenseDosage, HostBedGenotypes
     DenseDosage = (DenseDosage, CompactDosage)   # both are dense entry fields; the device call differs (_run_device_dense)
 
     def make_bases():
+        # (built here, not above: a streamed call has its first host -> device copies in flight by now.)  The covariates are
+        # stacked as contiguous planes [K, n] and handed over as the transposed VIEW: the prologue works plane by plane
+        cov = np.stack(cov_vals).T if cov_vals else np.empty((n_cols, 0))
         return [GroupBasis(np.column_stack(g), cov, mt.col_index, i if is_chained else None, w_vals[i])
                 for i, g in enumerate(y_vals)]
 
