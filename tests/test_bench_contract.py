@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import pytest
 
 
-@pytest.mark.parametrize("line", ["r01_bench_c2_end.json", "r02_bench_default_final.json"])
+@pytest.mark.parametrize("line", ["r01_bench_c2_end.json", "r02_bench_default_final.json", "r02b_bench_default_final.json"])
 def test_committed_bench_line_has_the_contract_keys(line):
     d = json.load(open(os.path.join(ROOT, "profiles", line)))
     if line.startswith("r02"):
@@ -20,6 +20,13 @@ def test_committed_bench_line_has_the_contract_keys(line):
         assert e["h2d_gbps_in_call"] > 0 and e["h2d_gbps_link_alone"] > 0 and e["slowest_stage"] in e["stage_seconds"]
         assert set(d["config"]) == {"workload", "samples", "variants_per_gpu", "phenotypes", "covariates", "missing_rate", "groups",
                                     "parallelism", "l2"}
+    if line.startswith("r02b"):
+        # second session: what the sweeps issued and the tensor roof next to the HBM roof; the host phases of every repetition
+        t = d["roofline"]["tensor"]
+        assert t["bound"] == "tensor" and t["unit"] == "TFLOP/s" and (t["sweep_launches"], t["mma_columns"]) == (1, 80)
+        assert abs(t["frac"] - t["achieved"] / t["peak"]) < 1e-3 and d["roofline"]["binding"] == "hbm"
+        assert len(d["e2e"]["host_phase_ms_per_rep"]) == d["e2e"]["reps"] == len(d["e2e"]["rep_seconds"])
+        assert max(d["e2e"]["rep_seconds"]) < 1.05 * min(d["e2e"]["rep_seconds"])     # no heavy tail left
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "gpu_launches", "roofline", "clocks", "e2e", "cpu_baseline"):
         assert k in d, k
