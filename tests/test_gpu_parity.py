@@ -531,6 +531,43 @@ def test_many_chained_groups(kernel):
         assert_fields_close(got, {k: v for k, v in want[g].items() if k != "_d"}, t_floor=1e-9, ctx=f"{kernel} g={g}")
 
 
+def test_prepared_buffers_are_reused_across_calls_and_returned_by_trim():
+    """The 4-bit sweep's prepared buffers live in grow-only pools (no cudaFree on the per-call path): calls whose groups
+    shrink, grow and change shape in turn give the float64 kernel's rows every time, lrr_trim hands the pools back once no
+    groups are held, and the next call simply builds them again."""
+    hb = _hb()
+    from hail_b200 import _lib
+    ctx = _lib.context(0)
+    rng = np.random.default_rng(44)
+    N, M = 3000, 700
+    mt = hb.balding_nichols_model(3, N, M, missing_rate=0.02, seed=9)
+    cov = rng.normal(size=(N, 12))
+    ys = rng.normal(size=(N, 6))
+    mt = mt.annotate_cols(**{f"c{i}": cov[:, i] for i in range(12)}, **{f"y{i}": ys[:, i] for i in range(6)})
+
+    def both(y, K):
+        covs = [1.0] + [mt[f"c{i}"] for i in range(K)]
+        a = hb.linear_regression_rows(y=y, x=mt.GT.n_alt_alleles(), covariates=covs, _kernel="tc4")
+        b = hb.linear_regression_rows(y=y, x=mt.GT.n_alt_alleles(), covariates=covs, _kernel="fp64")
+        assert np.array_equal(a.n, b.n) and np.array_equal(a.sum_x, b.sum_x)
+        for f in ("beta", "standard_error", "t_stat"):
+            fa, fb = a[f], b[f]
+            pairs = [(fa, fb)] if isinstance(fa, np.ndarray) else list(zip(fa, fb))   # chained: one array per group
+            for ga, gb in pairs:
+                assert O.d_eq(np.asarray(ga), np.asarray(gb), 1e-6).all(), f
+        return a
+
+    first = both(mt.y0, 3)
+    both([mt.y0, mt.y1, mt.y2, mt.y3, mt.y4, mt.y5], 12)      # many more digit columns: every pool grows
+    both([[mt.y0], [mt.y1, mt.y2]], 5)                        # chained groups, fewer columns: the pools are reused
+    again = both(mt.y0, 3)
+    assert np.array_equal(first.beta, again.beta, equal_nan=True) and np.array_equal(first.p_value, again.p_value, equal_nan=True)
+    ctx.check(ctx.lib.lrr_clear_groups(ctx.handle))
+    ctx.check(ctx.lib.lrr_trim(ctx.handle))
+    after = both(mt.y0, 3)
+    assert np.array_equal(first.beta, after.beta, equal_nan=True)
+
+
 # ---------------------------------------------------------------------------------------------
 # host-resident input: the streaming loop (lrr_stream_*) must give exactly the resident path's rows
 @pytest.mark.parametrize("block,depth", [(0, 0), (128, 2), (300, 3), (1000, 1), (4096, 5)])
