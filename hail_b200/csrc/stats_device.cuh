@@ -8,33 +8,41 @@
 
 namespace lrr {
 
+// Continued fraction of the regularised incomplete beta function, 1 / (1 + d_1 / (1 + d_2 / (1 + ...))) with
+// d_{2m+1} = -(a + m)(a + b + m) x / ((a + 2m)(a + 2m + 1)) and d_{2m} = m (b - m) x / ((a + 2m - 1)(a + 2m)), evaluated by the
+// FORWARD recurrence of its convergents A_n / B_n with every coefficient kept as numerator p_n over denominator q_n
+// (equivalence transformation: A_n = q_n A_{n-1} + q_{n-1} p_n A_{n-2}, same for B_n): no division inside the loop -- the
+// modified Lentz form it replaces chains four dependent float64 divisions per step, and the statistics kernel was bound by
+// exactly that latency.  The convergents are rescaled by a power of two every step (exact); the loop ends when two
+// consecutive convergents agree to 3e-15, tested as a cross product.  Same values as the Lentz form to ~1e-10 of the
+// fraction where it is of order a (large df), 1e-13 elsewhere; both sit equally far from scipy's pt().
 __device__ inline double betacf_dev(double a, double b, double x) {
-  const double tiny = 1e-300, eps = 3e-15;  // a tighter test can bounce a few ulp around 1 for hundreds of iterations
+  const double eps = 3e-15;
   const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
-  double c = 1.0, d = 1.0 - qab * x / qap;
-  if (fabs(d) < tiny) d = tiny;
-  d = 1.0 / d;
-  double h = d;
-  for (int m = 1; m <= 1000; ++m) {
-    const double m2 = 2.0 * m;
-    double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
-    d = 1.0 + aa * d;
-    if (fabs(d) < tiny) d = tiny;
-    c = 1.0 + aa / c;
-    if (fabs(c) < tiny) c = tiny;
-    d = 1.0 / d;
-    h *= d * c;
-    aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
-    d = 1.0 + aa * d;
-    if (fabs(d) < tiny) d = tiny;
-    c = 1.0 + aa / c;
-    if (fabs(c) < tiny) c = tiny;
-    d = 1.0 / d;
-    const double del = d * c;
-    h *= del;
-    if (fabs(del - 1.0) < eps) break;
+  double Am1 = 0.0, Bm1 = 1.0, A = 1.0, B = 1.0, qprev = 1.0;
+  for (int m = 0; m < 1000; ++m) {
+    const double dm = (double)m, m2 = 2.0 * dm;
+    double p = -(a + dm) * (qab + dm) * x, q = (a + m2) * (qap + m2);      // d_{2m+1}
+    double w = qprev * p;
+    double An = fma(q, A, w * Am1), Bn = fma(q, B, w * Bm1);
+    Am1 = A; Bm1 = B; A = An; B = Bn; qprev = q;
+    const double mm = dm + 1.0, mm2 = m2 + 2.0;
+    p = mm * (b - mm) * x;                                                    // d_{2m+2}
+    q = (qam + mm2) * (a + mm2);
+    w = qprev * p;
+    An = fma(q, A, w * Am1);
+    Bn = fma(q, B, w * Bm1);
+    Am1 = A; Bm1 = B; A = An; B = Bn; qprev = q;
+    // bring B back to [1, 2): multiply all four by 2^-exponent(B)
+    const int e = ((__double2hiint(B) >> 20) & 0x7ff) - 1023;
+    if (e > -1000 && e < 1000) {   // (B == 0, Inf or NaN: leave it to the caller's isnan / the final division)
+      const double sc = __hiloint2double((1023 - e) << 20, 0);
+      A *= sc; B *= sc; Am1 *= sc; Bm1 *= sc;
+    }
+    const double cross = A * Bm1;
+    if (fabs(cross - Am1 * B) <= eps * fabs(cross)) break;
   }
-  return h;
+  return A / B;
 }
 
 // p = 2 P[T_df <= -|t|]; lbeta = log B(df/2, 1/2).  Optionally log10(p), finite where p underflows.
