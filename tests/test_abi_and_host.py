@@ -138,6 +138,36 @@ def test_group_basis_matches_oracle_prologue(intercept_pos):
         GroupBasis(np.full((N, 1), np.nan), cov, np.arange(N))
 
 
+@pytest.mark.parametrize("case", ["gauss+1", "no_intercept", "uncentred", "affine_span", "const_only", "collinear",
+                                  "ill_conditioned", "planes_view"])
+def test_transposed_prologue_equals_the_general_construction(case):
+    """`orthonormal_basis_t` (the K x K-composed form the streamed call runs next to its host -> device copies) spans the same
+    space as `orthonormal_basis`, finds the intercept in the same cases, and keeps row 0 exactly constant with the other
+    rows summing to zero; rank-deficient and ill-conditioned covariates fall back to the general route."""
+    from hail_b200.statgen import orthonormal_basis, orthonormal_basis_t
+    rng = np.random.default_rng(11)
+    n = 5000
+    z = rng.normal(size=(n, 6))
+    c = {"gauss+1": np.column_stack([np.ones(n), z]),
+         "no_intercept": z,
+         "uncentred": z + 5.0,
+         "affine_span": np.column_stack([z[:, 0] + 3, z[:, 1] - 2 * z[:, 0] + 1, z[:, 2], np.full(n, 7.0)]),
+         "const_only": np.full((n, 1), 3.0),
+         "collinear": np.column_stack([np.ones(n), z[:, 0], 2 * z[:, 0] + 1]),
+         "ill_conditioned": np.column_stack([np.ones(n), z[:, 0], z[:, 0] + 1e-6 * z[:, 1]]),
+         "planes_view": np.stack([np.ones(n)] + [z[:, i] for i in range(6)]).T}[case]   # F-ordered view, as _execute passes it
+    q, has = orthonormal_basis(c)
+    q_t, has_t = orthonormal_basis_t(c)
+    assert has_t == has and q_t.shape == (q.shape[1], n) and q_t.flags["C_CONTIGUOUS"]
+    x = rng.normal(size=(n, 3))
+    assert np.abs(q @ (q.T @ x) - q_t.T @ (q_t @ x)).max() < 1e-11                 # same projector
+    assert np.abs(q_t @ q_t.T - np.eye(q_t.shape[0])).max() < 1e-12
+    if has_t:
+        assert np.all(q_t[0] == 1.0 / np.sqrt(n))
+        if q_t.shape[0] > 1:
+            assert np.abs(q_t[1:].sum(axis=1)).max() < 1e-12
+
+
 def test_bn_parameters_are_seeded_and_shardable():
     from hail_b200 import bn
 
