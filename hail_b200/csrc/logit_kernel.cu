@@ -123,7 +123,9 @@ __device__ bool invert(double (*A)[MM], double (*Inv)[MM], int m, double* logdet
   return true;
 }
 
-constexpr int TS = 32;   // samples per tile of the tiled form (MM > 20)
+constexpr int TS = 128;  // samples per tile of the tiled form (MM > 20): two threads per sample form eta; the serial exp / log of
+                         // a tile then runs on 128 lanes instead of 32 (with 32-sample tiles it was the longest phase)
+constexpr int TPS = LT / TS;   // threads per sample in that phase
 
 template <int MM>
 struct Shared {
@@ -282,7 +284,7 @@ __device__ void eval_pass(const LogitArgs& a, Shared<MM>& sh, const uint32_t* ro
 
 // The same evaluation for wide models (20 < m <= MM = 32 / 48 / 64): the (m + 1) m / 2 sums no longer fit the registers of
 // one thread, so the CTA walks the samples in tiles of TS: the tile of X = [covariates | x] is staged in shared memory (the
-// next tile's values travel in registers meanwhile), eight threads per sample form eta -> mu, w, the residual (MODE 1: and
+// next tile's values travel in registers meanwhile), two threads per sample form eta -> mu, w, the residual (MODE 1: and
 // the hat value x' Inv x), then the weighted Gram update F += X' diag(w) X runs as 4 x 4 register blocks: thread `tid` owns
 // block (bi >= bj) of the lower triangle for ALL samples, so F needs no reduction and its sum order is fixed; threads
 // nblk .. nblk + MM - 1 own one score entry each.
@@ -290,19 +292,25 @@ template <int MM, int MODE>
 __device__ void eval_pass_tiled(const LogitArgs& a, Shared<MM>& sh, Tile<MM>& tl, const uint32_t* row, const double* drow, int m,
                                 int m0, bool want_loglik) {
   constexpr int NB = MM / 4, NBLK = NB * (NB + 1) / 2;
+  // G thread groups share the samples of a tile (group g takes samples g, g + G, ...): 4 x 36 block threads for MM = 32,
+  // 2 x 78 for 48, 1 x 136 for 64; the groups' partial blocks are added in group order after the last tile
+  constexpr int G = (LT - MM) / NBLK >= 4 ? 4 : (LT - MM) / NBLK >= 2 ? 2 : 1;
   constexpr int PER = TS * MM / LT;   // staged values per thread and tile
-  static_assert(TS * MM % LT == 0 && NBLK + MM <= LT && LT / TS == 8, "thread mapping of the tiled form");
+  static_assert(TS * MM % LT == 0 && G * NBLK + MM <= LT && TPS * TS == LT && (TPS & (TPS - 1)) == 0 && TS % G == 0,
+                "thread mapping of the tiled form");
+  static_assert((G - 1) * NBLK * 16 <= 2 * MM * MM, "the partial blocks of groups 1.. fit the W | Inv scratch");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K;
   const double mean = sh.mean;
+  const int grp = tid / NBLK, blk = tid % NBLK;   // block threads: tid < G * NBLK
   int bi = 0, bj = 0;
-  if (tid < NBLK) {
-    int p = 0, rem = tid;
+  if (tid < G * NBLK) {
+    int p = 0, rem = blk;
     while (rem > p) { rem -= p + 1; ++p; }
     bi = p;
     bj = rem;
   }
-  const int sk = tid - NBLK;   // score entry of this thread (0 <= sk < MM)
+  const int sk = tid - G * NBLK;   // score entry of this thread (0 <= sk < MM)
   double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -338,24 +346,22 @@ __device__ void eval_pass_tiled(const LogitArgs& a, Shared<MM>& sh, Tile<MM>& tl
 #pragma unroll
       for (int q = 0; q < PER; ++q) nxt[q] = fetch(q, i0 + TS);
     }
-    {   // eta, mu, w, residual: eight threads per sample
-      const int t = tid >> 3, part = tid & 7;
+    {   // eta, mu, w, residual: TPS threads per sample
+      const int t = tid / TPS, part = tid % TPS;
       const double* xr = tl.X[t];
       double e = 0.0;
-      for (int k = part; k < m0; k += 8) e = fma(sh.b[k], xr[k], e);
-      e += __shfl_xor_sync(0xffffffffu, e, 1);
-      e += __shfl_xor_sync(0xffffffffu, e, 2);
-      e += __shfl_xor_sync(0xffffffffu, e, 4);
+      for (int k = part; k < m0; k += TPS) e = fma(sh.b[k], xr[k], e);
+#pragma unroll
+      for (int o = 1; o < TPS; o <<= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
       double h = 0.0;
       if (MODE == 1) {   // hat value x' Inv x (Inv symmetric)
-        for (int p = part; p < m; p += 8) {
+        for (int p = part; p < m; p += TPS) {
           double tp = 0.0;
           for (int c = 0; c < m; ++c) tp = fma(sh.Inv[p][c], xr[c], tp);
           h = fma(tp, xr[p], h);
         }
-        h += __shfl_xor_sync(0xffffffffu, h, 1);
-        h += __shfl_xor_sync(0xffffffffu, h, 2);
-        h += __shfl_xor_sync(0xffffffffu, h, 4);
+#pragma unroll
+        for (int o = 1; o < TPS; o <<= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
       }
       if (part == 0) {
         const int i = i0 + t;
@@ -373,9 +379,9 @@ __device__ void eval_pass_tiled(const LogitArgs& a, Shared<MM>& sh, Tile<MM>& tl
       }
     }
     __syncthreads();
-    if (MODE == 0 && tid < NBLK) {
+    if (MODE == 0 && tid < G * NBLK) {
 #pragma unroll 4
-      for (int t = 0; t < TS; ++t) {
+      for (int t = grp; t < TS; t += G) {
         const double2 a01 = *reinterpret_cast<const double2*>(&tl.X[t][4 * bi]), a23 = *reinterpret_cast<const double2*>(&tl.X[t][4 * bi + 2]);
         const double2 b01 = *reinterpret_cast<const double2*>(&tl.X[t][4 * bj]), b23 = *reinterpret_cast<const double2*>(&tl.X[t][4 * bj + 2]);
         const double wt = tl.w[t];
@@ -391,6 +397,23 @@ __device__ void eval_pass_tiled(const LogitArgs& a, Shared<MM>& sh, Tile<MM>& tl
       for (int t = 0; t < TS; ++t) sc = fma(tl.X[t][sk], tl.r[t], sc);
     }
     __syncthreads();
+  }
+  if (MODE == 0 && G > 1) {   // W | Inv are free during a MODE 0 evaluation: scratch for the partial blocks of groups 1..
+    double* scratch = &sh.W[0][0];
+    if (tid >= NBLK && tid < G * NBLK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) scratch[((grp - 1) * NBLK + blk) * 16 + i * 4 + j] = acc[i][j];
+    }
+    __syncthreads();
+    if (tid < NBLK) {
+      for (int g = 1; g < G; ++g)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += scratch[((g - 1) * NBLK + blk) * 16 + i * 4 + j];
+    }
   }
   if (MODE == 0 && tid < NBLK) {
 #pragma unroll
