@@ -35,32 +35,68 @@ def _sigmoid(z):
     return 1.0 / (1.0 + np.exp(-z))
 
 
+_GRAM_SLICES = 16     # fixed, so that the summation order (and with it every bit of the null fit) does not depend on the host
+_GRAM_THREADS = 4
+
+
+def _weighted_gram(Ct, w, pool):
+    """Ct diag(w) Ct' for covariate planes Ct [m, n]: the samples are cut into `_GRAM_SLICES` fixed slices whose partial Gram
+    matrices are computed by a few host threads (numpy releases the GIL inside BLAS) and added in slice order."""
+    m, n = Ct.shape
+    edges = [n * i // _GRAM_SLICES for i in range(_GRAM_SLICES + 1)]
+
+    def part(i):
+        lo, hi = edges[i], edges[i + 1]
+        a = Ct[:, lo:hi]
+        return (a * w[lo:hi]) @ a.T
+
+    parts = list(pool.map(part, range(_GRAM_SLICES))) if pool is not None else [part(i) for i in range(_GRAM_SLICES)]
+    g = parts[0]
+    for p_ in parts[1:]:
+        g = g + p_
+    return g
+
+
 def _fit_null(C, y, max_iter, tol):
-    """LogisticRegressionModel.fit from the intercept-only start (LogisticRegressionModel.scala:286-351)."""
+    """LogisticRegressionModel.fit from the intercept-only start (LogisticRegressionModel.scala:286-351).
+
+    Works on covariate PLANES [m, n] (eta and the score are row-wise dot products; the Fisher matrix is a sliced, threaded
+    Gram product): the n x m formulation with its n x m temporaries took 0.3 s at 10 covariates and 3.9 s at 63 for 400k
+    samples -- longer than the device needs for a few hundred variants."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from .statgen import _blas_limits
     n, m = C.shape
+    Ct = np.ascontiguousarray(C.T)
     b = np.zeros(m)
     avg = y.sum() / n
     b[0] = np.log(avg / (1.0 - avg))
-    mu = _sigmoid(C @ b)
-    score = C.T @ (y - mu)
-    fisher = C.T @ (C * (mu * (1.0 - mu))[:, None])
-    it, converged, exploded = 0, False, False
-    while not converged and not exploded and it < max_iter:
-        it += 1
-        try:
-            delta = np.linalg.solve(fisher, score)
-        except np.linalg.LinAlgError:
-            exploded = True
-            break
-        if np.isnan(delta[0]):
-            exploded = True
-        elif np.max(np.abs(delta)) < tol:
-            converged = True
-        else:
-            b = b + delta
-            mu = _sigmoid(C @ b)
-            score = C.T @ (y - mu)
-            fisher = C.T @ (C * (mu * (1.0 - mu))[:, None])
+    pool = ThreadPoolExecutor(_GRAM_THREADS) if n * m >= (1 << 20) else None
+    try:
+        with _blas_limits(limits=1):
+            mu = _sigmoid(b @ Ct)
+            score = Ct @ (y - mu)
+            fisher = _weighted_gram(Ct, mu * (1.0 - mu), pool)
+            it, converged, exploded = 0, False, False
+            while not converged and not exploded and it < max_iter:
+                it += 1
+                try:
+                    delta = np.linalg.solve(fisher, score)
+                except np.linalg.LinAlgError:
+                    exploded = True
+                    break
+                if np.isnan(delta[0]):
+                    exploded = True
+                elif np.max(np.abs(delta)) < tol:
+                    converged = True
+                else:
+                    b = b + delta
+                    mu = _sigmoid(b @ Ct)
+                    score = Ct @ (y - mu)
+                    fisher = _weighted_gram(Ct, mu * (1.0 - mu), pool)
+    finally:
+        if pool is not None:
+            pool.shutdown()
     return b, mu, score, fisher, it, converged, exploded
 
 
