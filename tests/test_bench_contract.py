@@ -25,6 +25,9 @@ def test_committed_bench_line_has_the_contract_keys(line):
         t = d["roofline"]["tensor"]
         assert t["bound"] == "tensor" and t["unit"] == "TFLOP/s" and (t["sweep_launches"], t["mma_columns"]) == (1, 80)
         assert abs(t["frac"] - t["achieved"] / t["peak"]) < 1e-3 and d["roofline"]["binding"] == "hbm"
+        # multiply-adds issued = variants x padded samples x MMA columns; achieved = 2 x that / the sweep's own duration
+        assert t["flop_per_launch"] == 2.0 * 1_000_000 * 400_384 * 80
+        assert abs(t["achieved"] - t["flop_per_launch"] / (d["roofline"]["kernel_ms"] / 1e3) / 1e12) < 0.1
         assert len(d["e2e"]["host_phase_ms_per_rep"]) == d["e2e"]["reps"] == len(d["e2e"]["rep_seconds"])
         assert max(d["e2e"]["rep_seconds"]) < 1.05 * min(d["e2e"]["rep_seconds"])     # no heavy tail left
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
