@@ -12,7 +12,7 @@ def __getattr__(name):  # lazy: these import torch-side helpers
     if name in ("PackedGenotypes", "HostBedGenotypes", "DenseDosage", "CompactDosage", "packed_stride"):
         from . import genotypes
         return getattr(genotypes, name)
-    if name in ("import_plink", "export_plink", "import_fam"):
+    if name in ("import_plink", "export_plink", "import_fam", "import_bgen", "read_bgen"):
         from . import impex
         return getattr(impex, name)
     if name == "logistic_regression_rows":
@@ -28,4 +28,4 @@ def __getattr__(name):  # lazy: these import torch-side helpers
 
 
 __all__ = ["linear_regression_rows", "lambda_gc", "hwe_normalized_pca", "logistic_regression_rows", "MatrixTable", "Table", "FatalError", "ExpressionException", "PackedGenotypes",
-           "HostBedGenotypes", "import_plink", "export_plink", "import_fam", "balding_nichols_model"]
+           "HostBedGenotypes", "CompactDosage", "import_plink", "export_plink", "import_fam", "import_bgen", "balding_nichols_model"]

@@ -228,6 +228,24 @@ class CompactDosage:
         self.ld = ld
         self.n_variants, self.n_samples = int(M), int(N)
 
+    @classmethod
+    def from_q(cls, q, scale, device=0):
+        """From the stored integers themselves: q uint16 [M, N] (0xFFFF = missing), value = q * scale -- what a BGEN file's
+        8-bit probabilities give directly (q = P(het) + 2 P(hom alt) in units of 1/255, `impex.import_bgen`)."""
+        dev = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        q = np.asarray(q)
+        assert q.ndim == 2 and q.dtype == np.uint16
+        self = cls.__new__(cls)
+        M, N = q.shape
+        ld = (N + 7) // 8 * 8
+        buf = np.zeros((M, ld), dtype=np.uint16)
+        buf[:, :N] = q
+        self.data = torch.from_numpy(buf.view(np.int16)).to(dev).contiguous()
+        self.scale = float(scale)
+        self.ld = ld
+        self.n_variants, self.n_samples = int(M), int(N)
+        return self
+
     @property
     def device(self):
         return self.data.device

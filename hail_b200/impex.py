@@ -1,4 +1,5 @@
-"""PLINK ingest / export for the B200 path: .bed/.bim/.fam <-> MatrixTable with packed GT.
+"""PLINK ingest / export for the B200 path: .bed/.bim/.fam <-> MatrixTable with packed GT;
+BGEN ingest: 8-bit genotype probabilities -> the compact uint16 dosage store.
 
 Reference behaviour followed:
   * `hl.import_plink` / `hl.import_fam`    hail/python/hail/methods/impex.py:2505 (defaults: a2_reference=True, missing='NA',
@@ -8,6 +9,11 @@ Reference behaviour followed:
                                            rows are SORTED by (locus, alleles) (:79-81), each keeping its .bed row index
   * `hl.export_plink`                      impex.py:324-470 (defaults, white-space check),
                                            hail/hail/src/is/hail/expr/ir/MatrixWriter.scala:2110-2285 (bytes written)
+  * `hl.import_bgen`                       impex.py:1100-1290 (entry_fields, sample_file); the decode and its fatal conditions
+                                           hail/hail/src/is/hail/io/bgen/StagedBGENReader.scala:120-520 (layout 2, biallelic,
+                                           diploid, unphased, 8 bits per probability; dosage = (d1 + 2 d2) / 255 with
+                                           d2 = 255 - d0 - d1, :350-353; an entry is missing when bit 7 of its ploidy byte is
+                                           set, :498), header / sample block hail/hail/src/is/hail/io/bgen/LoadBgen.scala
 The genotype bytes never pass through Python objects: they are read into page-locked memory (`resident=False`: the
 out-of-core form streamed by lrr_stream_*) or packed into the device store (`resident=True`).
 """
@@ -18,7 +24,7 @@ import re
 
 import numpy as np
 
-from .genotypes import BED_MAGIC, HostBedGenotypes, PackedGenotypes
+from .genotypes import BED_MAGIC, CompactDosage, HostBedGenotypes, PackedGenotypes
 from .matrixtable import MatrixTable
 from .statgen import FatalError
 
@@ -301,3 +307,174 @@ def _bed_rows_of(mt: MatrixTable) -> np.ndarray:
         code = np.concatenate([code, np.zeros((code.shape[0], pad), dtype=np.uint8)], axis=1)
     code = code.reshape(code.shape[0], -1, 4)
     return (code[:, :, 0] | (code[:, :, 1] << 2) | (code[:, :, 2] << 4) | (code[:, :, 3] << 6)).astype(np.uint8)
+
+
+# ---- BGEN (v1.2, layout 2) ---------------------------------------------------------------------
+def read_bgen(source, sample_file=None, want_probabilities=False):
+    """Decode a BGEN file (path or bytes) on the host.  Returns a dict: `q` uint16 [M, N] (the dosage in units of 1/255:
+    d1 + 2 d2 of the stored 8-bit probabilities, 0xFFFF = missing), `contig`, `position`, `alleles`, `rsid`, `varid`
+    (file order), `samples`, and with `want_probabilities` the stored bytes `d0`, `d1` uint8 [M, N].
+
+    Follows StagedBGENReader.scala: only what Hail reads is accepted (layout 2, two alleles, ploidy 2 for every sample,
+    unphased, 8 bits per probability; zlib or no compression -- zstd needs a codec this image does not ship), with its
+    fatal messages."""
+    import struct
+    import zlib
+    b = source if isinstance(source, (bytes, bytearray, memoryview)) else open(source, "rb").read()
+    b = bytes(b)
+    if len(b) < 24:
+        raise FatalError("BGEN file is too short to hold a header")
+    offset, = struct.unpack_from("<I", b, 0)
+    header_len, M, N = struct.unpack_from("<III", b, 4)
+    magic = b[16:20]
+    if magic not in (b"bgen", b"\0\0\0\0"):
+        raise FatalError(f"expected magic number 'bgen' or 0000, found {magic!r}")
+    flags, = struct.unpack_from("<I", b, 4 + header_len - 4)
+    compression, layout, has_ids = flags & 3, (flags >> 2) & 15, (flags >> 31) & 1
+    if layout != 2:
+        raise FatalError(f"Hail only supports BGEN version 1.2 (layout 2), found layout {layout}")
+    if compression not in (0, 1):
+        raise NotImplementedError("read_bgen: zstd-compressed BGEN needs a zstd codec (only zlib / uncompressed here)")
+    samples = None
+    if has_ids:
+        p = 4 + header_len
+        _, n_ids = struct.unpack_from("<II", b, p)
+        if n_ids != N:
+            raise FatalError(f"BGEN file is malformed -- number of sample IDs in header does not equal number in file: {N}, {n_ids}")
+        p += 8
+        samples = []
+        for _ in range(N):
+            ln, = struct.unpack_from("<H", b, p)
+            samples.append(b[p + 2:p + 2 + ln].decode())
+            p += 2 + ln
+    if sample_file is not None:   # impex.py:1103; LoadBgen.readSampleFile: two header lines, the id is column 1
+        with open(sample_file) as f:
+            lines = [ln.rstrip("\r\n") for ln in f if ln.strip()]
+        ids = [re.split(r"\s+", ln)[0] for ln in lines[2:]]
+        if len(ids) != N:
+            raise FatalError(f"BGEN file and sample file have different numbers of samples: {N} vs {len(ids)}")
+        samples = ids
+    if samples is None:
+        samples = [f"sample_{i}" for i in range(N)]   # (Hail: "sample_0", ... when the file carries no identifiers)
+    q = np.empty((M, N), dtype=np.uint16)
+    d0a = np.empty((M, N), dtype=np.uint8) if want_probabilities else None
+    d1a = np.empty((M, N), dtype=np.uint8) if want_probabilities else None
+    contig, position, alleles, rsid, varid = [], [], [], [], []
+    p = 4 + offset
+    for v in range(M):
+        fields = []
+        for _ in range(3):   # variant id, rsid, chromosome
+            ln, = struct.unpack_from("<H", b, p)
+            fields.append(b[p + 2:p + 2 + ln].decode())
+            p += 2 + ln
+        pos, n_alleles = struct.unpack_from("<IH", b, p)
+        p += 6
+        if n_alleles != 2:
+            raise FatalError(f"Only biallelic variants supported, found variant with {n_alleles} alleles: {fields[2]}:{pos}")
+        al = []
+        for _ in range(n_alleles):
+            ln, = struct.unpack_from("<I", b, p)
+            al.append(b[p + 4:p + 4 + ln].decode())
+            p += 4 + ln
+        size, = struct.unpack_from("<I", b, p)
+        p += 4
+        if compression:
+            raw_len, = struct.unpack_from("<I", b, p)
+            data = zlib.decompress(b[p + 4:p + size])
+            if len(data) != raw_len:
+                raise FatalError(f"BGEN block of {fields[2]}:{pos} decompresses to {len(data)} bytes, header says {raw_len}")
+        else:
+            data = b[p:p + size]
+        p += size
+        n_row, n_alleles2, min_ploidy, max_ploidy = struct.unpack_from("<IHBB", data, 0)
+        if n_row != N:
+            raise FatalError(f"Row nSamples is not equal to header nSamples: {n_row}, {N}")
+        if n_alleles2 != n_alleles:
+            raise FatalError("Value for 'nAlleles' in genotype probability data storage is not equal to value in variant "
+                             f"identifying data. Expected {n_alleles} but found {n_alleles2} at {fields[2]}:{pos}.")
+        if min_ploidy != 2 or max_ploidy != 2:
+            raise FatalError(f"Hail only supports diploid genotypes. Found min ploidy '{min_ploidy}' and max ploidy '{max_ploidy}'.")
+        ploidy = np.frombuffer(data, dtype=np.uint8, count=N, offset=8)
+        bad = (ploidy & 0x3F) != 2
+        if bad.any():
+            raise FatalError(f"Ploidy value must equal to 2. Found {int(ploidy[bad][0])}.")
+        phase, bits = data[8 + N], data[9 + N]
+        if phase not in (0, 1):
+            raise FatalError(f"Phase value must be 0 or 1. Found {phase}.")
+        if phase == 1:
+            raise FatalError("Hail does not support phased genotypes in 'import_bgen'.")
+        if bits < 1 or bits > 32:
+            raise FatalError(f"nBits value must be between 1 and 32 inclusive. Found {bits}.")
+        if bits != 8:
+            raise FatalError(f"Hail only supports 8-bit probabilities, found {bits}.")
+        if len(data) != 2 * N + N + 10:
+            raise FatalError(f"Number of uncompressed bytes '{len(data)}' does not match the expected size '{2 * N}'.")
+        pr = np.frombuffer(data, dtype=np.uint8, count=2 * N, offset=10 + N).reshape(N, 2)
+        d0, d1 = pr[:, 0].astype(np.int32), pr[:, 1].astype(np.int32)
+        qv = (d1 + 2 * (255 - d0 - d1)).astype(np.uint16)      # (d1 + (d2 << 1)) / 255.0, StagedBGENReader.scala:350-353
+        qv[(ploidy & 0x80) != 0] = CompactDosage.MISSING
+        q[v] = qv
+        if want_probabilities:
+            d0a[v], d1a[v] = pr[:, 0], pr[:, 1]
+        varid.append(fields[0])
+        rsid.append(fields[1])
+        contig.append(fields[2])
+        position.append(int(pos))
+        alleles.append(tuple(al))
+    out = {"q": q, "contig": contig, "position": np.array(position, dtype=np.int64), "alleles": alleles, "rsid": rsid,
+           "varid": varid, "samples": samples}
+    if want_probabilities:
+        out["d0"], out["d1"] = d0a, d1a
+    return out
+
+
+def import_bgen(path, entry_fields=("dosage",), sample_file=None, index_file_map=None, n_partitions=None, block_size=None,
+                variants=None, *, reference_genome="default", contig_recoding=None, skip_invalid_loci=False,
+                device=0) -> MatrixTable:
+    """`hl.import_bgen` (impex.py:1100) for the regression path: entry field `dosage` as the compact uint16 store
+    (`CompactDosage`, 2 bytes per entry on the device; `mt.dosage` is the float64 entry expression the reference yields,
+    exact multiples of 1/255), row fields `locus`, `alleles`, `rsid`, `varid` (key locus, alleles; rows sorted by key),
+    column key `s`.  `GT` / `GP` entry fields are not materialised on the device -- `read_bgen(...,
+    want_probabilities=True)` returns the stored probabilities on the host.  `index_file_map`, `n_partitions`,
+    `block_size` are accepted and inert (no index is needed to read the whole file); `variants` is not supported."""
+    entry_fields = list(entry_fields)
+    for f in entry_fields:
+        if f not in ("GT", "GP", "dosage"):
+            raise FatalError(f"Invalid entry field '{f}'. Expected one of 'GT', 'GP', 'dosage'.")   # impex.py import_bgen
+    if "dosage" not in entry_fields:
+        raise NotImplementedError("import_bgen: the device store holds the 'dosage' entry field; ask for it "
+                                  "(GT / GP: read_bgen(..., want_probabilities=True))")
+    if variants is not None:
+        raise NotImplementedError("import_bgen: variants= (index-based filtering) is not supported")
+    if reference_genome == "default":
+        reference_genome = "GRCh37"
+    if reference_genome not in (None, "GRCh37"):
+        raise NotImplementedError("import_bgen: only reference_genome='GRCh37' or None")
+    d = read_bgen(path, sample_file)
+    recode = contig_recoding or {}
+    rank = {c: i for i, c in enumerate(_GRCH37_CONTIGS)} if reference_genome is not None else None
+    keep, contig = [], []
+    for i, (c, pos) in enumerate(zip(d["contig"], d["position"])):
+        c = recode.get(c, c)
+        valid = rank is None or (c in rank and pos >= 1)
+        if not valid and not skip_invalid_loci:
+            raise FatalError(f"Invalid locus '{c}:{pos}' found. Contig '{c}' is not in the reference genome '{reference_genome}'.")
+        if valid:
+            keep.append(i)
+            contig.append(c)
+    keep = np.array(keep, dtype=np.int64)
+    pos = d["position"][keep]
+    alleles = [d["alleles"][i] for i in keep]
+    keys = [((rank[c] if rank is not None else c), int(p_), a) for c, p_, a in zip(contig, pos, alleles)]
+    order = np.array(sorted(range(len(keys)), key=keys.__getitem__), dtype=np.int64)
+    rows_sel = keep[order]
+    store = CompactDosage.from_q(np.ascontiguousarray(d["q"][rows_sel]), 1.0 / 255.0, device)
+    take = lambda seq: [seq[i] for i in rows_sel]
+    rows = {
+        "locus": np.array([(contig[i], int(pos[i])) for i in order] + [None], dtype=object)[:-1],
+        "alleles": np.array([alleles[i] for i in order] + [None], dtype=object)[:-1],
+        "rsid": np.array(take(d["rsid"]), dtype=object),
+        "varid": np.array(take(d["varid"]), dtype=object),
+    }
+    return MatrixTable(store, rows=rows, cols={"s": np.array(d["samples"], dtype=object)}, row_key=("locus", "alleles"),
+                       col_key=("s",))
