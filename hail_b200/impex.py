@@ -360,6 +360,7 @@ def read_bgen(source, sample_file=None, want_probabilities=False):
     d0a = np.empty((M, N), dtype=np.uint8) if want_probabilities else None
     d1a = np.empty((M, N), dtype=np.uint8) if want_probabilities else None
     contig, position, alleles, rsid, varid = [], [], [], [], []
+    blocks = []   # (offset of the genotype data, its size) per variant: the identifying data is walked serially ...
     p = 4 + offset
     for v in range(M):
         fields = []
@@ -378,20 +379,30 @@ def read_bgen(source, sample_file=None, want_probabilities=False):
             p += 4 + ln
         size, = struct.unpack_from("<I", b, p)
         p += 4
+        blocks.append((p, size))
+        p += size
+        varid.append(fields[0])
+        rsid.append(fields[1])
+        contig.append(fields[2])
+        position.append(int(pos))
+        alleles.append(tuple(al))
+
+    def decode(v):   # ... the probability blocks are decoded by a few threads (zlib and numpy release the GIL)
+        p, size = blocks[v]
+        where = f"{contig[v]}:{position[v]}"
         if compression:
             raw_len, = struct.unpack_from("<I", b, p)
             data = zlib.decompress(b[p + 4:p + size])
             if len(data) != raw_len:
-                raise FatalError(f"BGEN block of {fields[2]}:{pos} decompresses to {len(data)} bytes, header says {raw_len}")
+                raise FatalError(f"BGEN block of {where} decompresses to {len(data)} bytes, header says {raw_len}")
         else:
             data = b[p:p + size]
-        p += size
         n_row, n_alleles2, min_ploidy, max_ploidy = struct.unpack_from("<IHBB", data, 0)
         if n_row != N:
             raise FatalError(f"Row nSamples is not equal to header nSamples: {n_row}, {N}")
-        if n_alleles2 != n_alleles:
+        if n_alleles2 != 2:
             raise FatalError("Value for 'nAlleles' in genotype probability data storage is not equal to value in variant "
-                             f"identifying data. Expected {n_alleles} but found {n_alleles2} at {fields[2]}:{pos}.")
+                             f"identifying data. Expected 2 but found {n_alleles2} at {where}.")
         if min_ploidy != 2 or max_ploidy != 2:
             raise FatalError(f"Hail only supports diploid genotypes. Found min ploidy '{min_ploidy}' and max ploidy '{max_ploidy}'.")
         ploidy = np.frombuffer(data, dtype=np.uint8, count=N, offset=8)
@@ -416,11 +427,14 @@ def read_bgen(source, sample_file=None, want_probabilities=False):
         q[v] = qv
         if want_probabilities:
             d0a[v], d1a[v] = pr[:, 0], pr[:, 1]
-        varid.append(fields[0])
-        rsid.append(fields[1])
-        contig.append(fields[2])
-        position.append(int(pos))
-        alleles.append(tuple(al))
+
+    if M * N >= (1 << 22):
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(min(8, os.cpu_count() or 1)) as pool:
+            list(pool.map(decode, range(M)))   # (list: re-raises the first fatal condition)
+    else:
+        for v in range(M):
+            decode(v)
     out = {"q": q, "contig": contig, "position": np.array(position, dtype=np.int64), "alleles": alleles, "rsid": rsid,
            "varid": varid, "samples": samples}
     if want_probabilities:
