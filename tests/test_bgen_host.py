@@ -103,3 +103,26 @@ def test_fatal_conditions_of_the_decoder(kw, msg):   # StagedBGENReader.scala:20
     v = [("v", "rs", "20", 7, np.array([255, 0, 0, 10]), np.array([0, 255, 0, 20]), np.zeros(N, dtype=bool))]
     with pytest.raises(FatalError, match=msg):
         read_bgen(write_bgen(v, N, **kw))
+
+
+def test_threaded_decode_of_a_large_file():
+    """Files of more than 4M entries are decoded by a thread pool; the result is the serial one, and a fatal condition in any
+    block still surfaces."""
+    rng = np.random.default_rng(2)
+    N, M = 70_000, 64
+    vs = []
+    for v in range(M):
+        d0 = rng.integers(0, 256, N)
+        d1 = rng.integers(0, 256, N) * (255 - d0) // 255
+        vs.append((f"v{v}", f"rs{v}", "20", 100 + v, d0, d1, rng.random(N) < 0.01))
+    d = read_bgen(write_bgen(vs, N))
+    for v in range(M):
+        assert np.array_equal(d["q"][v], np.where(vs[v][6], 0xFFFF, vs[v][5] + 2 * (255 - vs[v][4] - vs[v][5])))
+    bad = write_bgen(vs[:63], N)
+    one = write_bgen(vs[63:], N, phased=1)
+    # splice a phased block behind 63 good ones: same header, one more variant
+    off1, = struct.unpack_from("<I", one, 0)
+    spliced = bytearray(bad + one[4 + off1:])
+    struct.pack_into("<I", spliced, 8, 64)
+    with pytest.raises(FatalError, match="phased genotypes"):
+        read_bgen(bytes(spliced))
